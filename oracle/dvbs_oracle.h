@@ -1,0 +1,235 @@
+/* oracle/dvbs_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, scalar, one thread) of the leandvb DVB-S receive
+ * path of pabr/leansdr, written from the behaviour of the reference sources
+ * (cited per function as /root/reference/src/<file>:<lines>).  It is the
+ * checker for the CUDA product path: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg may load it.  The product (leansdr_b200/) never
+ * includes, links or calls anything in this directory.
+ *
+ * Parity pin: every stage below is compared bit-for-bit with streams tapped
+ * from the UNMODIFIED reference runnables (oracle/ref_tap.cc, built into
+ * oracle/_ref/ from the sources where they lie) in tests/test_oracle_vs_ref.py
+ * and with the committed golden vectors under tests/golden/.
+ */
+#ifndef DVBS_ORACLE_H
+#define DVBS_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- tables */
+
+enum { ORC_BPSK = 0, ORC_QPSK = 1, ORC_8PSK = 2 };
+enum { ORC_FEC12 = 0, ORC_FEC23 = 1, ORC_FEC46 = 2, ORC_FEC34 = 3,
+       ORC_FEC56 = 4, ORC_FEC78 = 5 };
+
+/* One cell of the 256x256 constellation table (sdr.h:455-458, 529-560). */
+typedef struct {
+  int16_t cost;
+  int16_t symbol;        /* 0..nsymbols-1 */
+  int16_t phase_error;
+  int16_t pad;
+} orc_cstln_cell;
+
+typedef struct {
+  orc_cstln_cell cell[256][256];  /* indexed [(u8)I][(u8)Q] */
+  int8_t sym_re[256], sym_im[256];
+  int nsymbols, nrotations;
+} orc_cstln;
+
+void orc_cstln_build(orc_cstln *c, int kind, int harden);
+void orc_trig16_build(float *lut /* [65536][2] = cos,sin */);
+void orc_rs_tables(uint8_t *exp511, uint8_t *log256, uint8_t *gen17);
+void orc_derand_pattern(uint8_t *pat1504);
+/* filtergen.h:45-62 followed by normalize_dcgain (leandvb.cc:375-376). */
+int  orc_lowpass(int order, float Fcut, float *coeffs /* [order+1] */);
+int  orc_resample_design(float Fs, float Fm, float rolloff, float rej,
+			 unsigned decim_opt, float *coeffs, int max_coeffs,
+			 int *decim_out);
+/* filtergen.h:68-92. Returns ncoeffs. */
+int  orc_rrc(int order, float Fs, float rolloff, float *coeffs);
+/* dvb.h:205-292: deconvolution polynomials. Returns punctperiod. */
+int  orc_deconv_polys(int fec, uint64_t *deconv, uint64_t *deconv2,
+		      int *punctweight);
+
+/* ----------------------------------------------------------- front end */
+
+/* dsp.h:33-54 instantiated <u8,128,f32,0,1,1> etc. fmt: 0=u8 1=s8 2=u16 3=s16 */
+void orc_cconvert(const void *in, int fmt, float *out_cf32, size_t n);
+/* dsp.h:140-160 */
+void orc_scale(const float *in_cf32, float scale, float *out_cf32, size_t n);
+
+/* sdr.h:1228-1261 */
+typedef struct {
+  float lut_cos[65536], lut_sin[65536];
+  uint16_t index;
+} orc_rotator;
+void orc_rotator_init(orc_rotator *r, float freq);
+void orc_rotator_run(orc_rotator *r, const float *in, float *out, size_t n);
+
+/* dsp.h:219-285.  shifted = complex taps [ncoeffs][2]. */
+typedef struct {
+  unsigned ncoeffs, decim;
+  const float *coeffs;
+  float *shifted;
+  float current_freq;
+} orc_fir;
+void   orc_fir_init(orc_fir *f, unsigned ncoeffs, const float *coeffs, unsigned decim);
+void   orc_fir_set_freq(orc_fir *f, float freq);
+/* Consumes as the reference run() does given n_in readable samples and
+ * unlimited output space.  Returns outputs written, *consumed = samples read. */
+size_t orc_fir_run(orc_fir *f, const float *in, size_t n_in, float *out,
+		   size_t *consumed);
+
+/* generic.h:247-267 */
+size_t orc_decimate(const float *in, size_t n_in, unsigned d, float *out,
+		    size_t *consumed);
+
+/* sdr.h:46-154 + dsp.h:56-116 */
+#define ORC_NOTCH_N 4096
+#define ORC_NOTCH_MAXSLOTS 8
+typedef struct {
+  int nslots;
+  int phase;
+  float gain, k;
+  int decimation;
+  float agc_rms_setpoint;
+  struct {
+    int i;
+    float estim_re, estim_im;
+    float *expj;            /* [4096][2] */
+  } slots[ORC_NOTCH_MAXSLOTS];
+  /* fft tables */
+  int *bitrev;
+  float *omega_rev;         /* [4096][2] */
+} orc_notch;
+void   orc_notch_init(orc_notch *a, int nslots);
+/* processes whole 4096-blocks; returns samples consumed (= produced). */
+size_t orc_notch_run(orc_notch *a, const float *in, size_t n_in, float *out);
+/* cfft_engine::inplace (dsp.h:78-110) exposed for tests. */
+void   orc_fft_inplace(int n, float *data, int reverse);
+
+/* ------------------------------------------------------------ receiver */
+
+enum { ORC_SAMP_NEAREST = 0, ORC_SAMP_LINEAR = 1, ORC_SAMP_RRC = 2 };
+
+typedef struct {
+  /* configuration */
+  const orc_cstln *cstln;
+  const float *trig;        /* [65536][2] */
+  int sampler;
+  unsigned long meas_decimation;
+  float omega, min_omega, max_omega;
+  float freqw, min_freqw, max_freqw;
+  float pll_adjustment;
+  int allow_drift;
+  float kest;
+  /* rrc sampler */
+  int rrc_ncoeffs, rrc_sub;
+  const float *rrc_coeffs;
+  float *rrc_shifted;       /* [ncoeffs][2] */
+  int rrc_update_phase;
+  /* linear sampler copy of freqw (sdr.h:625) */
+  float samp_freqw;
+  /* state (sdr.h:921-934) */
+  float est_insp, agc_gain, mu, phase, est_sp, est_ep;
+  unsigned long meas_count;
+  struct { float p_re, p_im, c_re, c_im; } hist[3];
+  float freq_tap;
+} orc_rx;
+
+void orc_rx_init(orc_rx *r, const orc_cstln *c, const float *trig, int sampler);
+void orc_rx_set_omega(orc_rx *r, float omega);
+void orc_rx_set_freq(orc_rx *r, float freq);
+void orc_rx_set_rrc(orc_rx *r, int ncoeffs, const float *coeffs, int subsampling);
+int  orc_rx_readahead(const orc_rx *r);
+/* Runs whole 128-sample chunks while n_in >= 128+readahead (sdr.h:783-915).
+ * symbols_out: 4 bytes per symbol {int16 cost, u8 symbol, 0}.
+ * sampled_out (optional): one cf32 per chunk that produced a symbol.
+ * meas_out (optional): per measurement {freq_tap, ss, mer} floats.
+ * Returns samples consumed. */
+size_t orc_rx_run(orc_rx *r, const float *in, size_t n_in,
+		  uint8_t *symbols_out, size_t *n_symbols,
+		  float *sampled_out, size_t *n_sampled,
+		  float *meas_out, size_t *n_meas);
+
+/* ----------------------------------------------- deconvolution and sync */
+
+typedef struct {
+  uint8_t lut[2][2];
+  uint64_t in;  int n_in;
+  uint64_t out; int n_out;
+} orc_dsync;
+
+typedef struct {
+  int punctperiod, punctweight;
+  uint64_t deconv[8], deconv2[8];
+  orc_dsync syncs[4];
+  int locked;
+  int skip;
+} orc_deconv;
+
+void orc_deconv_init(orc_deconv *d, int fec);
+void orc_deconv_next_sync(orc_deconv *d);          /* dvb.h:185-193 */
+/* One reference run() (dvb.h:414-467, fastlock off) with n_in symbols
+ * readable and out_cap bytes writable. Returns bytes written. */
+size_t orc_deconv_run(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
+		      uint8_t *out, size_t out_cap, size_t *consumed);
+
+typedef struct {
+  int scan_syncs, want_syncs;
+  unsigned long lock_timeout;
+  uint8_t polarity;
+  int bitphase;
+  int synchronized;
+  int next_sync_count;
+  int phase8;
+  unsigned long lock_timeleft, locktime;
+  int report_state;
+} orc_mpegsync;
+
+void orc_mpegsync_init(orc_mpegsync *m);
+/* One reference run() (dvb.h:742-874, fastlock off).  deconv may be NULL.
+ * lock_out receives lock transitions (0/1), locktime_out one per packet. */
+size_t orc_mpegsync_run(orc_mpegsync *m, orc_deconv *deconv,
+			const uint8_t *in, size_t n_in,
+			uint8_t *out, size_t out_cap, size_t *consumed,
+			int *lock_out, size_t *n_lock,
+			uint64_t *locktime_out, size_t *n_locktime);
+
+/* dvb.h:926-948. Returns packets written. */
+size_t orc_deinterleave(const uint8_t *in, size_t n_in, uint8_t *out_packets,
+			size_t *consumed);
+
+/* dvb.h:985-1058 + rs.h:86-268.  One packet. Returns 1 if still corrupted. */
+int orc_rs_decode_packet(uint8_t *pin204 /* fixed in place like rs.h:261 */,
+			 uint8_t *pout188, int *bits_corrected);
+/* rs.h:131-160 (for round-trip tests) */
+void orc_rs_encode(uint8_t *msg204);
+
+typedef struct { int pos; } orc_derand;
+/* dvb.h:1107-1163.  Returns packets written (dropped packets are skipped). */
+size_t orc_derandomize(orc_derand *d, const uint8_t *in188, size_t npackets,
+		       uint8_t *out188);
+
+/* ------------------------------------------------------------- Viterbi */
+
+typedef struct orc_viterbi orc_viterbi;
+orc_viterbi *orc_viterbi_new(const orc_cstln *c, int fec);
+void   orc_viterbi_free(orc_viterbi *v);
+void   orc_viterbi_set_resync_period(orc_viterbi *v, int p);
+int    orc_viterbi_nsyncs(const orc_viterbi *v);
+int    orc_viterbi_current_sync(const orc_viterbi *v);
+/* dvb.h:1353-1414. Returns bytes written. */
+size_t orc_viterbi_run(orc_viterbi *v, const uint8_t *symbols4, size_t n_in,
+		       uint8_t *out, size_t out_cap, size_t *consumed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
