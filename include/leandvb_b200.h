@@ -1,0 +1,241 @@
+/* leandvb_b200.h -- C ABI of the B200-native leandvb DVB-S receive path.
+ *
+ * This is the drop-in boundary: plain C types, pointers and sizes only.  The
+ * entry points are what a `runnable` living inside the reference's own
+ * scheduler/pipebuf framework binds to (see INTEGRATION.md for the thin
+ * `gpu_dvbs_receiver : runnable` wrapper a maintainer adds to leandvb.cc).
+ * Citations are file:line under /root/reference/src/.
+ *
+ * One handle replaces the chain of reference runnables between the input
+ * pipebuf and `p_tspackets` in apps/leandvb.cc:204-596:
+ *
+ *   cconverter / scaler          leansdr/dsp.h:33-54, 140-160
+ *   auto_notch                   leansdr/sdr.h:46-154
+ *   rotator                      leansdr/sdr.h:1228-1261
+ *   fir_filter (+ decimator)     leansdr/dsp.h:219-285, generic.h:247-267
+ *   cstln_receiver + samplers    leansdr/sdr.h:589-938
+ *   deconvol_sync | viterbi_sync leansdr/dvb.h:122-476 | 1173-1416
+ *   mpeg_sync                    leansdr/dvb.h:712-891
+ *   deinterleaver                leansdr/dvb.h:926-948
+ *   rs_decoder                   leansdr/dvb.h:985-1058, rs.h:86-268
+ *   derandomizer                 leansdr/dvb.h:1107-1163
+ *
+ * Error convention: every function returns 0 on success or a negative
+ * LDVB_E* code; ldvb_strerror() gives text.  The runnable wrapper turns a
+ * non-zero code into the reference's fail()/exit(1) (framework.h:32-33).
+ * Nothing here throws, allocates on behalf of the caller, or takes ownership
+ * of caller buffers.  A handle is single-threaded like the reference
+ * (README.coding.md:29): one caller at a time.
+ */
+#ifndef LEANDVB_B200_H
+#define LEANDVB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDVB_ABI_VERSION 1
+
+/* ------------------------------------------------------------ error codes */
+enum {
+  LDVB_OK          = 0,
+  LDVB_EINVAL      = -1,   /* bad argument / unsupported configuration   */
+  LDVB_ENOMEM      = -2,   /* host or device allocation failed            */
+  LDVB_ECUDA       = -3,   /* CUDA runtime error (see ldvb_last_error)    */
+  LDVB_ENODEV      = -4,   /* no usable sm_100 device                     */
+  LDVB_EOVERFLOW   = -5,   /* more data than the handle was sized for     */
+  LDVB_ESTATE      = -6    /* call sequence error                         */
+};
+
+/* ------------------------------------------------------------- enumerations
+ * Values follow the order of the reference's own enums so that a wrapper can
+ * cast: config::input_format (leandvb.cc:46-50), cstln_lut::predef
+ * (sdr.h:305-311), code_rate (dvb.h:36-40), config::sampler (leandvb.cc:70). */
+enum { LDVB_FMT_U8 = 0, LDVB_FMT_S8 = 1, LDVB_FMT_U16 = 2, LDVB_FMT_S16 = 3,
+       LDVB_FMT_F32 = 4 };
+enum { LDVB_CSTLN_BPSK = 0, LDVB_CSTLN_QPSK = 1, LDVB_CSTLN_8PSK = 2 };
+enum { LDVB_FEC12 = 0, LDVB_FEC23 = 1, LDVB_FEC46 = 2, LDVB_FEC34 = 3,
+       LDVB_FEC56 = 4, LDVB_FEC78 = 5 };
+enum { LDVB_SAMP_NEAREST = 0, LDVB_SAMP_LINEAR = 1, LDVB_SAMP_RRC = 2 };
+
+/* Receiver scheduling mode.
+ *   EXACT: the symbol-timing / carrier recurrence (sdr.h:800-847) is walked
+ *          serially from the carried state: every softsymbol field is
+ *          bit-identical to the reference.
+ *   FAST:  the stream is cut into time spans that run concurrently from a
+ *          warm-up state; spans are stitched on symbol time, their 90-degree
+ *          ambiguity is resolved against the previous span, and every seam is
+ *          verified on hard decisions (failed seams are re-run exactly).
+ *          TS output is bit-identical whenever the seams verify; soft costs
+ *          may differ by one table cell (hard part 1). */
+enum { LDVB_RX_EXACT = 0, LDVB_RX_FAST = 1 };
+
+/* ------------------------------------------------------------------ config
+ * Mirrors the fields of leandvb's `struct config` that reach the hot path
+ * (apps/leandvb.cc:43-136) with the same meaning and defaults
+ * (ldvb_config_default).  Derived parameters (filter order, decimation,
+ * rrc_steps, PLL constants) are computed inside ldvb_create exactly as
+ * leandvb.cc:run() derives them (:353-384, :432-462, :476-502). */
+typedef struct ldvb_config {
+  uint32_t abi_version;      /* = LDVB_ABI_VERSION                           */
+  int32_t  input_format;     /* LDVB_FMT_*           --u8/--s8/--u16/--s16/--f32 */
+  float    float_scale;      /* --float-scale (f32 input only)               */
+  float    Fs;               /* -f   input sample rate, Hz                   */
+  float    Fm;               /* --sr symbol rate, Hz                         */
+  int32_t  anf;              /* --anf number of notch slots (0 disables)     */
+  float    Fderot;           /* --derotate Hz (0 disables the rotator)       */
+  int32_t  resample;         /* --resample: low-pass FIR + decimation        */
+  float    resample_rej;     /* --resample-rej                               */
+  uint32_t decim;            /* --decim (0 = auto when resampling)           */
+  int32_t  sampler;          /* LDVB_SAMP_*          --sampler               */
+  int32_t  rrc_steps;        /* --rrc-steps (0 = auto)                       */
+  float    rrc_rej;          /* --rrc-rej                                    */
+  float    rolloff;          /* --roll-off                                   */
+  int32_t  constellation;    /* LDVB_CSTLN_*         --const                 */
+  int32_t  fec;              /* LDVB_FEC*            --cr                    */
+  int32_t  viterbi;          /* --viterbi                                    */
+  int32_t  hard_metric;      /* --hard-metric                                */
+  int32_t  fastlock;         /* --fastlock (not supported yet: LDVB_EINVAL)  */
+  int32_t  allow_drift;      /* --drift                                      */
+  float    Ftune;            /* --tune Hz                                    */
+  float    Finfo;            /* measurement rate, Hz (leandvb.cc:117, 502)   */
+  /* ---- B200-side knobs (no reference counterpart) ---- */
+  int32_t  rx_mode;          /* LDVB_RX_EXACT | LDVB_RX_FAST                 */
+  int32_t  device;           /* CUDA device ordinal                          */
+  uint64_t max_batch;        /* largest n_samples passed to one push/process */
+  uint32_t span_chunks;      /* FAST: 128-sample chunks per span (0 = auto)  */
+  uint32_t warmup_chunks;    /* FAST: warm-up chunks before a span (0 = auto)*/
+  int32_t  keep_taps;        /* keep intermediate streams for ldvb_tap()     */
+  int32_t  reserved[7];
+} ldvb_config;
+
+typedef struct ldvb_handle ldvb_handle;
+
+/* Telemetry: what the reference emits on p_freq/p_ss/p_mer/p_lock/p_locktime/
+ * p_vber (leandvb.cc:600-616), sampled at the end of the last batch. */
+typedef struct ldvb_meas {
+  float    freq_tap;         /* cstln_receiver::freq_tap (sdr.h:917-919)     */
+  float    ss;               /* sqrtf(est_insp)        (sdr.h:908-909)       */
+  float    mer;              /* 10*log10(est_sp/est_ep) (sdr.h:910-911)      */
+  int32_t  lock;             /* mpeg_sync synchronized (dvb.h:825, 867)      */
+  uint64_t locktime;         /* packets since lock     (dvb.h:856-858)       */
+  uint64_t rs_bits;          /* sum of rs_decoder nbits (dvb.h:1009)         */
+  uint64_t rs_errs;          /* sum of corrected bits  (dvb.h:1032, rs.h:259)*/
+  uint64_t ts_packets;       /* TS packets emitted so far                    */
+  uint64_t ts_dropped;       /* packets dropped by the derandomizer (dvb.h:1146-1156) */
+  uint64_t samples_in;       /* IQ samples accepted so far                   */
+  uint64_t symbols;          /* soft symbols produced so far                 */
+  uint32_t seams_total;      /* FAST: span seams stitched                    */
+  uint32_t seams_repaired;   /* FAST: seams that failed verification and were re-run exactly */
+  uint32_t notch_repaired;   /* notch segments re-run after a carry mismatch */
+  uint32_t kernel_launches;  /* CUDA kernels launched by this handle so far  */
+} ldvb_meas;
+
+/* Intermediate streams readable with ldvb_tap() when keep_taps != 0; names
+ * follow the reference pipebufs (leandvb.cc:204-596). */
+enum {
+  LDVB_TAP_PREPROCESSED = 0, /* cf32, input of cstln_receiver (p_preprocessed) */
+  LDVB_TAP_SYMBOLS      = 1, /* softsymbol {int16 cost, u8 symbol, 0} (p_symbols) */
+  LDVB_TAP_BYTES        = 2, /* u8 (p_bytes)                                 */
+  LDVB_TAP_MPEGBYTES    = 3, /* u8 (p_mpegbytes)                             */
+  LDVB_TAP_RSPACKETS    = 4, /* 204-byte packets (p_rspackets)               */
+  LDVB_TAP_RTSPACKETS   = 5, /* 188-byte packets (p_rtspackets)              */
+  LDVB_TAP_RSFLAGS      = 6, /* per packet int32 {corrupted, bits corrected} */
+  LDVB_TAP_SAMPLED      = 7, /* cf32, last symbol of each chunk (p_sampled)  */
+  LDVB_TAP_MEAS         = 8  /* float {freq_tap, ss, mer} per measurement    */
+};
+
+/* Constant tables, as built on the host for upload (ldvb_table). */
+enum {
+  LDVB_TABLE_CSTLN   = 0,    /* 65536 x {int16 cost, int16 symbol, int16 phase_error, 0} (sdr.h:529-560) */
+  LDVB_TABLE_TRIG16  = 1,    /* 65536 x {cos, sin} float (math.h:95-111)     */
+  LDVB_TABLE_RS_EXP  = 2,    /* 512 bytes (rs.h:49-60)                       */
+  LDVB_TABLE_RS_LOG  = 3,    /* 256 bytes                                    */
+  LDVB_TABLE_DERAND  = 4,    /* 1504 bytes (dvb.h:1116-1129)                 */
+  LDVB_TABLE_FIR     = 5,    /* ncoeffs float (filtergen.h:45-62)            */
+  LDVB_TABLE_RRC     = 6,    /* ncoeffs float (filtergen.h:68-92)            */
+  LDVB_TABLE_DECONV  = 7,    /* punctperiod x uint64 (dvb.h:205-292)         */
+  LDVB_TABLE_TRELLIS = 8,    /* 64 x NCS x {pred, us} bytes (viterbi.h:61-92) */
+  LDVB_TABLE_VITMAP  = 9     /* nsyncs x {shift, map[nsymbols]} (dvb.h:1336-1351) */
+};
+
+/* --------------------------------------------------------------- lifecycle */
+void        ldvb_config_default(ldvb_config *cfg);  /* leandvb.cc:88-135 defaults */
+int         ldvb_create(const ldvb_config *cfg, ldvb_handle **out);
+int         ldvb_destroy(ldvb_handle *h);
+const char *ldvb_strerror(int code);
+const char *ldvb_last_error(const ldvb_handle *h);  /* detail of the last failure */
+int         ldvb_abi_version(void);
+
+/* ------------------------------------------------------------ host-side I/O
+ * What the runnable's run() calls.  ldvb_push copies n_samples IQ samples
+ * (interleaved I,Q in cfg.input_format) from host memory to the device and
+ * runs the whole chain on them; TS packets become available to ldvb_pull in
+ * order.  Data that a stage cannot consume yet (partial 128-sample chunk,
+ * partial packet, de-interleaver history ...) is carried to the next push,
+ * like unread items staying in a reference pipebuf.  ldvb_pull never blocks:
+ * it returns up to cap_packets 188-byte packets. */
+int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n_samples);
+int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets,
+	      size_t *n_packets);
+
+/* ------------------------------------------------------- device-resident I/O
+ * Same processing with the IQ batch already in HBM and the TS packets left in
+ * HBM: iq_dev and ts_dev are device pointers on cfg.device.  *n_packets is
+ * written on return (one small D2H read per call). */
+int ldvb_process_device(ldvb_handle *h, const void *iq_dev, size_t n_samples,
+			uint8_t *ts_dev, size_t cap_packets,
+			size_t *n_packets);
+
+/* ----------------------------------------------------------- introspection */
+int ldvb_get_meas(ldvb_handle *h, ldvb_meas *m);
+/* Copies the tap stream produced by the LAST push/process into host memory;
+ * *n_bytes receives its size (call with dst == NULL to query). */
+int ldvb_tap(ldvb_handle *h, int which, void *dst_host, size_t cap_bytes,
+	     size_t *n_bytes);
+int ldvb_table(ldvb_handle *h, int which, void *dst_host, size_t cap_bytes,
+	       size_t *n_bytes);
+
+/* Carry state of the serial stages: what rank r hands
+ * to rank r+1 in a time-sharded run, and what tests use to compare with the
+ * reference's private members.  Opaque blob of ldvb_state_size() bytes. */
+size_t ldvb_state_size(const ldvb_handle *h);
+int    ldvb_get_state(ldvb_handle *h, void *blob, size_t cap);
+int    ldvb_set_state(ldvb_handle *h, const void *blob, size_t size);
+
+/* Receiver part of the carry state in a documented layout, 22 x uint32
+ * (floats bit-cast): mu phase freqw est_insp agc_gain est_sp est_ep
+ * hist[3]{p.re,p.im,c.re,c.im} sampler_freqw freq_tap meas_count
+ * (sdr.h:921-934). */
+int ldvb_get_rx_state(ldvb_handle *h, uint32_t w[22]);
+int ldvb_set_rx_state(ldvb_handle *h, const uint32_t w[22]);
+
+/* ------------------------------------------------- stand-alone stage kernels
+ * Host in, host out; used by the parity tests and by callers that only need
+ * one block.  Each runs the same kernel the chain uses. */
+
+/* fir_filter<cf32,float> with decimation (dsp.h:246-259):
+ * y[k] = sum_i taps[i] * x[k*decim + ntaps - i], accumulated in that order.
+ * taps are complex (re,im) pairs: the caller passes shifted_coeffs
+ * (dsp.h:270-280).  Returns the number of outputs in *n_out. */
+int ldvb_fir_cf32(int device, const float *x_host, size_t n_in,
+		  const float *taps_cplx, uint32_t ntaps, uint32_t decim,
+		  float *y_host, size_t cap_out, size_t *n_out);
+
+/* deinterleaver + rs_decoder on aligned bytes (dvb.h:926-948, 985-1058):
+ * mpegbytes -> RS(204,188)-decoded, still randomised packets. */
+int ldvb_deint_rs(int device, const uint8_t *mpegbytes_host, size_t n_bytes,
+		  uint8_t *rts_host, size_t cap_packets, size_t *n_packets,
+		  int32_t *flags_host /* [n][2] corrupted, bits corrected; may be NULL */);
+
+/* rs_decoder alone on n 204-byte packets (dvb.h:1004-1047). */
+int ldvb_rs_decode(int device, const uint8_t *rs204_host, size_t n_packets,
+		   uint8_t *ts188_host, int32_t *flags_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEANDVB_B200_H */

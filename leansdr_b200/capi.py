@@ -1,0 +1,272 @@
+"""ctypes binding of libleandvb_b200.so (include/leandvb_b200.h).
+
+The library is the product: hand-written sm_100a kernels behind a C ABI.  This
+module only loads it and mirrors the structs; there is NO Python/NumPy/torch
+fallback -- if the shared object is missing or no B200 is present the calls
+fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libleandvb_b200.so")
+
+ABI_VERSION = 1
+FMT = {"u8": 0, "s8": 1, "u16": 2, "s16": 3, "f32": 4}
+FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16, "f32": np.float32}
+CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2}
+FEC = {"1/2": 0, "2/3": 1, "4/6": 2, "3/4": 3, "5/6": 4, "7/8": 5}
+SAMPLER = {"nearest": 0, "linear": 1, "rrc": 2}
+RX_EXACT, RX_FAST = 0, 1
+TAP = {"pp": 0, "symbols": 1, "bytes": 2, "mpegbytes": 3, "rspackets": 4, "rtspackets": 5,
+       "rsflags": 6, "sampled": 7, "meas": 8}
+TABLE = {"cstln": 0, "trig16": 1, "rs_exp": 2, "rs_log": 3, "derand": 4, "fir": 5, "rrc": 6,
+         "deconv": 7, "trellis": 8, "vitmap": 9}
+
+
+class LdvbError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where}: error {code}: {detail}")
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("input_format", C.c_int32), ("float_scale", C.c_float),
+        ("Fs", C.c_float), ("Fm", C.c_float), ("anf", C.c_int32), ("Fderot", C.c_float),
+        ("resample", C.c_int32), ("resample_rej", C.c_float), ("decim", C.c_uint32),
+        ("sampler", C.c_int32), ("rrc_steps", C.c_int32), ("rrc_rej", C.c_float),
+        ("rolloff", C.c_float), ("constellation", C.c_int32), ("fec", C.c_int32),
+        ("viterbi", C.c_int32), ("hard_metric", C.c_int32), ("fastlock", C.c_int32),
+        ("allow_drift", C.c_int32), ("Ftune", C.c_float), ("Finfo", C.c_float),
+        ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
+        ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
+        ("reserved", C.c_int32 * 7),
+    ]
+
+
+class Meas(C.Structure):
+    _fields_ = [
+        ("freq_tap", C.c_float), ("ss", C.c_float), ("mer", C.c_float), ("lock", C.c_int32),
+        ("locktime", C.c_uint64), ("rs_bits", C.c_uint64), ("rs_errs", C.c_uint64),
+        ("ts_packets", C.c_uint64), ("ts_dropped", C.c_uint64), ("samples_in", C.c_uint64),
+        ("symbols", C.c_uint64), ("seams_total", C.c_uint32), ("seams_repaired", C.c_uint32),
+        ("notch_repaired", C.c_uint32), ("kernel_launches", C.c_uint32),
+    ]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+EXPORTS = [
+    "ldvb_abi_version", "ldvb_strerror", "ldvb_last_error", "ldvb_config_default", "ldvb_create",
+    "ldvb_destroy", "ldvb_push", "ldvb_pull", "ldvb_process_device", "ldvb_get_meas", "ldvb_tap",
+    "ldvb_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
+    "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (built by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA extension is the product; there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.ldvb_abi_version.restype = C.c_int
+    L.ldvb_strerror.restype = C.c_char_p
+    L.ldvb_strerror.argtypes = [C.c_int]
+    L.ldvb_last_error.restype = C.c_char_p
+    L.ldvb_last_error.argtypes = [vp]
+    L.ldvb_config_default.argtypes = [C.POINTER(Config)]
+    L.ldvb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.ldvb_destroy.argtypes = [vp]
+    L.ldvb_push.argtypes = [vp, vp, sz]
+    L.ldvb_pull.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.ldvb_process_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
+    L.ldvb_get_meas.argtypes = [vp, C.POINTER(Meas)]
+    L.ldvb_tap.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    L.ldvb_table.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    L.ldvb_state_size.restype = sz
+    L.ldvb_state_size.argtypes = [vp]
+    L.ldvb_get_state.argtypes = [vp, vp, sz]
+    L.ldvb_set_state.argtypes = [vp, vp, sz]
+    L.ldvb_get_rx_state.argtypes = [vp, vp]
+    L.ldvb_set_rx_state.argtypes = [vp, vp]
+    L.ldvb_fir_cf32.argtypes = [C.c_int, vp, sz, vp, C.c_uint32, C.c_uint32, vp, sz, C.POINTER(sz)]
+    L.ldvb_deint_rs.argtypes = [C.c_int, vp, sz, vp, sz, C.POINTER(sz), vp]
+    L.ldvb_rs_decode.argtypes = [C.c_int, vp, sz, vp, vp]
+    _lib = L
+    return L
+
+
+def default_config(**kw) -> Config:
+    cfg = Config()
+    load().ldvb_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        if k == "fmt":
+            cfg.input_format = FMT[v]
+        elif k == "cstln":
+            cfg.constellation = CSTLN[v]
+        elif k == "fec":
+            cfg.fec = FEC[v] if isinstance(v, str) else v
+        elif k == "sampler":
+            cfg.sampler = SAMPLER[v] if isinstance(v, str) else v
+        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps"):
+            setattr(cfg, k, int(v))
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Receiver:
+    """Host-side mirror of the chain of reference runnables replaced by one handle.
+
+    push()/pull() move HOST buffers like a runnable's run() would between two
+    pipebufs; process_device() works on device pointers (torch tensors)."""
+
+    def __init__(self, cfg: Config | None = None, **kw):
+        self.L = load()
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self.h = C.c_void_p()
+        rc = self.L.ldvb_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            raise LdvbError(rc, "ldvb_create", self.L.ldvb_strerror(rc).decode())
+        self.fmt = {v: k for k, v in FMT.items()}[self.cfg.input_format]
+
+    def close(self):
+        if self.h:
+            self.L.ldvb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, where):
+        if rc != 0:
+            raise LdvbError(rc, where, self.L.ldvb_last_error(self.h).decode() or
+                            self.L.ldvb_strerror(rc).decode())
+
+    def push(self, iq: np.ndarray):
+        iq = np.ascontiguousarray(iq, dtype=FMT_DTYPE[self.fmt]).reshape(-1)
+        self._ck(self.L.ldvb_push(self.h, _p(iq), iq.size // 2), "ldvb_push")
+
+    def push_ptr(self, host_ptr: int, n_samples: int):
+        self._ck(self.L.ldvb_push(self.h, C.c_void_p(host_ptr), n_samples), "ldvb_push")
+
+    def pull(self, max_packets: int = 1 << 20) -> np.ndarray:
+        out = np.empty((max_packets, 188), np.uint8)
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_pull(self.h, _p(out), max_packets, C.byref(n)), "ldvb_pull")
+        return out[:n.value]
+
+    def pull_all(self) -> np.ndarray:
+        parts = []
+        while True:
+            p = self.pull(1 << 16)
+            if p.shape[0] == 0:
+                break
+            parts.append(p.copy())
+        return np.concatenate(parts) if parts else np.zeros((0, 188), np.uint8)
+
+    def process_device(self, iq_ptr: int, n_samples: int, ts_ptr: int, cap_packets: int) -> int:
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_process_device(self.h, C.c_void_p(iq_ptr), n_samples,
+                                            C.c_void_p(ts_ptr), cap_packets, C.byref(n)),
+                 "ldvb_process_device")
+        return n.value
+
+    def meas(self) -> dict:
+        m = Meas()
+        self._ck(self.L.ldvb_get_meas(self.h, C.byref(m)), "ldvb_get_meas")
+        return m.asdict()
+
+    def tap(self, name: str) -> np.ndarray:
+        which = TAP[name]
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_tap(self.h, which, None, 0, C.byref(n)), "ldvb_tap")
+        out = np.empty(n.value, np.uint8)
+        if n.value:
+            self._ck(self.L.ldvb_tap(self.h, which, _p(out), out.size, C.byref(n)), "ldvb_tap")
+        return out
+
+    def table(self, name: str) -> np.ndarray:
+        which = TABLE[name]
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_table(self.h, which, None, 0, C.byref(n)), "ldvb_table")
+        out = np.empty(n.value, np.uint8)
+        self._ck(self.L.ldvb_table(self.h, which, _p(out), out.size, C.byref(n)), "ldvb_table")
+        return out
+
+    def rx_state(self) -> np.ndarray:
+        w = np.zeros(22, np.uint32)
+        self._ck(self.L.ldvb_get_rx_state(self.h, _p(w)), "ldvb_get_rx_state")
+        return w
+
+    def set_rx_state(self, w):
+        w = np.ascontiguousarray(w, np.uint32)
+        self._ck(self.L.ldvb_set_rx_state(self.h, _p(w)), "ldvb_set_rx_state")
+
+    def get_state(self) -> np.ndarray:
+        n = self.L.ldvb_state_size(self.h)
+        b = np.zeros(n, np.uint8)
+        self._ck(self.L.ldvb_get_state(self.h, _p(b), n), "ldvb_get_state")
+        return b
+
+    def set_state(self, b):
+        b = np.ascontiguousarray(b, np.uint8)
+        self._ck(self.L.ldvb_set_state(self.h, _p(b), b.size), "ldvb_set_state")
+
+
+def fir_cf32(x: np.ndarray, taps_cplx: np.ndarray, decim: int = 1, device: int = 0) -> np.ndarray:
+    L = load()
+    x = np.ascontiguousarray(x, np.float32).reshape(-1)
+    t = np.ascontiguousarray(taps_cplx, np.float32).reshape(-1)
+    n_in, nt = x.size // 2, t.size // 2
+    out = np.empty(2 * (n_in // decim + 1), np.float32)
+    n = C.c_size_t(0)
+    rc = L.ldvb_fir_cf32(device, _p(x), n_in, _p(t), nt, decim, _p(out), out.size // 2, C.byref(n))
+    if rc:
+        raise LdvbError(rc, "ldvb_fir_cf32", L.ldvb_strerror(rc).decode())
+    return out[:2 * n.value]
+
+
+def rs_decode(packets204: np.ndarray, device: int = 0):
+    L = load()
+    p = np.ascontiguousarray(packets204, np.uint8).reshape(-1, 204)
+    out = np.empty((p.shape[0], 188), np.uint8)
+    flags = np.zeros((p.shape[0], 2), np.int32)
+    rc = L.ldvb_rs_decode(device, _p(p), p.shape[0], _p(out), _p(flags))
+    if rc:
+        raise LdvbError(rc, "ldvb_rs_decode", L.ldvb_strerror(rc).decode())
+    return out, flags
+
+
+def deint_rs(mpegbytes: np.ndarray, device: int = 0):
+    L = load()
+    m = np.ascontiguousarray(mpegbytes, np.uint8).reshape(-1)
+    cap = m.size // 204 + 1
+    out = np.empty((cap, 188), np.uint8)
+    flags = np.zeros((cap, 2), np.int32)
+    n = C.c_size_t(0)
+    rc = L.ldvb_deint_rs(device, _p(m), m.size, _p(out), cap, C.byref(n), _p(flags))
+    if rc:
+        raise LdvbError(rc, "ldvb_deint_rs", L.ldvb_strerror(rc).decode())
+    return out[:n.value], flags[:n.value]

@@ -1,0 +1,78 @@
+// common.cuh -- shared device helpers for the sm_100a DVB-S kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ldvb {
+
+// ----------------------------------------------------------------- arithmetic
+// Every float operation on the bit-exact path goes through the _rn intrinsics:
+// they are never contracted into FMAs, so the device rounds each product and
+// sum exactly like the reference's scalar SSE2 build (hard part 2).
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+// complex<float> operator* of the reference (math.h:38-41):
+//   (a.re*b.re - a.im*b.im, a.re*b.im + a.im*b.re)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fsub(fmul(a.x, b.x), fmul(a.y, b.y)),
+                     fadd(fmul(a.x, b.y), fmul(a.y, b.x)));
+}
+
+// (T)value conversions of the reference truncate toward zero (cvttss2si).
+__device__ __forceinline__ int f2i_trunc(float a) { return __float2int_rz(a); }
+
+// ------------------------------------------------------------ TMA bulk copies
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier
+// (SASS: UBLKCP).  dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Streaming stores: results are written once and read by a later kernel.
+__device__ __forceinline__ void st_stream(float2 *p, float2 v) { __stcs(p, v); }
+
+}  // namespace ldvb

@@ -1,0 +1,518 @@
+// k_fec.cu -- K4/K6/K7: algebraic deconvolution, MPEG sync tracking, byte
+// re-alignment, de-interleaving, Reed-Solomon RS(204,188) and de-randomisation.
+//
+// All of this is integer/bit work on a stream that is ~80x smaller than the IQ
+// input (0.104 byte per sample at QPSK 1/2), so the kernels are written for
+// exactness and full parallelism over bytes/packets, not for HBM peak.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ldvb {
+
+namespace {
+
+__device__ __forceinline__ unsigned par64(uint64_t v) { return __popcll(v) & 1; }
+
+// =============================================================== deconvolution
+// deconvol_sync::readbyte (dvb.h:369-389) as a position-indexed computation.
+// Bit group g (punctperiod bits) is the parity of the 64-bit IQ shift register
+// after K_g = k0 + g*(punctweight/2) symbols, k0 = symbols needed to fill the
+// carried register to 64 bits.  The register holds the last 32 symbols, two IQ
+// bits each, newest in the LSBs.  Output byte j = stream bits [8j, 8j+8) where
+// the carried accumulator supplies the first n_out bits.
+__device__ __forceinline__ uint64_t deconv_reg(const DeconvArgs &a, int64_t K) {
+  // Register after K symbols of this batch: (carry << 2K) | new IQ bits.
+  uint64_t reg = (K >= 32) ? 0ull : (a.reg_in << (2 * K));
+  const int64_t first = (K > 32) ? K - 32 : 0;
+  for (int64_t s = first; s < K; ++s) {
+    const uint32_t sym = (a.symbols[s] >> 16) & 3u;
+    reg |= (uint64_t)a.hyp[sym] << (2 * (K - 1 - s));
+  }
+  return reg;
+}
+
+__global__ void __launch_bounds__(256)
+k_deconv(DeconvArgs a, uint64_t *carry_out) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int pp = a.punctperiod, half = a.punctweight / 2;
+  const int64_t k0 = (a.n_in >= 64) ? 0 : (64 - a.n_in) / 2;  // n_in is always even
+  if (j < a.nbytes) {
+    unsigned byte = 0;
+    int64_t bit = (int64_t)8 * j;        // stream bit index of the byte's MSB
+    int got = 0;
+    // Bits still held by the carried accumulator.
+    while (got < 8 && bit < a.n_out) {
+      byte = (byte << 1) | (unsigned)((a.out_acc >> (a.n_out - 1 - bit)) & 1);
+      ++bit; ++got;
+    }
+    if (got < 8) {
+      int64_t g = (bit - a.n_out) / pp;
+      int within = (int)((bit - a.n_out) % pp);   // bits of group g already consumed
+      uint64_t reg = deconv_reg(a, k0 + g * half);
+      while (got < 8) {
+        for (int b = pp - 1 - within; b >= 0 && got < 8; --b) {
+          byte = (byte << 1) | par64(reg & a.deconv[b]);
+          ++got;
+        }
+        within = 0;
+        if (got < 8) {
+          // next group: shift in punctweight/2 more symbols
+          const int64_t K = k0 + g * half;
+          for (int s = 0; s < half; ++s) {
+            const uint32_t sym = (a.symbols[K + s] >> 16) & 3u;
+            reg = (reg << 2) | a.hyp[sym];
+          }
+          ++g;
+        }
+      }
+    }
+    a.out[j] = (uint8_t)byte;
+  }
+  // The thread after the last byte writes the carry for the next batch.
+  if (j == a.nbytes && carry_out) {
+    // Groups completed: the last byte ends at stream bit 8*nbytes-1.
+    const int64_t total_bits = (int64_t)8 * a.nbytes;
+    int64_t ngroups = 0;
+    if (total_bits > a.n_out) ngroups = (total_bits - a.n_out + pp - 1) / pp;
+    uint64_t reg = a.reg_in, acc = a.out_acc;
+    int n_in = a.n_in, n_out = a.n_out;
+    int64_t consumed = 0;
+    if (ngroups > 0) {
+      consumed = k0 + (ngroups - 1) * half;
+      reg = deconv_reg(a, consumed);
+      n_in = 64 - a.punctweight;
+      // Leftover bits: low bits of the last group.
+      const int64_t produced_bits = a.n_out + ngroups * pp;
+      n_out = (int)(produced_bits - total_bits);
+      acc = 0;
+      for (int b = pp - 1; b >= 0; --b) acc = (acc << 1) | par64(reg & a.deconv[b]);
+    } else {
+      n_out = (int)(a.n_out - total_bits);
+    }
+    carry_out[0] = reg; carry_out[1] = (uint64_t)(int64_t)n_in;
+    carry_out[2] = acc; carry_out[3] = (uint64_t)(int64_t)n_out;
+    carry_out[4] = (uint64_t)consumed;
+  }
+}
+
+// ================================================================= MPEG sync
+// mpeg_sync (dvb.h:742-874).  Locked tracking is data parallel (k_sync_flags +
+// a word-wise scan of the bad-sync mask); acquisition (run_searching,
+// search_sync) is a sequential window walk done by one thread.
+
+__device__ __forceinline__ unsigned realigned(const uint8_t *b, uint64_t i, int bitphase, int polarity) {
+  const unsigned w = ((unsigned)b[i] << 8) | b[i + 1];
+  return ((w >> bitphase) ^ (unsigned)polarity) & 0xffu;
+}
+
+__global__ void __launch_bounds__(256)
+k_sync_flags(const uint8_t *bytes, uint64_t npackets, const SyncState *st, uint32_t *bad_words) {
+  // One thread per packet; 32 packets per mask word (ballot).
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (p < npackets) {
+    const int phase8 = (int)((st->phase8 + p) & 7);
+    const unsigned expected = phase8 ? 0x47u : 0xb8u;
+    bad = realigned(bytes, 204 * p, st->bitphase, st->polarity) != expected;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && (p >> 5) <= ((npackets + 31) >> 5)) bad_words[p >> 5] = m;
+}
+
+// search_sync (dvb.h:798-840) on the window starting at bytes[pos].
+__device__ int sync_search_window(const uint8_t *bytes, uint64_t pos, SyncState &st) {
+  for (int i = 0; i < 204; ++i) {
+    int np = 0, nn = 0, ph_p = -1, ph_n = -1;
+    for (int j = 0; j < 8; ++j) {
+      const unsigned b = (((unsigned)bytes[pos + i + 204 * j] << 8 | bytes[pos + i + 204 * j + 1]) >> st.bitphase) & 0xffu;
+      if (b == 0x47u) { ++np; ph_n = (8 - j) & 7; }
+      if (b == 0xb8u) { ++nn; ph_p = (8 - j) & 7; }
+    }
+    int nsyncs;
+    if (np > nn) { st.polarity = 0; nsyncs = np; st.phase8 = ph_p; }
+    else { st.polarity = 0xff; nsyncs = nn; st.phase8 = ph_n; }
+    if (nsyncs >= 4 && st.phase8 >= 0) {
+      int skip = i;
+      if (!i) { skip = 204; st.phase8 = (st.phase8 + 1) & 7; }
+      st.synchronized = 1;
+      st.lock_timeleft = 4;
+      st.locktime = 0;
+      return skip;
+    }
+  }
+  return 0;
+}
+
+__global__ void k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_in,
+                             const uint32_t *bad_words, uint64_t npackets_flagged,
+                             SyncResult *res) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  SyncState st = *st_in;
+  SyncResult r;
+  r.consumed = 0; r.produced = 0; r.need_next_sync = 0; r.events = 0;
+  auto event = [&](int v, uint64_t pos) {
+    if (r.events < 16) { r.event_val[r.events] = v; r.event_pos[r.events] = pos; }
+    ++r.events;
+  };
+  if (st.report_state) { event(0, 0); st.report_state = 0; }
+  if (st.synchronized) {
+    // run_decoding (dvb.h:842-874): walk the mask until the lock times out.
+    uint64_t p = 0;
+    bool unlocked = false;
+    while (p < npackets_flagged) {
+      const uint32_t w = bad_words[p >> 5];
+      const uint64_t lim = min(npackets_flagged, (p & ~(uint64_t)31) + 32);
+      if (w == 0 && (p & 31) == 0 && lim - p == 32) {  // 32 good packets
+        st.lock_timeleft = 3;
+        st.locktime += 32;
+        p += 32;
+        continue;
+      }
+      for (; p < lim; ++p) {
+        ++st.locktime;
+        if (!((w >> (p & 31)) & 1)) st.lock_timeleft = 4;
+        --st.lock_timeleft;
+        if (!st.lock_timeleft) { unlocked = true; ++p; break; }
+      }
+      if (unlocked) break;
+    }
+    st.phase8 = (int)((st.phase8 + p) & 7);
+    r.consumed = 204 * p;
+    r.produced = 204 * p;
+    if (unlocked) {
+      st.synchronized = 0;
+      st.next_sync_count = 0;
+      event(0, r.consumed);
+    }
+  } else {
+    // run_searching (dvb.h:755-779): one bit phase per 8-packet window; a full
+    // sweep of the 8 phases without lock counts towards next_sync().  The sweep
+    // counter advances once per wrap (the reference's default buffering never
+    // sees two wraps inside one run() call).
+    uint64_t pos = 0;
+    const uint64_t chunk = 204 * 8;
+    while (nbytes - pos >= chunk + 1) {
+      const int skip = sync_search_window(bytes, pos, st);
+      if (skip) {
+        pos += skip;
+        event(1, pos);
+        break;
+      }
+      pos += chunk;
+      if (++st.bitphase == 8) {
+        st.bitphase = 0;
+        if (++st.next_sync_count >= 3) {
+          st.next_sync_count = 0;
+          r.need_next_sync = 1;
+          break;
+        }
+      }
+    }
+    r.consumed = pos;
+  }
+  r.st = st;
+  *res = r;
+}
+
+__global__ void __launch_bounds__(256)
+k_realign(const uint8_t *bytes, uint64_t n, int bitphase, int polarity, uint8_t *out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)realigned(bytes, i, bitphase, polarity);
+}
+
+// ============================================== de-interleaver + Reed-Solomon
+struct Gf {
+  const uint8_t *ex, *lg;
+  __device__ __forceinline__ unsigned mul(unsigned x, unsigned y) const {
+    if (!x || !y) return 0;
+    return ex[lg[x] + lg[y]];
+  }
+  __device__ __forceinline__ unsigned div(unsigned x, unsigned y) const {  // rs.h:68-72
+    if (!x) return 0;
+    return ex[lg[x] + 255 - lg[y]];
+  }
+  __device__ __forceinline__ unsigned inv(unsigned x) const { return ex[255 - lg[x]]; }
+};
+
+// Syndromes S_j = P(alpha^j), j = 0..15, P = sum_i r[i] x^(203-i) (rs.h:116-130).
+// Each lane folds its bytes (i = lane + 32k), lanes are combined by XOR.
+__device__ __forceinline__ bool rs_syndromes(const Gf &gf, const uint8_t *r, int lane, uint8_t synd[16]) {
+  unsigned acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0;
+  for (int i = lane; i < 204; i += 32) {
+    const unsigned v = r[i];
+    if (v) {
+      const unsigned lv = gf.lg[v];
+      const unsigned e = 203 - i;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] ^= gf.ex[(lv + j * e) % 255];
+    }
+  }
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    unsigned v = acc[j];
+    v ^= __shfl_xor_sync(0xffffffffu, v, 16);
+    v ^= __shfl_xor_sync(0xffffffffu, v, 8);
+    v ^= __shfl_xor_sync(0xffffffffu, v, 4);
+    v ^= __shfl_xor_sync(0xffffffffu, v, 2);
+    v ^= __shfl_xor_sync(0xffffffffu, v, 1);
+    synd[j] = (uint8_t)v;
+    any |= (v != 0);
+  }
+  return any;
+}
+
+__device__ __forceinline__ unsigned poly_eval(const Gf &gf, const uint8_t *poly, int deg, unsigned x) {
+  unsigned acc = 0;  // rs.h:133-138
+  for (; deg >= 0; --deg) acc = gf.mul(acc, x) ^ poly[deg];
+  return acc;
+}
+
+// rs_engine::correct (rs.h:176-268) for one packet held in shared memory.
+// Berlekamp-Massey and Omega run redundantly on every lane (no divergence); the
+// root scan alpha^0..alpha^254 is split across lanes (the error locator has at
+// most L roots, so scanning all candidates equals the reference's early exit).
+__device__ bool rs_correct(const Gf &gf, uint8_t *pin, uint8_t *pout, uint8_t synd[16], int lane,
+                           int *bits_corrected) {
+  uint8_t C[17], B[17], T[16];
+#pragma unroll
+  for (int i = 0; i < 17; ++i) { C[i] = 0; B[i] = 0; }
+  C[0] = 1; B[0] = 1;
+  int L = 0, m = 1;
+  unsigned b = 1;
+  for (int n = 0; n < 16; ++n) {
+    unsigned d = synd[n];
+    for (int i = 1; i <= L; ++i) d ^= gf.mul(C[i], synd[n - i]);
+    if (!d) {
+      ++m;
+    } else if (2 * L <= n) {
+      for (int i = 0; i < 16; ++i) T[i] = C[i];
+      const unsigned k = gf.inv(b);
+      for (int i = 0; i < 16 - m; ++i) C[m + i] ^= gf.mul(d, gf.mul(k, B[i]));
+      L = n + 1 - L;
+      for (int i = 0; i < 16; ++i) B[i] = T[i];
+      b = d;
+      m = 1;
+    } else {
+      const unsigned k = gf.inv(b);
+      for (int i = 0; i < 16 - m; ++i) C[m + i] ^= gf.mul(d, gf.mul(k, B[i]));
+      ++m;
+    }
+  }
+  uint8_t omega[16], Cp[15];
+  for (int i = 0; i < 16; ++i) omega[i] = 0;
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; i + j < 16; ++j) omega[i + j] ^= gf.mul(synd[i], C[j]);
+  for (int i = 0; i < 15; ++i) Cp[i] = (i & 1) ? 0 : C[i + 1];
+  int nbits = 0;
+  for (int i = lane; i < 255; i += 32) {
+    const unsigned r = gf.ex[i];
+    if (poly_eval(gf, C, L, r) == 0) {
+      const unsigned xk = gf.inv(r);
+      const int loc = (255 - i) % 255;
+      if (loc < 204) {
+        const unsigned num = gf.mul(xk, poly_eval(gf, omega, L < 16 ? L : 15, r));
+        const unsigned den = poly_eval(gf, Cp, 14, r);
+        const unsigned e = gf.div(num, den);
+        nbits += __popc(e);
+        if (loc >= 16) pout[203 - loc] ^= (uint8_t)e;
+        pin[203 - loc] ^= (uint8_t)e;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) nbits += __shfl_xor_sync(0xffffffffu, nbits, o);
+  *bits_corrected += nbits;
+  __syncwarp();
+  return rs_syndromes(gf, pin, lane, synd);
+}
+
+template <bool DEINT>
+__global__ void __launch_bounds__(128)
+k_rs(const uint8_t *src, uint64_t npackets, const uint8_t *gexp, const uint8_t *glog,
+     uint8_t *rs_out, uint8_t *rts_out, int32_t *flags) {
+  __shared__ uint8_t s_exp[512], s_log[256];
+  __shared__ uint8_t s_pkt[4][208], s_msg[4][192];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_exp[i] = gexp[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_log[i] = glog[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Gf gf{s_exp, s_log};
+  for (uint64_t p = (uint64_t)blockIdx.x * 4 + warp; p < npackets; p += (uint64_t)gridDim.x * 4) {
+    uint8_t *pin = s_pkt[warp], *pout = s_msg[warp];
+    for (int i = lane; i < 204; i += 32) {
+      uint8_t v;
+      if (DEINT) v = src[204 * (p + (uint64_t)(i % 12)) + i];  // dvb.h:936-941: in[2244+204p+i-12*delay_i]
+      else v = src[204 * p + i];
+      pin[i] = v;
+      if (i < 188) pout[i] = v;  // dvb.h:1011-1014
+    }
+    __syncwarp();
+    if (DEINT && rs_out)
+      for (int i = lane; i < 204; i += 32) rs_out[204 * p + i] = pin[i];
+    uint8_t synd[16];
+    bool corrupted = rs_syndromes(gf, pin, lane, synd);
+    int nerr = 0;
+    if (corrupted) corrupted = rs_correct(gf, pin, pout, synd, lane, &nerr);
+    __syncwarp();
+    if (corrupted && lane == 0) pout[0] ^= 0x55;  // dvb.h:1045
+    __syncwarp();
+    for (int i = lane; i < 188; i += 32) rts_out[188 * p + i] = pout[i];
+    if (lane == 0 && flags) { flags[2 * p] = corrupted ? 1 : 0; flags[2 * p + 1] = nerr; }
+    __syncwarp();
+  }
+}
+
+// ============================================================ de-randomiser
+// derandomizer::run (dvb.h:1131-1158).  pos_p = 188*((p - r_p) mod 8) with r_p
+// the last packet <= p whose first byte is an inverted sync (0xB8 or 0xB8^0x55);
+// before the first reset the carried position keeps cycling.  One CTA scans the
+// packet heads in tiles (inclusive max-scan of reset indices + exclusive sum of
+// kept packets); a second kernel XORs and writes the kept packets.
+__global__ void __launch_bounds__(1024)
+k_derand_scan(DerandArgs a) {
+  __shared__ long long s_last[32];
+  __shared__ unsigned s_cnt[32];
+  __shared__ long long carry_last;   // last reset index so far, or -1 - pos_in/188 sentinel
+  __shared__ unsigned long long carry_kept, carry_errs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { carry_last = -1; carry_kept = 0; carry_errs = 0; }
+  __syncthreads();
+  const long long start_phase = a.pos_in / 188;  // packets since the (virtual) last reset
+  for (uint64_t base = 0; base < a.npackets; base += 1024) {
+    const uint64_t p = base + tid;
+    const bool valid = p < a.npackets;
+    unsigned head = 0;
+    if (valid) head = a.rts[188 * p];
+    const bool reset = valid && (head == 0xb8u || head == (0xb8u ^ 0x55u));
+    long long last = reset ? (long long)p : -1;
+    // inclusive max-scan inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+      long long v = __shfl_up_sync(0xffffffffu, last, o);
+      if (lane >= o && v > last) last = v;
+    }
+    if (lane == 31) s_last[warp] = last;
+    __syncthreads();
+    if (warp == 0) {
+      long long v = s_last[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        long long u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o && u > v) v = u;
+      }
+      s_last[lane] = v;
+    }
+    __syncthreads();
+    if (warp > 0 && s_last[warp - 1] > last) last = s_last[warp - 1];
+    if (carry_last > last) last = carry_last;
+    int pos;
+    if (last >= 0) pos = (int)(((long long)p - last) & 7) * 188;
+    else pos = (int)(((long long)p + start_phase) & 7) * 188;
+    bool keep = false;
+    if (valid) keep = ((head ^ a.pattern[pos]) == 0x47u);
+    int nerr = (valid && a.flags) ? a.flags[2 * p + 1] : 0;
+    // exclusive sum of kept packets
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const unsigned before = __popc(bal & ((1u << lane) - 1));
+    for (int o = 16; o; o >>= 1) nerr += __shfl_xor_sync(0xffffffffu, nerr, o);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    unsigned wbase = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_cnt[w]; total += s_cnt[w]; }
+    if (valid) {
+      // scratch[p] = output index (bit 31 set when dropped), low bits of pos in scratch2
+      a.scratch[p] = keep ? (unsigned)(carry_kept + wbase + before) : 0xffffffffu;
+      a.scratch[a.npackets + p] = (unsigned)pos;
+    }
+    __syncthreads();
+    if (lane == 0 && nerr) atomicAdd(&carry_errs, (unsigned long long)nerr);
+    if (tid == 1023) {
+      carry_last = last;
+    }
+    if (tid == 0) carry_kept += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    long long last = carry_last;
+    int pos_out;
+    if (last >= 0) pos_out = (int)(((long long)a.npackets - last) & 7) * 188;
+    else pos_out = (int)(((long long)a.npackets + start_phase) & 7) * 188;
+    a.counts[0] = carry_kept;
+    a.counts[1] = a.npackets - carry_kept;
+    a.counts[2] = (uint64_t)pos_out;
+    a.counts[3] = carry_errs;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_derand_out(DerandArgs a) {
+  // 64 threads (one per 3 bytes... simply byte-wise) per packet, 4 packets per block.
+  const uint64_t p = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  if (p >= a.npackets) return;
+  const unsigned idx = a.scratch[p];
+  if (idx == 0xffffffffu || idx >= a.ts_cap) return;
+  const unsigned pos = a.scratch[a.npackets + p];
+  const uint8_t *src = a.rts + 188 * p;
+  uint8_t *dst = a.ts_out + 188 * (uint64_t)idx;
+  for (int i = threadIdx.x & 63; i < 188; i += 64) dst[i] = src[i] ^ a.pattern[pos + i];
+}
+
+}  // namespace
+
+cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st) {
+  const uint64_t n = a.nbytes + 1;
+  k_deconv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, carry_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sync_flags(const uint8_t *bytes, uint64_t npackets, const SyncState *st_dev,
+                              uint32_t *bad_words, cudaStream_t st) {
+  if (!npackets) return cudaSuccess;
+  k_sync_flags<<<(unsigned)((npackets + 255) / 256), 256, 0, st>>>(bytes, npackets, st_dev, bad_words);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_dev,
+                              const uint32_t *bad_words, uint64_t npackets_flagged, SyncResult *res,
+                              cudaStream_t st) {
+  k_sync_track<<<1, 32, 0, st>>>(bytes, nbytes, st_dev, bad_words, npackets_flagged, res);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_realign(const uint8_t *bytes, uint64_t n, int bitphase, int polarity, uint8_t *out,
+                           cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  k_realign<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bytes, n, bitphase, polarity, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_deint_rs(const DeintRsArgs &a, cudaStream_t st) {
+  if (!a.npackets) return cudaSuccess;
+  unsigned blocks = (unsigned)((a.npackets + 3) / 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_rs<true><<<blocks, 128, 0, st>>>(a.mpeg, a.npackets, a.gf_exp, a.gf_log, a.rs_out, a.rts_out, a.flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rs_only(const RsOnlyArgs &a, cudaStream_t st) {
+  if (!a.npackets) return cudaSuccess;
+  unsigned blocks = (unsigned)((a.npackets + 3) / 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_rs<false><<<blocks, 128, 0, st>>>(a.rs_in, a.npackets, a.gf_exp, a.gf_log, nullptr, a.rts_out, a.flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_derand(const DerandArgs &a, cudaStream_t st, int *launches) {
+  if (!a.npackets) {
+    // counts must still be defined
+    uint64_t z[4] = {0, 0, (uint64_t)a.pos_in, 0};
+    return cudaMemcpyAsync(a.counts, z, sizeof(z), cudaMemcpyHostToDevice, st);
+  }
+  k_derand_scan<<<1, 1024, 0, st>>>(a);
+  k_derand_out<<<(unsigned)((a.npackets + 3) / 4), 256, 0, st>>>(a);
+  if (launches) *launches += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace ldvb

@@ -1,0 +1,220 @@
+// k_notch.cu -- K2: auto_notch<f32> (sdr.h:46-154).
+//
+// detect(): every 1024*4096 input samples the reference runs a 4096-point
+//   radix-2 inverse FFT (cfft_engine::inplace, dsp.h:78-110) on the current
+//   block, takes hypotf() of every bin and picks the nslots strongest peaks
+//   (first maximum wins, neighbours zeroed; sdr.h:76-118).  One CTA per detect
+//   point reproduces the butterfly order and rounding exactly: butterflies of a
+//   stage are independent, so they run in parallel with the same per-element
+//   arithmetic; hypotf is evaluated like glibc does, in double.
+// process(): per sample and slot a one-pole estimate of the birdie
+//   estim = bb*k + estim*(1-k), bb = x*conj(e[n]), out = x - estim*e[n]
+//   (sdr.h:119-138).  The recurrence is serial in time and float addition is not
+//   associative, so an exact parallel prefix does not exist.  The stream is cut
+//   into segments that run concurrently; a segment that does not start at a
+//   known-exact state (batch start or a reset at a detect point) starts
+//   `warm_blocks` earlier from a zero estimate: the influence of the start value
+//   decays as 0.998^n and vanishes below one ulp, after which both trajectories
+//   round identically for ever.  Every segment records its state at entry and
+//   exit; the host checks entry(j+1) == exit(j) bit for bit and re-runs the rare
+//   segment whose warm-up had not merged (exact by induction over segments).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ldvb {
+
+namespace {
+
+__device__ __forceinline__ float2 load_sample(const RawSrc &src, int fmt, uint64_t idx, float scale) {
+  const void *raw = src.head;
+  if (src.main && idx >= src.c0) { raw = src.main; idx -= src.c0; }
+  switch (fmt) {
+    case 0: {
+      uchar2 v = reinterpret_cast<const uchar2 *>(raw)[idx];
+      return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128));
+    }
+    case 1: {
+      char2 v = reinterpret_cast<const char2 *>(raw)[idx];
+      return make_float2((float)(int)v.x, (float)(int)v.y);
+    }
+    case 2: {
+      ushort2 v = reinterpret_cast<const ushort2 *>(raw)[idx];
+      return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768));
+    }
+    case 3: {
+      short2 v = reinterpret_cast<const short2 *>(raw)[idx];
+      return make_float2((float)(int)v.x, (float)(int)v.y);
+    }
+    case 4: {
+      float2 v = __ldg(reinterpret_cast<const float2 *>(raw) + idx);
+      return make_float2(fmul(v.x, scale), fmul(v.y, scale));
+    }
+    default:
+      return __ldg(reinterpret_cast<const float2 *>(raw) + idx);
+  }
+}
+
+// --------------------------------------------------------------------- detect
+__global__ void __launch_bounds__(1024)
+k_notch_detect(NotchDetectArgs a) {
+  __shared__ float2 d[kNotchN];
+  float *amp = reinterpret_cast<float *>(d);  // reused once the spectrum is in registers
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  const int tid = threadIdx.x;
+  const uint64_t base = a.block_index[blockIdx.x] * (uint64_t)kNotchN;
+  // Load with the bit-reversal permutation applied (dsp.h:79-83 swaps i <-> rev(i)).
+  for (int i = tid; i < kNotchN; i += 1024) {
+    const int r = (int)(__brev((unsigned)i) >> 20);
+    d[r] = load_sample(a.src, a.fmt, base + i, a.scale);
+  }
+  __syncthreads();
+  // Danielson-Lanczos stages (dsp.h:85-102), twiddle om[k*dom] from the host table.
+  for (int s = 0; s < 12; ++s) {
+    const int hbs = 1 << s, dom = 1 << (11 - s);
+    for (int b = tid; b < kNotchN / 2; b += 1024) {
+      const int j = b >> s, k = b & (hbs - 1);
+      const int pidx = j * hbs * 2 + k, qidx = pidx + hbs;
+      const float2 w = a.twiddle_rev[k * dom];
+      const float2 q = d[qidx], p = d[pidx];
+      const float xr = fsub(fmul(w.x, q.x), fmul(w.y, q.y));
+      const float xi = fadd(fmul(w.x, q.y), fmul(w.y, q.x));
+      d[qidx] = make_float2(fsub(p.x, xr), fsub(p.y, xi));
+      d[pidx] = make_float2(fadd(p.x, xr), fadd(p.y, xi));
+    }
+    __syncthreads();
+  }
+  const float invn = 1.0f / kNotchN;  // dsp.h:104-109
+  float my_amp[kNotchN / 1024];
+  for (int q = 0; q < kNotchN / 1024; ++q) {
+    const int i = tid + 1024 * q;
+    const float re = fmul(d[i].x, invn), im = fmul(d[i].y, invn);
+    // glibc hypotf: (float)sqrt((double)x*x + (double)y*y)
+    const double s2 = __dadd_rn(__dmul_rn((double)re, (double)re), __dmul_rn((double)im, (double)im));
+    my_amp[q] = __double2float_rn(__dsqrt_rn(s2));
+  }
+  __syncthreads();
+  for (int q = 0; q < kNotchN / 1024; ++q) amp[tid + 1024 * q] = my_amp[q];
+  __syncthreads();
+  for (int slot = 0; slot < a.nslots; ++slot) {
+    // argmax, first maximum wins (strict '>' in the reference's forward scan).
+    float bv = -1.f; int bi = 0;
+    for (int i = tid; i < kNotchN; i += 1024) {
+      const float v = amp[i];
+      if (v > bv) { bv = v; bi = i; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+      bv = s_val[tid]; bi = s_idx[tid];
+      for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (tid == 0) {
+        a.bins_out[blockIdx.x * a.nslots + slot] = bi;
+        amp[bi] = 0;
+        if (bi - 1 >= 0) amp[bi - 1] = 0;
+        if (bi + 1 < kNotchN) amp[bi + 1] = 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------- apply
+__global__ void __launch_bounds__(64)
+k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
+  uint32_t seg = (only_segment >= 0) ? (uint32_t)only_segment : blockIdx.x * blockDim.x + threadIdx.x;
+  if (only_segment >= 0 && (blockIdx.x != 0 || threadIdx.x != 0)) return;
+  if (seg >= a.nsegs) return;
+  const uint64_t own_begin = (uint64_t)seg * a.seg_blocks;
+  uint64_t own_end = own_begin + a.seg_blocks;
+  if (own_end > a.nblocks) own_end = a.nblocks;
+
+  // Epoch at the start of the owned region, and whether it begins with a reset.
+  int ep = 0;
+  while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= own_begin) ++ep;
+  float er[kNotchMaxSlots], ei[kNotchMaxSlots];
+  bool exact = false;
+  uint64_t run_begin = own_begin;
+  if (forced_entry) {
+    for (int s = 0; s < a.nslots; ++s) { er[s] = forced_entry[s].x; ei[s] = forced_entry[s].y; }
+    exact = true;
+  } else if (seg == 0) {
+    for (int s = 0; s < a.nslots; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
+    exact = true;
+  } else {
+    // Warm-up from a zero estimate, clamped to the epoch start (tables change there).
+    uint64_t wb = (own_begin > a.warm_blocks) ? own_begin - a.warm_blocks : 0;
+    if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
+    run_begin = wb;
+    for (int s = 0; s < a.nslots; ++s) { er[s] = 0.f; ei[s] = 0.f; }
+    // Known-exact start: the segment begins exactly at an epoch whose slots all reset,
+    // or the warm-up reaches back to block 0 of the batch... (only resets are exact).
+    if (a.epochs[ep].first_block == own_begin) {
+      bool all = true;
+      for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
+      exact = all;
+    }
+  }
+  const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
+
+  for (uint64_t blk = run_begin; blk < own_end; ++blk) {
+    // Epoch switch (only possible at own_begin or later; warm-up is clamped).
+    while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= blk) ++ep;
+    if (a.epochs[ep].first_block == blk) {
+      for (int s = 0; s < a.nslots; ++s)
+        if (a.epochs[ep].reset[s]) { er[s] = 0.f; ei[s] = 0.f; }
+    }
+    if (blk == own_begin && a.seg_entry)
+      for (int s = 0; s < a.nslots; ++s) a.seg_entry[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+    const bool write = (blk >= own_begin);
+    const uint64_t base = blk * (uint64_t)kNotchN;
+    const float2 *tab[kNotchMaxSlots];
+    for (int s = 0; s < a.nslots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN;
+    for (int n = 0; n < kNotchN; ++n) {
+      const float2 x = load_sample(a.src, a.fmt, base + n, a.scale);
+      float outr = x.x, outi = x.y;
+      for (int s = 0; s < a.nslots; ++s) {
+        const float2 e = __ldg(tab[s] + n);
+        const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
+        const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
+        er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
+        ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
+        const float subr = fsub(fmul(er[s], e.x), fmul(ei[s], e.y));
+        const float subi = fadd(fmul(er[s], e.y), fmul(ei[s], e.x));
+        outr = fsub(outr, subr);
+        outi = fsub(outi, subi);
+      }
+      if (write) a.out[base + n] = make_float2(fmul(gain, outr), fmul(gain, outi));
+    }
+  }
+  if (a.seg_exit)
+    for (int s = 0; s < a.nslots; ++s) a.seg_exit[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+  if (a.seg_exact && !forced_entry) a.seg_exact[seg] = exact ? 1 : 0;
+}
+
+}  // namespace
+
+cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st) {
+  if (a.ndetect <= 0) return cudaSuccess;
+  k_notch_detect<<<a.ndetect, 1024, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
+                               cudaStream_t st) {
+  if (a.nsegs == 0 || a.nblocks == 0) return cudaSuccess;
+  if (only_segment >= 0) k_notch_apply<<<1, 32, 0, st>>>(a, only_segment, forced_entry);
+  else k_notch_apply<<<(a.nsegs + 31) / 32, 32, 0, st>>>(a, -1, nullptr);
+  return cudaGetLastError();
+}
+
+}  // namespace ldvb

@@ -1,0 +1,248 @@
+// kernels.h -- launch interfaces of the sm_100a kernels (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace ldvb {
+
+// Two-part view of an input stream: logical element i lives in `head` when
+// i < c0 or main == nullptr, else in main[i - c0].  `head` holds the samples
+// carried from the previous batch followed by the first samples of the new one,
+// so that a device-resident batch (`main`) is processed in place, without a copy.
+struct RawSrc {
+  const void *head; uint64_t head_count;
+  const void *main; uint64_t c0;
+};
+
+// ------------------------------------------------------------------ K1 frontend
+struct FrontendArgs {
+  RawSrc src;             // input stream (both parts 16-byte aligned)
+  int fmt;                // 0 u8, 1 s8, 2 u16, 3 s16, 4 f32 (scaled), 5 cf32 (as is)
+  float scale;            // --float-scale (fmt 4)
+  const float *rot_lut;   // 65536 cos then 65536 sin, or nullptr
+  uint32_t rot_index0;    // rotator index of sample 0
+  const float2 *taps;     // ntaps shifted complex taps, ntaps == 0: copy/decimate only
+  uint32_t ntaps, decim;
+  float2 *out;
+  uint64_t count;         // outputs to produce
+  // filled by launch_frontend
+  uint32_t tile_out, bytes_per_sample, max_raw_bytes;
+};
+int frontend_bytes_per_sample(int fmt);
+cudaError_t launch_frontend(FrontendArgs a, cudaStream_t st);
+
+// --------------------------------------------------------------------- K2 notch
+constexpr int kNotchN = 4096;
+constexpr int kNotchMaxSlots = 4;
+
+struct NotchSlotState { int32_t bin; float est_re, est_im; int32_t pad; };
+struct NotchState {
+  int32_t phase;          // samples since the last detect() (sdr.h:66-70)
+  float gain;
+  NotchSlotState slot[kNotchMaxSlots];
+};
+
+// Detection: one CTA per detect point runs the 4096-point radix-2 inverse FFT
+// and the peak search of auto_notch::detect() (sdr.h:76-118).
+struct NotchDetectArgs {
+  RawSrc src; int fmt; float scale;           // same sample access as the front end
+  const uint64_t *block_index;                // [ndetect] 4096-block index of each detect point
+  int ndetect, nslots;
+  const float2 *twiddle_rev;                  // [4096] omega_rev (dsp.h:70-76)
+  int32_t *bins_out;                          // [ndetect][nslots]
+};
+cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st);
+
+// Builds expj tables for an epoch: [nslots][4096] (sdr.h:104-108); computed on
+// the host (glibc cosf/sinf) and uploaded, the kernel only applies them.
+struct NotchEpoch {
+  uint64_t first_block;   // first 4096-block of the batch that uses this epoch's tables
+  int32_t bin[kNotchMaxSlots];
+  int32_t reset[kNotchMaxSlots];  // slot estimate is zeroed at first_block (bin changed)
+  uint32_t table_index[kNotchMaxSlots];  // which uploaded expj table each slot uses
+};
+
+struct NotchApplyArgs {
+  RawSrc src; int fmt; float scale;
+  float2 *out;
+  uint64_t nblocks;                // 4096-sample blocks to process
+  int nslots;
+  float k, gain;
+  const float2 *expj_tables;       // [ntables][4096]
+  const NotchEpoch *epochs;        // device, sorted by first_block
+  int nepochs;
+  uint32_t seg_blocks;             // blocks owned per segment
+  uint32_t warm_blocks;            // warm-up blocks before a speculative segment
+  uint32_t nsegs;
+  const NotchState *state_in;      // exact state at block 0
+  float2 *seg_entry;               // [nsegs][slots] state at segment start (after warm-up)
+  float2 *seg_exit;                // [nsegs][slots] state at segment end
+  uint8_t *seg_exact;              // [nsegs] 1 when the segment started from a known-exact state
+};
+cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
+                               cudaStream_t st);
+
+// ------------------------------------------------------------------ K3 receiver
+struct CstlnCellDev { int16_t cost, symbol, phase_error, pad; };
+
+struct RxParams {
+  const CstlnCellDev *cstln;   // [65536]
+  const float2 *trig;          // [65536]
+  int8_t sym_re[32], sym_im[32];
+  int nsymbols, sampler;
+  float omega, min_freqw, max_freqw;
+  float freq_alpha, freq_beta, gain_mu, kest;
+  int allow_drift;
+  uint32_t meas_decimation;
+  // rrc sampler
+  const float *rrc_coeffs; int rrc_n, rrc_sub;
+};
+
+// 22 words, same layout as ldvb_get_rx_state (include/leandvb_b200.h).
+struct RxState {
+  float mu, phase, freqw, est_insp, agc_gain, est_sp, est_ep;
+  float hist[12];          // hist[k] = {p.re, p.im, c.re, c.im}
+  float samp_freqw, freq_tap;
+  uint32_t meas_count;
+  int32_t rrc_update_phase;
+  int32_t pad;
+};
+
+struct RxSeamSym { float t; uint32_t sym; };  // time relative to the seam, hard symbol
+
+struct RxSpanInfo {
+  uint32_t n_out;          // symbols emitted in the owned region (sample index < end)
+  uint32_t n_tail;         // symbols emitted in the verification overlap after the end
+  uint32_t n_head_logged;  // entries in the head log
+  uint32_t pad;
+};
+
+constexpr int kRxChunk = 128;
+constexpr int kRxSeamLog = 384;        // log entries per seam side
+constexpr int kRxVerifyChunks = 2;     // chunks of overlap after a span end
+
+struct RxArgs {
+  RxParams p;
+  const float2 *x;           // preprocessed stream, chunk c starts at x[c*128]
+  uint64_t nchunks;          // chunks available in this batch
+  uint32_t span_chunks;      // owned chunks per span (exact mode: >= nchunks)
+  uint32_t warm_chunks;      // warm-up chunks (0 in exact mode)
+  uint32_t nspans;
+  uint32_t span_cap;         // symbol capacity of one span's output region
+  const RxState *state_in;   // exact/carried state at chunk 0
+  uint32_t *sym_out;         // [nspans][span_cap] softsymbols {cost:16, symbol:8, 0}
+  RxSpanInfo *info;          // [nspans]
+  RxState *state_end;        // [nspans] state at the span's nominal end
+  RxSeamSym *head_log;       // [nspans][kRxSeamLog]
+  RxSeamSym *tail_log;       // [nspans][kRxSeamLog]
+  float2 *sampled;           // optional [nchunks] tap (exact mode), may be null
+  uint32_t *sampled_flag;    // optional [nchunks]
+  float *meas;               // optional [max_meas][4] {chunk, freq_tap, ss, mer}
+  uint32_t *meas_count;      // optional counter
+  uint32_t max_meas;
+};
+// only_span < 0: all spans.  Otherwise re-run one span from forced_state (seam repair).
+cudaError_t launch_rx(const RxArgs &a, int only_span, const RxState *forced_state, cudaStream_t st);
+
+struct RxSeam {
+  int32_t ok;              // verification passed
+  int32_t rot;             // rotation of span j+1 relative to span j (units of 360/nrot)
+  int32_t extend_prev;     // span j keeps this many tail symbols (0/1)
+  int32_t skip_next;       // span j+1 drops this many head symbols (0/1)
+  int32_t compared;        // symbols compared
+  int32_t mismatches;
+};
+struct RxStitchArgs {
+  const RxSpanInfo *info; const RxSeamSym *head_log; const RxSeamSym *tail_log;
+  uint32_t nspans; int nrot; int nsymbols;
+  const uint8_t *rot_perm;   // [nrot][nsymbols] device
+  float omega;
+  RxSeam *seams;             // [nspans-1]
+};
+cudaError_t launch_rx_stitch(const RxStitchArgs &a, int only_seam, cudaStream_t st);
+
+// Concatenates the span outputs into one contiguous softsymbol stream, applying
+// each span's cumulative rotation to the hard symbol.
+struct RxCompactArgs {
+  const uint32_t *sym_in; uint32_t span_cap; uint32_t nspans;
+  const uint64_t *span_offset;   // [nspans+1] exclusive prefix of kept counts (device)
+  const uint32_t *span_skip;     // [nspans]
+  const uint8_t *span_rot;       // [nspans] cumulative rotation
+  const uint8_t *rot_perm; int nsymbols;
+  uint32_t *sym_out;             // appended after the carried symbols
+};
+cudaError_t launch_rx_compact(const RxCompactArgs &a, uint64_t total, cudaStream_t st);
+
+// -------------------------------------------------------------- K4 deconvolution
+struct DeconvArgs {
+  const uint32_t *symbols;   // softsymbols, element 0 = first unread symbol
+  uint64_t nbytes;           // bytes to produce
+  uint64_t reg_in; int n_in; // carried shift register of the locked hypothesis (dvb.h:297-303)
+  uint64_t out_acc; int n_out;
+  uint8_t hyp[4];            // symbol&3 -> IQ bits of the locked hypothesis
+  int punctperiod, punctweight;
+  uint64_t deconv[8];
+  uint8_t *out;
+};
+// carry_out (device, 5 x uint64): register, n_in, accumulator, n_out, symbols consumed.
+cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st);
+
+// ---------------------------------------------------------------- K6/K7 framing
+struct SyncState {
+  int32_t synchronized, bitphase, polarity, phase8;
+  int32_t next_sync_count;
+  uint32_t lock_timeleft;
+  uint64_t locktime;
+  int32_t report_state;
+  int32_t pad;
+};
+
+// Outcome of one pass of the MPEG sync tracker over the byte stream.
+struct SyncResult {
+  SyncState st;              // state after the pass
+  uint64_t consumed;         // bytes consumed from the input
+  uint64_t produced;         // aligned bytes to append to mpegbytes (multiple of 204)
+  int32_t need_next_sync;    // third fruitless sweep completed: switch hypothesis (dvb.h:771-778)
+  int32_t events;            // lock transitions in this pass
+  int32_t event_val[16];
+  uint64_t event_pos[16];
+};
+
+cudaError_t launch_sync_flags(const uint8_t *bytes, uint64_t npackets, const SyncState *st_dev,
+                              uint32_t *bad_words, cudaStream_t st);
+cudaError_t launch_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_dev,
+                              const uint32_t *bad_words, uint64_t npackets_flagged, SyncResult *res,
+                              cudaStream_t st);
+cudaError_t launch_realign(const uint8_t *bytes, uint64_t n, int bitphase, int polarity, uint8_t *out,
+                           cudaStream_t st);
+
+// Deinterleaver + RS(204,188) + flags; warp per packet.
+struct DeintRsArgs {
+  const uint8_t *mpeg;       // aligned byte stream, element 0 = oldest byte kept (history)
+  uint64_t npackets;         // packets to decode: packet p reads mpeg[204*p .. 204*p+2447]
+  const uint8_t *gf_exp, *gf_log;   // device tables (512, 256)
+  uint8_t *rs_out;           // optional tap: deinterleaved 204-byte packets (may be null)
+  uint8_t *rts_out;          // 188-byte packets
+  int32_t *flags;            // [npackets][2] corrupted, bits corrected
+};
+cudaError_t launch_deint_rs(const DeintRsArgs &a, cudaStream_t st);
+
+struct RsOnlyArgs {
+  const uint8_t *rs_in; uint64_t npackets; const uint8_t *gf_exp, *gf_log;
+  uint8_t *rts_out; int32_t *flags;
+};
+cudaError_t launch_rs_only(const RsOnlyArgs &a, cudaStream_t st);
+
+struct DerandArgs {
+  const uint8_t *rts; uint64_t npackets;
+  const uint8_t *pattern;    // 1504 bytes
+  int32_t pos_in;            // carried pattern position (multiple of 188)
+  uint8_t *ts_out; uint64_t ts_cap;
+  uint64_t *counts;          // device [4]: kept, dropped, pos_out, rs_errs_sum
+  const int32_t *flags;      // RS flags for the error sum (may be null)
+  uint32_t *scratch;         // [npackets + 64]
+};
+cudaError_t launch_derand(const DerandArgs &a, cudaStream_t st, int *launches);
+
+}  // namespace ldvb

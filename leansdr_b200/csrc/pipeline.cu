@@ -1,0 +1,1322 @@
+// pipeline.cu -- handle, stream bookkeeping and the C ABI (include/leandvb_b200.h).
+//
+// One handle owns the device-side equivalent of the reference pipebufs between
+// leandvb's input and p_tspackets (apps/leandvb.cc:204-596).  Each inter-stage
+// stream is a flat device buffer "[items carried from the previous batch | items
+// produced by this batch]": what a stage cannot consume yet stays at the front,
+// exactly like unread items in a reference pipebuf (framework.h:153-159).
+//
+// Control decisions that the reference takes per run() call (filter retune,
+// hypothesis switch, lock/unlock) are taken per batch on the host from small
+// device-side result records; all sample/symbol/byte arithmetic runs in the
+// kernels of k_*.cu.  There is no CPU fallback: without a CUDA device
+// ldvb_create fails with LDVB_ENODEV.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/leandvb_b200.h"
+#include "kernels.h"
+#include "tables.h"
+
+using namespace ldvb;
+
+namespace ldvb {
+// defined in k_fec.cu
+cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st);
+}
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t alloc(size_t n) {
+    bytes = n;
+    return cudaMalloc(&p, n ? n : 16);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// Flat FIFO of `elem`-byte items on the device.
+struct Stream {
+  DevBuf buf;
+  size_t elem = 1;
+  uint64_t cap = 0;     // items
+  uint64_t count = 0;   // items currently held (carry + new)
+  uint64_t fresh = 0;   // items appended by the current batch (for taps)
+  uint8_t *at(uint64_t i) const { return buf.as<uint8_t>() + i * elem; }
+};
+
+struct HypState { uint64_t reg = 0, acc = 0; int n_in = 0, n_out = 0; };
+
+struct Tap {
+  DevBuf buf;
+  uint64_t bytes = 0;
+};
+
+}  // namespace
+
+struct ldvb_handle {
+  ldvb_config cfg;
+  cudaStream_t st = nullptr;
+  std::string err;
+  ldvb_meas meas;
+  uint32_t launches = 0;
+
+  // ---- derived configuration
+  int bps_in = 2;
+  float Fs_rx = 0;
+  int decim = 1;
+  std::vector<float> fir_coeffs, fir_shifted;
+  float fir_current_freq = 0, fir_tol = 0.1f, fir_tap_mult = 1;
+  int fir_n = 0;
+  bool use_fir = false, use_decim = false, use_rot = false;
+  Cstln cst;
+  DeconvPolys dec;
+  RxParams rxp;
+  int readahead = 1;
+
+  // ---- device tables
+  DevBuf d_cstln, d_trig, d_rot, d_taps, d_gfexp, d_gflog, d_derand, d_rotperm, d_twiddle;
+
+  // ---- streams
+  Stream s_raw;      // head part of the raw stream (carry + start of batch, or whole batch for push)
+  Stream s_notched;  // cf32 after the notch (input of the front end when anf > 0)
+  Stream s_pp;       // cf32 preprocessed = receiver input
+  Stream s_sym;      // softsymbols
+  Stream s_bytes;    // deconvolved bytes
+  Stream s_mpeg;     // aligned bytes (with de-interleaver history)
+  DevBuf d_rts, d_rsflags, d_ts, d_scratch, d_badwords, d_rs204;
+  uint64_t ts_cap = 0;
+
+  // ---- carry state
+  NotchState notch;            // host mirror
+  std::map<int, uint32_t> notch_table_of_bin;
+  DevBuf d_notch_tables; uint32_t notch_tables_used = 0, notch_tables_cap = 0;
+  DevBuf d_notch_state, d_notch_epochs, d_notch_entry, d_notch_exit, d_notch_exact, d_notch_bins, d_notch_blocks;
+  uint32_t rot_index = 0;
+  RxState rx_state;            // host mirror of the exact/carried receiver state
+  DevBuf d_rx_state, d_rx_info, d_rx_end, d_rx_head, d_rx_tail, d_rx_seams, d_rx_spans;
+  DevBuf d_rx_off, d_rx_skip, d_rx_rot, d_rx_meas, d_rx_measn, d_rx_forced;
+  uint32_t rx_max_spans = 1, rx_span_cap = 0;
+  HypState hyp[4];
+  int locked = 0, skip = 0;
+  DevBuf d_deconv_carry;
+  SyncState sync;
+  DevBuf d_sync_state, d_sync_res;
+  int derand_pos = 0;
+  DevBuf d_counts;
+
+  // ---- host-side TS queue for push/pull
+  std::vector<uint8_t> ts_queue;
+  size_t ts_queue_rd = 0;
+
+  // ---- taps
+  Tap taps[9];
+  std::vector<float> meas_log;   // {freq_tap, ss, mer} per measurement of the last batch
+};
+
+namespace {
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      char b_[256];                                                                   \
+      snprintf(b_, sizeof b_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      h->err = b_;                                                                    \
+      return LDVB_ECUDA;                                                              \
+    }                                                                                 \
+  } while (0)
+
+int fail(ldvb_handle *h, int code, const char *msg) {
+  h->err = msg;
+  return code;
+}
+
+cudaError_t upload(DevBuf &b, const void *src, size_t n) {
+  cudaError_t e = b.alloc(n);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(b.p, src, n, cudaMemcpyHostToDevice);
+}
+
+int stream_alloc(ldvb_handle *h, Stream &s, size_t elem, uint64_t cap) {
+  s.elem = elem;
+  s.cap = cap;
+  s.count = 0;
+  CK(s.buf.alloc((size_t)(cap + 64) * elem + 256));
+  CK(cudaMemset(s.buf.p, 0, s.buf.bytes));
+  return LDVB_OK;
+}
+
+// Drop `n` items from the front, moving the remainder to offset 0.
+int stream_consume(ldvb_handle *h, Stream &s, uint64_t n, DevBuf &tmp) {
+  if (n > s.count) return fail(h, LDVB_ESTATE, "stream underflow");
+  const uint64_t left = s.count - n;
+  if (n && left) {
+    if (left <= n) {
+      CK(cudaMemcpyAsync(s.at(0), s.at(n), left * s.elem, cudaMemcpyDeviceToDevice, h->st));
+    } else {
+      if (tmp.bytes < left * s.elem) return fail(h, LDVB_EOVERFLOW, "carry larger than scratch");
+      CK(cudaMemcpyAsync(tmp.p, s.at(n), left * s.elem, cudaMemcpyDeviceToDevice, h->st));
+      CK(cudaMemcpyAsync(s.at(0), tmp.p, left * s.elem, cudaMemcpyDeviceToDevice, h->st));
+    }
+  }
+  s.count = left;
+  return LDVB_OK;
+}
+
+int tap_store(ldvb_handle *h, int which, const void *dev, uint64_t bytes) {
+  if (!h->cfg.keep_taps) return LDVB_OK;
+  Tap &t = h->taps[which];
+  if (t.buf.bytes < bytes) {
+    t.buf.release();
+    CK(t.buf.alloc(bytes + bytes / 4 + 4096));
+  }
+  if (bytes) CK(cudaMemcpyAsync(t.buf.p, dev, bytes, cudaMemcpyDeviceToDevice, h->st));
+  t.bytes = bytes;
+  return LDVB_OK;
+}
+
+// ------------------------------------------------------------------ receiver
+
+void rx_reset_state(ldvb_handle *h) {
+  RxState &s = h->rx_state;
+  memset(&s, 0, sizeof s);
+  s.est_insp = 75.0f * 75.0f;  // sdr.h:727
+  s.agc_gain = 1;
+}
+
+void rx_setup(ldvb_handle *h) {
+  const ldvb_config &c = h->cfg;
+  RxParams &p = h->rxp;
+  memset(&p, 0, sizeof p);
+  for (int s = 0; s < h->cst.nsymbols && s < 32; ++s) {
+    p.sym_re[s] = h->cst.sym_re[s];
+    p.sym_im[s] = h->cst.sym_im[s];
+  }
+  p.nsymbols = h->cst.nsymbols;
+  p.sampler = c.sampler;
+  // set_omega (sdr.h:738-743) then update_freq_limits (sdr.h:755-770) with the
+  // constellation already known (leandvb.cc:476-482).
+  const float omega = h->Fs_rx / c.Fm;
+  const float tol = 10e-6;
+  const float max_omega = omega * (1 + tol);
+  int n = 4;
+  switch (h->cst.nsymbols) { case 2: n = 2; break; case 4: n = 4; break; case 8: n = 8; break; default: n = 4; }
+  float freqw = 0;
+  if (c.Ftune) freqw = (c.Ftune / h->Fs_rx) * 65536;  // set_freq (sdr.h:745-749)
+  // The constructor's set_freq(0)/set_omega(1) are overwritten by these calls;
+  // note that set_freq() after set_omega() recomputes the limits around freqw.
+  p.omega = omega;
+  p.min_freqw = freqw - 65536 / max_omega / n / 2;
+  p.max_freqw = freqw + 65536 / max_omega / n / 2;
+  float pll_adjustment = 1.0f;
+  if (c.viterbi) pll_adjustment /= 6;  // leandvb.cc:498-501
+  p.freq_alpha = 0.04;                 // sdr.h:776-778
+  p.freq_beta = 0.0012 / omega * pll_adjustment;
+  p.gain_mu = 0.02 / (75.0f * 75.0f) * 2;
+  p.kest = 0.01f;
+  p.allow_drift = c.allow_drift;
+  int md = (int)(h->Fs_rx / c.Finfo);  // decimation(Fs, Finfo), leandvb.cc:138-141, 502
+  p.meas_decimation = (uint32_t)std::max(md, 1);
+  rx_reset_state(h);
+  h->rx_state.freqw = freqw;
+  h->rx_state.freq_tap = freqw / 65536;
+  h->readahead = (c.sampler == LDVB_SAMP_NEAREST) ? 0 : 1;
+}
+
+}  // namespace
+
+// =========================================================================== API
+
+extern "C" {
+
+int ldvb_abi_version(void) { return LDVB_ABI_VERSION; }
+
+const char *ldvb_strerror(int code) {
+  switch (code) {
+    case LDVB_OK: return "ok";
+    case LDVB_EINVAL: return "invalid argument or unsupported configuration";
+    case LDVB_ENOMEM: return "out of memory";
+    case LDVB_ECUDA: return "CUDA error";
+    case LDVB_ENODEV: return "no usable CUDA device (sm_100 required)";
+    case LDVB_EOVERFLOW: return "batch larger than the handle was sized for";
+    case LDVB_ESTATE: return "invalid call sequence / internal state";
+    default: return "unknown error";
+  }
+}
+
+const char *ldvb_last_error(const ldvb_handle *h) { return h ? h->err.c_str() : ""; }
+
+void ldvb_config_default(ldvb_config *c) {
+  memset(c, 0, sizeof *c);
+  c->abi_version = LDVB_ABI_VERSION;
+  c->input_format = LDVB_FMT_U8;
+  c->float_scale = 1.0f;
+  c->Fs = 2.4e6f;
+  c->Fm = 2e6f;
+  c->anf = 1;
+  c->resample_rej = 10;
+  c->sampler = LDVB_SAMP_LINEAR;
+  c->rrc_rej = 10;
+  c->rolloff = 0.35f;
+  c->constellation = LDVB_CSTLN_QPSK;
+  c->fec = LDVB_FEC12;
+  c->Finfo = 5;
+  c->rx_mode = LDVB_RX_EXACT;
+  c->device = 0;
+  c->max_batch = 1u << 22;
+}
+
+int ldvb_destroy(ldvb_handle *h) {
+  if (!h) return LDVB_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  DevBuf *bufs[] = {&h->d_cstln, &h->d_trig, &h->d_rot, &h->d_taps, &h->d_gfexp, &h->d_gflog, &h->d_derand,
+                    &h->d_rotperm, &h->d_twiddle, &h->s_raw.buf, &h->s_notched.buf, &h->s_pp.buf, &h->s_sym.buf,
+                    &h->s_bytes.buf, &h->s_mpeg.buf, &h->d_rts, &h->d_rsflags, &h->d_ts, &h->d_scratch,
+                    &h->d_badwords, &h->d_rs204, &h->d_notch_tables, &h->d_notch_state, &h->d_notch_epochs,
+                    &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
+                    &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
+                    &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
+                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
+  for (DevBuf *b : bufs) b->release();
+  for (Tap &t : h->taps) t.buf.release();
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return LDVB_OK;
+}
+
+int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
+  if (!cfg || !out) return LDVB_EINVAL;
+  *out = nullptr;
+  if (cfg->abi_version != LDVB_ABI_VERSION) return LDVB_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) return LDVB_ENODEV;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return LDVB_ENODEV;
+  if (prop.major < 10) return LDVB_ENODEV;  // kernels are built for sm_100a only
+  ldvb_handle *h = new (std::nothrow) ldvb_handle();
+  if (!h) return LDVB_ENOMEM;
+  h->cfg = *cfg;
+  memset(&h->meas, 0, sizeof h->meas);
+  const ldvb_config &c = h->cfg;
+  auto bail = [&](int code, const char *msg) {
+    fprintf(stderr, "ldvb_create: %s\n", msg);
+    ldvb_destroy(h);
+    return code;
+  };
+  if (c.input_format < 0 || c.input_format > LDVB_FMT_F32) return bail(LDVB_EINVAL, "bad input_format");
+  if (c.fastlock) return bail(LDVB_EINVAL, "--fastlock is not supported");
+  if (c.viterbi) return bail(LDVB_EINVAL, "--viterbi is not supported yet");
+  if (c.sampler == LDVB_SAMP_RRC) return bail(LDVB_EINVAL, "--sampler rrc is not supported yet");
+  if (c.sampler < 0 || c.sampler > 2) return bail(LDVB_EINVAL, "bad sampler");
+  if (c.anf < 0 || c.anf > kNotchMaxSlots) return bail(LDVB_EINVAL, "anf must be 0..4");
+  if (!(c.Fs > 0) || !(c.Fm > 0) || c.max_batch == 0) return bail(LDVB_EINVAL, "bad rates or max_batch");
+  if (cudaSetDevice(c.device) != cudaSuccess) return bail(LDVB_ENODEV, "cudaSetDevice failed");
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return bail(LDVB_ECUDA, "stream");
+
+  // ---- tables
+  h->cst = make_cstln(c.constellation, c.hard_metric != 0);
+  if (h->cst.nsymbols == 0) return bail(LDVB_EINVAL, "constellation not supported");
+  if (!make_deconv(c.fec, &h->dec)) return bail(LDVB_EINVAL, "code rate not supported");
+  std::vector<float> trig = make_trig16();
+  uint8_t gexp[512], glog[256];
+  make_rs_tables(gexp, glog);
+  std::vector<uint8_t> derand = make_derand_pattern();
+  std::vector<uint8_t> rotperm;
+  for (auto &r : h->cst.rot) rotperm.insert(rotperm.end(), r.begin(), r.end());
+  // FFT twiddles for the notch detector: omega_rev (dsp.h:70-76)
+  std::vector<float> tw(2 * kNotchN);
+  for (int i = 0; i < kNotchN; ++i) {
+    float a = (float)(2.0 * M_PI * i / kNotchN);
+    tw[2 * i] = cosf(a);
+    tw[2 * i + 1] = -sinf(a);
+  }
+  bool ok = upload(h->d_cstln, h->cst.cells.data(), h->cst.cells.size() * sizeof(CstlnCell)) == cudaSuccess &&
+            upload(h->d_trig, trig.data(), trig.size() * 4) == cudaSuccess &&
+            upload(h->d_gfexp, gexp, 512) == cudaSuccess && upload(h->d_gflog, glog, 256) == cudaSuccess &&
+            upload(h->d_derand, derand.data(), derand.size()) == cudaSuccess &&
+            upload(h->d_rotperm, rotperm.data(), rotperm.size()) == cudaSuccess &&
+            upload(h->d_twiddle, tw.data(), tw.size() * 4) == cudaSuccess;
+  if (!ok) return bail(LDVB_ECUDA, "table upload failed");
+
+  // ---- front end (leandvb.cc:310-399)
+  h->bps_in = frontend_bytes_per_sample(c.input_format);
+  float Fs = c.Fs;
+  h->use_rot = (c.Fderot != 0);
+  if (h->use_rot) {
+    std::vector<float> lut = make_rotator_lut(-c.Fderot / c.Fs);
+    if (upload(h->d_rot, lut.data(), lut.size() * 4) != cudaSuccess) return bail(LDVB_ECUDA, "rotator upload");
+  }
+  h->decim = 1;
+  if (c.resample) {
+    int d = 1;
+    h->fir_coeffs = design_resampler(Fs, c.Fm, c.rolloff, c.resample_rej, c.decim, &d);
+    h->fir_n = (int)h->fir_coeffs.size();
+    h->decim = d;
+    h->use_fir = true;
+    Fs /= d;
+    h->fir_tap_mult = 1.0f / d;                     // leandvb.cc:508
+    h->fir_tol = c.Fm / (Fs * d) * 0.1f;            // leandvb.cc:509 (Fs already divided)
+    h->fir_shifted = shift_taps(h->fir_coeffs, 0);
+    h->fir_current_freq = 0;
+    if (upload(h->d_taps, h->fir_shifted.data(), h->fir_shifted.size() * 4) != cudaSuccess)
+      return bail(LDVB_ECUDA, "taps upload");
+  } else if (c.decim > 1) {
+    h->decim = (int)c.decim;
+    h->use_decim = true;
+    Fs /= h->decim;
+  }
+  h->Fs_rx = Fs;
+  rx_setup(h);
+
+  // ---- stream buffers
+  const uint64_t M = c.max_batch;
+  const uint64_t carry_raw = 4096 + (uint64_t)h->fir_n + h->decim + 64;
+  const uint64_t pp_max = M / h->decim + 4096 + 512;
+  const double sym_per_sample = 1.0 / std::max(1.0f, h->rxp.omega - 0.15f);
+  const uint64_t sym_max = (uint64_t)(pp_max * sym_per_sample) + 4096;
+  const uint64_t bytes_max = sym_max * 2 / 8 + 4096;  // <= 2 bits per symbol out
+  const uint64_t pk_max = bytes_max / 204 + 16;
+  int rc;
+  if ((rc = stream_alloc(h, h->s_raw, h->bps_in, M + carry_raw))) return bail(rc, h->err.c_str());
+  if (c.anf && (rc = stream_alloc(h, h->s_notched, 8, M + carry_raw))) return bail(rc, h->err.c_str());
+  if ((rc = stream_alloc(h, h->s_pp, 8, pp_max + 1024))) return bail(rc, h->err.c_str());
+  if ((rc = stream_alloc(h, h->s_sym, 4, sym_max + 4096))) return bail(rc, h->err.c_str());
+  if ((rc = stream_alloc(h, h->s_bytes, 1, bytes_max + 4096))) return bail(rc, h->err.c_str());
+  if ((rc = stream_alloc(h, h->s_mpeg, 1, bytes_max + 8192))) return bail(rc, h->err.c_str());
+  h->ts_cap = pk_max;
+  // Receiver spans
+  uint32_t span_chunks = c.span_chunks ? c.span_chunks : 256;
+  uint32_t nsp = 1;
+  if (c.rx_mode == LDVB_RX_FAST) nsp = (uint32_t)((pp_max / kRxChunk + span_chunks - 1) / span_chunks) + 1;
+  h->rx_max_spans = nsp;
+  h->rx_span_cap = (c.rx_mode == LDVB_RX_FAST)
+                       ? (uint32_t)((span_chunks + kRxVerifyChunks + 1) * kRxChunk * sym_per_sample) + 64
+                       : 0;
+  bool aok =
+      h->d_rts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_rsflags.alloc(pk_max * 8 + 64) == cudaSuccess &&
+      h->d_ts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_scratch.alloc(std::max<uint64_t>(pk_max * 8 + 4096, 1 << 20)) == cudaSuccess &&
+      h->d_badwords.alloc(pk_max / 8 + 4096) == cudaSuccess && h->d_rs204.alloc(c.keep_taps ? pk_max * 204 + 256 : 16) == cudaSuccess &&
+      h->d_notch_state.alloc(sizeof(NotchState)) == cudaSuccess && h->d_rx_state.alloc(sizeof(RxState)) == cudaSuccess &&
+      h->d_rx_info.alloc(sizeof(RxSpanInfo) * nsp) == cudaSuccess && h->d_rx_end.alloc(sizeof(RxState) * nsp) == cudaSuccess &&
+      h->d_rx_head.alloc(sizeof(RxSeamSym) * kRxSeamLog * (size_t)nsp) == cudaSuccess &&
+      h->d_rx_tail.alloc(sizeof(RxSeamSym) * kRxSeamLog * (size_t)nsp) == cudaSuccess &&
+      h->d_rx_seams.alloc(sizeof(RxSeam) * nsp) == cudaSuccess &&
+      h->d_rx_spans.alloc((size_t)h->rx_span_cap * nsp * 4 + 64) == cudaSuccess &&
+      h->d_rx_off.alloc(8 * ((size_t)nsp + 1)) == cudaSuccess && h->d_rx_skip.alloc(4 * (size_t)nsp) == cudaSuccess &&
+      h->d_rx_rot.alloc(nsp) == cudaSuccess && h->d_rx_meas.alloc(16 * 4096) == cudaSuccess &&
+      h->d_rx_measn.alloc(4) == cudaSuccess && h->d_rx_forced.alloc(sizeof(RxState)) == cudaSuccess &&
+      h->d_deconv_carry.alloc(64) == cudaSuccess && h->d_sync_state.alloc(sizeof(SyncState)) == cudaSuccess &&
+      h->d_sync_res.alloc(sizeof(SyncResult)) == cudaSuccess && h->d_counts.alloc(64) == cudaSuccess;
+  if (!aok) return bail(LDVB_ENOMEM, "device allocation failed");
+  // Notch
+  memset(&h->notch, 0, sizeof h->notch);
+  h->notch.gain = 1;
+  for (int s = 0; s < kNotchMaxSlots; ++s) h->notch.slot[s].bin = -1;
+  if (c.anf) {
+    const uint64_t nblk = M / kNotchN + 2;
+    h->notch_tables_cap = 64;
+    bool nok = h->d_notch_tables.alloc((size_t)h->notch_tables_cap * kNotchN * 8) == cudaSuccess &&
+               h->d_notch_epochs.alloc(sizeof(NotchEpoch) * (nblk / 1024 + 4)) == cudaSuccess &&
+               h->d_notch_entry.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
+               h->d_notch_exit.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
+               h->d_notch_exact.alloc(nblk + 1) == cudaSuccess &&
+               h->d_notch_bins.alloc(4 * kNotchMaxSlots * (nblk / 1024 + 4)) == cudaSuccess &&
+               h->d_notch_blocks.alloc(8 * (nblk / 1024 + 4)) == cudaSuccess;
+    if (!nok) return bail(LDVB_ENOMEM, "notch allocation failed");
+    // Table 0 is all zeros: slots that never detected (bin -1) use it (sdr.h:57-63).
+    cudaMemset(h->d_notch_tables.p, 0, (size_t)kNotchN * 8);
+    h->notch_tables_used = 1;
+  }
+  // Deconvolution / sync / derandomiser carry
+  for (HypState &s : h->hyp) s = HypState();
+  h->locked = 0; h->skip = 0;
+  memset(&h->sync, 0, sizeof h->sync);
+  h->sync.report_state = 1;
+  h->sync.phase8 = -1;
+  h->derand_pos = 0;
+  *out = h;
+  return LDVB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// ------------------------------------------------------------------------- notch
+
+// expj table of one bin, built like auto_notch::detect() (sdr.h:104-108).
+int notch_table_for_bin(ldvb_handle *h, int bin, uint32_t *index) {
+  if (bin < 0) { *index = 0; return LDVB_OK; }
+  auto it = h->notch_table_of_bin.find(bin);
+  if (it != h->notch_table_of_bin.end()) { *index = it->second; return LDVB_OK; }
+  if (h->notch_tables_used >= h->notch_tables_cap) {
+    // Recycle: forget everything except the zero table and the bins in use.
+    h->notch_table_of_bin.clear();
+    h->notch_tables_used = 1;
+    for (int s = 0; s < h->cfg.anf; ++s) {
+      // tables of the live bins are rebuilt on demand below
+    }
+  }
+  std::vector<float> t(2 * kNotchN);
+  for (int i = 0; i < kNotchN; ++i) {
+    float a = (float)(2 * M_PI * bin * i / kNotchN);
+    t[2 * i] = cosf(a);
+    t[2 * i + 1] = sinf(a);
+  }
+  const uint32_t idx = h->notch_tables_used++;
+  CK(cudaMemcpyAsync(h->d_notch_tables.as<uint8_t>() + (size_t)idx * kNotchN * 8, t.data(), t.size() * 4,
+                     cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));  // `t` is a local buffer
+  h->notch_table_of_bin[bin] = idx;
+  *index = idx;
+  return LDVB_OK;
+}
+
+int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consumed) {
+  const ldvb_config &c = h->cfg;
+  const uint64_t nblocks = avail / kNotchN;
+  *consumed = nblocks * kNotchN;
+  h->s_notched.fresh = 0;
+  if (!nblocks) return LDVB_OK;
+  if (h->s_notched.count + nblocks * kNotchN > h->s_notched.cap) return fail(h, LDVB_EOVERFLOW, "notched stream overflow");
+  const int fmt = c.input_format;
+  // Detect points (sdr.h:64-71): phase advances by 4096 before the test.
+  std::vector<uint64_t> dblocks;
+  {
+    int64_t phase = h->notch.phase;
+    for (uint64_t b = 0; b < nblocks; ++b) {
+      phase += kNotchN;
+      if (phase >= 1024 * 4096) { phase -= 1024 * 4096; dblocks.push_back(b); }
+    }
+    h->notch.phase = (int32_t)phase;
+  }
+  std::vector<NotchEpoch> epochs;
+  {
+    NotchEpoch e0;
+    memset(&e0, 0, sizeof e0);
+    e0.first_block = 0;
+    for (int s = 0; s < c.anf; ++s) {
+      e0.bin[s] = h->notch.slot[s].bin;
+      int rc = notch_table_for_bin(h, e0.bin[s], &e0.table_index[s]);
+      if (rc) return rc;
+    }
+    epochs.push_back(e0);
+  }
+  if (!dblocks.empty()) {
+    NotchDetectArgs d;
+    d.src = src; d.fmt = fmt; d.scale = c.float_scale;
+    CK(cudaMemcpyAsync(h->d_notch_blocks.p, dblocks.data(), dblocks.size() * 8, cudaMemcpyHostToDevice, h->st));
+    d.block_index = h->d_notch_blocks.as<uint64_t>();
+    d.ndetect = (int)dblocks.size(); d.nslots = c.anf;
+    d.twiddle_rev = h->d_twiddle.as<float2>();
+    d.bins_out = h->d_notch_bins.as<int32_t>();
+    CK(launch_notch_detect(d, h->st)); ++h->launches;
+    std::vector<int32_t> bins(dblocks.size() * c.anf);
+    CK(cudaMemcpyAsync(bins.data(), h->d_notch_bins.p, bins.size() * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int cur[kNotchMaxSlots];
+    for (int s = 0; s < c.anf; ++s) cur[s] = h->notch.slot[s].bin;
+    for (size_t k = 0; k < dblocks.size(); ++k) {
+      bool changed = false;
+      NotchEpoch e = epochs.back();
+      for (int s = 0; s < kNotchMaxSlots; ++s) e.reset[s] = 0;
+      for (int s = 0; s < c.anf; ++s) {
+        const int nb = bins[k * c.anf + s];
+        if (nb != cur[s]) {  // sdr.h:97-109: new peak -> estimate reset, table rebuilt
+          changed = true;
+          cur[s] = nb;
+          e.bin[s] = nb;
+          e.reset[s] = 1;
+          int rc = notch_table_for_bin(h, nb, &e.table_index[s]);
+          if (rc) return rc;
+        }
+      }
+      if (changed) {
+        e.first_block = dblocks[k];
+        if (e.first_block == 0) epochs[0] = e; else epochs.push_back(e);
+      }
+    }
+    for (int s = 0; s < c.anf; ++s) h->notch.slot[s].bin = cur[s];
+  }
+  CK(cudaMemcpyAsync(h->d_notch_epochs.p, epochs.data(), epochs.size() * sizeof(NotchEpoch), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->d_notch_state.p, &h->notch, sizeof(NotchState), cudaMemcpyHostToDevice, h->st));
+
+  NotchApplyArgs a;
+  a.src = src; a.fmt = fmt; a.scale = c.float_scale;
+  a.out = reinterpret_cast<float2 *>(h->s_notched.at(h->s_notched.count));
+  a.nblocks = nblocks; a.nslots = c.anf;
+  a.k = 0.002f; a.gain = h->notch.gain;
+  a.expj_tables = h->d_notch_tables.as<float2>();
+  a.epochs = h->d_notch_epochs.as<NotchEpoch>();
+  a.nepochs = (int)epochs.size();
+  a.seg_blocks = 8;     // 32 Ki samples owned per segment
+  a.warm_blocks = 6;    // 24 Ki samples of warm-up: 0.998^24576 ~ 4e-22
+  a.nsegs = (uint32_t)((nblocks + a.seg_blocks - 1) / a.seg_blocks);
+  a.state_in = h->d_notch_state.as<NotchState>();
+  a.seg_entry = h->d_notch_entry.as<float2>();
+  a.seg_exit = h->d_notch_exit.as<float2>();
+  a.seg_exact = h->d_notch_exact.as<uint8_t>();
+  CK(launch_notch_apply(a, -1, nullptr, h->st)); ++h->launches;
+  // Verify entry(j+1) == exit(j) bit for bit; re-run (serially, in order) the
+  // segments whose warm-up had not merged with the true trajectory.
+  std::vector<float2> entry((size_t)a.nsegs * kNotchMaxSlots), exitv((size_t)a.nsegs * kNotchMaxSlots);
+  std::vector<uint8_t> exact(a.nsegs);
+  auto fetch = [&]() -> int {
+    CK(cudaMemcpyAsync(entry.data(), a.seg_entry, entry.size() * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(exitv.data(), a.seg_exit, exitv.size() * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(exact.data(), a.seg_exact, exact.size(), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return LDVB_OK;
+  };
+  int rc = fetch();
+  if (rc) return rc;
+  for (uint32_t j = 1; j < a.nsegs; ++j) {
+    if (exact[j]) continue;
+    bool same = true;
+    for (int s = 0; s < c.anf; ++s) {
+      const float2 e = entry[(size_t)j * kNotchMaxSlots + s], x = exitv[(size_t)(j - 1) * kNotchMaxSlots + s];
+      if (memcmp(&e, &x, 8) != 0) same = false;
+    }
+    if (same) continue;
+    // Exact re-run of segment j from the (now final) exit state of segment j-1.
+    CK(launch_notch_apply(a, (int)j, a.seg_exit + (size_t)(j - 1) * kNotchMaxSlots, h->st)); ++h->launches;
+    ++h->meas.notch_repaired;
+    rc = fetch();
+    if (rc) return rc;
+  }
+  for (int s = 0; s < c.anf; ++s) {
+    h->notch.slot[s].est_re = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].x;
+    h->notch.slot[s].est_im = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].y;
+  }
+  h->s_notched.count += nblocks * kNotchN;
+  h->s_notched.fresh = nblocks * kNotchN;
+  return LDVB_OK;
+}
+
+// --------------------------------------------------------------------- front end
+
+int run_frontend(ldvb_handle *h, const RawSrc &src, int fmt, uint64_t avail, uint64_t *consumed) {
+  const ldvb_config &c = h->cfg;
+  const uint32_t N = h->use_fir ? (uint32_t)h->fir_n : 0;
+  const uint32_t D = (uint32_t)h->decim;
+  uint64_t count;
+  if (N) count = (avail >= N) ? (avail - N) / D : 0;  // dsp.h:246-247
+  else count = avail / D;                              // generic.h:254
+  *consumed = count * D;
+  h->s_pp.fresh = 0;
+  if (!count) return LDVB_OK;
+  if (h->s_pp.count + count > h->s_pp.cap) return fail(h, LDVB_EOVERFLOW, "preprocessed stream overflow");
+  if (h->use_fir) {
+    // fir_filter retune from the demodulator's freq_tap (dsp.h:236-244), sampled
+    // once per batch (the reference samples it once per run() call).
+    const float new_freq = h->rx_state.freq_tap * h->fir_tap_mult;
+    if (fabsf(h->fir_current_freq - new_freq) > h->fir_tol) {
+      h->fir_shifted = shift_taps(h->fir_coeffs, new_freq);
+      h->fir_current_freq = new_freq;
+      CK(cudaMemcpyAsync(h->d_taps.p, h->fir_shifted.data(), h->fir_shifted.size() * 4, cudaMemcpyHostToDevice, h->st));
+      CK(cudaStreamSynchronize(h->st));
+    }
+  }
+  FrontendArgs a;
+  memset(&a, 0, sizeof a);
+  a.src = src; a.fmt = fmt; a.scale = c.float_scale;
+  a.rot_lut = h->use_rot ? h->d_rot.as<float>() : nullptr;
+  a.rot_index0 = h->rot_index;
+  a.taps = h->d_taps.as<float2>();
+  a.ntaps = N; a.decim = D;
+  a.out = reinterpret_cast<float2 *>(h->s_pp.at(h->s_pp.count));
+  a.count = count;
+  CK(launch_frontend(a, h->st)); ++h->launches;
+  h->rot_index = (uint32_t)((h->rot_index + *consumed) & 0xffffu);
+  h->s_pp.count += count;
+  h->s_pp.fresh = count;
+  return LDVB_OK;
+}
+
+// ----------------------------------------------------------------------- receiver
+
+int run_receiver(ldvb_handle *h) {
+  const ldvb_config &c = h->cfg;
+  Stream &in = h->s_pp;
+  h->s_sym.fresh = 0;
+  h->meas_log.clear();
+  if (in.count < (uint64_t)kRxChunk + h->readahead) return LDVB_OK;
+  const uint64_t nchunks = (in.count - h->readahead) / kRxChunk;  // sdr.h:783
+  RxArgs a;
+  memset(&a, 0, sizeof a);
+  a.p = h->rxp;
+  a.p.cstln = h->d_cstln.as<CstlnCellDev>();
+  a.p.trig = h->d_trig.as<float2>();
+  a.x = reinterpret_cast<const float2 *>(in.at(0));
+  a.nchunks = nchunks;
+  CK(cudaMemcpyAsync(h->d_rx_state.p, &h->rx_state, sizeof(RxState), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemsetAsync(h->d_rx_measn.p, 0, 4, h->st));
+  a.state_in = h->d_rx_state.as<RxState>();
+  a.info = h->d_rx_info.as<RxSpanInfo>();
+  a.state_end = h->d_rx_end.as<RxState>();
+  a.meas = h->d_rx_meas.as<float>();
+  a.meas_count = h->d_rx_measn.as<uint32_t>();
+  a.max_meas = 4096;
+  uint32_t *sym_dst = reinterpret_cast<uint32_t *>(h->s_sym.at(h->s_sym.count));
+  const uint64_t room = h->s_sym.cap - h->s_sym.count;
+  uint64_t produced = 0;
+  const bool fast = (c.rx_mode == LDVB_RX_FAST) && nchunks >= 4;
+  if (!fast) {
+    a.span_chunks = (uint32_t)std::min<uint64_t>(nchunks, 0xffffffffu);
+    a.warm_chunks = 0;
+    a.nspans = 1;
+    a.span_cap = (uint32_t)std::min<uint64_t>(room, 0xffffffffu);
+    a.sym_out = sym_dst;
+    DevBuf smp, smpf;
+    if (c.keep_taps) {
+      CK(smp.alloc(nchunks * 8)); CK(smpf.alloc(nchunks * 4));
+      a.sampled = smp.as<float2>(); a.sampled_flag = smpf.as<uint32_t>();
+    }
+    CK(launch_rx(a, -1, nullptr, h->st)); ++h->launches;
+    RxSpanInfo inf;
+    CK(cudaMemcpyAsync(&inf, a.info, sizeof inf, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&h->rx_state, a.state_end, sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (inf.n_out > a.span_cap) { smp.release(); smpf.release(); return fail(h, LDVB_EOVERFLOW, "symbol stream overflow"); }
+    produced = inf.n_out;
+    if (c.keep_taps) {
+      // p_sampled holds one entry per chunk that produced a symbol (sdr.h:857-861)
+      std::vector<float2> sv(nchunks); std::vector<uint32_t> fv(nchunks);
+      CK(cudaMemcpy(sv.data(), smp.p, nchunks * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(fv.data(), smpf.p, nchunks * 4, cudaMemcpyDeviceToHost));
+      std::vector<float2> packed;
+      for (uint64_t i = 0; i < nchunks; ++i) if (fv[i]) packed.push_back(sv[i]);
+      Tap &t = h->taps[LDVB_TAP_SAMPLED];
+      if (t.buf.bytes < packed.size() * 8) { t.buf.release(); CK(t.buf.alloc(packed.size() * 8 + 4096)); }
+      CK(cudaMemcpy(t.buf.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice));
+      t.bytes = packed.size() * 8;
+      smp.release(); smpf.release();
+    }
+  } else {
+    const uint32_t S = c.span_chunks ? c.span_chunks : 256;
+    const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 64;
+    a.span_chunks = S;
+    a.warm_chunks = W;
+    a.nspans = (uint32_t)((nchunks + S - 1) / S);
+    if (a.nspans > h->rx_max_spans) return fail(h, LDVB_EOVERFLOW, "too many receiver spans");
+    a.span_cap = h->rx_span_cap;
+    a.sym_out = h->d_rx_spans.as<uint32_t>();
+    a.head_log = h->d_rx_head.as<RxSeamSym>();
+    a.tail_log = h->d_rx_tail.as<RxSeamSym>();
+    CK(launch_rx(a, -1, nullptr, h->st)); ++h->launches;
+    RxStitchArgs sa;
+    sa.info = a.info; sa.head_log = a.head_log; sa.tail_log = a.tail_log;
+    sa.nspans = a.nspans; sa.nrot = h->cst.nrotations; sa.nsymbols = h->cst.nsymbols;
+    sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
+    sa.seams = h->d_rx_seams.as<RxSeam>();
+    CK(launch_rx_stitch(sa, -1, h->st)); ++h->launches;
+    std::vector<RxSeam> seams(a.nspans);
+    std::vector<RxSpanInfo> info(a.nspans);
+    auto fetch = [&]() -> int {
+      if (a.nspans > 1) CK(cudaMemcpyAsync(seams.data(), sa.seams, sizeof(RxSeam) * (a.nspans - 1), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaMemcpyAsync(info.data(), a.info, sizeof(RxSpanInfo) * a.nspans, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      return LDVB_OK;
+    };
+    int rc = fetch();
+    if (rc) return rc;
+    h->meas.seams_total += a.nspans - 1;
+    // Repair failed seams in stream order: span j+1 is re-run exactly from the
+    // end state of span j, then its two seams are stitched again.
+    for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
+      if (seams[j].ok) continue;
+      ++h->meas.seams_repaired;
+      CK(launch_rx(a, (int)(j + 1), a.state_end + j, h->st)); ++h->launches;
+      // An exact continuation needs no alignment: its first symbol follows span j's last.
+      if (j + 2 < a.nspans) { CK(launch_rx_stitch(sa, (int)(j + 1), h->st)); ++h->launches; }
+      rc = fetch();
+      if (rc) return rc;
+      seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0;
+    }
+    // Offsets, skips and cumulative rotations.
+    std::vector<uint64_t> off(a.nspans + 1, 0);
+    std::vector<uint32_t> skipv(a.nspans, 0);
+    std::vector<uint8_t> rot(a.nspans, 0);
+    int cum = 0;
+    for (uint32_t j = 0; j < a.nspans; ++j) {
+      if (info[j].n_out + info[j].n_tail > a.span_cap) return fail(h, LDVB_EOVERFLOW, "span capacity exceeded");
+      uint64_t keep = info[j].n_out;
+      if (j > 0) {
+        skipv[j] = (uint32_t)seams[j - 1].skip_next;
+        cum = (cum + seams[j - 1].rot) % h->cst.nrotations;
+      }
+      rot[j] = (uint8_t)cum;
+      keep -= skipv[j];
+      if (j + 1 < a.nspans) keep += (uint64_t)seams[j].extend_prev;
+      off[j + 1] = off[j] + keep;
+    }
+    produced = off[a.nspans];
+    if (produced > room) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
+    CK(cudaMemcpyAsync(h->d_rx_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->d_rx_skip.p, skipv.data(), skipv.size() * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->d_rx_rot.p, rot.data(), rot.size(), cudaMemcpyHostToDevice, h->st));
+    RxCompactArgs ca;
+    ca.sym_in = a.sym_out; ca.span_cap = a.span_cap; ca.nspans = a.nspans;
+    ca.span_offset = h->d_rx_off.as<uint64_t>(); ca.span_skip = h->d_rx_skip.as<uint32_t>();
+    ca.span_rot = h->d_rx_rot.as<uint8_t>(); ca.rot_perm = h->d_rotperm.as<uint8_t>();
+    ca.nsymbols = h->cst.nsymbols; ca.sym_out = sym_dst;
+    CK(launch_rx_compact(ca, produced, h->st)); ++h->launches;
+    // Carry: the end state of the last span.  Its phase is rotated back by the
+    // cumulative rotation so that the next batch continues in span 0's frame.
+    CK(cudaMemcpyAsync(&h->rx_state, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (cum) {
+      // Span frames differ by cum*65536/nrot phase units: symbols of the last span
+      // were de-rotated by `cum`; adding the same angle to the PLL phase makes the
+      // next batch's span 0 produce symbols in the reference frame directly.
+      float shift = (float)cum * (65536.0f / h->cst.nrotations);
+      h->rx_state.phase = fmodf(h->rx_state.phase - shift, 65536.0f);
+    }
+  }
+  // Measurements recorded by the kernel: {chunk, freq_tap, ss, mer}
+  {
+    uint32_t nm = 0;
+    CK(cudaMemcpy(&nm, h->d_rx_measn.p, 4, cudaMemcpyDeviceToHost));
+    nm = std::min(nm, 4096u);
+    if (nm) {
+      std::vector<float> m(4 * nm);
+      CK(cudaMemcpy(m.data(), h->d_rx_meas.p, m.size() * 4, cudaMemcpyDeviceToHost));
+      std::vector<std::pair<float, int>> order;
+      for (uint32_t i = 0; i < nm; ++i) order.push_back({m[4 * i], (int)i});
+      std::sort(order.begin(), order.end());
+      for (auto &o : order) {
+        h->meas_log.push_back(m[4 * o.second + 1]);
+        h->meas_log.push_back(m[4 * o.second + 2]);
+        h->meas_log.push_back(m[4 * o.second + 3]);
+      }
+    }
+  }
+  h->s_sym.count += produced;
+  h->s_sym.fresh = produced;
+  h->meas.symbols += produced;
+  int rc = stream_consume(h, in, nchunks * kRxChunk, h->d_scratch);
+  if (rc) return rc;
+  h->meas.freq_tap = h->rx_state.freq_tap;
+  h->meas.ss = sqrtf(h->rx_state.est_insp);
+  h->meas.mer = h->rx_state.est_ep ? 10 * logf(h->rx_state.est_sp / h->rx_state.est_ep) / logf(10) : 0;
+  return LDVB_OK;
+}
+
+// --------------------------------------------------------- deconvolution + sync
+
+// One run of the deconvolver of the locked hypothesis over the unread symbols.
+// Bytes are written behind the current end of s_bytes but nothing is committed:
+// the caller appends them, lets the sync tracker look at them and only then
+// commits the shift-register state and drops the symbols (deconv_commit).
+struct DeconvRun { uint64_t produced = 0, consumed = 0; HypState after; };
+
+int deconv_launch(ldvb_handle *h, uint64_t limit_bytes, DeconvRun *run) {
+  Stream &in = h->s_sym;
+  *run = DeconvRun();
+  run->after = h->hyp[h->locked];
+  if (in.count < 64) return LDVB_OK;  // dvb.h:419
+  const int pp = h->dec.punctperiod, pw = h->dec.punctweight;
+  uint64_t n = (in.count - 64) / (pw / 2) * pp / 8;  // dvb.h:420
+  n = std::min(n, limit_bytes);
+  n = std::min<uint64_t>(n, h->s_bytes.cap - h->s_bytes.count);
+  if (!n) return LDVB_OK;
+  const HypState &hs = h->hyp[h->locked];
+  DeconvArgs a;
+  memset(&a, 0, sizeof a);
+  a.symbols = reinterpret_cast<const uint32_t *>(in.at(0));
+  a.nbytes = n;
+  a.reg_in = hs.reg; a.n_in = hs.n_in; a.out_acc = hs.acc; a.n_out = hs.n_out;
+  for (int s = 0; s < 4; ++s) a.hyp[s] = h->dec.hyp_lut[h->locked][s];
+  a.punctperiod = pp; a.punctweight = pw;
+  for (int b = 0; b < 8; ++b) a.deconv[b] = h->dec.deconv[b];
+  a.out = h->s_bytes.at(h->s_bytes.count);
+  CK(launch_deconv_carry(a, h->d_deconv_carry.as<uint64_t>(), h->st)); ++h->launches;
+  uint64_t carry[5];
+  CK(cudaMemcpyAsync(carry, h->d_deconv_carry.p, sizeof carry, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  run->after.reg = carry[0]; run->after.n_in = (int)(int64_t)carry[1];
+  run->after.acc = carry[2]; run->after.n_out = (int)(int64_t)carry[3];
+  run->consumed = carry[4];
+  run->produced = n;
+  if (run->consumed > in.count) return fail(h, LDVB_ESTATE, "deconvolver over-consumed");
+  return LDVB_OK;
+}
+
+int deconv_commit(ldvb_handle *h, const DeconvRun &run) {
+  h->hyp[h->locked] = run.after;
+  return stream_consume(h, h->s_sym, run.consumed, h->d_scratch);
+}
+
+int run_sync(ldvb_handle *h) {
+  Stream &in = h->s_bytes;
+  Stream &out = h->s_mpeg;
+  out.fresh = 0;
+  for (int guard = 0; guard < 1000000; ++guard) {
+    uint64_t npk = 0;
+    CK(cudaMemcpyAsync(h->d_sync_state.p, &h->sync, sizeof(SyncState), cudaMemcpyHostToDevice, h->st));
+    if (h->sync.synchronized) {
+      npk = (in.count >= 205) ? (in.count - 1) / 204 : 0;  // dvb.h:843
+      npk = std::min<uint64_t>(npk, (out.cap - out.count) / 204);
+      if (!npk) break;
+      CK(launch_sync_flags(in.at(0), npk, h->d_sync_state.as<SyncState>(), h->d_badwords.as<uint32_t>(), h->st));
+      ++h->launches;
+    } else if (in.count < 204 * 8 + 1) {
+      break;  // dvb.h:758
+    }
+    CK(launch_sync_track(in.at(0), in.count, h->d_sync_state.as<SyncState>(), h->d_badwords.as<uint32_t>(), npk,
+                         h->d_sync_res.as<SyncResult>(), h->st));
+    ++h->launches;
+    SyncResult r;
+    CK(cudaMemcpyAsync(&r, h->d_sync_res.p, sizeof r, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (r.produced) {
+      CK(launch_realign(in.at(0), r.produced, h->sync.bitphase, h->sync.polarity, out.at(out.count), h->st));
+      ++h->launches;
+      out.count += r.produced;
+      out.fresh += r.produced;
+    }
+    h->sync = r.st;
+    for (int e = 0; e < r.events && e < 16; ++e) h->meas.lock = r.event_val[e];
+    int rc = stream_consume(h, in, r.consumed, h->d_scratch);
+    if (rc) return rc;
+    if (r.need_next_sync) {
+      // mpeg_sync asks the deconvolver for its next hypothesis (dvb.h:771-778,
+      // 185-193).  Bytes that the old hypothesis produced beyond the search
+      // position are discarded: their symbols are still unread (see run_chain).
+      return 1;
+    }
+    if (!r.consumed && !r.produced) break;
+  }
+  h->meas.locktime = h->sync.locktime;
+  return LDVB_OK;
+}
+
+int run_fec(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_out) {
+  Stream &in = h->s_mpeg;
+  *ts_out = 0;
+  uint64_t npk = (in.count >= 2448) ? (in.count - 2244) / 204 : 0;  // dvb.h:933
+  npk = std::min(npk, h->ts_cap);
+  if (!npk) return LDVB_OK;
+  DeintRsArgs a;
+  a.mpeg = in.at(0); a.npackets = npk;
+  a.gf_exp = h->d_gfexp.as<uint8_t>(); a.gf_log = h->d_gflog.as<uint8_t>();
+  a.rs_out = h->cfg.keep_taps ? h->d_rs204.as<uint8_t>() : nullptr;
+  a.rts_out = h->d_rts.as<uint8_t>();
+  a.flags = h->d_rsflags.as<int32_t>();
+  CK(launch_deint_rs(a, h->st)); ++h->launches;
+  DerandArgs d;
+  d.rts = a.rts_out; d.npackets = npk; d.pattern = h->d_derand.as<uint8_t>();
+  d.pos_in = h->derand_pos; d.ts_out = ts_dst; d.ts_cap = ts_cap;
+  d.counts = h->d_counts.as<uint64_t>(); d.flags = a.flags; d.scratch = h->d_scratch.as<uint32_t>();
+  int nl = 0;
+  CK(launch_derand(d, h->st, &nl)); h->launches += nl;
+  uint64_t counts[4];
+  CK(cudaMemcpyAsync(counts, h->d_counts.p, sizeof counts, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (counts[0] > ts_cap) return fail(h, LDVB_EOVERFLOW, "TS output buffer too small");
+  *ts_out = counts[0];
+  h->derand_pos = (int)counts[2];
+  h->meas.rs_bits += npk * 204 * 8;
+  h->meas.rs_errs += counts[3];
+  h->meas.ts_packets += counts[0];
+  h->meas.ts_dropped += counts[1];
+  int rc;
+  if ((rc = tap_store(h, LDVB_TAP_RSPACKETS, h->d_rs204.p, npk * 204))) return rc;
+  if ((rc = tap_store(h, LDVB_TAP_RTSPACKETS, h->d_rts.p, npk * 188))) return rc;
+  if ((rc = tap_store(h, LDVB_TAP_RSFLAGS, h->d_rsflags.p, npk * 8))) return rc;
+  return stream_consume(h, in, npk * 204, h->d_scratch);
+}
+
+// ------------------------------------------------------------------ whole chain
+
+int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_t n, uint8_t *ts_dst,
+              uint64_t ts_cap, uint64_t *ts_out) {
+  const ldvb_config &c = h->cfg;
+  *ts_out = 0;
+  if (n > c.max_batch) return fail(h, LDVB_EOVERFLOW, "n_samples exceeds max_batch");
+  if (cudaSetDevice(c.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  int rc;
+  // ---- raw stream view
+  Stream &raw = h->s_raw;
+  const uint64_t c0 = raw.count;
+  RawSrc src;
+  src.head = raw.at(0); src.main = nullptr; src.c0 = c0;
+  const uint64_t head_new = src_is_user_dev ? std::min<uint64_t>(n, 65536) : n;
+  if (src_is_user_dev && (reinterpret_cast<uintptr_t>(src_dev) & 15)) return fail(h, LDVB_EINVAL, "iq_dev must be 16-byte aligned");
+  if (n) {
+    // (host data was already copied behind the carry by ldvb_push)
+    if (src_is_user_dev) {
+      CK(cudaMemcpyAsync(raw.at(c0), src_dev, head_new * raw.elem, cudaMemcpyDeviceToDevice, h->st));
+      src.main = src_dev;
+    }
+  }
+  src.head_count = c0 + head_new;
+  const uint64_t avail = c0 + n;
+  h->meas.samples_in += n;
+  for (Tap &t : h->taps) t.bytes = 0;
+  h->s_bytes.fresh = 0;
+
+  // ---- notch / front end
+  uint64_t raw_consumed = 0;
+  if (c.anf) {
+    if ((rc = run_notch(h, src, avail, &raw_consumed))) return rc;
+    RawSrc nsrc;
+    nsrc.head = h->s_notched.at(0); nsrc.head_count = h->s_notched.count; nsrc.main = nullptr; nsrc.c0 = 0;
+    uint64_t ncons = 0;
+    if (h->use_fir || h->use_decim || h->use_rot) {
+      if ((rc = run_frontend(h, nsrc, 5, h->s_notched.count, &ncons))) return rc;
+      if ((rc = stream_consume(h, h->s_notched, ncons, h->d_scratch))) return rc;
+    } else {
+      // The notch output IS the preprocessed stream: move it over.
+      const uint64_t k = h->s_notched.count;
+      if (h->s_pp.count + k > h->s_pp.cap) return fail(h, LDVB_EOVERFLOW, "preprocessed stream overflow");
+      if (k) CK(cudaMemcpyAsync(h->s_pp.at(h->s_pp.count), h->s_notched.at(0), k * 8, cudaMemcpyDeviceToDevice, h->st));
+      h->s_pp.count += k; h->s_pp.fresh = k;
+      h->s_notched.count = 0;
+    }
+  } else {
+    if ((rc = run_frontend(h, src, c.input_format, avail, &raw_consumed))) return rc;
+  }
+  // Carry the unread raw samples.
+  {
+    const uint64_t left = avail - raw_consumed;
+    if (left > raw.cap) return fail(h, LDVB_EOVERFLOW, "raw carry overflow");
+    if (src_is_user_dev) {
+      // Unread samples are either in the head buffer or in the user's buffer.
+      if (raw_consumed < c0) {
+        // part of the old carry remains (tiny batch): keep head content, append the batch
+        if (n > head_new) return fail(h, LDVB_ESTATE, "batch too small to drain the carry");
+        raw.count = c0 + n;
+        if ((rc = stream_consume(h, raw, raw_consumed, h->d_scratch))) return rc;
+      } else if (left) {
+        const uint64_t from = raw_consumed - c0;  // index into the user's buffer
+        CK(cudaMemcpyAsync(raw.at(0), static_cast<const uint8_t *>(src_dev) + from * raw.elem, left * raw.elem,
+                           cudaMemcpyDeviceToDevice, h->st));
+        raw.count = left;
+      } else raw.count = 0;
+    } else {
+      raw.count = avail;
+      if ((rc = stream_consume(h, raw, raw_consumed, h->d_scratch))) return rc;
+    }
+  }
+  if ((rc = tap_store(h, LDVB_TAP_PREPROCESSED, h->s_pp.at(h->s_pp.count - h->s_pp.fresh), h->s_pp.fresh * 8))) return rc;
+
+  // ---- receiver
+  if ((rc = run_receiver(h))) return rc;
+  if ((rc = tap_store(h, LDVB_TAP_SYMBOLS, h->s_sym.at(h->s_sym.count - h->s_sym.fresh), h->s_sym.fresh * 4))) return rc;
+  if (h->cfg.keep_taps && !h->meas_log.empty()) {
+    Tap &t = h->taps[LDVB_TAP_MEAS];
+    if (t.buf.bytes < h->meas_log.size() * 4) { t.buf.release(); CK(t.buf.alloc(h->meas_log.size() * 4 + 4096)); }
+    CK(cudaMemcpy(t.buf.p, h->meas_log.data(), h->meas_log.size() * 4, cudaMemcpyHostToDevice));
+    t.bytes = h->meas_log.size() * 4;
+  }
+
+  // ---- deconvolution <-> sync (with the backward next_sync edge, dvb.h:771-778)
+  std::vector<uint8_t> tap_bytes;  // bytes that stay in the stream, for the tap
+  for (int guard = 0; guard < 64; ++guard) {
+    if (h->skip) {  // dvb.h:415-416
+      if (h->s_sym.count < (uint64_t)h->skip) break;
+      if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
+      h->skip = 0;
+    }
+    DeconvRun run;
+    if ((rc = deconv_launch(h, ~0ull, &run))) return rc;
+    const size_t tap_at = tap_bytes.size();
+    if (c.keep_taps && run.produced) {
+      tap_bytes.resize(tap_at + run.produced);
+      CK(cudaMemcpy(tap_bytes.data() + tap_at, h->s_bytes.at(h->s_bytes.count), run.produced, cudaMemcpyDeviceToHost));
+    }
+    h->s_bytes.count += run.produced;
+    h->s_bytes.fresh += run.produced;
+    rc = run_sync(h);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if ((rc = deconv_commit(h, run))) return rc;
+      break;
+    }
+    // Third fruitless sweep: mpeg_sync calls deconv->next_sync().  Bytes of this
+    // run that the search has not consumed are void (their symbols are re-read by
+    // the next hypothesis); the register state is re-derived at that exact byte.
+    const uint64_t left = h->s_bytes.count;
+    const uint64_t voided = std::min(left, run.produced);
+    const uint64_t used = run.produced - voided;
+    h->s_bytes.count = left - voided;
+    h->s_bytes.fresh -= voided;
+    if (c.keep_taps) tap_bytes.resize(tap_at + used);
+    DeconvRun kept;
+    kept.after = h->hyp[h->locked];
+    if (used && (rc = deconv_launch(h, used, &kept))) return rc;
+    if ((rc = deconv_commit(h, kept))) return rc;
+    if (++h->locked == 4) { h->locked = 0; h->skip = 1; }  // dvb.h:185-193
+  }
+  if (c.keep_taps) {
+    Tap &t = h->taps[LDVB_TAP_BYTES];
+    if (t.buf.bytes < tap_bytes.size()) { t.buf.release(); CK(t.buf.alloc(tap_bytes.size() + 4096)); }
+    if (!tap_bytes.empty()) CK(cudaMemcpy(t.buf.p, tap_bytes.data(), tap_bytes.size(), cudaMemcpyHostToDevice));
+    t.bytes = tap_bytes.size();
+  }
+  if ((rc = tap_store(h, LDVB_TAP_MPEGBYTES, h->s_mpeg.at(h->s_mpeg.count - h->s_mpeg.fresh), h->s_mpeg.fresh))) return rc;
+  // ---- de-interleave + RS + derandomise
+  if ((rc = run_fec(h, ts_dst, ts_cap, ts_out))) return rc;
+  h->meas.kernel_launches = h->launches;
+  return LDVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n) {
+  if (!h || (!iq_host && n)) return LDVB_EINVAL;
+  if (n > h->cfg.max_batch) return fail(h, LDVB_EOVERFLOW, "n_samples exceeds max_batch");
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  Stream &raw = h->s_raw;
+  if (raw.count + n > raw.cap) return fail(h, LDVB_EOVERFLOW, "raw stream overflow");
+  if (n) CK(cudaMemcpyAsync(raw.at(raw.count), iq_host, n * raw.elem, cudaMemcpyHostToDevice, h->st));
+  uint64_t got = 0;
+  int rc = run_chain(h, nullptr, false, n, h->d_ts.as<uint8_t>(), h->ts_cap, &got);
+  if (rc) return rc;
+  if (got) {
+    const size_t o = h->ts_queue.size();
+    h->ts_queue.resize(o + got * 188);
+    CK(cudaMemcpyAsync(h->ts_queue.data() + o, h->d_ts.p, got * 188, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  return LDVB_OK;
+}
+
+int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets, size_t *n_packets) {
+  if (!h || !n_packets) return LDVB_EINVAL;
+  const size_t avail = (h->ts_queue.size() - h->ts_queue_rd) / 188;
+  const size_t n = std::min(avail, cap_packets);
+  if (n && ts_host) memcpy(ts_host, h->ts_queue.data() + h->ts_queue_rd, n * 188);
+  h->ts_queue_rd += n * 188;
+  if (h->ts_queue_rd == h->ts_queue.size()) { h->ts_queue.clear(); h->ts_queue_rd = 0; }
+  *n_packets = n;
+  return LDVB_OK;
+}
+
+int ldvb_process_device(ldvb_handle *h, const void *iq_dev, size_t n, uint8_t *ts_dev, size_t cap_packets,
+                        size_t *n_packets) {
+  if (!h || !n_packets || (!iq_dev && n) || !ts_dev) return LDVB_EINVAL;
+  uint64_t got = 0;
+  int rc = run_chain(h, iq_dev, true, n, ts_dev, cap_packets, &got);
+  *n_packets = (size_t)got;
+  return rc;
+}
+
+int ldvb_get_meas(ldvb_handle *h, ldvb_meas *m) {
+  if (!h || !m) return LDVB_EINVAL;
+  h->meas.kernel_launches = h->launches;
+  *m = h->meas;
+  return LDVB_OK;
+}
+
+int ldvb_tap(ldvb_handle *h, int which, void *dst, size_t cap, size_t *n_bytes) {
+  if (!h || which < 0 || which > 8 || !n_bytes) return LDVB_EINVAL;
+  if (!h->cfg.keep_taps) return fail(h, LDVB_ESTATE, "handle created without keep_taps");
+  Tap &t = h->taps[which];
+  *n_bytes = (size_t)t.bytes;
+  if (!dst) return LDVB_OK;
+  if (cap < t.bytes) return LDVB_EOVERFLOW;
+  if (t.bytes) {
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaMemcpy(dst, t.buf.p, t.bytes, cudaMemcpyDeviceToHost));
+  }
+  return LDVB_OK;
+}
+
+int ldvb_table(ldvb_handle *h, int which, void *dst, size_t cap, size_t *n_bytes) {
+  if (!h || !n_bytes) return LDVB_EINVAL;
+  std::vector<uint8_t> blob;
+  auto put = [&](const void *p, size_t n) { blob.assign((const uint8_t *)p, (const uint8_t *)p + n); };
+  switch (which) {
+    case LDVB_TABLE_CSTLN: put(h->cst.cells.data(), h->cst.cells.size() * sizeof(CstlnCell)); break;
+    case LDVB_TABLE_TRIG16: { auto t = make_trig16(); put(t.data(), t.size() * 4); break; }
+    case LDVB_TABLE_RS_EXP: { uint8_t e[512], l[256]; make_rs_tables(e, l); put(e, 512); break; }
+    case LDVB_TABLE_RS_LOG: { uint8_t e[512], l[256]; make_rs_tables(e, l); put(l, 256); break; }
+    case LDVB_TABLE_DERAND: { auto t = make_derand_pattern(); put(t.data(), t.size()); break; }
+    case LDVB_TABLE_FIR: put(h->fir_coeffs.data(), h->fir_coeffs.size() * 4); break;
+    case LDVB_TABLE_DECONV: put(h->dec.deconv, 8 * (size_t)h->dec.punctperiod); break;
+    case LDVB_TABLE_RRC: {
+      int steps = 0;
+      auto t = design_rrc(h->Fs_rx, h->cfg.Fm, h->cfg.rolloff, h->cfg.rrc_rej, h->cfg.rrc_steps, &steps);
+      put(t.data(), t.size() * 4);
+      break;
+    }
+    case LDVB_TABLE_TRELLIS: {
+      Trellis t;
+      if (!make_trellis(h->cfg.fec, &t)) return LDVB_EINVAL;
+      for (size_t i = 0; i < t.pred.size(); ++i) { blob.push_back(t.pred[i]); blob.push_back(t.us[i]); }
+      break;
+    }
+    case LDVB_TABLE_VITMAP: {
+      Trellis t;
+      if (!make_trellis(h->cfg.fec, &t)) return LDVB_EINVAL;
+      VitSyncs v = make_vitsyncs(h->cst, t);
+      blob.push_back((uint8_t)v.nsyncs); blob.push_back((uint8_t)v.nshifts);
+      blob.push_back((uint8_t)v.bps); blob.push_back((uint8_t)h->cst.nsymbols);
+      for (int s = 0; s < v.nsyncs; ++s) {
+        blob.push_back((uint8_t)v.shift[s]);
+        blob.insert(blob.end(), v.map[s].begin(), v.map[s].end());
+      }
+      break;
+    }
+    default: return LDVB_EINVAL;
+  }
+  *n_bytes = blob.size();
+  if (!dst) return LDVB_OK;
+  if (cap < blob.size()) return LDVB_EOVERFLOW;
+  memcpy(dst, blob.data(), blob.size());
+  return LDVB_OK;
+}
+
+int ldvb_get_rx_state(ldvb_handle *h, uint32_t w[22]) {
+  if (!h || !w) return LDVB_EINVAL;
+  memcpy(w, &h->rx_state, 22 * 4);
+  return LDVB_OK;
+}
+
+int ldvb_set_rx_state(ldvb_handle *h, const uint32_t w[22]) {
+  if (!h || !w) return LDVB_EINVAL;
+  memcpy(&h->rx_state, w, 22 * 4);
+  return LDVB_OK;
+}
+
+namespace {
+struct StateBlob {
+  uint32_t magic;
+  NotchState notch;
+  uint32_t rot_index;
+  RxState rx;
+  HypState hyp[4];
+  int32_t locked, skip;
+  SyncState sync;
+  int32_t derand_pos;
+  float fir_current_freq;
+};
+}  // namespace
+
+size_t ldvb_state_size(const ldvb_handle *) { return sizeof(StateBlob); }
+
+int ldvb_get_state(ldvb_handle *h, void *blob, size_t cap) {
+  if (!h || !blob || cap < sizeof(StateBlob)) return LDVB_EINVAL;
+  StateBlob b = StateBlob();
+  b.magic = 0x4c445642;
+  b.notch = h->notch; b.rot_index = h->rot_index; b.rx = h->rx_state;
+  for (int i = 0; i < 4; ++i) b.hyp[i] = h->hyp[i];
+  b.locked = h->locked; b.skip = h->skip; b.sync = h->sync; b.derand_pos = h->derand_pos;
+  b.fir_current_freq = h->fir_current_freq;
+  memcpy(blob, &b, sizeof b);
+  return LDVB_OK;
+}
+
+int ldvb_set_state(ldvb_handle *h, const void *blob, size_t size) {
+  if (!h || !blob || size != sizeof(StateBlob)) return LDVB_EINVAL;
+  StateBlob b;
+  memcpy(&b, blob, sizeof b);
+  if (b.magic != 0x4c445642) return LDVB_EINVAL;
+  h->notch = b.notch; h->rot_index = b.rot_index; h->rx_state = b.rx;
+  for (int i = 0; i < 4; ++i) h->hyp[i] = b.hyp[i];
+  h->locked = b.locked; h->skip = b.skip; h->sync = b.sync; h->derand_pos = b.derand_pos;
+  return LDVB_OK;
+}
+
+// ------------------------------------------------------------ stand-alone stages
+
+int ldvb_fir_cf32(int device, const float *x, size_t n_in, const float *taps, uint32_t ntaps, uint32_t decim,
+                  float *y, size_t cap_out, size_t *n_out) {
+  if (!x || !taps || !y || !n_out || !ntaps || !decim) return LDVB_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return LDVB_ENODEV;
+  *n_out = 0;
+  if (n_in < ntaps) return LDVB_OK;
+  const size_t count = (n_in - ntaps) / decim;
+  if (count > cap_out) return LDVB_EOVERFLOW;
+  if (!count) return LDVB_OK;
+  DevBuf dx, dt, dy;
+  int rc = LDVB_OK;
+  if (dx.alloc(n_in * 8 + 512) != cudaSuccess || dt.alloc((size_t)ntaps * 8) != cudaSuccess ||
+      dy.alloc(count * 8) != cudaSuccess) rc = LDVB_ENOMEM;
+  if (!rc) {
+    cudaMemset(dx.p, 0, dx.bytes);
+    cudaMemcpy(dx.p, x, n_in * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dt.p, taps, (size_t)ntaps * 8, cudaMemcpyHostToDevice);
+    FrontendArgs a;
+    memset(&a, 0, sizeof a);
+    a.src.head = dx.p; a.src.head_count = n_in; a.src.main = nullptr; a.src.c0 = 0;
+    a.fmt = 5; a.scale = 1; a.taps = dt.as<float2>(); a.ntaps = ntaps; a.decim = decim;
+    a.out = dy.as<float2>(); a.count = count;
+    if (launch_frontend(a, 0) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) rc = LDVB_ECUDA;
+    else { cudaMemcpy(y, dy.p, count * 8, cudaMemcpyDeviceToHost); *n_out = count; }
+  }
+  dx.release(); dt.release(); dy.release();
+  return rc;
+}
+
+static int rs_common(int device, const uint8_t *src, size_t src_bytes, size_t npk, bool deint, uint8_t *rts,
+                     int32_t *flags) {
+  if (cudaSetDevice(device) != cudaSuccess) return LDVB_ENODEV;
+  if (!npk) return LDVB_OK;
+  uint8_t gexp[512], glog[256];
+  make_rs_tables(gexp, glog);
+  DevBuf ds, de, dl, dr, df;
+  int rc = LDVB_OK;
+  if (ds.alloc(src_bytes + 256) != cudaSuccess || de.alloc(512) != cudaSuccess || dl.alloc(256) != cudaSuccess ||
+      dr.alloc(npk * 188) != cudaSuccess || df.alloc(npk * 8) != cudaSuccess) rc = LDVB_ENOMEM;
+  if (!rc) {
+    cudaMemcpy(ds.p, src, src_bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(de.p, gexp, 512, cudaMemcpyHostToDevice);
+    cudaMemcpy(dl.p, glog, 256, cudaMemcpyHostToDevice);
+    cudaError_t e;
+    if (deint) {
+      DeintRsArgs a;
+      a.mpeg = ds.as<uint8_t>(); a.npackets = npk; a.gf_exp = de.as<uint8_t>(); a.gf_log = dl.as<uint8_t>();
+      a.rs_out = nullptr; a.rts_out = dr.as<uint8_t>(); a.flags = df.as<int32_t>();
+      e = launch_deint_rs(a, 0);
+    } else {
+      RsOnlyArgs a;
+      a.rs_in = ds.as<uint8_t>(); a.npackets = npk; a.gf_exp = de.as<uint8_t>(); a.gf_log = dl.as<uint8_t>();
+      a.rts_out = dr.as<uint8_t>(); a.flags = df.as<int32_t>();
+      e = launch_rs_only(a, 0);
+    }
+    if (e != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) rc = LDVB_ECUDA;
+    else {
+      cudaMemcpy(rts, dr.p, npk * 188, cudaMemcpyDeviceToHost);
+      if (flags) cudaMemcpy(flags, df.p, npk * 8, cudaMemcpyDeviceToHost);
+    }
+  }
+  ds.release(); de.release(); dl.release(); dr.release(); df.release();
+  return rc;
+}
+
+int ldvb_deint_rs(int device, const uint8_t *mpeg, size_t n_bytes, uint8_t *rts, size_t cap_packets, size_t *n_packets,
+                  int32_t *flags) {
+  if (!mpeg || !rts || !n_packets) return LDVB_EINVAL;
+  size_t npk = (n_bytes >= 2448) ? (n_bytes - 2244) / 204 : 0;
+  if (npk > cap_packets) return LDVB_EOVERFLOW;
+  *n_packets = npk;
+  return rs_common(device, mpeg, n_bytes, npk, true, rts, flags);
+}
+
+int ldvb_rs_decode(int device, const uint8_t *rs204, size_t npk, uint8_t *ts188, int32_t *flags) {
+  if (!rs204 || !ts188) return LDVB_EINVAL;
+  return rs_common(device, rs204, npk * 204, npk, false, ts188, flags);
+}
+
+}  // extern "C"
