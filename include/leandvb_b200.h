@@ -190,6 +190,25 @@ int ldvb_process_device(ldvb_handle *h, const void *iq_dev, size_t n_samples,
 			uint8_t *ts_dev, size_t cap_packets,
 			size_t *n_packets);
 
+/* Back to the state of a freshly created handle (streams empty, loops at
+ * their initial values: what restarting leandvb does), keeping tables and
+ * device buffers. */
+int ldvb_reset(ldvb_handle *h);
+
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) for every
+ * kernel and copy of this handle, so that the caller's events bracket them. */
+int ldvb_set_stream(ldvb_handle *h, void *cuda_stream);
+
+/* Per-kernel device time, measured with CUDA events on the handle's stream
+ * around every launch while enabled (bench.py's roofline numbers). */
+typedef struct ldvb_kernel_stat {
+  char     name[32];
+  uint32_t launches;
+  float    ms_total;
+} ldvb_kernel_stat;
+int ldvb_profile(ldvb_handle *h, int enable);     /* enabling clears the counters */
+int ldvb_get_profile(ldvb_handle *h, ldvb_kernel_stat *stats, int cap, int *n);
+
 /* ----------------------------------------------------------- introspection */
 int ldvb_get_meas(ldvb_handle *h, ldvb_meas *m);
 /* Copies the tap stream produced by the LAST push/process into host memory;
@@ -198,6 +217,10 @@ int ldvb_tap(ldvb_handle *h, int which, void *dst_host, size_t cap_bytes,
 	     size_t *n_bytes);
 int ldvb_table(ldvb_handle *h, int which, void *dst_host, size_t cap_bytes,
 	       size_t *n_bytes);
+/* Same tables from a configuration alone: pure host code, needs no device
+ * (used by the CPU-only tests to pin the table builders to the reference). */
+int ldvb_host_table(const ldvb_config *cfg, int which, void *dst_host,
+		    size_t cap_bytes, size_t *n_bytes);
 
 /* Carry state of the serial stages: what rank r hands
  * to rank r+1 in a time-sharded run, and what tests use to compare with the

@@ -5,8 +5,8 @@ kernels + the C ABI declared in include/leandvb_b200.h).  There is no CPU
 fallback: importing works anywhere, but creating a Receiver needs the built
 library and a B200.
 """
-from .capi import (Config, LdvbError, Meas, Receiver, default_config, deint_rs, fir_cf32,  # noqa: F401
+from .capi import (Config, LdvbError, Meas, Receiver, default_config, deint_rs, fir_cf32, host_table,  # noqa: F401
                    load, rs_decode, EXPORTS, LIB_PATH, RX_EXACT, RX_FAST)
 
-__all__ = ["Config", "LdvbError", "Meas", "Receiver", "default_config", "deint_rs", "fir_cf32",
+__all__ = ["Config", "LdvbError", "Meas", "Receiver", "default_config", "deint_rs", "fir_cf32", "host_table",
            "load", "rs_decode", "EXPORTS", "LIB_PATH", "RX_EXACT", "RX_FAST"]

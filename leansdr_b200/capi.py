@@ -65,9 +65,14 @@ class Meas(C.Structure):
 EXPORTS = [
     "ldvb_abi_version", "ldvb_strerror", "ldvb_last_error", "ldvb_config_default", "ldvb_create",
     "ldvb_destroy", "ldvb_push", "ldvb_pull", "ldvb_process_device", "ldvb_get_meas", "ldvb_tap",
-    "ldvb_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
+    "ldvb_table", "ldvb_host_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
     "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
+    "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
 ]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint32), ("ms_total", C.c_float)]
 
 _lib = None
 
@@ -97,6 +102,7 @@ def load():
     L.ldvb_get_meas.argtypes = [vp, C.POINTER(Meas)]
     L.ldvb_tap.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
     L.ldvb_table.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    L.ldvb_host_table.argtypes = [C.POINTER(Config), C.c_int, vp, sz, C.POINTER(sz)]
     L.ldvb_state_size.restype = sz
     L.ldvb_state_size.argtypes = [vp]
     L.ldvb_get_state.argtypes = [vp, vp, sz]
@@ -106,6 +112,10 @@ def load():
     L.ldvb_fir_cf32.argtypes = [C.c_int, vp, sz, vp, C.c_uint32, C.c_uint32, vp, sz, C.POINTER(sz)]
     L.ldvb_deint_rs.argtypes = [C.c_int, vp, sz, vp, sz, C.POINTER(sz), vp]
     L.ldvb_rs_decode.argtypes = [C.c_int, vp, sz, vp, vp]
+    L.ldvb_reset.argtypes = [vp]
+    L.ldvb_set_stream.argtypes = [vp, vp]
+    L.ldvb_profile.argtypes = [vp, C.c_int]
+    L.ldvb_get_profile.argtypes = [vp, C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -131,6 +141,20 @@ def default_config(**kw) -> Config:
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def host_table(cfg: Config, name: str) -> np.ndarray:
+    """Constant table built by the library's host code; needs no GPU."""
+    L = load()
+    n = C.c_size_t(0)
+    rc = L.ldvb_host_table(C.byref(cfg), TABLE[name], None, 0, C.byref(n))
+    if rc:
+        raise LdvbError(rc, "ldvb_host_table", L.ldvb_strerror(rc).decode())
+    out = np.empty(n.value, np.uint8)
+    rc = L.ldvb_host_table(C.byref(cfg), TABLE[name], _p(out), out.size, C.byref(n))
+    if rc:
+        raise LdvbError(rc, "ldvb_host_table", L.ldvb_strerror(rc).decode())
+    return out
 
 
 class Receiver:
@@ -192,6 +216,22 @@ class Receiver:
                                             C.c_void_p(ts_ptr), cap_packets, C.byref(n)),
                  "ldvb_process_device")
         return n.value
+
+    def reset(self):
+        self._ck(self.L.ldvb_reset(self.h), "ldvb_reset")
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.L.ldvb_set_stream(self.h, C.c_void_p(cuda_stream)), "ldvb_set_stream")
+
+    def profile(self, enable: bool):
+        self._ck(self.L.ldvb_profile(self.h, int(enable)), "ldvb_profile")
+
+    def get_profile(self) -> dict:
+        arr = (KernelStat * 64)()
+        n = C.c_int(0)
+        self._ck(self.L.ldvb_get_profile(self.h, arr, 64, C.byref(n)), "ldvb_get_profile")
+        return {arr[i].name.decode(): {"launches": arr[i].launches, "ms_total": arr[i].ms_total}
+                for i in range(n.value)}
 
     def meas(self) -> dict:
         m = Meas()

@@ -66,6 +66,8 @@ struct Tap {
   uint64_t bytes = 0;
 };
 
+struct ProfSpanRec { int id; cudaEvent_t a, b; };
+
 }  // namespace
 
 struct ldvb_handle {
@@ -123,6 +125,15 @@ struct ldvb_handle {
   std::vector<uint8_t> ts_queue;
   size_t ts_queue_rd = 0;
 
+  // ---- per-kernel timing (ldvb_profile)
+  bool profiling = false;
+  bool own_stream = true;
+  std::vector<std::string> prof_names;
+  std::vector<uint32_t> prof_launches;
+  std::vector<double> prof_ms;
+  std::vector<ProfSpanRec> prof_pending;
+  std::vector<cudaEvent_t> prof_free;
+
   // ---- taps
   Tap taps[9];
   std::vector<float> meas_log;   // {freq_tap, ss, mer} per measurement of the last batch
@@ -141,9 +152,70 @@ namespace {
     }                                                                                 \
   } while (0)
 
+// Kernel launch with optional per-kernel CUDA-event timing (ldvb_profile).
+struct ProfSpan { int id; cudaEvent_t a, b; };
+
+int prof_begin(ldvb_handle *h, const char *name, ProfSpan *sp);
+void prof_end(ldvb_handle *h, ProfSpan *sp);
+
+#define KL(name, call)                                                                \
+  do {                                                                                \
+    ProfSpan sp_;                                                                     \
+    const int prof_ = h->profiling ? prof_begin(h, name, &sp_) : 0;                   \
+    cudaError_t e_ = (call);                                                          \
+    if (prof_) prof_end(h, &sp_);                                                     \
+    ++h->launches;                                                                    \
+    if (e_ != cudaSuccess) {                                                          \
+      char b_[256];                                                                   \
+      snprintf(b_, sizeof b_, "%s:%d: kernel %s: %s", __FILE__, __LINE__, name, cudaGetErrorString(e_)); \
+      h->err = b_;                                                                    \
+      return LDVB_ECUDA;                                                              \
+    }                                                                                 \
+  } while (0)
+
 int fail(ldvb_handle *h, int code, const char *msg) {
   h->err = msg;
   return code;
+}
+
+int prof_begin(ldvb_handle *h, const char *name, ProfSpan *sp) {
+  int id = -1;
+  for (size_t i = 0; i < h->prof_names.size(); ++i)
+    if (h->prof_names[i] == name) { id = (int)i; break; }
+  if (id < 0) {
+    id = (int)h->prof_names.size();
+    h->prof_names.push_back(name);
+    h->prof_launches.push_back(0);
+    h->prof_ms.push_back(0);
+  }
+  auto get = [&](cudaEvent_t *e) {
+    if (!h->prof_free.empty()) { *e = h->prof_free.back(); h->prof_free.pop_back(); return true; }
+    return cudaEventCreate(e) == cudaSuccess;
+  };
+  if (!get(&sp->a) || !get(&sp->b)) return 0;
+  sp->id = id;
+  cudaEventRecord(sp->a, h->st);
+  return 1;
+}
+
+void prof_end(ldvb_handle *h, ProfSpan *sp) {
+  cudaEventRecord(sp->b, h->st);
+  h->prof_pending.push_back({sp->id, sp->a, sp->b});
+}
+
+void prof_harvest(ldvb_handle *h) {
+  if (h->prof_pending.empty()) return;
+  cudaStreamSynchronize(h->st);
+  for (auto &r : h->prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      h->prof_ms[r.id] += ms;
+      h->prof_launches[r.id] += 1;
+    }
+    h->prof_free.push_back(r.a);
+    h->prof_free.push_back(r.b);
+  }
+  h->prof_pending.clear();
 }
 
 cudaError_t upload(DevBuf &b, const void *src, size_t n) {
@@ -197,6 +269,33 @@ void rx_reset_state(ldvb_handle *h) {
   memset(&s, 0, sizeof s);
   s.est_insp = 75.0f * 75.0f;  // sdr.h:727
   s.agc_gain = 1;
+}
+
+// Everything a fresh handle starts from (also ldvb_reset).
+void reset_carry(ldvb_handle *h) {
+  Stream *ss[] = {&h->s_raw, &h->s_notched, &h->s_pp, &h->s_sym, &h->s_bytes, &h->s_mpeg};
+  for (Stream *s : ss) { s->count = 0; s->fresh = 0; }
+  memset(&h->notch, 0, sizeof h->notch);
+  h->notch.gain = 1;
+  for (int s = 0; s < kNotchMaxSlots; ++s) h->notch.slot[s].bin = -1;
+  h->rot_index = 0;
+  const float freqw = h->cfg.Ftune ? (h->cfg.Ftune / h->Fs_rx) * 65536 : 0.0f;
+  rx_reset_state(h);
+  h->rx_state.freqw = freqw;
+  h->rx_state.freq_tap = freqw / 65536;
+  if (h->use_fir && h->fir_current_freq != 0) {
+    h->fir_shifted = shift_taps(h->fir_coeffs, 0);
+    h->fir_current_freq = 0;
+    cudaMemcpy(h->d_taps.p, h->fir_shifted.data(), h->fir_shifted.size() * 4, cudaMemcpyHostToDevice);
+  }
+  for (HypState &s : h->hyp) s = HypState();
+  h->locked = 0; h->skip = 0;
+  memset(&h->sync, 0, sizeof h->sync);
+  h->sync.report_state = 1;
+  h->sync.phase8 = -1;
+  h->derand_pos = 0;
+  h->ts_queue.clear(); h->ts_queue_rd = 0;
+  memset(&h->meas, 0, sizeof h->meas);
 }
 
 void rx_setup(ldvb_handle *h) {
@@ -295,7 +394,9 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rx_forced, &h->d_deconv_carry, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
   for (DevBuf *b : bufs) b->release();
   for (Tap &t : h->taps) t.buf.release();
-  if (h->st) cudaStreamDestroy(h->st);
+  for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto &e : h->prof_free) cudaEventDestroy(e);
+  if (h->st && h->own_stream) cudaStreamDestroy(h->st);
   delete h;
   return LDVB_OK;
 }
@@ -443,14 +544,54 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     cudaMemset(h->d_notch_tables.p, 0, (size_t)kNotchN * 8);
     h->notch_tables_used = 1;
   }
-  // Deconvolution / sync / derandomiser carry
-  for (HypState &s : h->hyp) s = HypState();
-  h->locked = 0; h->skip = 0;
-  memset(&h->sync, 0, sizeof h->sync);
-  h->sync.report_state = 1;
-  h->sync.phase8 = -1;
-  h->derand_pos = 0;
+  reset_carry(h);
   *out = h;
+  return LDVB_OK;
+}
+
+int ldvb_reset(ldvb_handle *h) {
+  if (!h) return LDVB_EINVAL;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  CK(cudaStreamSynchronize(h->st));
+  reset_carry(h);
+  return LDVB_OK;
+}
+
+int ldvb_set_stream(ldvb_handle *h, void *cuda_stream) {
+  if (!h) return LDVB_EINVAL;
+  CK(cudaStreamSynchronize(h->st));
+  if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+  h->st = static_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
+  return LDVB_OK;
+}
+
+int ldvb_profile(ldvb_handle *h, int enable) {
+  if (!h) return LDVB_EINVAL;
+  prof_harvest(h);
+  h->profiling = enable != 0;
+  if (enable) {
+    std::fill(h->prof_ms.begin(), h->prof_ms.end(), 0.0);
+    std::fill(h->prof_launches.begin(), h->prof_launches.end(), 0u);
+  }
+  return LDVB_OK;
+}
+
+int ldvb_get_profile(ldvb_handle *h, ldvb_kernel_stat *stats, int cap, int *n) {
+  if (!h || !n) return LDVB_EINVAL;
+  prof_harvest(h);
+  int k = 0;
+  for (size_t i = 0; i < h->prof_names.size() && k < cap; ++i) {
+    if (!h->prof_launches[i]) continue;
+    if (stats) {
+      memset(&stats[k], 0, sizeof stats[k]);
+      snprintf(stats[k].name, sizeof stats[k].name, "%s", h->prof_names[i].c_str());
+      stats[k].launches = h->prof_launches[i];
+      stats[k].ms_total = (float)h->prof_ms[i];
+    }
+    ++k;
+  }
+  *n = k;
   return LDVB_OK;
 }
 
@@ -526,7 +667,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
     d.ndetect = (int)dblocks.size(); d.nslots = c.anf;
     d.twiddle_rev = h->d_twiddle.as<float2>();
     d.bins_out = h->d_notch_bins.as<int32_t>();
-    CK(launch_notch_detect(d, h->st)); ++h->launches;
+    KL("notch_detect", launch_notch_detect(d, h->st));
     std::vector<int32_t> bins(dblocks.size() * c.anf);
     CK(cudaMemcpyAsync(bins.data(), h->d_notch_bins.p, bins.size() * 4, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -572,7 +713,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   a.seg_entry = h->d_notch_entry.as<float2>();
   a.seg_exit = h->d_notch_exit.as<float2>();
   a.seg_exact = h->d_notch_exact.as<uint8_t>();
-  CK(launch_notch_apply(a, -1, nullptr, h->st)); ++h->launches;
+  KL("notch_apply", launch_notch_apply(a, -1, nullptr, h->st));
   // Verify entry(j+1) == exit(j) bit for bit; re-run (serially, in order) the
   // segments whose warm-up had not merged with the true trajectory.
   std::vector<float2> entry((size_t)a.nsegs * kNotchMaxSlots), exitv((size_t)a.nsegs * kNotchMaxSlots);
@@ -595,7 +736,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
     }
     if (same) continue;
     // Exact re-run of segment j from the (now final) exit state of segment j-1.
-    CK(launch_notch_apply(a, (int)j, a.seg_exit + (size_t)(j - 1) * kNotchMaxSlots, h->st)); ++h->launches;
+    KL("notch_apply", launch_notch_apply(a, (int)j, a.seg_exit + (size_t)(j - 1) * kNotchMaxSlots, h->st));
     ++h->meas.notch_repaired;
     rc = fetch();
     if (rc) return rc;
@@ -642,7 +783,7 @@ int run_frontend(ldvb_handle *h, const RawSrc &src, int fmt, uint64_t avail, uin
   a.ntaps = N; a.decim = D;
   a.out = reinterpret_cast<float2 *>(h->s_pp.at(h->s_pp.count));
   a.count = count;
-  CK(launch_frontend(a, h->st)); ++h->launches;
+  KL("frontend", launch_frontend(a, h->st));
   h->rot_index = (uint32_t)((h->rot_index + *consumed) & 0xffffu);
   h->s_pp.count += count;
   h->s_pp.fresh = count;
@@ -688,7 +829,7 @@ int run_receiver(ldvb_handle *h) {
       CK(smp.alloc(nchunks * 8)); CK(smpf.alloc(nchunks * 4));
       a.sampled = smp.as<float2>(); a.sampled_flag = smpf.as<uint32_t>();
     }
-    CK(launch_rx(a, -1, nullptr, h->st)); ++h->launches;
+    KL("rx", launch_rx(a, -1, nullptr, h->st));
     RxSpanInfo inf;
     CK(cudaMemcpyAsync(&inf, a.info, sizeof inf, cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(&h->rx_state, a.state_end, sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
@@ -719,13 +860,13 @@ int run_receiver(ldvb_handle *h) {
     a.sym_out = h->d_rx_spans.as<uint32_t>();
     a.head_log = h->d_rx_head.as<RxSeamSym>();
     a.tail_log = h->d_rx_tail.as<RxSeamSym>();
-    CK(launch_rx(a, -1, nullptr, h->st)); ++h->launches;
+    KL("rx", launch_rx(a, -1, nullptr, h->st));
     RxStitchArgs sa;
     sa.info = a.info; sa.head_log = a.head_log; sa.tail_log = a.tail_log;
     sa.nspans = a.nspans; sa.nrot = h->cst.nrotations; sa.nsymbols = h->cst.nsymbols;
     sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
     sa.seams = h->d_rx_seams.as<RxSeam>();
-    CK(launch_rx_stitch(sa, -1, h->st)); ++h->launches;
+    KL("rx_stitch", launch_rx_stitch(sa, -1, h->st));
     std::vector<RxSeam> seams(a.nspans);
     std::vector<RxSpanInfo> info(a.nspans);
     auto fetch = [&]() -> int {
@@ -742,9 +883,9 @@ int run_receiver(ldvb_handle *h) {
     for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
       if (seams[j].ok) continue;
       ++h->meas.seams_repaired;
-      CK(launch_rx(a, (int)(j + 1), a.state_end + j, h->st)); ++h->launches;
+      KL("rx", launch_rx(a, (int)(j + 1), a.state_end + j, h->st));
       // An exact continuation needs no alignment: its first symbol follows span j's last.
-      if (j + 2 < a.nspans) { CK(launch_rx_stitch(sa, (int)(j + 1), h->st)); ++h->launches; }
+      if (j + 2 < a.nspans) { KL("rx_stitch", launch_rx_stitch(sa, (int)(j + 1), h->st)); }
       rc = fetch();
       if (rc) return rc;
       seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0;
@@ -776,7 +917,7 @@ int run_receiver(ldvb_handle *h) {
     ca.span_offset = h->d_rx_off.as<uint64_t>(); ca.span_skip = h->d_rx_skip.as<uint32_t>();
     ca.span_rot = h->d_rx_rot.as<uint8_t>(); ca.rot_perm = h->d_rotperm.as<uint8_t>();
     ca.nsymbols = h->cst.nsymbols; ca.sym_out = sym_dst;
-    CK(launch_rx_compact(ca, produced, h->st)); ++h->launches;
+    KL("rx_compact", launch_rx_compact(ca, produced, h->st));
     // Carry: the end state of the last span.  Its phase is rotated back by the
     // cumulative rotation so that the next batch continues in span 0's frame.
     CK(cudaMemcpyAsync(&h->rx_state, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
@@ -846,7 +987,7 @@ int deconv_launch(ldvb_handle *h, uint64_t limit_bytes, DeconvRun *run) {
   a.punctperiod = pp; a.punctweight = pw;
   for (int b = 0; b < 8; ++b) a.deconv[b] = h->dec.deconv[b];
   a.out = h->s_bytes.at(h->s_bytes.count);
-  CK(launch_deconv_carry(a, h->d_deconv_carry.as<uint64_t>(), h->st)); ++h->launches;
+  KL("deconv_carry", launch_deconv_carry(a, h->d_deconv_carry.as<uint64_t>(), h->st));
   uint64_t carry[5];
   CK(cudaMemcpyAsync(carry, h->d_deconv_carry.p, sizeof carry, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -874,20 +1015,17 @@ int run_sync(ldvb_handle *h) {
       npk = (in.count >= 205) ? (in.count - 1) / 204 : 0;  // dvb.h:843
       npk = std::min<uint64_t>(npk, (out.cap - out.count) / 204);
       if (!npk) break;
-      CK(launch_sync_flags(in.at(0), npk, h->d_sync_state.as<SyncState>(), h->d_badwords.as<uint32_t>(), h->st));
-      ++h->launches;
+      KL("sync_flags", launch_sync_flags(in.at(0), npk, h->d_sync_state.as<SyncState>(), h->d_badwords.as<uint32_t>(), h->st));
     } else if (in.count < 204 * 8 + 1) {
       break;  // dvb.h:758
     }
-    CK(launch_sync_track(in.at(0), in.count, h->d_sync_state.as<SyncState>(), h->d_badwords.as<uint32_t>(), npk,
-                         h->d_sync_res.as<SyncResult>(), h->st));
-    ++h->launches;
+    KL("sync_track", launch_sync_track(in.at(0), in.count, h->d_sync_state.as<SyncState>(),
+                                       h->d_badwords.as<uint32_t>(), npk, h->d_sync_res.as<SyncResult>(), h->st));
     SyncResult r;
     CK(cudaMemcpyAsync(&r, h->d_sync_res.p, sizeof r, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     if (r.produced) {
-      CK(launch_realign(in.at(0), r.produced, h->sync.bitphase, h->sync.polarity, out.at(out.count), h->st));
-      ++h->launches;
+      KL("realign", launch_realign(in.at(0), r.produced, h->sync.bitphase, h->sync.polarity, out.at(out.count), h->st));
       out.count += r.produced;
       out.fresh += r.produced;
     }
@@ -919,13 +1057,14 @@ int run_fec(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_out) 
   a.rs_out = h->cfg.keep_taps ? h->d_rs204.as<uint8_t>() : nullptr;
   a.rts_out = h->d_rts.as<uint8_t>();
   a.flags = h->d_rsflags.as<int32_t>();
-  CK(launch_deint_rs(a, h->st)); ++h->launches;
+  KL("deint_rs", launch_deint_rs(a, h->st));
   DerandArgs d;
   d.rts = a.rts_out; d.npackets = npk; d.pattern = h->d_derand.as<uint8_t>();
   d.pos_in = h->derand_pos; d.ts_out = ts_dst; d.ts_cap = ts_cap;
   d.counts = h->d_counts.as<uint64_t>(); d.flags = a.flags; d.scratch = h->d_scratch.as<uint32_t>();
   int nl = 0;
-  CK(launch_derand(d, h->st, &nl)); h->launches += nl;
+  KL("derand", launch_derand(d, h->st, &nl));
+  h->launches += (nl > 0 ? nl - 1 : 0);
   uint64_t counts[4];
   CK(cudaMemcpyAsync(counts, h->d_counts.p, sizeof counts, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -1142,36 +1281,51 @@ int ldvb_tap(ldvb_handle *h, int which, void *dst, size_t cap, size_t *n_bytes) 
   return LDVB_OK;
 }
 
-int ldvb_table(ldvb_handle *h, int which, void *dst, size_t cap, size_t *n_bytes) {
-  if (!h || !n_bytes) return LDVB_EINVAL;
-  std::vector<uint8_t> blob;
+static int host_table(const ldvb_config &c, int which, std::vector<uint8_t> &blob) {
   auto put = [&](const void *p, size_t n) { blob.assign((const uint8_t *)p, (const uint8_t *)p + n); };
+  // Sample rate seen by the receiver (leandvb.cc:353-399).
+  float Fs = c.Fs;
+  int decim = 1;
+  std::vector<float> fir;
+  if (c.resample) { fir = design_resampler(Fs, c.Fm, c.rolloff, c.resample_rej, c.decim, &decim); Fs /= decim; }
+  else if (c.decim > 1) Fs /= c.decim;
   switch (which) {
-    case LDVB_TABLE_CSTLN: put(h->cst.cells.data(), h->cst.cells.size() * sizeof(CstlnCell)); break;
+    case LDVB_TABLE_CSTLN: {
+      Cstln cs = make_cstln(c.constellation, c.hard_metric != 0);
+      if (!cs.nsymbols) return LDVB_EINVAL;
+      put(cs.cells.data(), cs.cells.size() * sizeof(CstlnCell));
+      break;
+    }
     case LDVB_TABLE_TRIG16: { auto t = make_trig16(); put(t.data(), t.size() * 4); break; }
     case LDVB_TABLE_RS_EXP: { uint8_t e[512], l[256]; make_rs_tables(e, l); put(e, 512); break; }
     case LDVB_TABLE_RS_LOG: { uint8_t e[512], l[256]; make_rs_tables(e, l); put(l, 256); break; }
     case LDVB_TABLE_DERAND: { auto t = make_derand_pattern(); put(t.data(), t.size()); break; }
-    case LDVB_TABLE_FIR: put(h->fir_coeffs.data(), h->fir_coeffs.size() * 4); break;
-    case LDVB_TABLE_DECONV: put(h->dec.deconv, 8 * (size_t)h->dec.punctperiod); break;
+    case LDVB_TABLE_FIR: put(fir.data(), fir.size() * 4); break;
+    case LDVB_TABLE_DECONV: {
+      DeconvPolys d;
+      if (!make_deconv(c.fec, &d)) return LDVB_EINVAL;
+      put(d.deconv, 8 * (size_t)d.punctperiod);
+      break;
+    }
     case LDVB_TABLE_RRC: {
       int steps = 0;
-      auto t = design_rrc(h->Fs_rx, h->cfg.Fm, h->cfg.rolloff, h->cfg.rrc_rej, h->cfg.rrc_steps, &steps);
+      auto t = design_rrc(Fs, c.Fm, c.rolloff, c.rrc_rej, c.rrc_steps, &steps);
       put(t.data(), t.size() * 4);
       break;
     }
     case LDVB_TABLE_TRELLIS: {
       Trellis t;
-      if (!make_trellis(h->cfg.fec, &t)) return LDVB_EINVAL;
+      if (!make_trellis(c.fec, &t)) return LDVB_EINVAL;
       for (size_t i = 0; i < t.pred.size(); ++i) { blob.push_back(t.pred[i]); blob.push_back(t.us[i]); }
       break;
     }
     case LDVB_TABLE_VITMAP: {
       Trellis t;
-      if (!make_trellis(h->cfg.fec, &t)) return LDVB_EINVAL;
-      VitSyncs v = make_vitsyncs(h->cst, t);
+      Cstln cs = make_cstln(c.constellation, c.hard_metric != 0);
+      if (!cs.nsymbols || !make_trellis(c.fec, &t)) return LDVB_EINVAL;
+      VitSyncs v = make_vitsyncs(cs, t);
       blob.push_back((uint8_t)v.nsyncs); blob.push_back((uint8_t)v.nshifts);
-      blob.push_back((uint8_t)v.bps); blob.push_back((uint8_t)h->cst.nsymbols);
+      blob.push_back((uint8_t)v.bps); blob.push_back((uint8_t)cs.nsymbols);
       for (int s = 0; s < v.nsyncs; ++s) {
         blob.push_back((uint8_t)v.shift[s]);
         blob.insert(blob.end(), v.map[s].begin(), v.map[s].end());
@@ -1180,11 +1334,24 @@ int ldvb_table(ldvb_handle *h, int which, void *dst, size_t cap, size_t *n_bytes
     }
     default: return LDVB_EINVAL;
   }
+  return LDVB_OK;
+}
+
+int ldvb_host_table(const ldvb_config *cfg, int which, void *dst, size_t cap, size_t *n_bytes) {
+  if (!cfg || !n_bytes) return LDVB_EINVAL;
+  std::vector<uint8_t> blob;
+  int rc = host_table(*cfg, which, blob);
+  if (rc) return rc;
   *n_bytes = blob.size();
   if (!dst) return LDVB_OK;
   if (cap < blob.size()) return LDVB_EOVERFLOW;
   memcpy(dst, blob.data(), blob.size());
   return LDVB_OK;
+}
+
+int ldvb_table(ldvb_handle *h, int which, void *dst, size_t cap, size_t *n_bytes) {
+  if (!h) return LDVB_EINVAL;
+  return ldvb_host_table(&h->cfg, which, dst, cap, n_bytes);
 }
 
 int ldvb_get_rx_state(ldvb_handle *h, uint32_t w[22]) {

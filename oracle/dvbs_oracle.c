@@ -879,6 +879,13 @@ static inline uint8_t deconv_readbyte(orc_deconv *d, orc_dsync *s,
 
 size_t orc_deconv_run(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
 		      uint8_t *out, size_t out_cap, size_t *consumed) {
+  return orc_deconv_run2(d, symbols4, n_in, out, out_cap, consumed, 0);
+}
+
+void orc_deconv_set(orc_deconv *d, int locked, int skip) { d->locked = locked; d->skip = skip; }
+
+size_t orc_deconv_run2(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
+		       uint8_t *out, size_t out_cap, size_t *consumed, int big_batch) {
   /* dvb.h:414-467 with fastlock == false */
   size_t skipped = 0;
   if ( d->skip ) {
@@ -892,7 +899,7 @@ size_t orc_deconv_run(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
   long maxwr = (long)out_cap;
   long n = (maxrd < maxwr) ? maxrd : maxwr;
   if ( !n ) return 0;
-  if ( n < 32 ) return 0;
+  if ( n < 32 && !big_batch ) return 0;
   const uint8_t *pin = symbols4 + 4*skipped, *pin0 = pin;
   uint8_t *pout = out;
   orc_dsync *s = &d->syncs[d->locked];
@@ -949,7 +956,23 @@ size_t orc_mpegsync_run(orc_mpegsync *m, orc_deconv *deconv,
 			uint8_t *out, size_t out_cap, size_t *consumed,
 			int *lock_out, size_t *n_lock,
 			uint64_t *locktime_out, size_t *n_locktime) {
+  return orc_mpegsync_run2(m, deconv, in, n_in, out, out_cap, consumed,
+			   lock_out, n_lock, locktime_out, n_locktime, 0, NULL);
+}
+
+/* per_wrap != 0 selects the large-batch schedule documented in DESIGN.md: the
+   sweep counter advances at every wrap of the bit phase (what the reference
+   does with its default buffers, where one run() call never sees two wraps) and
+   the call returns as soon as deconv->next_sync() fired (*switched = 1) so that
+   the caller can restart the deconvolver at exactly that byte. */
+size_t orc_mpegsync_run2(orc_mpegsync *m, orc_deconv *deconv,
+			 const uint8_t *in, size_t n_in,
+			 uint8_t *out, size_t out_cap, size_t *consumed,
+			 int *lock_out, size_t *n_lock,
+			 uint64_t *locktime_out, size_t *n_locktime,
+			 int per_wrap, int *switched) {
   const int P = 204;
+  if ( switched ) *switched = 0;
   size_t rd = 0, wr = 0, nl = 0, nlt = 0;
   if ( m->report_state ) {                     /* dvb.h:743-747 */
     if ( lock_out ) lock_out[nl] = 0;
@@ -997,7 +1020,19 @@ size_t orc_mpegsync_run(orc_mpegsync *m, orc_deconv *deconv,
       }
       rd += chunk;
       ++m->bitphase;
-      if ( m->bitphase == 8 ) { m->bitphase = 0; next_sync = 1; }
+      if ( m->bitphase == 8 ) {
+	m->bitphase = 0;
+	next_sync = 1;
+	if ( per_wrap ) {
+	  next_sync = 0;
+	  if ( ++m->next_sync_count >= 3 ) {
+	    m->next_sync_count = 0;
+	    if ( deconv ) orc_deconv_next_sync(deconv);
+	    if ( switched ) *switched = 1;
+	    goto done;
+	  }
+	}
+      }
     }
     if ( next_sync ) {
       ++m->next_sync_count;

@@ -181,6 +181,10 @@ void orc_deconv_next_sync(orc_deconv *d);          /* dvb.h:185-193 */
 size_t orc_deconv_run(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
 		      uint8_t *out, size_t out_cap, size_t *consumed);
 
+size_t orc_deconv_run2(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
+		       uint8_t *out, size_t out_cap, size_t *consumed, int big_batch);
+void   orc_deconv_set(orc_deconv *d, int locked, int skip);
+
 typedef struct {
   int scan_syncs, want_syncs;
   unsigned long lock_timeout;
@@ -201,6 +205,13 @@ size_t orc_mpegsync_run(orc_mpegsync *m, orc_deconv *deconv,
 			uint8_t *out, size_t out_cap, size_t *consumed,
 			int *lock_out, size_t *n_lock,
 			uint64_t *locktime_out, size_t *n_locktime);
+
+size_t orc_mpegsync_run2(orc_mpegsync *m, orc_deconv *deconv,
+			 const uint8_t *in, size_t n_in,
+			 uint8_t *out, size_t out_cap, size_t *consumed,
+			 int *lock_out, size_t *n_lock,
+			 uint64_t *locktime_out, size_t *n_locktime,
+			 int per_wrap, int *switched);
 
 /* dvb.h:926-948. Returns packets written. */
 size_t orc_deinterleave(const uint8_t *in, size_t n_in, uint8_t *out_packets,

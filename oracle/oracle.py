@@ -101,11 +101,17 @@ def lib():
         L.orc_deconv_next_sync.argtypes = [vp]
         L.orc_deconv_run.restype = sz
         L.orc_deconv_run.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
+        L.orc_deconv_run2.restype = sz
+        L.orc_deconv_run2.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int]
+        L.orc_deconv_set.argtypes = [vp, C.c_int, C.c_int]
         L.orc_deconv_get.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
         L.orc_mpegsync_init.argtypes = [vp]
         L.orc_mpegsync_run.restype = sz
         L.orc_mpegsync_run.argtypes = [vp, vp, vp, sz, vp, sz, C.POINTER(sz),
                                        vp, C.POINTER(sz), vp, C.POINTER(sz)]
+        L.orc_mpegsync_run2.restype = sz
+        L.orc_mpegsync_run2.argtypes = [vp, vp, vp, sz, vp, sz, C.POINTER(sz),
+                                        vp, C.POINTER(sz), vp, C.POINTER(sz), C.c_int, C.POINTER(C.c_int)]
         L.orc_mpegsync_get.argtypes = [vp, vp]
         L.orc_deinterleave.restype = sz
         L.orc_deinterleave.argtypes = [vp, sz, vp, C.POINTER(sz)]
@@ -352,13 +358,18 @@ class Deconv:
         return {"locked": v[0].value, "skip": v[1].value,
                 "punctperiod": v[2].value, "punctweight": v[3].value}
 
-    def run(self, symbols4, out_cap=None):
+    def run(self, symbols4, out_cap=None, big_batch=False):
+        """One reference run(); big_batch drops the `n < 32` early return (dvb.h:424-426),
+        which only matters for the last few bytes of a stream."""
         s = np.ascontiguousarray(symbols4, np.uint8).reshape(-1, 4)
         cap = out_cap if out_cap is not None else s.shape[0] + 64
         out = np.zeros(max(cap, 1), np.uint8)
         cons = C.c_size_t(0)
-        k = lib().orc_deconv_run(self.o.p, _p(s), s.shape[0], _p(out), cap, C.byref(cons))
+        k = lib().orc_deconv_run2(self.o.p, _p(s), s.shape[0], _p(out), cap, C.byref(cons), int(big_batch))
         return out[:k], cons.value
+
+    def set_locked(self, locked, skip):
+        lib().orc_deconv_set(self.o.p, locked, skip)
 
     def snapshot(self): return self.o.buf.copy()
     def restore(self, b): self.o.buf[:] = b
@@ -374,17 +385,20 @@ class MpegSync:
         return dict(zip(["bitphase", "polarity", "synchronized", "phase8",
                          "next_sync_count", "lock_timeleft", "locktime"], v.tolist()))
 
-    def run(self, data, deconv=None, out_cap=None):
+    def run(self, data, deconv=None, out_cap=None, per_wrap=False):
+        """-> (aligned bytes, consumed, lock events, locktimes[, switched when per_wrap])"""
         d = np.ascontiguousarray(data, np.uint8)
         cap = out_cap if out_cap is not None else d.size + 204 * 9
         out = np.zeros(cap, np.uint8)
         lock = np.zeros(d.size // 204 + 8, np.int32)
         lt = np.zeros(d.size // 204 + 8, np.uint64)
         cons, nl, nlt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
-        k = lib().orc_mpegsync_run(self.o.p, deconv.o.p if deconv else None, _p(d), d.size,
-                                   _p(out), cap, C.byref(cons), _p(lock), C.byref(nl),
-                                   _p(lt), C.byref(nlt))
-        return out[:k], cons.value, lock[:nl.value].copy(), lt[:nlt.value].copy()
+        sw = C.c_int(0)
+        k = lib().orc_mpegsync_run2(self.o.p, deconv.o.p if deconv else None, _p(d), d.size,
+                                    _p(out), cap, C.byref(cons), _p(lock), C.byref(nl),
+                                    _p(lt), C.byref(nlt), int(per_wrap), C.byref(sw))
+        res = (out[:k], cons.value, lock[:nl.value].copy(), lt[:nlt.value].copy())
+        return res + (bool(sw.value),) if per_wrap else res
 
 
 def deinterleave(data):
@@ -577,23 +591,27 @@ class Chain:
 
     def _deconv_sync(self, symbols):
         """Algebraic deconvolution + MPEG sync with the backward next_sync() edge
-        (dvb.h:771-778) under the one-shot schedule: the deconvolver hypothesis
-        is switched right after the byte that completed the third fruitless sweep."""
+        (dvb.h:771-778) under the large-batch schedule: the sweep counter
+        advances per wrap of the bit phase; when it fires, the bytes that the old
+        hypothesis produced beyond the search position are void and the next
+        hypothesis starts at the symbol that follows the last consumed byte."""
         by_all, outs, locks, lts = [], [], [], []
         spos = 0
-        while True:
+        for _ in range(256):
+            if self.deconv.get()["skip"]:
+                if len(symbols) - spos < 1:
+                    break
             snap = self.deconv.snapshot()
-            locked0 = self.deconv.get()["locked"]
-            by, scons = self.deconv.run(symbols[spos:])
-            if by.size == 0:
+            by, scons = self.deconv.run(symbols[spos:], big_batch=True)
+            if by.size == 0 and not self.deconv.get()["skip"]:
                 break
             bpos = 0
             switched = False
             while True:
-                o, c, lk, lt = self.sync.run(by[bpos:], self.deconv)
+                o, c, lk, lt, sw = self.sync.run(by[bpos:], self.deconv, per_wrap=True)
                 outs.append(o); locks.append(lk); lts.append(lt)
                 bpos += c
-                if self.deconv.get()["locked"] != locked0 or self.deconv.get()["skip"]:
+                if sw:
                     switched = True
                     break
                 if c == 0 and o.size == 0:
@@ -601,17 +619,13 @@ class Chain:
             if not switched:
                 by_all.append(by)
                 break
-            # Re-run the deconvolver for exactly the bytes the sync consumed
-            # (plus the look-ahead byte), then apply the switch.
-            newlocked, newskip = self.deconv.get()["locked"], self.deconv.get()["skip"]
-            self.deconv.restore(snap)
-            keep = bpos + 1
-            by2, scons2 = self.deconv.run(symbols[spos:], out_cap=keep)
-            by_all.append(by2[:bpos])
-            # the look-ahead byte is dropped: sync restarts on fresh bytes
-            while self.deconv.get()["locked"] != newlocked:
-                self.deconv.next_sync()
+            st = self.deconv.get()
+            self.deconv.restore(snap)              # back to the state before this run
+            used = bpos
+            by2, scons2 = self.deconv.run(symbols[spos:], out_cap=used, big_batch=True) if used else (by[:0], 0)
+            by_all.append(by2)
             spos += scons2
+            self.deconv.set_locked(st["locked"], st["skip"])
         by = np.concatenate(by_all) if by_all else np.zeros(0, np.uint8)
         return (by, np.concatenate(outs) if outs else np.zeros(0, np.uint8),
                 np.concatenate(locks) if locks else np.zeros(0, np.int32),

@@ -1,0 +1,104 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol declared in
+include/leandvb_b200.h, refuses to run without a device (no fallback), and its
+host-side table builders reproduce the reference's tables."""
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, have_gpu
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_exports_match_header(product):
+    hdr = open(os.path.join(ROOT, "include", "leandvb_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ldvb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = product.load()
+    missing = [f for f in sorted(declared) if not hasattr(L, f)]
+    assert not missing, f"declared in include/leandvb_b200.h but not exported: {missing}"
+    assert set(product.EXPORTS) == declared
+
+
+def test_abi_and_defaults(product):
+    L = product.load()
+    assert L.ldvb_abi_version() == 1
+    c = product.default_config()
+    # leandvb.cc:88-135 defaults
+    assert (c.input_format, c.anf, c.sampler, c.constellation, c.fec) == (0, 1, 1, 1, 0)
+    assert abs(c.Fs - 2.4e6) < 1 and abs(c.Fm - 2e6) < 1 and abs(c.rolloff - 0.35) < 1e-6
+    assert c.resample == 0 and c.viterbi == 0 and c.fastlock == 0 and abs(c.Finfo - 5) < 1e-6
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-device behaviour")
+def test_create_fails_loudly_without_gpu(product):
+    with pytest.raises(product.LdvbError) as e:
+        product.Receiver()
+    assert e.value.code == -4  # LDVB_ENODEV: there is no CPU fallback
+
+
+def test_unsupported_config_is_rejected(product):
+    import ctypes as C
+    L = product.load()
+    cfg = product.default_config()
+    cfg.abi_version = 99
+    h = C.c_void_p()
+    assert L.ldvb_create(C.byref(cfg), C.byref(h)) == -1
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_host_tables_match_reference_dumps(product):
+    """Tables dumped from the unmodified reference headers (tests/golden/tables.json,
+    made by oracle/_ref/ref_tables) vs the library's own host builders."""
+    g = json.load(open(os.path.join(GOLDEN, "tables.json")))
+    P = product
+    c = P.default_config()
+    assert _sha(P.host_table(c, "cstln")) == g["cstln_qpsk.bin"]["sha256"]
+    assert _sha(P.host_table(P.default_config(cstln="BPSK"), "cstln")) == g["cstln_bpsk.bin"]["sha256"]
+    assert _sha(P.host_table(P.default_config(cstln="8PSK"), "cstln")) == g["cstln_8psk.bin"]["sha256"]
+    assert _sha(P.host_table(P.default_config(hard_metric=True), "cstln")) == g["cstln_qpsk_hard.bin"]["sha256"]
+    assert _sha(P.host_table(c, "trig16")) == g["trig16.f32"]["sha256"]
+    assert _sha(P.host_table(c, "derand")) == g["derand.u8"]["sha256"]
+    assert _sha(P.host_table(c, "rs_log")) == g["rs_log.u8"]["sha256"]
+    assert _sha(P.host_table(c, "rs_exp")[:511]) == g["rs_exp.u8"]["sha256"]
+    assert _sha(P.host_table(P.default_config(resample=True), "fir")) == g["lowpass_fs2.4_sr2.f32"]["sha256"]
+    assert _sha(P.host_table(P.default_config(resample=True, Fs=9.6e6), "fir")) == g["lowpass_fs9.6_sr2.f32"]["sha256"]
+    assert _sha(P.host_table(P.default_config(resample=True, Fs=240e6), "fir")) == g["lowpass_fs240_sr2.f32"]["sha256"]
+    assert _sha(P.host_table(P.default_config(sampler="rrc"), "rrc")) == g["rrc_fs2.4_sr2.f32"]["sha256"]
+    assert _sha(P.host_table(P.default_config(sampler="rrc", Fs=4e6), "rrc")) == g["rrc_fs4_sr2.f32"]["sha256"]
+    assert _sha(P.host_table(c, "vitmap")) == g["vitmap_qpsk12.u8"]["sha256"]
+    assert _sha(P.host_table(P.default_config(fec="7/8"), "vitmap")) == g["vitmap_qpsk78.u8"]["sha256"]
+
+
+def test_known_answers(product):
+    """Literals the reference asserts or documents."""
+    P = product
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    c = P.default_config()
+    dec = P.host_table(c, "deconv").view(np.uint64)
+    assert int(dec[0]) == int(kat["deconv_fec12"], 16)          # dvb.h:120, 239
+    cells = P.host_table(c, "cstln").view(np.int16).reshape(256, 256, 4)
+    assert cells[53, 53, :3].tolist() == kat["lookup_53_53"]
+    assert cells[10, (-3) & 255, :3].tolist() == kat["lookup_10_m3"]
+    for fec, f in (("1/2", "deconv_12.u64"), ("3/4", "deconv_34.u64"), ("7/8", "deconv_78.u64")):
+        ref = np.fromfile(os.path.join(GOLDEN, f), dtype=np.uint64)
+        pp = int(ref[0])
+        got = P.host_table(P.default_config(fec=fec), "deconv").view(np.uint64)
+        assert np.array_equal(got, ref[2:2 + pp])
+    # Trellis: compare the branches that exist (the reference leaves `us` of absent
+    # branches uninitialised, viterbi.h:52-55).
+    ref = np.fromfile(os.path.join(GOLDEN, "trellis_12.bin"), dtype=np.uint8).reshape(-1, 2)
+    got = P.host_table(c, "trellis").reshape(-1, 2)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    m = ref[:, 0] != 65
+    assert np.array_equal(got[m, 1], ref[m, 1])
+    gexp = np.fromfile(os.path.join(GOLDEN, "rs_exp.u8"), dtype=np.uint8)
+    assert np.array_equal(P.host_table(c, "rs_exp")[:511], gexp)

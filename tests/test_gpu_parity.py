@@ -1,0 +1,201 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on
+the same seeded / generated inputs.  Integer, byte and index streams must be bit-exact;
+float streams (preprocessed IQ) are bit-exact too (explicit _rn arithmetic, host tables).
+Run with `pytest -m gpu` on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import vectors as V
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def run_product(P, raw, n_batch=None, **kw):
+    fmt = kw.get("fmt", "u8")
+    n = raw.size // 2
+    step = n_batch or n
+    rx = P.Receiver(keep_taps=1, max_batch=step, **kw)
+    taps = {k: [] for k in ("pp", "symbols", "bytes", "mpegbytes", "rspackets", "rtspackets", "rsflags", "sampled")}
+    ts = []
+    for s in range(0, n, step):
+        rx.push(raw[2 * s: 2 * min(n, s + step)])
+        ts.append(rx.pull_all())
+        for k in taps:
+            taps[k].append(rx.tap(k))
+    out = {k: np.concatenate(v) for k, v in taps.items()}
+    out["ts"] = np.concatenate(ts)
+    out["meas"] = rx.meas()
+    out["rx_state"] = rx.rx_state()
+    rx.close()
+    return out
+
+
+def assert_prefix(a, b, what, slack=0):
+    a = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    b = np.ascontiguousarray(b).reshape(-1).view(np.uint8)
+    n = min(a.size, b.size)
+    assert n > 0, what
+    assert np.array_equal(a[:n], b[:n]), f"{what}: first difference at byte {int(np.nonzero(a[:n] != b[:n])[0][0])}"
+    assert abs(a.size - b.size) <= slack, f"{what}: sizes {a.size} vs {b.size}"
+
+
+EXACT_CASES = [
+    ("f32-default", dict(fmt="f32"), {}, 300),
+    ("f32-resample", dict(fmt="f32", resample=True), {}, 300),
+    ("u8-default", dict(fmt="u8"), {}, 300),
+    ("u8-anf0-nearest", dict(fmt="u8", anf=0, sampler="nearest"), dict(ratio="4/1"), 80),
+    ("f32-derot-anf2", dict(fmt="f32", anf=2, Fderot=20000.0), {}, 300),
+    ("f32-scale-decim2", dict(fmt="f32", anf=0, decim=2, Fs=4.8e6, float_scale=0.5), dict(ratio="12/5", power=43.5), 200),
+    ("f32-noise", dict(fmt="f32", resample=True), dict(noise_db=22), 300),
+    ("f32-8psk-hard", dict(fmt="f32", anf=0, cstln="8PSK", hard_metric=True), {}, 120),
+]
+
+
+@pytest.mark.parametrize("name,kw,gkw,npk", EXACT_CASES, ids=[c[0] for c in EXACT_CASES])
+def test_exact_mode_every_stream_bit_exact(product, oracle, name, kw, gkw, npk):
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["pp"], ref["pp"], "preprocessed IQ")
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["sampled"], ref["sampled"], "sampled symbols")
+    assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=8)
+    assert_prefix(got["mpegbytes"], ref["mpegbytes"], "aligned bytes")
+    assert_prefix(got["rspackets"], ref["rspackets"], "RS packets")
+    assert_prefix(got["rtspackets"], ref["rtspackets"], "RS-decoded packets")
+    assert_prefix(got["ts"], ref["ts"], "TS")
+    fl = got["rsflags"].view(np.int32).reshape(-1, 2)
+    assert np.array_equal(fl[:, 0] != 0, ref["rs_bad"]) and np.array_equal(fl[:, 1], ref["rs_nerr"])
+    assert got["meas"]["kernel_launches"] > 0
+
+
+def test_exact_mode_streaming_is_batch_invariant(product, oracle):
+    """Pushing the stream in uneven batches (carry across every stage) gives the same
+    streams as one shot -- the analogue of the reference's --buf-factor invariance."""
+    P, O = product, oracle
+    raw = V.ref_iq(300, fmt="u8")
+    ref = O.Chain(O.Config(fmt="u8", resample=True)).run(raw)
+    got = run_product(P, raw, n_batch=77777, fmt="u8", resample=True)
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["mpegbytes"], ref["mpegbytes"], "aligned bytes", slack=204)
+    assert_prefix(got["ts"], ref["ts"], "TS", slack=188)
+
+
+def test_exact_mode_carry_state_matches_oracle(product, oracle):
+    P, O = product, oracle
+    raw = V.ref_iq(200, fmt="f32")
+    ch = O.Chain(O.Config(fmt="f32", anf=0))
+    ch.run(raw)
+    got = run_product(P, raw, fmt="f32", anf=0)
+    assert np.array_equal(got["rx_state"][:21], ch.rx.get_state()[:21])
+
+
+def test_notch_detect_and_segment_verification(product, oracle):
+    """> 4 Mi samples: auto_notch::detect() fires; the segment-parallel recurrence must be
+    bit-exact (verified carries, repaired when a warm-up did not merge)."""
+    P, O = product, oracle
+    raw = V.ref_iq(2250, fmt="u8")
+    ref = O.Chain(O.Config(fmt="u8")).run(raw)
+    got = run_product(P, raw, fmt="u8", rx_mode=P.RX_FAST)
+    assert_prefix(got["pp"], ref["pp"], "notched IQ")
+    assert_prefix(got["ts"], ref["ts"], "TS")
+
+
+FAST_CASES = [
+    ("clean", dict(fmt="f32", resample=True), {}, 1200),
+    ("noise22", dict(fmt="f32", resample=True), dict(noise_db=22), 1200),
+    ("u8", dict(fmt="u8"), {}, 1200),
+]
+
+
+@pytest.mark.parametrize("name,kw,gkw,npk", FAST_CASES, ids=[c[0] for c in FAST_CASES])
+def test_fast_mode_ts_bit_exact(product, oracle, name, kw, gkw, npk):
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_FAST, **kw)
+    assert_prefix(got["ts"], ref["ts"], "TS")
+    m = got["meas"]
+    assert m["seams_total"] > 10
+    # hard decisions: count symbol mismatches (reported, not assumed)
+    a = got["symbols"].reshape(-1, 4)[:, 2]
+    b = ref["symbols"][:, 2]
+    assert a.size == b.size
+    mism = int((a != b).sum())
+    assert mism <= (0 if "noise" not in name else 20), f"{mism} hard-symbol mismatches, {m}"
+
+
+def test_golden_fixture_through_cuda(product):
+    """Committed vector decoded by the unmodified reference (tests/golden/make_golden.py)."""
+    P = product
+    raw = np.fromfile(os.path.join(GOLDEN, "c1_160.u8"), dtype=np.uint8)
+    for name, kw in (("c1_160.ts", {}), ("c1_160_resample.ts", {"resample": True}), ("c1_160_anf0.ts", {"anf": 0})):
+        want = np.fromfile(os.path.join(GOLDEN, name), dtype=np.uint8).reshape(-1, 188)
+        for mode in (P.RX_EXACT, P.RX_FAST):
+            got = run_product(P, raw, fmt="u8", rx_mode=mode, **kw)["ts"]
+            n = min(len(got), len(want))
+            assert n >= 80 and np.array_equal(got[:n], want[:n]) and 0 <= len(got) - len(want) <= 1
+
+
+def test_loopback_identity_large(product):
+    """Size-independent property at a larger size: decoded packets are a contiguous slice of
+    the transmitted counter packets (BER 0)."""
+    P = product
+    npk = 6000
+    raw = V.ref_iq(npk, fmt="f32")
+    got = run_product(P, raw, fmt="f32", resample=True, rx_mode=P.RX_FAST)["ts"]
+    sent = V.ts_packets(npk)
+    assert len(got) > npk - 80
+    first = int(got[3, 1]) << 16 | int(got[3, 2]) << 8 | int(got[3, 3])
+    assert np.array_equal(got[3:], sent[first:first + len(got) - 3])
+
+
+def test_fir_kernel_standalone(product, oracle):
+    """fir_filter with long taps and decimation (config 5b shape: N=313, D=30) plus ragged
+    and too-short inputs."""
+    P, O = product, oracle
+    rng = np.random.default_rng(7)
+    for n, ntaps, decim in ((200000, 313, 30), (70001, 13, 1), (4099, 5, 3), (312, 313, 30), (313, 313, 1), (0, 5, 1)):
+        x = rng.standard_normal(2 * n).astype(np.float32) * 50
+        taps = rng.standard_normal(ntaps).astype(np.float32)
+        f = O.Fir(taps, decim)
+        f.set_freq(0.0123)
+        want, _ = f.run(x)
+        got = P.fir_cf32(x, f.shifted(), decim)
+        assert got.size == want.size
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, ntaps, decim)
+
+
+def test_rs_kernel_error_patterns(product, oracle):
+    P, O = product, oracle
+    rng = np.random.default_rng(3)
+    msg = rng.integers(0, 256, (512, 188), dtype=np.uint8)
+    code = O.rs_encode(msg)
+    for k in range(len(code)):
+        ne = k % 11          # 0..10 byte errors: up to 8 correctable, 9 and 10 not
+        pos = rng.choice(204, ne, replace=False)
+        code[k, pos] ^= rng.integers(1, 256, ne, dtype=np.uint8)
+    want_ts, want_bad, want_nerr, _ = O.rs_decode(code)
+    got_ts, flags = P.rs_decode(code)
+    assert np.array_equal(flags[:, 0] != 0, want_bad)
+    assert np.array_equal(got_ts, want_ts)
+    assert np.array_equal(flags[:, 1], want_nerr)
+    ok = ~want_bad
+    assert np.array_equal(got_ts[ok], msg[ok]) and ok.sum() > 400
+
+
+def test_empty_and_tiny_inputs(product):
+    P = product
+    rx = P.Receiver(fmt="u8", max_batch=1 << 16)
+    rx.push(np.zeros(0, np.uint8))
+    rx.push(np.full(2 * 100, 128, np.uint8))
+    rx.push(np.full(2 * 5000, 128, np.uint8))
+    assert rx.pull_all().shape[0] == 0
+    with pytest.raises(P.LdvbError):
+        rx.push(np.zeros(2 * ((1 << 16) + 1), np.uint8))
+    rx.close()

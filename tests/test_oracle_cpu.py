@@ -1,0 +1,148 @@
+"""The oracle (plain-C restatement) pinned against the reference:
+  * committed golden vectors made by the unmodified reference binaries,
+  * when oracle/_ref is present, stage-by-stage streams tapped from the reference
+    runnables (oracle/ref_tap.cc) on freshly generated vectors.
+CPU only; sized to run in well under a minute."""
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import vectors as V
+from tests.conftest import ROOT
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _golden_iq():
+    return np.fromfile(os.path.join(GOLDEN, "c1_160.u8"), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("c1_160.ts", {}),
+    ("c1_160_resample.ts", {"resample": True}),
+    ("c1_160_anf0.ts", {"anf": 0}),
+])
+def test_oracle_ts_equals_reference_golden(oracle, name, kw):
+    O = oracle
+    want = np.fromfile(os.path.join(GOLDEN, name), dtype=np.uint8).reshape(-1, 188)
+    got = O.Chain(O.Config(fmt="u8", **kw)).run(_golden_iq())["ts"]
+    n = min(len(got), len(want))
+    assert n >= 80
+    assert np.array_equal(got[:n], want[:n])
+    # one-shot schedule drains at most one more packet than the reference's default buffers
+    assert 0 <= len(got) - len(want) <= 1
+
+
+def test_oracle_taps_equal_reference_golden_digests(oracle):
+    O = oracle
+    g = json.load(open(os.path.join(GOLDEN, "c1_160_taps.json")))
+    t = O.Chain(O.Config(fmt="u8")).run(_golden_iq())
+    for key, fname in (("pp", "pp.cf32"), ("symbols", "symbols.bin"), ("mpegbytes", "mpegbytes.u8"),
+                       ("rspackets", "rspackets.u8"), ("rtspackets", "rtspackets.u8"),
+                       ("sampled", "sampled.cf32")):
+        b = np.ascontiguousarray(t[key]).tobytes()[: g[fname]["bytes"]]
+        assert len(b) == g[fname]["bytes"], key
+        assert hashlib.sha256(b).hexdigest() == g[fname]["sha256"], key
+    b = t["bytes"].tobytes()[: g["bytes.u8"]["bytes"]]   # reference keeps a <32-byte tail unread
+    assert hashlib.sha256(b).hexdigest() == g["bytes.u8"]["sha256"]
+
+
+def test_loopback_identity(oracle):
+    """leantsgen packets carry their own counter: decoded TS must be a contiguous slice
+    of what was transmitted (BER 0), SURVEY.md 8c."""
+    O = oracle
+    ts = O.Chain(O.Config(fmt="u8")).run(_golden_iq())["ts"]
+    sent = V.ts_packets(160)
+    first = int(ts[3, 1]) << 16 | int(ts[3, 2]) << 8 | int(ts[3, 3])
+    k = len(ts) - 3
+    assert np.array_equal(ts[3:], sent[first:first + k])
+
+
+def test_rs_roundtrip_and_limits(oracle):
+    O = oracle
+    rng = np.random.default_rng(1)
+    msg = rng.integers(0, 256, (64, 188), dtype=np.uint8)
+    code = O.rs_encode(msg)
+    ts, bad, nerr, _ = O.rs_decode(code)
+    assert not bad.any() and np.array_equal(ts, msg) and nerr.sum() == 0
+    for nerrs in (1, 4, 8):
+        c = code.copy()
+        for k in range(len(c)):
+            pos = rng.choice(204, nerrs, replace=False)
+            c[k, pos] ^= rng.integers(1, 256, nerrs, dtype=np.uint8)
+        ts, bad, nerr, _ = O.rs_decode(c)
+        assert not bad.any() and np.array_equal(ts, msg)
+    c = code.copy()
+    for k in range(len(c)):
+        pos = rng.choice(204, 9, replace=False)
+        c[k, pos] ^= rng.integers(1, 256, 9, dtype=np.uint8)
+    ts, bad, nerr, _ = O.rs_decode(c)
+    assert bad.all()                       # beyond t = 8: flagged, first byte marked with 0x55
+    gen = np.fromfile(os.path.join(GOLDEN, "rs_gen.u8"), dtype=np.uint8)
+    assert np.array_equal(O.rs_tables()[2], gen)
+
+
+needs_ref = pytest.mark.skipif(not V.have_ref(), reason="oracle/_ref binaries not built")
+
+CASES = [
+    ("f32-default", "f32", [], dict(fmt="f32"), {}),
+    ("f32-resample", "f32", ["--resample"], dict(fmt="f32", resample=True), {}),
+    ("u8-anf2-derot", "u8", ["--anf", "2", "--derotate", "20000"], dict(fmt="u8", anf=2, Fderot=20000), {}),
+    ("f32-rrc", "f32", ["--sampler", "rrc"], dict(fmt="f32", sampler="rrc"), {}),
+    ("f32-noise", "f32", [], dict(fmt="f32"), dict(noise_db=22)),
+    ("f32-viterbi-noise", "f32", ["--viterbi"], dict(fmt="f32", viterbi=True), dict(noise_db=25)),
+    ("f32-decim2", "f32", ["--anf", "0", "--decim", "2", "-f", "4800e3"], dict(fmt="f32", anf=0, decim=2, Fs=4.8e6),
+     dict(ratio="12/5")),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,fmt,flags,okw,gkw", CASES, ids=[c[0] for c in CASES])
+def test_oracle_stages_equal_reference_taps(oracle, name, fmt, flags, okw, gkw):
+    O = oracle
+    raw = V.ref_iq(260, fmt=fmt, **gkw)
+    d = tempfile.mkdtemp()
+    ts_ref = subprocess.run([O.ref_bin("ref_tap"), "--" + fmt, *flags, "--tap-dir", d], input=raw.tobytes(),
+                            stdout=subprocess.PIPE, check=True).stdout
+    t = O.Chain(O.Config(**okw)).run(raw)
+    for key, f in (("pp", "pp.cf32"), ("symbols", "symbols.bin"), ("bytes", "bytes.u8"),
+                   ("mpegbytes", "mpegbytes.u8"), ("rspackets", "rspackets.u8"), ("sampled", "sampled.cf32"),
+                   ("lock", "lock.i32")):
+        a = np.ascontiguousarray(t[key]).reshape(-1).view(np.uint8)
+        b = np.fromfile(os.path.join(d, f), dtype=np.uint8)
+        n = min(a.size, b.size)
+        assert n > 0 and np.array_equal(a[:n], b[:n]), f"{name}: {key} differs"
+        assert a.size >= b.size and a.size - b.size <= 64 * max(1, a.itemsize), f"{name}: {key} length"
+    # RS output: identical on packets the decoder accepts; packets it gives up on depend on
+    # an uninitialised table entry in the reference (rs.h:53-60 never writes lut_log[0]).
+    ref_rts = np.fromfile(os.path.join(d, "rtspackets.u8"), dtype=np.uint8).reshape(-1, 188)
+    n = min(len(ref_rts), len(t["rtspackets"]))
+    good = ~t["rs_bad"][:n]
+    assert np.array_equal(t["rtspackets"][:n][good], ref_rts[:n][good])
+    ts = t["ts"].tobytes()
+    n = min(len(ts), len(ts_ref))
+    assert n > 0 and ts[:n] == ts_ref[:n]
+    assert 0 <= len(ts) - len(ts_ref) <= 188
+
+
+@needs_ref
+def test_oracle_notch_detect_path(oracle):
+    """>4 Mi samples so that auto_notch::detect() (sdr.h:76-118) runs once."""
+    O = oracle
+    raw = V.ref_iq(2250, fmt="u8")
+    assert raw.size // 2 > 1024 * 4096 + 8192
+    d = tempfile.mkdtemp()
+    ts_ref = subprocess.run([O.ref_bin("ref_tap"), "--u8", "--tap-dir", d], input=raw.tobytes(),
+                            stdout=subprocess.PIPE, check=True).stdout
+    t = O.Chain(O.Config(fmt="u8")).run(raw)
+    b = np.fromfile(os.path.join(d, "pp.cf32"), dtype=np.uint8)
+    a = t["pp"].view(np.uint8)
+    assert np.array_equal(a[:b.size], b)
+    st = open(os.path.join(d, "state.txt")).read()
+    assert "notch.slot0 -1" not in st           # a bin was selected
+    assert t["ts"].tobytes()[:len(ts_ref)] == ts_ref
