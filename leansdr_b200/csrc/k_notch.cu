@@ -129,77 +129,168 @@ k_notch_detect(NotchDetectArgs a) {
 }
 
 // ---------------------------------------------------------------------- apply
-__global__ void __launch_bounds__(64)
-k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
-  uint32_t seg = (only_segment >= 0) ? (uint32_t)only_segment : blockIdx.x * blockDim.x + threadIdx.x;
-  if (only_segment >= 0 && (blockIdx.x != 0 || threadIdx.x != 0)) return;
-  if (seg >= a.nsegs) return;
-  const uint64_t own_begin = (uint64_t)seg * a.seg_blocks;
-  uint64_t own_end = own_begin + a.seg_blocks;
-  if (own_end > a.nblocks) own_end = a.nblocks;
+// One lane = one segment.  The 32 lanes of a warp walk 32 segments in lock step;
+// each lane stages ITS next 64 raw samples in a private shared-memory row with
+// one TMA bulk copy per tile (double buffered, mbarrier-signalled), converts on
+// the fly and streams its results out.
+constexpr int kNTile = 64;
+constexpr int kNPitch = 528;          // row pitch: (64 + 2) cf32, = 16 (mod 128) bytes
+constexpr int kNStages = 2;
+constexpr int kNWarps = 2;
 
-  // Epoch at the start of the owned region, and whether it begins with a reset.
-  int ep = 0;
-  while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= own_begin) ++ep;
-  float er[kNotchMaxSlots], ei[kNotchMaxSlots];
-  bool exact = false;
-  uint64_t run_begin = own_begin;
-  if (forced_entry) {
-    for (int s = 0; s < a.nslots; ++s) { er[s] = forced_entry[s].x; ei[s] = forced_entry[s].y; }
-    exact = true;
-  } else if (seg == 0) {
-    for (int s = 0; s < a.nslots; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
-    exact = true;
-  } else {
-    // Warm-up from a zero estimate, clamped to the epoch start (tables change there).
-    uint64_t wb = (own_begin > a.warm_blocks) ? own_begin - a.warm_blocks : 0;
-    if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
-    run_begin = wb;
-    for (int s = 0; s < a.nslots; ++s) { er[s] = 0.f; ei[s] = 0.f; }
-    // Known-exact start: the segment begins exactly at an epoch whose slots all reset,
-    // or the warm-up reaches back to block 0 of the batch... (only resets are exact).
-    if (a.epochs[ep].first_block == own_begin) {
-      bool all = true;
-      for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
-      exact = all;
-    }
+__device__ __forceinline__ float2 row_sample(const unsigned char *row, int fmt, uint32_t idx, float scale) {
+  switch (fmt) {
+    case 0: { uchar2 v = reinterpret_cast<const uchar2 *>(row)[idx];
+      return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+    case 1: { char2 v = reinterpret_cast<const char2 *>(row)[idx];
+      return make_float2((float)(int)v.x, (float)(int)v.y); }
+    case 2: { ushort2 v = reinterpret_cast<const ushort2 *>(row)[idx];
+      return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768)); }
+    case 3: { short2 v = reinterpret_cast<const short2 *>(row)[idx];
+      return make_float2((float)(int)v.x, (float)(int)v.y); }
+    case 4: { float2 v = reinterpret_cast<const float2 *>(row)[idx];
+      return make_float2(fmul(v.x, scale), fmul(v.y, scale)); }
+    default: return reinterpret_cast<const float2 *>(row)[idx];
   }
-  const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
-
-  for (uint64_t blk = run_begin; blk < own_end; ++blk) {
-    // Epoch switch (only possible at own_begin or later; warm-up is clamped).
-    while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= blk) ++ep;
-    if (a.epochs[ep].first_block == blk) {
-      for (int s = 0; s < a.nslots; ++s)
-        if (a.epochs[ep].reset[s]) { er[s] = 0.f; ei[s] = 0.f; }
-    }
-    if (blk == own_begin && a.seg_entry)
-      for (int s = 0; s < a.nslots; ++s) a.seg_entry[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
-    const bool write = (blk >= own_begin);
-    const uint64_t base = blk * (uint64_t)kNotchN;
-    const float2 *tab[kNotchMaxSlots];
-    for (int s = 0; s < a.nslots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN;
-    for (int n = 0; n < kNotchN; ++n) {
-      const float2 x = load_sample(a.src, a.fmt, base + n, a.scale);
-      float outr = x.x, outi = x.y;
-      for (int s = 0; s < a.nslots; ++s) {
-        const float2 e = __ldg(tab[s] + n);
-        const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
-        const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
-        er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
-        ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
-        const float subr = fsub(fmul(er[s], e.x), fmul(ei[s], e.y));
-        const float subi = fadd(fmul(er[s], e.y), fmul(ei[s], e.x));
-        outr = fsub(outr, subr);
-        outi = fsub(outi, subi);
-      }
-      if (write) a.out[base + n] = make_float2(fmul(gain, outr), fmul(gain, outi));
-    }
-  }
-  if (a.seg_exit)
-    for (int s = 0; s < a.nslots; ++s) a.seg_exit[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
-  if (a.seg_exact && !forced_entry) a.seg_exact[seg] = exact ? 1 : 0;
 }
+
+__global__ void __launch_bounds__(kNWarps * 32)
+k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[kNWarps * kNStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warp_global = blockIdx.x * kNWarps + warp;
+  uint32_t seg; bool have;
+  if (only_segment >= 0) { seg = (uint32_t)only_segment; have = (warp_global == 0 && lane == 0); }
+  else { seg = warp_global * 32 + lane; have = seg < a.nsegs; }
+
+  uint64_t own_begin = 0, own_end = 0, run_begin = 0;
+  int ep = 0;
+  float er[kNotchMaxSlots], ei[kNotchMaxSlots];
+  for (int s = 0; s < kNotchMaxSlots; ++s) { er[s] = 0.f; ei[s] = 0.f; }
+  bool exact = false;
+  if (have) {
+    own_begin = (uint64_t)seg * a.seg_blocks;
+    own_end = own_begin + a.seg_blocks;
+    if (own_end > a.nblocks) own_end = a.nblocks;
+    while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= own_begin) ++ep;
+    run_begin = own_begin;
+    if (forced_entry) {
+      for (int s = 0; s < a.nslots; ++s) { er[s] = forced_entry[s].x; ei[s] = forced_entry[s].y; }
+      exact = true;
+    } else if (seg == 0) {
+      for (int s = 0; s < a.nslots; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
+      exact = true;
+    } else {
+      // Warm-up from a zero estimate; never across an epoch start (tables change there).
+      uint64_t wb = (own_begin > a.warm_blocks) ? own_begin - a.warm_blocks : 0;
+      if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
+      run_begin = wb;
+      if (wb == 0 && a.epochs[ep].first_block == 0 && ep == 0) {
+        // The warm-up reaches the start of the batch inside the first epoch: start
+        // from the true carried state instead of zero (exact).
+        for (int s = 0; s < a.nslots; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
+        exact = true;
+      } else if (a.epochs[ep].first_block == wb) {
+        bool all = true;   // every slot is reset at this epoch start: exact zero state
+        for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
+        exact = all;
+      }
+    }
+  }
+  // Common iteration space: local block i -> block = base + i.
+  int64_t base; uint64_t iters;
+  if (only_segment >= 0) { base = (int64_t)run_begin; iters = own_end - run_begin; }
+  else { base = (int64_t)((uint64_t)seg * a.seg_blocks) - (int64_t)a.warm_blocks; iters = (uint64_t)a.warm_blocks + a.seg_blocks; }
+  iters = __shfl_sync(0xffffffffu, iters, 0);
+
+  unsigned char *smem_warp = smem + (size_t)warp * kNStages * 32 * kNPitch;
+  unsigned char *row[kNStages];
+  for (int s = 0; s < kNStages; ++s) row[s] = smem_warp + (size_t)s * 32 * kNPitch + (size_t)lane * kNPitch;
+  uint64_t *full = bars + warp * kNStages;
+  if (lane == 0) {
+    for (int s = 0; s < kNStages; ++s) mbar_init(&full[s], 32);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const uint32_t bps = (a.fmt <= 1) ? 2u : (a.fmt <= 3 ? 4u : 8u);
+  const uint32_t align_elems = 16 / bps;
+  constexpr int kTilesPerBlock = kNotchN / kNTile;
+  const uint64_t total_tiles = iters * kTilesPerBlock;
+  uint32_t lead_of_stage[kNStages] = {0, 0};
+  auto issue = [&](uint64_t tile) {
+    const int st = (int)(tile % kNStages);
+    const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
+    const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
+    if (active) {
+      uint64_t idx = (uint64_t)blk * kNotchN + (tile % kTilesPerBlock) * kNTile;
+      const unsigned char *part = static_cast<const unsigned char *>(a.src.head);
+      if (a.src.main && idx >= a.src.c0) { part = static_cast<const unsigned char *>(a.src.main); idx -= a.src.c0; }
+      const uint64_t al = idx & ~(uint64_t)(align_elems - 1);
+      const uint32_t lead = (uint32_t)(idx - al);
+      const uint32_t bytes = ((lead + kNTile) * bps + 15u) & ~15u;
+      lead_of_stage[st] = lead;
+      mbar_expect_tx(&full[st], bytes);
+      tma_load_1d(row[st], part + al * bps, bytes, &full[st]);
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");
+    }
+  };
+
+  const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
+  for (uint64_t t = 0; t < (uint64_t)kNStages - 1 && t < total_tiles; ++t) issue(t);
+  for (uint64_t tile = 0; tile < total_tiles; ++tile) {
+    if (tile + kNStages - 1 < total_tiles) issue(tile + kNStages - 1);
+    const int st = (int)(tile % kNStages);
+    mbar_wait(&full[st], (uint32_t)((tile / kNStages) & 1));
+    const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
+    const int tib = (int)(tile % kTilesPerBlock);
+    const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
+    if (active) {
+      if (tib == 0) {
+        // Block start: epoch switch / resets (sdr.h:97-109), entry snapshot.
+        while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= (uint64_t)blk) ++ep;
+        if ((uint64_t)blk == own_begin && a.seg_entry && !forced_entry)
+          for (int s = 0; s < a.nslots; ++s) a.seg_entry[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+        if (a.epochs[ep].first_block == (uint64_t)blk) {
+          for (int s = 0; s < a.nslots; ++s)
+            if (a.epochs[ep].reset[s]) { er[s] = 0.f; ei[s] = 0.f; }
+        }
+      }
+      const bool write = ((uint64_t)blk >= own_begin);
+      const float2 *tab[kNotchMaxSlots];
+      for (int s = 0; s < a.nslots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
+      float2 *outp = a.out + (uint64_t)blk * kNotchN + (uint64_t)tib * kNTile;
+      const uint32_t lead = lead_of_stage[st];
+#pragma unroll 4
+      for (int n = 0; n < kNTile; ++n) {
+        const float2 x = row_sample(row[st], a.fmt, lead + n, a.scale);
+        float outr = x.x, outi = x.y;
+        for (int s = 0; s < a.nslots; ++s) {
+          const float2 e = __ldg(tab[s] + n);
+          const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
+          const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
+          er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
+          ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
+          const float subr = fsub(fmul(er[s], e.x), fmul(ei[s], e.y));
+          const float subi = fadd(fmul(er[s], e.y), fmul(ei[s], e.x));
+          outr = fsub(outr, subr);
+          outi = fsub(outi, subi);
+        }
+        if (write) st_stream(outp + n, make_float2(fmul(gain, outr), fmul(gain, outi)));
+      }
+    }
+    __syncwarp();
+  }
+  if (have) {
+    if (a.seg_exit)
+      for (int s = 0; s < a.nslots; ++s) a.seg_exit[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+    if (a.seg_exact && !forced_entry) a.seg_exact[seg] = exact ? 1 : 0;
+  }
+}
+
+constexpr size_t kNotchSmem = (size_t)kNWarps * kNStages * 32 * kNPitch;
 
 }  // namespace
 
@@ -212,8 +303,15 @@ cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st) {
 cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
                                cudaStream_t st) {
   if (a.nsegs == 0 || a.nblocks == 0) return cudaSuccess;
-  if (only_segment >= 0) k_notch_apply<<<1, 32, 0, st>>>(a, only_segment, forced_entry);
-  else k_notch_apply<<<(a.nsegs + 31) / 32, 32, 0, st>>>(a, -1, nullptr);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_notch_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNotchSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const unsigned per_block = kNWarps * 32;
+  if (only_segment >= 0) k_notch_apply<<<1, per_block, kNotchSmem, st>>>(a, only_segment, forced_entry);
+  else k_notch_apply<<<(a.nsegs + per_block - 1) / per_block, per_block, kNotchSmem, st>>>(a, -1, nullptr);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,8 @@ struct Stream {
 
 struct HypState { uint64_t reg = 0, acc = 0; int n_in = 0, n_out = 0; };
 
+constexpr uint64_t kRxTargetSpans = 56 * 1024;  // ~ resident lanes of k_rx on 148 SMs
+
 struct Tap {
   DevBuf buf;
   uint64_t bytes = 0;
@@ -112,7 +114,8 @@ struct ldvb_handle {
   RxState rx_state;            // host mirror of the exact/carried receiver state
   DevBuf d_rx_state, d_rx_info, d_rx_end, d_rx_head, d_rx_tail, d_rx_seams, d_rx_spans;
   DevBuf d_rx_off, d_rx_skip, d_rx_rot, d_rx_meas, d_rx_measn, d_rx_forced;
-  uint32_t rx_max_spans = 1, rx_span_cap = 0;
+  uint32_t rx_max_spans = 1;
+  double rx_sym_per_sample = 1;
   HypState hyp[4];
   int locked = 0, skip = 0;
   DevBuf d_deconv_carry;
@@ -501,14 +504,18 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   if ((rc = stream_alloc(h, h->s_bytes, 1, bytes_max + 4096))) return bail(rc, h->err.c_str());
   if ((rc = stream_alloc(h, h->s_mpeg, 1, bytes_max + 8192))) return bail(rc, h->err.c_str());
   h->ts_cap = pk_max;
-  // Receiver spans
-  uint32_t span_chunks = c.span_chunks ? c.span_chunks : 256;
+  // Receiver spans (FAST): sized for the shortest span the auto rule can pick.
+  h->rx_sym_per_sample = sym_per_sample;
   uint32_t nsp = 1;
-  if (c.rx_mode == LDVB_RX_FAST) nsp = (uint32_t)((pp_max / kRxChunk + span_chunks - 1) / span_chunks) + 1;
+  size_t span_bytes = 64;
+  if (c.rx_mode == LDVB_RX_FAST) {
+    const uint64_t nch = pp_max / kRxChunk + 1;
+    const uint32_t smin = c.span_chunks ? c.span_chunks : 4;
+    nsp = (uint32_t)(nch / smin + 2);
+    const double cap_min = (smin + kRxVerifyChunks + 1) * kRxChunk * sym_per_sample + 64;
+    span_bytes = (size_t)(std::max((double)nsp * cap_min, 1.25 * sym_max) * 4) + 4096;
+  }
   h->rx_max_spans = nsp;
-  h->rx_span_cap = (c.rx_mode == LDVB_RX_FAST)
-                       ? (uint32_t)((span_chunks + kRxVerifyChunks + 1) * kRxChunk * sym_per_sample) + 64
-                       : 0;
   bool aok =
       h->d_rts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_rsflags.alloc(pk_max * 8 + 64) == cudaSuccess &&
       h->d_ts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_scratch.alloc(std::max<uint64_t>(pk_max * 8 + 4096, 1 << 20)) == cudaSuccess &&
@@ -518,7 +525,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
       h->d_rx_head.alloc(sizeof(RxSeamSym) * kRxSeamLog * (size_t)nsp) == cudaSuccess &&
       h->d_rx_tail.alloc(sizeof(RxSeamSym) * kRxSeamLog * (size_t)nsp) == cudaSuccess &&
       h->d_rx_seams.alloc(sizeof(RxSeam) * nsp) == cudaSuccess &&
-      h->d_rx_spans.alloc((size_t)h->rx_span_cap * nsp * 4 + 64) == cudaSuccess &&
+      h->d_rx_spans.alloc(span_bytes) == cudaSuccess &&
       h->d_rx_off.alloc(8 * ((size_t)nsp + 1)) == cudaSuccess && h->d_rx_skip.alloc(4 * (size_t)nsp) == cudaSuccess &&
       h->d_rx_rot.alloc(nsp) == cudaSuccess && h->d_rx_meas.alloc(16 * 4096) == cudaSuccess &&
       h->d_rx_measn.alloc(4) == cudaSuccess && h->d_rx_forced.alloc(sizeof(RxState)) == cudaSuccess &&
@@ -706,8 +713,12 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   a.expj_tables = h->d_notch_tables.as<float2>();
   a.epochs = h->d_notch_epochs.as<NotchEpoch>();
   a.nepochs = (int)epochs.size();
-  a.seg_blocks = 8;     // 32 Ki samples owned per segment
-  a.warm_blocks = 6;    // 24 Ki samples of warm-up: 0.998^24576 ~ 4e-22
+  // Segment size: as many concurrent segments as the stream allows (the kernel is
+  // latency bound per lane), 4 blocks (16 Ki samples) of warm-up: from a zero
+  // estimate the float trajectories merge bit for bit after 4..10 Ki samples
+  // (0.998^n decay below one ulp), measured in DESIGN.md.
+  a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 16383) / 16384));
+  a.warm_blocks = 4;
   a.nsegs = (uint32_t)((nblocks + a.seg_blocks - 1) / a.seg_blocks);
   a.state_in = h->d_notch_state.as<NotchState>();
   a.seg_entry = h->d_notch_entry.as<float2>();
@@ -850,13 +861,18 @@ int run_receiver(ldvb_handle *h) {
       smp.release(); smpf.release();
     }
   } else {
-    const uint32_t S = c.span_chunks ? c.span_chunks : 256;
-    const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 64;
+    // Span length: fill the machine (one lane per span, ~57 K resident lanes), at
+    // least 4 chunks; 4 chunks of warm-up (timing and carrier loops re-converge
+    // within ~200 symbols when freqw and the AGC are carried).
+    uint32_t S = c.span_chunks;
+    if (!S) S = (uint32_t)std::max<uint64_t>(4, (nchunks + kRxTargetSpans - 1) / kRxTargetSpans);
+    const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 4;
     a.span_chunks = S;
     a.warm_chunks = W;
     a.nspans = (uint32_t)((nchunks + S - 1) / S);
-    if (a.nspans > h->rx_max_spans) return fail(h, LDVB_EOVERFLOW, "too many receiver spans");
-    a.span_cap = h->rx_span_cap;
+    a.span_cap = (uint32_t)((S + kRxVerifyChunks + 1) * kRxChunk * h->rx_sym_per_sample) + 64;
+    if (a.nspans > h->rx_max_spans || (uint64_t)a.nspans * a.span_cap * 4 > h->d_rx_spans.bytes)
+      return fail(h, LDVB_EOVERFLOW, "receiver span buffers too small for this batch");
     a.sym_out = h->d_rx_spans.as<uint32_t>();
     a.head_log = h->d_rx_head.as<RxSeamSym>();
     a.tail_log = h->d_rx_tail.as<RxSeamSym>();

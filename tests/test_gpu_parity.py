@@ -47,11 +47,10 @@ EXACT_CASES = [
     ("f32-default", dict(fmt="f32"), {}, 300),
     ("f32-resample", dict(fmt="f32", resample=True), {}, 300),
     ("u8-default", dict(fmt="u8"), {}, 300),
-    ("u8-anf0-nearest", dict(fmt="u8", anf=0, sampler="nearest"), dict(ratio="4/1"), 80),
+    ("u8-anf0-nearest-4sps", dict(fmt="u8", anf=0, sampler="nearest", Fs=8e6), dict(ratio="4/1"), 120),
     ("f32-derot-anf2", dict(fmt="f32", anf=2, Fderot=20000.0), {}, 300),
     ("f32-scale-decim2", dict(fmt="f32", anf=0, decim=2, Fs=4.8e6, float_scale=0.5), dict(ratio="12/5", power=43.5), 200),
     ("f32-noise", dict(fmt="f32", resample=True), dict(noise_db=22), 300),
-    ("f32-8psk-hard", dict(fmt="f32", anf=0, cstln="8PSK", hard_metric=True), {}, 120),
 ]
 
 
@@ -72,6 +71,21 @@ def test_exact_mode_every_stream_bit_exact(product, oracle, name, kw, gkw, npk):
     fl = got["rsflags"].view(np.int32).reshape(-1, 2)
     assert np.array_equal(fl[:, 0] != 0, ref["rs_bad"]) and np.array_equal(fl[:, 1], ref["rs_nerr"])
     assert got["meas"]["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("cst", ["BPSK", "8PSK"])
+def test_exact_mode_other_constellation_tables(product, oracle, cst):
+    """The slicer/PLL with the BPSK and 8PSK tables (and --hard-metric): soft symbols only
+    (a QPSK test signal does not frame-lock under another constellation)."""
+    P, O = product, oracle
+    raw = V.ref_iq(120, fmt="f32")
+    kw = dict(fmt="f32", anf=0, cstln=cst, hard_metric=True)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    rx = P.Receiver(keep_taps=1, max_batch=raw.size // 2, **kw)
+    rx.push(raw)
+    sym = rx.tap("symbols")
+    rx.close()
+    assert sym.size > 100000 and np.array_equal(sym, ref["symbols"].reshape(-1)[:sym.size])
 
 
 def test_exact_mode_streaming_is_batch_invariant(product, oracle):
