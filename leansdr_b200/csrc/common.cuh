@@ -72,6 +72,20 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
       : "memory");
 }
 
+// 16-byte asynchronous copies global -> shared (SASS LDGSTS), L1-bypassing.
+// Used where each lane of a warp walks its own place in a stream: rows of a few
+// hundred bytes are too small for the TMA engine (measured: ~0.6 us per 272-byte
+// cp.async.bulk request, serialised per SM), so the 32 rows of a warp are
+// fetched cooperatively, 16 B per lane per instruction, contiguous within a row.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Streaming stores: results are written once and read by a later kernel.
 __device__ __forceinline__ void st_stream(float2 *p, float2 v) { __stcs(p, v); }
 

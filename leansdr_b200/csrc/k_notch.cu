@@ -130,9 +130,9 @@ k_notch_detect(NotchDetectArgs a) {
 
 // ---------------------------------------------------------------------- apply
 // One lane = one segment.  The 32 lanes of a warp walk 32 segments in lock step;
-// each lane stages ITS next 64 raw samples in a private shared-memory row with
-// one TMA bulk copy per tile (double buffered, mbarrier-signalled), converts on
-// the fly and streams its results out.
+// per tile the warp stages every lane's next 64 raw samples in a private
+// shared-memory row (cooperative 16-byte cp.async copies, contiguous within a
+// row, double buffered); lanes convert on the fly and stream their results out.
 constexpr int kNTile = 64;
 constexpr int kNPitch = 528;          // row pitch: (64 + 2) cf32, = 16 (mod 128) bytes
 constexpr int kNStages = 2;
@@ -205,45 +205,54 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
   iters = __shfl_sync(0xffffffffu, iters, 0);
 
   unsigned char *smem_warp = smem + (size_t)warp * kNStages * 32 * kNPitch;
-  unsigned char *row[kNStages];
-  for (int s = 0; s < kNStages; ++s) row[s] = smem_warp + (size_t)s * 32 * kNPitch + (size_t)lane * kNPitch;
-  uint64_t *full = bars + warp * kNStages;
-  if (lane == 0) {
-    for (int s = 0; s < kNStages; ++s) mbar_init(&full[s], 32);
-    mbar_fence_init();
-  }
-  __syncwarp();
+  unsigned char *stage_base[kNStages];
+  for (int s = 0; s < kNStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kNPitch;
+  (void)bars;
+  // Row r of the warp = lane r's segment; its block at local iteration i is base_r + i.
+  const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
+  const int64_t base_step = (only_segment >= 0) ? 0 : (int64_t)a.seg_blocks;
 
   const uint32_t bps = (a.fmt <= 1) ? 2u : (a.fmt <= 3 ? 4u : 8u);
   const uint32_t align_elems = 16 / bps;
   constexpr int kTilesPerBlock = kNotchN / kNTile;
   const uint64_t total_tiles = iters * kTilesPerBlock;
-  uint32_t lead_of_stage[kNStages] = {0, 0};
+  // Where sample `idx` of the two-part stream lives, aligned down to 16 bytes.
+  auto locate = [&](uint64_t idx, const unsigned char *&src, uint32_t &lead) {
+    const unsigned char *part = static_cast<const unsigned char *>(a.src.head);
+    if (a.src.main && idx >= a.src.c0) { part = static_cast<const unsigned char *>(a.src.main); idx -= a.src.c0; }
+    const uint64_t al = idx & ~(uint64_t)(align_elems - 1);
+    lead = (uint32_t)(idx - al);
+    src = part + al * bps;
+  };
+  const int n16_max = (int)(((kNTile + align_elems) * bps + 15u) / 16u);
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kNStages);
-    const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
+    const uint64_t i = tile / kTilesPerBlock;
+    const int64_t blk = base + (int64_t)i;
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
-    if (active) {
-      uint64_t idx = (uint64_t)blk * kNotchN + (tile % kTilesPerBlock) * kNTile;
-      const unsigned char *part = static_cast<const unsigned char *>(a.src.head);
-      if (a.src.main && idx >= a.src.c0) { part = static_cast<const unsigned char *>(a.src.main); idx -= a.src.c0; }
-      const uint64_t al = idx & ~(uint64_t)(align_elems - 1);
-      const uint32_t lead = (uint32_t)(idx - al);
-      const uint32_t bytes = ((lead + kNTile) * bps + 15u) & ~15u;
-      lead_of_stage[st] = lead;
-      mbar_expect_tx(&full[st], bytes);
-      tma_load_1d(row[st], part + al * bps, bytes, &full[st]);
-    } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    const uint64_t col0 = (tile % kTilesPerBlock) * kNTile;
+    const int total = 32 * n16_max;
+    for (int id = lane; id < total; id += 32) {
+      const int r = id / n16_max, q = id - r * n16_max;
+      if ((mask >> r) & 1u) {
+        const uint64_t idx = (uint64_t)(base0 + (int64_t)r * base_step + (int64_t)i) * kNotchN + col0;
+        const unsigned char *src; uint32_t lead;
+        locate(idx, src, lead);
+        const int n16 = (int)(((lead + kNTile) * bps + 15u) / 16u);
+        if (q < n16) cp_async16(stage_base[st] + (size_t)r * kNPitch + q * 16, src + q * 16);
+      }
     }
+    cp_async_commit();
   };
 
   const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
-  for (uint64_t t = 0; t < (uint64_t)kNStages - 1 && t < total_tiles; ++t) issue(t);
+  if (total_tiles) issue(0);
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
-    if (tile + kNStages - 1 < total_tiles) issue(tile + kNStages - 1);
+    if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncwarp();
     const int st = (int)(tile % kNStages);
-    mbar_wait(&full[st], (uint32_t)((tile / kNStages) & 1));
     const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
     const int tib = (int)(tile % kTilesPerBlock);
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
@@ -262,10 +271,11 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
       const float2 *tab[kNotchMaxSlots];
       for (int s = 0; s < a.nslots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
       float2 *outp = a.out + (uint64_t)blk * kNotchN + (uint64_t)tib * kNTile;
-      const uint32_t lead = lead_of_stage[st];
+      uint32_t lead; { const unsigned char *unused; locate((uint64_t)blk * kNotchN + (uint64_t)tib * kNTile, unused, lead); }
+      const unsigned char *myrow = stage_base[st] + (size_t)lane * kNPitch;
 #pragma unroll 4
       for (int n = 0; n < kNTile; ++n) {
-        const float2 x = row_sample(row[st], a.fmt, lead + n, a.scale);
+        const float2 x = row_sample(myrow, a.fmt, lead + n, a.scale);
         float outr = x.x, outi = x.y;
         for (int s = 0; s < a.nslots; ++s) {
           const float2 e = __ldg(tab[s] + n);

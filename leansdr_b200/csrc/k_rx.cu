@@ -16,12 +16,14 @@
 //               k_rx_stitch can align, de-rotate and VERIFY neighbouring spans.
 //
 // Data movement: the 32 lanes of a warp walk 32 different places of the IQ
-// stream in lock step.  Every lane brings ITS next 32 samples (+2 look-ahead)
-// into a private shared-memory row with one TMA bulk copy (cp.async.bulk, SASS
-// UBLKCP) per tile, double buffered and signalled on an mbarrier; the row pitch
-// (272 B) makes the 16-byte row reads of the 32 lanes bank-conflict free.  HBM
-// therefore sees only full, aligned 272-byte bursts and the recurrence never
-// waits on a global load.  The two tables (trig16, cstln: 512 KB each) are read
+// stream in lock step.  Per tile the warp stages, for every lane, that lane's
+// next 32 samples (+2 look-ahead) in a private shared-memory row: 32 rows x
+// 272 B, fetched cooperatively with 16-byte asynchronous copies (cp.async.cg,
+// SASS LDGSTS; contiguous within a row), double buffered.  The row pitch (272 B)
+// makes the 16-byte row reads of the 32 lanes bank-conflict free.  HBM sees
+// full, aligned 272-byte bursts and the recurrence never waits on a global
+// load.  (One TMA bulk copy per row was measured first: ~0.6 us per 272-byte
+// request, serialised per SM -- rows this small are below the TMA's grain.)  The two tables (trig16, cstln: 512 KB each) are read
 // through the read-only path; their accesses cluster around the current carrier
 // phase and the constellation points.
 #include "common.cuh"
@@ -212,27 +214,33 @@ __device__ void rx_warp(const RxArgs &a, int only_span, const RxState *forced, u
   else { base = (int64_t)((uint64_t)span * S) - (int64_t)W; iters = W + S + kRxVerifyChunks; }
   iters = __shfl_sync(0xffffffffu, iters, 0);
 
-  unsigned char *row[kStages];
-  for (int s = 0; s < kStages; ++s) row[s] = smem_warp + (size_t)s * 32 * kRowBytes + (size_t)lane * kRowBytes;
-  uint64_t *full = bars;  // [kStages], one arrival per lane
-  if (lane == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 32);
-    mbar_fence_init();
-  }
-  __syncwarp();
+  unsigned char *stage_base[kStages];
+  for (int s = 0; s < kStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kRowBytes;
+  // Row r of the warp = lane r's span; its chunk at local iteration i is base_r + i.
+  const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
+  const int64_t base_step = (only_span >= 0) ? 0 : (int64_t)S;
+  (void)bars;
 
   const uint64_t total_tiles = iters * kTilesPerChunk;
+  constexpr int kChunks16 = kRowBytes / 16;  // 17 x 16 B per row
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kStages);
-    const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
+    const uint64_t i = tile / kTilesPerChunk;
+    const int64_t c = base + (int64_t)i;
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
-    if (active) {
-      const float2 *src = a.x + (uint64_t)c * kRxChunk + (tile % kTilesPerChunk) * kTile;
-      mbar_expect_tx(&full[st], kRowBytes);
-      tma_load_1d(row[st], src, kRowBytes, &full[st]);
-    } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    const uint64_t col0 = (tile % kTilesPerChunk) * kTile;
+#pragma unroll
+    for (int k = 0; k < kChunks16; ++k) {
+      const int id = k * 32 + lane;
+      const int r = id / kChunks16, q = id - r * kChunks16;
+      if ((mask >> r) & 1u) {
+        const int64_t cr = base0 + (int64_t)r * base_step + (int64_t)i;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + (uint64_t)cr * kRxChunk + col0) + q * 16;
+        cp_async16(stage_base[st] + (size_t)r * kRowBytes + q * 16, src);
+      }
     }
+    cp_async_commit();
   };
 
   uint32_t *out = a.sym_out + (size_t)span * a.span_cap;
@@ -241,18 +249,19 @@ __device__ void rx_warp(const RxArgs &a, int only_span, const RxState *forced, u
   uint32_t n_out = 0, n_tail = 0, n_head = 0;
   const uint32_t cap = a.span_cap;
 
-  for (uint64_t t = 0; t < (uint64_t)kStages - 1 && t < total_tiles; ++t) issue(t);
+  if (total_tiles) issue(0);
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
-    if (tile + kStages - 1 < total_tiles) issue(tile + kStages - 1);
+    if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncwarp();   // every lane's copies of this stage are visible to the whole warp
     const int st = (int)(tile % kStages);
-    mbar_wait(&full[st], (uint32_t)((tile / kStages) & 1));
     const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
     const int tic = (int)(tile % kTilesPerChunk);
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
     if (active) {
       const int phase_of_run = ((uint64_t)c < own_begin) ? 0 : ((uint64_t)c < own_end ? 1 : 2);
       if (tic == 0) rx_chunk_begin(r, SAMPLER);
-      const float4 *rp = reinterpret_cast<const float4 *>(row[st]);
+      const float4 *rp = reinterpret_cast<const float4 *>(stage_base[st] + (size_t)lane * kRowBytes);
       float4 w = rp[0];
       float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
       const float t_head = (float)(((int64_t)c - (int64_t)own_begin) * kRxChunk + tic * kTile);

@@ -244,9 +244,14 @@ int stream_consume(ldvb_handle *h, Stream &s, uint64_t n, DevBuf &tmp) {
     if (left <= n) {
       CK(cudaMemcpyAsync(s.at(0), s.at(n), left * s.elem, cudaMemcpyDeviceToDevice, h->st));
     } else {
-      if (tmp.bytes < left * s.elem) return fail(h, LDVB_EOVERFLOW, "carry larger than scratch");
-      CK(cudaMemcpyAsync(tmp.p, s.at(n), left * s.elem, cudaMemcpyDeviceToDevice, h->st));
-      CK(cudaMemcpyAsync(s.at(0), tmp.p, left * s.elem, cudaMemcpyDeviceToDevice, h->st));
+      // Overlapping move: forward, in pieces staged through the scratch buffer.
+      const uint64_t piece = tmp.bytes / s.elem;
+      if (!piece) return fail(h, LDVB_EOVERFLOW, "no scratch for the carry");
+      for (uint64_t off = 0; off < left; off += piece) {
+        const uint64_t k = std::min(piece, left - off);
+        CK(cudaMemcpyAsync(tmp.p, s.at(n + off), k * s.elem, cudaMemcpyDeviceToDevice, h->st));
+        CK(cudaMemcpyAsync(s.at(off), tmp.p, k * s.elem, cudaMemcpyDeviceToDevice, h->st));
+      }
     }
   }
   s.count = left;
