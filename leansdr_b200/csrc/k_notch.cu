@@ -129,6 +129,105 @@ k_notch_detect(NotchDetectArgs a) {
 }
 
 // ---------------------------------------------------------------------- apply
+// Start-state guess.  The estimate forgets its past with a time constant of
+// 1/k = 500 samples, so the state at any point is, to ~1e-7 relative, the
+// exponentially weighted sum of the last few thousand inputs:
+//   estim(P) ~ sum_{m>=1} (bb[P-m]*k) * (1-k)^(m-1)
+// One warp evaluates that sum for one segment (parallel over m).  The guess is
+// NOT exact; it only has to land within a few ulps so that the exact serial
+// run that follows merges with the true trajectory inside the one warm-up block
+// (measured: median 1000 samples, max < 3000).  Every segment is
+// still verified against its predecessor and re-run when it did not merge.
+constexpr int kGuessWindow = 8192;
+
+template <int FMT>
+__device__ __forceinline__ float2 ld_raw(const RawSrc &src, uint64_t idx, float scale) {
+  const void *raw = src.head;
+  if (src.main && idx >= src.c0) { raw = src.main; idx -= src.c0; }
+  if (FMT == 0) { uchar2 v = reinterpret_cast<const uchar2 *>(raw)[idx];
+    return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+  if (FMT == 1) { char2 v = reinterpret_cast<const char2 *>(raw)[idx];
+    return make_float2((float)(int)v.x, (float)(int)v.y); }
+  if (FMT == 2) { ushort2 v = reinterpret_cast<const ushort2 *>(raw)[idx];
+    return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768)); }
+  if (FMT == 3) { short2 v = reinterpret_cast<const short2 *>(raw)[idx];
+    return make_float2((float)(int)v.x, (float)(int)v.y); }
+  float2 v = __ldg(reinterpret_cast<const float2 *>(raw) + idx);
+  if (FMT == 4) v = make_float2(fmul(v.x, scale), fmul(v.y, scale));
+  return v;
+}
+
+// Segment geometry shared by the guess and apply kernels.
+struct SegPlan {
+  uint64_t own_begin, own_end, run_begin;  // blocks
+  int epoch;                               // epoch of run_begin
+  int start_kind;                          // 0 exact carried state, 1 exact zero (full reset), 2 guess
+};
+
+__device__ __forceinline__ SegPlan plan_segment(const NotchApplyArgs &a, uint32_t seg) {
+  SegPlan p;
+  p.own_begin = (uint64_t)seg * a.seg_blocks;
+  p.own_end = p.own_begin + a.seg_blocks;
+  if (p.own_end > a.nblocks) p.own_end = a.nblocks;
+  int ep = 0;
+  while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= p.own_begin) ++ep;
+  p.epoch = ep;
+  if (seg == 0) { p.run_begin = 0; p.start_kind = 0; return p; }
+  // One warm-up block, never across an epoch start (tables / resets change there).
+  uint64_t wb = (p.own_begin > a.warm_blocks) ? p.own_begin - a.warm_blocks : 0;
+  if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
+  p.run_begin = wb;
+  if (wb == 0 && ep == 0) { p.start_kind = 0; return p; }   // reaches the carried state
+  if (a.epochs[ep].first_block == wb) {
+    bool all = true;
+    for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
+    if (all) { p.start_kind = 1; return p; }
+  }
+  p.start_kind = 2;
+  return p;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(128)
+k_notch_guess(NotchApplyArgs a, float2 *guess /* [nsegs][kNotchMaxSlots] */, const float *weights) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (seg >= a.nsegs) return;
+  const SegPlan p = plan_segment(a, seg);
+  if (p.start_kind != 2) return;
+  const int ep = p.epoch;
+  const uint64_t P = p.run_begin * (uint64_t)kNotchN;            // state wanted after sample P-1
+  const uint64_t floor_s = a.epochs[ep].first_block * (uint64_t)kNotchN;  // history starts here
+  uint64_t M = P - floor_s;
+  const bool reaches_floor = M <= (uint64_t)kGuessWindow;
+  if (!reaches_floor) M = kGuessWindow;
+  for (int s = 0; s < a.nslots; ++s) {
+    const float2 *tab = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN;
+    float accr = 0.f, acci = 0.f;
+    for (uint64_t m = 1 + lane; m <= M; m += 32) {
+      const uint64_t idx = P - m;
+      const float2 x = ld_raw<FMT>(a.src, idx, a.scale);
+      const float2 e = __ldg(tab + (idx & (kNotchN - 1)));
+      const float bbr = x.x * e.x + x.y * e.y;
+      const float bbi = -x.x * e.y + x.y * e.x;
+      const float w = __ldg(weights + (m - 1));
+      accr += bbr * a.k * w;
+      acci += bbi * a.k * w;
+    }
+    for (int o = 16; o; o >>= 1) {
+      accr += __shfl_xor_sync(0xffffffffu, accr, o);
+      acci += __shfl_xor_sync(0xffffffffu, acci, o);
+    }
+    if (reaches_floor && !a.epochs[ep].reset[s] && ep == 0 && floor_s == 0) {
+      // history runs into the carried state of the batch
+      const float w = __ldg(weights + (M ? M - 1 : 0)) * (M ? (1.0f - a.k) : 1.0f);
+      accr += a.state_in->slot[s].est_re * w;
+      acci += a.state_in->slot[s].est_im * w;
+    }
+    if (lane == 0) guess[(size_t)seg * kNotchMaxSlots + s] = make_float2(accr, acci);
+  }
+}
+
 // One lane = one segment.  The 32 lanes of a warp walk 32 segments in lock step;
 // per tile the warp stages every lane's next 64 raw samples in a private
 // shared-memory row (cooperative 16-byte cp.async copies, contiguous within a
@@ -138,66 +237,53 @@ constexpr int kNPitch = 528;          // row pitch: (64 + 2) cf32, = 16 (mod 128
 constexpr int kNStages = 2;
 constexpr int kNWarps = 2;
 
-__device__ __forceinline__ float2 row_sample(const unsigned char *row, int fmt, uint32_t idx, float scale) {
-  switch (fmt) {
-    case 0: { uchar2 v = reinterpret_cast<const uchar2 *>(row)[idx];
-      return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
-    case 1: { char2 v = reinterpret_cast<const char2 *>(row)[idx];
-      return make_float2((float)(int)v.x, (float)(int)v.y); }
-    case 2: { ushort2 v = reinterpret_cast<const ushort2 *>(row)[idx];
-      return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768)); }
-    case 3: { short2 v = reinterpret_cast<const short2 *>(row)[idx];
-      return make_float2((float)(int)v.x, (float)(int)v.y); }
-    case 4: { float2 v = reinterpret_cast<const float2 *>(row)[idx];
-      return make_float2(fmul(v.x, scale), fmul(v.y, scale)); }
-    default: return reinterpret_cast<const float2 *>(row)[idx];
-  }
+template <int FMT>
+__device__ __forceinline__ float2 row_sample(const unsigned char *row, uint32_t idx, float scale) {
+  if (FMT == 0) { uchar2 v = reinterpret_cast<const uchar2 *>(row)[idx];
+    return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+  if (FMT == 1) { char2 v = reinterpret_cast<const char2 *>(row)[idx];
+    return make_float2((float)(int)v.x, (float)(int)v.y); }
+  if (FMT == 2) { ushort2 v = reinterpret_cast<const ushort2 *>(row)[idx];
+    return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768)); }
+  if (FMT == 3) { short2 v = reinterpret_cast<const short2 *>(row)[idx];
+    return make_float2((float)(int)v.x, (float)(int)v.y); }
+  float2 v = reinterpret_cast<const float2 *>(row)[idx];
+  if (FMT == 4) v = make_float2(fmul(v.x, scale), fmul(v.y, scale));
+  return v;
 }
 
+template <int FMT, int NSLOTS>
 __global__ void __launch_bounds__(kNWarps * 32)
-k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
+k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry, const float2 *guess) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[kNWarps * kNStages];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * kNWarps + warp;
   uint32_t seg; bool have;
   if (only_segment >= 0) { seg = (uint32_t)only_segment; have = (warp_global == 0 && lane == 0); }
   else { seg = warp_global * 32 + lane; have = seg < a.nsegs; }
 
-  uint64_t own_begin = 0, own_end = 0, run_begin = 0;
+  SegPlan p;
+  p.own_begin = p.own_end = p.run_begin = 0; p.epoch = 0; p.start_kind = 0;
+  float er[NSLOTS], ei[NSLOTS];
+#pragma unroll
+  for (int s = 0; s < NSLOTS; ++s) { er[s] = 0.f; ei[s] = 0.f; }
   int ep = 0;
-  float er[kNotchMaxSlots], ei[kNotchMaxSlots];
-  for (int s = 0; s < kNotchMaxSlots; ++s) { er[s] = 0.f; ei[s] = 0.f; }
-  bool exact = false;
   if (have) {
-    own_begin = (uint64_t)seg * a.seg_blocks;
-    own_end = own_begin + a.seg_blocks;
-    if (own_end > a.nblocks) own_end = a.nblocks;
-    while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= own_begin) ++ep;
-    run_begin = own_begin;
+    p = plan_segment(a, seg);
+    ep = p.epoch;
     if (forced_entry) {
-      for (int s = 0; s < a.nslots; ++s) { er[s] = forced_entry[s].x; ei[s] = forced_entry[s].y; }
-      exact = true;
-    } else if (seg == 0) {
-      for (int s = 0; s < a.nslots; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
-      exact = true;
-    } else {
-      // Warm-up from a zero estimate; never across an epoch start (tables change there).
-      uint64_t wb = (own_begin > a.warm_blocks) ? own_begin - a.warm_blocks : 0;
-      if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
-      run_begin = wb;
-      if (wb == 0 && a.epochs[ep].first_block == 0 && ep == 0) {
-        // The warm-up reaches the start of the batch inside the first epoch: start
-        // from the true carried state instead of zero (exact).
-        for (int s = 0; s < a.nslots; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
-        exact = true;
-      } else if (a.epochs[ep].first_block == wb) {
-        bool all = true;   // every slot is reset at this epoch start: exact zero state
-        for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
-        exact = all;
-      }
+      p.run_begin = p.own_begin;
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) { er[s] = forced_entry[s].x; ei[s] = forced_entry[s].y; }
+    } else if (p.start_kind == 0) {
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
+    } else if (p.start_kind == 2) {
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) { const float2 g = guess[(size_t)seg * kNotchMaxSlots + s]; er[s] = g.x; ei[s] = g.y; }
     }
   }
+  const uint64_t own_begin = p.own_begin, own_end = p.own_end, run_begin = p.run_begin;
   // Common iteration space: local block i -> block = base + i.
   int64_t base; uint64_t iters;
   if (only_segment >= 0) { base = (int64_t)run_begin; iters = own_end - run_begin; }
@@ -206,17 +292,16 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
 
   unsigned char *smem_warp = smem + (size_t)warp * kNStages * 32 * kNPitch;
   unsigned char *stage_base[kNStages];
+#pragma unroll
   for (int s = 0; s < kNStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kNPitch;
-  (void)bars;
-  // Row r of the warp = lane r's segment; its block at local iteration i is base_r + i.
   const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
   const int64_t base_step = (only_segment >= 0) ? 0 : (int64_t)a.seg_blocks;
 
-  const uint32_t bps = (a.fmt <= 1) ? 2u : (a.fmt <= 3 ? 4u : 8u);
-  const uint32_t align_elems = 16 / bps;
+  constexpr uint32_t bps = (FMT <= 1) ? 2u : (FMT <= 3 ? 4u : 8u);
+  constexpr uint32_t align_elems = 16 / bps;
   constexpr int kTilesPerBlock = kNotchN / kNTile;
+  constexpr int n16_max = (int)(((kNTile + align_elems) * bps + 15u) / 16u);
   const uint64_t total_tiles = iters * kTilesPerBlock;
-  // Where sample `idx` of the two-part stream lives, aligned down to 16 bytes.
   auto locate = [&](uint64_t idx, const unsigned char *&src, uint32_t &lead) {
     const unsigned char *part = static_cast<const unsigned char *>(a.src.head);
     if (a.src.main && idx >= a.src.c0) { part = static_cast<const unsigned char *>(a.src.main); idx -= a.src.c0; }
@@ -224,7 +309,6 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
     lead = (uint32_t)(idx - al);
     src = part + al * bps;
   };
-  const int n16_max = (int)(((kNTile + align_elems) * bps + 15u) / 16u);
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kNStages);
     const uint64_t i = tile / kTilesPerBlock;
@@ -232,8 +316,9 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
     const unsigned mask = __ballot_sync(0xffffffffu, active);
     const uint64_t col0 = (tile % kTilesPerBlock) * kNTile;
-    const int total = 32 * n16_max;
-    for (int id = lane; id < total; id += 32) {
+#pragma unroll
+    for (int kk = 0; kk < n16_max; ++kk) {
+      const int id = kk * 32 + lane;
       const int r = id / n16_max, q = id - r * n16_max;
       if ((mask >> r) & 1u) {
         const uint64_t idx = (uint64_t)(base0 + (int64_t)r * base_step + (int64_t)i) * kNotchN + col0;
@@ -247,6 +332,7 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
   };
 
   const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
+  const bool unit_gain = (gain == 1.0f);
   if (total_tiles) issue(0);
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
@@ -258,49 +344,101 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry) {
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
     if (active) {
       if (tib == 0) {
-        // Block start: epoch switch / resets (sdr.h:97-109), entry snapshot.
+        // Block start: entry snapshot, epoch switch / resets (sdr.h:97-109).
         while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= (uint64_t)blk) ++ep;
-        if ((uint64_t)blk == own_begin && a.seg_entry && !forced_entry)
-          for (int s = 0; s < a.nslots; ++s) a.seg_entry[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+        if ((uint64_t)blk == own_begin && a.seg_entry && !forced_entry) {
+#pragma unroll
+          for (int s = 0; s < NSLOTS; ++s) a.seg_entry[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+        }
         if (a.epochs[ep].first_block == (uint64_t)blk) {
-          for (int s = 0; s < a.nslots; ++s)
+#pragma unroll
+          for (int s = 0; s < NSLOTS; ++s)
             if (a.epochs[ep].reset[s]) { er[s] = 0.f; ei[s] = 0.f; }
         }
       }
       const bool write = ((uint64_t)blk >= own_begin);
-      const float2 *tab[kNotchMaxSlots];
-      for (int s = 0; s < a.nslots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
+      const float2 *tab[NSLOTS];
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
       float2 *outp = a.out + (uint64_t)blk * kNotchN + (uint64_t)tib * kNTile;
       uint32_t lead; { const unsigned char *unused; locate((uint64_t)blk * kNotchN + (uint64_t)tib * kNTile, unused, lead); }
       const unsigned char *myrow = stage_base[st] + (size_t)lane * kNPitch;
+      if (write) {
 #pragma unroll 4
-      for (int n = 0; n < kNTile; ++n) {
-        const float2 x = row_sample(myrow, a.fmt, lead + n, a.scale);
-        float outr = x.x, outi = x.y;
-        for (int s = 0; s < a.nslots; ++s) {
-          const float2 e = __ldg(tab[s] + n);
-          const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
-          const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
-          er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
-          ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
-          const float subr = fsub(fmul(er[s], e.x), fmul(ei[s], e.y));
-          const float subi = fadd(fmul(er[s], e.y), fmul(ei[s], e.x));
-          outr = fsub(outr, subr);
-          outi = fsub(outi, subi);
+        for (int n = 0; n < kNTile; ++n) {
+          const float2 x = row_sample<FMT>(myrow, lead + n, a.scale);
+          float outr = x.x, outi = x.y;
+#pragma unroll
+          for (int s = 0; s < NSLOTS; ++s) {
+            const float2 e = __ldg(tab[s] + n);
+            const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
+            const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
+            er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
+            ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
+            outr = fsub(outr, fsub(fmul(er[s], e.x), fmul(ei[s], e.y)));
+            outi = fsub(outi, fadd(fmul(er[s], e.y), fmul(ei[s], e.x)));
+          }
+          if (!unit_gain) { outr = fmul(gain, outr); outi = fmul(gain, outi); }
+          st_stream(outp + n, make_float2(outr, outi));
         }
-        if (write) st_stream(outp + n, make_float2(fmul(gain, outr), fmul(gain, outi)));
+      } else {
+        // Warm-up block: only the estimate recurrence, nothing is written.
+#pragma unroll 4
+        for (int n = 0; n < kNTile; ++n) {
+          const float2 x = row_sample<FMT>(myrow, lead + n, a.scale);
+#pragma unroll
+          for (int s = 0; s < NSLOTS; ++s) {
+            const float2 e = __ldg(tab[s] + n);
+            const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
+            const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
+            er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
+            ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
+          }
+        }
       }
     }
     __syncwarp();
   }
   if (have) {
-    if (a.seg_exit)
-      for (int s = 0; s < a.nslots; ++s) a.seg_exit[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
-    if (a.seg_exact && !forced_entry) a.seg_exact[seg] = exact ? 1 : 0;
+    if (a.seg_exit) {
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) a.seg_exit[(size_t)seg * kNotchMaxSlots + s] = make_float2(er[s], ei[s]);
+    }
+    if (a.seg_exact && !forced_entry) a.seg_exact[seg] = (p.start_kind != 2) ? 1 : 0;
   }
 }
 
 constexpr size_t kNotchSmem = (size_t)kNWarps * kNStages * 32 * kNPitch;
+
+template <int FMT, int NSLOTS>
+cudaError_t launch_apply_t(const NotchApplyArgs &a, int only_segment, const float2 *forced_entry,
+                           const float2 *guess, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kNotchSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const unsigned per_block = kNWarps * 32;
+  if (only_segment >= 0)
+    k_notch_apply<FMT, NSLOTS><<<1, per_block, kNotchSmem, st>>>(a, only_segment, forced_entry, guess);
+  else
+    k_notch_apply<FMT, NSLOTS><<<(a.nsegs + per_block - 1) / per_block, per_block, kNotchSmem, st>>>(a, -1, nullptr, guess);
+  return cudaGetLastError();
+}
+
+template <int FMT>
+cudaError_t launch_apply_f(const NotchApplyArgs &a, int only_segment, const float2 *forced_entry,
+                           const float2 *guess, cudaStream_t st) {
+  switch (a.nslots) {
+    case 1: return launch_apply_t<FMT, 1>(a, only_segment, forced_entry, guess, st);
+    case 2: return launch_apply_t<FMT, 2>(a, only_segment, forced_entry, guess, st);
+    case 3: return launch_apply_t<FMT, 3>(a, only_segment, forced_entry, guess, st);
+    case 4: return launch_apply_t<FMT, 4>(a, only_segment, forced_entry, guess, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
 
 }  // namespace
 
@@ -310,19 +448,31 @@ cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
-                               cudaStream_t st) {
-  if (a.nsegs == 0 || a.nblocks == 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_notch_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNotchSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
+cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const float *weights, cudaStream_t st) {
+  if (a.nsegs <= 1) return cudaSuccess;
+  const unsigned blocks = (a.nsegs + 3) / 4;
+  switch (a.fmt) {
+    case 0: k_notch_guess<0><<<blocks, 128, 0, st>>>(a, guess, weights); break;
+    case 1: k_notch_guess<1><<<blocks, 128, 0, st>>>(a, guess, weights); break;
+    case 2: k_notch_guess<2><<<blocks, 128, 0, st>>>(a, guess, weights); break;
+    case 3: k_notch_guess<3><<<blocks, 128, 0, st>>>(a, guess, weights); break;
+    case 4: k_notch_guess<4><<<blocks, 128, 0, st>>>(a, guess, weights); break;
+    default: k_notch_guess<5><<<blocks, 128, 0, st>>>(a, guess, weights); break;
   }
-  const unsigned per_block = kNWarps * 32;
-  if (only_segment >= 0) k_notch_apply<<<1, per_block, kNotchSmem, st>>>(a, only_segment, forced_entry);
-  else k_notch_apply<<<(a.nsegs + per_block - 1) / per_block, per_block, kNotchSmem, st>>>(a, -1, nullptr);
   return cudaGetLastError();
+}
+
+cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
+                               const float2 *guess, cudaStream_t st) {
+  if (a.nsegs == 0 || a.nblocks == 0) return cudaSuccess;
+  switch (a.fmt) {
+    case 0: return launch_apply_f<0>(a, only_segment, forced_entry, guess, st);
+    case 1: return launch_apply_f<1>(a, only_segment, forced_entry, guess, st);
+    case 2: return launch_apply_f<2>(a, only_segment, forced_entry, guess, st);
+    case 3: return launch_apply_f<3>(a, only_segment, forced_entry, guess, st);
+    case 4: return launch_apply_f<4>(a, only_segment, forced_entry, guess, st);
+    default: return launch_apply_f<5>(a, only_segment, forced_entry, guess, st);
+  }
 }
 
 }  // namespace ldvb

@@ -80,8 +80,10 @@ struct NotchApplyArgs {
   float2 *seg_exit;                // [nsegs][slots] state at segment end
   uint8_t *seg_exact;              // [nsegs] 1 when the segment started from a known-exact state
 };
+// guess: [nsegs][kNotchMaxSlots] start states written by launch_notch_guess.
+cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const float *weights, cudaStream_t st);
 cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
-                               cudaStream_t st);
+                               const float2 *guess, cudaStream_t st);
 
 // ------------------------------------------------------------------ K3 receiver
 struct CstlnCellDev { int16_t cost, symbol, phase_error, pad; };

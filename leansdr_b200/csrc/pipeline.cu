@@ -109,6 +109,7 @@ struct ldvb_handle {
   NotchState notch;            // host mirror
   std::map<int, uint32_t> notch_table_of_bin;
   DevBuf d_notch_tables; uint32_t notch_tables_used = 0, notch_tables_cap = 0;
+  DevBuf d_notch_guess, d_notch_weights;
   DevBuf d_notch_state, d_notch_epochs, d_notch_entry, d_notch_exit, d_notch_exact, d_notch_bins, d_notch_blocks;
   uint32_t rot_index = 0;
   RxState rx_state;            // host mirror of the exact/carried receiver state
@@ -396,7 +397,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rotperm, &h->d_twiddle, &h->s_raw.buf, &h->s_notched.buf, &h->s_pp.buf, &h->s_sym.buf,
                     &h->s_bytes.buf, &h->s_mpeg.buf, &h->d_rts, &h->d_rsflags, &h->d_ts, &h->d_scratch,
                     &h->d_badwords, &h->d_rs204, &h->d_notch_tables, &h->d_notch_state, &h->d_notch_epochs,
-                    &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
+                    &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
                     &h->d_rx_forced, &h->d_deconv_carry, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
@@ -549,9 +550,16 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
                h->d_notch_entry.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
                h->d_notch_exit.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
                h->d_notch_exact.alloc(nblk + 1) == cudaSuccess &&
+               h->d_notch_guess.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
                h->d_notch_bins.alloc(4 * kNotchMaxSlots * (nblk / 1024 + 4)) == cudaSuccess &&
                h->d_notch_blocks.alloc(8 * (nblk / 1024 + 4)) == cudaSuccess;
     if (!nok) return bail(LDVB_ENOMEM, "notch allocation failed");
+    {  // (1-k)^m, m = 0..8191, for the start-state guess
+      std::vector<float> w(8192);
+      const double c1 = (double)(1.0f - 0.002f);
+      for (int m = 0; m < 8192; ++m) w[m] = (float)pow(c1, (double)m);
+      if (upload(h->d_notch_weights, w.data(), w.size() * 4) != cudaSuccess) return bail(LDVB_ECUDA, "notch weights");
+    }
     // Table 0 is all zeros: slots that never detected (bin -1) use it (sdr.h:57-63).
     cudaMemset(h->d_notch_tables.p, 0, (size_t)kNotchN * 8);
     h->notch_tables_used = 1;
@@ -722,14 +730,15 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // latency bound per lane), 4 blocks (16 Ki samples) of warm-up: from a zero
   // estimate the float trajectories merge bit for bit after 4..10 Ki samples
   // (0.998^n decay below one ulp), measured in DESIGN.md.
-  a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 16383) / 16384));
-  a.warm_blocks = 4;
+  a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 32767) / 32768));
+  a.warm_blocks = 1;   // one exact block after the parallel weighted-sum guess
   a.nsegs = (uint32_t)((nblocks + a.seg_blocks - 1) / a.seg_blocks);
   a.state_in = h->d_notch_state.as<NotchState>();
   a.seg_entry = h->d_notch_entry.as<float2>();
   a.seg_exit = h->d_notch_exit.as<float2>();
   a.seg_exact = h->d_notch_exact.as<uint8_t>();
-  KL("notch_apply", launch_notch_apply(a, -1, nullptr, h->st));
+  KL("notch_guess", launch_notch_guess(a, h->d_notch_guess.as<float2>(), h->d_notch_weights.as<float>(), h->st));
+  KL("notch_apply", launch_notch_apply(a, -1, nullptr, h->d_notch_guess.as<float2>(), h->st));
   // Verify entry(j+1) == exit(j) bit for bit; re-run (serially, in order) the
   // segments whose warm-up had not merged with the true trajectory.
   std::vector<float2> entry((size_t)a.nsegs * kNotchMaxSlots), exitv((size_t)a.nsegs * kNotchMaxSlots);
@@ -752,7 +761,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
     }
     if (same) continue;
     // Exact re-run of segment j from the (now final) exit state of segment j-1.
-    KL("notch_apply", launch_notch_apply(a, (int)j, a.seg_exit + (size_t)(j - 1) * kNotchMaxSlots, h->st));
+    KL("notch_apply", launch_notch_apply(a, (int)j, a.seg_exit + (size_t)(j - 1) * kNotchMaxSlots, nullptr, h->st));
     ++h->meas.notch_repaired;
     rc = fetch();
     if (rc) return rc;
