@@ -119,9 +119,18 @@ k_sync_flags(const uint8_t *bytes, uint64_t npackets, const SyncState *st, uint3
   if ((threadIdx.x & 31) == 0 && (p >> 5) <= ((npackets + 31) >> 5)) bad_words[p >> 5] = m;
 }
 
-// search_sync (dvb.h:798-840) on the window starting at bytes[pos].
-__device__ int sync_search_window(const uint8_t *bytes, uint64_t pos, SyncState &st) {
-  for (int i = 0; i < 204; ++i) {
+// search_sync (dvb.h:798-840) on the window starting at bytes[pos]; the 204 byte
+// offsets are examined by 204 threads, the lowest offset that qualifies wins
+// (the reference scans i = 0..203 and stops at the first hit).  Called by the
+// whole block; returns the number of bytes to skip (0 = no lock) to every thread.
+__device__ int sync_search_window(const uint8_t *bytes, uint64_t pos, SyncState &st, int *s_best,
+                                  int *s_pol, int *s_ph) {
+  const int i = threadIdx.x;
+  if (i == 0) *s_best = 1 << 30;
+  __syncthreads();
+  int pol = 0, ph8 = -1;
+  bool hit = false;
+  if (i < 204) {
     int np = 0, nn = 0, ph_p = -1, ph_n = -1;
     for (int j = 0; j < 8; ++j) {
       const unsigned b = (((unsigned)bytes[pos + i + 204 * j] << 8 | bytes[pos + i + 204 * j + 1]) >> st.bitphase) & 0xffu;
@@ -129,25 +138,34 @@ __device__ int sync_search_window(const uint8_t *bytes, uint64_t pos, SyncState 
       if (b == 0xb8u) { ++nn; ph_p = (8 - j) & 7; }
     }
     int nsyncs;
-    if (np > nn) { st.polarity = 0; nsyncs = np; st.phase8 = ph_p; }
-    else { st.polarity = 0xff; nsyncs = nn; st.phase8 = ph_n; }
-    if (nsyncs >= 4 && st.phase8 >= 0) {
-      int skip = i;
-      if (!i) { skip = 204; st.phase8 = (st.phase8 + 1) & 7; }
-      st.synchronized = 1;
-      st.lock_timeleft = 4;
-      st.locktime = 0;
-      return skip;
-    }
+    if (np > nn) { pol = 0; nsyncs = np; ph8 = ph_p; }
+    else { pol = 0xff; nsyncs = nn; ph8 = ph_n; }
+    hit = (nsyncs >= 4 && ph8 >= 0);
+    if (hit) atomicMin(s_best, i);
+    if (i == 203) { s_pol[1] = pol; s_ph[1] = ph8; }   // what a fruitless scan leaves behind
   }
+  __syncthreads();
+  const int best = *s_best;
+  if (hit && i == best) { s_pol[0] = pol; s_ph[0] = ph8; }
+  __syncthreads();
+  if (best < 204) {
+    st.polarity = s_pol[0]; st.phase8 = s_ph[0];
+    int skip = best;
+    if (!best) { skip = 204; st.phase8 = (st.phase8 + 1) & 7; }
+    st.synchronized = 1;
+    st.lock_timeleft = 4;
+    st.locktime = 0;
+    return skip;
+  }
+  st.polarity = s_pol[1]; st.phase8 = s_ph[1];
   return 0;
 }
 
-__global__ void k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_in,
-                             const uint32_t *bad_words, uint64_t npackets_flagged,
-                             SyncResult *res) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  SyncState st = *st_in;
+__global__ void __launch_bounds__(256)
+k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_in,
+             const uint32_t *bad_words, uint64_t npackets_flagged, SyncResult *res) {
+  __shared__ int s_best, s_pol[2], s_ph[2];
+  SyncState st = *st_in;          // every thread keeps an identical copy
   SyncResult r;
   r.consumed = 0; r.produced = 0; r.need_next_sync = 0; r.events = 0;
   auto event = [&](int v, uint64_t pos) {
@@ -156,6 +174,7 @@ __global__ void k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncSt
   };
   if (st.report_state) { event(0, 0); st.report_state = 0; }
   if (st.synchronized) {
+    if (threadIdx.x != 0) return;
     // run_decoding (dvb.h:842-874): walk the mask until the lock times out.
     uint64_t p = 0;
     bool unlocked = false;
@@ -192,7 +211,7 @@ __global__ void k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncSt
     uint64_t pos = 0;
     const uint64_t chunk = 204 * 8;
     while (nbytes - pos >= chunk + 1) {
-      const int skip = sync_search_window(bytes, pos, st);
+      const int skip = sync_search_window(bytes, pos, st, &s_best, s_pol, s_ph);
       if (skip) {
         pos += skip;
         event(1, pos);
@@ -209,6 +228,7 @@ __global__ void k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncSt
       }
     }
     r.consumed = pos;
+    if (threadIdx.x != 0) return;
   }
   r.st = st;
   *res = r;
@@ -476,7 +496,7 @@ cudaError_t launch_sync_flags(const uint8_t *bytes, uint64_t npackets, const Syn
 cudaError_t launch_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_dev,
                               const uint32_t *bad_words, uint64_t npackets_flagged, SyncResult *res,
                               cudaStream_t st) {
-  k_sync_track<<<1, 32, 0, st>>>(bytes, nbytes, st_dev, bad_words, npackets_flagged, res);
+  k_sync_track<<<1, 256, 0, st>>>(bytes, nbytes, st_dev, bad_words, npackets_flagged, res);
   return cudaGetLastError();
 }
 

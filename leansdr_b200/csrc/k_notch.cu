@@ -254,13 +254,18 @@ __device__ __forceinline__ float2 row_sample(const unsigned char *row, uint32_t 
 
 template <int FMT, int NSLOTS>
 __global__ void __launch_bounds__(kNWarps * 32)
-k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry, const float2 *guess) {
+k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const float2 *guess) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * kNWarps + warp;
+  // Normal mode: lane g owns segment g.  Repair mode (seg_list): lane g re-runs
+  // segment seg_list[g] exactly, from the exit state of its predecessor.
+  const bool repair = (seg_list != nullptr);
   uint32_t seg; bool have;
-  if (only_segment >= 0) { seg = (uint32_t)only_segment; have = (warp_global == 0 && lane == 0); }
-  else { seg = warp_global * 32 + lane; have = seg < a.nsegs; }
+  const uint32_t g = warp_global * 32 + lane;
+  if (repair) { have = g < nlist; seg = have ? seg_list[g] : 0; }
+  else { seg = g; have = seg < a.nsegs; }
+  const float2 *forced_entry = (repair && have) ? a.seg_exit + (size_t)(seg - 1) * kNotchMaxSlots : nullptr;
 
   SegPlan p;
   p.own_begin = p.own_end = p.run_begin = 0; p.epoch = 0; p.start_kind = 0;
@@ -286,16 +291,14 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry, co
   const uint64_t own_begin = p.own_begin, own_end = p.own_end, run_begin = p.run_begin;
   // Common iteration space: local block i -> block = base + i.
   int64_t base; uint64_t iters;
-  if (only_segment >= 0) { base = (int64_t)run_begin; iters = own_end - run_begin; }
+  if (repair) { base = (int64_t)run_begin; iters = a.seg_blocks; }
   else { base = (int64_t)((uint64_t)seg * a.seg_blocks) - (int64_t)a.warm_blocks; iters = (uint64_t)a.warm_blocks + a.seg_blocks; }
-  iters = __shfl_sync(0xffffffffu, iters, 0);
 
   unsigned char *smem_warp = smem + (size_t)warp * kNStages * 32 * kNPitch;
   unsigned char *stage_base[kNStages];
 #pragma unroll
   for (int s = 0; s < kNStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kNPitch;
   const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
-  const int64_t base_step = (only_segment >= 0) ? 0 : (int64_t)a.seg_blocks;
 
   constexpr uint32_t bps = (FMT <= 1) ? 2u : (FMT <= 3 ? 4u : 8u);
   constexpr uint32_t align_elems = 16 / bps;
@@ -320,8 +323,10 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry, co
     for (int kk = 0; kk < n16_max; ++kk) {
       const int id = kk * 32 + lane;
       const int r = id / n16_max, q = id - r * n16_max;
+      // Row r belongs to lane r: segments are consecutive in normal mode, arbitrary in repair mode.
+      const int64_t base_r = repair ? __shfl_sync(0xffffffffu, base, r) : base0 + (int64_t)r * (int64_t)a.seg_blocks;
       if ((mask >> r) & 1u) {
-        const uint64_t idx = (uint64_t)(base0 + (int64_t)r * base_step + (int64_t)i) * kNotchN + col0;
+        const uint64_t idx = (uint64_t)(base_r + (int64_t)i) * kNotchN + col0;
         const unsigned char *src; uint32_t lead;
         locate(idx, src, lead);
         const int n16 = (int)(((lead + kNTile) * bps + 15u) / 16u);
@@ -411,7 +416,7 @@ k_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry, co
 constexpr size_t kNotchSmem = (size_t)kNWarps * kNStages * 32 * kNPitch;
 
 template <int FMT, int NSLOTS>
-cudaError_t launch_apply_t(const NotchApplyArgs &a, int only_segment, const float2 *forced_entry,
+cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, uint32_t nlist,
                            const float2 *guess, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
@@ -421,21 +426,20 @@ cudaError_t launch_apply_t(const NotchApplyArgs &a, int only_segment, const floa
     configured = true;
   }
   const unsigned per_block = kNWarps * 32;
-  if (only_segment >= 0)
-    k_notch_apply<FMT, NSLOTS><<<1, per_block, kNotchSmem, st>>>(a, only_segment, forced_entry, guess);
-  else
-    k_notch_apply<FMT, NSLOTS><<<(a.nsegs + per_block - 1) / per_block, per_block, kNotchSmem, st>>>(a, -1, nullptr, guess);
+  const uint32_t lanes = seg_list ? nlist : a.nsegs;
+  if (!lanes) return cudaSuccess;
+  k_notch_apply<FMT, NSLOTS><<<(lanes + per_block - 1) / per_block, per_block, kNotchSmem, st>>>(a, seg_list, nlist, guess);
   return cudaGetLastError();
 }
 
 template <int FMT>
-cudaError_t launch_apply_f(const NotchApplyArgs &a, int only_segment, const float2 *forced_entry,
+cudaError_t launch_apply_f(const NotchApplyArgs &a, const uint32_t *seg_list, uint32_t nlist,
                            const float2 *guess, cudaStream_t st) {
   switch (a.nslots) {
-    case 1: return launch_apply_t<FMT, 1>(a, only_segment, forced_entry, guess, st);
-    case 2: return launch_apply_t<FMT, 2>(a, only_segment, forced_entry, guess, st);
-    case 3: return launch_apply_t<FMT, 3>(a, only_segment, forced_entry, guess, st);
-    case 4: return launch_apply_t<FMT, 4>(a, only_segment, forced_entry, guess, st);
+    case 1: return launch_apply_t<FMT, 1>(a, seg_list, nlist, guess, st);
+    case 2: return launch_apply_t<FMT, 2>(a, seg_list, nlist, guess, st);
+    case 3: return launch_apply_t<FMT, 3>(a, seg_list, nlist, guess, st);
+    case 4: return launch_apply_t<FMT, 4>(a, seg_list, nlist, guess, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -462,16 +466,16 @@ cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const flo
   return cudaGetLastError();
 }
 
-cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
+cudaError_t launch_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist,
                                const float2 *guess, cudaStream_t st) {
   if (a.nsegs == 0 || a.nblocks == 0) return cudaSuccess;
   switch (a.fmt) {
-    case 0: return launch_apply_f<0>(a, only_segment, forced_entry, guess, st);
-    case 1: return launch_apply_f<1>(a, only_segment, forced_entry, guess, st);
-    case 2: return launch_apply_f<2>(a, only_segment, forced_entry, guess, st);
-    case 3: return launch_apply_f<3>(a, only_segment, forced_entry, guess, st);
-    case 4: return launch_apply_f<4>(a, only_segment, forced_entry, guess, st);
-    default: return launch_apply_f<5>(a, only_segment, forced_entry, guess, st);
+    case 0: return launch_apply_f<0>(a, seg_list, nlist, guess, st);
+    case 1: return launch_apply_f<1>(a, seg_list, nlist, guess, st);
+    case 2: return launch_apply_f<2>(a, seg_list, nlist, guess, st);
+    case 3: return launch_apply_f<3>(a, seg_list, nlist, guess, st);
+    case 4: return launch_apply_f<4>(a, seg_list, nlist, guess, st);
+    default: return launch_apply_f<5>(a, seg_list, nlist, guess, st);
   }
 }
 

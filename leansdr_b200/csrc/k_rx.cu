@@ -341,14 +341,17 @@ k_rx(RxArgs a, int only_span, const RxState *forced) {
 
 // ---------------------------------------------------------------- seam stitching
 
-__global__ void k_rx_stitch(RxStitchArgs a, int only_seam) {
-  uint32_t j = (only_seam >= 0) ? (uint32_t)only_seam : blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per seam: lanes stride over the logged symbols.
+__global__ void __launch_bounds__(128)
+k_rx_stitch(RxStitchArgs a, int only_seam) {
+  const int lane = threadIdx.x & 31;
+  uint32_t j = (only_seam >= 0) ? (uint32_t)only_seam : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (only_seam >= 0 && (blockIdx.x != 0 || (threadIdx.x >> 5) != 0)) return;
   if (j + 1 >= a.nspans) return;
-  if (only_seam >= 0 && (blockIdx.x != 0 || threadIdx.x != 0)) return;
   const RxSeamSym *tail = a.tail_log + (size_t)j * kRxSeamLog;
   const RxSeamSym *head = a.head_log + (size_t)(j + 1) * kRxSeamLog;
-  uint32_t nt = min(a.info[j].n_tail, (uint32_t)kRxSeamLog);
-  uint32_t nh = min(a.info[j + 1].n_head_logged, (uint32_t)kRxSeamLog);
+  const uint32_t nt = min(a.info[j].n_tail, (uint32_t)kRxSeamLog);
+  const uint32_t nh = min(a.info[j + 1].n_head_logged, (uint32_t)kRxSeamLog);
   RxSeam s;
   s.ok = 0; s.rot = 0; s.extend_prev = 0; s.skip_next = 0; s.compared = 0; s.mismatches = 0;
   if (nt >= 8 && nh >= 8) {
@@ -360,23 +363,27 @@ __global__ void k_rx_stitch(RxStitchArgs a, int only_seam) {
     else if (d < -half) { ih0 = 1; s.skip_next = 1; }    // next span repeats the previous span's last symbol
     const int n = (int)min(nt - it0, nh - ih0);
     int best_rot = 0, best_mis = 1 << 30;
+    bool time_ok = true;
     for (int rot = 0; rot < a.nrot; ++rot) {
       const uint8_t *perm = a.rot_perm + rot * a.nsymbols;
       int mis = 0;
-      for (int i = 0; i < n; ++i)
-        if (perm[head[ih0 + i].sym] != tail[it0 + i].sym) ++mis;
+      for (int i = lane; i < n; i += 32) {
+        const RxSeamSym hs = head[ih0 + i], ts = tail[it0 + i];
+        if (perm[hs.sym] != ts.sym) ++mis;
+        if (rot == 0 && fabsf(hs.t - ts.t) > 0.25f * a.omega) time_ok = false;
+      }
+      for (int o = 16; o; o >>= 1) mis += __shfl_xor_sync(0xffffffffu, mis, o);
       if (mis < best_mis) { best_mis = mis; best_rot = rot; }
+      if (best_mis * 16 <= n) break;   // good enough: the other rotations disagree on ~3/4 of the symbols
     }
-    bool time_ok = true;
-    for (int i = 0; i < n; ++i)
-      if (fabsf(head[ih0 + i].t - tail[it0 + i].t) > 0.25f * a.omega) time_ok = false;
+    time_ok = __all_sync(0xffffffffu, time_ok);
     s.rot = best_rot; s.compared = n; s.mismatches = best_mis;
     // Isolated disagreements are noise-level decision flips between two converged
     // loops (either span may be the one that differs from the serial reference);
     // an unconverged or rotated span disagrees on half or more of the symbols.
     s.ok = (time_ok && n >= 8 && best_mis * 16 <= n) ? 1 : 0;
   }
-  a.seams[j] = s;
+  if (lane == 0) a.seams[j] = s;
 }
 
 __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
@@ -423,7 +430,7 @@ cudaError_t launch_rx(const RxArgs &a, int only_span, const RxState *forced, cud
 cudaError_t launch_rx_stitch(const RxStitchArgs &a, int only_seam, cudaStream_t st) {
   if (a.nspans < 2) return cudaSuccess;
   if (only_seam >= 0) k_rx_stitch<<<1, 32, 0, st>>>(a, only_seam);
-  else k_rx_stitch<<<(a.nspans - 1 + 63) / 64, 64, 0, st>>>(a, -1);
+  else k_rx_stitch<<<(a.nspans - 1 + 3) / 4, 128, 0, st>>>(a, -1);
   return cudaGetLastError();
 }
 

@@ -82,7 +82,9 @@ struct NotchApplyArgs {
 };
 // guess: [nsegs][kNotchMaxSlots] start states written by launch_notch_guess.
 cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const float *weights, cudaStream_t st);
-cudaError_t launch_notch_apply(NotchApplyArgs a, int only_segment, const float2 *forced_entry,
+// seg_list == nullptr: every segment (warm-up from `guess`).  Otherwise the listed segments
+// are re-run exactly from the exit state of their predecessors (a.seg_exit).
+cudaError_t launch_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist,
                                const float2 *guess, cudaStream_t st);
 
 // ------------------------------------------------------------------ K3 receiver

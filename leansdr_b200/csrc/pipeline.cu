@@ -109,7 +109,7 @@ struct ldvb_handle {
   NotchState notch;            // host mirror
   std::map<int, uint32_t> notch_table_of_bin;
   DevBuf d_notch_tables; uint32_t notch_tables_used = 0, notch_tables_cap = 0;
-  DevBuf d_notch_guess, d_notch_weights;
+  DevBuf d_notch_guess, d_notch_weights, d_notch_list;
   DevBuf d_notch_state, d_notch_epochs, d_notch_entry, d_notch_exit, d_notch_exact, d_notch_bins, d_notch_blocks;
   uint32_t rot_index = 0;
   RxState rx_state;            // host mirror of the exact/carried receiver state
@@ -397,7 +397,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rotperm, &h->d_twiddle, &h->s_raw.buf, &h->s_notched.buf, &h->s_pp.buf, &h->s_sym.buf,
                     &h->s_bytes.buf, &h->s_mpeg.buf, &h->d_rts, &h->d_rsflags, &h->d_ts, &h->d_scratch,
                     &h->d_badwords, &h->d_rs204, &h->d_notch_tables, &h->d_notch_state, &h->d_notch_epochs,
-                    &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
+                    &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
                     &h->d_rx_forced, &h->d_deconv_carry, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
@@ -551,6 +551,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
                h->d_notch_exit.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
                h->d_notch_exact.alloc(nblk + 1) == cudaSuccess &&
                h->d_notch_guess.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
+               h->d_notch_list.alloc(4 * (nblk + 1)) == cudaSuccess &&
                h->d_notch_bins.alloc(4 * kNotchMaxSlots * (nblk / 1024 + 4)) == cudaSuccess &&
                h->d_notch_blocks.alloc(8 * (nblk / 1024 + 4)) == cudaSuccess;
     if (!nok) return bail(LDVB_ENOMEM, "notch allocation failed");
@@ -738,34 +739,41 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   a.seg_exit = h->d_notch_exit.as<float2>();
   a.seg_exact = h->d_notch_exact.as<uint8_t>();
   KL("notch_guess", launch_notch_guess(a, h->d_notch_guess.as<float2>(), h->d_notch_weights.as<float>(), h->st));
-  KL("notch_apply", launch_notch_apply(a, -1, nullptr, h->d_notch_guess.as<float2>(), h->st));
-  // Verify entry(j+1) == exit(j) bit for bit; re-run (serially, in order) the
-  // segments whose warm-up had not merged with the true trajectory.
+  KL("notch_apply", launch_notch_apply(a, nullptr, 0, h->d_notch_guess.as<float2>(), h->st));
+  // Verify entry(j) == exit(j-1) bit for bit.  Segments whose warm-up had not merged
+  // with the true trajectory are re-run exactly from their predecessor's exit state,
+  // all of them in one launch per round (a segment whose predecessor is also being
+  // repaired waits for the next round).
   std::vector<float2> entry((size_t)a.nsegs * kNotchMaxSlots), exitv((size_t)a.nsegs * kNotchMaxSlots);
   std::vector<uint8_t> exact(a.nsegs);
-  auto fetch = [&]() -> int {
-    CK(cudaMemcpyAsync(entry.data(), a.seg_entry, entry.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(entry.data(), a.seg_entry, entry.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(exact.data(), a.seg_exact, exact.size(), cudaMemcpyDeviceToHost, h->st));
+  int rc = LDVB_OK;
+  for (int round = 0; round < 1 << 20; ++round) {
     CK(cudaMemcpyAsync(exitv.data(), a.seg_exit, exitv.size() * 8, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(exact.data(), a.seg_exact, exact.size(), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    return LDVB_OK;
-  };
-  int rc = fetch();
-  if (rc) return rc;
-  for (uint32_t j = 1; j < a.nsegs; ++j) {
-    if (exact[j]) continue;
-    bool same = true;
-    for (int s = 0; s < c.anf; ++s) {
-      const float2 e = entry[(size_t)j * kNotchMaxSlots + s], x = exitv[(size_t)(j - 1) * kNotchMaxSlots + s];
-      if (memcmp(&e, &x, 8) != 0) same = false;
+    std::vector<uint32_t> todo;
+    bool prev_failed = false;
+    for (uint32_t j = 1; j < a.nsegs; ++j) {
+      bool same = exact[j] != 0;
+      if (!same) same = memcmp(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * (size_t)c.anf) == 0;
+      if (!same && !prev_failed) todo.push_back(j);
+      prev_failed = !same;
     }
-    if (same) continue;
-    // Exact re-run of segment j from the (now final) exit state of segment j-1.
-    KL("notch_apply", launch_notch_apply(a, (int)j, a.seg_exit + (size_t)(j - 1) * kNotchMaxSlots, nullptr, h->st));
-    ++h->meas.notch_repaired;
-    rc = fetch();
-    if (rc) return rc;
+    if (todo.empty()) {
+      bool any = false;
+      for (uint32_t j = 1; j < a.nsegs && !any; ++j)
+        any = !exact[j] && memcmp(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * (size_t)c.anf) != 0;
+      if (!any) break;
+      continue;
+    }
+    CK(cudaMemcpyAsync(h->d_notch_list.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, h->st));
+    KL("notch_apply", launch_notch_apply(a, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st));
+    h->meas.notch_repaired += (uint32_t)todo.size();
+    for (uint32_t j : todo)   // by construction the repaired segment entered with exit(j-1)
+      memcpy(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * kNotchMaxSlots);
   }
+  (void)rc;
   for (int s = 0; s < c.anf; ++s) {
     h->notch.slot[s].est_re = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].x;
     h->notch.slot[s].est_im = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].y;
