@@ -123,8 +123,8 @@ struct RxSpanInfo {
 };
 
 constexpr int kRxChunk = 128;
-constexpr int kRxSeamLog = 384;        // log entries per seam side
-constexpr int kRxVerifyChunks = 2;     // chunks of overlap after a span end
+constexpr int kRxSeamLog = 192;        // log entries per seam side
+constexpr int kRxVerifyChunks = 1;     // chunks of overlap after a span end
 
 struct RxArgs {
   RxParams p;

@@ -732,7 +732,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // estimate the float trajectories merge bit for bit after 4..10 Ki samples
   // (0.998^n decay below one ulp), measured in DESIGN.md.
   a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 32767) / 32768));
-  a.warm_blocks = 1;   // one exact block after the parallel weighted-sum guess
+  a.warm_blocks = 2;   // exact blocks after the parallel weighted-sum guess (merge: median 1 Ki, max ~3 Ki samples)
   a.nsegs = (uint32_t)((nblocks + a.seg_blocks - 1) / a.seg_blocks);
   a.state_in = h->d_notch_state.as<NotchState>();
   a.seg_entry = h->d_notch_entry.as<float2>();

@@ -1,0 +1,118 @@
+// gpu_runnables.h -- the reference-side binding of the B200 DVB-S receive path.
+//
+// A `runnable` for leansdr's own data-flow framework (reference
+// src/leansdr/framework.h:124-131): the scheduler only ever calls run() and
+// shutdown() (framework.h:92-95, 105-108) and the data contract is
+// pipereader<T>{readable,rd,read} / pipewriter<T>{writable,wr,written}
+// (framework.h:190-249).  This block replaces every runnable that
+// apps/leandvb.cc:204-596 instantiates between the input pipebuf and
+// p_tspackets; it owns one ldvb_handle (include/leandvb_b200.h) and moves
+// whole pipebuf contents through ldvb_push()/ldvb_pull().
+//
+// Include AFTER "leansdr/framework.h" and "leansdr/dvb.h" of the reference tree
+// (this header uses leansdr::runnable, pipebuf, pipereader, pipewriter, fail and
+// tspacket from them; it defines nothing that the reference already defines).
+#ifndef LEANSDR_B200_GPU_RUNNABLES_H
+#define LEANSDR_B200_GPU_RUNNABLES_H
+
+#include <stdio.h>
+#include "leandvb_b200.h"
+
+namespace leansdr {
+
+// Tin: complex<u8> / complex<s8> / complex<u16> / complex<s16> / complex<f32>,
+// matching cfg.input_format.  Tpacket: dvb.h's tspacket (188 bytes).
+template<typename Tin, typename Tpacket>
+struct gpu_dvbs_receiver : runnable {
+  // Batching: run() hands everything readable to the GPU, but not less than
+  // [min_batch] samples unless the input has stalled for [patience] calls
+  // (end of stream): small pushes are legal but waste launch latency.
+  unsigned long min_batch;
+  int patience;
+
+  gpu_dvbs_receiver(scheduler *sch, pipebuf<Tin> &_in, pipebuf<Tpacket> &_out,
+		    const ldvb_config &cfg,
+		    pipebuf<float> *_freq_out=NULL, pipebuf<float> *_ss_out=NULL,
+		    pipebuf<float> *_mer_out=NULL, pipebuf<int> *_lock_out=NULL,
+		    pipebuf<float> *_vber_out=NULL)
+    : runnable(sch, "gpu_dvbs_receiver"),
+      min_batch(1<<16), patience(2),
+      in(_in), out(_out), handle(NULL), starved(0), last_readable(0),
+      last_lock(-1), rs_bits(0), rs_errs(0) {
+    if ( sizeof(Tpacket) != 188 ) fail("gpu_dvbs_receiver: Tpacket must be 188 bytes");
+    freq_out = opt_writer(_freq_out);
+    ss_out = opt_writer(_ss_out);
+    mer_out = opt_writer(_mer_out);
+    lock_out = opt_writer(_lock_out);
+    vber_out = opt_writer(_vber_out);
+    int rc = ldvb_create(&cfg, &handle);
+    if ( rc ) { fprintf(stderr, "ldvb_create: %s\n", ldvb_strerror(rc)); fail("gpu_dvbs_receiver"); }
+    max_batch = cfg.max_batch;
+  }
+
+  void run() {
+    // 1. Drain finished packets first (never blocks, no progress if none).
+    drain();
+    // 2. Feed.  No progress when starved, progress whenever possible
+    //    (framework.h:96-113 detects the fixpoint on the pipe counters).
+    unsigned long n = in.readable();
+    if ( n > max_batch ) n = max_batch;
+    if ( !n ) return;
+    if ( n < min_batch ) {
+      // Wait for more unless the producer has stopped delivering.
+      if ( n != last_readable ) { last_readable = n; starved = 0; return; }
+      if ( ++starved < patience ) return;
+    }
+    starved = 0; last_readable = 0;
+    int rc = ldvb_push(handle, in.rd(), n);
+    if ( rc ) { fprintf(stderr, "ldvb_push: %s (%s)\n", ldvb_strerror(rc), ldvb_last_error(handle)); fail("gpu_dvbs_receiver"); }
+    in.read(n);
+    telemetry();
+    drain();
+  }
+
+  void shutdown() {
+    if ( handle ) { ldvb_destroy(handle); handle = NULL; }
+  }
+
+private:
+  void drain() {
+    while ( 1 ) {
+      unsigned long w = out.writable();
+      if ( !w ) return;
+      size_t got = 0;
+      int rc = ldvb_pull(handle, (uint8_t*)out.wr(), w, &got);
+      if ( rc ) fail("ldvb_pull");
+      if ( !got ) return;
+      out.written(got);
+    }
+  }
+  // p_freq/p_ss/p_mer/p_lock/p_vber of leandvb.cc:600-616, once per batch.
+  void telemetry() {
+    ldvb_meas m;
+    if ( ldvb_get_meas(handle, &m) ) return;
+    if ( freq_out && freq_out->writable() ) freq_out->write(m.freq_tap);
+    if ( ss_out && ss_out->writable() ) ss_out->write(m.ss);
+    if ( mer_out && mer_out->writable() ) mer_out->write(m.mer);
+    if ( lock_out && m.lock != last_lock && lock_out->writable() ) { lock_out->write(m.lock); last_lock = m.lock; }
+    if ( vber_out && m.rs_bits > rs_bits && vber_out->writable() ) {
+      vber_out->write((float)(m.rs_errs-rs_errs) / (float)(m.rs_bits-rs_bits));  // generic.h:296-299
+      rs_bits = m.rs_bits; rs_errs = m.rs_errs;
+    }
+  }
+
+  pipereader<Tin> in;
+  pipewriter<Tpacket> out;
+  ldvb_handle *handle;
+  unsigned long max_batch;
+  int starved;
+  unsigned long last_readable;
+  pipewriter<float> *freq_out, *ss_out, *mer_out, *vber_out;
+  pipewriter<int> *lock_out;
+  int last_lock;
+  uint64_t rs_bits, rs_errs;
+};
+
+}  // namespace
+
+#endif  // LEANSDR_B200_GPU_RUNNABLES_H

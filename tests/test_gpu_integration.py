@@ -1,0 +1,31 @@
+"""Drop-in check: the reference's OWN scheduler / pipebuf / file_reader / file_writer
+(compiled from /root/reference in the dev container into oracle/_ref/leandvb_gpu, together
+with leansdr_b200/host/gpu_runnables.h) driving the CUDA path, against the unmodified
+reference `leandvb` on the same IQ."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import vectors as V
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "leandvb_gpu")),
+                    reason="oracle/_ref/leandvb_gpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("fmt,flags", [("f32", ["--resample"]), ("u8", []), ("f32", ["--anf", "0", "--gpu-exact"])])
+def test_reference_scheduler_runs_gpu_runnable(product, oracle, fmt, flags):
+    O = oracle
+    raw = V.ref_iq(1500, fmt=fmt)
+    base = ["--" + fmt, "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2"]
+    ref_flags = [f for f in flags if not f.startswith("--gpu")]
+    want = V.ref_leandvb(raw, base + ref_flags)
+    out = subprocess.run([O.ref_bin("leandvb_gpu"), *base, *flags, "--gpu-batch", str(1 << 20)],
+                         input=raw.tobytes(), stdout=subprocess.PIPE, check=True).stdout
+    got = np.frombuffer(out, dtype=np.uint8).reshape(-1, 188)
+    n = min(len(got), len(want))
+    assert n > 1400
+    assert np.array_equal(got[:n], want[:n])
+    assert 0 <= len(got) - len(want) <= 1
