@@ -192,6 +192,23 @@ struct DeconvArgs {
 // carry_out (device, 5 x uint64): register, n_in, accumulator, n_out, symbols consumed.
 cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st);
 
+// --------------------------------------------------------------------- K5 Viterbi
+struct VitDecState { int32_t cost[64]; uint64_t path[64]; int32_t bank, pad; };
+struct VitCtl { int32_t current_sync, resync_phase; };
+struct VitArgs {
+  const uint32_t *symbols;   // softsymbols, element 0 = first unread symbol
+  uint64_t nchunks;          // chunks of 128 FEC blocks (dvb.h:1372-1373)
+  int bits_in, bits_out, bps, nshifts, nsyncs, ncs, nsymbols;
+  int path_nbits, path_depth, path32, resync_period;
+  const uint8_t *trellis_pred, *trellis_us;   // [64][ncs], pred == 65: no branch
+  const uint8_t *maps;       // [nsyncs][nsymbols] (dvb.h:1336-1351)
+  const int32_t *shifts;     // [nsyncs]
+  VitDecState *state;        // [nsyncs]
+  VitCtl *ctl;
+  uint8_t *out;              // nchunks * 128 * bits_in / 8 bytes
+};
+cudaError_t launch_viterbi(const VitArgs &a, cudaStream_t st);
+
 // ---------------------------------------------------------------- K6/K7 framing
 struct SyncState {
   int32_t synchronized, bitphase, polarity, phase8;

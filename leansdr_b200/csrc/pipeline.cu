@@ -120,6 +120,9 @@ struct ldvb_handle {
   HypState hyp[4];
   int locked = 0, skip = 0;
   DevBuf d_deconv_carry;
+  // Viterbi (viterbi_sync)
+  Trellis trellis; VitSyncs vsyncs;
+  DevBuf d_vit_pred, d_vit_us, d_vit_maps, d_vit_shifts, d_vit_state, d_vit_ctl;
   SyncState sync;
   DevBuf d_sync_state, d_sync_res;
   int derand_pos = 0;
@@ -299,6 +302,10 @@ void reset_carry(ldvb_handle *h) {
   }
   for (HypState &s : h->hyp) s = HypState();
   h->locked = 0; h->skip = 0;
+  if (h->d_vit_state.p) {   // viterbi_dec constructor: metrics 0, paths 0 (viterbi.h:133-145)
+    cudaMemset(h->d_vit_state.p, 0, h->d_vit_state.bytes);
+    cudaMemset(h->d_vit_ctl.p, 0, h->d_vit_ctl.bytes);
+  }
   memset(&h->sync, 0, sizeof h->sync);
   h->sync.report_state = 1;
   h->sync.phase8 = -1;
@@ -400,7 +407,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
-                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
+                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
   for (DevBuf *b : bufs) b->release();
   for (Tap &t : h->taps) t.buf.release();
   for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -431,7 +438,6 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   };
   if (c.input_format < 0 || c.input_format > LDVB_FMT_F32) return bail(LDVB_EINVAL, "bad input_format");
   if (c.fastlock) return bail(LDVB_EINVAL, "--fastlock is not supported");
-  if (c.viterbi) return bail(LDVB_EINVAL, "--viterbi is not supported yet");
   if (c.sampler == LDVB_SAMP_RRC) return bail(LDVB_EINVAL, "--sampler rrc is not supported yet");
   if (c.sampler < 0 || c.sampler > 2) return bail(LDVB_EINVAL, "bad sampler");
   if (c.anf < 0 || c.anf > kNotchMaxSlots) return bail(LDVB_EINVAL, "anf must be 0..4");
@@ -442,7 +448,26 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   // ---- tables
   h->cst = make_cstln(c.constellation, c.hard_metric != 0);
   if (h->cst.nsymbols == 0) return bail(LDVB_EINVAL, "constellation not supported");
-  if (!make_deconv(c.fec, &h->dec)) return bail(LDVB_EINVAL, "code rate not supported");
+  int fec = c.fec;
+  if (c.viterbi && fec == LDVB_FEC23 && h->cst.nsymbols == 4) fec = LDVB_FEC46;  // leandvb.cc:533-537
+  if (!c.viterbi && !make_deconv(fec, &h->dec)) return bail(LDVB_EINVAL, "code rate not supported");
+  if (c.viterbi) {
+    if (!make_trellis(fec, &h->trellis)) return bail(LDVB_EINVAL, "code rate not supported by the Viterbi decoder");
+    int bps = 0; while ((1 << bps) < h->cst.nsymbols) ++bps;
+    if (h->trellis.bits_out % bps) return bail(LDVB_EINVAL, "code rate not suitable for this constellation");  // dvb.h:1247-1251
+    h->vsyncs = make_vitsyncs(h->cst, h->trellis);
+    if (h->vsyncs.nsyncs > 16) return bail(LDVB_EINVAL, "too many Viterbi hypotheses");
+    std::vector<uint8_t> maps;
+    for (auto &m : h->vsyncs.map) maps.insert(maps.end(), m.begin(), m.end());
+    std::vector<int32_t> shifts(h->vsyncs.shift.begin(), h->vsyncs.shift.end());
+    bool vok = upload(h->d_vit_pred, h->trellis.pred.data(), h->trellis.pred.size()) == cudaSuccess &&
+               upload(h->d_vit_us, h->trellis.us.data(), h->trellis.us.size()) == cudaSuccess &&
+               upload(h->d_vit_maps, maps.data(), maps.size()) == cudaSuccess &&
+               upload(h->d_vit_shifts, shifts.data(), shifts.size() * 4) == cudaSuccess &&
+               h->d_vit_state.alloc(sizeof(VitDecState) * h->vsyncs.nsyncs) == cudaSuccess &&
+               h->d_vit_ctl.alloc(sizeof(VitCtl)) == cudaSuccess;
+    if (!vok) return bail(LDVB_ECUDA, "viterbi tables");
+  }
   std::vector<float> trig = make_trig16();
   uint8_t gexp[512], glog[256];
   make_rs_tables(gexp, glog);
@@ -1042,6 +1067,36 @@ int deconv_commit(ldvb_handle *h, const DeconvRun &run) {
   return stream_consume(h, h->s_sym, run.consumed, h->d_scratch);
 }
 
+// viterbi_sync::run (dvb.h:1366-1414): whole chunks of 128 FEC blocks.
+int run_viterbi(ldvb_handle *h, uint64_t *produced) {
+  Stream &in = h->s_sym;
+  *produced = 0;
+  const int nsh = h->vsyncs.nshifts, bits_in = h->trellis.bits_in;
+  const uint64_t need = (uint64_t)nsh * 128 + (nsh - 1);
+  if (in.count < need) return LDVB_OK;
+  uint64_t nchunks = (in.count - (nsh - 1)) / ((uint64_t)nsh * 128);
+  const uint64_t bpc = (uint64_t)16 * bits_in;   // bytes per chunk
+  nchunks = std::min(nchunks, (h->s_bytes.cap - h->s_bytes.count) / bpc);
+  if (!nchunks) return LDVB_OK;
+  VitArgs a;
+  memset(&a, 0, sizeof a);
+  a.symbols = reinterpret_cast<const uint32_t *>(in.at(0));
+  a.nchunks = nchunks;
+  a.bits_in = bits_in; a.bits_out = h->trellis.bits_out; a.bps = h->vsyncs.bps; a.nshifts = nsh;
+  a.nsyncs = h->vsyncs.nsyncs; a.ncs = h->trellis.ncs; a.nsymbols = h->cst.nsymbols;
+  a.path_nbits = h->trellis.path_nbits; a.path_depth = h->trellis.path_depth; a.path32 = h->trellis.path32 ? 1 : 0;
+  a.resync_period = 32;   // dvb.h:1241
+  a.trellis_pred = h->d_vit_pred.as<uint8_t>(); a.trellis_us = h->d_vit_us.as<uint8_t>();
+  a.maps = h->d_vit_maps.as<uint8_t>(); a.shifts = h->d_vit_shifts.as<int32_t>();
+  a.state = h->d_vit_state.as<VitDecState>(); a.ctl = h->d_vit_ctl.as<VitCtl>();
+  a.out = h->s_bytes.at(h->s_bytes.count);
+  KL("viterbi", launch_viterbi(a, h->st));
+  *produced = nchunks * bpc;
+  h->s_bytes.count += *produced;
+  h->s_bytes.fresh += *produced;
+  return stream_consume(h, in, nchunks * 128 * (uint64_t)nsh, h->d_scratch);
+}
+
 int run_sync(ldvb_handle *h) {
   Stream &in = h->s_bytes;
   Stream &out = h->s_mpeg;
@@ -1206,7 +1261,22 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
 
   // ---- deconvolution <-> sync (with the backward next_sync edge, dvb.h:771-778)
   std::vector<uint8_t> tap_bytes;  // bytes that stay in the stream, for the tap
-  for (int guard = 0; guard < 64; ++guard) {
+  if (c.viterbi) {
+    uint64_t produced = 0;
+    const uint64_t at = h->s_bytes.count;
+    if ((rc = run_viterbi(h, &produced))) return rc;
+    if (c.keep_taps && produced) {
+      tap_bytes.resize(produced);
+      CK(cudaMemcpy(tap_bytes.data(), h->s_bytes.at(at), produced, cudaMemcpyDeviceToHost));
+    }
+    // mpeg_sync has no deconvolver to poke in this mode (leandvb.cc:560: r_deconv == NULL)
+    for (int guard = 0; guard < 1 << 20; ++guard) {
+      rc = run_sync(h);
+      if (rc < 0) return rc;
+      if (rc == 0) break;
+    }
+  }
+  for (int guard = 0; guard < 64 && !c.viterbi; ++guard) {
     if (h->skip) {  // dvb.h:415-416
       if (h->s_sym.count < (uint64_t)h->skip) break;
       if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;

@@ -144,6 +144,29 @@ def test_fast_mode_ts_bit_exact(product, oracle, name, kw, gkw, npk):
     assert mism <= (0 if "noise" not in name else 20), f"{mism} hard-symbol mismatches, {m}"
 
 
+VIT_CASES = [
+    ("vit12-noise", dict(fmt="f32", viterbi=True), dict(noise_db=25), 400),
+    ("vit12-u8", dict(fmt="u8", viterbi=True, resample=True), {}, 300),
+    ("vit78", dict(fmt="f32", viterbi=True, fec="7/8", Fs=55e6, Fm=27.5e6), dict(cr="7/8", ratio="2"), 260),
+    ("vit34", dict(fmt="f32", viterbi=True, fec="3/4", Fs=4e6, Fm=2e6), dict(cr="3/4", ratio="2"), 260),
+]
+
+
+@pytest.mark.parametrize("name,kw,gkw,npk", VIT_CASES, ids=[c[0] for c in VIT_CASES])
+def test_viterbi_bit_exact(product, oracle, name, kw, gkw, npk):
+    """viterbi_sync on the GPU (trellis ACS, hypothesis tracking) against the oracle, which is
+    itself pinned to the reference's viterbi_sync (tests/test_oracle_cpu.py)."""
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["bytes"], ref["bytes"], "Viterbi bytes")
+    assert_prefix(got["mpegbytes"], ref["mpegbytes"], "aligned bytes")
+    assert_prefix(got["ts"], ref["ts"], "TS")
+    assert len(ref["ts"]) > npk - 120
+
+
 def test_golden_fixture_through_cuda(product):
     """Committed vector decoded by the unmodified reference (tests/golden/make_golden.py)."""
     P = product
