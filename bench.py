@@ -116,7 +116,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--packets", type=int, default=16384, help="TS packets in the synthetic stream (1 packet ~ 1958 samples)")
+    ap.add_argument("--packets", type=int, default=65536, help="TS packets in the synthetic stream (1 packet ~ 1958 samples)")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -132,6 +132,8 @@ def default_config(**kw) -> Config:
             cfg.fec = FEC[v] if isinstance(v, str) else v
         elif k == "sampler":
             cfg.sampler = SAMPLER[v] if isinstance(v, str) else v
+        elif k == "sub_batch":
+            cfg.reserved[0] = int(v)
         elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps"):
             setattr(cfg, k, int(v))
         else:

@@ -368,36 +368,47 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
       float2 *outp = a.out + (uint64_t)blk * kNotchN + (uint64_t)tib * kNTile;
       uint32_t lead; { const unsigned char *unused; locate((uint64_t)blk * kNotchN + (uint64_t)tib * kNTile, unused, lead); }
       const unsigned char *myrow = stage_base[st] + (size_t)lane * kNPitch;
-      if (write) {
-#pragma unroll 4
-        for (int n = 0; n < kNTile; ++n) {
-          const float2 x = row_sample<FMT>(myrow, lead + n, a.scale);
-          float outr = x.x, outi = x.y;
+      // Eight samples per step: loads and the products that do not depend on the
+      // estimate are issued first (ILP), then the 8-step serial chain
+      // estim = bb*k + estim*(1-k), then the subtraction and the stores.
+      constexpr int U = 8;
+#pragma unroll 1
+      for (int n0 = 0; n0 < kNTile; n0 += U) {
+        float2 x[U], e[U][NSLOTS];
+        float bkr[U][NSLOTS], bki[U][NSLOTS];
 #pragma unroll
-          for (int s = 0; s < NSLOTS; ++s) {
-            const float2 e = __ldg(tab[s] + n);
-            const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
-            const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
-            er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
-            ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
-            outr = fsub(outr, fsub(fmul(er[s], e.x), fmul(ei[s], e.y)));
-            outi = fsub(outi, fadd(fmul(er[s], e.y), fmul(ei[s], e.x)));
-          }
-          if (!unit_gain) { outr = fmul(gain, outr); outi = fmul(gain, outi); }
-          st_stream(outp + n, make_float2(outr, outi));
+        for (int j = 0; j < U; ++j) {
+          x[j] = row_sample<FMT>(myrow, lead + n0 + j, a.scale);
+#pragma unroll
+          for (int s = 0; s < NSLOTS; ++s) e[j][s] = __ldg(tab[s] + n0 + j);
         }
-      } else {
-        // Warm-up block: only the estimate recurrence, nothing is written.
-#pragma unroll 4
-        for (int n = 0; n < kNTile; ++n) {
-          const float2 x = row_sample<FMT>(myrow, lead + n, a.scale);
+#pragma unroll
+        for (int j = 0; j < U; ++j)
 #pragma unroll
           for (int s = 0; s < NSLOTS; ++s) {
-            const float2 e = __ldg(tab[s] + n);
-            const float bbr = fadd(fmul(x.x, e.x), fmul(x.y, e.y));
-            const float bbi = fadd(fmul(-x.x, e.y), fmul(x.y, e.x));
-            er[s] = fadd(fmul(bbr, k), fmul(er[s], omk));
-            ei[s] = fadd(fmul(bbi, k), fmul(ei[s], omk));
+            bkr[j][s] = fmul(fadd(fmul(x[j].x, e[j][s].x), fmul(x[j].y, e[j][s].y)), k);
+            bki[j][s] = fmul(fadd(fmul(-x[j].x, e[j][s].y), fmul(x[j].y, e[j][s].x)), k);
+          }
+        float esr[U][NSLOTS], esi[U][NSLOTS];
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+#pragma unroll
+          for (int s = 0; s < NSLOTS; ++s) {
+            er[s] = fadd(bkr[j][s], fmul(er[s], omk));
+            ei[s] = fadd(bki[j][s], fmul(ei[s], omk));
+            esr[j][s] = er[s]; esi[j][s] = ei[s];
+          }
+        if (write) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            float outr = x[j].x, outi = x[j].y;
+#pragma unroll
+            for (int s = 0; s < NSLOTS; ++s) {
+              outr = fsub(outr, fsub(fmul(esr[j][s], e[j][s].x), fmul(esi[j][s], e[j][s].y)));
+              outi = fsub(outi, fadd(fmul(esr[j][s], e[j][s].y), fmul(esi[j][s], e[j][s].x)));
+            }
+            if (!unit_gain) { outr = fmul(gain, outr); outi = fmul(gain, outi); }
+            st_stream(outp + n0 + j, make_float2(outr, outi));
           }
         }
       }

@@ -168,16 +168,19 @@ __device__ __forceinline__ void rx_chunk_end(const RxParams &p, RxRun &r) {
 }
 
 template <int SAMPLER>
-__device__ void rx_warp(const RxArgs &a, int only_span, const RxState *forced, unsigned char *smem_warp,
-                        uint64_t *bars) {
+__device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_warp) {
   const RxParams &p = a.p;
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  // Span of this lane.  In repair mode only lane 0 of warp 0 works, on `only_span`.
+  // Span of this lane.  Repair mode (span_list): lane g re-runs span span_list[g] exactly,
+  // from the end state of its predecessor (a.state_end[span - 1]).
+  const bool repair = (span_list != nullptr);
+  const uint32_t g = warp_global * 32 + lane;
   uint32_t span;
   bool have_span;
-  if (only_span >= 0) { span = (uint32_t)only_span; have_span = (warp_global == 0 && lane == 0); }
-  else { span = warp_global * 32 + lane; have_span = span < a.nspans; }
+  if (repair) { have_span = g < nlist; span = have_span ? span_list[g] : 0; }
+  else { span = g; have_span = span < a.nspans; }
+  const RxState *forced = (repair && have_span) ? a.state_end + (span - 1) : nullptr;
 
   const uint64_t S = a.span_chunks, W = a.warm_chunks;
   uint64_t own_begin = 0, own_end = 0, run_begin = 0, run_end = 0;
@@ -210,16 +213,13 @@ __device__ void rx_warp(const RxArgs &a, int only_span, const RxState *forced, u
   // Lanes outside [run_begin, run_end) idle but keep the barrier protocol.
   int64_t base;          // chunk index of local iteration 0 for this lane
   uint64_t iters;
-  if (only_span >= 0) { base = (int64_t)run_begin; iters = run_end - run_begin; }
+  if (repair) { base = (int64_t)run_begin; iters = S + kRxVerifyChunks; }
   else { base = (int64_t)((uint64_t)span * S) - (int64_t)W; iters = W + S + kRxVerifyChunks; }
-  iters = __shfl_sync(0xffffffffu, iters, 0);
 
   unsigned char *stage_base[kStages];
   for (int s = 0; s < kStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kRowBytes;
   // Row r of the warp = lane r's span; its chunk at local iteration i is base_r + i.
   const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
-  const int64_t base_step = (only_span >= 0) ? 0 : (int64_t)S;
-  (void)bars;
 
   const uint64_t total_tiles = iters * kTilesPerChunk;
   constexpr int kChunks16 = kRowBytes / 16;  // 17 x 16 B per row
@@ -234,8 +234,10 @@ __device__ void rx_warp(const RxArgs &a, int only_span, const RxState *forced, u
     for (int k = 0; k < kChunks16; ++k) {
       const int id = k * 32 + lane;
       const int r = id / kChunks16, q = id - r * kChunks16;
+      // Row r belongs to lane r: consecutive spans in normal mode, arbitrary in repair mode.
+      const int64_t base_r = repair ? __shfl_sync(0xffffffffu, base, r) : base0 + (int64_t)r * (int64_t)S;
       if ((mask >> r) & 1u) {
-        const int64_t cr = base0 + (int64_t)r * base_step + (int64_t)i;
+        const int64_t cr = base_r + (int64_t)i;
         const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + (uint64_t)cr * kRxChunk + col0) + q * 16;
         cp_async16(stage_base[st] + (size_t)r * kRowBytes + q * 16, src);
       }
@@ -330,23 +332,22 @@ __device__ void rx_warp(const RxArgs &a, int only_span, const RxState *forced, u
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_rx(RxArgs a, int only_span, const RxState *forced) {
+k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[kWarpsPerBlock * kStages];
   const int warp = threadIdx.x >> 5;
   unsigned char *smem_warp = smem + (size_t)warp * kStages * 32 * kRowBytes;
-  if (a.p.sampler == 0) rx_warp<0>(a, only_span, forced, smem_warp, bars + warp * kStages);
-  else rx_warp<1>(a, only_span, forced, smem_warp, bars + warp * kStages);
+  if (a.p.sampler == 0) rx_warp<0>(a, span_list, nlist, smem_warp);
+  else rx_warp<1>(a, span_list, nlist, smem_warp);
 }
 
 // ---------------------------------------------------------------- seam stitching
 
 // One warp per seam: lanes stride over the logged symbols.
 __global__ void __launch_bounds__(128)
-k_rx_stitch(RxStitchArgs a, int only_seam) {
+k_rx_stitch(RxStitchArgs a, const uint32_t *seam_list, uint32_t nlist) {
   const int lane = threadIdx.x & 31;
-  uint32_t j = (only_seam >= 0) ? (uint32_t)only_seam : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (only_seam >= 0 && (blockIdx.x != 0 || (threadIdx.x >> 5) != 0)) return;
+  uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (seam_list) { if (j >= nlist) return; j = seam_list[j]; }
   if (j + 1 >= a.nspans) return;
   const RxSeamSym *tail = a.tail_log + (size_t)j * kRxSeamLog;
   const RxSeamSym *head = a.head_log + (size_t)(j + 1) * kRxSeamLog;
@@ -409,28 +410,24 @@ constexpr size_t kRxSmemPerBlock = (size_t)kWarpsPerBlock * kStages * 32 * kRowB
 
 }  // namespace
 
-cudaError_t launch_rx(const RxArgs &a, int only_span, const RxState *forced, cudaStream_t st) {
-  if (a.nspans == 0) return cudaSuccess;
+cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st) {
+  if (a.nspans == 0 || (span_list && !nlist)) return cudaSuccess;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxSmemPerBlock);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (only_span >= 0) {
-    k_rx<<<1, kWarpsPerBlock * 32, kRxSmemPerBlock, st>>>(a, only_span, forced);
-  } else {
-    const unsigned per_block = kWarpsPerBlock * 32;
-    const unsigned blocks = (a.nspans + per_block - 1) / per_block;
-    k_rx<<<blocks, per_block, kRxSmemPerBlock, st>>>(a, -1, nullptr);
-  }
+  const unsigned per_block = kWarpsPerBlock * 32;
+  const unsigned lanes = span_list ? nlist : a.nspans;
+  k_rx<<<(lanes + per_block - 1) / per_block, per_block, kRxSmemPerBlock, st>>>(a, span_list, nlist);
   return cudaGetLastError();
 }
 
-cudaError_t launch_rx_stitch(const RxStitchArgs &a, int only_seam, cudaStream_t st) {
-  if (a.nspans < 2) return cudaSuccess;
-  if (only_seam >= 0) k_rx_stitch<<<1, 32, 0, st>>>(a, only_seam);
-  else k_rx_stitch<<<(a.nspans - 1 + 3) / 4, 128, 0, st>>>(a, -1);
+cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st) {
+  if (a.nspans < 2 || (seam_list && !nlist)) return cudaSuccess;
+  const unsigned n = seam_list ? nlist : a.nspans - 1;
+  k_rx_stitch<<<(n + 3) / 4, 128, 0, st>>>(a, seam_list, nlist);
   return cudaGetLastError();
 }
 

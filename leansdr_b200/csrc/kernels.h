@@ -146,8 +146,9 @@ struct RxArgs {
   uint32_t *meas_count;      // optional counter
   uint32_t max_meas;
 };
-// only_span < 0: all spans.  Otherwise re-run one span from forced_state (seam repair).
-cudaError_t launch_rx(const RxArgs &a, int only_span, const RxState *forced_state, cudaStream_t st);
+// span_list == nullptr: all spans.  Otherwise the listed spans are re-run exactly from the end
+// state of their predecessors (a.state_end[span - 1]) -- seam repair.
+cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st);
 
 struct RxSeam {
   int32_t ok;              // verification passed
@@ -164,7 +165,7 @@ struct RxStitchArgs {
   float omega;
   RxSeam *seams;             // [nspans-1]
 };
-cudaError_t launch_rx_stitch(const RxStitchArgs &a, int only_seam, cudaStream_t st);
+cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st);
 
 // Concatenates the span outputs into one contiguous softsymbol stream, applying
 // each span's cumulative rotation to the hard symbol.

@@ -128,6 +128,13 @@ struct ldvb_handle {
   int derand_pos = 0;
   DevBuf d_counts;
 
+  // ---- pipelined host input (ldvb_push): copy engine fills one staging buffer while
+  // the chain works on the other
+  DevBuf d_stage[2];
+  cudaStream_t copy_st = nullptr;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};
+  uint64_t sub_batch = 0;
+
   // ---- host-side TS queue for push/pull
   std::vector<uint8_t> ts_queue;
   size_t ts_queue_rd = 0;
@@ -410,6 +417,8 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
   for (DevBuf *b : bufs) b->release();
   for (Tap &t : h->taps) t.buf.release();
+  for (int i = 0; i < 2; ++i) { h->d_stage[i].release(); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
+  if (h->copy_st) cudaStreamDestroy(h->copy_st);
   for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto &e : h->prof_free) cudaEventDestroy(e);
   if (h->st && h->own_stream) cudaStreamDestroy(h->st);
@@ -518,6 +527,8 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   }
   h->Fs_rx = Fs;
   rx_setup(h);
+  // Host batches larger than this are pipelined (copy/compute overlap); reserved[0] overrides.
+  h->sub_batch = c.reserved[0] > 0 ? (uint64_t)c.reserved[0] : (uint64_t)16 << 20;
 
   // ---- stream buffers
   const uint64_t M = c.max_batch;
@@ -887,7 +898,7 @@ int run_receiver(ldvb_handle *h) {
       CK(smp.alloc(nchunks * 8)); CK(smpf.alloc(nchunks * 4));
       a.sampled = smp.as<float2>(); a.sampled_flag = smpf.as<uint32_t>();
     }
-    KL("rx", launch_rx(a, -1, nullptr, h->st));
+    KL("rx", launch_rx(a, nullptr, 0, h->st));
     RxSpanInfo inf;
     CK(cudaMemcpyAsync(&inf, a.info, sizeof inf, cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(&h->rx_state, a.state_end, sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
@@ -923,13 +934,13 @@ int run_receiver(ldvb_handle *h) {
     a.sym_out = h->d_rx_spans.as<uint32_t>();
     a.head_log = h->d_rx_head.as<RxSeamSym>();
     a.tail_log = h->d_rx_tail.as<RxSeamSym>();
-    KL("rx", launch_rx(a, -1, nullptr, h->st));
+    KL("rx", launch_rx(a, nullptr, 0, h->st));
     RxStitchArgs sa;
     sa.info = a.info; sa.head_log = a.head_log; sa.tail_log = a.tail_log;
     sa.nspans = a.nspans; sa.nrot = h->cst.nrotations; sa.nsymbols = h->cst.nsymbols;
     sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
     sa.seams = h->d_rx_seams.as<RxSeam>();
-    KL("rx_stitch", launch_rx_stitch(sa, -1, h->st));
+    KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
     std::vector<RxSeam> seams(a.nspans);
     std::vector<RxSpanInfo> info(a.nspans);
     auto fetch = [&]() -> int {
@@ -941,18 +952,37 @@ int run_receiver(ldvb_handle *h) {
     int rc = fetch();
     if (rc) return rc;
     h->meas.seams_total += a.nspans - 1;
-    // Repair failed seams in stream order: span j+1 is re-run exactly from the
-    // end state of span j, then its two seams are stitched again.
-    for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
-      if (seams[j].ok) continue;
-      ++h->meas.seams_repaired;
-      KL("rx", launch_rx(a, (int)(j + 1), a.state_end + j, h->st));
-      // An exact continuation needs no alignment: its first symbol follows span j's last.
-      if (j + 2 < a.nspans) { KL("rx_stitch", launch_rx_stitch(sa, (int)(j + 1), h->st)); }
+    // Repair failed seams: span j+1 is re-run exactly from the end state of span j.  All
+    // failed spans whose predecessor is final are repaired in ONE launch per round; the
+    // seam behind each repaired span is stitched again (its tail changed).
+    std::vector<uint8_t> fixed(a.nspans, 0);   // seam j resolved by an exact re-run of span j+1
+    for (int round = 0; round < 1 << 20; ++round) {
+      std::vector<uint32_t> spans, restitch;
+      bool prev_bad = false;
+      for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
+        const bool bad = !seams[j].ok && !fixed[j];
+        if (bad && !prev_bad) spans.push_back(j + 1);
+        prev_bad = bad;
+      }
+      if (spans.empty()) break;
+      h->meas.seams_repaired += (uint32_t)spans.size();
+      for (uint32_t sp : spans) {
+        fixed[sp - 1] = 1;
+        if (sp + 1 < a.nspans) { fixed[sp] = 0; restitch.push_back(sp); }
+      }
+      if (h->d_scratch.bytes < (spans.size() + restitch.size()) * 4) return fail(h, LDVB_EOVERFLOW, "repair list");
+      uint32_t *d_list = h->d_scratch.as<uint32_t>();
+      CK(cudaMemcpyAsync(d_list, spans.data(), spans.size() * 4, cudaMemcpyHostToDevice, h->st));
+      KL("rx", launch_rx(a, d_list, (uint32_t)spans.size(), h->st));
+      if (!restitch.empty()) {
+        CK(cudaMemcpyAsync(d_list + spans.size(), restitch.data(), restitch.size() * 4, cudaMemcpyHostToDevice, h->st));
+        KL("rx_stitch", launch_rx_stitch(sa, d_list + spans.size(), (uint32_t)restitch.size(), h->st));
+      }
       rc = fetch();
       if (rc) return rc;
-      seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0;
     }
+    for (uint32_t j = 0; j + 1 < a.nspans; ++j)
+      if (fixed[j]) { seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0; }
     // Offsets, skips and cumulative rotations.
     std::vector<uint64_t> off(a.nspans + 1, 0);
     std::vector<uint32_t> skipv(a.nspans, 0);
@@ -1267,7 +1297,8 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
     if ((rc = run_viterbi(h, &produced))) return rc;
     if (c.keep_taps && produced) {
       tap_bytes.resize(produced);
-      CK(cudaMemcpy(tap_bytes.data(), h->s_bytes.at(at), produced, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpyAsync(tap_bytes.data(), h->s_bytes.at(at), produced, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
     }
     // mpeg_sync has no deconvolver to poke in this mode (leandvb.cc:560: r_deconv == NULL)
     for (int guard = 0; guard < 1 << 20; ++guard) {
@@ -1329,23 +1360,61 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
 
 extern "C" {
 
+static int push_collect(ldvb_handle *h, uint64_t got) {
+  if (!got) return LDVB_OK;
+  const size_t o = h->ts_queue.size();
+  h->ts_queue.resize(o + got * 188);
+  CK(cudaMemcpyAsync(h->ts_queue.data() + o, h->d_ts.p, got * 188, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return LDVB_OK;
+}
+
+// Large host batches: sub-batches are copied to two device staging buffers on a
+// separate stream while the chain processes the previous one in place, so the
+// PCIe transfer overlaps the kernels.
+static int push_pipelined(ldvb_handle *h, const uint8_t *host, size_t n) {
+  const uint64_t sub = h->sub_batch;
+  const size_t bps = h->s_raw.elem;
+  if (!h->copy_st) {
+    CK(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(h->d_stage[i].alloc(sub * bps + 256));
+      CK(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+    }
+  }
+  const uint64_t nsub = (n + sub - 1) / sub;
+  auto issue = [&](uint64_t i) -> int {
+    const uint64_t off = i * sub, m = std::min<uint64_t>(sub, n - off);
+    CK(cudaMemcpyAsync(h->d_stage[i & 1].p, host + off * bps, m * bps, cudaMemcpyHostToDevice, h->copy_st));
+    CK(cudaEventRecord(h->copy_done[i & 1], h->copy_st));
+    return LDVB_OK;
+  };
+  int rc = issue(0);
+  if (rc) return rc;
+  for (uint64_t i = 0; i < nsub; ++i) {
+    CK(cudaStreamWaitEvent(h->st, h->copy_done[i & 1], 0));
+    if (i + 1 < nsub && (rc = issue(i + 1))) return rc;   // the other buffer is idle: run_chain is synchronous
+    const uint64_t m = std::min<uint64_t>(sub, n - i * sub);
+    uint64_t got = 0;
+    if ((rc = run_chain(h, h->d_stage[i & 1].p, true, m, h->d_ts.as<uint8_t>(), h->ts_cap, &got))) return rc;
+    if ((rc = push_collect(h, got))) return rc;
+  }
+  return LDVB_OK;
+}
+
 int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n) {
   if (!h || (!iq_host && n)) return LDVB_EINVAL;
   if (n > h->cfg.max_batch) return fail(h, LDVB_EOVERFLOW, "n_samples exceeds max_batch");
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  if (h->sub_batch && n > h->sub_batch + h->sub_batch / 2)
+    return push_pipelined(h, static_cast<const uint8_t *>(iq_host), n);
   Stream &raw = h->s_raw;
   if (raw.count + n > raw.cap) return fail(h, LDVB_EOVERFLOW, "raw stream overflow");
   if (n) CK(cudaMemcpyAsync(raw.at(raw.count), iq_host, n * raw.elem, cudaMemcpyHostToDevice, h->st));
   uint64_t got = 0;
   int rc = run_chain(h, nullptr, false, n, h->d_ts.as<uint8_t>(), h->ts_cap, &got);
   if (rc) return rc;
-  if (got) {
-    const size_t o = h->ts_queue.size();
-    h->ts_queue.resize(o + got * 188);
-    CK(cudaMemcpyAsync(h->ts_queue.data() + o, h->d_ts.p, got * 188, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-  }
-  return LDVB_OK;
+  return push_collect(h, got);
 }
 
 int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets, size_t *n_packets) {

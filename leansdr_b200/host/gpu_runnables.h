@@ -24,20 +24,18 @@ namespace leansdr {
 // matching cfg.input_format.  Tpacket: dvb.h's tspacket (188 bytes).
 template<typename Tin, typename Tpacket>
 struct gpu_dvbs_receiver : runnable {
-  // Batching: run() hands everything readable to the GPU, but not less than
-  // [min_batch] samples unless the input has stalled for [patience] calls
-  // (end of stream): small pushes are legal but waste launch latency.
-  unsigned long min_batch;
-  int patience;
-
+  // run() hands everything readable to the GPU at once.  It must not hold data
+  // back: a step in which no pipe counter moves ends scheduler::run()
+  // (framework.h:96-104), so "wait for a bigger batch" is not expressible.  Batch
+  // size is therefore set by the input pipebuf (--inbuf / --buf-factor): a
+  // file_reader fills it completely on every step (generic.h:51).
   gpu_dvbs_receiver(scheduler *sch, pipebuf<Tin> &_in, pipebuf<Tpacket> &_out,
 		    const ldvb_config &cfg,
 		    pipebuf<float> *_freq_out=NULL, pipebuf<float> *_ss_out=NULL,
 		    pipebuf<float> *_mer_out=NULL, pipebuf<int> *_lock_out=NULL,
 		    pipebuf<float> *_vber_out=NULL)
     : runnable(sch, "gpu_dvbs_receiver"),
-      min_batch(1<<16), patience(2),
-      in(_in), out(_out), handle(NULL), starved(0), last_readable(0),
+      in(_in), out(_out), handle(NULL),
       last_lock(-1), rs_bits(0), rs_errs(0) {
     if ( sizeof(Tpacket) != 188 ) fail("gpu_dvbs_receiver: Tpacket must be 188 bytes");
     freq_out = opt_writer(_freq_out);
@@ -58,12 +56,6 @@ struct gpu_dvbs_receiver : runnable {
     unsigned long n = in.readable();
     if ( n > max_batch ) n = max_batch;
     if ( !n ) return;
-    if ( n < min_batch ) {
-      // Wait for more unless the producer has stopped delivering.
-      if ( n != last_readable ) { last_readable = n; starved = 0; return; }
-      if ( ++starved < patience ) return;
-    }
-    starved = 0; last_readable = 0;
     int rc = ldvb_push(handle, in.rd(), n);
     if ( rc ) { fprintf(stderr, "ldvb_push: %s (%s)\n", ldvb_strerror(rc), ldvb_last_error(handle)); fail("gpu_dvbs_receiver"); }
     in.read(n);
@@ -105,8 +97,6 @@ private:
   pipewriter<Tpacket> out;
   ldvb_handle *handle;
   unsigned long max_batch;
-  int starved;
-  unsigned long last_readable;
   pipewriter<float> *freq_out, *ss_out, *mer_out, *vber_out;
   pipewriter<int> *lock_out;
   int last_lock;

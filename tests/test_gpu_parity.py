@@ -167,6 +167,20 @@ def test_viterbi_bit_exact(product, oracle, name, kw, gkw, npk):
     assert len(ref["ts"]) > npk - 120
 
 
+def test_pipelined_host_push(product, oracle):
+    """ldvb_push of a batch larger than the sub-batch size: copies overlap the kernels
+    (two staging buffers); the result must not depend on how the batch was cut."""
+    P, O = product, oracle
+    raw = V.ref_iq(1500, fmt="u8")
+    ref = O.Chain(O.Config(fmt="u8", resample=True)).run(raw)
+    rx = P.Receiver(fmt="u8", resample=True, rx_mode=P.RX_FAST, max_batch=raw.size // 2, sub_batch=300000)
+    rx.push(raw)
+    ts = rx.pull_all()
+    rx.close()
+    n = min(len(ts), len(ref["ts"]))
+    assert n > 1400 and np.array_equal(ts[:n], ref["ts"][:n]) and abs(len(ts) - len(ref["ts"])) <= 1
+
+
 def test_golden_fixture_through_cuda(product):
     """Committed vector decoded by the unmodified reference (tests/golden/make_golden.py)."""
     P = product
