@@ -200,7 +200,8 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
       load_state(r, *forced);
       run_begin = own_begin;
     } else if (run_begin > 0) {
-      // Warm-up: the carried loop state with the timing / phase registers cleared.
+      // Warm-up: the carried loop state (frequency, AGC) with the timing / phase registers cleared.
+      load_state(r, *a.warm_in);
       r.mu = 0.f; r.phase = 0.f;
       r.h0pr = r.h0pi = r.h0cr = r.h0ci = 0.f;
       r.h1pr = r.h1pi = r.h1cr = r.h1ci = 0.f;

@@ -135,6 +135,7 @@ struct RxArgs {
   uint32_t nspans;
   uint32_t span_cap;         // symbol capacity of one span's output region
   const RxState *state_in;   // exact/carried state at chunk 0
+  const RxState *warm_in;    // loop state (freqw, AGC) that warm-ups start from; usually == state_in
   uint32_t *sym_out;         // [nspans][span_cap] softsymbols {cost:16, symbol:8, 0}
   RxSpanInfo *info;          // [nspans]
   RxState *state_end;        // [nspans] state at the span's nominal end

@@ -528,7 +528,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   h->Fs_rx = Fs;
   rx_setup(h);
   // Host batches larger than this are pipelined (copy/compute overlap); reserved[0] overrides.
-  h->sub_batch = c.reserved[0] > 0 ? (uint64_t)c.reserved[0] : (uint64_t)16 << 20;
+  h->sub_batch = c.reserved[0] > 0 ? (uint64_t)c.reserved[0] : (uint64_t)32 << 20;
 
   // ---- stream buffers
   const uint64_t M = c.max_batch;
@@ -878,6 +878,7 @@ int run_receiver(ldvb_handle *h) {
   CK(cudaMemcpyAsync(h->d_rx_state.p, &h->rx_state, sizeof(RxState), cudaMemcpyHostToDevice, h->st));
   CK(cudaMemsetAsync(h->d_rx_measn.p, 0, 4, h->st));
   a.state_in = h->d_rx_state.as<RxState>();
+  a.warm_in = a.state_in;
   a.info = h->d_rx_info.as<RxSpanInfo>();
   a.state_end = h->d_rx_end.as<RxState>();
   a.meas = h->d_rx_meas.as<float>();
@@ -951,6 +952,33 @@ int run_receiver(ldvb_handle *h) {
     };
     int rc = fetch();
     if (rc) return rc;
+    // Cold start with a carrier offset: the carried freqw (0) is far from the truth, most
+    // warm-ups do not converge and most seams fail.  Re-seed the warm-up state with the
+    // median frequency / power that the spans themselves reached and run them again; the
+    // loops pull in a little more each pass (span 0 always keeps the exact carried state).
+    for (int attempt = 0; attempt < 6 && a.nspans > 8; ++attempt) {
+      uint32_t nfail = 0;
+      for (uint32_t j = 0; j + 1 < a.nspans; ++j) nfail += seams[j].ok ? 0 : 1;
+      if (nfail <= std::max<uint32_t>(4, a.nspans / 32)) break;
+      std::vector<RxState> ends(a.nspans);
+      CK(cudaMemcpyAsync(ends.data(), a.state_end, sizeof(RxState) * a.nspans, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      std::vector<float> fw(a.nspans), pw(a.nspans);
+      for (uint32_t j = 0; j < a.nspans; ++j) { fw[j] = ends[j].freqw; pw[j] = ends[j].est_insp; }
+      std::nth_element(fw.begin(), fw.begin() + fw.size() / 2, fw.end());
+      std::nth_element(pw.begin(), pw.begin() + pw.size() / 2, pw.end());
+      RxState warm = h->rx_state;
+      warm.freqw = fw[fw.size() / 2];
+      warm.est_insp = pw[pw.size() / 2];
+      if (warm.est_insp > 0) warm.agc_gain = 75.0f / sqrtf(warm.est_insp);
+      CK(cudaMemcpyAsync(h->d_rx_forced.p, &warm, sizeof warm, cudaMemcpyHostToDevice, h->st));
+      a.warm_in = h->d_rx_forced.as<RxState>();
+      ++h->meas.seams_repaired;   // counted as one (global) repair pass
+      KL("rx", launch_rx(a, nullptr, 0, h->st));
+      KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
+      rc = fetch();
+      if (rc) return rc;
+    }
     h->meas.seams_total += a.nspans - 1;
     // Repair failed seams: span j+1 is re-run exactly from the end state of span j.  All
     // failed spans whose predecessor is final are repaired in ONE launch per round; the

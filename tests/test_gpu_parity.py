@@ -167,6 +167,37 @@ def test_viterbi_bit_exact(product, oracle, name, kw, gkw, npk):
     assert len(ref["ts"]) > npk - 120
 
 
+def _freq_shift(raw, f_rel, phase0=0.3):
+    x = raw.view(np.float32).reshape(-1, 2).astype(np.float64)
+    z = (x[:, 0] + 1j * x[:, 1]) * np.exp(1j * (2 * np.pi * f_rel * np.arange(x.shape[0]) + phase0))
+    out = np.empty((z.size, 2), np.float32)
+    out[:, 0] = z.real
+    out[:, 1] = z.imag
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("name,f_rel,noise,batch", [
+    ("offset-20kHz", 0.0083, None, None),
+    ("offset-20kHz-streamed", 0.0083, None, 500000),
+    ("offset-minus72kHz", -0.03, None, None),
+    ("offset-20kHz-noise25", 0.0083, 25, None),
+])
+def test_fast_mode_with_carrier_offset(product, oracle, name, f_rel, noise, batch):
+    """Carrier offset: the PLL has to acquire, every span may lock on another of the four
+    QPSK phases and batches hand a rotated frame to the next one.  TS must still be
+    bit-identical to the serial reference algorithm."""
+    P, O = product, oracle
+    raw = _freq_shift(V.ref_iq(1500, fmt="f32", noise_db=noise), f_rel)
+    ref = O.Chain(O.Config(fmt="f32", anf=0)).run(raw)
+    assert len(ref["ts"]) > 1000
+    got = run_product(P, raw, n_batch=batch, rx_mode=P.RX_FAST, fmt="f32", anf=0)
+    assert_prefix(got["ts"], ref["ts"], "TS", slack=188)
+    m = got["meas"]
+    a = got["symbols"].reshape(-1, 4)[:, 2]
+    b = ref["symbols"][:, 2]
+    assert abs(a.size - b.size) <= 2, (a.size, b.size, m)
+
+
 def test_pipelined_host_push(product, oracle):
     """ldvb_push of a batch larger than the sub-batch size: copies overlap the kernels
     (two staging buffers); the result must not depend on how the batch was cut."""
