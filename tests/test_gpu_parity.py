@@ -191,11 +191,27 @@ def test_fast_mode_with_carrier_offset(product, oracle, name, f_rel, noise, batc
     ref = O.Chain(O.Config(fmt="f32", anf=0)).run(raw)
     assert len(ref["ts"]) > 1000
     got = run_product(P, raw, n_batch=batch, rx_mode=P.RX_FAST, fmt="f32", anf=0)
-    assert_prefix(got["ts"], ref["ts"], "TS", slack=188)
     m = got["meas"]
     a = got["symbols"].reshape(-1, 4)[:, 2]
     b = ref["symbols"][:, 2]
     assert abs(a.size - b.size) <= 2, (a.size, b.size, m)
+    if noise is None:
+        assert_prefix(got["ts"], ref["ts"], "TS", slack=188)
+    else:
+        # MER ~10 dB: the reference itself loses packets (RS gives up on 13 of 1500).  A span
+        # that re-converged makes a handful of different hard decisions than the serial loop,
+        # so packets at the edge of the RS correction radius can fall on either side.  What
+        # must hold: every delivered packet is a correct transmitted packet, and the two
+        # outputs differ by a few packets at most (reported, not assumed).
+        sent = V.ts_packets(1500)
+        def check(ts):
+            ts = ts[8:]
+            ctr = (ts[:, 5].astype(np.int64) << 16) | (ts[:, 6].astype(np.int64) << 8) | ts[:, 7]
+            assert (ctr < 1500).all()
+            assert np.array_equal(ts, sent[ctr])
+            return set(ctr.tolist())
+        cg, co = check(got["ts"]), check(ref["ts"])
+        assert len(cg ^ co) <= 6, (len(cg), len(co), sorted(cg ^ co))
 
 
 def test_pipelined_host_push(product, oracle):
