@@ -19,9 +19,9 @@
 // stream in lock step.  Per tile the warp stages, for every lane, that lane's
 // next 32 samples (+2 look-ahead) in a private shared-memory row: 32 rows x
 // 272 B, fetched cooperatively with 16-byte asynchronous copies (cp.async.cg,
-// SASS LDGSTS; contiguous within a row), double buffered.  The row pitch (272 B)
-// makes the 16-byte row reads of the 32 lanes bank-conflict free.  HBM sees
-// full, aligned 272-byte bursts and the recurrence never waits on a global
+// SASS LDGSTS; contiguous within a row), double buffered.  The row pitch (304 B =
+// 76 words, 12 mod 32) makes the 16-byte row reads of any 8 consecutive lanes
+// bank-conflict free.  HBM sees full, aligned 304-byte bursts and the recurrence never waits on a global
 // load.  (One TMA bulk copy per row was measured first: ~0.6 us per 272-byte
 // request, serialised per SM -- rows this small are below the TMA's grain.)  The two tables (trig16, cstln: 512 KB each) are read
 // through the read-only path; their accesses cluster around the current carrier
@@ -34,7 +34,10 @@ namespace ldvb {
 namespace {
 
 constexpr int kTile = 32;                       // samples per staged tile
-constexpr int kRowBytes = (kTile + 2) * 8;      // 272: tile + 2 look-ahead samples
+// Row = tile + look-ahead: 2 samples for the nearest/linear samplers (272 B), 6 for the RRC
+// sampler (304 B, up to 6 taps).  Both pitches are 16 B mod 128-friendly: any 8 consecutive
+// lanes read 16 B each from distinct banks.
+template <int SAMPLER> struct RowCfg { static constexpr int kBytes = (kTile + (SAMPLER == 2 ? 6 : 2)) * 8; };
 constexpr int kStages = 2;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kTilesPerChunk = kRxChunk / kTile;
@@ -44,6 +47,9 @@ struct RxRun {
   float h0pr, h0pi, h0cr, h0ci, h1pr, h1pi, h1cr, h1ci, h2pr, h2pi, h2cr, h2ci;
   float samp_freqw, freq_tap;
   uint32_t meas_count;
+  // fir_sampler (sdr.h:635-689): frequency the taps were last shifted for, update throttle
+  float rrc_f;
+  int rrc_update_phase;
   // per-chunk scratch (sdr.h:795-798)
   float sg_re, sg_im, s_re, s_im, cp_re, cp_im;
   int have_point;
@@ -56,6 +62,7 @@ __device__ __forceinline__ void load_state(RxRun &r, const RxState &s) {
   r.h1pr = s.hist[4]; r.h1pi = s.hist[5]; r.h1cr = s.hist[6]; r.h1ci = s.hist[7];
   r.h2pr = s.hist[8]; r.h2pi = s.hist[9]; r.h2cr = s.hist[10]; r.h2ci = s.hist[11];
   r.samp_freqw = s.samp_freqw; r.freq_tap = s.freq_tap; r.meas_count = s.meas_count;
+  r.rrc_f = s.rrc_f; r.rrc_update_phase = s.rrc_update_phase;
 }
 
 __device__ __forceinline__ void store_state(RxState &s, const RxRun &r) {
@@ -65,7 +72,7 @@ __device__ __forceinline__ void store_state(RxState &s, const RxRun &r) {
   s.hist[4] = r.h1pr; s.hist[5] = r.h1pi; s.hist[6] = r.h1cr; s.hist[7] = r.h1ci;
   s.hist[8] = r.h2pr; s.hist[9] = r.h2pi; s.hist[10] = r.h2cr; s.hist[11] = r.h2ci;
   s.samp_freqw = r.samp_freqw; s.freq_tap = r.freq_tap; s.meas_count = r.meas_count;
-  s.rrc_update_phase = 0; s.pad = 0;
+  s.rrc_update_phase = r.rrc_update_phase; s.rrc_f = r.rrc_f;
 }
 
 // trig16::expi(float) (math.h:104-110): index = (uint16)(int16)(int32)a.
@@ -77,13 +84,29 @@ __device__ __forceinline__ float2 expi(const float2 *__restrict__ trig, float a)
 // cur = pin[0], nxt = pin[1].  Returns true and fills `word` when a symbol is emitted.
 template <int SAMPLER>
 __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cur, float2 nxt,
-                                          uint32_t &word, float &mu_emit) {
+                                          const float2 *pin, uint32_t &word, float &mu_emit) {
   bool emitted = false;
   if (r.mu < 1.0f) {
-    // --- sampler (sdr.h:595-597, 609-618)
+    // --- sampler (sdr.h:595-597, 609-618, 647-665)
     const float2 e0 = expi(p.trig, -r.phase);
     const float2 s0 = cmul(cur, e0);
-    if (SAMPLER == 1) {
+    if (SAMPLER == 2) {
+      // fir_sampler::interp: acc = sum_j shifted[off + j*sub] * pin[j], then derotate.
+      // shifted[i] = expi(-f*(i - n/2)) * coeffs[i] (do_update_freq, sdr.h:678-682) is
+      // re-evaluated from the saved f instead of being kept as a per-lane table.
+      const int off = f2i_trunc(fmul(fsub(1.0f, r.mu), (float)p.rrc_sub));
+      float acc_re = 0.f, acc_im = 0.f;
+      int j = 0;
+      for (int ci = off; ci < p.rrc_n; ci += p.rrc_sub, ++j) {
+        const float2 e = expi(p.trig, fmul(-r.rrc_f, (float)(ci - p.rrc_n / 2)));
+        const float cf = __ldg(p.rrc_coeffs + ci);
+        const float2 pr = cmul(make_float2(fmul(e.x, cf), fmul(e.y, cf)), pin[j]);
+        acc_re = fadd(acc_re, pr.x);
+        acc_im = fadd(acc_im, pr.y);
+      }
+      const float2 sg = cmul(e0, make_float2(acc_re, acc_im));
+      r.sg_re = sg.x; r.sg_im = sg.y;
+    } else if (SAMPLER == 1) {
       const float2 e1 = expi(p.trig, -fadd(r.phase, r.samp_freqw));
       const float2 s1 = cmul(nxt, e1);
       const float a = fsub(1.0f, r.mu);
@@ -129,8 +152,15 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
   return emitted;
 }
 
-__device__ __forceinline__ void rx_chunk_begin(RxRun &r, int sampler) {
+__device__ __forceinline__ void rx_chunk_begin(const RxParams &p, RxRun &r, int sampler) {
   if (sampler == 1) r.samp_freqw = r.freqw;  // linear_sampler::update_freq (sdr.h:620)
+  if (sampler == 2) {                        // fir_sampler::update_freq (sdr.h:667-675)
+    r.rrc_update_phase -= kRxChunk;
+    if (r.rrc_update_phase <= 0) {
+      r.rrc_update_phase = p.rrc_n * 16;
+      r.rrc_f = __fdiv_rn(r.freqw, (float)p.rrc_sub);
+    }
+  }
   r.have_point = 0;
 }
 
@@ -168,7 +198,9 @@ __device__ __forceinline__ void rx_chunk_end(const RxParams &p, RxRun &r) {
 }
 
 template <int SAMPLER>
-__device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_warp) {
+__device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_all) {
+  constexpr int kRowBytes = RowCfg<SAMPLER>::kBytes;
+  unsigned char *smem_warp = smem_all + (size_t)(threadIdx.x >> 5) * kStages * 32 * kRowBytes;
   const RxParams &p = a.p;
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -207,6 +239,16 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
       r.h1pr = r.h1pi = r.h1cr = r.h1ci = 0.f;
       r.h2pr = r.h2pi = r.h2cr = r.h2ci = 0.f;
       r.meas_count = (uint32_t)(((uint64_t)a.state_in->meas_count + run_begin * (uint64_t)kRxChunk) % p.meas_decimation);
+      if (SAMPLER == 2) {
+        // The tap-update throttle is a pure function of the position: first update at
+        // chunk i0, then every ceil(n*16/128) chunks.
+        const int R = p.rrc_n * 16, P = (R + kRxChunk - 1) / kRxChunk;
+        const int p0 = a.state_in->rrc_update_phase;
+        const int64_t i0 = (p0 <= kRxChunk) ? 0 : (p0 + kRxChunk - 1) / kRxChunk - 1;
+        if ((int64_t)run_begin <= i0) r.rrc_update_phase = p0 - kRxChunk * (int)run_begin;
+        else r.rrc_update_phase = R - kRxChunk * (int)(((int64_t)run_begin - i0 - 1) % P);
+        r.rrc_f = __fdiv_rn(r.freqw, (float)p.rrc_sub);
+      }
     }
     // run_begin == 0: the true state at the start of the batch (exact).
   }
@@ -263,7 +305,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
     if (active) {
       const int phase_of_run = ((uint64_t)c < own_begin) ? 0 : ((uint64_t)c < own_end ? 1 : 2);
-      if (tic == 0) rx_chunk_begin(r, SAMPLER);
+      if (tic == 0) rx_chunk_begin(p, r, SAMPLER);
       const float4 *rp = reinterpret_cast<const float4 *>(stage_base[st] + (size_t)lane * kRowBytes);
       float4 w = rp[0];
       float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
@@ -276,7 +318,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
         if ((n & 1) == 0) { w = rp[(n >> 1) + 1]; nxt2 = make_float2(w.x, w.y); }
         else nxt2 = make_float2(w.z, w.w);
         uint32_t word; float mu_e;
-        if (rx_sample<SAMPLER>(p, r, cur, nxt, word, mu_e)) {
+        if (rx_sample<SAMPLER>(p, r, cur, nxt, reinterpret_cast<const float2 *>(rp) + n, word, mu_e)) {
           if (phase_of_run == 1) {
             if (n_out < cap) out[n_out] = word;
             ++n_out;
@@ -335,10 +377,9 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5;
-  unsigned char *smem_warp = smem + (size_t)warp * kStages * 32 * kRowBytes;
-  if (a.p.sampler == 0) rx_warp<0>(a, span_list, nlist, smem_warp);
-  else rx_warp<1>(a, span_list, nlist, smem_warp);
+  if (a.p.sampler == 0) rx_warp<0>(a, span_list, nlist, smem);
+  else if (a.p.sampler == 1) rx_warp<1>(a, span_list, nlist, smem);
+  else rx_warp<2>(a, span_list, nlist, smem);
 }
 
 // ---------------------------------------------------------------- seam stitching
@@ -407,7 +448,7 @@ __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
   }
 }
 
-constexpr size_t kRxSmemPerBlock = (size_t)kWarpsPerBlock * kStages * 32 * kRowBytes;
+constexpr size_t kRxSmemMax = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<2>::kBytes;
 
 }  // namespace
 
@@ -415,13 +456,14 @@ cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist
   if (a.nspans == 0 || (span_list && !nlist)) return cudaSuccess;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxSmemPerBlock);
+    cudaError_t e = cudaFuncSetAttribute(k_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxSmemMax);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const unsigned per_block = kWarpsPerBlock * 32;
   const unsigned lanes = span_list ? nlist : a.nspans;
-  k_rx<<<(lanes + per_block - 1) / per_block, per_block, kRxSmemPerBlock, st>>>(a, span_list, nlist);
+  const size_t smem = (size_t)kWarpsPerBlock * kStages * 32 * (a.p.sampler == 2 ? RowCfg<2>::kBytes : RowCfg<1>::kBytes);
+  k_rx<<<(lanes + per_block - 1) / per_block, per_block, smem, st>>>(a, span_list, nlist);
   return cudaGetLastError();
 }
 

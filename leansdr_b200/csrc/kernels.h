@@ -109,8 +109,8 @@ struct RxState {
   float hist[12];          // hist[k] = {p.re, p.im, c.re, c.im}
   float samp_freqw, freq_tap;
   uint32_t meas_count;
-  int32_t rrc_update_phase;
-  int32_t pad;
+  int32_t rrc_update_phase;  // fir_sampler::update_freq_phase (sdr.h:688)
+  float rrc_f;               // freqw/subsampling at the last tap update (sdr.h:679)
 };
 
 struct RxSeamSym { float t; uint32_t sym; };  // time relative to the seam, hard symbol

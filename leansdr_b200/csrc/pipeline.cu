@@ -90,9 +90,11 @@ struct ldvb_handle {
   Cstln cst;
   DeconvPolys dec;
   RxParams rxp;
+  std::vector<float> rrc_coeffs;
   int readahead = 1;
 
   // ---- device tables
+  DevBuf d_rrc;
   DevBuf d_cstln, d_trig, d_rot, d_taps, d_gfexp, d_gflog, d_derand, d_rotperm, d_twiddle;
 
   // ---- streams
@@ -358,6 +360,13 @@ void rx_setup(ldvb_handle *h) {
   h->rx_state.freqw = freqw;
   h->rx_state.freq_tap = freqw / 65536;
   h->readahead = (c.sampler == LDVB_SAMP_NEAREST) ? 0 : 1;
+  if (c.sampler == LDVB_SAMP_RRC) {   // leandvb.cc:437-456
+    int steps = 0;
+    h->rrc_coeffs = design_rrc(h->Fs_rx, c.Fm, c.rolloff, c.rrc_rej, c.rrc_steps, &steps);
+    p.rrc_n = (int)h->rrc_coeffs.size();
+    p.rrc_sub = steps;
+    h->readahead = p.rrc_n - 1;       // sdr.h:645
+  }
 }
 
 }  // namespace
@@ -407,7 +416,7 @@ int ldvb_destroy(ldvb_handle *h) {
   if (!h) return LDVB_OK;
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
-  DevBuf *bufs[] = {&h->d_cstln, &h->d_trig, &h->d_rot, &h->d_taps, &h->d_gfexp, &h->d_gflog, &h->d_derand,
+  DevBuf *bufs[] = {&h->d_rrc, &h->d_cstln, &h->d_trig, &h->d_rot, &h->d_taps, &h->d_gfexp, &h->d_gflog, &h->d_derand,
                     &h->d_rotperm, &h->d_twiddle, &h->s_raw.buf, &h->s_notched.buf, &h->s_pp.buf, &h->s_sym.buf,
                     &h->s_bytes.buf, &h->s_mpeg.buf, &h->d_rts, &h->d_rsflags, &h->d_ts, &h->d_scratch,
                     &h->d_badwords, &h->d_rs204, &h->d_notch_tables, &h->d_notch_state, &h->d_notch_epochs,
@@ -447,7 +456,6 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   };
   if (c.input_format < 0 || c.input_format > LDVB_FMT_F32) return bail(LDVB_EINVAL, "bad input_format");
   if (c.fastlock) return bail(LDVB_EINVAL, "--fastlock is not supported");
-  if (c.sampler == LDVB_SAMP_RRC) return bail(LDVB_EINVAL, "--sampler rrc is not supported yet");
   if (c.sampler < 0 || c.sampler > 2) return bail(LDVB_EINVAL, "bad sampler");
   if (c.anf < 0 || c.anf > kNotchMaxSlots) return bail(LDVB_EINVAL, "anf must be 0..4");
   if (!(c.Fs > 0) || !(c.Fm > 0) || c.max_batch == 0) return bail(LDVB_EINVAL, "bad rates or max_batch");
@@ -527,6 +535,11 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   }
   h->Fs_rx = Fs;
   rx_setup(h);
+  if (c.sampler == LDVB_SAMP_RRC) {
+    if ((h->rxp.rrc_n + h->rxp.rrc_sub - 1) / h->rxp.rrc_sub > 6) return bail(LDVB_EINVAL, "RRC sampler: more than 6 taps per symbol");
+    if (upload(h->d_rrc, h->rrc_coeffs.data(), h->rrc_coeffs.size() * 4) != cudaSuccess) return bail(LDVB_ECUDA, "rrc upload");
+    h->rxp.rrc_coeffs = h->d_rrc.as<float>();
+  }
   // Host batches larger than this are pipelined (copy/compute overlap); reserved[0] overrides.
   h->sub_batch = c.reserved[0] > 0 ? (uint64_t)c.reserved[0] : (uint64_t)32 << 20;
 

@@ -51,6 +51,8 @@ EXACT_CASES = [
     ("f32-derot-anf2", dict(fmt="f32", anf=2, Fderot=20000.0), {}, 300),
     ("f32-scale-decim2", dict(fmt="f32", anf=0, decim=2, Fs=4.8e6, float_scale=0.5), dict(ratio="12/5", power=43.5), 200),
     ("f32-noise", dict(fmt="f32", resample=True), dict(noise_db=22), 300),
+    ("f32-rrc", dict(fmt="f32", sampler="rrc"), {}, 300),
+    ("f32-rrc-4sps-noise", dict(fmt="f32", sampler="rrc", anf=0, Fs=4e6), dict(ratio="2", noise_db=22), 200),
 ]
 
 
@@ -122,6 +124,7 @@ def test_notch_detect_and_segment_verification(product, oracle):
 
 FAST_CASES = [
     ("clean", dict(fmt="f32", resample=True), {}, 1200),
+    ("rrc", dict(fmt="f32", sampler="rrc"), {}, 1200),
     ("noise22", dict(fmt="f32", resample=True), dict(noise_db=22), 1200),
     ("u8", dict(fmt="u8"), {}, 1200),
 ]
