@@ -232,8 +232,8 @@ k_notch_guess(NotchApplyArgs a, float2 *guess /* [nsegs][kNotchMaxSlots] */, con
 // per tile the warp stages every lane's next 64 raw samples in a private
 // shared-memory row (cooperative 16-byte cp.async copies, contiguous within a
 // row, double buffered); lanes convert on the fly and stream their results out.
-constexpr int kNTile = 64;
-constexpr int kNPitch = 528;          // row pitch: (64 + 2) cf32, = 16 (mod 128) bytes
+constexpr int kNTile = 32;
+constexpr int kNPitch = 272;          // row pitch: (32 + 2) cf32, = 16 (mod 128) bytes
 constexpr int kNStages = 2;
 constexpr int kNWarps = 2;
 
@@ -248,7 +248,7 @@ __device__ __forceinline__ float2 row_sample(const unsigned char *row, uint32_t 
   if (FMT == 3) { short2 v = reinterpret_cast<const short2 *>(row)[idx];
     return make_float2((float)(int)v.x, (float)(int)v.y); }
   float2 v = reinterpret_cast<const float2 *>(row)[idx];
-  if (FMT == 4) v = make_float2(fmul(v.x, scale), fmul(v.y, scale));
+  if (FMT == 4 && scale != 1.0f) v = make_float2(fmul(v.x, scale), fmul(v.y, scale));  // x*1 == x
   return v;
 }
 
@@ -294,17 +294,14 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   if (repair) { base = (int64_t)run_begin; iters = a.seg_blocks; }
   else { base = (int64_t)((uint64_t)seg * a.seg_blocks) - (int64_t)a.warm_blocks; iters = (uint64_t)a.warm_blocks + a.seg_blocks; }
 
-  unsigned char *smem_warp = smem + (size_t)warp * kNStages * 32 * kNPitch;
-  unsigned char *stage_base[kNStages];
-#pragma unroll
-  for (int s = 0; s < kNStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kNPitch;
-  const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
+  // This lane's private row in each stage.
+  const uint32_t row_off = (uint32_t)(warp * kNStages * 32 * kNPitch + lane * kNPitch);
 
   constexpr uint32_t bps = (FMT <= 1) ? 2u : (FMT <= 3 ? 4u : 8u);
   constexpr uint32_t align_elems = 16 / bps;
   constexpr int kTilesPerBlock = kNotchN / kNTile;
-  constexpr int n16_max = (int)(((kNTile + align_elems) * bps + 15u) / 16u);
   const uint64_t total_tiles = iters * kTilesPerBlock;
+  // Where sample `idx` of the two-part stream lives, aligned down to 16 bytes.
   auto locate = [&](uint64_t idx, const unsigned char *&src, uint32_t &lead) {
     const unsigned char *part = static_cast<const unsigned char *>(a.src.head);
     if (a.src.main && idx >= a.src.c0) { part = static_cast<const unsigned char *>(a.src.main); idx -= a.src.c0; }
@@ -312,26 +309,20 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
     lead = (uint32_t)(idx - al);
     src = part + al * bps;
   };
+  constexpr int n16_max = (int)(((kNTile + align_elems) * bps + 15u) / 16u);
+  // Each lane fetches ITS row with 16-byte asynchronous copies (LDGSTS).
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kNStages);
-    const uint64_t i = tile / kTilesPerBlock;
-    const int64_t blk = base + (int64_t)i;
+    const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
-    const unsigned mask = __ballot_sync(0xffffffffu, active);
-    const uint64_t col0 = (tile % kTilesPerBlock) * kNTile;
+    if (active) {
+      const unsigned char *src; uint32_t lead;
+      locate((uint64_t)blk * kNotchN + (tile % kTilesPerBlock) * kNTile, src, lead);
+      const int n16 = (int)(((lead + kNTile) * bps + 15u) / 16u);
+      unsigned char *dst = smem + row_off + (size_t)st * 32 * kNPitch;
 #pragma unroll
-    for (int kk = 0; kk < n16_max; ++kk) {
-      const int id = kk * 32 + lane;
-      const int r = id / n16_max, q = id - r * n16_max;
-      // Row r belongs to lane r: segments are consecutive in normal mode, arbitrary in repair mode.
-      const int64_t base_r = repair ? __shfl_sync(0xffffffffu, base, r) : base0 + (int64_t)r * (int64_t)a.seg_blocks;
-      if ((mask >> r) & 1u) {
-        const uint64_t idx = (uint64_t)(base_r + (int64_t)i) * kNotchN + col0;
-        const unsigned char *src; uint32_t lead;
-        locate(idx, src, lead);
-        const int n16 = (int)(((lead + kNTile) * bps + 15u) / 16u);
-        if (q < n16) cp_async16(stage_base[st] + (size_t)r * kNPitch + q * 16, src + q * 16);
-      }
+      for (int q = 0; q < n16_max; ++q)
+        if (q < n16) cp_async16(dst + q * 16, src + q * 16);
     }
     cp_async_commit();
   };
@@ -342,8 +333,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
-    __syncwarp();
-    const int st = (int)(tile % kNStages);
+    const int st = (int)(tile % kNStages);   // (a lane only reads the row it copied itself)
     const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
     const int tib = (int)(tile % kTilesPerBlock);
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
@@ -367,7 +357,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
       for (int s = 0; s < NSLOTS; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
       float2 *outp = a.out + (uint64_t)blk * kNotchN + (uint64_t)tib * kNTile;
       uint32_t lead; { const unsigned char *unused; locate((uint64_t)blk * kNotchN + (uint64_t)tib * kNTile, unused, lead); }
-      const unsigned char *myrow = stage_base[st] + (size_t)lane * kNPitch;
+      const unsigned char *myrow = smem + row_off + (size_t)st * 32 * kNPitch;
       // Eight samples per step: loads and the products that do not depend on the
       // estimate are issued first (ILP), then the 8-step serial chain
       // estim = bb*k + estim*(1-k), then the subtraction and the stores.

@@ -33,7 +33,7 @@ namespace ldvb {
 
 namespace {
 
-constexpr int kTile = 32;                       // samples per staged tile
+constexpr int kTile = 16;                       // samples per staged tile
 // Row = tile + look-ahead: 2 samples for the nearest/linear samplers (272 B), 6 for the RRC
 // sampler (304 B, up to 6 taps).  Both pitches are 16 B mod 128-friendly: any 8 consecutive
 // lanes read 16 B each from distinct banks.
@@ -200,7 +200,6 @@ __device__ __forceinline__ void rx_chunk_end(const RxParams &p, RxRun &r) {
 template <int SAMPLER>
 __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_all) {
   constexpr int kRowBytes = RowCfg<SAMPLER>::kBytes;
-  unsigned char *smem_warp = smem_all + (size_t)(threadIdx.x >> 5) * kStages * 32 * kRowBytes;
   const RxParams &p = a.p;
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -259,31 +258,20 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   if (repair) { base = (int64_t)run_begin; iters = S + kRxVerifyChunks; }
   else { base = (int64_t)((uint64_t)span * S) - (int64_t)W; iters = W + S + kRxVerifyChunks; }
 
-  unsigned char *stage_base[kStages];
-  for (int s = 0; s < kStages; ++s) stage_base[s] = smem_warp + (size_t)s * 32 * kRowBytes;
-  // Row r of the warp = lane r's span; its chunk at local iteration i is base_r + i.
-  const int64_t base0 = __shfl_sync(0xffffffffu, base, 0);
-
+  // This lane's private row in each stage (shared-memory window of the warp).
+  const uint32_t row_off = (uint32_t)((threadIdx.x >> 5) * kStages * 32 * kRowBytes + lane * kRowBytes);
   const uint64_t total_tiles = iters * kTilesPerChunk;
-  constexpr int kChunks16 = kRowBytes / 16;  // 17 x 16 B per row
+  constexpr int kChunks16 = kRowBytes / 16;
+  // Each lane fetches ITS row: kChunks16 x 16 B asynchronous copies (LDGSTS), no index math.
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kStages);
-    const uint64_t i = tile / kTilesPerChunk;
-    const int64_t c = base + (int64_t)i;
+    const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
-    const unsigned mask = __ballot_sync(0xffffffffu, active);
-    const uint64_t col0 = (tile % kTilesPerChunk) * kTile;
+    if (active) {
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + (uint64_t)c * kRxChunk + (tile % kTilesPerChunk) * kTile);
+      unsigned char *dst = smem_all + row_off + (size_t)st * 32 * kRowBytes;
 #pragma unroll
-    for (int k = 0; k < kChunks16; ++k) {
-      const int id = k * 32 + lane;
-      const int r = id / kChunks16, q = id - r * kChunks16;
-      // Row r belongs to lane r: consecutive spans in normal mode, arbitrary in repair mode.
-      const int64_t base_r = repair ? __shfl_sync(0xffffffffu, base, r) : base0 + (int64_t)r * (int64_t)S;
-      if ((mask >> r) & 1u) {
-        const int64_t cr = base_r + (int64_t)i;
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + (uint64_t)cr * kRxChunk + col0) + q * 16;
-        cp_async16(stage_base[st] + (size_t)r * kRowBytes + q * 16, src);
-      }
+      for (int q = 0; q < kChunks16; ++q) cp_async16(dst + q * 16, src + q * 16);
     }
     cp_async_commit();
   };
@@ -298,15 +286,14 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
-    __syncwarp();   // every lane's copies of this stage are visible to the whole warp
-    const int st = (int)(tile % kStages);
+    const int st = (int)(tile % kStages);   // (a lane only reads the row it copied itself)
     const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
     const int tic = (int)(tile % kTilesPerChunk);
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
     if (active) {
       const int phase_of_run = ((uint64_t)c < own_begin) ? 0 : ((uint64_t)c < own_end ? 1 : 2);
       if (tic == 0) rx_chunk_begin(p, r, SAMPLER);
-      const float4 *rp = reinterpret_cast<const float4 *>(stage_base[st] + (size_t)lane * kRowBytes);
+      const float4 *rp = reinterpret_cast<const float4 *>(smem_all + row_off + (size_t)st * 32 * kRowBytes);
       float4 w = rp[0];
       float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
       const float t_head = (float)(((int64_t)c - (int64_t)own_begin) * kRxChunk + tic * kTile);
@@ -457,6 +444,11 @@ cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxSmemMax);
+    if (e != cudaSuccess) return e;
+    // Leave about half of the SM's unified cache to L1: the two 512 KB tables are read
+    // through it, and their hot lines (current carrier phase, constellation clusters)
+    // must stay resident -- table latency is what bounds this kernel.
+    e = cudaFuncSetAttribute(k_rx, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     if (e != cudaSuccess) return e;
     configured = true;
   }
