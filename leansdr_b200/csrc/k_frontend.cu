@@ -127,6 +127,48 @@ k_frontend(FrontendArgs a) {
     for (uint32_t o = threadIdx.x; o < nout; o += kThreads) st_stream(out + o, x[(size_t)o * D]);
     return;
   }
+  if (D == 1) {
+    // Undecimated filter: each thread produces PAIRS of consecutive outputs so that the
+    // N+1 input samples of a pair are read once (sliding window), and -- when every tap is
+    // real, which is the case whenever the filter is not retuned (dsp.h:270-280 with f=0:
+    // im = c*sinf(0) = +-0) -- the products with the zero imaginary part are skipped.
+    // That is bit-exact for finite inputs: a term c.im*x = +-0 can only change the sign of
+    // an exact zero, and an accumulator that starts at +0 never becomes -0.
+    const uint32_t t2 = 2 * threadIdx.x;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+    for (uint32_t o = t2; o < nout; o += 2 * kThreads) {
+      const float2 *xs = x + o;
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      float2 prev = xs[N];
+      if (a.real_taps) {
+#pragma unroll 5
+        for (uint32_t i = 0; i < N; ++i) {
+          const float2 cur = xs[N - 1 - i];
+          const float c = s_taps[i].x;
+          a1.x = fadd(a1.x, fmul(c, prev.x)); a1.y = fadd(a1.y, fmul(c, prev.y));
+          a0.x = fadd(a0.x, fmul(c, cur.x));  a0.y = fadd(a0.y, fmul(c, cur.y));
+          prev = cur;
+        }
+      } else {
+        for (uint32_t i = 0; i < N; ++i) {
+          const float2 cur = xs[N - 1 - i];
+          const float2 c = s_taps[i];
+          const float2 p1 = cmul(c, prev), p0 = cmul(c, cur);
+          a1.x = fadd(a1.x, p1.x); a1.y = fadd(a1.y, p1.y);
+          a0.x = fadd(a0.x, p0.x); a0.y = fadd(a0.y, p0.y);
+          prev = cur;
+        }
+      }
+      if (o + 1 < nout) {
+        if (aligned16) __stcs(reinterpret_cast<float4 *>(out + o), make_float4(a0.x, a0.y, a1.x, a1.y));
+        else { st_stream(out + o, a0); st_stream(out + o + 1, a1); }
+      } else {
+        st_stream(out + o, a0);
+      }
+    }
+    return;
+  }
   // Output o (local) = sum_i taps[i] * x[o*D + (N-1) - i].
   float2 acc[kOutPerThread];
 #pragma unroll

@@ -24,6 +24,7 @@ struct FrontendArgs {
   uint32_t rot_index0;    // rotator index of sample 0
   const float2 *taps;     // ntaps shifted complex taps, ntaps == 0: copy/decimate only
   uint32_t ntaps, decim;
+  int real_taps;          // every tap has a zero imaginary part (no retune in force)
   float2 *out;
   uint64_t count;         // outputs to produce
   // filled by launch_frontend

@@ -863,6 +863,8 @@ int run_frontend(ldvb_handle *h, const RawSrc &src, int fmt, uint64_t avail, uin
   a.rot_index0 = h->rot_index;
   a.taps = h->d_taps.as<float2>();
   a.ntaps = N; a.decim = D;
+  a.real_taps = 1;
+  for (uint32_t i = 0; i < N; ++i) if (h->fir_shifted[2 * i + 1] != 0.0f) a.real_taps = 0;
   a.out = reinterpret_cast<float2 *>(h->s_pp.at(h->s_pp.count));
   a.count = count;
   KL("frontend", launch_frontend(a, h->st));
