@@ -250,6 +250,8 @@ def main():
         "deconv_carry": sym * 4 + sym // 8,
         "deint_rs": (sym // 8) * 2,
     }
+    wall = {k[5:]: v["ms_total"] / a.steps for k, v in prof.items() if k.startswith("wall:")}
+    prof = {k: v for k, v in prof.items() if not k.startswith("wall:")}
     kern = {k: v["ms_total"] / max(v["launches"], 1) for k, v in prof.items()}
     per_step = {k: v["ms_total"] / a.steps for k, v in prof.items()}
     dom = max(per_step, key=per_step.get) if per_step else None
@@ -293,7 +295,7 @@ def main():
                     "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches),
             "roofline": roof, "roofline_fir": fir,
-            "kernel_ms_per_step": per_step,
+            "kernel_ms_per_step": per_step, "stage_wall_ms_per_step": wall,
             "cpu_baseline": cpu,
             "ts_packets_per_step": int(npk), "ts_bit_exact_vs_reference": ts_match,
             "seams": {"total": meas["seams_total"], "repaired": meas["seams_repaired"], "notch_repaired": meas["notch_repaired"]}}

@@ -31,45 +31,96 @@ __device__ __forceinline__ uint64_t deconv_reg(const DeconvArgs &a, int64_t K) {
   return reg;
 }
 
+// Tiled version: a CTA produces 1024 output bytes.  It first packs the IQ bit pairs
+// of every symbol it needs (plus the 32 carried ones) into a shared-memory bit string
+// -- 16 symbols per word, loaded 4 symbols per 16-byte access, each symbol read from
+// HBM exactly once -- then every thread extracts the 64-bit register of a bit group
+// with three shared loads and two funnel shifts.
+constexpr int kDcBytes = 1024;
+constexpr int kDcWords = 576;
+
 __global__ void __launch_bounds__(256)
-k_deconv(DeconvArgs a, uint64_t *carry_out) {
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+k_deconv_tiled(DeconvArgs a, uint64_t nsym) {
+  __shared__ uint32_t s_bits[kDcWords];
   const int pp = a.punctperiod, half = a.punctweight / 2;
-  const int64_t k0 = (a.n_in >= 64) ? 0 : (64 - a.n_in) / 2;  // n_in is always even
-  if (j < a.nbytes) {
+  const int64_t k0 = (a.n_in >= 64) ? 0 : (64 - a.n_in) / 2;
+  const uint64_t b0 = (uint64_t)blockIdx.x * kDcBytes;
+  if (b0 >= a.nbytes) return;
+  const uint32_t nb = (uint32_t)min((uint64_t)kDcBytes, a.nbytes - b0);
+  // Bit groups touched by this CTA's bytes (stream bit i >= n_out belongs to group (i-n_out)/pp).
+  const int64_t bit_first = (int64_t)8 * b0, bit_last = (int64_t)8 * (b0 + nb) - 1;
+  const int64_t g0 = (bit_first > a.n_out) ? (bit_first - a.n_out) / pp : 0;
+  const int64_t g1 = (bit_last >= a.n_out) ? (bit_last - a.n_out) / pp : -1;
+  // Extended symbol stream E: E[0..31] = the carried register, E[32+s] = symbol s.
+  // The register of group g is E[K_g .. K_g+32), K_g = k0 + g*half.
+  const int64_t e_base = (k0 + g0 * half) & ~(int64_t)15;
+  const int64_t e_end = (g1 >= 0) ? k0 + g1 * half + 32 : e_base;
+  const int nwords = (int)((e_end - e_base + 15) / 16) + 2;
+  for (int w = threadIdx.x; w < nwords && w < kDcWords; w += blockDim.x) {
+    const int64_t e0 = e_base + (int64_t)16 * w;
+    uint32_t word = 0;
+    if (e0 >= 32 && (uint64_t)(e0 - 32 + 16) <= nsym) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(a.symbols + (e0 - 32));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = __ldg(src + q);
+        word |= (uint32_t)a.hyp[(v.x >> 16) & 3u] << (30 - 8 * q);
+        word |= (uint32_t)a.hyp[(v.y >> 16) & 3u] << (28 - 8 * q);
+        word |= (uint32_t)a.hyp[(v.z >> 16) & 3u] << (26 - 8 * q);
+        word |= (uint32_t)a.hyp[(v.w >> 16) & 3u] << (24 - 8 * q);
+      }
+    } else {
+      for (int i = 0; i < 16; ++i) {
+        const int64_t e = e0 + i;
+        uint32_t code = 0;
+        if (e < 32) code = (uint32_t)(a.reg_in >> (2 * (31 - e))) & 3u;
+        else if ((uint64_t)(e - 32) < nsym) code = a.hyp[(a.symbols[e - 32] >> 16) & 3u];
+        word |= code << (30 - 2 * i);
+      }
+    }
+    s_bits[w] = word;
+  }
+  __syncthreads();
+  auto reg_at = [&](int64_t K) -> uint64_t {   // E[K .. K+32) as a 64-bit string
+    const int64_t bo = 2 * (K - e_base);
+    const int wi = (int)(bo >> 5), sh = (int)(bo & 31);
+    const uint32_t hi = s_bits[wi], mid = s_bits[wi + 1], lo = s_bits[wi + 2];
+    const uint32_t r_hi = __funnelshift_l(mid, hi, sh), r_lo = __funnelshift_l(lo, mid, sh);
+    return ((uint64_t)r_hi << 32) | r_lo;
+  };
+  for (uint32_t t = threadIdx.x; t < nb; t += blockDim.x) {
+    const uint64_t j = b0 + t;
     unsigned byte = 0;
-    int64_t bit = (int64_t)8 * j;        // stream bit index of the byte's MSB
+    int64_t bit = (int64_t)8 * j;
     int got = 0;
-    // Bits still held by the carried accumulator.
-    while (got < 8 && bit < a.n_out) {
+    while (got < 8 && bit < a.n_out) {   // bits still held by the carried accumulator
       byte = (byte << 1) | (unsigned)((a.out_acc >> (a.n_out - 1 - bit)) & 1);
       ++bit; ++got;
     }
     if (got < 8) {
       int64_t g = (bit - a.n_out) / pp;
-      int within = (int)((bit - a.n_out) % pp);   // bits of group g already consumed
-      uint64_t reg = deconv_reg(a, k0 + g * half);
+      int within = (int)((bit - a.n_out) % pp);
       while (got < 8) {
+        const uint64_t reg = reg_at(k0 + g * half);
         for (int b = pp - 1 - within; b >= 0 && got < 8; --b) {
           byte = (byte << 1) | par64(reg & a.deconv[b]);
           ++got;
         }
         within = 0;
-        if (got < 8) {
-          // next group: shift in punctweight/2 more symbols
-          const int64_t K = k0 + g * half;
-          for (int s = 0; s < half; ++s) {
-            const uint32_t sym = (a.symbols[K + s] >> 16) & 3u;
-            reg = (reg << 2) | a.hyp[sym];
-          }
-          ++g;
-        }
+        ++g;
       }
     }
     a.out[j] = (uint8_t)byte;
   }
-  // The thread after the last byte writes the carry for the next batch.
-  if (j == a.nbytes && carry_out) {
+}
+
+// Carry for the next batch (register, leftover bits, symbols consumed): one thread.
+__global__ void k_deconv(DeconvArgs a, uint64_t *carry_out) {
+  const uint64_t j = a.nbytes;
+  const int pp = a.punctperiod, half = a.punctweight / 2;
+  const int64_t k0 = (a.n_in >= 64) ? 0 : (64 - a.n_in) / 2;  // n_in is always even
+  if (threadIdx.x == 0 && blockIdx.x == 0 && carry_out) {
+    (void)j;
     // Groups completed: the last byte ends at stream bit 8*nbytes-1.
     const int64_t total_bits = (int64_t)8 * a.nbytes;
     int64_t ngroups = 0;
@@ -480,9 +531,9 @@ k_derand_out(DerandArgs a) {
 
 }  // namespace
 
-cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st) {
-  const uint64_t n = a.nbytes + 1;
-  k_deconv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, carry_out);
+cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t nsym, uint64_t *carry_out, cudaStream_t st) {
+  if (a.nbytes) k_deconv_tiled<<<(unsigned)((a.nbytes + kDcBytes - 1) / kDcBytes), 256, 0, st>>>(a, nsym);
+  k_deconv<<<1, 32, 0, st>>>(a, carry_out);
   return cudaGetLastError();
 }
 

@@ -193,7 +193,7 @@ struct DeconvArgs {
   uint8_t *out;
 };
 // carry_out (device, 5 x uint64): register, n_in, accumulator, n_out, symbols consumed.
-cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st);
+cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t nsym, uint64_t *carry_out, cudaStream_t st);
 
 // --------------------------------------------------------------------- K5 Viterbi
 struct VitDecState { int32_t cost[64]; uint64_t path[64]; int32_t bank, pad; };

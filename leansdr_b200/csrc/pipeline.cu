@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +31,7 @@ using namespace ldvb;
 
 namespace ldvb {
 // defined in k_fec.cu
-cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t *carry_out, cudaStream_t st);
+cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t nsym, uint64_t *carry_out, cudaStream_t st);
 }
 
 namespace {
@@ -233,6 +234,22 @@ void prof_harvest(ldvb_handle *h) {
   }
   h->prof_pending.clear();
 }
+
+// Host wall-clock per stage (kernels + copies + synchronisations), reported next to the
+// per-kernel device times as pseudo entries "wall:<stage>" while profiling is on.
+struct WallTimer {
+  ldvb_handle *h; const char *name;
+  std::chrono::steady_clock::time_point t0;
+  WallTimer(ldvb_handle *hh, const char *n) : h(hh), name(n), t0(std::chrono::steady_clock::now()) {}
+  ~WallTimer() {
+    if (!h->profiling) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    int id = -1;
+    for (size_t i = 0; i < h->prof_names.size(); ++i) if (h->prof_names[i] == name) { id = (int)i; break; }
+    if (id < 0) { id = (int)h->prof_names.size(); h->prof_names.push_back(name); h->prof_launches.push_back(0); h->prof_ms.push_back(0); }
+    h->prof_ms[id] += ms; h->prof_launches[id] += 1;
+  }
+};
 
 cudaError_t upload(DevBuf &b, const void *src, size_t n) {
   cudaError_t e = b.alloc(n);
@@ -1123,7 +1140,7 @@ int deconv_launch(ldvb_handle *h, uint64_t limit_bytes, DeconvRun *run) {
   a.punctperiod = pp; a.punctweight = pw;
   for (int b = 0; b < 8; ++b) a.deconv[b] = h->dec.deconv[b];
   a.out = h->s_bytes.at(h->s_bytes.count);
-  KL("deconv_carry", launch_deconv_carry(a, h->d_deconv_carry.as<uint64_t>(), h->st));
+  KL("deconv_carry", launch_deconv_carry(a, in.count, h->d_deconv_carry.as<uint64_t>(), h->st));
   uint64_t carry[5];
   CK(cudaMemcpyAsync(carry, h->d_deconv_carry.p, sizeof carry, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -1278,6 +1295,8 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   h->s_bytes.fresh = 0;
 
   // ---- notch / front end
+  WallTimer *wt = new WallTimer(h, "wall:front");
+  struct WtGuard { WallTimer *&p; ~WtGuard() { delete p; } } wt_guard{wt};
   uint64_t raw_consumed = 0;
   if (c.anf) {
     if ((rc = run_notch(h, src, avail, &raw_consumed))) return rc;
@@ -1323,6 +1342,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   if ((rc = tap_store(h, LDVB_TAP_PREPROCESSED, h->s_pp.at(h->s_pp.count - h->s_pp.fresh), h->s_pp.fresh * 8))) return rc;
 
   // ---- receiver
+  delete wt; wt = new WallTimer(h, "wall:rx");
   if ((rc = run_receiver(h))) return rc;
   if ((rc = tap_store(h, LDVB_TAP_SYMBOLS, h->s_sym.at(h->s_sym.count - h->s_sym.fresh), h->s_sym.fresh * 4))) return rc;
   if (h->cfg.keep_taps && !h->meas_log.empty()) {
@@ -1332,6 +1352,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
     t.bytes = h->meas_log.size() * 4;
   }
 
+  delete wt; wt = new WallTimer(h, "wall:deconv_sync");
   // ---- deconvolution <-> sync (with the backward next_sync edge, dvb.h:771-778)
   std::vector<uint8_t> tap_bytes;  // bytes that stay in the stream, for the tap
   if (c.viterbi) {
@@ -1394,6 +1415,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   }
   if ((rc = tap_store(h, LDVB_TAP_MPEGBYTES, h->s_mpeg.at(h->s_mpeg.count - h->s_mpeg.fresh), h->s_mpeg.fresh))) return rc;
   // ---- de-interleave + RS + derandomise
+  delete wt; wt = new WallTimer(h, "wall:fec");
   if ((rc = run_fec(h, ts_dst, ts_cap, ts_out))) return rc;
   h->meas.kernel_launches = h->launches;
   return LDVB_OK;
