@@ -447,6 +447,27 @@ cudaError_t launch_apply_f(const NotchApplyArgs &a, const uint32_t *seg_list, ui
 
 }  // namespace
 
+namespace {
+// entry(j) == exit(j-1), bit for bit, for every segment that started from a guess.
+__global__ void k_notch_verify(const float2 *entry, const float2 *exitv, const uint8_t *exact, uint32_t nsegs,
+                               int nslots, uint32_t *nfail) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0 || j >= nsegs || exact[j]) return;
+  bool same = true;
+  for (int s = 0; s < nslots; ++s) {
+    const float2 e = entry[(size_t)j * kNotchMaxSlots + s], x = exitv[(size_t)(j - 1) * kNotchMaxSlots + s];
+    same = same && __float_as_uint(e.x) == __float_as_uint(x.x) && __float_as_uint(e.y) == __float_as_uint(x.y);
+  }
+  if (!same) atomicAdd(nfail, 1u);
+}
+}  // namespace
+
+cudaError_t launch_notch_verify(const NotchApplyArgs &a, uint32_t *nfail, cudaStream_t st) {
+  if (a.nsegs < 2) return cudaSuccess;
+  k_notch_verify<<<(a.nsegs + 255) / 256, 256, 0, st>>>(a.seg_entry, a.seg_exit, a.seg_exact, a.nsegs, a.nslots, nfail);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st) {
   if (a.ndetect <= 0) return cudaSuccess;
   k_notch_detect<<<a.ndetect, 1024, 0, st>>>(a);

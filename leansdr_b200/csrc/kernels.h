@@ -83,6 +83,8 @@ struct NotchApplyArgs {
 };
 // guess: [nsegs][kNotchMaxSlots] start states written by launch_notch_guess.
 cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const float *weights, cudaStream_t st);
+// Counts the segments whose entry state differs from their predecessor's exit state.
+cudaError_t launch_notch_verify(const NotchApplyArgs &a, uint32_t *nfail, cudaStream_t st);
 // seg_list == nullptr: every segment (warm-up from `guess`).  Otherwise the listed segments
 // are re-run exactly from the exit state of their predecessors (a.seg_exit).
 cudaError_t launch_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist,
@@ -168,6 +170,13 @@ struct RxStitchArgs {
   RxSeam *seams;             // [nspans-1]
 };
 cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st);
+
+// One-CTA scan over the seams: offsets / skips / cumulative rotations of every span.
+// result[0] = seams that failed verification, [1] = symbols kept, [2] = rotation of the
+// last span, [3] = spans that overflowed their capacity.
+cudaError_t launch_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
+                           uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot, uint64_t *result,
+                           cudaStream_t st);
 
 // Concatenates the span outputs into one contiguous softsymbol stream, applying
 // each span's cumulative rotation to the hard symbol.

@@ -810,11 +810,20 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // with the true trajectory are re-run exactly from their predecessor's exit state,
   // all of them in one launch per round (a segment whose predecessor is also being
   // repaired waits for the next round).
-  std::vector<float2> entry((size_t)a.nsegs * kNotchMaxSlots), exitv((size_t)a.nsegs * kNotchMaxSlots);
+  // Device-side check first: the host only reads a counter and the last exit state.
+  CK(cudaMemsetAsync(h->d_counts.p, 0, 4, h->st));
+  KL("notch_verify", launch_notch_verify(a, h->d_counts.as<uint32_t>(), h->st));
+  uint32_t nfail = 0;
+  std::vector<float2> entry, exitv((size_t)a.nsegs * kNotchMaxSlots);
+  CK(cudaMemcpyAsync(&nfail, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots], a.seg_exit + (size_t)(a.nsegs - 1) * kNotchMaxSlots,
+                     8 * kNotchMaxSlots, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (nfail) {
+  entry.resize((size_t)a.nsegs * kNotchMaxSlots);
   std::vector<uint8_t> exact(a.nsegs);
   CK(cudaMemcpyAsync(entry.data(), a.seg_entry, entry.size() * 8, cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(exact.data(), a.seg_exact, exact.size(), cudaMemcpyDeviceToHost, h->st));
-  int rc = LDVB_OK;
   for (int round = 0; round < 1 << 20; ++round) {
     CK(cudaMemcpyAsync(exitv.data(), a.seg_exit, exitv.size() * 8, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -826,20 +835,14 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
       if (!same && !prev_failed) todo.push_back(j);
       prev_failed = !same;
     }
-    if (todo.empty()) {
-      bool any = false;
-      for (uint32_t j = 1; j < a.nsegs && !any; ++j)
-        any = !exact[j] && memcmp(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * (size_t)c.anf) != 0;
-      if (!any) break;
-      continue;
-    }
+    if (todo.empty()) break;
     CK(cudaMemcpyAsync(h->d_notch_list.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, h->st));
     KL("notch_apply", launch_notch_apply(a, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st));
     h->meas.notch_repaired += (uint32_t)todo.size();
     for (uint32_t j : todo)   // by construction the repaired segment entered with exit(j-1)
       memcpy(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * kNotchMaxSlots);
   }
-  (void)rc;
+  }
   for (int s = 0; s < c.anf; ++s) {
     h->notch.slot[s].est_re = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].x;
     h->notch.slot[s].est_im = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].y;
@@ -974,6 +977,19 @@ int run_receiver(ldvb_handle *h) {
     sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
     sa.seams = h->d_rx_seams.as<RxSeam>();
     KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
+    // Fast path: offsets / skips / rotations are resolved on the device; the host reads back
+    // four numbers.  Only when a seam failed (or a span overflowed) the seams are fetched
+    // and repaired below.
+    KL("rx_plan", launch_rx_plan(a.info, sa.seams, a.nspans, a.span_cap, h->cst.nrotations, h->d_rx_off.as<uint64_t>(),
+                                 h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(), h->d_counts.as<uint64_t>(), h->st));
+    uint64_t plan[4];
+    CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int cum = (int)plan[2];
+    const bool slow = (plan[0] != 0 || plan[3] != 0);
+    h->meas.seams_total += slow ? 0 : a.nspans - 1;
+    produced = plan[1];
+    if (slow) {
     std::vector<RxSeam> seams(a.nspans);
     std::vector<RxSpanInfo> info(a.nspans);
     auto fetch = [&]() -> int {
@@ -1047,7 +1063,7 @@ int run_receiver(ldvb_handle *h) {
     std::vector<uint64_t> off(a.nspans + 1, 0);
     std::vector<uint32_t> skipv(a.nspans, 0);
     std::vector<uint8_t> rot(a.nspans, 0);
-    int cum = 0;
+    cum = 0;
     for (uint32_t j = 0; j < a.nspans; ++j) {
       if (info[j].n_out + info[j].n_tail > a.span_cap) return fail(h, LDVB_EOVERFLOW, "span capacity exceeded");
       uint64_t keep = info[j].n_out;
@@ -1065,6 +1081,9 @@ int run_receiver(ldvb_handle *h) {
     CK(cudaMemcpyAsync(h->d_rx_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->d_rx_skip.p, skipv.data(), skipv.size() * 4, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->d_rx_rot.p, rot.data(), rot.size(), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));   // the vectors above are locals
+    }  // slow path
+    if (produced > room) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
     RxCompactArgs ca;
     ca.sym_in = a.sym_out; ca.span_cap = a.span_cap; ca.nspans = a.nspans;
     ca.span_offset = h->d_rx_off.as<uint64_t>(); ca.span_skip = h->d_rx_skip.as<uint32_t>();
