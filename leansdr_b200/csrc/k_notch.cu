@@ -166,18 +166,18 @@ struct SegPlan {
 
 __device__ __forceinline__ SegPlan plan_segment(const NotchApplyArgs &a, uint32_t seg) {
   SegPlan p;
-  p.own_begin = (uint64_t)seg * a.seg_blocks;
+  p.own_begin = a.block0 + (uint64_t)seg * a.seg_blocks;
   p.own_end = p.own_begin + a.seg_blocks;
   if (p.own_end > a.nblocks) p.own_end = a.nblocks;
   int ep = 0;
   while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= p.own_begin) ++ep;
   p.epoch = ep;
-  if (seg == 0) { p.run_begin = 0; p.start_kind = 0; return p; }
+  if (seg == 0 && a.first_exact) { p.run_begin = p.own_begin; p.start_kind = 0; return p; }
   // One warm-up block, never across an epoch start (tables / resets change there).
   uint64_t wb = (p.own_begin > a.warm_blocks) ? p.own_begin - a.warm_blocks : 0;
   if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
   p.run_begin = wb;
-  if (wb == 0 && ep == 0) { p.start_kind = 0; return p; }   // reaches the carried state
+  if (wb == 0 && ep == 0 && a.first_exact) { p.start_kind = 0; return p; }   // reaches the carried state
   if (a.epochs[ep].first_block == wb) {
     bool all = true;
     for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
@@ -218,7 +218,7 @@ k_notch_guess(NotchApplyArgs a, float2 *guess /* [nsegs][kNotchMaxSlots] */, con
       accr += __shfl_xor_sync(0xffffffffu, accr, o);
       acci += __shfl_xor_sync(0xffffffffu, acci, o);
     }
-    if (reaches_floor && !a.epochs[ep].reset[s] && ep == 0 && floor_s == 0) {
+    if (reaches_floor && !a.epochs[ep].reset[s] && ep == 0 && floor_s == 0 && a.first_exact) {
       // history runs into the carried state of the batch
       const float w = __ldg(weights + (M ? M - 1 : 0)) * (M ? (1.0f - a.k) : 1.0f);
       accr += a.state_in->slot[s].est_re * w;
@@ -292,7 +292,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   // Common iteration space: local block i -> block = base + i.
   int64_t base; uint64_t iters;
   if (repair) { base = (int64_t)run_begin; iters = a.seg_blocks; }
-  else { base = (int64_t)((uint64_t)seg * a.seg_blocks) - (int64_t)a.warm_blocks; iters = (uint64_t)a.warm_blocks + a.seg_blocks; }
+  else { base = (int64_t)(a.block0 + (uint64_t)seg * a.seg_blocks) - (int64_t)a.warm_blocks; iters = (uint64_t)a.warm_blocks + a.seg_blocks; }
 
   // This lane's private row in each stage.
   const uint32_t row_off = (uint32_t)(warp * kNStages * 32 * kNPitch + lane * kNPitch);

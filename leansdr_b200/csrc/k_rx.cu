@@ -211,7 +211,8 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   bool have_span;
   if (repair) { have_span = g < nlist; span = have_span ? span_list[g] : 0; }
   else { span = g; have_span = span < a.nspans; }
-  const RxState *forced = (repair && have_span) ? a.state_end + (span - 1) : nullptr;
+  const RxState *forced = nullptr;
+  if (repair && have_span) forced = span ? a.state_end + (span - 1) : a.prev_end;
 
   const uint64_t S = a.span_chunks, W = a.warm_chunks;
   uint64_t own_begin = 0, own_end = 0, run_begin = 0, run_end = 0;
@@ -220,7 +221,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   load_state(r, *a.state_in);
   r.sg_re = r.sg_im = r.s_re = r.s_im = r.cp_re = r.cp_im = 0.f; r.have_point = 0;
   if (have_span) {
-    own_begin = (uint64_t)span * S;
+    own_begin = a.chunk0 + (uint64_t)span * S;
     own_end = own_begin + S;
     if (own_end > a.nchunks) own_end = a.nchunks;
     last = own_end >= a.nchunks;
@@ -230,7 +231,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     if (forced) {
       load_state(r, *forced);
       run_begin = own_begin;
-    } else if (run_begin > 0) {
+    } else if (run_begin > 0 || !a.first_exact) {
       // Warm-up: the carried loop state (frequency, AGC) with the timing / phase registers cleared.
       load_state(r, *a.warm_in);
       r.mu = 0.f; r.phase = 0.f;
@@ -256,7 +257,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   int64_t base;          // chunk index of local iteration 0 for this lane
   uint64_t iters;
   if (repair) { base = (int64_t)run_begin; iters = S + kRxVerifyChunks; }
-  else { base = (int64_t)((uint64_t)span * S) - (int64_t)W; iters = W + S + kRxVerifyChunks; }
+  else { base = (int64_t)(a.chunk0 + (uint64_t)span * S) - (int64_t)W; iters = W + S + kRxVerifyChunks; }
 
   // This lane's private row in each stage (shared-memory window of the warp).
   const uint32_t row_off = (uint32_t)((threadIdx.x >> 5) * kStages * 32 * kRowBytes + lane * kRowBytes);
@@ -298,7 +299,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
       float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
       const float t_head = (float)(((int64_t)c - (int64_t)own_begin) * kRxChunk + tic * kTile);
       const float t_tail = (float)(((int64_t)c - (int64_t)own_end) * kRxChunk + tic * kTile);
-      const bool log_head = hlog && span > 0 && phase_of_run == 1 && ((uint64_t)c - own_begin) < kRxVerifyChunks;
+      const bool log_head = hlog && (span > 0 || !a.first_exact) && phase_of_run == 1 && ((uint64_t)c - own_begin) < kRxVerifyChunks;
 #pragma unroll 2
       for (int n = 0; n < kTile; ++n) {
         float2 nxt2;
@@ -372,16 +373,8 @@ k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
 // ---------------------------------------------------------------- seam stitching
 
 // One warp per seam: lanes stride over the logged symbols.
-__global__ void __launch_bounds__(128)
-k_rx_stitch(RxStitchArgs a, const uint32_t *seam_list, uint32_t nlist) {
-  const int lane = threadIdx.x & 31;
-  uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (seam_list) { if (j >= nlist) return; j = seam_list[j]; }
-  if (j + 1 >= a.nspans) return;
-  const RxSeamSym *tail = a.tail_log + (size_t)j * kRxSeamLog;
-  const RxSeamSym *head = a.head_log + (size_t)(j + 1) * kRxSeamLog;
-  const uint32_t nt = min(a.info[j].n_tail, (uint32_t)kRxSeamLog);
-  const uint32_t nh = min(a.info[j + 1].n_head_logged, (uint32_t)kRxSeamLog);
+__device__ RxSeam stitch_seam(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t nt, const RxSeamSym *head,
+                              uint32_t nh, int lane) {
   RxSeam s;
   s.ok = 0; s.rot = 0; s.extend_prev = 0; s.skip_next = 0; s.compared = 0; s.mismatches = 0;
   if (nt >= 8 && nh >= 8) {
@@ -413,7 +406,25 @@ k_rx_stitch(RxStitchArgs a, const uint32_t *seam_list, uint32_t nlist) {
     // an unconverged or rotated span disagrees on half or more of the symbols.
     s.ok = (time_ok && n >= 8 && best_mis * 16 <= n) ? 1 : 0;
   }
+  return s;
+}
+
+__global__ void __launch_bounds__(128)
+k_rx_stitch(RxStitchArgs a, const uint32_t *seam_list, uint32_t nlist) {
+  const int lane = threadIdx.x & 31;
+  uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (seam_list) { if (j >= nlist) return; j = seam_list[j]; }
+  if (j + 1 >= a.nspans) return;
+  const RxSeam s = stitch_seam(a, a.tail_log + (size_t)j * kRxSeamLog, min(a.info[j].n_tail, (uint32_t)kRxSeamLog),
+                               a.head_log + (size_t)(j + 1) * kRxSeamLog,
+                               min(a.info[j + 1].n_head_logged, (uint32_t)kRxSeamLog), lane);
   if (lane == 0) a.seams[j] = s;
+}
+
+__global__ void k_rx_stitch_pair(RxStitchArgs a, const RxSeamSym *tail, uint32_t n_tail, RxSeam *out) {
+  const RxSeam s = stitch_seam(a, tail, min(n_tail, (uint32_t)kRxSeamLog), a.head_log,
+                               min(a.info[0].n_head_logged, (uint32_t)kRxSeamLog), threadIdx.x & 31);
+  if (threadIdx.x == 0) *out = s;
 }
 
 __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
@@ -530,6 +541,12 @@ cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, u
   if (a.nspans < 2 || (seam_list && !nlist)) return cudaSuccess;
   const unsigned n = seam_list ? nlist : a.nspans - 1;
   k_rx_stitch<<<(n + 3) / 4, 128, 0, st>>>(a, seam_list, nlist);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, RxSeam *out,
+                                  cudaStream_t st) {
+  k_rx_stitch_pair<<<1, 32, 0, st>>>(a, tail, n_tail, out);
   return cudaGetLastError();
 }
 

@@ -73,6 +73,8 @@ struct NotchApplyArgs {
   const float2 *expj_tables;       // [ntables][4096]
   const NotchEpoch *epochs;        // device, sorted by first_block
   int nepochs;
+  uint64_t block0;                 // first owned block (time-sharded mode: blocks before it are halo)
+  int first_exact;                 // segment 0 starts from the exact carried state (state_in)
   uint32_t seg_blocks;             // blocks owned per segment
   uint32_t warm_blocks;            // warm-up blocks before a speculative segment
   uint32_t nsegs;
@@ -133,6 +135,9 @@ struct RxArgs {
   RxParams p;
   const float2 *x;           // preprocessed stream, chunk c starts at x[c*128]
   uint64_t nchunks;          // chunks available in this batch
+  uint64_t chunk0;           // first owned chunk (time-sharded mode: chunks before it are halo)
+  int first_exact;           // span 0 starts from the exact carried state (state_in)
+  const RxState *prev_end;   // repair mode: end state of the span before span 0 (previous rank), or null
   uint32_t span_chunks;      // owned chunks per span (exact mode: >= nchunks)
   uint32_t warm_chunks;      // warm-up chunks (0 in exact mode)
   uint32_t nspans;
@@ -170,6 +175,9 @@ struct RxStitchArgs {
   RxSeam *seams;             // [nspans-1]
 };
 cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st);
+// One seam between an imported tail log (previous rank) and span 0's head log.
+cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, RxSeam *out,
+                                  cudaStream_t st);
 
 // One-CTA scan over the seams: offsets / skips / cumulative rotations of every span.
 // result[0] = seams that failed verification, [1] = symbols kept, [2] = rotation of the

@@ -789,6 +789,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   a.src = src; a.fmt = fmt; a.scale = c.float_scale;
   a.out = reinterpret_cast<float2 *>(h->s_notched.at(h->s_notched.count));
   a.nblocks = nblocks; a.nslots = c.anf;
+  a.block0 = 0; a.first_exact = 1;
   a.k = 0.002f; a.gain = h->notch.gain;
   a.expj_tables = h->d_notch_tables.as<float2>();
   a.epochs = h->d_notch_epochs.as<NotchEpoch>();
@@ -910,6 +911,7 @@ int run_receiver(ldvb_handle *h) {
   a.p.trig = h->d_trig.as<float2>();
   a.x = reinterpret_cast<const float2 *>(in.at(0));
   a.nchunks = nchunks;
+  a.chunk0 = 0; a.first_exact = 1; a.prev_end = nullptr;
   CK(cudaMemcpyAsync(h->d_rx_state.p, &h->rx_state, sizeof(RxState), cudaMemcpyHostToDevice, h->st));
   CK(cudaMemsetAsync(h->d_rx_measn.p, 0, 4, h->st));
   a.state_in = h->d_rx_state.as<RxState>();
