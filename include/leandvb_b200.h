@@ -236,6 +236,38 @@ int    ldvb_set_state(ldvb_handle *h, const void *blob, size_t size);
 int ldvb_get_rx_state(ldvb_handle *h, uint32_t w[22]);
 int ldvb_set_rx_state(ldvb_handle *h, const uint32_t w[22]);
 
+/* ------------------------------------------------------------ time sharding
+ * one stream, N handles (one per GPU, one process each).  The
+ * stream is cut into consecutive time chunks; chunk k goes to rank k mod N.
+ * A rank holds [halo | chunk] in HBM, the halo being the last samples of the
+ * previous chunk (the "chunk-edge samples" it received from its neighbour).
+ *
+ *   ldvb_shard_detect  auto_notch::detect() on the detect points of the chunk
+ *                      (needs only raw samples): turns the notch bins in force
+ *                      at the chunk start into those at its end, so that the
+ *                      neighbour can start before this rank has finished.
+ *   ldvb_shard_front   notch + front end + receiver on the chunk, speculatively:
+ *                      every segment/span starts from a warm-up inside the halo.
+ *                      This is the expensive part and needs nothing from the
+ *                      previous rank except the halo and the notch bins.
+ *   ldvb_shard_back    receives the previous rank's EDGE (its last span's seam log
+ *                      and loop state, deconvolver registers, sync state, unread
+ *                      symbols/bytes, de-interleaver history, PRBS position: a few
+ *                      KB), stitches and verifies the seam, runs the exact FEC back
+ *                      end and produces this rank's EDGE for the next one.
+ * Constraints: rx_mode = LDVB_RX_FAST; n_halo, n_chunk and abs_raw0 (absolute
+ * index of the first halo sample) multiples of lcm(4096, 128*decimation);
+ * n_halo >= ldvb_shard_min_halo() except for the first chunk of the stream
+ * (n_halo = 0, edge_in = NULL). */
+size_t ldvb_edge_size(void);
+size_t ldvb_shard_min_halo(const ldvb_handle *h);
+int ldvb_shard_detect(ldvb_handle *h, const void *iq_dev, size_t n_halo, size_t n_chunk,
+		      uint64_t abs_raw0, const int32_t bins_before[4], int32_t bins_after[4]);
+int ldvb_shard_front(ldvb_handle *h, const void *iq_dev, size_t n_halo, size_t n_chunk,
+		     uint64_t abs_raw0, const int32_t bins_before[4]);
+int ldvb_shard_back(ldvb_handle *h, const void *edge_in, uint8_t *ts_dev, size_t cap_packets,
+		    size_t *n_packets, void *edge_out);
+
 /* ------------------------------------------------- stand-alone stage kernels
  * Host in, host out; used by the parity tests and by callers that only need
  * one block.  Each runs the same kernel the chain uses. */

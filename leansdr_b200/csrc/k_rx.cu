@@ -216,7 +216,6 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
 
   const uint64_t S = a.span_chunks, W = a.warm_chunks;
   uint64_t own_begin = 0, own_end = 0, run_begin = 0, run_end = 0;
-  bool last = false;
   RxRun r;
   load_state(r, *a.state_in);
   r.sg_re = r.sg_im = r.s_re = r.s_im = r.cp_re = r.cp_im = 0.f; r.have_point = 0;
@@ -224,10 +223,11 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     own_begin = a.chunk0 + (uint64_t)span * S;
     own_end = own_begin + S;
     if (own_end > a.nchunks) own_end = a.nchunks;
-    last = own_end >= a.nchunks;
     run_begin = (own_begin > W) ? own_begin - W : 0;
-    run_end = own_end;
-    if (!last) { run_end = own_end + kRxVerifyChunks; if (run_end > a.nchunks) run_end = a.nchunks; }
+    // Verification overlap: as far as the data goes (avail_chunks == nchunks except in
+    // time-sharded mode, where the last span also runs into the next rank's territory).
+    run_end = own_end + kRxVerifyChunks;
+    if (run_end > a.avail_chunks) run_end = a.avail_chunks;
     if (forced) {
       load_state(r, *forced);
       run_begin = own_begin;
@@ -451,7 +451,7 @@ __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
 // reads back two numbers when every seam verified.
 __global__ void __launch_bounds__(1024)
 k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
-          uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot, uint64_t *result /* [4] */) {
+          int rot0, uint32_t skip0, uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot, uint64_t *result /* [4] */) {
   __shared__ unsigned long long s_sum[32];
   __shared__ int s_rot[32];
   __shared__ unsigned long long carry_sum;
@@ -471,8 +471,10 @@ k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t
         const RxSeam sm = seams[j - 1];
         if (!sm.ok) atomicAdd(&nfail, 1u);
         skip = (uint32_t)sm.skip_next; rot = sm.rot;
-        keep -= skip;
+      } else {
+        skip = skip0; rot = rot0;   // seam in front of span 0 (previous rank), 0 otherwise
       }
+      keep -= skip;
       if (j + 1 < nspans) keep += (unsigned long long)seams[j].extend_prev;
     }
     // inclusive scans (sum of keep, sum of rot mod nrot) across the block
@@ -551,9 +553,9 @@ cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, 
 }
 
 cudaError_t launch_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
-                           uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot, uint64_t *result,
-                           cudaStream_t st) {
-  k_rx_plan<<<1, 1024, 0, st>>>(info, seams, nspans, span_cap, nrot, span_offset, span_skip, span_rot, result);
+                           int rot0, uint32_t skip0, uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot,
+                           uint64_t *result, cudaStream_t st) {
+  k_rx_plan<<<1, 1024, 0, st>>>(info, seams, nspans, span_cap, nrot, rot0, skip0, span_offset, span_skip, span_rot, result);
   return cudaGetLastError();
 }
 

@@ -134,7 +134,8 @@ constexpr int kRxVerifyChunks = 1;     // chunks of overlap after a span end
 struct RxArgs {
   RxParams p;
   const float2 *x;           // preprocessed stream, chunk c starts at x[c*128]
-  uint64_t nchunks;          // chunks available in this batch
+  uint64_t nchunks;          // end of the owned chunks (spans cover [chunk0, nchunks))
+  uint64_t avail_chunks;     // chunks present in x (>= nchunks; == nchunks outside time-sharded mode)
   uint64_t chunk0;           // first owned chunk (time-sharded mode: chunks before it are halo)
   int first_exact;           // span 0 starts from the exact carried state (state_in)
   const RxState *prev_end;   // repair mode: end state of the span before span 0 (previous rank), or null
@@ -183,8 +184,8 @@ cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, 
 // result[0] = seams that failed verification, [1] = symbols kept, [2] = rotation of the
 // last span, [3] = spans that overflowed their capacity.
 cudaError_t launch_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
-                           uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot, uint64_t *result,
-                           cudaStream_t st);
+                           int rot0, uint32_t skip0, uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot,
+                           uint64_t *result, cudaStream_t st);
 
 // Concatenates the span outputs into one contiguous softsymbol stream, applying
 // each span's cumulative rotation to the hard symbol.

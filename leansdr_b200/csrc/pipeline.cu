@@ -716,6 +716,49 @@ int notch_table_for_bin(ldvb_handle *h, int bin, uint32_t *index) {
   return LDVB_OK;
 }
 
+// Verifies entry(j) == exit(j-1) for every segment (device-side count first) and re-runs the
+// segments that did not merge, all of them in one launch per round.  exitv receives the exit
+// states (at least the last one).
+int notch_verify_repair(ldvb_handle *h, NotchApplyArgs &a, std::vector<float2> &exitv_out) {
+  const ldvb_config &c = h->cfg;
+  // Device-side check first: the host only reads a counter and the last exit state.
+  CK(cudaMemsetAsync(h->d_counts.p, 0, 4, h->st));
+  KL("notch_verify", launch_notch_verify(a, h->d_counts.as<uint32_t>(), h->st));
+  uint32_t nfail = 0;
+  std::vector<float2> entry;
+  std::vector<float2> &exitv = exitv_out;
+  exitv.assign((size_t)a.nsegs * kNotchMaxSlots, make_float2(0.f, 0.f));
+  CK(cudaMemcpyAsync(&nfail, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots], a.seg_exit + (size_t)(a.nsegs - 1) * kNotchMaxSlots,
+                     8 * kNotchMaxSlots, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (nfail) {
+  entry.resize((size_t)a.nsegs * kNotchMaxSlots);
+  std::vector<uint8_t> exact(a.nsegs);
+  CK(cudaMemcpyAsync(entry.data(), a.seg_entry, entry.size() * 8, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(exact.data(), a.seg_exact, exact.size(), cudaMemcpyDeviceToHost, h->st));
+  for (int round = 0; round < 1 << 20; ++round) {
+    CK(cudaMemcpyAsync(exitv.data(), a.seg_exit, exitv.size() * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    std::vector<uint32_t> todo;
+    bool prev_failed = false;
+    for (uint32_t j = 1; j < a.nsegs; ++j) {
+      bool same = exact[j] != 0;
+      if (!same) same = memcmp(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * (size_t)c.anf) == 0;
+      if (!same && !prev_failed) todo.push_back(j);
+      prev_failed = !same;
+    }
+    if (todo.empty()) break;
+    CK(cudaMemcpyAsync(h->d_notch_list.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, h->st));
+    KL("notch_apply", launch_notch_apply(a, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st));
+    h->meas.notch_repaired += (uint32_t)todo.size();
+    for (uint32_t j : todo)   // by construction the repaired segment entered with exit(j-1)
+      memcpy(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * kNotchMaxSlots);
+  }
+  }
+  return LDVB_OK;
+}
+
 int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consumed) {
   const ldvb_config &c = h->cfg;
   const uint64_t nblocks = avail / kNotchN;
@@ -811,39 +854,8 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // with the true trajectory are re-run exactly from their predecessor's exit state,
   // all of them in one launch per round (a segment whose predecessor is also being
   // repaired waits for the next round).
-  // Device-side check first: the host only reads a counter and the last exit state.
-  CK(cudaMemsetAsync(h->d_counts.p, 0, 4, h->st));
-  KL("notch_verify", launch_notch_verify(a, h->d_counts.as<uint32_t>(), h->st));
-  uint32_t nfail = 0;
-  std::vector<float2> entry, exitv((size_t)a.nsegs * kNotchMaxSlots);
-  CK(cudaMemcpyAsync(&nfail, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->st));
-  CK(cudaMemcpyAsync(&exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots], a.seg_exit + (size_t)(a.nsegs - 1) * kNotchMaxSlots,
-                     8 * kNotchMaxSlots, cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
-  if (nfail) {
-  entry.resize((size_t)a.nsegs * kNotchMaxSlots);
-  std::vector<uint8_t> exact(a.nsegs);
-  CK(cudaMemcpyAsync(entry.data(), a.seg_entry, entry.size() * 8, cudaMemcpyDeviceToHost, h->st));
-  CK(cudaMemcpyAsync(exact.data(), a.seg_exact, exact.size(), cudaMemcpyDeviceToHost, h->st));
-  for (int round = 0; round < 1 << 20; ++round) {
-    CK(cudaMemcpyAsync(exitv.data(), a.seg_exit, exitv.size() * 8, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    std::vector<uint32_t> todo;
-    bool prev_failed = false;
-    for (uint32_t j = 1; j < a.nsegs; ++j) {
-      bool same = exact[j] != 0;
-      if (!same) same = memcmp(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * (size_t)c.anf) == 0;
-      if (!same && !prev_failed) todo.push_back(j);
-      prev_failed = !same;
-    }
-    if (todo.empty()) break;
-    CK(cudaMemcpyAsync(h->d_notch_list.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, h->st));
-    KL("notch_apply", launch_notch_apply(a, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st));
-    h->meas.notch_repaired += (uint32_t)todo.size();
-    for (uint32_t j : todo)   // by construction the repaired segment entered with exit(j-1)
-      memcpy(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * kNotchMaxSlots);
-  }
-  }
+  std::vector<float2> exitv;
+  { int rcv = notch_verify_repair(h, a, exitv); if (rcv) return rcv; }
   for (int s = 0; s < c.anf; ++s) {
     h->notch.slot[s].est_re = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].x;
     h->notch.slot[s].est_im = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].y;
@@ -897,6 +909,183 @@ int run_frontend(ldvb_handle *h, const RawSrc &src, int fmt, uint64_t avail, uin
 
 // ----------------------------------------------------------------------- receiver
 
+// FAST receiver, part 1: cut the owned chunks into spans, run them, stitch the seams.
+int rx_fast_launch(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, uint64_t nchunks_owned) {
+  const ldvb_config &c = h->cfg;
+  const uint64_t nchunks = nchunks_owned;
+    // Span length: fill the machine (one lane per span, ~57 K resident lanes), at
+    // least 4 chunks; 4 chunks of warm-up (timing and carrier loops re-converge
+    // within ~200 symbols when freqw and the AGC are carried, see DESIGN.md).
+    uint32_t S = c.span_chunks;
+    if (!S) S = (uint32_t)std::max<uint64_t>(4, (nchunks + kRxTargetSpans - 1) / kRxTargetSpans);
+    const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 4;
+    a.span_chunks = S;
+    a.warm_chunks = W;
+    a.nspans = (uint32_t)((nchunks + S - 1) / S);
+    a.span_cap = (uint32_t)((S + kRxVerifyChunks + 1) * kRxChunk * h->rx_sym_per_sample) + 64;
+    if (a.nspans > h->rx_max_spans || (uint64_t)a.nspans * a.span_cap * 4 > h->d_rx_spans.bytes)
+      return fail(h, LDVB_EOVERFLOW, "receiver span buffers too small for this batch");
+    a.sym_out = h->d_rx_spans.as<uint32_t>();
+    a.head_log = h->d_rx_head.as<RxSeamSym>();
+    a.tail_log = h->d_rx_tail.as<RxSeamSym>();
+    KL("rx", launch_rx(a, nullptr, 0, h->st));
+    sa.info = a.info; sa.head_log = a.head_log; sa.tail_log = a.tail_log;
+    sa.nspans = a.nspans; sa.nrot = h->cst.nrotations; sa.nsymbols = h->cst.nsymbols;
+    sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
+    sa.seams = h->d_rx_seams.as<RxSeam>();
+    KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
+  return LDVB_OK;
+}
+
+// Seam verdicts and span counts of the last rx / rx_stitch launches.
+int rx_fetch(ldvb_handle *h, const RxArgs &a, const RxStitchArgs &sa, std::vector<RxSeam> &seams,
+             std::vector<RxSpanInfo> &info) {
+  seams.resize(a.nspans); info.resize(a.nspans);
+  if (a.nspans > 1) CK(cudaMemcpyAsync(seams.data(), sa.seams, sizeof(RxSeam) * (a.nspans - 1), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(info.data(), a.info, sizeof(RxSpanInfo) * a.nspans, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return LDVB_OK;
+}
+
+// Cold start with a carrier offset: the carried freqw (0) is far from the truth, most
+// warm-ups do not converge and most seams fail.  Re-seed the warm-up state with the
+// median frequency / power that the spans themselves reached and run them again; the
+// loops pull in a little more each pass (span 0 keeps the exact carried state when it
+// has one).
+int rx_fast_reseed(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, std::vector<RxSeam> &seams,
+                   std::vector<RxSpanInfo> &info) {
+  for (int attempt = 0; attempt < 6 && a.nspans > 8; ++attempt) {
+    uint32_t nfail = 0;
+    for (uint32_t j = 0; j + 1 < a.nspans; ++j) nfail += seams[j].ok ? 0 : 1;
+    if (nfail <= std::max<uint32_t>(4, a.nspans / 32)) break;
+    std::vector<RxState> ends(a.nspans);
+    CK(cudaMemcpyAsync(ends.data(), a.state_end, sizeof(RxState) * a.nspans, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    std::vector<float> fw(a.nspans), pw(a.nspans);
+    for (uint32_t j = 0; j < a.nspans; ++j) { fw[j] = ends[j].freqw; pw[j] = ends[j].est_insp; }
+    std::nth_element(fw.begin(), fw.begin() + fw.size() / 2, fw.end());
+    std::nth_element(pw.begin(), pw.begin() + pw.size() / 2, pw.end());
+    RxState warm = h->rx_state;
+    warm.freqw = fw[fw.size() / 2];
+    warm.est_insp = pw[pw.size() / 2];
+    if (warm.est_insp > 0) warm.agc_gain = 75.0f / sqrtf(warm.est_insp);
+    CK(cudaMemcpyAsync(h->d_rx_forced.p, &warm, sizeof warm, cudaMemcpyHostToDevice, h->st));
+    a.warm_in = h->d_rx_forced.as<RxState>();
+    ++h->meas.seams_repaired;   // counted as one (global) repair pass
+    KL("rx", launch_rx(a, nullptr, 0, h->st));
+    KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
+    int rc = rx_fetch(h, a, sa, seams, info);
+    if (rc) return rc;
+  }
+  return LDVB_OK;
+}
+
+// FAST receiver, part 2: resolve the seams (device plan, host repair on failure), write the
+// contiguous symbol stream at sym_dst and carry the loop state.  rot0 / skip0 describe the
+// seam in front of span 0 (time-sharded mode; 0 otherwise).
+int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint32_t skip0, uint32_t *sym_dst,
+                    uint64_t room, uint64_t *produced_out, int *cum_out) {
+  uint64_t produced = 0;
+    // Fast path: offsets / skips / rotations are resolved on the device; the host reads back
+    // four numbers.  Only when a seam failed (or a span overflowed) the seams are fetched
+    // and repaired below.
+    KL("rx_plan", launch_rx_plan(a.info, sa.seams, a.nspans, a.span_cap, h->cst.nrotations, rot0, skip0,
+                                 h->d_rx_off.as<uint64_t>(), h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(),
+                                 h->d_counts.as<uint64_t>(), h->st));
+    uint64_t plan[4];
+    CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int cum = (int)plan[2];
+    const bool slow = (plan[0] != 0 || plan[3] != 0);
+    h->meas.seams_total += slow ? 0 : a.nspans - 1;
+    produced = plan[1];
+    if (slow) {
+    std::vector<RxSeam> seams(a.nspans);
+    std::vector<RxSpanInfo> info(a.nspans);
+    auto fetch = [&]() -> int { return rx_fetch(h, a, sa, seams, info); };
+    int rc = fetch();
+    if (rc) return rc;
+    if ((rc = rx_fast_reseed(h, a, sa, seams, info))) return rc;
+    h->meas.seams_total += a.nspans - 1;
+    // Repair failed seams: span j+1 is re-run exactly from the end state of span j.  All
+    // failed spans whose predecessor is final are repaired in ONE launch per round; the
+    // seam behind each repaired span is stitched again (its tail changed).
+    std::vector<uint8_t> fixed(a.nspans, 0);   // seam j resolved by an exact re-run of span j+1
+    for (int round = 0; round < 1 << 20; ++round) {
+      std::vector<uint32_t> spans, restitch;
+      bool prev_bad = false;
+      for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
+        const bool bad = !seams[j].ok && !fixed[j];
+        if (bad && !prev_bad) spans.push_back(j + 1);
+        prev_bad = bad;
+      }
+      if (spans.empty()) break;
+      h->meas.seams_repaired += (uint32_t)spans.size();
+      for (uint32_t sp : spans) {
+        fixed[sp - 1] = 1;
+        if (sp + 1 < a.nspans) { fixed[sp] = 0; restitch.push_back(sp); }
+      }
+      if (h->d_scratch.bytes < (spans.size() + restitch.size()) * 4) return fail(h, LDVB_EOVERFLOW, "repair list");
+      uint32_t *d_list = h->d_scratch.as<uint32_t>();
+      CK(cudaMemcpyAsync(d_list, spans.data(), spans.size() * 4, cudaMemcpyHostToDevice, h->st));
+      KL("rx", launch_rx(a, d_list, (uint32_t)spans.size(), h->st));
+      if (!restitch.empty()) {
+        CK(cudaMemcpyAsync(d_list + spans.size(), restitch.data(), restitch.size() * 4, cudaMemcpyHostToDevice, h->st));
+        KL("rx_stitch", launch_rx_stitch(sa, d_list + spans.size(), (uint32_t)restitch.size(), h->st));
+      }
+      rc = fetch();
+      if (rc) return rc;
+    }
+    for (uint32_t j = 0; j + 1 < a.nspans; ++j)
+      if (fixed[j]) { seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0; }
+    // Offsets, skips and cumulative rotations.
+    std::vector<uint64_t> off(a.nspans + 1, 0);
+    std::vector<uint32_t> skipv(a.nspans, 0);
+    std::vector<uint8_t> rot(a.nspans, 0);
+    cum = rot0 % h->cst.nrotations;
+    skipv[0] = skip0;
+    for (uint32_t j = 0; j < a.nspans; ++j) {
+      if (info[j].n_out + info[j].n_tail > a.span_cap) return fail(h, LDVB_EOVERFLOW, "span capacity exceeded");
+      uint64_t keep = info[j].n_out;
+      if (j > 0) {
+        skipv[j] = (uint32_t)seams[j - 1].skip_next;
+        cum = (cum + seams[j - 1].rot) % h->cst.nrotations;
+      }
+      rot[j] = (uint8_t)cum;
+      keep -= skipv[j];
+      if (j + 1 < a.nspans) keep += (uint64_t)seams[j].extend_prev;
+      off[j + 1] = off[j] + keep;
+    }
+    produced = off[a.nspans];
+    if (produced > room) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
+    CK(cudaMemcpyAsync(h->d_rx_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->d_rx_skip.p, skipv.data(), skipv.size() * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->d_rx_rot.p, rot.data(), rot.size(), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));   // the vectors above are locals
+    }  // slow path
+    if (produced > room) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
+    RxCompactArgs ca;
+    ca.sym_in = a.sym_out; ca.span_cap = a.span_cap; ca.nspans = a.nspans;
+    ca.span_offset = h->d_rx_off.as<uint64_t>(); ca.span_skip = h->d_rx_skip.as<uint32_t>();
+    ca.span_rot = h->d_rx_rot.as<uint8_t>(); ca.rot_perm = h->d_rotperm.as<uint8_t>();
+    ca.nsymbols = h->cst.nsymbols; ca.sym_out = sym_dst;
+    KL("rx_compact", launch_rx_compact(ca, produced, h->st));
+    // Carry: the end state of the last span.  Its phase is rotated back by the
+    // cumulative rotation so that the next batch continues in span 0's frame.
+    CK(cudaMemcpyAsync(&h->rx_state, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (cum) {
+      // Span frames differ by cum*65536/nrot phase units: symbols of the last span
+      // were de-rotated by `cum`; adding the same angle to the PLL phase makes the
+      // next batch's span 0 produce symbols in the reference frame directly.
+      float shift = (float)cum * (65536.0f / h->cst.nrotations);
+      h->rx_state.phase = fmodf(h->rx_state.phase - shift, 65536.0f);
+    }
+    *produced_out = produced;
+  *cum_out = cum;
+  return LDVB_OK;
+}
+
 int run_receiver(ldvb_handle *h) {
   const ldvb_config &c = h->cfg;
   Stream &in = h->s_pp;
@@ -910,7 +1099,7 @@ int run_receiver(ldvb_handle *h) {
   a.p.cstln = h->d_cstln.as<CstlnCellDev>();
   a.p.trig = h->d_trig.as<float2>();
   a.x = reinterpret_cast<const float2 *>(in.at(0));
-  a.nchunks = nchunks;
+  a.nchunks = nchunks; a.avail_chunks = nchunks;
   a.chunk0 = 0; a.first_exact = 1; a.prev_end = nullptr;
   CK(cudaMemcpyAsync(h->d_rx_state.p, &h->rx_state, sizeof(RxState), cudaMemcpyHostToDevice, h->st));
   CK(cudaMemsetAsync(h->d_rx_measn.p, 0, 4, h->st));
@@ -957,152 +1146,11 @@ int run_receiver(ldvb_handle *h) {
       smp.release(); smpf.release();
     }
   } else {
-    // Span length: fill the machine (one lane per span, ~57 K resident lanes), at
-    // least 4 chunks; 4 chunks of warm-up (timing and carrier loops re-converge
-    // within ~200 symbols when freqw and the AGC are carried, see DESIGN.md).
-    uint32_t S = c.span_chunks;
-    if (!S) S = (uint32_t)std::max<uint64_t>(4, (nchunks + kRxTargetSpans - 1) / kRxTargetSpans);
-    const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 4;
-    a.span_chunks = S;
-    a.warm_chunks = W;
-    a.nspans = (uint32_t)((nchunks + S - 1) / S);
-    a.span_cap = (uint32_t)((S + kRxVerifyChunks + 1) * kRxChunk * h->rx_sym_per_sample) + 64;
-    if (a.nspans > h->rx_max_spans || (uint64_t)a.nspans * a.span_cap * 4 > h->d_rx_spans.bytes)
-      return fail(h, LDVB_EOVERFLOW, "receiver span buffers too small for this batch");
-    a.sym_out = h->d_rx_spans.as<uint32_t>();
-    a.head_log = h->d_rx_head.as<RxSeamSym>();
-    a.tail_log = h->d_rx_tail.as<RxSeamSym>();
-    KL("rx", launch_rx(a, nullptr, 0, h->st));
     RxStitchArgs sa;
-    sa.info = a.info; sa.head_log = a.head_log; sa.tail_log = a.tail_log;
-    sa.nspans = a.nspans; sa.nrot = h->cst.nrotations; sa.nsymbols = h->cst.nsymbols;
-    sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
-    sa.seams = h->d_rx_seams.as<RxSeam>();
-    KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
-    // Fast path: offsets / skips / rotations are resolved on the device; the host reads back
-    // four numbers.  Only when a seam failed (or a span overflowed) the seams are fetched
-    // and repaired below.
-    KL("rx_plan", launch_rx_plan(a.info, sa.seams, a.nspans, a.span_cap, h->cst.nrotations, h->d_rx_off.as<uint64_t>(),
-                                 h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(), h->d_counts.as<uint64_t>(), h->st));
-    uint64_t plan[4];
-    CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    int cum = (int)plan[2];
-    const bool slow = (plan[0] != 0 || plan[3] != 0);
-    h->meas.seams_total += slow ? 0 : a.nspans - 1;
-    produced = plan[1];
-    if (slow) {
-    std::vector<RxSeam> seams(a.nspans);
-    std::vector<RxSpanInfo> info(a.nspans);
-    auto fetch = [&]() -> int {
-      if (a.nspans > 1) CK(cudaMemcpyAsync(seams.data(), sa.seams, sizeof(RxSeam) * (a.nspans - 1), cudaMemcpyDeviceToHost, h->st));
-      CK(cudaMemcpyAsync(info.data(), a.info, sizeof(RxSpanInfo) * a.nspans, cudaMemcpyDeviceToHost, h->st));
-      CK(cudaStreamSynchronize(h->st));
-      return LDVB_OK;
-    };
-    int rc = fetch();
-    if (rc) return rc;
-    // Cold start with a carrier offset: the carried freqw (0) is far from the truth, most
-    // warm-ups do not converge and most seams fail.  Re-seed the warm-up state with the
-    // median frequency / power that the spans themselves reached and run them again; the
-    // loops pull in a little more each pass (span 0 always keeps the exact carried state).
-    for (int attempt = 0; attempt < 6 && a.nspans > 8; ++attempt) {
-      uint32_t nfail = 0;
-      for (uint32_t j = 0; j + 1 < a.nspans; ++j) nfail += seams[j].ok ? 0 : 1;
-      if (nfail <= std::max<uint32_t>(4, a.nspans / 32)) break;
-      std::vector<RxState> ends(a.nspans);
-      CK(cudaMemcpyAsync(ends.data(), a.state_end, sizeof(RxState) * a.nspans, cudaMemcpyDeviceToHost, h->st));
-      CK(cudaStreamSynchronize(h->st));
-      std::vector<float> fw(a.nspans), pw(a.nspans);
-      for (uint32_t j = 0; j < a.nspans; ++j) { fw[j] = ends[j].freqw; pw[j] = ends[j].est_insp; }
-      std::nth_element(fw.begin(), fw.begin() + fw.size() / 2, fw.end());
-      std::nth_element(pw.begin(), pw.begin() + pw.size() / 2, pw.end());
-      RxState warm = h->rx_state;
-      warm.freqw = fw[fw.size() / 2];
-      warm.est_insp = pw[pw.size() / 2];
-      if (warm.est_insp > 0) warm.agc_gain = 75.0f / sqrtf(warm.est_insp);
-      CK(cudaMemcpyAsync(h->d_rx_forced.p, &warm, sizeof warm, cudaMemcpyHostToDevice, h->st));
-      a.warm_in = h->d_rx_forced.as<RxState>();
-      ++h->meas.seams_repaired;   // counted as one (global) repair pass
-      KL("rx", launch_rx(a, nullptr, 0, h->st));
-      KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
-      rc = fetch();
-      if (rc) return rc;
-    }
-    h->meas.seams_total += a.nspans - 1;
-    // Repair failed seams: span j+1 is re-run exactly from the end state of span j.  All
-    // failed spans whose predecessor is final are repaired in ONE launch per round; the
-    // seam behind each repaired span is stitched again (its tail changed).
-    std::vector<uint8_t> fixed(a.nspans, 0);   // seam j resolved by an exact re-run of span j+1
-    for (int round = 0; round < 1 << 20; ++round) {
-      std::vector<uint32_t> spans, restitch;
-      bool prev_bad = false;
-      for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
-        const bool bad = !seams[j].ok && !fixed[j];
-        if (bad && !prev_bad) spans.push_back(j + 1);
-        prev_bad = bad;
-      }
-      if (spans.empty()) break;
-      h->meas.seams_repaired += (uint32_t)spans.size();
-      for (uint32_t sp : spans) {
-        fixed[sp - 1] = 1;
-        if (sp + 1 < a.nspans) { fixed[sp] = 0; restitch.push_back(sp); }
-      }
-      if (h->d_scratch.bytes < (spans.size() + restitch.size()) * 4) return fail(h, LDVB_EOVERFLOW, "repair list");
-      uint32_t *d_list = h->d_scratch.as<uint32_t>();
-      CK(cudaMemcpyAsync(d_list, spans.data(), spans.size() * 4, cudaMemcpyHostToDevice, h->st));
-      KL("rx", launch_rx(a, d_list, (uint32_t)spans.size(), h->st));
-      if (!restitch.empty()) {
-        CK(cudaMemcpyAsync(d_list + spans.size(), restitch.data(), restitch.size() * 4, cudaMemcpyHostToDevice, h->st));
-        KL("rx_stitch", launch_rx_stitch(sa, d_list + spans.size(), (uint32_t)restitch.size(), h->st));
-      }
-      rc = fetch();
-      if (rc) return rc;
-    }
-    for (uint32_t j = 0; j + 1 < a.nspans; ++j)
-      if (fixed[j]) { seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0; }
-    // Offsets, skips and cumulative rotations.
-    std::vector<uint64_t> off(a.nspans + 1, 0);
-    std::vector<uint32_t> skipv(a.nspans, 0);
-    std::vector<uint8_t> rot(a.nspans, 0);
-    cum = 0;
-    for (uint32_t j = 0; j < a.nspans; ++j) {
-      if (info[j].n_out + info[j].n_tail > a.span_cap) return fail(h, LDVB_EOVERFLOW, "span capacity exceeded");
-      uint64_t keep = info[j].n_out;
-      if (j > 0) {
-        skipv[j] = (uint32_t)seams[j - 1].skip_next;
-        cum = (cum + seams[j - 1].rot) % h->cst.nrotations;
-      }
-      rot[j] = (uint8_t)cum;
-      keep -= skipv[j];
-      if (j + 1 < a.nspans) keep += (uint64_t)seams[j].extend_prev;
-      off[j + 1] = off[j] + keep;
-    }
-    produced = off[a.nspans];
-    if (produced > room) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
-    CK(cudaMemcpyAsync(h->d_rx_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(h->d_rx_skip.p, skipv.data(), skipv.size() * 4, cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemcpyAsync(h->d_rx_rot.p, rot.data(), rot.size(), cudaMemcpyHostToDevice, h->st));
-    CK(cudaStreamSynchronize(h->st));   // the vectors above are locals
-    }  // slow path
-    if (produced > room) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
-    RxCompactArgs ca;
-    ca.sym_in = a.sym_out; ca.span_cap = a.span_cap; ca.nspans = a.nspans;
-    ca.span_offset = h->d_rx_off.as<uint64_t>(); ca.span_skip = h->d_rx_skip.as<uint32_t>();
-    ca.span_rot = h->d_rx_rot.as<uint8_t>(); ca.rot_perm = h->d_rotperm.as<uint8_t>();
-    ca.nsymbols = h->cst.nsymbols; ca.sym_out = sym_dst;
-    KL("rx_compact", launch_rx_compact(ca, produced, h->st));
-    // Carry: the end state of the last span.  Its phase is rotated back by the
-    // cumulative rotation so that the next batch continues in span 0's frame.
-    CK(cudaMemcpyAsync(&h->rx_state, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    if (cum) {
-      // Span frames differ by cum*65536/nrot phase units: symbols of the last span
-      // were de-rotated by `cum`; adding the same angle to the PLL phase makes the
-      // next batch's span 0 produce symbols in the reference frame directly.
-      float shift = (float)cum * (65536.0f / h->cst.nrotations);
-      h->rx_state.phase = fmodf(h->rx_state.phase - shift, 65536.0f);
-    }
+    int rcf = rx_fast_launch(h, a, sa, nchunks);
+    if (rcf) return rcf;
+    int cum = 0;
+    if ((rcf = rx_fast_resolve(h, a, sa, 0, 0, sym_dst, room, &produced, &cum))) return rcf;
   }
   // Measurements recorded by the kernel: {chunk, freq_tap, ss, mer}
   {
@@ -1286,6 +1334,80 @@ int run_fec(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_out) 
   return stream_consume(h, in, npk * 204, h->d_scratch);
 }
 
+// Deconvolution <-> sync -> de-interleave -> RS -> derandomise on the symbols in s_sym.
+int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_out) {
+  const ldvb_config &c = h->cfg;
+  int rc;
+  WallTimer *wt = nullptr;
+  struct WtGuard { WallTimer *&p; ~WtGuard() { delete p; } } wt_guard{wt};
+  delete wt; wt = new WallTimer(h, "wall:deconv_sync");
+  // ---- deconvolution <-> sync (with the backward next_sync edge, dvb.h:771-778)
+  std::vector<uint8_t> tap_bytes;  // bytes that stay in the stream, for the tap
+  if (c.viterbi) {
+    uint64_t produced = 0;
+    const uint64_t at = h->s_bytes.count;
+    if ((rc = run_viterbi(h, &produced))) return rc;
+    if (c.keep_taps && produced) {
+      tap_bytes.resize(produced);
+      CK(cudaMemcpyAsync(tap_bytes.data(), h->s_bytes.at(at), produced, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+    }
+    // mpeg_sync has no deconvolver to poke in this mode (leandvb.cc:560: r_deconv == NULL)
+    for (int guard = 0; guard < 1 << 20; ++guard) {
+      rc = run_sync(h);
+      if (rc < 0) return rc;
+      if (rc == 0) break;
+    }
+  }
+  for (int guard = 0; guard < 64 && !c.viterbi; ++guard) {
+    if (h->skip) {  // dvb.h:415-416
+      if (h->s_sym.count < (uint64_t)h->skip) break;
+      if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
+      h->skip = 0;
+    }
+    DeconvRun run;
+    if ((rc = deconv_launch(h, ~0ull, &run))) return rc;
+    const size_t tap_at = tap_bytes.size();
+    if (c.keep_taps && run.produced) {
+      tap_bytes.resize(tap_at + run.produced);
+      CK(cudaMemcpy(tap_bytes.data() + tap_at, h->s_bytes.at(h->s_bytes.count), run.produced, cudaMemcpyDeviceToHost));
+    }
+    h->s_bytes.count += run.produced;
+    h->s_bytes.fresh += run.produced;
+    rc = run_sync(h);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if ((rc = deconv_commit(h, run))) return rc;
+      break;
+    }
+    // Third fruitless sweep: mpeg_sync calls deconv->next_sync().  Bytes of this
+    // run that the search has not consumed are void (their symbols are re-read by
+    // the next hypothesis); the register state is re-derived at that exact byte.
+    const uint64_t left = h->s_bytes.count;
+    const uint64_t voided = std::min(left, run.produced);
+    const uint64_t used = run.produced - voided;
+    h->s_bytes.count = left - voided;
+    h->s_bytes.fresh -= voided;
+    if (c.keep_taps) tap_bytes.resize(tap_at + used);
+    DeconvRun kept;
+    kept.after = h->hyp[h->locked];
+    if (used && (rc = deconv_launch(h, used, &kept))) return rc;
+    if ((rc = deconv_commit(h, kept))) return rc;
+    if (++h->locked == 4) { h->locked = 0; h->skip = 1; }  // dvb.h:185-193
+  }
+  if (c.keep_taps) {
+    Tap &t = h->taps[LDVB_TAP_BYTES];
+    if (t.buf.bytes < tap_bytes.size()) { t.buf.release(); CK(t.buf.alloc(tap_bytes.size() + 4096)); }
+    if (!tap_bytes.empty()) CK(cudaMemcpy(t.buf.p, tap_bytes.data(), tap_bytes.size(), cudaMemcpyHostToDevice));
+    t.bytes = tap_bytes.size();
+  }
+  if ((rc = tap_store(h, LDVB_TAP_MPEGBYTES, h->s_mpeg.at(h->s_mpeg.count - h->s_mpeg.fresh), h->s_mpeg.fresh))) return rc;
+  // ---- de-interleave + RS + derandomise
+  delete wt; wt = new WallTimer(h, "wall:fec");
+  if ((rc = run_fec(h, ts_dst, ts_cap, ts_out))) return rc;
+  return LDVB_OK;
+}
+
 // ------------------------------------------------------------------ whole chain
 
 int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_t n, uint8_t *ts_dst,
@@ -1373,71 +1495,8 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
     t.bytes = h->meas_log.size() * 4;
   }
 
-  delete wt; wt = new WallTimer(h, "wall:deconv_sync");
-  // ---- deconvolution <-> sync (with the backward next_sync edge, dvb.h:771-778)
-  std::vector<uint8_t> tap_bytes;  // bytes that stay in the stream, for the tap
-  if (c.viterbi) {
-    uint64_t produced = 0;
-    const uint64_t at = h->s_bytes.count;
-    if ((rc = run_viterbi(h, &produced))) return rc;
-    if (c.keep_taps && produced) {
-      tap_bytes.resize(produced);
-      CK(cudaMemcpyAsync(tap_bytes.data(), h->s_bytes.at(at), produced, cudaMemcpyDeviceToHost, h->st));
-      CK(cudaStreamSynchronize(h->st));
-    }
-    // mpeg_sync has no deconvolver to poke in this mode (leandvb.cc:560: r_deconv == NULL)
-    for (int guard = 0; guard < 1 << 20; ++guard) {
-      rc = run_sync(h);
-      if (rc < 0) return rc;
-      if (rc == 0) break;
-    }
-  }
-  for (int guard = 0; guard < 64 && !c.viterbi; ++guard) {
-    if (h->skip) {  // dvb.h:415-416
-      if (h->s_sym.count < (uint64_t)h->skip) break;
-      if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
-      h->skip = 0;
-    }
-    DeconvRun run;
-    if ((rc = deconv_launch(h, ~0ull, &run))) return rc;
-    const size_t tap_at = tap_bytes.size();
-    if (c.keep_taps && run.produced) {
-      tap_bytes.resize(tap_at + run.produced);
-      CK(cudaMemcpy(tap_bytes.data() + tap_at, h->s_bytes.at(h->s_bytes.count), run.produced, cudaMemcpyDeviceToHost));
-    }
-    h->s_bytes.count += run.produced;
-    h->s_bytes.fresh += run.produced;
-    rc = run_sync(h);
-    if (rc < 0) return rc;
-    if (rc == 0) {
-      if ((rc = deconv_commit(h, run))) return rc;
-      break;
-    }
-    // Third fruitless sweep: mpeg_sync calls deconv->next_sync().  Bytes of this
-    // run that the search has not consumed are void (their symbols are re-read by
-    // the next hypothesis); the register state is re-derived at that exact byte.
-    const uint64_t left = h->s_bytes.count;
-    const uint64_t voided = std::min(left, run.produced);
-    const uint64_t used = run.produced - voided;
-    h->s_bytes.count = left - voided;
-    h->s_bytes.fresh -= voided;
-    if (c.keep_taps) tap_bytes.resize(tap_at + used);
-    DeconvRun kept;
-    kept.after = h->hyp[h->locked];
-    if (used && (rc = deconv_launch(h, used, &kept))) return rc;
-    if ((rc = deconv_commit(h, kept))) return rc;
-    if (++h->locked == 4) { h->locked = 0; h->skip = 1; }  // dvb.h:185-193
-  }
-  if (c.keep_taps) {
-    Tap &t = h->taps[LDVB_TAP_BYTES];
-    if (t.buf.bytes < tap_bytes.size()) { t.buf.release(); CK(t.buf.alloc(tap_bytes.size() + 4096)); }
-    if (!tap_bytes.empty()) CK(cudaMemcpy(t.buf.p, tap_bytes.data(), tap_bytes.size(), cudaMemcpyHostToDevice));
-    t.bytes = tap_bytes.size();
-  }
-  if ((rc = tap_store(h, LDVB_TAP_MPEGBYTES, h->s_mpeg.at(h->s_mpeg.count - h->s_mpeg.fresh), h->s_mpeg.fresh))) return rc;
-  // ---- de-interleave + RS + derandomise
-  delete wt; wt = new WallTimer(h, "wall:fec");
-  if ((rc = run_fec(h, ts_dst, ts_cap, ts_out))) return rc;
+  delete wt; wt = nullptr;
+  if ((rc = run_backend(h, ts_dst, ts_cap, ts_out))) return rc;
   h->meas.kernel_launches = h->launches;
   return LDVB_OK;
 }
