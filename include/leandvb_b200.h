@@ -258,13 +258,25 @@ int ldvb_set_rx_state(ldvb_handle *h, const uint32_t w[22]);
  * Constraints: rx_mode = LDVB_RX_FAST; n_halo, n_chunk and abs_raw0 (absolute
  * index of the first halo sample) multiples of lcm(4096, 128*decimation);
  * n_halo >= ldvb_shard_min_halo() except for the first chunk of the stream
- * (n_halo = 0, edge_in = NULL). */
+ * (abs_raw0 = 0, n_halo = 0, edge_in = NULL), whose front stage also resets the handle. */
+typedef struct ldvb_shard {
+  const void *iq_dev;        /* device: [n_halo | n_chunk] samples in cfg.input_format   */
+  uint64_t abs_raw0;         /* absolute stream index of iq_dev[0]                       */
+  uint64_t n_halo, n_chunk;  /* samples                                                  */
+  uint64_t n_halo_next;      /* halo the NEXT chunk will be given (0 for the last chunk) */
+  int32_t  last;             /* final chunk of the stream: nothing is left for a successor */
+  int32_t  reserved;
+  int32_t  bins_before[4];   /* auto_notch slot bins in force at abs_raw0 (-1 = none)    */
+  int32_t  bins_after[4];    /* out (ldvb_shard_detect): bins in force where the next
+                                chunk's halo starts = its bins_before                    */
+} ldvb_shard;
+
 size_t ldvb_edge_size(void);
 size_t ldvb_shard_min_halo(const ldvb_handle *h);
-int ldvb_shard_detect(ldvb_handle *h, const void *iq_dev, size_t n_halo, size_t n_chunk,
-		      uint64_t abs_raw0, const int32_t bins_before[4], int32_t bins_after[4]);
-int ldvb_shard_front(ldvb_handle *h, const void *iq_dev, size_t n_halo, size_t n_chunk,
-		     uint64_t abs_raw0, const int32_t bins_before[4]);
+int ldvb_shard_detect(ldvb_handle *h, ldvb_shard *s);
+int ldvb_shard_front(ldvb_handle *h, const ldvb_shard *s);
+/* edge_in: ldvb_edge_size() bytes from the previous chunk's ldvb_shard_back (NULL for the
+ * first chunk); edge_out: ldvb_edge_size() bytes for the next chunk (may be NULL). Host memory. */
 int ldvb_shard_back(ldvb_handle *h, const void *edge_in, uint8_t *ts_dev, size_t cap_packets,
 		    size_t *n_packets, void *edge_out);
 

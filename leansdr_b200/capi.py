@@ -68,7 +68,15 @@ EXPORTS = [
     "ldvb_table", "ldvb_host_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
     "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
     "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
+    "ldvb_edge_size", "ldvb_shard_min_halo", "ldvb_shard_detect", "ldvb_shard_front", "ldvb_shard_back",
 ]
+
+
+class Shard(C.Structure):
+    """ldvb_shard (include/leandvb_b200.h): one time chunk [halo | chunk] of the stream."""
+    _fields_ = [("iq_dev", C.c_void_p), ("abs_raw0", C.c_uint64), ("n_halo", C.c_uint64), ("n_chunk", C.c_uint64),
+                ("n_halo_next", C.c_uint64), ("last", C.c_int32), ("reserved", C.c_int32),
+                ("bins_before", C.c_int32 * 4), ("bins_after", C.c_int32 * 4)]
 
 
 class KernelStat(C.Structure):
@@ -116,6 +124,12 @@ def load():
     L.ldvb_set_stream.argtypes = [vp, vp]
     L.ldvb_profile.argtypes = [vp, C.c_int]
     L.ldvb_get_profile.argtypes = [vp, C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]
+    L.ldvb_edge_size.restype = sz
+    L.ldvb_shard_min_halo.restype = sz
+    L.ldvb_shard_min_halo.argtypes = [vp]
+    L.ldvb_shard_detect.argtypes = [vp, C.POINTER(Shard)]
+    L.ldvb_shard_front.argtypes = [vp, C.POINTER(Shard)]
+    L.ldvb_shard_back.argtypes = [vp, vp, vp, sz, C.POINTER(sz), vp]
     _lib = L
     return L
 
@@ -265,6 +279,37 @@ class Receiver:
     def set_rx_state(self, w):
         w = np.ascontiguousarray(w, np.uint32)
         self._ck(self.L.ldvb_set_rx_state(self.h, _p(w)), "ldvb_set_rx_state")
+
+    # ---- time sharding (one stream over several handles)
+    def edge_size(self) -> int:
+        return int(self.L.ldvb_edge_size())
+
+    def shard_min_halo(self) -> int:
+        return int(self.L.ldvb_shard_min_halo(self.h))
+
+    def shard(self, iq_ptr: int, abs_raw0: int, n_halo: int, n_chunk: int, n_halo_next: int, last: bool = False,
+              bins_before=(-1, -1, -1, -1)) -> Shard:
+        s = Shard()
+        s.iq_dev = iq_ptr; s.abs_raw0 = abs_raw0; s.n_halo = n_halo; s.n_chunk = n_chunk
+        s.n_halo_next = n_halo_next; s.last = 1 if last else 0
+        for i in range(4):
+            s.bins_before[i] = int(bins_before[i]); s.bins_after[i] = -1
+        return s
+
+    def shard_detect(self, s: Shard):
+        """Fills s.bins_after; returns it as a tuple."""
+        self._ck(self.L.ldvb_shard_detect(self.h, C.byref(s)), "ldvb_shard_detect")
+        return tuple(int(v) for v in s.bins_after)
+
+    def shard_front(self, s: Shard):
+        self._ck(self.L.ldvb_shard_front(self.h, C.byref(s)), "ldvb_shard_front")
+
+    def shard_back(self, edge_in, ts_ptr: int, cap_packets: int, edge_out) -> int:
+        """edge_in / edge_out: uint8 numpy arrays of edge_size() bytes, or None."""
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_shard_back(self.h, _p(edge_in) if edge_in is not None else None, ts_ptr, cap_packets,
+                                        C.byref(n), _p(edge_out) if edge_out is not None else None), "ldvb_shard_back")
+        return int(n.value)
 
     def get_state(self) -> np.ndarray:
         n = self.L.ldvb_state_size(self.h)

@@ -131,6 +131,19 @@ struct ldvb_handle {
   int derand_pos = 0;
   DevBuf d_counts;
 
+  // ---- time-sharded mode (ldvb_shard_*): what the front stage leaves for the back stage
+  struct Shard {
+    bool det_valid = false, valid = false;
+    ldvb_shard desc;
+    std::vector<NotchEpoch> epochs;      // local block units
+    // geometry (absolute units unless noted)
+    uint64_t R0 = 0, base_chunk = 0, own_begin = 0, own_end = 0, avail_end = 0, notch_b0 = 0;
+    bool first = false;
+    RxArgs a; RxStitchArgs sa; NotchApplyArgs na;
+    const float2 *pp = nullptr;
+  } shard;
+  DevBuf d_edge_tail, d_edge_state, d_edge_seam;
+
   // ---- pipelined host input (ldvb_push): copy engine fills one staging buffer while
   // the chain works on the other
   DevBuf d_stage[2];
@@ -440,7 +453,8 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
-                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts};
+                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
+                    &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam};
   for (DevBuf *b : bufs) b->release();
   for (Tap &t : h->taps) t.buf.release();
   for (int i = 0; i < 2; ++i) { h->d_stage[i].release(); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
@@ -1501,6 +1515,433 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   return LDVB_OK;
 }
 
+
+// ============================================================== time sharding
+// SURVEY.md 8(e).  One stream, consecutive chunks on different handles (GPUs).
+// Front stage (speculative, needs only the halo): notch, front end, receiver spans.
+// Back stage (exact, needs the previous chunk's EDGE): seam to the previous chunk,
+// symbol stream, deconvolution/sync/FEC, then this chunk's EDGE.
+
+constexpr uint32_t kEdgeMagic = 0x45474445;
+constexpr uint32_t kEdgeSym = 2048, kEdgeBytes = 4096, kEdgeMpeg = 4096, kEdgeVit = 16;
+
+struct EdgeBlob {
+  uint32_t magic, size;
+  uint64_t abs_raw_end;        // one past the last raw sample the exporting handle held
+  uint64_t own_end_chunk;      // absolute receiver chunk where the next handle's ownership starts
+  // receiver: loop state at own_end_chunk (reference frame), last span's verification log
+  RxState rx_end;
+  int32_t cum_rot, have_tail;
+  uint32_t n_tail, tail_first_word;
+  RxSeamSym tail_log[kRxSeamLog];
+  // notch: estimates entering block notch_block
+  NotchState notch;
+  uint64_t notch_block;
+  // deconvolution / framing
+  HypState hyp[4];
+  int32_t locked, skip;
+  SyncState sync;
+  int32_t derand_pos, lock;
+  VitCtl vit_ctl;
+  int32_t n_vit, pad0;
+  VitDecState vit[kEdgeVit];
+  uint32_t n_sym, n_bytes, n_mpeg, pad1;
+  uint32_t sym[kEdgeSym];
+  uint8_t bytes[kEdgeBytes];
+  uint8_t mpeg[kEdgeMpeg];
+};
+
+uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+
+uint64_t shard_unit(const ldvb_handle *h) {
+  uint64_t u = (uint64_t)kRxChunk * h->decim;
+  if (h->cfg.anf) u = u / gcd64(u, kNotchN) * kNotchN;
+  return u;
+}
+
+// Receiver chunks that can be run when the raw stream is known up to (absolute) sample E.
+uint64_t shard_chunks_avail(const ldvb_handle *h, uint64_t E) {
+  const uint64_t N = h->use_fir ? (uint64_t)h->fir_n : 0, D = (uint64_t)h->decim;
+  const uint64_t pp = N ? (E >= N ? (E - N) / D : 0) : E / D;   // dsp.h:246-247, generic.h:254
+  return pp >= (uint64_t)kRxChunk + h->readahead ? (pp - h->readahead) / kRxChunk : 0;   // sdr.h:783
+}
+
+uint32_t shard_warm_chunks(const ldvb_handle *h) { return h->cfg.warmup_chunks ? h->cfg.warmup_chunks : 4; }
+constexpr uint64_t kNotchLead = (uint64_t)kNotchN * 4;   // 2 exact warm-up blocks + the 8192-sample guess window
+
+uint64_t shard_min_halo(const ldvb_handle *h) {
+  const uint64_t u = shard_unit(h), D = (uint64_t)h->decim;
+  uint64_t need = (h->use_fir ? h->fir_n : 0) + (uint64_t)h->readahead * D +
+                  (2 + kRxVerifyChunks + shard_warm_chunks(h)) * (uint64_t)kRxChunk * D + u + (h->cfg.anf ? kNotchLead : 0);
+  return (need + u - 1) / u * u + u;
+}
+
+// Where a chunk [A0, A0+H+C) starts its stages.  Pure function of (A0, H): the handle that
+// exports an EDGE evaluates it for its successor.
+struct ShardStart { uint64_t R0, own_begin, notch_b0; };
+ShardStart shard_start(const ldvb_handle *h, uint64_t A0, uint64_t H) {
+  ShardStart g;
+  if (H == 0) { g.R0 = A0; g.own_begin = A0 / ((uint64_t)kRxChunk * h->decim); g.notch_b0 = A0 / kNotchN; return g; }
+  const uint64_t u = shard_unit(h), cs = (uint64_t)kRxChunk * h->decim;
+  g.own_begin = shard_chunks_avail(h, A0 + H) - kRxVerifyChunks;
+  const uint64_t cw = g.own_begin - shard_warm_chunks(h);
+  g.R0 = cw * cs / u * u;
+  g.notch_b0 = g.R0 / kNotchN;
+  return g;
+}
+
+int shard_check(ldvb_handle *h, const ldvb_shard *s) {
+  if (!h || !s) return LDVB_EINVAL;
+  if (h->cfg.rx_mode != LDVB_RX_FAST) return fail(h, LDVB_EINVAL, "time sharding needs rx_mode = LDVB_RX_FAST");
+  if (h->cfg.sampler == LDVB_SAMP_RRC) return fail(h, LDVB_EINVAL, "time sharding: RRC sampler not supported yet");
+  const uint64_t u = shard_unit(h);
+  if (s->n_halo % u || s->n_chunk % u || s->abs_raw0 % u || s->n_halo_next % u)
+    return fail(h, LDVB_EINVAL, "time sharding: abs_raw0, n_halo, n_chunk must be multiples of lcm(4096, 128*decimation)");
+  if (!s->iq_dev || (reinterpret_cast<uintptr_t>(s->iq_dev) & 15)) return fail(h, LDVB_EINVAL, "iq_dev must be 16-byte aligned");
+  if (s->n_halo + s->n_chunk > h->cfg.max_batch) return fail(h, LDVB_EOVERFLOW, "halo + chunk exceed max_batch");
+  if (s->n_halo == 0 && s->abs_raw0 != 0) return fail(h, LDVB_EINVAL, "only the first chunk of the stream may come without a halo");
+  if (s->n_halo && s->n_halo < shard_min_halo(h)) return fail(h, LDVB_EINVAL, "halo shorter than ldvb_shard_min_halo()");
+  if (s->n_halo_next && s->n_halo_next < shard_min_halo(h)) return fail(h, LDVB_EINVAL, "next halo shorter than ldvb_shard_min_halo()");
+  if (s->n_chunk < 4 * s->n_halo_next + 16 * u || s->n_chunk < 4 * s->n_halo) return fail(h, LDVB_EINVAL, "chunk too small for its halo");
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  return LDVB_OK;
+}
+
+// auto_notch::detect() (sdr.h:76-118) on the detect points inside [halo | chunk]; builds the
+// epoch list of the chunk and the bins in force where the next chunk's halo starts.
+int shard_detect(ldvb_handle *h, ldvb_shard *s) {
+  const ldvb_config &c = h->cfg;
+  ldvb_handle::Shard &sh = h->shard;
+  sh.det_valid = false; sh.valid = false;
+  sh.epochs.clear();
+  for (int i = 0; i < 4; ++i) s->bins_after[i] = (c.anf && i < c.anf) ? s->bins_before[i] : -1;
+  if (!c.anf) { sh.desc = *s; sh.det_valid = true; return LDVB_OK; }
+  const uint64_t nblocks = (s->n_halo + s->n_chunk) / kNotchN, blk0 = s->abs_raw0 / kNotchN;
+  const uint64_t next_blk = (s->n_halo + s->n_chunk - s->n_halo_next) / kNotchN;   // local
+  std::vector<uint64_t> dblocks;
+  for (uint64_t b = 1023 - (blk0 % 1024); b < nblocks; b += 1024) dblocks.push_back(b);   // (blk0 + b + 1) % 1024 == 0
+  NotchEpoch e0;
+  memset(&e0, 0, sizeof e0);
+  int cur[kNotchMaxSlots];
+  for (int sl = 0; sl < kNotchMaxSlots; ++sl) { cur[sl] = sl < c.anf ? s->bins_before[sl] : -1; e0.bin[sl] = cur[sl]; }
+  for (int sl = 0; sl < c.anf; ++sl) { int rc = notch_table_for_bin(h, cur[sl], &e0.table_index[sl]); if (rc) return rc; }
+  sh.epochs.push_back(e0);
+  if (!dblocks.empty()) {
+    if (dblocks.size() * 8 > h->d_notch_blocks.bytes) return fail(h, LDVB_EOVERFLOW, "too many notch detect points");
+    NotchDetectArgs d;
+    d.src.head = s->iq_dev; d.src.head_count = s->n_halo + s->n_chunk; d.src.main = nullptr; d.src.c0 = 0;
+    d.fmt = c.input_format; d.scale = c.float_scale;
+    CK(cudaMemcpyAsync(h->d_notch_blocks.p, dblocks.data(), dblocks.size() * 8, cudaMemcpyHostToDevice, h->st));
+    d.block_index = h->d_notch_blocks.as<uint64_t>();
+    d.ndetect = (int)dblocks.size(); d.nslots = c.anf;
+    d.twiddle_rev = h->d_twiddle.as<float2>();
+    d.bins_out = h->d_notch_bins.as<int32_t>();
+    KL("notch_detect", launch_notch_detect(d, h->st));
+    std::vector<int32_t> bins(dblocks.size() * c.anf);
+    CK(cudaMemcpyAsync(bins.data(), h->d_notch_bins.p, bins.size() * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (size_t k = 0; k < dblocks.size(); ++k) {
+      if (dblocks[k] < next_blk) for (int sl = 0; sl < c.anf; ++sl) s->bins_after[sl] = bins[k * c.anf + sl];
+      bool changed = false;
+      NotchEpoch e = sh.epochs.back();
+      for (int sl = 0; sl < kNotchMaxSlots; ++sl) e.reset[sl] = 0;
+      for (int sl = 0; sl < c.anf; ++sl) {
+        const int nb = bins[k * c.anf + sl];
+        if (nb != cur[sl]) {
+          changed = true; cur[sl] = nb; e.bin[sl] = nb; e.reset[sl] = 1;
+          int rc = notch_table_for_bin(h, nb, &e.table_index[sl]);
+          if (rc) return rc;
+        }
+      }
+      if (changed) { e.first_block = dblocks[k]; if (e.first_block == 0) sh.epochs[0] = e; else sh.epochs.push_back(e); }
+    }
+  }
+  sh.desc = *s;
+  sh.det_valid = true;
+  return LDVB_OK;
+}
+
+// The speculative stages on [halo | chunk].  exact_notch != nullptr: the notch of the first
+// owned block starts from that (imported) state instead of a warm-up.
+int shard_run_front(ldvb_handle *h, const NotchState *exact_notch) {
+  const ldvb_config &c = h->cfg;
+  ldvb_handle::Shard &sh = h->shard;
+  const ldvb_shard &s = sh.desc;
+  int rc;
+  const uint64_t total = s.n_halo + s.n_chunk, D = (uint64_t)h->decim, cs = (uint64_t)kRxChunk * D;
+  const uint64_t R0l = sh.R0 - s.abs_raw0;   // local raw index where the front end starts
+  RawSrc src;
+  src.head = s.iq_dev; src.head_count = total; src.main = nullptr; src.c0 = 0;
+  Stream *ss[] = {&h->s_raw, &h->s_notched, &h->s_pp};
+  for (Stream *q : ss) { q->count = 0; q->fresh = 0; }
+  {
+    WallTimer wt(h, "wall:front");
+    if (c.anf) {
+      CK(cudaMemcpyAsync(h->d_notch_epochs.p, sh.epochs.data(), sh.epochs.size() * sizeof(NotchEpoch), cudaMemcpyHostToDevice, h->st));
+      NotchState st_in;
+      memset(&st_in, 0, sizeof st_in);
+      st_in.gain = 1;
+      if (exact_notch) st_in = *exact_notch;
+      else if (sh.first) st_in = h->notch;
+      CK(cudaMemcpyAsync(h->d_notch_state.p, &st_in, sizeof st_in, cudaMemcpyHostToDevice, h->st));
+      NotchApplyArgs &a = sh.na;
+      a.src = src; a.fmt = c.input_format; a.scale = c.float_scale;
+      a.out = reinterpret_cast<float2 *>(h->s_notched.at(0));
+      a.nblocks = total / kNotchN; a.nslots = c.anf;
+      a.block0 = sh.notch_b0 - s.abs_raw0 / kNotchN;
+      a.first_exact = (sh.first || exact_notch) ? 1 : 0;
+      a.k = 0.002f; a.gain = 1.0f;
+      a.expj_tables = h->d_notch_tables.as<float2>();
+      a.epochs = h->d_notch_epochs.as<NotchEpoch>();
+      a.nepochs = (int)sh.epochs.size();
+      a.seg_blocks = 1; a.warm_blocks = 2;
+      a.nsegs = (uint32_t)(a.nblocks - a.block0);
+      a.state_in = h->d_notch_state.as<NotchState>();
+      a.seg_entry = h->d_notch_entry.as<float2>();
+      a.seg_exit = h->d_notch_exit.as<float2>();
+      a.seg_exact = h->d_notch_exact.as<uint8_t>();
+      KL("notch_guess", launch_notch_guess(a, h->d_notch_guess.as<float2>(), h->d_notch_weights.as<float>(), h->st));
+      KL("notch_apply", launch_notch_apply(a, nullptr, 0, h->d_notch_guess.as<float2>(), h->st));
+      std::vector<float2> exitv;
+      if ((rc = notch_verify_repair(h, a, exitv))) return rc;
+    }
+    // front end (rotator + FIR + decimation) from R0
+    const bool need_fe = !c.anf || h->use_fir || h->use_decim || h->use_rot;
+    if (need_fe) {
+      RawSrc fsrc;
+      int fmt = c.input_format;
+      if (c.anf) { fsrc.head = h->s_notched.at(R0l); fmt = 5; }
+      else fsrc.head = static_cast<const uint8_t *>(s.iq_dev) + R0l * h->s_raw.elem;
+      fsrc.head_count = total - R0l; fsrc.main = nullptr; fsrc.c0 = 0;
+      h->rot_index = (uint32_t)(sh.R0 & 0xffffu);
+      uint64_t used = 0;
+      if ((rc = run_frontend(h, fsrc, fmt, total - R0l, &used))) return rc;
+      sh.pp = reinterpret_cast<const float2 *>(h->s_pp.at(0));
+      h->s_pp.count = 0;
+    } else {
+      sh.pp = reinterpret_cast<const float2 *>(h->s_notched.at(R0l));
+    }
+  }
+  WallTimer wt(h, "wall:rx");
+  RxArgs &a = sh.a;
+  memset(&a, 0, sizeof a);
+  a.p = h->rxp;
+  a.p.cstln = h->d_cstln.as<CstlnCellDev>();
+  a.p.trig = h->d_trig.as<float2>();
+  a.x = sh.pp;
+  a.chunk0 = sh.own_begin - sh.base_chunk;
+  a.nchunks = sh.own_end - sh.base_chunk;
+  a.avail_chunks = sh.avail_end - sh.base_chunk;
+  a.first_exact = sh.first ? 1 : 0;
+  a.prev_end = nullptr;
+  RxState st0 = h->rx_state;   // loop state the warm-ups start from: this handle's latest
+  st0.meas_count = (uint32_t)((sh.base_chunk * (uint64_t)kRxChunk) % h->rxp.meas_decimation);
+  CK(cudaMemcpyAsync(h->d_rx_state.p, &st0, sizeof st0, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemsetAsync(h->d_rx_measn.p, 0, 4, h->st));
+  a.state_in = h->d_rx_state.as<RxState>();
+  a.warm_in = a.state_in;
+  a.info = h->d_rx_info.as<RxSpanInfo>();
+  a.state_end = h->d_rx_end.as<RxState>();
+  a.meas = nullptr; a.meas_count = nullptr; a.max_meas = 0;
+  if ((rc = rx_fast_launch(h, a, sh.sa, sh.own_end - sh.own_begin))) return rc;
+  // Cold start (carrier offset): most warm-ups fail; pull the loops in before the back stage.
+  if (a.nspans > 8) {
+    KL("rx_plan", launch_rx_plan(a.info, sh.sa.seams, a.nspans, a.span_cap, h->cst.nrotations, 0, 0,
+                                 h->d_rx_off.as<uint64_t>(), h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(),
+                                 h->d_counts.as<uint64_t>(), h->st));
+    uint64_t plan[4];
+    CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (plan[0] > std::max<uint32_t>(4, a.nspans / 32)) {
+      std::vector<RxSeam> seams; std::vector<RxSpanInfo> info;
+      if ((rc = rx_fetch(h, a, sh.sa, seams, info))) return rc;
+      if ((rc = rx_fast_reseed(h, a, sh.sa, seams, info))) return rc;
+    }
+  }
+  (void)cs;
+  return LDVB_OK;
+}
+
+int shard_front(ldvb_handle *h, const ldvb_shard *s) {
+  int rc;
+  ldvb_handle::Shard &sh = h->shard;
+  const bool same = sh.det_valid && sh.desc.iq_dev == s->iq_dev && sh.desc.abs_raw0 == s->abs_raw0 &&
+                    sh.desc.n_halo == s->n_halo && sh.desc.n_chunk == s->n_chunk && sh.desc.n_halo_next == s->n_halo_next &&
+                    memcmp(sh.desc.bins_before, s->bins_before, sizeof s->bins_before) == 0;
+  if (!same) { ldvb_shard tmp = *s; if ((rc = shard_detect(h, &tmp))) return rc; }
+  sh.valid = false;
+  sh.desc.last = s->last;
+  sh.first = (s->n_halo == 0);
+  if (sh.first) reset_carry(h);
+  const uint64_t cs = (uint64_t)kRxChunk * h->decim;
+  const ShardStart g = shard_start(h, s->abs_raw0, s->n_halo);
+  sh.R0 = g.R0; sh.own_begin = g.own_begin; sh.notch_b0 = g.notch_b0;
+  sh.base_chunk = sh.R0 / cs;
+  sh.avail_end = shard_chunks_avail(h, s->abs_raw0 + s->n_halo + s->n_chunk);
+  sh.own_end = s->last ? sh.avail_end : sh.avail_end - kRxVerifyChunks;
+  if (sh.R0 < s->abs_raw0 + (h->cfg.anf && !sh.first ? kNotchLead : 0)) return fail(h, LDVB_EINVAL, "halo too short");
+  if (sh.own_end < sh.own_begin + 8) return fail(h, LDVB_EINVAL, "chunk too small");
+  if ((rc = shard_run_front(h, nullptr))) return rc;
+  sh.valid = true;
+  return LDVB_OK;
+}
+
+int shard_back(ldvb_handle *h, const EdgeBlob *in, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_out, EdgeBlob *out) {
+  const ldvb_config &c = h->cfg;
+  ldvb_handle::Shard &sh = h->shard;
+  const ldvb_shard &s = sh.desc;
+  *ts_out = 0;
+  if (!sh.valid) return fail(h, LDVB_ESTATE, "ldvb_shard_back without ldvb_shard_front");
+  if (!in != sh.first) return fail(h, LDVB_ESTATE, "an EDGE is needed for every chunk except the first");
+  int rc;
+  if (!h->d_edge_tail.p) {
+    CK(h->d_edge_tail.alloc(sizeof(RxSeamSym) * kRxSeamLog));
+    CK(h->d_edge_state.alloc(sizeof(RxState)));
+    CK(h->d_edge_seam.alloc(sizeof(RxSeam)));
+  }
+  for (Tap &t : h->taps) t.bytes = 0;
+  h->s_bytes.fresh = 0;
+  h->meas.samples_in += s.n_chunk;
+  RxArgs &a = sh.a;
+  int rot0 = 0; uint32_t skip0 = 0;
+  Stream &sym = h->s_sym;
+  WallTimer *wt = new WallTimer(h, "wall:rx");
+  struct WtGuard { WallTimer *&p; ~WtGuard() { delete p; } } wt_guard{wt};
+  if (in) {
+    if (in->magic != kEdgeMagic || in->size != sizeof(EdgeBlob)) return fail(h, LDVB_EINVAL, "bad EDGE blob");
+    if (in->abs_raw_end != s.abs_raw0 + s.n_halo || in->own_end_chunk != sh.own_begin)
+      return fail(h, LDVB_ESTATE, "EDGE does not belong in front of this chunk");
+    if (in->n_sym > kEdgeSym || in->n_bytes > kEdgeBytes || in->n_mpeg > kEdgeMpeg) return fail(h, LDVB_EINVAL, "bad EDGE blob");
+    // ---- serial state of the stages behind the receiver
+    for (int i = 0; i < 4; ++i) h->hyp[i] = in->hyp[i];
+    h->locked = in->locked; h->skip = in->skip; h->sync = in->sync; h->derand_pos = in->derand_pos;
+    h->meas.lock = in->lock;
+    sym.count = in->n_sym; h->s_bytes.count = in->n_bytes; h->s_mpeg.count = in->n_mpeg;
+    if (in->n_sym) CK(cudaMemcpyAsync(sym.at(0), in->sym, in->n_sym * 4, cudaMemcpyHostToDevice, h->st));
+    if (in->n_bytes) CK(cudaMemcpyAsync(h->s_bytes.at(0), in->bytes, in->n_bytes, cudaMemcpyHostToDevice, h->st));
+    if (in->n_mpeg) CK(cudaMemcpyAsync(h->s_mpeg.at(0), in->mpeg, in->n_mpeg, cudaMemcpyHostToDevice, h->st));
+    if (c.viterbi) {
+      if (in->n_vit != h->vsyncs.nsyncs) return fail(h, LDVB_EINVAL, "EDGE: Viterbi state of another configuration");
+      CK(cudaMemcpyAsync(h->d_vit_state.p, in->vit, sizeof(VitDecState) * in->n_vit, cudaMemcpyHostToDevice, h->st));
+      CK(cudaMemcpyAsync(h->d_vit_ctl.p, &in->vit_ctl, sizeof(VitCtl), cudaMemcpyHostToDevice, h->st));
+    }
+    // ---- notch seam: did the warm-up merge with the previous chunk's trajectory?
+    if (c.anf) {
+      float2 entry[kNotchMaxSlots];
+      CK(cudaMemcpyAsync(entry, sh.na.seg_entry, sizeof entry, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      bool same = in->notch_block == sh.notch_b0;
+      for (int sl = 0; sl < c.anf; ++sl)
+        same = same && memcmp(&entry[sl].x, &in->notch.slot[sl].est_re, 4) == 0 && memcmp(&entry[sl].y, &in->notch.slot[sl].est_im, 4) == 0;
+      if (!same) {
+        if (in->notch_block != sh.notch_b0) return fail(h, LDVB_ESTATE, "EDGE: notch state of another block");
+        ++h->meas.notch_repaired;
+        NotchState st = in->notch;
+        st.gain = 1;
+        if ((rc = shard_run_front(h, &st))) return rc;   // everything downstream of the notch again
+      }
+    }
+    // ---- receiver seam
+    RxSeam seam;
+    memset(&seam, 0, sizeof seam);
+    if (in->have_tail) {
+      CK(cudaMemcpyAsync(h->d_edge_tail.p, in->tail_log, sizeof in->tail_log, cudaMemcpyHostToDevice, h->st));
+      KL("rx_stitch", launch_rx_stitch_pair(sh.sa, h->d_edge_tail.as<RxSeamSym>(), in->n_tail, h->d_edge_seam.as<RxSeam>(), h->st));
+      CK(cudaMemcpyAsync(&seam, h->d_edge_seam.p, sizeof seam, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+    }
+    ++h->meas.seams_total;
+    if (!seam.ok) {
+      // Span 0 again, exactly, from the loop state the previous chunk ended with (already
+      // in the reference frame), then the seam behind it.
+      ++h->meas.seams_repaired;
+      CK(cudaMemcpyAsync(h->d_edge_state.p, &in->rx_end, sizeof(RxState), cudaMemcpyHostToDevice, h->st));
+      a.prev_end = h->d_edge_state.as<RxState>();
+      const uint32_t zero = 0;
+      CK(cudaMemcpyAsync(h->d_scratch.p, &zero, 4, cudaMemcpyHostToDevice, h->st));
+      KL("rx", launch_rx(a, h->d_scratch.as<uint32_t>(), 1, h->st));
+      if (a.nspans > 1) KL("rx_stitch", launch_rx_stitch(sh.sa, h->d_scratch.as<uint32_t>(), 1, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      rot0 = 0; skip0 = 0;
+    } else {
+      rot0 = (in->cum_rot + seam.rot) % h->cst.nrotations;
+      skip0 = (uint32_t)seam.skip_next;
+      if (seam.extend_prev) {
+        CK(cudaMemcpyAsync(sym.at(sym.count), &in->tail_first_word, 4, cudaMemcpyHostToDevice, h->st));
+        ++sym.count;
+      }
+    }
+  } else {
+    sym.count = 0; h->s_bytes.count = 0; h->s_mpeg.count = 0;
+  }
+  uint64_t produced = 0;
+  int cum = 0;
+  if ((rc = rx_fast_resolve(h, a, sh.sa, rot0, skip0, reinterpret_cast<uint32_t *>(sym.at(sym.count)), sym.cap - sym.count,
+                            &produced, &cum))) return rc;
+  sym.count += produced; sym.fresh = produced;
+  h->meas.symbols += produced;
+  h->meas.freq_tap = h->rx_state.freq_tap;
+  h->meas.ss = sqrtf(h->rx_state.est_insp);
+  h->meas.mer = h->rx_state.est_ep ? 10 * logf(h->rx_state.est_sp / h->rx_state.est_ep) / logf(10) : 0;
+  delete wt; wt = nullptr;
+  if ((rc = run_backend(h, ts_dst, ts_cap, ts_out))) return rc;
+  h->meas.kernel_launches = h->launches;
+  sh.valid = false; sh.det_valid = false;
+  if (!out) return LDVB_OK;
+
+  // ---- this chunk's EDGE
+  EdgeBlob &e = *out;
+  memset(static_cast<void *>(&e), 0, sizeof e);
+  e.magic = kEdgeMagic; e.size = sizeof(EdgeBlob);
+  e.abs_raw_end = s.abs_raw0 + s.n_halo + s.n_chunk;
+  e.own_end_chunk = sh.own_end;
+  e.rx_end = h->rx_state;
+  e.cum_rot = cum;
+  const uint32_t lastsp = a.nspans - 1;
+  if (!s.last) {
+    RxSpanInfo inf;
+    CK(cudaMemcpyAsync(&inf, a.info + lastsp, sizeof inf, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(e.tail_log, a.tail_log + (size_t)lastsp * kRxSeamLog, sizeof e.tail_log, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    e.have_tail = 1;
+    e.n_tail = inf.n_tail;
+    if (inf.n_tail && inf.n_out < a.span_cap) {
+      uint32_t w = 0;
+      CK(cudaMemcpy(&w, a.sym_out + (size_t)lastsp * a.span_cap + inf.n_out, 4, cudaMemcpyDeviceToHost));
+      if (cum) w = (w & 0xffffu) | ((uint32_t)h->cst.rot[cum][(w >> 16) & 0xffu] << 16);
+      e.tail_first_word = w;
+    }
+  }
+  if (c.anf && !s.last) {
+    const ShardStart nx = shard_start(h, e.abs_raw_end - s.n_halo_next, s.n_halo_next);
+    e.notch_block = nx.notch_b0;
+    const uint64_t nbl = nx.notch_b0 - s.abs_raw0 / kNotchN;   // local block
+    if (nbl <= sh.na.block0 || nbl > sh.na.nblocks) return fail(h, LDVB_ESTATE, "next chunk's notch start outside this chunk");
+    float2 ex[kNotchMaxSlots];
+    CK(cudaMemcpy(ex, sh.na.seg_exit + (size_t)(nbl - sh.na.block0 - 1) * kNotchMaxSlots, sizeof ex, cudaMemcpyDeviceToHost));
+    e.notch.gain = 1;
+    for (int sl = 0; sl < kNotchMaxSlots; ++sl) { e.notch.slot[sl].bin = -1; e.notch.slot[sl].est_re = ex[sl].x; e.notch.slot[sl].est_im = ex[sl].y; }
+    for (const NotchEpoch &ep : sh.epochs)
+      if (ep.first_block < nbl) for (int sl = 0; sl < c.anf; ++sl) e.notch.slot[sl].bin = ep.bin[sl];
+  }
+  for (int i = 0; i < 4; ++i) e.hyp[i] = h->hyp[i];
+  e.locked = h->locked; e.skip = h->skip; e.sync = h->sync; e.derand_pos = h->derand_pos; e.lock = h->meas.lock;
+  if (sym.count > kEdgeSym || h->s_bytes.count > kEdgeBytes || h->s_mpeg.count > kEdgeMpeg)
+    return fail(h, LDVB_EOVERFLOW, "unread stream remainders do not fit the EDGE");
+  e.n_sym = (uint32_t)sym.count; e.n_bytes = (uint32_t)h->s_bytes.count; e.n_mpeg = (uint32_t)h->s_mpeg.count;
+  if (e.n_sym) CK(cudaMemcpyAsync(e.sym, sym.at(0), e.n_sym * 4, cudaMemcpyDeviceToHost, h->st));
+  if (e.n_bytes) CK(cudaMemcpyAsync(e.bytes, h->s_bytes.at(0), e.n_bytes, cudaMemcpyDeviceToHost, h->st));
+  if (e.n_mpeg) CK(cudaMemcpyAsync(e.mpeg, h->s_mpeg.at(0), e.n_mpeg, cudaMemcpyDeviceToHost, h->st));
+  if (c.viterbi) {
+    e.n_vit = h->vsyncs.nsyncs;
+    if (e.n_vit > (int)kEdgeVit) return fail(h, LDVB_EOVERFLOW, "too many Viterbi hypotheses for the EDGE");
+    CK(cudaMemcpyAsync(e.vit, h->d_vit_state.p, sizeof(VitDecState) * e.n_vit, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&e.vit_ctl, h->d_vit_ctl.p, sizeof(VitCtl), cudaMemcpyDeviceToHost, h->st));
+  }
+  CK(cudaStreamSynchronize(h->st));
+  return LDVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1725,6 +2166,34 @@ int ldvb_set_state(ldvb_handle *h, const void *blob, size_t size) {
   for (int i = 0; i < 4; ++i) h->hyp[i] = b.hyp[i];
   h->locked = b.locked; h->skip = b.skip; h->sync = b.sync; h->derand_pos = b.derand_pos;
   return LDVB_OK;
+}
+
+// -------------------------------------------------------------- time sharding
+
+size_t ldvb_edge_size(void) { return sizeof(EdgeBlob); }
+
+size_t ldvb_shard_min_halo(const ldvb_handle *h) { return h ? (size_t)shard_min_halo(h) : 0; }
+
+int ldvb_shard_detect(ldvb_handle *h, ldvb_shard *s) {
+  int rc = shard_check(h, s);
+  if (rc) return rc;
+  return shard_detect(h, s);
+}
+
+int ldvb_shard_front(ldvb_handle *h, const ldvb_shard *s) {
+  int rc = shard_check(h, s);
+  if (rc) return rc;
+  return shard_front(h, s);
+}
+
+int ldvb_shard_back(ldvb_handle *h, const void *edge_in, uint8_t *ts_dev, size_t cap_packets, size_t *n_packets,
+                    void *edge_out) {
+  if (!h || !ts_dev || !n_packets) return LDVB_EINVAL;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  uint64_t got = 0;
+  int rc = shard_back(h, static_cast<const EdgeBlob *>(edge_in), ts_dev, cap_packets, &got, static_cast<EdgeBlob *>(edge_out));
+  *n_packets = (size_t)got;
+  return rc;
 }
 
 // ------------------------------------------------------------ stand-alone stages
