@@ -44,6 +44,13 @@ def run_sharded(P, raw, n_chunks, n_engines, halo_units=None, **kw):
     return np.concatenate(out), meas, chunks
 
 
+def _tail(raw, chunks):
+    """Packets that may be missing at the end: the samples that plan_stream() leaves out
+    (less than one alignment unit per chunk), at ~1958 samples per packet and more, + 2."""
+    unused = raw.size // 2 - (chunks[-1].start + chunks[-1].n_chunk)
+    return 2 + -(-unused // 1900)
+
+
 def check_ts(got, want, lost_tail=2):
     n = min(len(got), len(want))
     assert n > 0.9 * len(want)
@@ -67,7 +74,7 @@ def test_time_sharded_ts_bit_exact(product, oracle, name, kw, gkw, npk, nch, nen
     raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
     want = O.Chain(O.Config(**kw)).run(raw)["ts"]
     got, meas, chunks = run_sharded(P, raw, nch, neng, **kw)
-    check_ts(got, want, lost_tail=2 + (chunks[0].n_chunk * nch < raw.size // 2 - 1958))
+    check_ts(got, want, lost_tail=_tail(raw, chunks))
     assert sum(m["seams_total"] for m in meas) > nch
 
 
@@ -78,8 +85,8 @@ def test_time_sharded_cold_start_with_carrier_offset(product, oracle):
     raw = _freq_shift(V.ref_iq(2400, fmt="f32"), 1.5e-3)
     kw = dict(fmt="f32", resample=True)
     want = O.Chain(O.Config(**kw)).run(raw)["ts"]
-    got, meas, _ = run_sharded(P, raw, 3, 3, **kw)
-    check_ts(got, want, lost_tail=3)
+    got, meas, chunks = run_sharded(P, raw, 3, 3, **kw)
+    check_ts(got, want, lost_tail=_tail(raw, chunks))
 
 
 def test_time_sharded_seam_repair_path(product, oracle):
@@ -89,8 +96,8 @@ def test_time_sharded_seam_repair_path(product, oracle):
     raw = V.ref_iq(1600, fmt="f32", noise_db=22)
     kw = dict(fmt="f32", resample=True)
     want = O.Chain(O.Config(**kw)).run(raw)["ts"]
-    got, meas, _ = run_sharded(P, raw, 4, 2, warmup_chunks=1, span_chunks=4, **kw)
-    check_ts(got, want, lost_tail=3)
+    got, meas, chunks = run_sharded(P, raw, 4, 2, warmup_chunks=1, span_chunks=4, **kw)
+    check_ts(got, want, lost_tail=_tail(raw, chunks))
     assert sum(m["seams_repaired"] for m in meas) > 0
 
 
