@@ -110,6 +110,152 @@ def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int):
     return replicas * n / best / 1e6, ts
 
 
+def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
+    """N > 1: one stream of N * C samples, chunk k on rank k.  Per step the
+    whole stream is demodulated once from the reset state: halo exchange, notch-bin chain,
+    speculative front stages on all ranks concurrently, EDGE chain through the back stages."""
+    from leansdr_b200 import shard as S
+    from tests import vectors as V
+    dev = torch.device("cuda", local)
+    unit = 4096
+    C = int(a.packets * 1958.4) // unit * unit
+    rx = P.Receiver(fmt="f32", resample=True, anf=a.anf, rx_mode=P.RX_FAST, max_batch=C + (1 << 17), device=local)
+    stream = torch.cuda.current_stream()
+    rx.set_stream(stream.cuda_stream)
+    H = -(-rx.shard_min_halo() // unit) * unit
+    chunks = S.plan_stream(world * C, world, unit, H)
+    ch = chunks[rank]
+    raw = V.ref_iq_slice(ch.abs_raw0, ch.n_halo + ch.n_chunk)
+    buf = torch.from_numpy(raw).to(dev)                      # [halo | chunk], interleaved I/Q floats
+    own_halo = buf[: 2 * ch.n_halo].clone()
+    buf[: 2 * ch.n_halo].zero_()                             # the halo only ever arrives over NCCL
+    cap = C // 1900 + 64
+    ts_dev = torch.empty(cap * 188, dtype=torch.uint8, device=dev)
+    engine = S.GpuEngine(rx, ts_dev.data_ptr(), cap)
+    ring = S.Ring(dist, dev)
+    halo_send = buf[buf.numel() - 2 * ch.n_halo_next:] if ch.n_halo_next else None
+    halo_recv = buf[: 2 * ch.n_halo] if ch.n_halo else None
+    tl = {}
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(timeline=None):
+        return S.run_round(engine, ring, ch, buf.data_ptr(), halo_send, halo_recv, timeline)
+
+    for _ in range(W):
+        npk = step()
+    ring.flush()
+    torch.cuda.synchronize()
+    halo_ok = bool(torch.equal(buf[: 2 * ch.n_halo], own_halo))
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    rx.profile(True)
+    l0 = rx.meas()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        npk = step(tl)
+    ring.flush()
+    e1.record(stream)
+    barrier()
+    ms = max(e0.elapsed_time(e1), 0.0)
+    ms_host = (time.perf_counter() - t0) * 1e3
+    prof = rx.get_profile()
+    rx.profile(False)
+    meas = rx.meas()
+    launches = meas["kernel_launches"] - l0
+    ts_gpu = ts_dev[: npk * 188].cpu().numpy().reshape(-1, 188)
+
+    # ---- e2e: the chunk comes from pinned host memory every step, the TS goes back to the host
+    pinned = torch.from_numpy(raw[2 * ch.n_halo:]).pin_memory()
+    ts_host = torch.empty(cap * 188, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        buf[2 * ch.n_halo:].copy_(pinned, non_blocking=True)
+        k = step()
+        ts_host[: k * 188].copy_(ts_dev[: k * 188], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return k
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        k = e2e_step()
+    ring.flush()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.summary()
+
+    # ---- correctness: decoded packets are the transmitted numbered packets, contiguous over ranks
+    ctr = (ts_gpu[:, 1].astype(np.int64) << 16) | (ts_gpu[:, 2].astype(np.int64) << 8) | ts_gpu[:, 3]
+    i0 = 3 if rank == 0 else 0                     # the stream opens with the interleaver's fill
+    ok = len(ts_gpu) > i0 + 8 and np.array_equal(ts_gpu[i0:], V.ts_packets(len(ts_gpu) - i0, int(ctr[i0])))
+    mine = torch.tensor([float(ms), float(e2e_ms), float(ms_host), float(ctr[i0]) if len(ctr) > i0 else -1.0,
+                         float(ctr[-1]) if len(ctr) else -1.0, float(ok), float(len(ts_gpu)), float(launches), float(halo_ok),
+                         tl.get("early", 0.0), tl.get("front", 0.0), tl.get("wait_edge", 0.0), tl.get("back", 0.0),
+                         float(meas["seams_repaired"]), float(meas["notch_repaired"])],
+                        dtype=torch.float64, device=dev)
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    if rank != 0:
+        return
+    allv = torch.stack(allv).cpu().numpy()
+    ms = float(allv[:, 0].max()); e2e_ms = float(allv[:, 1].max())
+    total = C * world * a.steps
+    value = total / (ms * 1e-3) / 1e6
+    e2e_value = total / (e2e_ms * 1e-3) / 1e6
+    contiguous = all(allv[k, 3] == allv[k - 1, 4] + 1 for k in range(1, world))
+    ts_ok = bool(allv[:, 5].all() and contiguous and allv[:, 8].all())
+    peaks, peak_kind = measured_peaks()
+    wall = {k[5:]: v["ms_total"] / a.steps for k, v in prof.items() if k.startswith("wall:")}
+    prof = {k: v for k, v in prof.items() if not k.startswith("wall:")}
+    kern = {k: v["ms_total"] / max(v["launches"], 1) for k, v in prof.items()}
+    per_step = {k: v["ms_total"] / a.steps for k, v in prof.items()}
+    nloc = ch.n_halo + ch.n_chunk
+    alg_bytes = {"frontend": nloc * 16, "notch_apply": nloc * 16, "rx": nloc * 8 + int(nloc / 1.2) * 4}
+    dom = max(per_step, key=per_step.get)
+    ab = alg_bytes.get(dom, nloc * 8)
+    ach = ab / (kern[dom] * 1e-3) / 1e9
+    roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind, "ms_per_launch": kern[dom],
+            "algorithmic_bytes_per_launch": ab, "share_of_step": per_step[dom] / (ms / a.steps), "rank": 0}
+    fir = None
+    if "frontend" in kern:
+        achf = alg_bytes["frontend"] / (kern["frontend"] * 1e-3) / 1e9
+        fir = {"kernel": "frontend(FIR)", "achieved": achf, "frac": achf / peaks["hbm_gbs"], "unit": "GB/s",
+               "ms_per_launch": kern["frontend"]}
+    line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {**workload, "samples_per_step_per_gpu": C, "stream_samples_per_step": C * world, "rx_mode": "fast",
+                       "l2": "per-GPU chunk (%d MB) larger than L2, re-read every step" % (C * 8 >> 20),
+                       "parallelism": "ONE stream time-sharded over %d GPUs: chunk k on GPU k; per step and boundary one NCCL "
+                                      "send/recv of %d halo samples (%d KB), 16 B of notch bins and a %d-byte EDGE (carry state); "
+                                      "front stages concurrent, back stages chained" % (world, H, H * 8 >> 10, engine.edge_size)},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": int(C * 8 * world),
+                    "d2h_bytes_per_step": int(allv[:, 6].sum() * 188), "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": int(allv[:, 7].sum()),
+            "roofline": roof, "roofline_fir": fir,
+            "kernel_ms_per_step": per_step, "stage_wall_ms_per_step": wall,
+            "cpu_baseline": None,
+            "ts_packets_per_step": int(allv[:, 6].sum()),
+            "ts_bit_exact_vs_reference": None,
+            "ts_equals_transmitted_packets_contiguous_over_ranks": ts_ok,
+            "halo_received_equals_own_generation": bool(allv[:, 8].all()),
+            "shard_timeline_ms_per_step": [{"rank": k, "early": allv[k, 9] / a.steps, "front": allv[k, 10] / a.steps,
+                                            "wait_edge": allv[k, 11] / a.steps, "back": allv[k, 12] / a.steps,
+                                            "device_ms": allv[k, 0] / a.steps} for k in range(world)],
+            "seams": {"repaired": int(allv[:, 13].sum()), "notch_repaired": int(allv[:, 14].sum())}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -120,6 +266,9 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", default="time", choices=["time", "streams"],
+                    help="N > 1: 'time' = ONE stream cut into N time chunks (halo + EDGE over NCCL), "
+                         "'streams' = N independent streams (replicas)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -167,6 +316,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    if world > 1 and a.shard == "time":
+        return bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P)
 
     raw = gen_vector(a.packets)
     n = raw.size // 2

@@ -137,14 +137,16 @@ class Ring:
         return t.cpu().numpy()
 
 
-def run_round(engine, ring: Ring, chunk: Chunk, iq_ptr: int, halo_send=None, halo_recv=None):
+def run_round(engine, ring: Ring, chunk: Chunk, iq_ptr: int, halo_send=None, halo_recv=None, timeline=None):
     """This rank's turn in the ring: `chunk` is chunk number chunk.index of the stream and
     chunk.index % ring.world == ring.rank.  halo_send: device view of this chunk's last
     n_halo_next samples; halo_recv: device view of the halo region in front of the chunk.
     Returns the number of TS packets produced."""
+    import time
     r, n = ring.rank, ring.world
     first, last = chunk.index == 0, chunk.last
     prv, nxt = (r - 1) % n, (r + 1) % n
+    t0 = time.perf_counter()
     ring.flush()
     bins = (-1, -1, -1, -1)
     if not first:
@@ -154,9 +156,16 @@ def run_round(engine, ring: Ring, chunk: Chunk, iq_ptr: int, halo_send=None, hal
     if not last:
         ring.isend_early(halo_send, nxt)
         ring.isend_early_bytes(np.asarray(after, np.int32), nxt)
+    t1 = time.perf_counter()
     engine.front()
+    t2 = time.perf_counter()
     edge_in = None if first else ring.recv_edge(engine.edge_size, prv)
+    t3 = time.perf_counter()
     npk, edge_out = engine.back(edge_in, not last)
     if not last:
         ring.send_edge(edge_out, nxt)
+    t4 = time.perf_counter()
+    if timeline is not None:   # host wall clock per phase, ms (accumulated)
+        for k, v in (("early", t1 - t0), ("front", t2 - t1), ("wait_edge", t3 - t2), ("back", t4 - t3)):
+            timeline[k] = timeline.get(k, 0.0) + v * 1e3
     return npk
