@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libleandvb_b200.so")
+LIB_PATH = os.environ.get("LDVB_LIB") or os.path.join(_HERE, "libleandvb_b200.so")   # LDVB_LIB: experiment builds only
 
 ABI_VERSION = 1
 FMT = {"u8": 0, "s8": 1, "u16": 2, "s16": 3, "f32": 4}

@@ -80,6 +80,11 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+// Same, allocating in L1 (.ca): the two 16-byte halves of a 32-byte sector then cost one L2
+// request instead of two (the second one merges with the outstanding miss).
+__device__ __forceinline__ void cp_async16_ca(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -88,5 +93,6 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // Streaming stores: results are written once and read by a later kernel.
 __device__ __forceinline__ void st_stream(float2 *p, float2 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
 
 }  // namespace ldvb

@@ -19,6 +19,8 @@
 //   exit; the host checks entry(j+1) == exit(j) bit for bit and re-runs the rare
 //   segment whose warm-up had not merged (exact by induction over segments).
 #include "common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace ldvb {
@@ -138,7 +140,6 @@ k_notch_detect(NotchDetectArgs a) {
 // run that follows merges with the true trajectory inside the one warm-up block
 // (measured: median 1000 samples, max < 3000).  Every segment is
 // still verified against its predecessor and re-run when it did not merge.
-constexpr int kGuessWindow = 8192;
 
 template <int FMT>
 __device__ __forceinline__ float2 ld_raw(const RawSrc &src, uint64_t idx, float scale) {
@@ -187,51 +188,75 @@ __device__ __forceinline__ SegPlan plan_segment(const NotchApplyArgs &a, uint32_
   return p;
 }
 
+// Block sums: S_b = sum over the samples i of block b of bb[i]*k*(1-k)^(4095-i), i.e. what
+// block b alone contributes to the estimate at its end.  One CTA per block, every sample of
+// the stream is read once (coalesced); the start state of a segment is then assembled from
+// the two block sums in front of its warm-up (guess_from_sums).
 template <int FMT>
 __global__ void __launch_bounds__(128)
-k_notch_guess(NotchApplyArgs a, float2 *guess /* [nsegs][kNotchMaxSlots] */, const float *weights) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (seg >= a.nsegs) return;
-  const SegPlan p = plan_segment(a, seg);
-  if (p.start_kind != 2) return;
-  const int ep = p.epoch;
-  const uint64_t P = p.run_begin * (uint64_t)kNotchN;            // state wanted after sample P-1
-  const uint64_t floor_s = a.epochs[ep].first_block * (uint64_t)kNotchN;  // history starts here
-  uint64_t M = P - floor_s;
-  const bool reaches_floor = M <= (uint64_t)kGuessWindow;
-  if (!reaches_floor) M = kGuessWindow;
-  for (int s = 0; s < a.nslots; ++s) {
-    const float2 *tab = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN;
-    float accr = 0.f, acci = 0.f;
-    for (uint64_t m = 1 + lane; m <= M; m += 32) {
-      const uint64_t idx = P - m;
-      const float2 x = ld_raw<FMT>(a.src, idx, a.scale);
-      const float2 e = __ldg(tab + (idx & (kNotchN - 1)));
-      const float bbr = x.x * e.x + x.y * e.y;
-      const float bbi = -x.x * e.y + x.y * e.x;
-      const float w = __ldg(weights + (m - 1));
-      accr += bbr * a.k * w;
-      acci += bbi * a.k * w;
+k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][kNotchMaxSlots] */, const float *weights) {
+  __shared__ float2 part[4][kNotchMaxSlots];
+  const uint64_t b = first_block + blockIdx.x;
+  if (b >= a.nblocks) return;
+  int ep = 0;
+  while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= b) ++ep;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float accr[kNotchMaxSlots], acci[kNotchMaxSlots];
+  for (int s = 0; s < kNotchMaxSlots; ++s) { accr[s] = 0.f; acci[s] = 0.f; }
+  const uint64_t base = b * (uint64_t)kNotchN;
+  for (int j = 0; j < kNotchN / 128; ++j) {
+    const int i = j * 128 + tid;
+    const float2 x = ld_raw<FMT>(a.src, base + i, a.scale);
+    const float w = __ldg(weights + (kNotchN - 1 - i)) * a.k;
+    for (int s = 0; s < a.nslots; ++s) {
+      const float2 e = __ldg(a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + i);
+      accr[s] += (x.x * e.x + x.y * e.y) * w;
+      acci[s] += (-x.x * e.y + x.y * e.x) * w;
     }
-    for (int o = 16; o; o >>= 1) {
-      accr += __shfl_xor_sync(0xffffffffu, accr, o);
-      acci += __shfl_xor_sync(0xffffffffu, acci, o);
-    }
-    if (reaches_floor && !a.epochs[ep].reset[s] && ep == 0 && floor_s == 0 && a.first_exact) {
-      // history runs into the carried state of the batch
-      const float w = __ldg(weights + (M ? M - 1 : 0)) * (M ? (1.0f - a.k) : 1.0f);
-      accr += a.state_in->slot[s].est_re * w;
-      acci += a.state_in->slot[s].est_im * w;
-    }
-    if (lane == 0) guess[(size_t)seg * kNotchMaxSlots + s] = make_float2(accr, acci);
   }
+  for (int s = 0; s < a.nslots; ++s) {
+    for (int o = 16; o; o >>= 1) {
+      accr[s] += __shfl_xor_sync(0xffffffffu, accr[s], o);
+      acci[s] += __shfl_xor_sync(0xffffffffu, acci[s], o);
+    }
+    if (lane == 0) part[warp][s] = make_float2(accr[s], acci[s]);
+  }
+  __syncthreads();
+  if (tid < a.nslots) {
+    float2 t = part[0][tid];
+    for (int w = 1; w < 4; ++w) { t.x += part[w][tid].x; t.y += part[w][tid].y; }
+    sums[b * kNotchMaxSlots + tid] = t;
+  }
+}
+
+// Start state of a segment whose exact run begins at block p.run_begin (start_kind 2): the
+// estimate forgets with (1-k)^n, so the two blocks in front of it (8192 samples, weight of
+// anything older < 1e-7) decide it.  History never reaches across the start of the epoch
+// (tables change there); at the very start of the stream it runs into the carried state.
+__device__ __forceinline__ float2 guess_from_sums(const NotchApplyArgs &a, const SegPlan &p, const float2 *sums, int s) {
+  const uint64_t floor_b = a.epochs[p.epoch].first_block;
+  const uint64_t rb = p.run_begin;
+  const uint64_t nh = (rb - floor_b) < 2 ? (rb - floor_b) : 2;     // history blocks available
+  const float w4096 = a.w_block;                                     // (1-k)^4096
+  float2 g = make_float2(0.f, 0.f);
+  if (nh >= 1) g = sums[(rb - 1) * kNotchMaxSlots + s];
+  if (nh >= 2) { const float2 o = sums[(rb - 2) * kNotchMaxSlots + s]; g.x += o.x * w4096; g.y += o.y * w4096; }
+  if (nh < 2 && !a.epochs[p.epoch].reset[s] && p.epoch == 0 && floor_b == 0 && a.first_exact) {
+    const float w = nh ? w4096 : 1.0f;
+    g.x += a.state_in->slot[s].est_re * w;
+    g.y += a.state_in->slot[s].est_im * w;
+  }
+  return g;
 }
 
 // One lane = one segment.  The 32 lanes of a warp walk 32 segments in lock step;
 // per tile the warp stages every lane's next 64 raw samples in a private
 // shared-memory row (cooperative 16-byte cp.async copies, contiguous within a
 // row, double buffered); lanes convert on the fly and stream their results out.
+#ifndef LDVB_NOTCH_CA
+#define LDVB_NOTCH_CA 0
+#endif
+constexpr bool kNotchCa = LDVB_NOTCH_CA != 0;
 constexpr int kNTile = 32;
 constexpr int kNPitch = 272;          // row pitch: (32 + 2) cf32, = 16 (mod 128) bytes
 constexpr int kNStages = 2;
@@ -285,7 +310,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
       for (int s = 0; s < NSLOTS; ++s) { er[s] = a.state_in->slot[s].est_re; ei[s] = a.state_in->slot[s].est_im; }
     } else if (p.start_kind == 2) {
 #pragma unroll
-      for (int s = 0; s < NSLOTS; ++s) { const float2 g = guess[(size_t)seg * kNotchMaxSlots + s]; er[s] = g.x; ei[s] = g.y; }
+      for (int s = 0; s < NSLOTS; ++s) { const float2 g = guess_from_sums(a, p, guess, s); er[s] = g.x; ei[s] = g.y; }
     }
   }
   const uint64_t own_begin = p.own_begin, own_end = p.own_end, run_begin = p.run_begin;
@@ -322,13 +347,14 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
       unsigned char *dst = smem + row_off + (size_t)st * 32 * kNPitch;
 #pragma unroll
       for (int q = 0; q < n16_max; ++q)
-        if (q < n16) cp_async16(dst + q * 16, src + q * 16);
+        if (q < n16) { if (kNotchCa) cp_async16_ca(dst + q * 16, src + q * 16); else cp_async16(dst + q * 16, src + q * 16); }
     }
     cp_async_commit();
   };
 
   const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
   const bool unit_gain = (gain == 1.0f);
+  const bool out16 = (reinterpret_cast<uintptr_t>(a.out) & 15u) == 0;   // carry in front: only 8-byte aligned
   if (total_tiles) issue(0);
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
@@ -362,13 +388,32 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
       // estimate are issued first (ILP), then the 8-step serial chain
       // estim = bb*k + estim*(1-k), then the subtraction and the stores.
       constexpr int U = 8;
-#pragma unroll 1
+      // Groups of a tile are unrolled so that the loads / products of group g+1 overlap the
+      // serial chain of group g (few warps per scheduler: ILP has to come from the lane itself).
+      constexpr int kUnroll = NSLOTS == 1 ? 4 : (NSLOTS == 2 ? 2 : 1);
+#pragma unroll kUnroll
       for (int n0 = 0; n0 < kNTile; n0 += U) {
         float2 x[U], e[U][NSLOTS];
         float bkr[U][NSLOTS], bki[U][NSLOTS];
+        if (FMT >= 4 && (lead & 1u) == 0) {
+          // cf32 rows, 16-byte aligned: two samples per shared-memory load (conflict-free at
+          // this row pitch, half the wavefronts of 8-byte loads)
+          const float4 *row4 = reinterpret_cast<const float4 *>(myrow) + ((lead + n0) >> 1);
+#pragma unroll
+          for (int j = 0; j < U; j += 2) {
+            const float4 v = row4[j >> 1];
+            x[j] = make_float2(v.x, v.y); x[j + 1] = make_float2(v.z, v.w);
+            if (FMT == 4 && a.scale != 1.0f) {
+              x[j] = make_float2(fmul(x[j].x, a.scale), fmul(x[j].y, a.scale));
+              x[j + 1] = make_float2(fmul(x[j + 1].x, a.scale), fmul(x[j + 1].y, a.scale));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < U; ++j) x[j] = row_sample<FMT>(myrow, lead + n0 + j, a.scale);
+        }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          x[j] = row_sample<FMT>(myrow, lead + n0 + j, a.scale);
 #pragma unroll
           for (int s = 0; s < NSLOTS; ++s) e[j][s] = __ldg(tab[s] + n0 + j);
         }
@@ -389,6 +434,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
             esr[j][s] = er[s]; esi[j][s] = ei[s];
           }
         if (write) {
+          float2 o[U];
 #pragma unroll
           for (int j = 0; j < U; ++j) {
             float outr = x[j].x, outi = x[j].y;
@@ -398,7 +444,15 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
               outi = fsub(outi, fadd(fmul(esr[j][s], e[j][s].y), fmul(esi[j][s], e[j][s].x)));
             }
             if (!unit_gain) { outr = fmul(gain, outr); outi = fmul(gain, outi); }
-            st_stream(outp + n0 + j, make_float2(outr, outi));
+            o[j] = make_float2(outr, outi);
+          }
+          if (out16) {   // 16-byte stores: half the store wavefronts
+#pragma unroll
+            for (int j = 0; j < U; j += 2)
+              st_stream(reinterpret_cast<float4 *>(outp + n0 + j), make_float4(o[j].x, o[j].y, o[j + 1].x, o[j + 1].y));
+          } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) st_stream(outp + n0 + j, o[j]);
           }
         }
       }
@@ -424,6 +478,14 @@ cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, ui
     cudaError_t e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kNotchSmem);
     if (e != cudaSuccess) return e;
+    // Four resident CTAs per SM cover the whole grid at the bench size; asking for no more
+    // shared memory than that leaves ~64 KB of L1 for the e^{j theta} tables (32 KB per bin),
+    // which every lane reads once per sample (ncu: 29 % L1 hit rate with the default split).
+    static const int carve = [] { const char *v = getenv("LDVB_NOTCH_CARVEOUT"); return v ? atoi(v) : 72; }();
+    if (carve >= 0 && carve <= 100) {
+      e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      if (e != cudaSuccess) return e;
+    }
     configured = true;
   }
   const unsigned per_block = kNWarps * 32;
@@ -474,16 +536,19 @@ cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const float *weights, cudaStream_t st) {
-  if (a.nsegs <= 1) return cudaSuccess;
-  const unsigned blocks = (a.nsegs + 3) / 4;
+cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *sums, const float *weights, cudaStream_t st) {
+  // Blocks whose sums can be asked for: from two blocks in front of the first warm-up on.
+  const uint64_t lead = (uint64_t)a.warm_blocks + 2;
+  const uint64_t first = a.block0 > lead ? a.block0 - lead : 0;
+  if (a.nblocks <= first) return cudaSuccess;
+  const unsigned blocks = (unsigned)(a.nblocks - first);
   switch (a.fmt) {
-    case 0: k_notch_guess<0><<<blocks, 128, 0, st>>>(a, guess, weights); break;
-    case 1: k_notch_guess<1><<<blocks, 128, 0, st>>>(a, guess, weights); break;
-    case 2: k_notch_guess<2><<<blocks, 128, 0, st>>>(a, guess, weights); break;
-    case 3: k_notch_guess<3><<<blocks, 128, 0, st>>>(a, guess, weights); break;
-    case 4: k_notch_guess<4><<<blocks, 128, 0, st>>>(a, guess, weights); break;
-    default: k_notch_guess<5><<<blocks, 128, 0, st>>>(a, guess, weights); break;
+    case 0: k_notch_guess<0><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 1: k_notch_guess<1><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 2: k_notch_guess<2><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 3: k_notch_guess<3><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 4: k_notch_guess<4><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    default: k_notch_guess<5><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
   }
   return cudaGetLastError();
 }

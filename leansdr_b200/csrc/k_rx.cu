@@ -27,20 +27,25 @@
 // through the read-only path; their accesses cluster around the current carrier
 // phase and the constellation points.
 #include "common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace ldvb {
 
 namespace {
 
-constexpr int kTile = 16;                       // samples per staged tile
+// Samples per staged tile: template parameter TILE (8 or 16) of rx_warp / k_rx.
 // Row = tile + look-ahead: 2 samples for the nearest/linear samplers (272 B), 6 for the RRC
 // sampler (304 B, up to 6 taps).  Both pitches are 16 B mod 128-friendly: any 8 consecutive
 // lanes read 16 B each from distinct banks.
-template <int SAMPLER> struct RowCfg { static constexpr int kBytes = (kTile + (SAMPLER == 2 ? 6 : 2)) * 8; };
+template <int SAMPLER, int TILE> struct RowCfg { static constexpr int kBytes = (TILE + (SAMPLER == 2 ? 6 : 2)) * 8; };
+#ifndef LDVB_RX_CA
+#define LDVB_RX_CA 0
+#endif
+constexpr bool kRxCa = LDVB_RX_CA != 0;
 constexpr int kStages = 2;
 constexpr int kWarpsPerBlock = 4;
-constexpr int kTilesPerChunk = kRxChunk / kTile;
 
 struct RxRun {
   float mu, phase, freqw, est_insp, agc_gain, est_sp, est_ep;
@@ -197,9 +202,11 @@ __device__ __forceinline__ void rx_chunk_end(const RxParams &p, RxRun &r) {
   r.freq_tap = __fdiv_rn(r.freqw, 65536.0f);  // sdr.h:917-919
 }
 
-template <int SAMPLER>
+template <int SAMPLER, int TILE>
 __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_all) {
-  constexpr int kRowBytes = RowCfg<SAMPLER>::kBytes;
+  constexpr int kTile = TILE;
+  constexpr int kTilesPerChunk = kRxChunk / kTile;
+  constexpr int kRowBytes = RowCfg<SAMPLER, TILE>::kBytes;
   const RxParams &p = a.p;
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -272,7 +279,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
       const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + (uint64_t)c * kRxChunk + (tile % kTilesPerChunk) * kTile);
       unsigned char *dst = smem_all + row_off + (size_t)st * 32 * kRowBytes;
 #pragma unroll
-      for (int q = 0; q < kChunks16; ++q) cp_async16(dst + q * 16, src + q * 16);
+      for (int q = 0; q < kChunks16; ++q) { if (kRxCa) cp_async16_ca(dst + q * 16, src + q * 16); else cp_async16(dst + q * 16, src + q * 16); }
     }
     cp_async_commit();
   };
@@ -362,12 +369,13 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   }
 }
 
+template <int TILE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
   extern __shared__ __align__(128) unsigned char smem[];
-  if (a.p.sampler == 0) rx_warp<0>(a, span_list, nlist, smem);
-  else if (a.p.sampler == 1) rx_warp<1>(a, span_list, nlist, smem);
-  else rx_warp<2>(a, span_list, nlist, smem);
+  if (a.p.sampler == 0) rx_warp<0, TILE>(a, span_list, nlist, smem);
+  else if (a.p.sampler == 1) rx_warp<1, TILE>(a, span_list, nlist, smem);
+  else rx_warp<2, TILE>(a, span_list, nlist, smem);
 }
 
 // ---------------------------------------------------------------- seam stitching
@@ -429,14 +437,13 @@ __global__ void k_rx_stitch_pair(RxStitchArgs a, const RxSeamSym *tail, uint32_t
 
 __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
   // One block row per span; threads copy with the span's rotation applied.
-  const uint32_t span = blockIdx.y;
+  const uint32_t span = blockIdx.x;
   const uint64_t base = a.span_offset[span];
   const uint64_t n = a.span_offset[span + 1] - base;
   const uint32_t *src = a.sym_in + (size_t)span * a.span_cap + a.span_skip[span];
   const uint8_t *perm = a.rot_perm + (size_t)a.span_rot[span] * a.nsymbols;
   const bool identity = (a.span_rot[span] == 0);
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
     uint32_t w = src[i];
     if (!identity) {
       uint32_t sym = (w >> 16) & 0xffu;
@@ -515,28 +522,45 @@ k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t
   }
 }
 
-constexpr size_t kRxSmemMax = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<2>::kBytes;
 
 }  // namespace
 
-cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st) {
-  if (a.nspans == 0 || (span_list && !nlist)) return cudaSuccess;
+namespace {
+template <int TILE>
+cudaError_t launch_rx_t(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, int carveout, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxSmemMax);
+    constexpr size_t smem_max = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<2, TILE>::kBytes;
+    cudaError_t e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return e;
     // Leave about half of the SM's unified cache to L1: the two 512 KB tables are read
     // through it, and their hot lines (current carrier phase, constellation clusters)
     // must stay resident -- table latency is what bounds this kernel.
-    e = cudaFuncSetAttribute(k_rx, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const unsigned per_block = kWarpsPerBlock * 32;
   const unsigned lanes = span_list ? nlist : a.nspans;
-  const size_t smem = (size_t)kWarpsPerBlock * kStages * 32 * (a.p.sampler == 2 ? RowCfg<2>::kBytes : RowCfg<1>::kBytes);
-  k_rx<<<(lanes + per_block - 1) / per_block, per_block, smem, st>>>(a, span_list, nlist);
+  const size_t smem = (size_t)kWarpsPerBlock * kStages * 32 *
+                      (a.p.sampler == 2 ? RowCfg<2, TILE>::kBytes : RowCfg<1, TILE>::kBytes);
+  k_rx<TILE><<<(lanes + per_block - 1) / per_block, per_block, smem, st>>>(a, span_list, nlist);
   return cudaGetLastError();
+}
+}  // namespace
+
+// Tuning knobs (read once): LDVB_RX_TILE = 8 | 16 samples per staged tile,
+// LDVB_RX_CARVEOUT = shared-memory share of the unified cache in percent.
+int rx_tile_config() {
+  static int tile = [] { const char *e = getenv("LDVB_RX_TILE"); int t = e ? atoi(e) : 16; return t == 8 ? 8 : 16; }();
+  return tile;
+}
+
+cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st) {
+  if (a.nspans == 0 || (span_list && !nlist)) return cudaSuccess;
+  static int carveout = [] { const char *e = getenv("LDVB_RX_CARVEOUT"); int c = e ? atoi(e) : 50; return (c < 0 || c > 100) ? 50 : c; }();
+  if (rx_tile_config() == 8) return launch_rx_t<8>(a, span_list, nlist, carveout, st);
+  return launch_rx_t<16>(a, span_list, nlist, carveout, st);
 }
 
 cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st) {
@@ -562,8 +586,7 @@ cudaError_t launch_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t
 cudaError_t launch_rx_compact(const RxCompactArgs &a, uint64_t total, cudaStream_t st) {
   if (a.nspans == 0 || total == 0) return cudaSuccess;
   // Spans are short (a few thousand symbols): one 256-thread block per span.
-  dim3 grid(1, a.nspans);
-  k_rx_compact<<<grid, 256, 0, st>>>(a, total);
+  k_rx_compact<<<a.nspans, 256, 0, st>>>(a, total);
   return cudaGetLastError();
 }
 

@@ -70,6 +70,7 @@ struct NotchApplyArgs {
   uint64_t nblocks;                // 4096-sample blocks to process
   int nslots;
   float k, gain;
+  float w_block;                   // (1-k)^4096, for the start-state guess
   const float2 *expj_tables;       // [ntables][4096]
   const NotchEpoch *epochs;        // device, sorted by first_block
   int nepochs;
@@ -83,7 +84,8 @@ struct NotchApplyArgs {
   float2 *seg_exit;                // [nsegs][slots] state at segment end
   uint8_t *seg_exact;              // [nsegs] 1 when the segment started from a known-exact state
 };
-// guess: [nsegs][kNotchMaxSlots] start states written by launch_notch_guess.
+// guess: [nblocks][kNotchMaxSlots] per-block weighted sums written by launch_notch_guess;
+// launch_notch_apply assembles the start states of speculative segments from them.
 cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *guess, const float *weights, cudaStream_t st);
 // Counts the segments whose entry state differs from their predecessor's exit state.
 cudaError_t launch_notch_verify(const NotchApplyArgs &a, uint32_t *nfail, cudaStream_t st);

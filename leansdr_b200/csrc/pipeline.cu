@@ -848,6 +848,7 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   a.nblocks = nblocks; a.nslots = c.anf;
   a.block0 = 0; a.first_exact = 1;
   a.k = 0.002f; a.gain = h->notch.gain;
+  a.w_block = (float)pow((double)(1.0f - 0.002f), (double)kNotchN);
   a.expj_tables = h->d_notch_tables.as<float2>();
   a.epochs = h->d_notch_epochs.as<NotchEpoch>();
   a.nepochs = (int)epochs.size();
@@ -931,7 +932,8 @@ int rx_fast_launch(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, uint64_t nchunks
     // least 4 chunks; 4 chunks of warm-up (timing and carrier loops re-converge
     // within ~200 symbols when freqw and the AGC are carried).
     uint32_t S = c.span_chunks;
-    if (!S) S = (uint32_t)std::max<uint64_t>(4, (nchunks + kRxTargetSpans - 1) / kRxTargetSpans);
+    static const uint64_t target = [] { const char *e = getenv("LDVB_RX_SPANS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : kRxTargetSpans; }();
+    if (!S) S = (uint32_t)std::max<uint64_t>(4, (nchunks + target - 1) / target);
     const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 4;
     a.span_chunks = S;
     a.warm_chunks = W;
@@ -1691,6 +1693,7 @@ int shard_run_front(ldvb_handle *h, const NotchState *exact_notch) {
       a.block0 = sh.notch_b0 - s.abs_raw0 / kNotchN;
       a.first_exact = (sh.first || exact_notch) ? 1 : 0;
       a.k = 0.002f; a.gain = 1.0f;
+      a.w_block = (float)pow((double)(1.0f - 0.002f), (double)kNotchN);
       a.expj_tables = h->d_notch_tables.as<float2>();
       a.epochs = h->d_notch_epochs.as<NotchEpoch>();
       a.nepochs = (int)sh.epochs.size();
