@@ -109,7 +109,11 @@ typedef struct ldvb_config {
   uint32_t span_chunks;      /* FAST: 128-sample chunks per span (0 = auto)  */
   uint32_t warmup_chunks;    /* FAST: warm-up chunks before a span (0 = auto)*/
   int32_t  keep_taps;        /* keep intermediate streams for ldvb_tap()     */
-  int32_t  reserved[7];
+  int32_t  push_sub_batch;   /* ldvb_push: samples per pipelined sub-batch (0 = 32 Mi) */
+  int32_t  cnr;              /* --cnr: cnr_fft (sdr.h:1273-1345), needs Fs > 4 Fm */
+  int32_t  spectrum;         /* spectrum (sdr.h:1347-1404); leandvb always runs it
+                                (leandvb.cc:333-343), ldvb_config_default sets 1 */
+  int32_t  reserved[4];
 } ldvb_config;
 
 typedef struct ldvb_handle ldvb_handle;
@@ -235,6 +239,14 @@ int    ldvb_set_state(ldvb_handle *h, const void *blob, size_t size);
  * (sdr.h:921-934). */
 int ldvb_get_rx_state(ldvb_handle *h, uint32_t w[22]);
 int ldvb_set_rx_state(ldvb_handle *h, const uint32_t w[22]);
+
+/* ---------------------------------------------------- CNR / spectrum telemetry
+ * What the reference writes to p_cnr (one float per second of signal, leandvb.cc:322-329)
+ * and p_spectrum (float[1024] per second, leandvb.cc:333-343), queued per batch.  The centre
+ * bin of cnr_fft follows freq_tap as sampled when the batch starts (the reference samples it
+ * whenever its scheduler happens to run the block). */
+int ldvb_pull_cnr(ldvb_handle *h, float *dst, size_t cap, size_t *n);
+int ldvb_pull_spectrum(ldvb_handle *h, float *dst, size_t cap_rows, size_t *n_rows);
 
 /* ------------------------------------------------------------ time sharding
  * one stream, N handles (one per GPU, one process each).  The

@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("allow_drift", C.c_int32), ("Ftune", C.c_float), ("Finfo", C.c_float),
         ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
         ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -68,6 +68,7 @@ EXPORTS = [
     "ldvb_table", "ldvb_host_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
     "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
     "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
+    "ldvb_pull_cnr", "ldvb_pull_spectrum",
     "ldvb_edge_size", "ldvb_shard_min_halo", "ldvb_shard_detect", "ldvb_shard_front", "ldvb_shard_back",
 ]
 
@@ -124,6 +125,8 @@ def load():
     L.ldvb_set_stream.argtypes = [vp, vp]
     L.ldvb_profile.argtypes = [vp, C.c_int]
     L.ldvb_get_profile.argtypes = [vp, C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]
+    L.ldvb_pull_cnr.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.ldvb_pull_spectrum.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.ldvb_edge_size.restype = sz
     L.ldvb_shard_min_halo.restype = sz
     L.ldvb_shard_min_halo.argtypes = [vp]
@@ -147,7 +150,7 @@ def default_config(**kw) -> Config:
         elif k == "sampler":
             cfg.sampler = SAMPLER[v] if isinstance(v, str) else v
         elif k == "sub_batch":
-            cfg.reserved[0] = int(v)
+            cfg.push_sub_batch = int(v)
         elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps"):
             setattr(cfg, k, int(v))
         else:
@@ -279,6 +282,18 @@ class Receiver:
     def set_rx_state(self, w):
         w = np.ascontiguousarray(w, np.uint32)
         self._ck(self.L.ldvb_set_rx_state(self.h, _p(w)), "ldvb_set_rx_state")
+
+    def pull_cnr(self, cap: int = 4096) -> np.ndarray:
+        """p_cnr: one C/N value (dB) per second of signal (--cnr)."""
+        out = np.zeros(cap, np.float32); n = C.c_size_t(0)
+        self._ck(self.L.ldvb_pull_cnr(self.h, _p(out), cap, C.byref(n)), "ldvb_pull_cnr")
+        return out[: n.value]
+
+    def pull_spectrum(self, cap_rows: int = 1024) -> np.ndarray:
+        """p_spectrum: float[1024] rows (dB, fft-shifted), one per second of signal."""
+        out = np.zeros((cap_rows, 1024), np.float32); n = C.c_size_t(0)
+        self._ck(self.L.ldvb_pull_spectrum(self.h, _p(out), cap_rows, C.byref(n)), "ldvb_pull_spectrum")
+        return out[: n.value]
 
     # ---- time sharding (one stream over several handles, SURVEY.md 8e)
     def edge_size(self) -> int:

@@ -94,6 +94,33 @@ cudaError_t launch_notch_verify(const NotchApplyArgs &a, uint32_t *nfail, cudaSt
 cudaError_t launch_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist,
                                const float2 *guess, cudaStream_t st);
 
+// ------------------------------------------------------- K8 cnr_fft / spectrum
+// [carry | rest]: `carry` holds cf32 samples (converted, not rotated) kept from the previous
+// batch, `rest` is the batch in its input format starting at element rest_off.
+struct MeasSrc {
+  const float2 *carry; uint64_t carry_count;
+  RawSrc rest; uint64_t rest_off; int fmt; float scale;
+  const float *rot_lut; uint32_t rot_index0;   // rotator index of element 0 (or no rotator)
+};
+struct MeasArgs {
+  MeasSrc src;
+  const uint64_t *point_start;   // [npoints] element index of each measured block
+  int npoints, logn;             // block = 2^logn samples (12: cnr_fft, 10: spectrum)
+  const float2 *twiddle_rev;     // [4096] omega_rev of the 4096-point engine
+  float *power;                  // [npoints][n]
+};
+cudaError_t launch_meas_power(const MeasArgs &a, cudaStream_t st);
+struct MeasEmaArgs {
+  const float *power; int npoints, n;
+  float kavg;
+  float *avg; int *have;         // carried average (device)
+  int bwslots, icf;              // cnr_fft band geometry (bwslots == 0: none)
+  float *sums;                   // [npoints][3] c2+n2, noise left, noise right
+  float *rows;                   // [npoints][n] average after each measurement, or null
+};
+cudaError_t launch_meas_ema(const MeasEmaArgs &a, cudaStream_t st);
+cudaError_t launch_meas_save(const MeasSrc &src, uint64_t start, uint32_t count, float2 *dst, cudaStream_t st);
+
 // ------------------------------------------------------------------ K3 receiver
 struct CstlnCellDev { int16_t cost, symbol, phase_error, pad; };
 

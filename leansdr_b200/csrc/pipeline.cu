@@ -62,6 +62,7 @@ struct Stream {
 
 struct HypState { uint64_t reg = 0, acc = 0; int n_in = 0, n_out = 0; };
 
+constexpr int kMeasGroup = 256;                 // cnr/spectrum measurements per launch
 constexpr uint64_t kRxTargetSpans = 56 * 1024;  // ~ resident lanes of k_rx on 148 SMs
 
 struct Tap {
@@ -130,6 +131,21 @@ struct ldvb_handle {
   DevBuf d_sync_state, d_sync_res;
   int derand_pos = 0;
   DevBuf d_counts;
+
+  // ---- cnr_fft / spectrum (telemetry in front of the FIR)
+  struct MeasUnit {
+    bool on = false;
+    int logn = 12;
+    float kavg = 0.1f, bandwidth = 0;
+    int64_t decimation = 1, phase = 0;
+    uint64_t pos = 0;              // absolute index of the next unread sample
+    DevBuf d_avg, d_have;
+  } m_cnr, m_spec;
+  DevBuf d_meas_carry[2], d_meas_points, d_meas_power, d_meas_sums, d_meas_rows;
+  int meas_carry_sel = 0;
+  uint64_t meas_carry_count = 0;   // samples kept from the previous batch (< 4096)
+  uint64_t meas_abs_next = 0;      // absolute index of the next new sample
+  std::vector<float> cnr_queue, spec_queue;
 
   // ---- time-sharded mode (ldvb_shard_*): what the front stage leaves for the back stage
   struct Shard {
@@ -351,6 +367,12 @@ void reset_carry(ldvb_handle *h) {
   h->derand_pos = 0;
   h->ts_queue.clear(); h->ts_queue_rd = 0;
   memset(&h->meas, 0, sizeof h->meas);
+  for (ldvb_handle::MeasUnit *u : {&h->m_cnr, &h->m_spec}) {
+    u->phase = 0; u->pos = 0;
+    if (u->d_have.p) cudaMemset(u->d_have.p, 0, 4);
+  }
+  h->meas_carry_count = 0; h->meas_abs_next = 0;
+  h->cnr_queue.clear(); h->spec_queue.clear();
 }
 
 void rx_setup(ldvb_handle *h) {
@@ -440,6 +462,7 @@ void ldvb_config_default(ldvb_config *c) {
   c->rx_mode = LDVB_RX_EXACT;
   c->device = 0;
   c->max_batch = 1u << 22;
+  c->spectrum = 1;   // leandvb.cc:333-343: always instantiated
 }
 
 int ldvb_destroy(ldvb_handle *h) {
@@ -454,7 +477,9 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
                     &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
-                    &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam};
+                    &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam,
+                    &h->m_cnr.d_avg, &h->m_cnr.d_have, &h->m_spec.d_avg, &h->m_spec.d_have, &h->d_meas_carry[0], &h->d_meas_carry[1],
+                    &h->d_meas_points, &h->d_meas_power, &h->d_meas_sums, &h->d_meas_rows};
   for (DevBuf *b : bufs) b->release();
   for (Tap &t : h->taps) t.buf.release();
   for (int i = 0; i < 2; ++i) { h->d_stage[i].release(); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
@@ -487,6 +512,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   };
   if (c.input_format < 0 || c.input_format > LDVB_FMT_F32) return bail(LDVB_EINVAL, "bad input_format");
   if (c.fastlock) return bail(LDVB_EINVAL, "--fastlock is not supported");
+  if (c.cnr && c.Fm / c.Fs > 0.25f) return bail(LDVB_EINVAL, "CNR estimator requires Fsampling > 4x Fsignal");   // sdr.h:1283-1284
   if (c.sampler < 0 || c.sampler > 2) return bail(LDVB_EINVAL, "bad sampler");
   if (c.anf < 0 || c.anf > kNotchMaxSlots) return bail(LDVB_EINVAL, "anf must be 0..4");
   if (!(c.Fs > 0) || !(c.Fm > 0) || c.max_batch == 0) return bail(LDVB_EINVAL, "bad rates or max_batch");
@@ -571,8 +597,8 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     if (upload(h->d_rrc, h->rrc_coeffs.data(), h->rrc_coeffs.size() * 4) != cudaSuccess) return bail(LDVB_ECUDA, "rrc upload");
     h->rxp.rrc_coeffs = h->d_rrc.as<float>();
   }
-  // Host batches larger than this are pipelined (copy/compute overlap); reserved[0] overrides.
-  h->sub_batch = c.reserved[0] > 0 ? (uint64_t)c.reserved[0] : (uint64_t)32 << 20;
+  // Host batches larger than this are pipelined (copy/compute overlap); push_sub_batch overrides.
+  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : (uint64_t)32 << 20;
 
   // ---- stream buffers
   const uint64_t M = c.max_batch;
@@ -618,6 +644,21 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
       h->d_deconv_carry.alloc(64) == cudaSuccess && h->d_sync_state.alloc(sizeof(SyncState)) == cudaSuccess &&
       h->d_sync_res.alloc(sizeof(SyncResult)) == cudaSuccess && h->d_counts.alloc(64) == cudaSuccess;
   if (!aok) return bail(LDVB_ENOMEM, "device allocation failed");
+  // cnr_fft / spectrum (leandvb.cc:322-343)
+  {
+    const int dec1 = std::max((int)(c.Fs / 1.0f), 1);   // decimation(cfg.Fs, 1), leandvb.cc:138-141
+    h->m_cnr.on = c.cnr != 0; h->m_cnr.logn = 12; h->m_cnr.kavg = 0.1f; h->m_cnr.bandwidth = c.Fm / c.Fs; h->m_cnr.decimation = dec1;
+    h->m_spec.on = c.spectrum != 0; h->m_spec.logn = 10; h->m_spec.kavg = 0.5f; h->m_spec.bandwidth = 0; h->m_spec.decimation = dec1;
+    bool mok = true;
+    for (ldvb_handle::MeasUnit *u : {&h->m_cnr, &h->m_spec})
+      if (u->on) mok = mok && u->d_avg.alloc(4096 * 4) == cudaSuccess && u->d_have.alloc(4) == cudaSuccess &&
+                       cudaMemset(u->d_have.p, 0, 4) == cudaSuccess;
+    if (h->m_cnr.on || h->m_spec.on)
+      mok = mok && h->d_meas_carry[0].alloc(4096 * 8) == cudaSuccess && h->d_meas_carry[1].alloc(4096 * 8) == cudaSuccess &&
+            h->d_meas_points.alloc(kMeasGroup * 8) == cudaSuccess && h->d_meas_power.alloc((size_t)kMeasGroup * 4096 * 4) == cudaSuccess &&
+            h->d_meas_sums.alloc(kMeasGroup * 12) == cudaSuccess && h->d_meas_rows.alloc((size_t)kMeasGroup * 1024 * 4) == cudaSuccess;
+    if (!mok) return bail(LDVB_ENOMEM, "telemetry allocation failed");
+  }
   // Notch
   memset(&h->notch, 0, sizeof h->notch);
   h->notch.gain = 1;
@@ -1424,6 +1465,107 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
   return LDVB_OK;
 }
 
+// ------------------------------------------------------------ cnr_fft / spectrum
+
+// One telemetry runnable over the samples [abs0, abs0 + avail) held in `src`.
+int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, uint64_t abs0, uint64_t avail) {
+  if (!u.on) return LDVB_OK;
+  const int64_t n = (int64_t)1 << u.logn;
+  const uint64_t abs_end = abs0 + avail;
+  // Measured blocks: phase advances by n per block, a block is measured when it reaches the
+  // decimation (sdr.h:1294-1302, 1362-1370).  Closed form instead of a walk over every block.
+  std::vector<uint64_t> points;
+  while (u.pos + (uint64_t)n <= abs_end) {
+    int64_t k = (u.decimation - u.phase + n - 1) / n;
+    if (k < 1) k = 1;
+    const uint64_t left = (abs_end - u.pos) / (uint64_t)n;
+    if ((uint64_t)k > left) { u.phase += (int64_t)left * n; u.pos += left * (uint64_t)n; break; }
+    u.phase += k * n - u.decimation;
+    u.pos += (uint64_t)k * (uint64_t)n;
+    points.push_back(u.pos - (uint64_t)n - abs0);
+  }
+  const bool is_cnr = u.bandwidth > 0;
+  // do_cnr (sdr.h:1306-1308, 1322): centre bin from freq_tap as of the start of the batch
+  const float tap_multiplier = (float)(1.0 / h->decim);          // leandvb.cc:514
+  const float center_freq = h->rx_state.freq_tap * tap_multiplier;
+  const int icf = (int)floor(center_freq * (float)n + 0.5);
+  const int bwslots = is_cnr ? (int)((u.bandwidth / 4) * (float)n) : 0;
+  for (size_t g0 = 0; g0 < points.size(); g0 += kMeasGroup) {
+    const int np = (int)std::min<size_t>(kMeasGroup, points.size() - g0);
+    CK(cudaMemcpyAsync(h->d_meas_points.p, points.data() + g0, (size_t)np * 8, cudaMemcpyHostToDevice, h->st));
+    MeasArgs a;
+    a.src = src; a.point_start = h->d_meas_points.as<uint64_t>(); a.npoints = np; a.logn = u.logn;
+    a.twiddle_rev = h->d_twiddle.as<float2>(); a.power = h->d_meas_power.as<float>();
+    KL("meas_power", launch_meas_power(a, h->st));
+    MeasEmaArgs e;
+    e.power = a.power; e.npoints = np; e.n = (int)n; e.kavg = u.kavg;
+    e.avg = u.d_avg.as<float>(); e.have = u.d_have.as<int>();
+    e.bwslots = bwslots; e.icf = icf; e.sums = h->d_meas_sums.as<float>();
+    e.rows = is_cnr ? nullptr : h->d_meas_rows.as<float>();
+    KL("meas_ema", launch_meas_ema(e, h->st));
+    if (is_cnr) {
+      if (!bwslots) continue;                                    // sdr.h:1324
+      std::vector<float> sums(3 * (size_t)np);
+      CK(cudaMemcpyAsync(sums.data(), e.sums, sums.size() * 4, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      for (int p = 0; p < np; ++p) {                             // sdr.h:1326-1330 (glibc logf)
+        const float c2plusn2 = sums[3 * p];
+        const float n2 = (sums[3 * p + 1] + sums[3 * p + 2]) / 2;
+        const float c2 = c2plusn2 - n2;
+        const float cnr = (c2 > 0 && n2 > 0) ? 10 * logf(c2 / n2) / logf(10) : -50;
+        h->cnr_queue.push_back(cnr);
+      }
+    } else {
+      std::vector<float> rows((size_t)np * n);
+      CK(cudaMemcpyAsync(rows.data(), e.rows, rows.size() * 4, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      const size_t o = h->spec_queue.size();
+      h->spec_queue.resize(o + rows.size());
+      for (int p = 0; p < np; ++p) {                             // sdr.h:1390-1394 (glibc log10f)
+        const float *avg = rows.data() + (size_t)p * n;
+        float *row = h->spec_queue.data() + o + (size_t)p * n;
+        for (int i = 0; i < n / 2; ++i) {
+          row[i] = 10 * log10f(avg[n / 2 + i]);
+          row[n / 2 + i] = 10 * log10f(avg[i]);
+        }
+      }
+    }
+  }
+  return LDVB_OK;
+}
+
+// cnr_fft and spectrum on the new samples of this batch: `rest` at element rest_off holds
+// n_new samples in format fmt, continuing the stream after the carried (< 4096) samples.
+int run_meas(ldvb_handle *h, const RawSrc &rest, uint64_t rest_off, int fmt, uint64_t n_new) {
+  if (!h->m_cnr.on && !h->m_spec.on) return LDVB_OK;
+  WallTimer wt(h, "wall:telemetry");
+  MeasSrc src;
+  src.carry = h->d_meas_carry[h->meas_carry_sel].as<float2>();
+  src.carry_count = h->meas_carry_count;
+  src.rest = rest; src.rest_off = rest_off; src.fmt = fmt; src.scale = h->cfg.float_scale;
+  const uint64_t abs0 = h->meas_abs_next - h->meas_carry_count;
+  src.rot_lut = h->use_rot ? h->d_rot.as<float>() : nullptr;
+  src.rot_index0 = (uint32_t)(abs0 & 0xffffu);
+  const uint64_t avail = h->meas_carry_count + n_new;
+  int rc;
+  if ((rc = run_meas_unit(h, h->m_cnr, src, abs0, avail))) return rc;
+  if ((rc = run_meas_unit(h, h->m_spec, src, abs0, avail))) return rc;
+  // Keep what the slower reader has not consumed yet.
+  uint64_t keep_from = abs0 + avail;
+  if (h->m_cnr.on) keep_from = std::min(keep_from, h->m_cnr.pos);
+  if (h->m_spec.on) keep_from = std::min(keep_from, h->m_spec.pos);
+  const uint64_t keep = abs0 + avail - keep_from;
+  if (keep >= 4096) return fail(h, LDVB_ESTATE, "telemetry carry overflow");
+  if (keep) {
+    const int other = h->meas_carry_sel ^ 1;
+    KL("meas_save", launch_meas_save(src, keep_from - abs0, (uint32_t)keep, h->d_meas_carry[other].as<float2>(), h->st));
+    h->meas_carry_sel = other;
+  }
+  h->meas_carry_count = keep;
+  h->meas_abs_next = abs0 + avail;
+  return LDVB_OK;
+}
+
 // ------------------------------------------------------------------ whole chain
 
 int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_t n, uint8_t *ts_dst,
@@ -1459,6 +1601,11 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   uint64_t raw_consumed = 0;
   if (c.anf) {
     if ((rc = run_notch(h, src, avail, &raw_consumed))) return rc;
+    {   // cnr_fft / spectrum read the notched stream (leandvb.cc:296-343); the rotator is applied on load
+      RawSrc fresh;
+      fresh.head = h->s_notched.at(0); fresh.head_count = h->s_notched.count; fresh.main = nullptr; fresh.c0 = 0;
+      if ((rc = run_meas(h, fresh, h->s_notched.count - h->s_notched.fresh, 5, h->s_notched.fresh))) return rc;
+    }
     RawSrc nsrc;
     nsrc.head = h->s_notched.at(0); nsrc.head_count = h->s_notched.count; nsrc.main = nullptr; nsrc.c0 = 0;
     uint64_t ncons = 0;
@@ -1474,6 +1621,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
       h->s_notched.count = 0;
     }
   } else {
+    if ((rc = run_meas(h, src, c0, c.input_format, n))) return rc;
     if ((rc = run_frontend(h, src, c.input_format, avail, &raw_consumed))) return rc;
   }
   // Carry the unread raw samples.
@@ -2168,6 +2316,26 @@ int ldvb_set_state(ldvb_handle *h, const void *blob, size_t size) {
   h->notch = b.notch; h->rot_index = b.rot_index; h->rx_state = b.rx;
   for (int i = 0; i < 4; ++i) h->hyp[i] = b.hyp[i];
   h->locked = b.locked; h->skip = b.skip; h->sync = b.sync; h->derand_pos = b.derand_pos;
+  return LDVB_OK;
+}
+
+// ------------------------------------------------------------ CNR / spectrum
+
+int ldvb_pull_cnr(ldvb_handle *h, float *dst, size_t cap, size_t *n) {
+  if (!h || !n) return LDVB_EINVAL;
+  const size_t k = std::min(cap, h->cnr_queue.size());
+  if (k && dst) memcpy(dst, h->cnr_queue.data(), k * 4);
+  h->cnr_queue.erase(h->cnr_queue.begin(), h->cnr_queue.begin() + k);
+  *n = k;
+  return LDVB_OK;
+}
+
+int ldvb_pull_spectrum(ldvb_handle *h, float *dst, size_t cap_rows, size_t *n_rows) {
+  if (!h || !n_rows) return LDVB_EINVAL;
+  const size_t k = std::min(cap_rows, h->spec_queue.size() / 1024);
+  if (k && dst) memcpy(dst, h->spec_queue.data(), k * 1024 * 4);
+  h->spec_queue.erase(h->spec_queue.begin(), h->spec_queue.begin() + k * 1024);
+  *n_rows = k;
   return LDVB_OK;
 }
 

@@ -33,7 +33,9 @@ struct gpu_dvbs_receiver : runnable {
 		    const ldvb_config &cfg,
 		    pipebuf<float> *_freq_out=NULL, pipebuf<float> *_ss_out=NULL,
 		    pipebuf<float> *_mer_out=NULL, pipebuf<int> *_lock_out=NULL,
-		    pipebuf<float> *_vber_out=NULL)
+		    pipebuf<float> *_vber_out=NULL,
+		    pipebuf<float> *_cnr_out=NULL,             // p_cnr, leandvb.cc:322
+		    pipebuf<float[1024]> *_spectrum_out=NULL)   // p_spectrum, leandvb.cc:333-338
     : runnable(sch, "gpu_dvbs_receiver"),
       in(_in), out(_out), handle(NULL),
       last_lock(-1), rs_bits(0), rs_errs(0) {
@@ -43,6 +45,8 @@ struct gpu_dvbs_receiver : runnable {
     mer_out = opt_writer(_mer_out);
     lock_out = opt_writer(_lock_out);
     vber_out = opt_writer(_vber_out);
+    cnr_out = opt_writer(_cnr_out);
+    spectrum_out = _spectrum_out ? new pipewriter<float[1024]>(*_spectrum_out) : NULL;
     int rc = ldvb_create(&cfg, &handle);
     if ( rc ) { fprintf(stderr, "ldvb_create: %s\n", ldvb_strerror(rc)); fail("gpu_dvbs_receiver"); }
     max_batch = cfg.max_batch;
@@ -91,13 +95,20 @@ private:
       vber_out->write((float)(m.rs_errs-rs_errs) / (float)(m.rs_bits-rs_bits));  // generic.h:296-299
       rs_bits = m.rs_bits; rs_errs = m.rs_errs;
     }
+    // cnr_fft / spectrum (sdr.h:1273-1404): one value / one row per second of signal
+    size_t k = 0;
+    float v;
+    while ( cnr_out && cnr_out->writable() && !ldvb_pull_cnr(handle, &v, 1, &k) && k ) cnr_out->write(v);
+    while ( spectrum_out && spectrum_out->writable() &&
+	    !ldvb_pull_spectrum(handle, (float*)spectrum_out->wr(), 1, &k) && k ) spectrum_out->written(1);
   }
 
   pipereader<Tin> in;
   pipewriter<Tpacket> out;
   ldvb_handle *handle;
   unsigned long max_batch;
-  pipewriter<float> *freq_out, *ss_out, *mer_out, *vber_out;
+  pipewriter<float> *freq_out, *ss_out, *mer_out, *vber_out, *cnr_out;
+  pipewriter<float[1024]> *spectrum_out;
   pipewriter<int> *lock_out;
   int last_lock;
   uint64_t rs_bits, rs_errs;

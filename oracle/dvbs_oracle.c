@@ -503,6 +503,62 @@ void orc_fft_inplace(int n, float *dataf, int reverse) {  /* dsp.h:78-110 */
   }
 }
 
+/* ------------------------------------------------------ cnr_fft / spectrum */
+
+void orc_meas_init(orc_meas *m, int n, float bandwidth, float kavg, int decimation) {
+  memset(m, 0, sizeof(*m));
+  m->n = n; m->bandwidth = bandwidth; m->kavg = kavg; m->decimation = decimation;
+}
+
+static float meas_avgslots(const orc_meas *m, int i0, int i1) {   /* sdr.h:1333-1337 */
+  float s = 0;
+  for ( int i = i0; i <= i1; ++i ) s += m->avgpower[i & (m->n-1)];
+  return s / (i1-i0+1);
+}
+
+size_t orc_meas_run(orc_meas *m, const float *in, size_t n_in, float center_freq, float *out,
+		    size_t cap_points, size_t *consumed) {
+  size_t points = 0, pos = 0;
+  const int n = m->n;
+  float *data = malloc(sizeof(float)*2*n), *power = malloc(sizeof(float)*n);
+  while ( n_in - pos >= (size_t)n && points < cap_points ) {     /* sdr.h:1294-1302, 1362-1370 */
+    m->phase += n;
+    if ( m->phase >= m->decimation ) {
+      m->phase -= m->decimation;
+      memcpy(data, in + 2*pos, sizeof(float)*2*n);
+      orc_fft_inplace(n, data, 1);
+      for ( int i = 0; i < n; ++i )
+	power[i] = data[2*i]*data[2*i] + data[2*i+1]*data[2*i+1];
+      if ( !m->have_avg ) { memcpy(m->avgpower, power, sizeof(float)*n); m->have_avg = 1; }
+      for ( int i = 0; i < n; ++i )
+	m->avgpower[i] = m->avgpower[i]*(1-m->kavg) + power[i]*m->kavg;
+      if ( m->bandwidth > 0 ) {                                  /* do_cnr, sdr.h:1306-1331 */
+	int icf = (int)floor(center_freq*n+0.5);
+	int bwslots = (int)((m->bandwidth/4) * n);
+	if ( bwslots ) {
+	  float c2plusn2 = meas_avgslots(m, icf-bwslots, icf+bwslots);
+	  float n2 = ( meas_avgslots(m, icf-bwslots*4, icf-bwslots*3) +
+		       meas_avgslots(m, icf+bwslots*3, icf+bwslots*4) ) / 2;
+	  float c2 = c2plusn2 - n2;
+	  float cnr = (c2>0 && n2>0) ? 10 * logf(c2/n2)/logf(10) : -50;
+	  out[points++] = cnr;
+	}
+      } else {                                                   /* do_spectrum, sdr.h:1390-1396 */
+	float *row = out + points*(size_t)n;
+	for ( int i = 0; i < n/2; ++i ) {
+	  row[i] = 10 * log10f(m->avgpower[n/2+i]);
+	  row[n/2+i] = 10 * log10f(m->avgpower[i]);
+	}
+	++points;
+      }
+    }
+    pos += n;
+  }
+  free(data); free(power);
+  *consumed = pos;
+  return points;
+}
+
 void orc_notch_init(orc_notch *a, int nslots) {       /* sdr.h:53-63 */
   memset(a, 0, sizeof(*a));
   a->nslots = nslots;
@@ -1398,6 +1454,7 @@ size_t orc_sizeof(int what) {
   case 5: return sizeof(orc_deconv);
   case 6: return sizeof(orc_mpegsync);
   case 7: return sizeof(orc_derand);
+  case 8: return sizeof(orc_meas);
   default: return 0;
   }
 }

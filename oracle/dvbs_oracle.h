@@ -114,6 +114,26 @@ size_t orc_notch_run(orc_notch *a, const float *in, size_t n_in, float *out);
 /* cfft_engine::inplace (dsp.h:78-110) exposed for tests. */
 void   orc_fft_inplace(int n, float *data, int reverse);
 
+/* ------------------------------------------------------------ cnr_fft / spectrum
+ * sdr.h:1273-1345 (cnr_fft<f32>, nfft 4096) and sdr.h:1347-1404 (spectrum<f32>, nfft 1024).
+ * Both read the stream in front of the FIR (leandvb.cc:322-343).  One struct serves both:
+ * n = 4096 + bandwidth > 0 -> CNR values; n = 1024 + bandwidth = 0 -> 1024-bin rows. */
+typedef struct {
+  int n;
+  float bandwidth;          /* Fm/Fs (cnr) */
+  float kavg;               /* 0.1 (cnr), 0.5 (spectrum as leandvb sets it, :342) */
+  int decimation;           /* decimation(Fs, 1), leandvb.cc:328,341 */
+  int phase;
+  int have_avg;
+  float avgpower[4096];
+} orc_meas;
+void   orc_meas_init(orc_meas *m, int n, float bandwidth, float kavg, int decimation);
+/* Consumes whole n-sample blocks of cf32 `in`; center_freq = *freq_tap * tap_multiplier at
+ * the time of the call (cnr only).  Writes one float per CNR point, or n floats per spectrum
+ * row, up to cap points; returns the number of points, *consumed = samples read. */
+size_t orc_meas_run(orc_meas *m, const float *in, size_t n_in, float center_freq, float *out,
+		    size_t cap_points, size_t *consumed);
+
 /* ------------------------------------------------------------ receiver */
 
 enum { ORC_SAMP_NEAREST = 0, ORC_SAMP_LINEAR = 1, ORC_SAMP_RRC = 2 };

@@ -82,6 +82,9 @@ def lib():
         L.orc_notch_init.argtypes = [vp, C.c_int]
         L.orc_notch_run.restype = sz
         L.orc_notch_run.argtypes = [vp, vp, sz, vp]
+        L.orc_meas_init.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.orc_meas_run.restype = sz
+        L.orc_meas_run.argtypes = [vp, vp, sz, C.c_float, vp, sz, C.POINTER(sz)]
         L.orc_notch_get_state.argtypes = [vp, vp, vp, vp, vp]
         L.orc_fft_inplace.argtypes = [C.c_int, vp, C.c_int]
         L.orc_rx_init.argtypes = [vp, vp, vp, C.c_int]
@@ -297,6 +300,25 @@ class Notch:
         return {"phase": ph.value, "gain": g.value, "slot_i": si, "estim": es}
 
 
+class Meas:
+    """cnr_fft (n = 4096, bandwidth = Fm/Fs) or spectrum (n = 1024, bandwidth = 0)."""
+
+    def __init__(self, n, bandwidth, kavg, decimation):
+        self.o = _Obj(8)
+        self.n = n
+        self.rows = bandwidth == 0
+        lib().orc_meas_init(self.o.p, C.c_int(n), C.c_float(bandwidth), C.c_float(kavg), C.c_int(decimation))
+
+    def run(self, x, center_freq=0.0):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1)
+        cap = x.size // 2 // self.n + 1
+        out = np.zeros(cap * (self.n if self.rows else 1), np.float32)
+        used = C.c_size_t(0)
+        k = lib().orc_meas_run(self.o.p, _p(x), C.c_size_t(x.size // 2), C.c_float(center_freq), _p(out),
+                               C.c_size_t(cap), C.byref(used))
+        return (out[:k * self.n].reshape(k, self.n) if self.rows else out[:k]), used.value
+
+
 def fft_inplace(x, reverse=True):
     x = np.ascontiguousarray(x, np.float32).reshape(-1).copy()
     lib().orc_fft_inplace(x.size // 2, _p(x), int(reverse))
@@ -493,6 +515,7 @@ class Config:
     allow_drift: bool = False
     Ftune: float = 0.0
     Finfo: float = 5.0
+    cnr: bool = False          # --cnr (leandvb.cc:322-329); the spectrum is always measured (:333-343)
 
 
 def _idecim(a, b):
@@ -556,6 +579,13 @@ class Chain:
             t["notched"] = x
         if self.rot:
             x = self.rot.run(x)
+        # cnr_fft / spectrum read the stream in front of the FIR (leandvb.cc:322-343);
+        # freq_tap is the demodulator's value when the batch starts (0 after a reset)
+        dec1 = _idecim(self.cfg.Fs, 1)
+        if self.cfg.cnr:
+            bw = np.float32(self.cfg.Fm) / np.float32(self.cfg.Fs)
+            t["cnr"], _ = Meas(4096, float(bw), 0.1, dec1).run(x, 0.0)
+        t["spectrum"], _ = Meas(1024, 0.0, 0.5, dec1).run(x)
         if self.fir:
             x, _ = self.fir.run(x)
         elif self.decim > 1:

@@ -7,6 +7,7 @@ where /root/reference is mounted and `make -C oracle ref` has built oracle/_ref)
   c1_160_anf0.ts       leandvb --u8 ... --anf 0                              < c1_160.u8
   c1_160_taps.json     sha256 + sizes of every stream tapped by oracle/_ref/ref_tap (default flags)
   tables.json          sha256 of the constant tables dumped by oracle/_ref/ref_tables
+  c1_160_spectrum_fs100k.f32  spectrum rows (p_spectrum) of ref_tap --u8 -f 100000 --sr 83333 < c1_160.u8
   kat.json             known answers quoted in SURVEY.md 8(c)
 """
 import hashlib, json, os, subprocess, sys, tempfile
@@ -17,6 +18,15 @@ from oracle import oracle as O
 from tests import vectors as V
 
 def sha(b): return hashlib.sha256(b).hexdigest()
+
+def spectrum_golden(iq):
+    """spectrum<f32> (sdr.h:1347-1404): at -f 100000 the 291 k-sample fixture yields 2 rows."""
+    d = tempfile.mkdtemp()
+    subprocess.run([O.ref_bin("ref_tap"), "--u8", "-f", "100000", "--sr", "83333", "--tap-dir", d], input=iq.tobytes(),
+                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+    rows = np.fromfile(os.path.join(d, "spectrum.f32"), np.float32)
+    assert rows.size == 2 * 1024
+    rows.tofile(os.path.join(HERE, "c1_160_spectrum_fs100k.f32"))
 
 def main():
     iq = V.ref_iq(160, fmt="u8")
@@ -32,6 +42,7 @@ def main():
         b = open(os.path.join(d, f), "rb").read()
         taps[f] = {"bytes": len(b), "sha256": sha(b)}
     json.dump(taps, open(os.path.join(HERE, "c1_160_taps.json"), "w"), indent=1)
+    spectrum_golden(iq)
     d2 = tempfile.mkdtemp()
     subprocess.run([O.ref_bin("ref_tables"), d2], check=True)
     tabs = {f: {"bytes": os.path.getsize(os.path.join(d2, f)), "sha256": sha(open(os.path.join(d2, f), "rb").read())}

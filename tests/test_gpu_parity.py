@@ -301,3 +301,51 @@ def test_empty_and_tiny_inputs(product):
     with pytest.raises(P.LdvbError):
         rx.push(np.zeros(2 * ((1 << 16) + 1), np.uint8))
     rx.close()
+
+
+def _telemetry(P, raw, n_batch, **kw):
+    n = raw.size // 2
+    rx = P.Receiver(max_batch=n_batch, rx_mode=P.RX_FAST, **kw)
+    cnr, rows = [], []
+    for s in range(0, n, n_batch):
+        rx.push(raw[2 * s: 2 * min(n, s + n_batch)])
+        rx.pull_all()
+        cnr.append(rx.pull_cnr()); rows.append(rx.pull_spectrum())
+    rx.close()
+    return np.concatenate(cnr), np.concatenate(rows)
+
+
+@pytest.mark.parametrize("name,kw,gkw,npk,batch", [
+    ("f32-5sps-anf1-one-batch", dict(fmt="f32", Fs=10e6, anf=1, cnr=True), dict(ratio="5/1"), 2500, None),
+    ("u8-5sps-anf0-odd-batches", dict(fmt="u8", Fs=10e6, anf=0, cnr=True), dict(ratio="5/1"), 2500, 3_000_001),
+    ("f32-5sps-anf2-batches", dict(fmt="f32", Fs=10e6, anf=2, cnr=True), dict(ratio="5/1"), 2500, 5_000_000),
+], ids=lambda v: v if isinstance(v, str) else None)
+def test_cnr_and_spectrum_bit_exact(product, oracle, name, kw, gkw, npk, batch):
+    """cnr_fft (sdr.h:1273-1345) and spectrum (sdr.h:1347-1404): p_cnr and p_spectrum, float for
+    float.  Odd batch sizes exercise the < 4096-sample carry in front of the measured blocks."""
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    cnr, rows = _telemetry(P, raw, batch or raw.size // 2, **kw)
+    assert len(ref["cnr"]) >= 2 and np.array_equal(cnr, ref["cnr"][: len(cnr)]) and len(cnr) >= len(ref["cnr"]) - 1
+    assert np.array_equal(rows, ref["spectrum"][: len(rows)]) and len(rows) >= len(ref["spectrum"]) - 1
+
+
+def test_spectrum_with_rotator_and_golden(product, oracle):
+    """The rotator (leandvb.cc:310-318) is applied on load by the telemetry kernel; plus the
+    committed rows of the unmodified reference (tests/golden/make_golden.py)."""
+    P, O = product, oracle
+    raw = V.ref_iq(1400, fmt="u8")
+    kw = dict(fmt="u8", Fs=600000.0, Fm=500000.0, anf=0, Fderot=7000.0)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    _, rows = _telemetry(P, raw, 700_001, **kw)
+    assert len(rows) >= 3 and np.array_equal(rows, ref["spectrum"][: len(rows)])
+    iq = np.fromfile(os.path.join(GOLDEN, "c1_160.u8"), dtype=np.uint8)
+    want = np.fromfile(os.path.join(GOLDEN, "c1_160_spectrum_fs100k.f32"), dtype=np.float32).reshape(-1, 1024)
+    _, rows = _telemetry(P, iq, iq.size // 2, fmt="u8", Fs=100000.0, Fm=83333.0)
+    assert np.array_equal(rows, want)
+
+
+def test_cnr_needs_four_samples_per_symbol(product):
+    with pytest.raises(product.LdvbError):
+        product.Receiver(fmt="f32", cnr=True)     # Fs/Fm = 1.2 (sdr.h:1283-1284)

@@ -146,3 +146,42 @@ def test_oracle_notch_detect_path(oracle):
     st = open(os.path.join(d, "state.txt")).read()
     assert "notch.slot0 -1" not in st           # a bin was selected
     assert t["ts"].tobytes()[:len(ts_ref)] == ts_ref
+
+
+def test_oracle_spectrum_equals_reference_golden(oracle):
+    """spectrum<f32> (sdr.h:1347-1404) restated in the oracle against rows written by the
+    unmodified reference (tests/golden/make_golden.py: ref_tap --u8 -f 100000 --sr 83333)."""
+    O = oracle
+    iq = np.fromfile(os.path.join(GOLDEN, "c1_160.u8"), dtype=np.uint8)
+    want = np.fromfile(os.path.join(GOLDEN, "c1_160_spectrum_fs100k.f32"), dtype=np.float32).reshape(-1, 1024)
+    got = O.Chain(O.Config(fmt="u8", Fs=100000.0, Fm=83333.0)).run(iq)["spectrum"]
+    assert want.shape == (2, 1024) and np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not V.have_ref(), reason="oracle/_ref not built")
+def test_oracle_cnr_and_spectrum_equal_reference_taps(oracle):
+    """cnr_fft<f32> (sdr.h:1273-1345, needs Fs > 4 Fm) and spectrum against the reference's own
+    p_cnr / p_spectrum on a 5 samples/symbol stream; with a derotator the centre bin follows
+    freq_tap (icf = -12 here), which the oracle takes as an argument."""
+    import subprocess, tempfile
+    O = oracle
+    raw = V.ref_iq(1300, ratio="5/1", fmt="f32")
+    for anf, derot, icf in ((1, 0.0, 0), (0, 30000.0, -12)):
+        d = tempfile.mkdtemp()
+        flags = ["--f32", "-f", "10e6", "--sr", "2e6", "--cnr", "--anf", str(anf), "--tap-dir", d]
+        if derot:
+            flags += ["--derotate", str(derot)]
+        subprocess.run([O.ref_bin("ref_tap"), *flags], input=raw.tobytes(), stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, check=True)
+        want_c = np.fromfile(d + "/cnr.f32", np.float32)
+        want_s = np.fromfile(d + "/spectrum.f32", np.float32).reshape(-1, 1024)
+        c = O.Chain(O.Config(fmt="f32", Fs=10e6, Fm=2e6, anf=anf, Fderot=derot, cnr=True))
+        out = c.run(raw)
+        assert len(want_s) >= 1 and np.array_equal(out["spectrum"][: len(want_s)], want_s)
+        x = raw
+        if c.notch:
+            x, _ = c.notch.__class__(anf).run(x)
+        if c.rot:
+            x = O.Rotator(np.float32(-np.float32(derot) / np.float32(10e6))).run(x)
+        got_c, _ = O.Meas(4096, float(np.float32(2e6) / np.float32(10e6)), 0.1, O._idecim(10e6, 1)).run(x, icf / 4096.0)
+        assert want_c.size >= 1 and np.array_equal(got_c[: want_c.size], want_c)
