@@ -363,8 +363,9 @@ def main():
 
     # ---- e2e: host buffers through push/pull
     pinned = torch.from_numpy(raw).pin_memory()
+    ts_host = torch.empty(cap * 188, dtype=torch.uint8)       # the caller's TS buffer (ldvb_pull copies into it)
     for _ in range(2):
-        rx.reset(); rx.push_ptr(pinned.data_ptr(), n); rx.pull_all()
+        rx.reset(); rx.push_ptr(pinned.data_ptr(), n); rx.pull_ptr(ts_host.data_ptr(), cap)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
@@ -373,11 +374,12 @@ def main():
     for _ in range(a.steps):
         rx.reset()
         rx.push_ptr(pinned.data_ptr(), n)
-        d2h = rx.pull_all().nbytes
+        d2h = rx.pull_ptr(ts_host.data_ptr(), cap) * 188
     f1.record(stream)
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
     clk = clocks.summary()
+    e2e_ts_ok = bool(d2h == npk * 188 and np.array_equal(ts_host[:d2h].numpy().reshape(-1, 188), ts_gpu))
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -450,6 +452,7 @@ def main():
             "kernel_ms_per_step": per_step, "stage_wall_ms_per_step": wall,
             "cpu_baseline": cpu,
             "ts_packets_per_step": int(npk), "ts_bit_exact_vs_reference": ts_match,
+            "e2e_ts_equals_device_resident_ts": e2e_ts_ok,
             "seams": {"total": meas["seams_total"], "repaired": meas["seams_repaired"], "notch_repaired": meas["notch_repaired"]}}
     print(json.dumps(line))
 

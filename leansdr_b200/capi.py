@@ -220,13 +220,21 @@ class Receiver:
         self._ck(self.L.ldvb_pull(self.h, _p(out), max_packets, C.byref(n)), "ldvb_pull")
         return out[:n.value]
 
+    def pull_ptr(self, host_ptr: int, cap_packets: int) -> int:
+        """ldvb_pull into caller memory (address of cap_packets * 188 bytes); returns the packet count."""
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_pull(self.h, C.c_void_p(host_ptr), cap_packets, C.byref(n)), "ldvb_pull")
+        return n.value
+
     def pull_all(self) -> np.ndarray:
         parts = []
         while True:
             p = self.pull(1 << 16)
             if p.shape[0] == 0:
                 break
-            parts.append(p.copy())
+            parts.append(p)
+        if len(parts) == 1:
+            return parts[0]
         return np.concatenate(parts) if parts else np.zeros((0, 188), np.uint8)
 
     def process_device(self, iq_ptr: int, n_samples: int, ts_ptr: int, cap_packets: int) -> int:

@@ -167,9 +167,10 @@ struct ldvb_handle {
   cudaEvent_t copy_done[2] = {nullptr, nullptr};
   uint64_t sub_batch = 0;
 
-  // ---- host-side TS queue for push/pull
-  std::vector<uint8_t> ts_queue;
-  size_t ts_queue_rd = 0;
+  // ---- host-side TS queue for push/pull: page-locked, so the D2H of a sub-batch's packets is a
+  // true asynchronous DMA that overlaps the next sub-batch (bytes [rd, wr) are unread)
+  uint8_t *ts_queue = nullptr;
+  size_t ts_queue_cap = 0, ts_queue_rd = 0, ts_queue_wr = 0;
 
   // ---- per-kernel timing (ldvb_profile)
   bool profiling = false;
@@ -365,7 +366,7 @@ void reset_carry(ldvb_handle *h) {
   h->sync.report_state = 1;
   h->sync.phase8 = -1;
   h->derand_pos = 0;
-  h->ts_queue.clear(); h->ts_queue_rd = 0;
+  h->ts_queue_rd = h->ts_queue_wr = 0;
   memset(&h->meas, 0, sizeof h->meas);
   for (ldvb_handle::MeasUnit *u : {&h->m_cnr, &h->m_spec}) {
     u->phase = 0; u->pos = 0;
@@ -484,6 +485,7 @@ int ldvb_destroy(ldvb_handle *h) {
   for (Tap &t : h->taps) t.buf.release();
   for (int i = 0; i < 2; ++i) { h->d_stage[i].release(); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
   if (h->copy_st) cudaStreamDestroy(h->copy_st);
+  if (h->ts_queue) cudaFreeHost(h->ts_queue);
   for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto &e : h->prof_free) cudaEventDestroy(e);
   if (h->st && h->own_stream) cudaStreamDestroy(h->st);
@@ -598,7 +600,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     h->rxp.rrc_coeffs = h->d_rrc.as<float>();
   }
   // Host batches larger than this are pipelined (copy/compute overlap); push_sub_batch overrides.
-  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : (uint64_t)32 << 20;
+  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : (uint64_t)16 << 20;
 
   // ---- stream buffers
   const uint64_t M = c.max_batch;
@@ -2097,12 +2099,24 @@ int shard_back(ldvb_handle *h, const EdgeBlob *in, uint8_t *ts_dst, uint64_t ts_
 
 extern "C" {
 
+// Queues the `got` packets of d_ts for ldvb_pull.  The copy is asynchronous on the handle's stream
+// (ordered before the next chain's kernels overwrite d_ts); ldvb_push synchronises once at its end.
 static int push_collect(ldvb_handle *h, uint64_t got) {
   if (!got) return LDVB_OK;
-  const size_t o = h->ts_queue.size();
-  h->ts_queue.resize(o + got * 188);
-  CK(cudaMemcpyAsync(h->ts_queue.data() + o, h->d_ts.p, got * 188, cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
+  const size_t need = h->ts_queue_wr + got * 188;
+  if (need > h->ts_queue_cap) {
+    // Grow (rare: the queue is sized for two full batches at the first push).
+    CK(cudaStreamSynchronize(h->st));
+    const size_t unread = h->ts_queue_wr - h->ts_queue_rd;
+    size_t cap = std::max<size_t>(2 * (size_t)h->ts_cap * 188, 2 * (unread + got * 188));
+    uint8_t *q = nullptr;
+    CK(cudaHostAlloc((void **)&q, cap, cudaHostAllocDefault));
+    if (unread) memcpy(q, h->ts_queue + h->ts_queue_rd, unread);
+    if (h->ts_queue) cudaFreeHost(h->ts_queue);
+    h->ts_queue = q; h->ts_queue_cap = cap; h->ts_queue_rd = 0; h->ts_queue_wr = unread;
+  }
+  CK(cudaMemcpyAsync(h->ts_queue + h->ts_queue_wr, h->d_ts.p, got * 188, cudaMemcpyDeviceToHost, h->st));
+  h->ts_queue_wr += got * 188;
   return LDVB_OK;
 }
 
@@ -2136,6 +2150,7 @@ static int push_pipelined(ldvb_handle *h, const uint8_t *host, size_t n) {
     if ((rc = run_chain(h, h->d_stage[i & 1].p, true, m, h->d_ts.as<uint8_t>(), h->ts_cap, &got))) return rc;
     if ((rc = push_collect(h, got))) return rc;
   }
+  CK(cudaStreamSynchronize(h->st));
   return LDVB_OK;
 }
 
@@ -2151,16 +2166,18 @@ int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n) {
   uint64_t got = 0;
   int rc = run_chain(h, nullptr, false, n, h->d_ts.as<uint8_t>(), h->ts_cap, &got);
   if (rc) return rc;
-  return push_collect(h, got);
+  if ((rc = push_collect(h, got))) return rc;
+  CK(cudaStreamSynchronize(h->st));
+  return LDVB_OK;
 }
 
 int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets, size_t *n_packets) {
   if (!h || !n_packets) return LDVB_EINVAL;
-  const size_t avail = (h->ts_queue.size() - h->ts_queue_rd) / 188;
+  const size_t avail = (h->ts_queue_wr - h->ts_queue_rd) / 188;
   const size_t n = std::min(avail, cap_packets);
-  if (n && ts_host) memcpy(ts_host, h->ts_queue.data() + h->ts_queue_rd, n * 188);
+  if (n && ts_host) memcpy(ts_host, h->ts_queue + h->ts_queue_rd, n * 188);
   h->ts_queue_rd += n * 188;
-  if (h->ts_queue_rd == h->ts_queue.size()) { h->ts_queue.clear(); h->ts_queue_rd = 0; }
+  if (h->ts_queue_rd == h->ts_queue_wr) h->ts_queue_rd = h->ts_queue_wr = 0;
   *n_packets = n;
   return LDVB_OK;
 }

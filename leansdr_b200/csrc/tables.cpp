@@ -197,17 +197,8 @@ std::vector<float> shift_taps(const std::vector<float> &coeffs, float freq) {
   return out;
 }
 
-std::vector<float> design_rrc(float Fs, float Fm, float rolloff, float rej,
-                              int steps_opt, int *steps_out) {
-  int steps = steps_opt;
-  if (steps == 0) {  // leandvb.cc:442-445
-    steps = (int)(64 * Fm / Fs);
-    if (steps < 1) steps = 1;
-  }
-  float Frrc = Fs * steps;
-  float transition = (Fm / 2) * rolloff;
-  int order = (int)(rej * Frrc / (22 * transition));
-  float fs = Fm / Frrc;  // symbol rate relative to the RRC sample rate
+// filtergen::root_raised_cosine (filtergen.h:68-92), float overloads of sin/cos/sqrt.
+static std::vector<float> rrc_taps(int order, float fs, float rolloff) {
   float B = rolloff, pi = (float)M_PI;
   int n = (order + 1) | 1;  // filtergen.h:70
   std::vector<float> c(n);
@@ -226,8 +217,47 @@ std::vector<float> design_rrc(float Fs, float Fm, float rolloff, float rej,
     c[i] = v;
   }
   dc_normalise(c, 1);
+  return c;
+}
+
+std::vector<float> design_rrc(float Fs, float Fm, float rolloff, float rej,
+                              int steps_opt, int *steps_out) {
+  int steps = steps_opt;
+  if (steps == 0) {  // leandvb.cc:442-445
+    steps = (int)(64 * Fm / Fs);
+    if (steps < 1) steps = 1;
+  }
+  float Frrc = Fs * steps;
+  float transition = (Fm / 2) * rolloff;
+  int order = (int)(rej * Frrc / (22 * transition));
+  float fs = Fm / Frrc;  // symbol rate relative to the RRC sample rate
+  std::vector<float> c = rrc_taps(order, fs, rolloff);
   *steps_out = steps;
   return c;
+}
+
+// leandvbtx.cc:131-138: interpolation RRC, then filtergen::normalize_power (filtergen.h:26-33).
+std::vector<float> design_tx_rrc(int interp, float rolloff, float rrc_rej, float amp) {
+  float Fm = 1.0 / interp;
+  int order = interp * rrc_rej;
+  std::vector<float> c = rrc_taps(order, Fm, rolloff);
+  float gain = amp / 75.0f;   // cstln_amp (sdr.h:287)
+  float s2 = 0;
+  for (size_t i = 0; i < c.size(); ++i) s2 = s2 + c[i] * c[i];
+  if (s2) gain /= sqrtf(s2);
+  for (size_t i = 0; i < c.size(); ++i) c[i] = c[i] * gain;
+  return c;
+}
+
+// fir_resampler::set_freq (dsp.h:352-361): no centring of the tap index here.
+std::vector<float> shift_taps_resampler(const std::vector<float> &coeffs, float freq) {
+  std::vector<float> out(2 * coeffs.size());
+  for (size_t i = 0; i < coeffs.size(); ++i) {
+    float a = (float)(2 * M_PI * freq * (int)i);
+    out[2 * i] = coeffs[i] * cosf(a);
+    out[2 * i + 1] = coeffs[i] * sinf(a);
+  }
+  return out;
 }
 
 std::vector<float> make_rotator_lut(float freq) {

@@ -34,6 +34,10 @@ std::vector<float> shift_taps(const std::vector<float> &coeffs, float freq);
 // leandvb.cc:437-456 + filtergen.h:68-92.
 std::vector<float> design_rrc(float Fs, float Fm, float rolloff, float rej,
                               int steps_opt, int *steps_out);
+// leandvbtx.cc:131-138: RRC interpolation taps scaled by normalize_power(amp / cstln_amp).
+std::vector<float> design_tx_rrc(int interp, float rolloff, float rrc_rej, float amp);
+// fir_resampler::set_freq (dsp.h:352-361): complex taps {c*cosf(a), c*sinf(a)}, a = 2*pi*f*i.
+std::vector<float> shift_taps_resampler(const std::vector<float> &coeffs, float freq);
 // sdr.h:1231-1241: 65536 x cos then 65536 x sin.
 std::vector<float> make_rotator_lut(float freq);
 

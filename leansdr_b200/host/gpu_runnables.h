@@ -17,6 +17,7 @@
 
 #include <stdio.h>
 #include "leandvb_b200.h"
+#include "leandvb_b200_tx.h"
 
 namespace leansdr {
 
@@ -112,6 +113,46 @@ private:
   pipewriter<int> *lock_out;
   int last_lock;
   uint64_t rs_bits, rs_errs;
+};
+
+// The transmit side: replaces every runnable that apps/leandvbtx.cc:79-197 instantiates
+// between p_tspackets and the output file_writer (randomizer, rs_encoder, interleaver,
+// dvb_convol, cstln_transmitter, fir_resampler, decimator, simple_agc) with one
+// ldvbtx_handle (include/leandvb_b200_tx.h).  Tpacket: dvb.h's tspacket; Tout: complex<f32>.
+template<typename Tpacket, typename Tout>
+struct gpu_dvbs_transmitter : runnable {
+  gpu_dvbs_transmitter(scheduler *sch, pipebuf<Tpacket> &_in, pipebuf<Tout> &_out,
+		       const ldvbtx_config &cfg)
+    : runnable(sch, "gpu_dvbs_transmitter"),
+      in(_in), out(_out), handle(NULL), max_packets(cfg.max_packets) {
+    if ( sizeof(Tpacket) != 188 || sizeof(Tout) != 8 ) fail("gpu_dvbs_transmitter: tspacket in, cf32 out");
+    int rc = ldvbtx_create(&cfg, &handle);
+    if ( rc ) { fprintf(stderr, "ldvbtx_create: %s\n", ldvb_strerror(rc)); fail("gpu_dvbs_transmitter"); }
+  }
+
+  void run() {
+    // Take as many packets as the output pipe can certainly hold the samples of; no
+    // progress when starved or when the output is full (framework.h:96-113).
+    unsigned long n = in.readable();
+    if ( n > max_packets ) n = max_packets;
+    while ( n && ldvbtx_max_samples(handle, n) > out.writable() ) n /= 2;
+    if ( !n ) return;
+    size_t got = 0;
+    int rc = ldvbtx_push(handle, (const uint8_t*)in.rd(), n, (float*)out.wr(), out.writable(), &got);
+    if ( rc ) { fprintf(stderr, "ldvbtx_push: %s (%s)\n", ldvb_strerror(rc), ldvbtx_last_error(handle)); fail("gpu_dvbs_transmitter"); }
+    in.read(n);
+    out.written(got);
+  }
+
+  void shutdown() {
+    if ( handle ) { ldvbtx_destroy(handle); handle = NULL; }
+  }
+
+private:
+  pipereader<Tpacket> in;
+  pipewriter<Tout> out;
+  ldvbtx_handle *handle;
+  unsigned long max_packets;
 };
 
 }  // namespace

@@ -260,6 +260,23 @@ int    orc_viterbi_current_sync(const orc_viterbi *v);
 size_t orc_viterbi_run(orc_viterbi *v, const uint8_t *symbols4, size_t n_in,
 		       uint8_t *out, size_t out_cap, size_t *consumed);
 
+/* ------------------------------------------------------------ transmit chain
+ * oracle/dvbs_tx_oracle.c: leandvbtx (apps/leandvbtx.cc:79-197), stage by stage. */
+void   orc_tx_randomize(const uint8_t *ts, size_t npk, uint8_t *out);
+void   orc_tx_rs_encode(const uint8_t *ts188, size_t npk, uint8_t *rs204);
+size_t orc_tx_interleave(const uint8_t *rs204, size_t npk, uint8_t *out);
+size_t orc_tx_convol(int fec, int bps, const uint8_t *in, size_t n, uint8_t *out, size_t *consumed);
+void   orc_tx_map(const orc_cstln *c, const uint8_t *sym, size_t n, float *out_cf32);
+float  orc_tx_amp(const char *power_db);
+int    orc_tx_taps(int interp, float rolloff, float rrc_rej, float amp, float *coeffs);
+size_t orc_tx_resample(const float *xin, size_t n_in, const float *coeffs, int ncoeffs, int interp,
+		       float *yout, size_t *consumed);
+size_t orc_tx_agc(const float *xin, size_t n, float out_rms, float bw, float *yout);
+size_t orc_tx_chain(const uint8_t *ts, size_t npk, int cstln_kind, int fec, int interp, int decim,
+		    float rolloff, float rrc_rej, const char *power_db, int agc,
+		    float *out, size_t cap_samples,
+		    uint8_t *tap_mpegbytes, size_t *n_mpegbytes, uint8_t *tap_symbols, size_t *n_symbols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16,
 def build(force: bool = False) -> str:
     """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = [os.path.join(_HERE, f) for f in ("dvbs_oracle.c", "dvbs_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("dvbs_oracle.c", "dvbs_tx_oracle.c", "dvbs_oracle.h")]
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in src)
     if force or stale:
@@ -121,6 +121,17 @@ def lib():
         L.orc_rs_decode_packet.restype = C.c_int
         L.orc_rs_decode_packet.argtypes = [vp, vp, C.POINTER(C.c_int)]
         L.orc_rs_encode.argtypes = [vp]
+        L.orc_tx_chain.restype = sz
+        L.orc_tx_chain.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_char_p,
+                                   C.c_int, vp, sz, vp, C.POINTER(sz), vp, C.POINTER(sz)]
+        L.orc_tx_taps.restype = C.c_int
+        L.orc_tx_taps.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, vp]
+        L.orc_tx_amp.restype = C.c_float
+        L.orc_tx_amp.argtypes = [C.c_char_p]
+        L.orc_tx_resample.restype = sz
+        L.orc_tx_resample.argtypes = [vp, sz, vp, C.c_int, C.c_int, vp, C.POINTER(sz)]
+        L.orc_tx_randomize.argtypes = [vp, sz, vp]
+        L.orc_tx_rs_encode.argtypes = [vp, sz, vp]
         L.orc_derandomize.restype = sz
         L.orc_derandomize.argtypes = [vp, vp, sz, vp]
         L.orc_viterbi_new.restype = vp
@@ -660,6 +671,54 @@ class Chain:
         return (by, np.concatenate(outs) if outs else np.zeros(0, np.uint8),
                 np.concatenate(locks) if locks else np.zeros(0, np.int32),
                 np.concatenate(lts) if lts else np.zeros(0, np.uint64))
+
+
+# ------------------------------------------------------------------ transmit chain
+
+def tx_taps(interp: int, rolloff: float = 0.35, rrc_rej: float = 10.0, power: str = "0") -> np.ndarray:
+    """leandvbtx.cc:131-138: RRC interpolation taps after normalize_power."""
+    L = lib()
+    out = np.zeros(int(interp * rrc_rej) + 8, np.float32)
+    n = L.orc_tx_taps(interp, rolloff, rrc_rej, L.orc_tx_amp(str(power).encode()), _p(out))
+    return out[:n].copy()
+
+
+def tx_resample(x: np.ndarray, coeffs: np.ndarray, interp: int) -> np.ndarray:
+    """fir_resampler<cf32,float> with real coefficients at frequency 0 (dsp.h:290-364)."""
+    x = np.ascontiguousarray(x, np.float32).reshape(-1)
+    c = np.ascontiguousarray(coeffs, np.float32)
+    y = np.zeros(2 * (x.size // 2 * interp + 8), np.float32)
+    used = C.c_size_t(0)
+    n = lib().orc_tx_resample(_p(x), x.size // 2, _p(c), c.size, interp, _p(y), C.byref(used))
+    return y[: 2 * n].copy()
+
+
+def tx_rs_packets(ts: np.ndarray) -> np.ndarray:
+    """randomizer + rs_encoder (dvb.h:1063-1102, 957-980): [n,188] -> [n,204]."""
+    ts = np.ascontiguousarray(ts, np.uint8).reshape(-1, 188)
+    r = np.zeros_like(ts)
+    lib().orc_tx_randomize(_p(ts), ts.shape[0], _p(r))
+    out = np.zeros((ts.shape[0], 204), np.uint8)
+    lib().orc_tx_rs_encode(_p(r), ts.shape[0], _p(out))
+    return out
+
+
+def tx_chain(ts: np.ndarray, cstln: str = "QPSK", cr: str = "1/2", ratio: str = "2", power: str = "0",
+             agc: bool = False, rolloff: float = 0.35, rrc_rej: float = 10.0) -> dict:
+    """The whole leandvbtx chain (apps/leandvbtx.cc:79-197) on TS packets [n,188]:
+    {"iq": interleaved floats, "mpegbytes": u8, "symbols": u8}."""
+    ts = np.ascontiguousarray(ts, np.uint8).reshape(-1, 188)
+    npk = ts.shape[0]
+    parts = str(ratio).split("/")
+    I, D = int(parts[0]), (int(parts[1]) if len(parts) > 1 else 1)
+    cap = npk * 204 * 16 * I // D + 4096
+    iq = np.zeros(2 * cap, np.float32)
+    mb = np.zeros(npk * 204 + 16, np.uint8)
+    sym = np.zeros(npk * 204 * 16 + 64, np.uint8)
+    nmb, nsym = C.c_size_t(0), C.c_size_t(0)
+    n = lib().orc_tx_chain(_p(ts), npk, CSTLN[cstln], FEC[cr], I, D, rolloff, rrc_rej, str(power).encode(), int(agc),
+                           _p(iq), cap, _p(mb), C.byref(nmb), _p(sym), C.byref(nsym))
+    return {"iq": iq[: 2 * n].copy(), "mpegbytes": mb[: nmb.value].copy(), "symbols": sym[: nsym.value].copy()}
 
 
 def ref_bin(name: str) -> str:

@@ -9,6 +9,8 @@ where /root/reference is mounted and `make -C oracle ref` has built oracle/_ref)
   tables.json          sha256 of the constant tables dumped by oracle/_ref/ref_tables
   c1_160_spectrum_fs100k.f32  spectrum rows (p_spectrum) of ref_tap --u8 -f 100000 --sr 83333 < c1_160.u8
   kat.json             known answers quoted in SURVEY.md 8(c)
+  tx_kat.json          sha256 + length of oracle/_ref/leandvbtx's cf32 output for tests/tx_cases.py
+                       (`python make_golden.py tx` regenerates only this file)
 """
 import hashlib, json, os, subprocess, sys, tempfile
 import numpy as np
@@ -28,7 +30,22 @@ def spectrum_golden(iq):
     assert rows.size == 2 * 1024
     rows.tofile(os.path.join(HERE, "c1_160_spectrum_fs100k.f32"))
 
+def tx_golden():
+    from tests.tx_cases import TX_CASES
+    kat = {}
+    for name, npk, cst, cr, ratio, power, agc, rolloff in TX_CASES:
+        args = [O.ref_bin("leandvbtx"), "--const", cst, "--cr", cr, "-f", ratio, "--power", power, "--roll-off", str(rolloff)]
+        if agc: args.append("--agc")
+        out = subprocess.run(args, input=V.ts_packets(npk).tobytes(), stdout=subprocess.PIPE, check=True).stdout
+        kat[name] = {"samples": len(out) // 8, "sha256": sha(out), "cmd": " ".join(["leantsgen -c %d |" % npk, "leandvbtx"] + args[1:])}
+    json.dump(kat, open(os.path.join(HERE, "tx_kat.json"), "w"), indent=1)
+
 def main():
+    if sys.argv[1:] == ["tx"]:
+        tx_golden()
+        print("tx golden regenerated")
+        return
+    tx_golden()
     iq = V.ref_iq(160, fmt="u8")
     iq.tofile(os.path.join(HERE, "c1_160.u8"))
     base = ["--u8", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2"]

@@ -14,15 +14,33 @@ from tests.conftest import ROOT, have_gpu
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def test_exports_match_header(product):
-    hdr = open(os.path.join(ROOT, "include", "leandvb_b200.h")).read()
+def _declared(header, prefix):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(ldvb_[a-z0-9_]+)\s*\(", hdr))
-    assert declared, "no declarations parsed"
+    return set(re.findall(r"\b(%s_[a-z0-9_]+)\s*\(" % prefix, hdr))
+
+
+def test_exports_match_header(product):
+    """Every include/*.h is covered: leandvb_b200.h (receive path) and leandvb_b200_tx.h (transmit chain)."""
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["leandvb_b200.h", "leandvb_b200_tx.h"]
     L = product.load()
-    missing = [f for f in sorted(declared) if not hasattr(L, f)]
-    assert not missing, f"declared in include/leandvb_b200.h but not exported: {missing}"
-    assert set(product.EXPORTS) == declared
+    for header, prefix, listed in (("leandvb_b200.h", "ldvb", product.EXPORTS), ("leandvb_b200_tx.h", "ldvbtx", product.TX_EXPORTS)):
+        declared = _declared(header, prefix)
+        assert declared, "no declarations parsed"
+        missing = [f for f in sorted(declared) if not hasattr(L, f)]
+        assert not missing, f"declared in include/{header} but not exported: {missing}"
+        assert set(listed) == declared
+
+
+def test_tx_defaults_and_no_device(product):
+    cfg = product.tx_config()
+    # leandvbtx.cc:69-76 defaults
+    assert (cfg.constellation, cfg.fec, cfg.interp, cfg.decim, cfg.agc) == (1, 0, 2, 1, 0)
+    assert abs(cfg.rolloff - 0.35) < 1e-6 and abs(cfg.rrc_rej - 10) < 1e-6 and cfg.power_db == b"0"
+    if not have_gpu():
+        with pytest.raises(product.LdvbError) as e:
+            product.Transmitter(cfg)
+        assert e.value.code == -4      # LDVB_ENODEV: no CPU fallback
 
 
 def test_abi_and_defaults(product):

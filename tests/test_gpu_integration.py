@@ -29,3 +29,20 @@ def test_reference_scheduler_runs_gpu_runnable(product, oracle, fmt, flags):
     assert n > 1400
     assert np.array_equal(got[:n], want[:n])
     assert 0 <= len(got) - len(want) <= 1
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "leandvbtx_gpu")),
+                    reason="oracle/_ref/leandvbtx_gpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("flags,batch", [(["-f", "6/5", "--power", "37.5", "--agc"], 256),
+                                         (["--cr", "7/8", "-f", "2", "--power", "37.5", "--agc"], 4096),
+                                         (["--const", "8PSK", "--cr", "2/3", "-f", "4"], 100)])
+def test_reference_scheduler_runs_gpu_transmitter(product, oracle, flags, batch):
+    """leantsgen | leandvbtx_gpu (the reference's scheduler driving gpu_dvbs_transmitter) equals
+    leantsgen | leandvbtx (the unmodified reference), bit for bit including the length."""
+    O = oracle
+    ts = subprocess.run([O.ref_bin("leantsgen"), "-c", "1500"], stdout=subprocess.PIPE, check=True).stdout
+    want = subprocess.run([O.ref_bin("leandvbtx"), *flags], input=ts, stdout=subprocess.PIPE, check=True).stdout
+    got = subprocess.run([O.ref_bin("leandvbtx_gpu"), *flags, "--gpu-batch", str(batch)], input=ts,
+                         stdout=subprocess.PIPE, check=True).stdout
+    assert len(got) == len(want) and len(got) > 1000000
+    assert got == want
