@@ -81,6 +81,25 @@ def gen_vector(npackets: int) -> np.ndarray:
     return V.ref_iq(npackets, fmt="f32")
 
 
+def gen_vector_device(npackets: int, dev, torch, P):
+    """The same waveform synthesised in HBM by the B200 transmit chain (include/leandvb_b200_tx.h;
+    bit-identical to leantsgen | leandvbtx, tests/test_gpu_tx.py): numbered TS packets ->
+    randomizer, RS, interleaver, convolutional code, QPSK, RRC x6/5, AGC.  Returns a float32 device
+    tensor of interleaved I/Q."""
+    tx = P.Transmitter(ratio="6/5", power="37.5", agc=True, max_packets=npackets, device=dev.index or 0)
+    ts = torch.empty(npackets * 188, dtype=torch.uint8, device=dev)
+    tx.tsgen_device(0, npackets, ts.data_ptr())
+    cap = tx.max_samples(npackets)
+    iq = torch.empty(2 * cap, dtype=torch.float32, device=dev)
+    n = tx.process_device(ts.data_ptr(), npackets, iq.data_ptr(), cap)
+    torch.cuda.synchronize()
+    tx.close()
+    out = iq[: 2 * n].clone()
+    del iq, ts
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int):
     """Times oracle/_ref/leandvb on `raw` (page-cached file), `replicas` processes at once.
     Returns (MS/s aggregate, TS bytes of one replica)."""
@@ -266,6 +285,8 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-gen", action="store_true", help="synthesise the IQ with the reference binaries on the host "
+                    "instead of the B200 transmit chain (N = 1)")
     ap.add_argument("--shard", default="time", choices=["time", "streams"],
                     help="N > 1: 'time' = ONE stream cut into N time chunks (halo + EDGE over NCCL), "
                          "'streams' = N independent streams (replicas)")
@@ -320,13 +341,23 @@ def main():
     if world > 1 and a.shard == "time":
         return bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P)
 
-    raw = gen_vector(a.packets)
+    vector_check = None
+    if a.cpu_gen:
+        raw = gen_vector(a.packets)
+        iq_dev = torch.from_numpy(raw).to(dev)
+        workload["synthesis"] = "oracle/_ref leantsgen | leandvbtx on the host"
+    else:
+        iq_dev = gen_vector_device(a.packets, dev, torch, P)
+        raw = iq_dev.cpu().numpy()
+        workload["synthesis"] = "B200 transmit chain (ldvbtx_*), bit-identical to leantsgen | leandvbtx"
+        if rank == 0:
+            head = gen_vector(min(a.packets, 2048))          # the unmodified reference transmitter, same packets
+            vector_check = bool(head.size > 1000000 and np.array_equal(head.view(np.uint32), raw[: head.size].view(np.uint32)))
     n = raw.size // 2
     mode = P.RX_FAST if a.mode == "fast" else P.RX_EXACT
     rx = P.Receiver(fmt="f32", resample=True, anf=a.anf, rx_mode=mode, max_batch=n, device=local)
     stream = torch.cuda.current_stream()
     rx.set_stream(stream.cuda_stream)
-    iq_dev = torch.from_numpy(raw).to(dev)
     cap = n // 1900 + 64
     ts_dev = torch.empty(cap * 188, dtype=torch.uint8, device=dev)
 
@@ -453,6 +484,7 @@ def main():
             "cpu_baseline": cpu,
             "ts_packets_per_step": int(npk), "ts_bit_exact_vs_reference": ts_match,
             "e2e_ts_equals_device_resident_ts": e2e_ts_ok,
+            "vector_equals_reference_transmitter_prefix": vector_check,
             "seams": {"total": meas["seams_total"], "repaired": meas["seams_repaired"], "notch_repaired": meas["notch_repaired"]}}
     print(json.dumps(line))
 

@@ -257,10 +257,20 @@ __device__ __forceinline__ float2 guess_from_sums(const NotchApplyArgs &a, const
 #define LDVB_NOTCH_CA 0
 #endif
 constexpr bool kNotchCa = LDVB_NOTCH_CA != 0;
-constexpr int kNTile = 32;
-constexpr int kNPitch = 272;          // row pitch: (32 + 2) cf32, = 16 (mod 128) bytes
-constexpr int kNStages = 2;
-constexpr int kNWarps = 2;
+#ifndef LDVB_NOTCH_TILE
+#define LDVB_NOTCH_TILE 32
+#endif
+#ifndef LDVB_NOTCH_STAGES
+#define LDVB_NOTCH_STAGES 2
+#endif
+#ifndef LDVB_NOTCH_WARPS
+#define LDVB_NOTCH_WARPS 2
+#endif
+constexpr int kNTile = LDVB_NOTCH_TILE;            // 16, 32 or 64 samples per staged tile
+constexpr int kNPitch = (kNTile + 2) * 8;          // row pitch: (tile + 2) cf32, = 16 (mod 128) bytes
+constexpr int kNStages = LDVB_NOTCH_STAGES;        // tiles in flight per lane: kNStages - 1 ahead of the one in use
+constexpr int kNWarps = LDVB_NOTCH_WARPS;
+static_assert(kNPitch % 128 == 16 && kNotchN % kNTile == 0 && kNStages >= 2, "row geometry");
 
 template <int FMT>
 __device__ __forceinline__ float2 row_sample(const unsigned char *row, uint32_t idx, float scale) {
@@ -355,10 +365,11 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   const float k = a.k, omk = fsub(1.0f, a.k), gain = a.gain;
   const bool unit_gain = (gain == 1.0f);
   const bool out16 = (reinterpret_cast<uintptr_t>(a.out) & 15u) == 0;   // carry in front: only 8-byte aligned
-  if (total_tiles) issue(0);
+  // One commit group per tile, kNStages - 1 tiles ahead (empty groups past the end keep the count uniform).
+  for (int s = 0; s < kNStages - 1; ++s) { if ((uint64_t)s < total_tiles) issue(s); else cp_async_commit(); }
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
-    if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
+    if (tile + kNStages - 1 < total_tiles) issue(tile + kNStages - 1); else cp_async_commit();
+    cp_async_wait<kNStages - 1>();
     const int st = (int)(tile % kNStages);   // (a lane only reads the row it copied itself)
     const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
     const int tib = (int)(tile % kTilesPerBlock);

@@ -44,7 +44,10 @@ template <int SAMPLER, int TILE> struct RowCfg { static constexpr int kBytes = (
 #define LDVB_RX_CA 0
 #endif
 constexpr bool kRxCa = LDVB_RX_CA != 0;
-constexpr int kStages = 2;
+#ifndef LDVB_RX_STAGES
+#define LDVB_RX_STAGES 2
+#endif
+constexpr int kStages = LDVB_RX_STAGES;   // tiles in flight per lane (kStages - 1 ahead of the one in use)
 constexpr int kWarpsPerBlock = 4;
 
 struct RxRun {
@@ -290,10 +293,10 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   uint32_t n_out = 0, n_tail = 0, n_head = 0;
   const uint32_t cap = a.span_cap;
 
-  if (total_tiles) issue(0);
+  for (int s = 0; s < kStages - 1; ++s) { if ((uint64_t)s < total_tiles) issue(s); else cp_async_commit(); }
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
-    if (tile + 1 < total_tiles) { issue(tile + 1); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
+    if (tile + kStages - 1 < total_tiles) issue(tile + kStages - 1); else cp_async_commit();
+    cp_async_wait<kStages - 1>();
     const int st = (int)(tile % kStages);   // (a lane only reads the row it copied itself)
     const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
     const int tic = (int)(tile % kTilesPerChunk);

@@ -600,7 +600,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     h->rxp.rrc_coeffs = h->d_rrc.as<float>();
   }
   // Host batches larger than this are pipelined (copy/compute overlap); push_sub_batch overrides.
-  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : (uint64_t)16 << 20;
+  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : (uint64_t)24 << 20;
 
   // ---- stream buffers
   const uint64_t M = c.max_batch;
@@ -2133,9 +2133,14 @@ static int push_pipelined(ldvb_handle *h, const uint8_t *host, size_t n) {
       CK(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
     }
   }
-  const uint64_t nsub = (n + sub - 1) / sub;
+  // Even split (multiples of 4096 samples): a short last sub-batch would finish its copy long
+  // before the chain of the one in front of it is done, and the chain's fixed cost (~1.9 ms of
+  // serial-recurrence latency) would show twice at the end.
+  const uint64_t nsub0 = (n + sub - 1) / sub;
+  const uint64_t each = std::min<uint64_t>(sub, ((n + nsub0 - 1) / nsub0 + 4095) / 4096 * 4096);
+  const uint64_t nsub = (n + each - 1) / each;
   auto issue = [&](uint64_t i) -> int {
-    const uint64_t off = i * sub, m = std::min<uint64_t>(sub, n - off);
+    const uint64_t off = i * each, m = std::min<uint64_t>(each, n - off);
     CK(cudaMemcpyAsync(h->d_stage[i & 1].p, host + off * bps, m * bps, cudaMemcpyHostToDevice, h->copy_st));
     CK(cudaEventRecord(h->copy_done[i & 1], h->copy_st));
     return LDVB_OK;
@@ -2145,7 +2150,7 @@ static int push_pipelined(ldvb_handle *h, const uint8_t *host, size_t n) {
   for (uint64_t i = 0; i < nsub; ++i) {
     CK(cudaStreamWaitEvent(h->st, h->copy_done[i & 1], 0));
     if (i + 1 < nsub && (rc = issue(i + 1))) return rc;   // the other buffer is idle: run_chain is synchronous
-    const uint64_t m = std::min<uint64_t>(sub, n - i * sub);
+    const uint64_t m = std::min<uint64_t>(each, n - i * each);
     uint64_t got = 0;
     if ((rc = run_chain(h, h->d_stage[i & 1].p, true, m, h->d_ts.as<uint8_t>(), h->ts_cap, &got))) return rc;
     if ((rc = push_collect(h, got))) return rc;

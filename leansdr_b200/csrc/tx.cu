@@ -209,28 +209,50 @@ __global__ void k_tx_amp2(const float2 *x, uint64_t nchunks, float *amp2) {
   amp2[c] = __fdiv_rn(acc, (float)kAgcChunk);
 }
 
-// simple_agc::run (sdr.h:260-262): the estimate advances once per chunk; one lane walks it,
-// the warp prefetches 32 chunk powers at a time.
-__global__ void k_tx_agc(const float *amp2, uint64_t nchunks, float bw, float out_rms, float *estimated_io, float *gain) {
-  const int lane = threadIdx.x;
-  float est = *estimated_io;
+// simple_agc::run (sdr.h:260-262): the estimate advances once per chunk.  One CTA: the threads
+// stage 1024 chunk powers (and their products with bw) in shared memory, thread 0 walks the
+// two-operation chain est = est*(1-bw) + amp2*bw over them, the threads turn the 1024 estimates
+// into gains.  `if (!estimated) estimated = amp2` can only fire while the estimate is zero; once
+// it is a normal positive number it stays one (amp2 >= 0, 1-bw >= 1/2), so the test leaves the chain.
+constexpr int kAgcTile = 1024;
+__global__ void __launch_bounds__(256) k_tx_agc(const float *amp2, uint64_t nchunks, float bw, float out_rms,
+                                                float *estimated_io, float *gain) {
+  __shared__ float s_a[kAgcTile], s_ab[kAgcTile], s_e[kAgcTile];
+  __shared__ float s_est;
   const float omb = fsub(1.0f, bw);
-  for (uint64_t base = 0; base < nchunks; base += 32) {
-    const float mine = (base + lane < nchunks) ? amp2[base + lane] : 0.f;
-    float g = 0.f;
-    const int m = (int)min((uint64_t)32, nchunks - base);
-    for (int j = 0; j < m; ++j) {
-      const float a2 = __shfl_sync(0xffffffffu, mine, j);
-      if (est == 0.0f) est = a2;
-      est = fadd(fmul(est, omb), fmul(a2, bw));
-      if (lane == j) g = est;
+  const bool safe = bw <= 0.5f && bw >= 0.0f;
+  if (threadIdx.x == 0) s_est = *estimated_io;
+  for (uint64_t base = 0; base < nchunks; base += kAgcTile) {
+    const int m = (int)min((uint64_t)kAgcTile, nchunks - base);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const float a = amp2[base + i];
+      s_a[i] = a; s_ab[i] = fmul(a, bw);
     }
-    if (base + lane < nchunks) {
-      const float e = g;
-      gain[base + lane] = (e != 0.0f) ? __fdiv_rn(out_rms, __fsqrt_rn(e)) : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float est = s_est;
+      int i = 0;
+      while (i < m) {
+        if (safe && est >= 1e-30f && est <= 3e38f) {
+          const int stop = min(m, i + 32);
+#pragma unroll 8
+          for (; i < stop; ++i) { est = fadd(fmul(est, omb), s_ab[i]); s_e[i] = est; }
+        } else {
+          if (est == 0.0f) est = s_a[i];
+          est = fadd(fmul(est, omb), s_ab[i]);
+          s_e[i] = est; ++i;
+        }
+      }
+      s_est = est;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const float e = s_e[i];
+      gain[base + i] = (e != 0.0f) ? __fdiv_rn(out_rms, __fsqrt_rn(e)) : 0.f;
+    }
+    __syncthreads();
   }
-  if (lane == 0) *estimated_io = est;
+  if (threadIdx.x == 0) *estimated_io = s_est;
 }
 
 __global__ void k_tx_scale(const float2 *x, const float *gain, uint64_t n, float2 *out) {
@@ -440,7 +462,7 @@ int tx_process(ldvbtx_handle *h, const uint8_t *ts_dev, uint64_t n, float2 *out,
     if (p.chunks) {
       k_tx_amp2<<<(unsigned)((p.chunks + 127) / 128), 128, 0, h->st>>>(raw, p.chunks, h->d_amp2.as<float>());
       TCK(cudaGetLastError());
-      k_tx_agc<<<1, 32, 0, h->st>>>(h->d_amp2.as<float>(), p.chunks, h->bw, h->out_rms, h->d_est.as<float>(),
+      k_tx_agc<<<1, 256, 0, h->st>>>(h->d_amp2.as<float>(), p.chunks, h->bw, h->out_rms, h->d_est.as<float>(),
                                     h->d_gain.as<float>());
       TCK(cudaGetLastError());
       const uint64_t ns = p.chunks * kAgcChunk;
