@@ -253,10 +253,6 @@ __device__ __forceinline__ float2 guess_from_sums(const NotchApplyArgs &a, const
 // per tile the warp stages every lane's next 64 raw samples in a private
 // shared-memory row (cooperative 16-byte cp.async copies, contiguous within a
 // row, double buffered); lanes convert on the fly and stream their results out.
-#ifndef LDVB_NOTCH_CA
-#define LDVB_NOTCH_CA 0
-#endif
-constexpr bool kNotchCa = LDVB_NOTCH_CA != 0;
 #ifndef LDVB_NOTCH_TILE
 #define LDVB_NOTCH_TILE 32
 #endif
@@ -271,6 +267,8 @@ constexpr int kNPitch = (kNTile + 2) * 8;          // row pitch: (tile + 2) cf32
 constexpr int kNStages = LDVB_NOTCH_STAGES;        // tiles in flight per lane: kNStages - 1 ahead of the one in use
 constexpr int kNWarps = LDVB_NOTCH_WARPS;
 static_assert(kNPitch % 128 == 16 && kNotchN % kNTile == 0 && kNStages >= 2, "row geometry");
+// dynamic shared memory: [input rows: warps x stages x 32 x pitch | table tiles: warps x stages x slots x tile | output tiles]
+constexpr size_t kNotchSmemIn = (size_t)kNWarps * kNStages * 32 * kNPitch + (size_t)kNWarps * kNStages * 4 * kNTile * 8;
 
 template <int FMT>
 __device__ __forceinline__ float2 row_sample(const unsigned char *row, uint32_t idx, float scale) {
@@ -344,20 +342,86 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
     lead = (uint32_t)(idx - al);
     src = part + al * bps;
   };
-  constexpr int n16_max = (int)(((kNTile + align_elems) * bps + 15u) / 16u);
+  constexpr int kRowChunks = (int)(kNTile * bps / 16u);      // whole 16-byte pieces of a row
+  constexpr int kRowsPerCopy = 32 / kRowChunks;              // rows covered by one warp-wide copy
+  static_assert(kRowChunks >= 1 && 32 % kRowChunks == 0, "row geometry");
+  // The e^{j theta} tile of the warp: the 32 lanes walk 32 different blocks but sit at the SAME
+  // offset inside them, so they all need the same kNTile table entries per slot.  When the
+  // active lanes agree on the table (always, except in a warp that straddles a bin change) the
+  // tile is staged once per warp with the rows (kNTile * 8 bytes per slot, 16 B per lane) and
+  // read back as shared-memory broadcasts: the table leaves the dependent-load path (ncu: the
+  // products waiting on these LDGs were 45 % of the kernel's stall samples).
+  float2 *wtab = reinterpret_cast<float2 *>(smem + (size_t)kNWarps * kNStages * 32 * kNPitch) +
+                 (size_t)warp * kNStages * kNotchMaxSlots * kNTile;
+  uint32_t staged_mask = 0;           // bit st: stage st holds a valid table tile (warp uniform)
+  int epi = p.epoch;                  // epoch cursor of the issue stream
+  uint32_t tixi[NSLOTS];
+#pragma unroll
+  for (int s = 0; s < NSLOTS; ++s) tixi[s] = have ? a.epochs[epi].table_index[s] : 0u;
   // Each lane fetches ITS row with 16-byte asynchronous copies (LDGSTS).
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kNStages);
     const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
+    const int tibi = (int)(tile % kTilesPerBlock);
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
+    const unsigned char *src = nullptr; uint32_t lead = 0;
     if (active) {
-      const unsigned char *src; uint32_t lead;
-      locate((uint64_t)blk * kNotchN + (tile % kTilesPerBlock) * kNTile, src, lead);
-      const int n16 = (int)(((lead + kNTile) * bps + 15u) / 16u);
-      unsigned char *dst = smem + row_off + (size_t)st * 32 * kNPitch;
+      locate((uint64_t)blk * kNotchN + (uint64_t)tibi * kNTile, src, lead);
+      if (tibi == 0) {
+        const int before = epi;
+        while (epi + 1 < a.nepochs && a.epochs[epi + 1].first_block <= (uint64_t)blk) ++epi;
+        if (epi != before) {
 #pragma unroll
-      for (int q = 0; q < n16_max; ++q)
-        if (q < n16) { if (kNotchCa) cp_async16_ca(dst + q * 16, src + q * 16); else cp_async16(dst + q * 16, src + q * 16); }
+          for (int s = 0; s < NSLOTS; ++s) tixi[s] = a.epochs[epi].table_index[s];
+        }
+      }
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (act) {
+      // Rows are fetched by the WARP, not by their owners: kRowChunks lanes cover one row with
+      // consecutive 16-byte pieces, so one LDGSTS touches 32 / kRowChunks rows (2 x 128-byte lines
+      // each) instead of 32 different lines -- the per-lane version kept the L1 -> crossbar request
+      // path 57 % busy (ncu, round 1), which is what bounded the kernel.  Row addresses travel by
+      // shuffle; the odd 16-byte piece of a row that does not start on a 16-byte boundary is
+      // fetched by its owner.
+      const uint32_t slo = (uint32_t)reinterpret_cast<uintptr_t>(src), shi = (uint32_t)(reinterpret_cast<uintptr_t>(src) >> 32);
+      const int q = lane % kRowChunks, sub = lane / kRowChunks;
+      unsigned char *stage_base = smem + (size_t)warp * kNStages * 32 * kNPitch + (size_t)st * 32 * kNPitch;
+#pragma unroll
+      for (int r = 0; r < 32; r += kRowsPerCopy) {
+        const int row = r + sub;
+        const uint32_t lo = __shfl_sync(0xffffffffu, slo, row), hi = __shfl_sync(0xffffffffu, shi, row);
+        if ((act >> row) & 1u) {
+          const unsigned char *rs = reinterpret_cast<const unsigned char *>(((uintptr_t)hi << 32) | lo);
+          cp_async16(stage_base + (size_t)row * kNPitch + q * 16, rs + q * 16);
+        }
+      }
+      if (active && (lead + kNTile) * bps > (uint32_t)kRowChunks * 16u)
+        cp_async16(stage_base + (size_t)lane * kNPitch + kRowChunks * 16, src + kRowChunks * 16);
+    }
+    // Same tables on every active lane?  (all lanes of the warp are here: no divergence)
+    bool uniform = act != 0;
+    uint32_t lead_tix[NSLOTS];
+    if (act) {
+      const int leader = __ffs(act) - 1;
+      bool same = true;
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) {
+        lead_tix[s] = __shfl_sync(0xffffffffu, tixi[s], leader);
+        same = same && (!active || tixi[s] == lead_tix[s]);
+      }
+      uniform = __all_sync(0xffffffffu, same);
+    }
+    if (uniform) {
+      staged_mask |= 1u << st;
+      constexpr int kChunks = kNTile * 8 / 16;       // 16-byte pieces per slot
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s)
+        for (int q = lane; q < kChunks; q += 32)
+          cp_async16_ca(reinterpret_cast<unsigned char *>(wtab + ((size_t)st * kNotchMaxSlots + s) * kNTile) + q * 16,
+                        reinterpret_cast<const unsigned char *>(a.expj_tables + (size_t)lead_tix[s] * kNotchN + (size_t)tibi * kNTile) + q * 16);
+    } else {
+      staged_mask &= ~(1u << st);
     }
     cp_async_commit();
   };
@@ -370,10 +434,14 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + kNStages - 1 < total_tiles) issue(tile + kNStages - 1); else cp_async_commit();
     cp_async_wait<kNStages - 1>();
-    const int st = (int)(tile % kNStages);   // (a lane only reads the row it copied itself)
+    __syncwarp();                            // the table tile was copied by other lanes (rows are private)
+    const int st = (int)(tile % kNStages);
     const int64_t blk = base + (int64_t)(tile / kTilesPerBlock);
     const int tib = (int)(tile % kTilesPerBlock);
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
+    const bool write = active && ((uint64_t)blk >= own_begin);
+    float2 *outp = a.out + (uint64_t)(active ? blk : 0) * kNotchN + (uint64_t)tib * kNTile;
+    unsigned char *orow_base = smem + kNotchSmemIn + (size_t)warp * 32 * kNPitch;   // the warp's output tile
     if (active) {
       if (tib == 0) {
         // Block start: entry snapshot, epoch switch / resets (sdr.h:97-109).
@@ -388,11 +456,16 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
             if (a.epochs[ep].reset[s]) { er[s] = 0.f; ei[s] = 0.f; }
         }
       }
-      const bool write = ((uint64_t)blk >= own_begin);
-      const float2 *tab[NSLOTS];
+      const bool staged = (staged_mask >> st) & 1u;
+      const float2 *tab[NSLOTS];       // this lane's table in global memory (used when the tile is not staged)
 #pragma unroll
-      for (int s = 0; s < NSLOTS; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
-      float2 *outp = a.out + (uint64_t)blk * kNotchN + (uint64_t)tib * kNTile;
+      for (int s = 0; s < NSLOTS; ++s) tab[s] = nullptr;
+      if (!staged) {
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
+      }
+      const float4 *stab = reinterpret_cast<const float4 *>(wtab + (size_t)st * kNotchMaxSlots * kNTile);   // shared
+      float4 *myout = reinterpret_cast<float4 *>(orow_base + (size_t)lane * kNPitch);
       uint32_t lead; { const unsigned char *unused; locate((uint64_t)blk * kNotchN + (uint64_t)tib * kNTile, unused, lead); }
       const unsigned char *myrow = smem + row_off + (size_t)st * 32 * kNPitch;
       // Eight samples per step: loads and the products that do not depend on the
@@ -423,10 +496,20 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
 #pragma unroll
           for (int j = 0; j < U; ++j) x[j] = row_sample<FMT>(myrow, lead + n0 + j, a.scale);
         }
+        if (staged) {                  // warp-uniform: shared-memory broadcasts, two entries per load
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
+          for (int s = 0; s < NSLOTS; ++s)
 #pragma unroll
-          for (int s = 0; s < NSLOTS; ++s) e[j][s] = __ldg(tab[s] + n0 + j);
+            for (int j = 0; j < U; j += 2) {
+              const float4 v = stab[(s * kNTile + n0 + j) >> 1];
+              e[j][s] = make_float2(v.x, v.y); e[j + 1][s] = make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+#pragma unroll
+            for (int s = 0; s < NSLOTS; ++s) e[j][s] = __ldg(tab[s] + n0 + j);
+          }
         }
 #pragma unroll
         for (int j = 0; j < U; ++j)
@@ -457,14 +540,29 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
             if (!unit_gain) { outr = fmul(gain, outr); outi = fmul(gain, outi); }
             o[j] = make_float2(outr, outi);
           }
-          if (out16) {   // 16-byte stores: half the store wavefronts
+          // into the lane's row of the warp's output tile (conflict-free pitch); the warp writes it out below
 #pragma unroll
-            for (int j = 0; j < U; j += 2)
-              st_stream(reinterpret_cast<float4 *>(outp + n0 + j), make_float4(o[j].x, o[j].y, o[j + 1].x, o[j + 1].y));
-          } else {
+          for (int j = 0; j < U; j += 2) myout[(n0 + j) >> 1] = make_float4(o[j].x, o[j].y, o[j + 1].x, o[j + 1].y);
+        }
+      }
+    }
+    // Output rows leave through the warp as well: 16 lanes per 256-byte row, two rows per store
+    // instruction (full 128-byte lines instead of 32 scattered 16-byte pieces).
+    const unsigned wmask = __ballot_sync(0xffffffffu, write);
+    if (wmask) {
+      __syncwarp();
+      const uint32_t olo = (uint32_t)reinterpret_cast<uintptr_t>(outp), ohi = (uint32_t)(reinterpret_cast<uintptr_t>(outp) >> 32);
+      constexpr int kOutChunks = kNTile * 8 / 16, kOutRows = 32 / kOutChunks;
+      const int q = lane % kOutChunks, sub = lane / kOutChunks;
 #pragma unroll
-            for (int j = 0; j < U; ++j) st_stream(outp + n0 + j, o[j]);
-          }
+      for (int r = 0; r < 32; r += kOutRows) {
+        const int row = r + sub;
+        const uint32_t lo = __shfl_sync(0xffffffffu, olo, row), hi = __shfl_sync(0xffffffffu, ohi, row);
+        if ((wmask >> row) & 1u) {
+          const float4 v = *reinterpret_cast<const float4 *>(orow_base + (size_t)row * kNPitch + q * 16);
+          unsigned char *dst = reinterpret_cast<unsigned char *>(((uintptr_t)hi << 32) | lo) + q * 16;
+          if (out16) st_stream(reinterpret_cast<float4 *>(dst), v);
+          else { st_stream(reinterpret_cast<float2 *>(dst), make_float2(v.x, v.y)); st_stream(reinterpret_cast<float2 *>(dst) + 1, make_float2(v.z, v.w)); }
         }
       }
     }
@@ -479,7 +577,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   }
 }
 
-constexpr size_t kNotchSmem = (size_t)kNWarps * kNStages * 32 * kNPitch;
+constexpr size_t kNotchSmem = kNotchSmemIn + (size_t)kNWarps * 32 * kNPitch;   // + one output tile per warp
 
 template <int FMT, int NSLOTS>
 cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, uint32_t nlist,
@@ -489,10 +587,9 @@ cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, ui
     cudaError_t e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kNotchSmem);
     if (e != cudaSuccess) return e;
-    // Four resident CTAs per SM cover the whole grid at the bench size; asking for no more
-    // shared memory than that leaves ~64 KB of L1 for the e^{j theta} tables (32 KB per bin),
-    // which every lane reads once per sample (ncu: 29 % L1 hit rate with the default split).
-    static const int carve = [] { const char *v = getenv("LDVB_NOTCH_CARVEOUT"); return v ? atoi(v) : 72; }();
+    // Four resident CTAs per SM (4 x 55 KB of rows, table tiles and output tiles) cover the whole
+    // grid at the bench size; the e^{j theta} tables are staged in shared memory, so L1 is not needed.
+    static const int carve = [] { const char *v = getenv("LDVB_NOTCH_CARVEOUT"); return v ? atoi(v) : 100; }();
     if (carve >= 0 && carve <= 100) {
       e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
       if (e != cudaSuccess) return e;

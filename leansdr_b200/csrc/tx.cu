@@ -233,10 +233,15 @@ __global__ void __launch_bounds__(256) k_tx_agc(const float *amp2, uint64_t nchu
       float est = s_est;
       int i = 0;
       while (i < m) {
-        if (safe && est >= 1e-30f && est <= 3e38f) {
-          const int stop = min(m, i + 32);
-#pragma unroll 8
-          for (; i < stop; ++i) { est = fadd(fmul(est, omb), s_ab[i]); s_e[i] = est; }
+        if (safe && est >= 1e-30f && est <= 3e38f && i + 16 <= m) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = s_ab[i + j];           // loads off the chain
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { est = fadd(fmul(est, omb), v[j]); v[j] = est; }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s_e[i + j] = v[j];
+          i += 16;
         } else {
           if (est == 0.0f) est = s_a[i];
           est = fadd(fmul(est, omb), s_ab[i]);
