@@ -273,16 +273,29 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   const uint32_t row_off = (uint32_t)((threadIdx.x >> 5) * kStages * 32 * kRowBytes + lane * kRowBytes);
   const uint64_t total_tiles = iters * kTilesPerChunk;
   constexpr int kChunks16 = kRowBytes / 16;
-  // Each lane fetches ITS row: kChunks16 x 16 B asynchronous copies (LDGSTS), no index math.
+  // Rows are fetched by the WARP: the 32 x kChunks16 16-byte pieces of a tile are dealt to the lanes
+  // in row-major order, so one LDGSTS covers 32 / kChunks16 (~3.5) consecutive rows -- a few whole
+  // 128-byte lines -- instead of 32 different lines (the per-lane version kept the L1 -> crossbar
+  // request path 45 % busy, ncu round 1).  Row addresses travel by shuffle.
   auto issue = [&](uint64_t tile) {
     const int st = (int)(tile % kStages);
     const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
-    if (active) {
-      const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + (uint64_t)c * kRxChunk + (tile % kTilesPerChunk) * kTile);
-      unsigned char *dst = smem_all + row_off + (size_t)st * 32 * kRowBytes;
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (act) {
+      const uintptr_t src = active ? reinterpret_cast<uintptr_t>(a.x + (uint64_t)c * kRxChunk + (tile % kTilesPerChunk) * kTile) : 0;
+      const uint32_t slo = (uint32_t)src, shi = (uint32_t)(src >> 32);
+      unsigned char *stage_base = smem_all + (size_t)(threadIdx.x >> 5) * kStages * 32 * kRowBytes + (size_t)st * 32 * kRowBytes;
 #pragma unroll
-      for (int q = 0; q < kChunks16; ++q) { if (kRxCa) cp_async16_ca(dst + q * 16, src + q * 16); else cp_async16(dst + q * 16, src + q * 16); }
+      for (int i = 0; i < kChunks16; ++i) {
+        const int piece = i * 32 + lane, row = piece / kChunks16, q = piece % kChunks16;
+        const uint32_t lo = __shfl_sync(0xffffffffu, slo, row), hi = __shfl_sync(0xffffffffu, shi, row);
+        if ((act >> row) & 1u) {
+          const unsigned char *rs = reinterpret_cast<const unsigned char *>(((uintptr_t)hi << 32) | lo);
+          if (kRxCa) cp_async16_ca(stage_base + (size_t)row * kRowBytes + q * 16, rs + q * 16);
+          else cp_async16(stage_base + (size_t)row * kRowBytes + q * 16, rs + q * 16);
+        }
+      }
     }
     cp_async_commit();
   };
@@ -297,7 +310,8 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   for (uint64_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + kStages - 1 < total_tiles) issue(tile + kStages - 1); else cp_async_commit();
     cp_async_wait<kStages - 1>();
-    const int st = (int)(tile % kStages);   // (a lane only reads the row it copied itself)
+    __syncwarp();                           // rows were copied by other lanes
+    const int st = (int)(tile % kStages);
     const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
     const int tic = (int)(tile % kTilesPerChunk);
     const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;

@@ -901,6 +901,12 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // (0.998^n decay below one ulp), measured in DESIGN.md.
   a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 32767) / 32768));
   a.warm_blocks = 2;   // exact blocks after the parallel weighted-sum guess (merge: median 1 Ki, max ~3 Ki samples)
+  {  // tuning knobs (experiments): LDVB_NOTCH_SEG = blocks per segment, LDVB_NOTCH_WARM = warm-up blocks
+    static const int seg_env = [] { const char *e = getenv("LDVB_NOTCH_SEG"); return e ? atoi(e) : 0; }();
+    static const int warm_env = [] { const char *e = getenv("LDVB_NOTCH_WARM"); return e ? atoi(e) : 0; }();
+    if (seg_env > 0) a.seg_blocks = (uint32_t)seg_env;
+    if (warm_env > 0) a.warm_blocks = (uint32_t)warm_env;
+  }
   a.nsegs = (uint32_t)((nblocks + a.seg_blocks - 1) / a.seg_blocks);
   a.state_in = h->d_notch_state.as<NotchState>();
   a.seg_entry = h->d_notch_entry.as<float2>();
