@@ -98,7 +98,7 @@ typedef struct ldvb_config {
   int32_t  fec;              /* LDVB_FEC*            --cr                    */
   int32_t  viterbi;          /* --viterbi                                    */
   int32_t  hard_metric;      /* --hard-metric                                */
-  int32_t  fastlock;         /* --fastlock (not supported yet: LDVB_EINVAL)  */
+  int32_t  fastlock;         /* --fastlock (dvb.h:391-454, 781-796; leandvb.cc:540-565) */
   int32_t  allow_drift;      /* --drift                                      */
   float    Ftune;            /* --tune Hz                                    */
   float    Finfo;            /* measurement rate, Hz (leandvb.cc:117, 502)   */
@@ -113,7 +113,9 @@ typedef struct ldvb_config {
   int32_t  cnr;              /* --cnr: cnr_fft (sdr.h:1273-1345), needs Fs > 4 Fm */
   int32_t  spectrum;         /* spectrum (sdr.h:1347-1404); leandvb always runs it
                                 (leandvb.cc:333-343), ldvb_config_default sets 1 */
-  int32_t  reserved[4];
+  int32_t  vber;             /* rate_estimator on the RS decoder's counts (leandvb.cc:583-587): values
+                                are queued for ldvb_pull_vber                                      */
+  int32_t  reserved[3];
 } ldvb_config;
 
 typedef struct ldvb_handle ldvb_handle;
@@ -247,6 +249,11 @@ int ldvb_set_rx_state(ldvb_handle *h, const uint32_t w[22]);
  * whenever its scheduler happens to run the block). */
 int ldvb_pull_cnr(ldvb_handle *h, float *dst, size_t cap, size_t *n);
 int ldvb_pull_spectrum(ldvb_handle *h, float *dst, size_t cap_rows, size_t *n_rows);
+/* What the reference writes to p_vber: rate_estimator<float> (generic.h:272-305) over rs_decoder's
+ * (bits corrected, bits processed) counts with sample_size = max(Fm/2, 50000) (leandvb.cc:583-587).
+ * The reference adds the counts of one rs_decoder::run() call at a time (1..4 packets with its
+ * default buffers); here the threshold is tested after every packet.  Needs cfg.vber. */
+int ldvb_pull_vber(ldvb_handle *h, float *dst, size_t cap, size_t *n);
 
 /* ------------------------------------------------------------ time sharding
  * one stream, N handles (one per GPU, one process each).  The

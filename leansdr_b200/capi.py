@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("allow_drift", C.c_int32), ("Ftune", C.c_float), ("Finfo", C.c_float),
         ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
         ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
-        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -68,7 +68,7 @@ EXPORTS = [
     "ldvb_table", "ldvb_host_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
     "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
     "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
-    "ldvb_pull_cnr", "ldvb_pull_spectrum",
+    "ldvb_pull_cnr", "ldvb_pull_spectrum", "ldvb_pull_vber",
     "ldvb_edge_size", "ldvb_shard_min_halo", "ldvb_shard_detect", "ldvb_shard_front", "ldvb_shard_back",
 ]
 
@@ -127,6 +127,7 @@ def load():
     L.ldvb_get_profile.argtypes = [vp, C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]
     L.ldvb_pull_cnr.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.ldvb_pull_spectrum.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.ldvb_pull_vber.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.ldvb_edge_size.restype = sz
     L.ldvb_shard_min_halo.restype = sz
     L.ldvb_shard_min_halo.argtypes = [vp]
@@ -151,7 +152,7 @@ def default_config(**kw) -> Config:
             cfg.sampler = SAMPLER[v] if isinstance(v, str) else v
         elif k == "sub_batch":
             cfg.push_sub_batch = int(v)
-        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps"):
+        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps", "vber"):
             setattr(cfg, k, int(v))
         else:
             setattr(cfg, k, v)
@@ -295,6 +296,12 @@ class Receiver:
         """p_cnr: one C/N value (dB) per second of signal (--cnr)."""
         out = np.zeros(cap, np.float32); n = C.c_size_t(0)
         self._ck(self.L.ldvb_pull_cnr(self.h, _p(out), cap, C.byref(n)), "ldvb_pull_cnr")
+        return out[: n.value]
+
+    def pull_vber(self, cap: int = 4096) -> np.ndarray:
+        """p_vber: rate_estimator over the RS decoder's counts (needs vber=True)."""
+        out = np.zeros(cap, np.float32); n = C.c_size_t(0)
+        self._ck(self.L.ldvb_pull_vber(self.h, _p(out), cap, C.byref(n)), "ldvb_pull_vber")
         return out[: n.value]
 
     def pull_spectrum(self, cap_rows: int = 1024) -> np.ndarray:

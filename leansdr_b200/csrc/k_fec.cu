@@ -88,6 +88,20 @@ k_deconv_tiled(DeconvArgs a, uint64_t nsym) {
     const uint32_t r_hi = __funnelshift_l(mid, hi, sh), r_lo = __funnelshift_l(lo, mid, sh);
     return ((uint64_t)r_hi << 32) | r_lo;
   };
+  if (a.err_out) {
+    // readerrors (dvb.h:391-412): every group whose first bit lies in this CTA's bytes, all pp bits of it.
+    unsigned err = 0;
+    for (uint32_t t = threadIdx.x; t < nb; t += blockDim.x) {
+      const int64_t lo = max((int64_t)8 * (b0 + t), (int64_t)a.n_out), hi = (int64_t)8 * (b0 + t) + 8;
+      for (int64_t g = (lo - a.n_out + pp - 1) / pp; a.n_out + g * pp < hi; ++g) {
+        const uint64_t reg = reg_at(k0 + g * half);
+        for (int b = pp - 1; b >= 0; --b) err += par64(reg & a.deconv[b]) ^ par64(reg & a.deconv2[b]);
+      }
+    }
+    for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+    if ((threadIdx.x & 31) == 0 && err) atomicAdd(a.err_out, (unsigned long long)err);
+    return;
+  }
   for (uint32_t t = threadIdx.x; t < nb; t += blockDim.x) {
     const uint64_t j = b0 + t;
     unsigned byte = 0;
@@ -261,6 +275,27 @@ k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_in,
     // sees two wraps inside one run() call).
     uint64_t pos = 0;
     const uint64_t chunk = 204 * 8;
+    if (st.fastlock) {
+      // run_searching_fast (dvb.h:781-796): at every resync_period-th packet position all eight
+      // bit phases are tried in order; the position advances by ONE packet.
+      bool locked = false;
+      while (nbytes - pos >= chunk + 1) {
+        if (st.resync_phase == 0) {
+          for (st.bitphase = 0; st.bitphase <= 7; ++st.bitphase) {
+            const int skip = sync_search_window(bytes, pos, st, &s_best, s_pol, s_ph);
+            if (skip) { pos += skip; event(1, pos); locked = true; break; }
+          }
+          if (locked) break;
+        }
+        pos += 204;
+        if (++st.resync_phase >= st.resync_period) st.resync_phase = 0;
+      }
+      r.consumed = pos;
+      if (threadIdx.x != 0) return;
+      r.st = st;
+      *res = r;
+      return;
+    }
     while (nbytes - pos >= chunk + 1) {
       const int skip = sync_search_window(bytes, pos, st, &s_best, s_pol, s_ph);
       if (skip) {

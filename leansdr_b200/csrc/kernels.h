@@ -238,6 +238,11 @@ struct DeconvArgs {
   int punctperiod, punctweight;
   uint64_t deconv[8];
   uint8_t *out;
+  // --fastlock (dvb.h:391-412, 428-442): when err_out is set the kernel writes no bytes; it counts,
+  // over every bit group that STARTS inside the window, the bits on which the alternate polynomials
+  // deconv2 disagree with deconv (readerrors on the auxiliary register reg_in/n_in/n_out).
+  uint64_t deconv2[8];
+  unsigned long long *err_out;
 };
 // carry_out (device, 5 x uint64): register, n_in, accumulator, n_out, symbols consumed.
 cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t nsym, uint64_t *carry_out, cudaStream_t st);
@@ -266,7 +271,9 @@ struct SyncState {
   uint32_t lock_timeleft;
   uint64_t locktime;
   int32_t report_state;
-  int32_t pad;
+  int32_t fastlock;          // run_searching_fast instead of run_searching (dvb.h:751, 781-796)
+  int32_t resync_period;     // dvb.h:717: search every resync_period-th packet position
+  int32_t resync_phase;
 };
 
 // Outcome of one pass of the MPEG sync tracker over the byte stream.

@@ -122,6 +122,7 @@ struct ldvb_handle {
   uint32_t rx_max_spans = 1;
   double rx_sym_per_sample = 1;
   HypState hyp[4];
+  HypState hyp2[4];          // --fastlock: auxiliary registers in2/n_in2/n_out2 (dvb.h:303-306)
   int locked = 0, skip = 0;
   DevBuf d_deconv_carry;
   // Viterbi (viterbi_sync)
@@ -146,6 +147,11 @@ struct ldvb_handle {
   uint64_t meas_carry_count = 0;   // samples kept from the previous batch (< 4096)
   uint64_t meas_abs_next = 0;      // absolute index of the next new sample
   std::vector<float> cnr_queue, spec_queue;
+  // rate_estimator<float> (generic.h:272-305) on the RS counts: accumulators and queued ratios
+  std::vector<float> vber_queue;
+  int64_t vber_num = 0, vber_den = 0;
+  int vber_sample = 50000;
+  std::vector<int32_t> vber_flags;
 
   // ---- time-sharded mode (ldvb_shard_*): what the front stage leaves for the back stage
   struct Shard {
@@ -357,6 +363,7 @@ void reset_carry(ldvb_handle *h) {
     cudaMemcpy(h->d_taps.p, h->fir_shifted.data(), h->fir_shifted.size() * 4, cudaMemcpyHostToDevice);
   }
   for (HypState &s : h->hyp) s = HypState();
+  for (HypState &s : h->hyp2) s = HypState();
   h->locked = 0; h->skip = 0;
   if (h->d_vit_state.p) {   // viterbi_dec constructor: metrics 0, paths 0 (viterbi.h:133-145)
     cudaMemset(h->d_vit_state.p, 0, h->d_vit_state.bytes);
@@ -365,6 +372,8 @@ void reset_carry(ldvb_handle *h) {
   memset(&h->sync, 0, sizeof h->sync);
   h->sync.report_state = 1;
   h->sync.phase8 = -1;
+  h->sync.fastlock = h->cfg.fastlock ? 1 : 0;    // leandvb.cc:565
+  h->sync.resync_period = 1;                     // dvb.h:729 (and leandvb.cc:553 with --fastlock)
   h->derand_pos = 0;
   h->ts_queue_rd = h->ts_queue_wr = 0;
   memset(&h->meas, 0, sizeof h->meas);
@@ -374,6 +383,8 @@ void reset_carry(ldvb_handle *h) {
   }
   h->meas_carry_count = 0; h->meas_abs_next = 0;
   h->cnr_queue.clear(); h->spec_queue.clear();
+  h->vber_queue.clear(); h->vber_num = h->vber_den = 0;
+  h->vber_sample = std::max(50000, (int)(h->cfg.Fm / 2));   // leandvb.cc:585-587
 }
 
 void rx_setup(ldvb_handle *h) {
@@ -513,7 +524,6 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     return code;
   };
   if (c.input_format < 0 || c.input_format > LDVB_FMT_F32) return bail(LDVB_EINVAL, "bad input_format");
-  if (c.fastlock) return bail(LDVB_EINVAL, "--fastlock is not supported");
   if (c.cnr && c.Fm / c.Fs > 0.25f) return bail(LDVB_EINVAL, "CNR estimator requires Fsampling > 4x Fsignal");   // sdr.h:1283-1284
   if (c.sampler < 0 || c.sampler > 2) return bail(LDVB_EINVAL, "bad sampler");
   if (c.anf < 0 || c.anf > kNotchMaxSlots) return bail(LDVB_EINVAL, "anf must be 0..4");
@@ -643,7 +653,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
       h->d_rx_off.alloc(8 * ((size_t)nsp + 1)) == cudaSuccess && h->d_rx_skip.alloc(4 * (size_t)nsp) == cudaSuccess &&
       h->d_rx_rot.alloc(nsp) == cudaSuccess && h->d_rx_meas.alloc(16 * 4096) == cudaSuccess &&
       h->d_rx_measn.alloc(4) == cudaSuccess && h->d_rx_forced.alloc(sizeof(RxState)) == cudaSuccess &&
-      h->d_deconv_carry.alloc(64) == cudaSuccess && h->d_sync_state.alloc(sizeof(SyncState)) == cudaSuccess &&
+      h->d_deconv_carry.alloc(256) == cudaSuccess && h->d_sync_state.alloc(sizeof(SyncState)) == cudaSuccess &&
       h->d_sync_res.alloc(sizeof(SyncResult)) == cudaSuccess && h->d_counts.alloc(64) == cudaSuccess;
   if (!aok) return bail(LDVB_ENOMEM, "device allocation failed");
   // cnr_fft / spectrum (leandvb.cc:322-343)
@@ -1286,6 +1296,52 @@ int deconv_launch(ldvb_handle *h, uint64_t limit_bytes, DeconvRun *run) {
   return LDVB_OK;
 }
 
+// --fastlock (dvb.h:428-454): one reference run() sees a window of n bytes, counts for each of the
+// four alignments the disagreements between the deconvolution polynomials and their alternates on
+// that alignment's AUXILIARY register (readerrors, dvb.h:391-412), locks the best one and asks for a
+// one-symbol skip when even the best one is wrong on more than a third of the bits.  Here a window is
+// what one batch lets the deconvolver produce; while the alignment is still wrong it is cut to
+// kFastlockProbe bytes so that the skip takes effect after a window of about the size the reference
+// sees with its default buffers instead of after a whole batch.
+constexpr uint64_t kFastlockProbe = 1024;
+
+uint64_t deconv_window(ldvb_handle *h) {
+  const Stream &in = h->s_sym;
+  if (in.count < 64) return 0;                                                        // dvb.h:419
+  uint64_t n = (in.count - 64) / (h->dec.punctweight / 2) * h->dec.punctperiod / 8;  // dvb.h:420
+  return std::min<uint64_t>(n, h->s_bytes.cap - h->s_bytes.count);
+}
+
+int fastlock_evaluate(ldvb_handle *h, uint64_t n, uint64_t *errors_best) {
+  Stream &in = h->s_sym;
+  uint64_t *dev = h->d_deconv_carry.as<uint64_t>();   // [4] error counts, [4][5] carries
+  CK(cudaMemsetAsync(dev, 0, 4 * 8, h->st));
+  for (int k = 0; k < 4; ++k) {
+    DeconvArgs a;
+    memset(&a, 0, sizeof a);
+    a.symbols = reinterpret_cast<const uint32_t *>(in.at(0));
+    a.nbytes = n;
+    a.reg_in = h->hyp2[k].reg; a.n_in = h->hyp2[k].n_in; a.out_acc = 0; a.n_out = h->hyp2[k].n_out;
+    for (int s = 0; s < 4; ++s) a.hyp[s] = h->dec.hyp_lut[k][s];
+    a.punctperiod = h->dec.punctperiod; a.punctweight = h->dec.punctweight;
+    for (int b = 0; b < 8; ++b) { a.deconv[b] = h->dec.deconv[b]; a.deconv2[b] = h->dec.deconv2[b]; }
+    a.err_out = reinterpret_cast<unsigned long long *>(dev + k);
+    KL("deconv_errors", launch_deconv_carry(a, in.count, dev + 4 + 5 * k, h->st));
+  }
+  uint64_t host[24];
+  CK(cudaMemcpyAsync(host, dev, sizeof host, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  uint64_t best_err = 1ull << 30; int best = 0;
+  for (int k = 0; k < 4; ++k) {
+    if (host[k] < best_err) { best_err = host[k]; best = k; }                          // dvb.h:436-439
+    const uint64_t *c = host + 4 + 5 * k;
+    h->hyp2[k].reg = c[0]; h->hyp2[k].n_in = (int)(int64_t)c[1]; h->hyp2[k].n_out = (int)(int64_t)c[3];
+  }
+  h->locked = best;                                                                    // dvb.h:441-447
+  *errors_best = best_err;
+  return LDVB_OK;
+}
+
 int deconv_commit(ldvb_handle *h, const DeconvRun &run) {
   h->hyp[h->locked] = run.after;
   return stream_consume(h, h->s_sym, run.consumed, h->d_scratch);
@@ -1309,7 +1365,7 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
   a.bits_in = bits_in; a.bits_out = h->trellis.bits_out; a.bps = h->vsyncs.bps; a.nshifts = nsh;
   a.nsyncs = h->vsyncs.nsyncs; a.ncs = h->trellis.ncs; a.nsymbols = h->cst.nsymbols;
   a.path_nbits = h->trellis.path_nbits; a.path_depth = h->trellis.path_depth; a.path32 = h->trellis.path32 ? 1 : 0;
-  a.resync_period = 32;   // dvb.h:1241
+  a.resync_period = h->cfg.fastlock ? 1 : 32;   // dvb.h:1241, leandvb.cc:540
   a.trellis_pred = h->d_vit_pred.as<uint8_t>(); a.trellis_us = h->d_vit_us.as<uint8_t>();
   a.maps = h->d_vit_maps.as<uint8_t>(); a.shifts = h->d_vit_shifts.as<int32_t>();
   a.state = h->d_vit_state.as<VitDecState>(); a.ctl = h->d_vit_ctl.as<VitCtl>();
@@ -1390,6 +1446,21 @@ int run_fec(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_out) 
   h->derand_pos = (int)counts[2];
   h->meas.rs_bits += npk * 204 * 8;
   h->meas.rs_errs += counts[3];
+  if (h->cfg.vber) {
+    // rs_decoder::run (dvb.h:1004-1052) reports (nbits, nerrs); rate_estimator::run adds them and
+    // emits num/den once den >= sample_size (generic.h:286-299) -- tested after every packet here.
+    h->vber_flags.resize(npk * 2);
+    CK(cudaMemcpyAsync(h->vber_flags.data(), a.flags, npk * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (uint64_t p = 0; p < npk; ++p) {
+      h->vber_num += h->vber_flags[2 * p + 1];
+      h->vber_den += 204 * 8;
+      if (h->vber_den >= h->vber_sample) {
+        h->vber_queue.push_back((float)h->vber_num / h->vber_den);
+        h->vber_num = h->vber_den = 0;
+      }
+    }
+  }
   h->meas.ts_packets += counts[0];
   h->meas.ts_dropped += counts[1];
   int rc;
@@ -1424,13 +1495,44 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
       if (rc == 0) break;
     }
   }
-  for (int guard = 0; guard < 64 && !c.viterbi; ++guard) {
+  for (int guard = 0; guard < (c.fastlock ? 4096 : 64) && !c.viterbi; ++guard) {
     if (h->skip) {  // dvb.h:415-416
       if (h->s_sym.count < (uint64_t)h->skip) break;
       if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
       h->skip = 0;
     }
     DeconvRun run;
+    if (c.fastlock) {
+      uint64_t n = deconv_window(h);
+      if (n < 32) break;                                                               // dvb.h:424-426
+      HypState aux[4];
+      for (int k = 0; k < 4; ++k) aux[k] = h->hyp2[k];
+      const int locked_before = h->locked;
+      uint64_t eb = 0;
+      if ((rc = fastlock_evaluate(h, n, &eb))) return rc;
+      if (eb > n * 8 / 3 && n > kFastlockProbe) {        // still misaligned: a short window, then look again
+        for (int k = 0; k < 4; ++k) h->hyp2[k] = aux[k];
+        h->locked = locked_before;
+        n = kFastlockProbe;
+        if ((rc = fastlock_evaluate(h, n, &eb))) return rc;
+      }
+      if (eb > n * 8 / 3) h->skip = 1;                                                 // dvb.h:449-453
+      if ((rc = deconv_launch(h, n, &run))) return rc;
+      const size_t tap_at0 = tap_bytes.size();
+      if (c.keep_taps && run.produced) {
+        tap_bytes.resize(tap_at0 + run.produced);
+        CK(cudaMemcpy(tap_bytes.data() + tap_at0, h->s_bytes.at(h->s_bytes.count), run.produced, cudaMemcpyDeviceToHost));
+      }
+      h->s_bytes.count += run.produced;
+      h->s_bytes.fresh += run.produced;
+      if ((rc = deconv_commit(h, run))) return rc;
+      for (int g2 = 0; g2 < 1 << 20; ++g2) {             // mpeg_sync never calls next_sync() here (dvb.h:751)
+        rc = run_sync(h);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+      }
+      continue;                                          // more windows while symbols remain
+    }
     if ((rc = deconv_launch(h, ~0ull, &run))) return rc;
     const size_t tap_at = tap_bytes.size();
     if (c.keep_taps && run.produced) {
@@ -1752,6 +1854,7 @@ int shard_check(ldvb_handle *h, const ldvb_shard *s) {
   if (!h || !s) return LDVB_EINVAL;
   if (h->cfg.rx_mode != LDVB_RX_FAST) return fail(h, LDVB_EINVAL, "time sharding needs rx_mode = LDVB_RX_FAST");
   if (h->cfg.sampler == LDVB_SAMP_RRC) return fail(h, LDVB_EINVAL, "time sharding: RRC sampler not supported yet");
+  if (h->cfg.fastlock) return fail(h, LDVB_EINVAL, "time sharding: --fastlock not supported");
   const uint64_t u = shard_unit(h);
   if (s->n_halo % u || s->n_chunk % u || s->abs_raw0 % u || s->n_halo_next % u)
     return fail(h, LDVB_EINVAL, "time sharding: abs_raw0, n_halo, n_chunk must be multiples of lcm(4096, 128*decimation)");
@@ -2354,6 +2457,15 @@ int ldvb_pull_cnr(ldvb_handle *h, float *dst, size_t cap, size_t *n) {
   const size_t k = std::min(cap, h->cnr_queue.size());
   if (k && dst) memcpy(dst, h->cnr_queue.data(), k * 4);
   h->cnr_queue.erase(h->cnr_queue.begin(), h->cnr_queue.begin() + k);
+  *n = k;
+  return LDVB_OK;
+}
+
+int ldvb_pull_vber(ldvb_handle *h, float *dst, size_t cap, size_t *n) {
+  if (!h || !n) return LDVB_EINVAL;
+  const size_t k = std::min(cap, h->vber_queue.size());
+  if (k && dst) memcpy(dst, h->vber_queue.data(), k * 4);
+  h->vber_queue.erase(h->vber_queue.begin(), h->vber_queue.begin() + k);
   *n = k;
   return LDVB_OK;
 }

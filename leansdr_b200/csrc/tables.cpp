@@ -312,6 +312,23 @@ void smallest_solution(const uint64_t resp[64], uint64_t fixed, int nfixed,
 
 }  // namespace
 
+// Alternate deconvolution polynomials for --fastlock: for every minimal polynomial d the
+// reference pairs a second inverse d2 = d ^ (a parity check of the punctured code), chosen by
+// its author and listed as constants (dvb.h:236-262).  They are data, reproduced here as
+// {d, d2} pairs; make_deconv() verifies each one against the code (it must invert the encoder
+// exactly like d does), so a wrong entry cannot go unnoticed.
+static const uint64_t kAltPolys[][2] = {
+    {0x3baull, 0x38ccaull},                                                          // 1/2
+    {0xf29ull, 0x3c569329ull}, {0x3c552ull, 0x1dee1cull}, {0x7948ull, 0x1e2b49948ull}, {0x1deull, 0x1e2a90ull},   // 2/3
+    {0xf247ull, 0xfd6383bull}, {0xfd9eeull, 0xfd91392ull}, {0xf248d8ull, 0xfd9eef18ull},                          // 3/4
+    {0xf5727full, 0x3d5c909758full}, {0x3d5c90aaull, 0x0f5727f0229c90aaull}, {0x3daa371cull, 0x3d5f45630ecull},
+    {0xf5727ff48ull, 0xf57d28260348ull}, {0xf57d28260ull, 0xf5727ff48128260ull},                                  // 5/6
+    {0xfbeac76c454full, 0xfb11d6ba045a8full}, {0xfb11d6baull, 0xfbea3c7d930e16baull},
+    {0xfb112d5038dcull, 0xfb112d5038271cull}, {0xfbea3c7d68ull, 0xfbeac7975462a8ull},
+    {0xfb112d50ull, 0xfbea3c86793290ull}, {0xfb112dabd2e0ull, 0xfb112d50c3cd20ull},
+    {0xfb11d640ull, 0xfbea3c8679c980ull},                                                                         // 7/8
+};
+
 bool make_deconv(int fec, DeconvPolys *out) {
   Puncturer pc;
   pc.g[0] = 0171; pc.g[1] = 0133;  // dvb.h:83-84
@@ -337,6 +354,13 @@ bool make_deconv(int fec, DeconvPolys *out) {
     // bit b and nothing else from the response to every single input bit.
     for (int i = 0; i < 64; ++i)
       if (par64(resp[i] & best) != (unsigned)(b == i)) return false;
+    uint64_t alt = best;
+    for (const auto &pr : kAltPolys)
+      if (pr[0] == best) alt = pr[1];
+    if (alt == best) return false;   // dvb.h:263: "Alt polynomial not provided"
+    for (int i = 0; i < 64; ++i)
+      if (par64(resp[i] & alt) != (unsigned)(b == i)) return false;
+    out->deconv2[b] = alt;
   }
   // Hypotheses {0, 90 degrees} x {direct, conjugate} (dvb.h:309-360); indexed by
   // the constellation symbol: bit1 of the symbol = (re<0), bit0 = (im<0) for

@@ -88,17 +88,15 @@ private:
   void telemetry() {
     ldvb_meas m;
     if ( ldvb_get_meas(handle, &m) ) return;
+    size_t k = 0;
+    float v;
     if ( freq_out && freq_out->writable() ) freq_out->write(m.freq_tap);
     if ( ss_out && ss_out->writable() ) ss_out->write(m.ss);
     if ( mer_out && mer_out->writable() ) mer_out->write(m.mer);
     if ( lock_out && m.lock != last_lock && lock_out->writable() ) { lock_out->write(m.lock); last_lock = m.lock; }
-    if ( vber_out && m.rs_bits > rs_bits && vber_out->writable() ) {
-      vber_out->write((float)(m.rs_errs-rs_errs) / (float)(m.rs_bits-rs_bits));  // generic.h:296-299
-      rs_bits = m.rs_bits; rs_errs = m.rs_errs;
-    }
+    // rate_estimator (generic.h:272-305, leandvb.cc:583-587): needs cfg.vber
+    while ( vber_out && vber_out->writable() && !ldvb_pull_vber(handle, &v, 1, &k) && k ) vber_out->write(v);
     // cnr_fft / spectrum (sdr.h:1273-1404): one value / one row per second of signal
-    size_t k = 0;
-    float v;
     while ( cnr_out && cnr_out->writable() && !ldvb_pull_cnr(handle, &v, 1, &k) && k ) cnr_out->write(v);
     while ( spectrum_out && spectrum_out->writable() &&
 	    !ldvb_pull_spectrum(handle, (float*)spectrum_out->wr(), 1, &k) && k ) spectrum_out->written(1);

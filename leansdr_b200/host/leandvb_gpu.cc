@@ -72,6 +72,8 @@ int main(int argc, const char *argv[]) {
     else if ( !strcmp(a,"--drift") ) cfg.allow_drift = 1;
     else if ( !strcmp(a,"--roll-off") && more ) cfg.rolloff = atof(argv[++i]);
     else if ( !strcmp(a,"--hard-metric") ) cfg.hard_metric = 1;
+    else if ( !strcmp(a,"--fastlock") ) cfg.fastlock = 1;
+    else if ( !strcmp(a,"--viterbi") ) cfg.viterbi = 1;
     else if ( !strcmp(a,"--standard") && more ) ++i;       // DVB-S only
     else if ( !strcmp(a,"--cr") && more ) {
       const char *v = argv[++i];
@@ -85,7 +87,7 @@ int main(int argc, const char *argv[]) {
     else if ( !strcmp(a,"--gpu-exact") ) cfg.rx_mode = LDVB_RX_EXACT;
     else if ( !strcmp(a,"--gpu-batch") && more ) cfg.max_batch = strtoull(argv[++i], NULL, 0);
     else if ( !strcmp(a,"--gpu-device") && more ) cfg.device = atoi(argv[++i]);
-    else if ( !strcmp(a,"--fd-info") && more ) { info = (atoi(argv[++i]) == 2); }
+    else if ( !strcmp(a,"--fd-info") && more ) { info = (atoi(argv[++i]) == 2); cfg.vber = 1; }
     else { fprintf(stderr, "leandvb_gpu: unsupported option %s\n", a); return 1; }
   }
   unsigned long inbuf = cfg.max_batch;

@@ -890,6 +890,7 @@ static void deconv_init_syncs(orc_deconv *d) {        /* dvb.h:309-360 */
       }
     d->syncs[sync_id].in = 0;  d->syncs[sync_id].n_in = 0;
     d->syncs[sync_id].out = 0; d->syncs[sync_id].n_out = 0;
+    d->syncs[sync_id].in2 = 0; d->syncs[sync_id].n_in2 = 0; d->syncs[sync_id].n_out2 = 0;
   }
 }
 
@@ -933,6 +934,38 @@ static inline uint8_t deconv_readbyte(orc_deconv *d, orc_dsync *s,
   return res;
 }
 
+/* deconvol_sync::readerrors (dvb.h:391-412): disagreements between the deconvolution
+   polynomials and their alternates on the auxiliary register. */
+static inline unsigned long deconv_readerrors(orc_deconv *d, orc_dsync *s,
+					      const uint8_t **pp) {
+  const int traceback = 64;
+  const uint8_t *p = *pp;
+  unsigned long res = 0;
+  while ( s->n_out2 < 8 ) {
+    uint64_t iq = s->in2;
+    while ( s->n_in2 < traceback ) {
+      uint8_t sym = p[2];
+      uint8_t iqbits = s->lut[(sym & 2) ? 1 : 0][sym & 1];
+      p += 4;
+      iq = (iq << 2) | iqbits;
+      s->n_in2 += 2;
+    }
+    s->in2 = iq;
+    for ( int b = d->punctperiod-1; b >= 0; --b ) {
+      uint8_t bit  = parity64(iq & d->deconv[b]);
+      uint8_t bit2 = parity64(iq & d->deconv2[b]);
+      if ( bit2 != bit ) ++res;
+    }
+    s->n_out2 += d->punctperiod;
+    s->n_in2 -= d->punctweight;
+  }
+  s->n_out2 -= 8;
+  *pp = p;
+  return res;
+}
+
+void orc_deconv_set_fastlock(orc_deconv *d, int on) { d->fastlock = on; }
+
 size_t orc_deconv_run(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
 		      uint8_t *out, size_t out_cap, size_t *consumed) {
   return orc_deconv_run2(d, symbols4, n_in, out, out_cap, consumed, 0);
@@ -955,7 +988,19 @@ size_t orc_deconv_run2(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
   long maxwr = (long)out_cap;
   long n = (maxrd < maxwr) ? maxrd : maxwr;
   if ( !n ) return 0;
-  if ( n < 32 && !big_batch ) return 0;
+  if ( n < 32 && (!big_batch || d->fastlock) ) return 0;
+  if ( d->fastlock ) {                         /* dvb.h:428-454: try all sync alignments */
+    unsigned long errors_best = 1 << 30;
+    int best = 0;
+    for ( int k = 0; k < 4; ++k ) {
+      const uint8_t *p = symbols4 + 4*skipped;
+      unsigned long errors = 0;
+      for ( long c = n; c--; ) errors += deconv_readerrors(d, &d->syncs[k], &p);
+      if ( errors < errors_best ) { errors_best = errors; best = k; }
+    }
+    if ( best != d->locked ) d->locked = best;
+    if ( errors_best > (unsigned long)(n*8/3) ) d->skip = 1;
+  }
   const uint8_t *pin = symbols4 + 4*skipped, *pin0 = pin;
   uint8_t *pout = out;
   orc_dsync *s = &d->syncs[d->locked];
@@ -970,6 +1015,11 @@ void orc_mpegsync_init(orc_mpegsync *m) {             /* dvb.h:719-741 */
   m->polarity = 0; m->bitphase = 0; m->synchronized = 0;
   m->next_sync_count = 0; m->report_state = 1;
   m->phase8 = -1;
+  m->fastlock = 0; m->resync_period = 1; m->resync_phase = 0;
+}
+
+void orc_mpegsync_set_fastlock(orc_mpegsync *m, int fastlock, int resync_period) {
+  m->fastlock = fastlock; m->resync_period = resync_period;
 }
 
 /* dvb.h:798-840.  tmp must hold 204*8 bytes.  Returns bytes to skip (>0) on
@@ -1061,6 +1111,24 @@ size_t orc_mpegsync_run2(orc_mpegsync *m, orc_deconv *deconv,
 	++nl;
 	break;
       }
+    }
+  } else if ( m->fastlock ) {                  /* run_searching_fast, dvb.h:781-796 */
+    int chunk = P * m->scan_syncs;
+    uint8_t tmp[204*9];
+    while ( n_in - rd >= (size_t)chunk+1 && out_cap - wr >= (size_t)chunk ) {
+      if ( m->resync_phase == 0 ) {
+	for ( m->bitphase = 0; m->bitphase <= 7; ++m->bitphase ) {
+	  int skip = mpegsync_search(m, in + rd, tmp);
+	  if ( skip ) {
+	    rd += skip;
+	    if ( lock_out ) lock_out[nl] = 1;
+	    ++nl;
+	    goto done;
+	  }
+	}
+      }
+      rd += P;
+      if ( ++m->resync_phase >= m->resync_period ) m->resync_phase = 0;
     }
   } else {                                     /* run_searching, dvb.h:755-779 */
     int next_sync = 0;

@@ -184,6 +184,7 @@ typedef struct {
   uint8_t lut[2][2];
   uint64_t in;  int n_in;
   uint64_t out; int n_out;
+  uint64_t in2; int n_in2, n_out2;   /* auxiliary register for fastlock (dvb.h:303-306) */
 } orc_dsync;
 
 typedef struct {
@@ -192,6 +193,7 @@ typedef struct {
   orc_dsync syncs[4];
   int locked;
   int skip;
+  int fastlock;                      /* dvb.h:195, 428-454 */
 } orc_deconv;
 
 void orc_deconv_init(orc_deconv *d, int fec);
@@ -204,6 +206,7 @@ size_t orc_deconv_run(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
 size_t orc_deconv_run2(orc_deconv *d, const uint8_t *symbols4, size_t n_in,
 		       uint8_t *out, size_t out_cap, size_t *consumed, int big_batch);
 void   orc_deconv_set(orc_deconv *d, int locked, int skip);
+void   orc_deconv_set_fastlock(orc_deconv *d, int on);
 
 typedef struct {
   int scan_syncs, want_syncs;
@@ -215,9 +218,11 @@ typedef struct {
   int phase8;
   unsigned long lock_timeleft, locktime;
   int report_state;
+  int fastlock, resync_period, resync_phase;   /* dvb.h:716-717, 781-796 */
 } orc_mpegsync;
 
 void orc_mpegsync_init(orc_mpegsync *m);
+void orc_mpegsync_set_fastlock(orc_mpegsync *m, int fastlock, int resync_period);
 /* One reference run() (dvb.h:742-874, fastlock off).  deconv may be NULL.
  * lock_out receives lock transitions (0/1), locktime_out one per packet. */
 size_t orc_mpegsync_run(orc_mpegsync *m, orc_deconv *deconv,

@@ -107,6 +107,8 @@ def lib():
         L.orc_deconv_run2.restype = sz
         L.orc_deconv_run2.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int]
         L.orc_deconv_set.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_deconv_set_fastlock.argtypes = [vp, C.c_int]
+        L.orc_mpegsync_set_fastlock.argtypes = [vp, C.c_int, C.c_int]
         L.orc_deconv_get.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
         L.orc_mpegsync_init.argtypes = [vp]
         L.orc_mpegsync_run.restype = sz
@@ -379,9 +381,12 @@ class Receiver:
 
 
 class Deconv:
-    def __init__(self, fec="1/2"):
+    def __init__(self, fec="1/2", fastlock=False):
         self.o = _Obj(5)
         lib().orc_deconv_init(self.o.p, FEC[fec])
+        self.fastlock = bool(fastlock)
+        if fastlock:
+            lib().orc_deconv_set_fastlock(self.o.p, 1)
 
     def next_sync(self): lib().orc_deconv_next_sync(self.o.p)
 
@@ -409,9 +414,11 @@ class Deconv:
 
 
 class MpegSync:
-    def __init__(self):
+    def __init__(self, fastlock=False, resync_period=1):
         self.o = _Obj(6)
         lib().orc_mpegsync_init(self.o.p)
+        if fastlock:
+            lib().orc_mpegsync_set_fastlock(self.o.p, 1, resync_period)
 
     def get(self):
         v = np.zeros(7, np.int64); lib().orc_mpegsync_get(self.o.p, _p(v))
@@ -573,8 +580,10 @@ class Chain:
         if cfg.viterbi and fec == "2/3" and cfg.cstln == "QPSK":
             fec = "4/6"
         self.vit = Viterbi(self.cst, fec) if cfg.viterbi else None
-        self.deconv = None if cfg.viterbi else Deconv(fec)
-        self.sync = MpegSync()
+        if self.vit and cfg.fastlock:
+            self.vit.set_resync_period(1)                      # leandvb.cc:540
+        self.deconv = None if cfg.viterbi else Deconv(fec, fastlock=cfg.fastlock)
+        self.sync = MpegSync(fastlock=cfg.fastlock, resync_period=1)   # leandvb.cc:553, 565
         self.derand = Derand()
 
     def run(self, raw: np.ndarray) -> dict:
@@ -608,6 +617,9 @@ class Chain:
             by, _ = self.vit.run(r["symbols"])
             t["bytes"] = by
             mp, lock, lt = self._sync_all(by, None)
+        elif cfg.fastlock:
+            by, mp, lock, lt = self._deconv_sync_fastlock(r["symbols"])
+            t["bytes"] = by
         else:
             by, mp, lock, lt = self._deconv_sync(r["symbols"])
             t["bytes"] = by
@@ -629,6 +641,39 @@ class Chain:
                 break
             pos += c
         return np.concatenate(outs), np.concatenate(locks), np.concatenate(lts)
+
+    FASTLOCK_PROBE = 1024
+
+    def _deconv_sync_fastlock(self, symbols):
+        """--fastlock under the large-batch schedule (DESIGN.md): one deconvol_sync::run() per
+        window (dvb.h:414-467), a window being everything the batch allows -- cut to FASTLOCK_PROBE
+        bytes while even the best alignment is wrong on more than a third of the bits, so that the
+        one-symbol skip (dvb.h:449-453) acts after a window of the size the reference sees with
+        its default buffers; mpeg_sync searches with run_searching_fast (dvb.h:781-796)."""
+        by_all, outs, locks, lts = [], [], [], []
+        spos = 0
+        bbuf = np.zeros(0, np.uint8)
+        for _ in range(1 << 20):
+            snap = self.deconv.snapshot()
+            by, cons = self.deconv.run(symbols[spos:], big_batch=True)
+            if by.size == 0 and cons == 0:
+                break
+            if self.deconv.get()["skip"] and by.size > self.FASTLOCK_PROBE:
+                self.deconv.restore(snap)
+                by, cons = self.deconv.run(symbols[spos:], out_cap=self.FASTLOCK_PROBE, big_batch=True)
+            spos += cons
+            by_all.append(by)
+            bbuf = np.concatenate([bbuf, by])
+            while True:
+                o, c, lk, lt = self.sync.run(bbuf, None)
+                outs.append(o); locks.append(lk); lts.append(lt)
+                bbuf = bbuf[c:]
+                if c == 0 and o.size == 0:
+                    break
+        by = np.concatenate(by_all) if by_all else np.zeros(0, np.uint8)
+        return (by, np.concatenate(outs) if outs else np.zeros(0, np.uint8),
+                np.concatenate(locks) if locks else np.zeros(0, np.int32),
+                np.concatenate(lts) if lts else np.zeros(0, np.uint64))
 
     def _deconv_sync(self, symbols):
         """Algebraic deconvolution + MPEG sync with the backward next_sync() edge

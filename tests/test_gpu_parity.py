@@ -349,3 +349,51 @@ def test_spectrum_with_rotator_and_golden(product, oracle):
 def test_cnr_needs_four_samples_per_symbol(product):
     with pytest.raises(product.LdvbError):
         product.Receiver(fmt="f32", cnr=True)     # Fs/Fm = 1.2 (sdr.h:1283-1284)
+
+
+FASTLOCK_CASES = [
+    ("qpsk12", dict(fmt="f32", fastlock=True), {}, 300),
+    ("qpsk78-skips", dict(fmt="f32", fastlock=True, fec="7/8", Fs=4e6, anf=0), dict(ratio="2", cr="7/8"), 400),
+    ("qpsk34", dict(fmt="f32", fastlock=True, fec="3/4", Fs=4e6), dict(ratio="2", cr="3/4"), 300),
+    ("qpsk78-viterbi", dict(fmt="f32", fastlock=True, viterbi=True, fec="7/8", Fs=4e6), dict(ratio="2", cr="7/8"), 200),
+    ("qpsk12-noise", dict(fmt="f32", fastlock=True, resample=True), dict(noise_db=22), 300),
+]
+
+
+@pytest.mark.parametrize("name,kw,gkw,npk", FASTLOCK_CASES, ids=[c[0] for c in FASTLOCK_CASES])
+def test_fastlock_every_stream_bit_exact(product, oracle, name, kw, gkw, npk):
+    """--fastlock (dvb.h:391-454, 781-796; leandvb.cc:540-565): alignment chosen per window by the
+    error counts of the alternate polynomials, one-symbol skips, mpeg_sync's fast search, Viterbi
+    re-sync every chunk.  The oracle (pinned to the reference runnables window by window) runs the
+    same large-batch schedule: every stream bit-exact.  7/8 takes alignment switches and skips."""
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=40)
+    assert_prefix(got["mpegbytes"], ref["mpegbytes"], "aligned bytes")
+    assert_prefix(got["rspackets"], ref["rspackets"], "RS packets")
+    assert_prefix(got["ts"], ref["ts"], "TS")
+    assert len(got["ts"]) > npk - 80
+
+
+def test_vber_rate_estimator(product, oracle):
+    """p_vber (rate_estimator, generic.h:272-305; sample_size = max(Fm/2, 50000), leandvb.cc:583-587)
+    from the RS decoder's per-packet counts: equal to the estimator restated over the oracle's
+    per-packet counts (threshold tested after every packet), float for float."""
+    P, O = product, oracle
+    raw = V.ref_iq(2600, fmt="f32", noise_db=22)
+    ref = O.Chain(O.Config(fmt="f32", resample=True)).run(raw)
+    want, num, den = [], 0, 0
+    for e in ref["rs_nerr"]:
+        num += int(e); den += 204 * 8
+        if den >= 1000000:
+            want.append(np.float32(num) / np.float32(den)); num = den = 0
+    rx = P.Receiver(fmt="f32", resample=True, vber=True, rx_mode=P.RX_EXACT, max_batch=raw.size // 2)
+    rx.push(raw)
+    got = rx.pull_vber()
+    rx.close()
+    assert len(want) >= 4 and any(w > 0 for w in want)
+    assert got.size in (len(want), len(want) + 1)          # the product drains one more packet at the end
+    assert np.array_equal(got[: len(want)], np.array(want, np.float32))

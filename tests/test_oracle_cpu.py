@@ -185,3 +185,89 @@ def test_oracle_cnr_and_spectrum_equal_reference_taps(oracle):
             x = O.Rotator(np.float32(-np.float32(derot) / np.float32(10e6))).run(x)
         got_c, _ = O.Meas(4096, float(np.float32(2e6) / np.float32(10e6)), 0.1, O._idecim(10e6, 1)).run(x, icf / 4096.0)
         assert want_c.size >= 1 and np.array_equal(got_c[: want_c.size], want_c)
+
+
+# ------------------------------------------------------------------ --fastlock
+
+def _ref_fastlock(O, sym, fec_id, W, period, fastlock):
+    d = tempfile.mkdtemp()
+    sym.tofile(os.path.join(d, "s.bin"))
+    subprocess.run([O.ref_bin("ref_fastlock"), str(fec_id), str(W), str(period), str(int(fastlock)),
+                    os.path.join(d, "s.bin"), os.path.join(d, "o")], check=True)
+    return (np.fromfile(os.path.join(d, "o.bytes"), np.uint8), np.fromfile(os.path.join(d, "o.mpeg"), np.uint8),
+            np.loadtxt(os.path.join(d, "o.state"), dtype=int).reshape(-1, 2))
+
+
+def _oracle_fastlock(O, sym, fec, W, period, fastlock):
+    """The oracle fed with the schedule oracle/ref_fastlock.cc gives the reference runnables:
+    W more symbols, one deconvol_sync::run(), mpeg_sync::run() until it stops moving."""
+    sym = sym.reshape(-1, 4)
+    dec = O.Deconv(fec, fastlock=fastlock)
+    syn = O.MpegSync(fastlock=fastlock, resync_period=period)
+    by_all, mp_all, states = [], [], []
+    pos = fed = 0
+    bbuf = np.zeros(0, np.uint8)
+    n = sym.shape[0]
+    while True:
+        eof = fed + W > n
+        fed = min(n, fed + W)
+        by, cons = dec.run(sym[pos:fed])
+        pos += cons
+        g = dec.get()
+        states.append((g["locked"], g["skip"]))
+        by_all.append(by)
+        bbuf = np.concatenate([bbuf, by])
+        while True:
+            o, c, _, _ = syn.run(bbuf, None if fastlock else dec)
+            mp_all.append(o)
+            bbuf = bbuf[c:]
+            if c == 0 and o.size == 0:
+                break
+        if eof:
+            break
+    return np.concatenate(by_all), np.concatenate(mp_all), np.array(states)
+
+
+@pytest.mark.skipif(not V.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cr,fec_id,ratio,Fs", [("1/2", 0, "6/5", 2.4e6), ("7/8", 5, "2", 4e6)])
+def test_fastlock_oracle_equals_reference_runnables(oracle, cr, fec_id, ratio, Fs):
+    """deconvol_sync with fastlock (readerrors, best alignment, skip; dvb.h:391-454) and mpeg_sync's
+    run_searching_fast (dvb.h:781-796): the UNMODIFIED reference runnables driven window by window
+    (oracle/_ref/ref_fastlock) vs the oracle given the same windows -- bytes, aligned bytes and the
+    (locked, skip) sequence, bit for bit.  7/8 exercises alignment switches and skips."""
+    O = oracle
+    raw = V.ref_iq(300, ratio=ratio, cr=cr, fmt="f32")
+    sym = np.ascontiguousarray(O.Chain(O.Config(fmt="f32", fec=cr, Fs=Fs)).run(raw)["symbols"]).view(np.uint8).reshape(-1)
+    for W, fl, period in ((4096, True, 1), (1000, True, 1), (20000, True, 32), (4096, False, 1)):
+        rb, rm, rs = _ref_fastlock(O, sym, fec_id, W, period, fl)
+        ob, om, os_ = _oracle_fastlock(O, sym, cr, W, period, fl)
+        assert rb.size == ob.size and np.array_equal(rb, ob), (W, fl, period)
+        assert rm.size == om.size and np.array_equal(rm, om), (W, fl, period)
+        assert rs.shape == os_.shape and np.array_equal(rs, os_), (W, fl, period)
+
+
+@pytest.mark.skipif(not V.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cr,ratio,Fs,vit,exact", [("1/2", "6/5", 2.4e6, False, True), ("3/4", "2", 4e6, False, True),
+                                                    ("7/8", "2", 4e6, True, True), ("7/8", "2", 4e6, False, False)])
+def test_fastlock_chain_vs_reference_leandvb(oracle, cr, ratio, Fs, vit, exact):
+    """`leandvb --fastlock` (unmodified reference, default buffers) vs the oracle chain under the
+    large-batch schedule.  Where the first window is already aligned the TS is identical; at 7/8
+    without Viterbi the acquisition (which window sees which alignment) depends on the schedule:
+    both decode the transmitted packets, the reference starts a few packets earlier."""
+    O = oracle
+    raw = V.ref_iq(400, ratio=ratio, cr=cr, fmt="f32")
+    flags = ["--f32", "-f", str(Fs), "--sr", "2000e3", "--cr", cr, "--fastlock"] + (["--viterbi"] if vit else [])
+    want = V.ref_leandvb(raw, flags)
+    got = O.Chain(O.Config(fmt="f32", fec=cr, Fs=Fs, fastlock=True, viterbi=vit)).run(raw)["ts"]
+    if exact:
+        n = min(len(want), len(got))
+        assert n > 300 and np.array_equal(want[:n], got[:n]) and abs(len(want) - len(got)) <= 1
+        return
+    sent = V.ts_packets(400)
+
+    def good(p):
+        c = (p[:, 1].astype(int) << 16) | (p[:, 2].astype(int) << 8) | p[:, 3]
+        return [int(k) for i, k in enumerate(c) if k < 400 and np.array_equal(p[i], sent[k])]
+    gw, gg = good(want), good(got)
+    assert len(gg) > 300 and gg == list(range(gg[0], gg[-1] + 1))       # contiguous numbered packets
+    assert gw[-1] == gg[-1] and gg[0] - gw[0] < 64                       # same end, start within the schedule slack
