@@ -339,7 +339,10 @@ def main():
     dev = torch.device("cuda", local)
 
     if world > 1 and a.shard == "time":
-        return bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P)
+        bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     vector_check = None
     if a.cpu_gen:

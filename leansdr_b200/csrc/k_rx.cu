@@ -550,9 +550,11 @@ cudaError_t launch_rx_t(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     constexpr size_t smem_max = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<2, TILE>::kBytes;
     cudaError_t e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return e;
-    // Leave about half of the SM's unified cache to L1: the two 512 KB tables are read
-    // through it, and their hot lines (current carrier phase, constellation clusters)
-    // must stay resident -- table latency is what bounds this kernel.
+    // Leave most of the SM's unified cache to L1: the two 512 KB tables are read through it,
+    // and their hot lines (current carrier phase, constellation clusters) must stay resident --
+    // table latency is what bounds this kernel.  Measured (round 1): 8-sample tiles (20 KB of rows
+    // per CTA, 3 CTAs per SM) with a 30-40 % shared-memory carve-out beat 16-sample tiles at 50 %
+    // by 4 %; every split that gives L1 less than half is 30-130 % slower.
     e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -569,13 +571,13 @@ cudaError_t launch_rx_t(const RxArgs &a, const uint32_t *span_list, uint32_t nli
 // Tuning knobs (read once): LDVB_RX_TILE = 8 | 16 samples per staged tile,
 // LDVB_RX_CARVEOUT = shared-memory share of the unified cache in percent.
 int rx_tile_config() {
-  static int tile = [] { const char *e = getenv("LDVB_RX_TILE"); int t = e ? atoi(e) : 16; return t == 8 ? 8 : 16; }();
+  static int tile = [] { const char *e = getenv("LDVB_RX_TILE"); int t = e ? atoi(e) : 8; return t == 16 ? 16 : 8; }();
   return tile;
 }
 
 cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st) {
   if (a.nspans == 0 || (span_list && !nlist)) return cudaSuccess;
-  static int carveout = [] { const char *e = getenv("LDVB_RX_CARVEOUT"); int c = e ? atoi(e) : 50; return (c < 0 || c > 100) ? 50 : c; }();
+  static int carveout = [] { const char *e = getenv("LDVB_RX_CARVEOUT"); int c = e ? atoi(e) : 35; return (c < 0 || c > 100) ? 35 : c; }();
   if (rx_tile_config() == 8) return launch_rx_t<8>(a, span_list, nlist, carveout, st);
   return launch_rx_t<16>(a, span_list, nlist, carveout, st);
 }
