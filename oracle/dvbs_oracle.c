@@ -1523,6 +1523,8 @@ size_t orc_sizeof(int what) {
   case 6: return sizeof(orc_mpegsync);
   case 7: return sizeof(orc_derand);
   case 8: return sizeof(orc_meas);
+  case 9: return sizeof(orc_hsrx);
+  case 10: return sizeof(orc_hsdeconv);
   default: return 0;
   }
 }

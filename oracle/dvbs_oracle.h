@@ -282,6 +282,39 @@ size_t orc_tx_chain(const uint8_t *ts, size_t npk, int cstln_kind, int fec, int 
 		    float *out, size_t cap_samples,
 		    uint8_t *tap_mpegbytes, size_t *n_mpegbytes, uint8_t *tap_symbols, size_t *n_symbols);
 
+/* ------------------------------------------------------------- --hs path
+ * oracle/dvbs_hs_oracle.c: fast_qpsk_receiver<u8> (sdr.h:946-1189) and
+ * dvb_deconvol_sync_hard (dvb.h:612-707, convolutional.h:75-192). */
+typedef struct {
+  unsigned long meas_decimation;
+  float omega, min_omega, max_omega;
+  signed long freqw, min_freqw, max_freqw;
+  float pll_adjustment;
+  int allow_drift;
+  uint16_t polar_a[256][256]; uint8_t polar_r[256][256];   /* lut_polar {a, r} */
+  uint8_t rect[256][256][2];                                 /* lut_rect[angle][r] {re, im} */
+  uint8_t sincos[65536][2];                                  /* lut_sincos {re, im} */
+  struct { uint8_t p_re, p_im, c_re, c_im; } hist[3];
+  float mu;
+  uint16_t phase;
+  unsigned long meas_count;
+} orc_hsrx;
+void   orc_hsrx_init(orc_hsrx *r);
+void   orc_hsrx_set_omega(orc_hsrx *r, float omega);
+void   orc_hsrx_set_freq(orc_hsrx *r, float freq);
+void   orc_hsrx_config(orc_hsrx *r, int allow_drift, unsigned long meas_decimation);
+size_t orc_hsrx_run(orc_hsrx *r, const uint8_t *in, size_t n_in, uint8_t *sym_out, size_t *n_sym,
+		    float *freq_out, size_t *n_freq);
+
+typedef struct {
+  int resync_period, resync_phase, locked;
+  uint32_t inI[4], inQ[4];
+  uint8_t lut[4][4];
+} orc_hsdeconv;
+void   orc_hsdeconv_init(orc_hsdeconv *d, int resync_period);
+size_t orc_hsdeconv_run(orc_hsdeconv *d, const uint8_t *sym, size_t n_in, uint8_t *out, size_t out_cap,
+			size_t *consumed);
+
 #ifdef __cplusplus
 }
 #endif

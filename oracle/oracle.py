@@ -34,7 +34,7 @@ FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16,
 def build(force: bool = False) -> str:
     """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = [os.path.join(_HERE, f) for f in ("dvbs_oracle.c", "dvbs_tx_oracle.c", "dvbs_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("dvbs_oracle.c", "dvbs_tx_oracle.c", "dvbs_hs_oracle.c", "dvbs_oracle.h")]
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in src)
     if force or stale:
@@ -123,6 +123,15 @@ def lib():
         L.orc_rs_decode_packet.restype = C.c_int
         L.orc_rs_decode_packet.argtypes = [vp, vp, C.POINTER(C.c_int)]
         L.orc_rs_encode.argtypes = [vp]
+        L.orc_hsrx_init.argtypes = [vp]
+        L.orc_hsrx_set_omega.argtypes = [vp, C.c_float]
+        L.orc_hsrx_set_freq.argtypes = [vp, C.c_float]
+        L.orc_hsrx_config.argtypes = [vp, C.c_int, C.c_ulong]
+        L.orc_hsrx_run.restype = sz
+        L.orc_hsrx_run.argtypes = [vp, vp, sz, vp, C.POINTER(sz), vp, C.POINTER(sz)]
+        L.orc_hsdeconv_init.argtypes = [vp, C.c_int]
+        L.orc_hsdeconv_run.restype = sz
+        L.orc_hsdeconv_run.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
         L.orc_tx_chain.restype = sz
         L.orc_tx_chain.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_char_p,
                                    C.c_int, vp, sz, vp, C.POINTER(sz), vp, C.POINTER(sz)]
@@ -716,6 +725,66 @@ class Chain:
         return (by, np.concatenate(outs) if outs else np.zeros(0, np.uint8),
                 np.concatenate(locks) if locks else np.zeros(0, np.int32),
                 np.concatenate(lts) if lts else np.zeros(0, np.uint64))
+
+
+# ------------------------------------------------------------------ --hs path
+
+class HsReceiver:
+    """fast_qpsk_receiver<u8> (sdr.h:946-1189)."""
+    def __init__(self, omega, freq=0.0, allow_drift=False, meas_decimation=1048576):
+        self.o = _Obj(9)
+        lib().orc_hsrx_init(self.o.p)
+        lib().orc_hsrx_set_omega(self.o.p, np.float32(omega))
+        if freq:
+            lib().orc_hsrx_set_freq(self.o.p, np.float32(freq))
+        lib().orc_hsrx_config(self.o.p, int(allow_drift), int(meas_decimation))
+
+    def run(self, raw_u8):
+        x = np.ascontiguousarray(raw_u8, np.uint8).reshape(-1)
+        n = x.size // 2
+        sym = np.zeros(n + 256, np.uint8)
+        freq = np.zeros(n // 128 + 8, np.float32)
+        ns, nf = C.c_size_t(0), C.c_size_t(0)
+        used = lib().orc_hsrx_run(self.o.p, _p(x), n, _p(sym), C.byref(ns), _p(freq), C.byref(nf))
+        return sym[: ns.value].copy(), freq[: nf.value].copy(), used
+
+
+class HsDeconv:
+    """dvb_deconvol_sync_hard (dvb.h:612-707)."""
+    def __init__(self, resync_period=32):
+        self.o = _Obj(10)
+        lib().orc_hsdeconv_init(self.o.p, resync_period)
+
+    def run(self, sym):
+        s = np.ascontiguousarray(sym, np.uint8)
+        out = np.zeros(s.size // 8 + 64, np.uint8)
+        cons = C.c_size_t(0)
+        k = lib().orc_hsdeconv_run(self.o.p, _p(s), s.size, _p(out), out.size, C.byref(cons))
+        return out[:k].copy(), cons.value
+
+
+def hs_chain(raw_u8, Fs=2.4e6, Fm=2e6, fastlock=False, Ftune=0.0, allow_drift=False, Finfo=5.0) -> dict:
+    """run_highspeed (apps/leandvb.cc:727-969) stage by stage on a whole u8 IQ array."""
+    f32 = np.float32
+    period = 1 if fastlock else 32                                  # leandvb.cc:853, 863
+    rx = HsReceiver(f32(f32(Fs) / f32(Fm)), f32(f32(Ftune) / f32(Fs)) if Ftune else 0.0, allow_drift,
+                    _idecim(f32(Fs), Finfo))
+    t = {}
+    t["symbols"], t["freq"], _ = rx.run(raw_u8)
+    t["bytes"], _ = HsDeconv(period).run(t["symbols"])
+    sync = MpegSync(fastlock=True, resync_period=period)
+    outs, bbuf = [], t["bytes"]
+    while True:
+        o, c, _, _ = sync.run(bbuf, None)
+        outs.append(o); bbuf = bbuf[c:]
+        if c == 0 and o.size == 0:
+            break
+    t["mpegbytes"] = np.concatenate(outs)
+    t["rspackets"], _ = deinterleave(t["mpegbytes"])
+    ts, bad, nerr, _ = rs_decode(t["rspackets"])
+    t["rtspackets"] = ts; t["rs_bad"] = bad; t["rs_nerr"] = nerr
+    t["ts"] = Derand().run(ts)
+    return t
 
 
 # ------------------------------------------------------------------ transmit chain
