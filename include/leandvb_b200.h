@@ -19,6 +19,8 @@
  *   deinterleaver                leansdr/dvb.h:926-948
  *   rs_decoder                   leansdr/dvb.h:985-1058, rs.h:86-268
  *   derandomizer                 leansdr/dvb.h:1107-1163
+ *   (--hs) fast_qpsk_receiver    leansdr/sdr.h:946-1189
+ *   (--hs) dvb_deconvol_sync_hard leansdr/dvb.h:612-707, convolutional.h:75-192
  *
  * Error convention: every function returns 0 on success or a negative
  * LDVB_E* code; ldvb_strerror() gives text.  The runnable wrapper turns a
@@ -115,7 +117,10 @@ typedef struct ldvb_config {
                                 (leandvb.cc:333-343), ldvb_config_default sets 1 */
   int32_t  vber;             /* rate_estimator on the RS decoder's counts (leandvb.cc:583-587): values
                                 are queued for ldvb_pull_vber                                      */
-  int32_t  reserved[3];
+  int32_t  hs;               /* --hs (leandvb.cc:727-969): fast_qpsk_receiver<u8> + dvb_deconvol_sync_hard +
+                                mpeg_sync with fastlock; needs u8 input, QPSK, code rate 1/2; no notch,
+                                filter, CNR or spectrum blocks exist on that path                  */
+  int32_t  reserved[2];
 } ldvb_config;
 
 typedef struct ldvb_handle ldvb_handle;

@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("allow_drift", C.c_int32), ("Ftune", C.c_float), ("Finfo", C.c_float),
         ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
         ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
-        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("hs", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -152,7 +152,7 @@ def default_config(**kw) -> Config:
             cfg.sampler = SAMPLER[v] if isinstance(v, str) else v
         elif k == "sub_batch":
             cfg.push_sub_batch = int(v)
-        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps", "vber"):
+        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps", "vber", "hs"):
             setattr(cfg, k, int(v))
         else:
             setattr(cfg, k, v)

@@ -160,6 +160,79 @@ __global__ void k_deconv(DeconvArgs a, uint64_t *carry_out) {
   }
 }
 
+// ============================================== --hs: dvb_deconvol_sync_hard
+// dvb_deconvol_sync<u8>::run (dvb.h:633-660) over deconvol_poly2<u8,uint32_t,uint64_t,0x3ba,0x38f70>
+// (convolutional.h:96-187).  The reference convolves 32 symbols at a time with bit-sliced shift
+// registers; written out per position it is a GF(2) FIR over the remapped I/Q bits:
+//     decoded bit m = XOR_b  PD_I[b] & I[m-b]  ^  PD_Q[b] & Q[m-b]        (taps b = 0..4,  poly 0x3ba)
+//     error   bit m = XOR_b  PE_I[b] & I[m-b]  ^  PE_Q[b] & Q[m-b]        (taps b = 2..8,  poly 0x38f70)
+// with poly bit 2b+1 = I tap b, bit 2b = Q tap b, and (I,Q) = lut[alignment][symbol].  Errors are
+// counted over the second half of a 64-byte chunk (bits 256..511) for all four alignments on every
+// resync_period-th chunk; the best one decodes from the NEXT chunk on.  Everything is a function of
+// the position, so the chunks are processed in parallel; only the "which alignment is locked" chain
+// is walked by one thread over the (few) resync chunks.
+__device__ __constant__ uint8_t kHsLut[4][4] = {{0, 1, 2, 3}, {2, 0, 3, 1}, {1, 0, 3, 2}, {0, 2, 1, 3}};   // dvb.h:674-705
+
+// Remapped (I,Q) bit pair of the symbol at stream position n (n < 0: the carried history).
+__device__ __forceinline__ uint32_t hs_iq(const HsDeconvArgs &a, int64_t n, int sync) {
+  uint32_t sym;
+  if (n >= 0) sym = (__ldg(a.symbols + n) >> 16) & 3u;
+  else {
+    const int back = (int)(-n);                    // 1 = the symbol right in front of symbols[0]
+    if (back > a.hist_valid || back > 32) return 0; // registers start at zero (convolutional.h:92)
+    sym = (uint32_t)(a.hist >> (2 * (back - 1))) & 3u;
+  }
+  return kHsLut[sync][sym];
+}
+
+__device__ __forceinline__ uint32_t hs_fir_bit(const HsDeconvArgs &a, int64_t m, int sync, uint32_t poly, int ntaps) {
+  uint32_t acc = 0;
+  for (int b = 0; b < ntaps; ++b) {
+    const uint32_t sel = (poly >> (2 * b)) & 3u;   // bit 1: I tap, bit 0: Q tap
+    if (sel) acc ^= hs_iq(a, m - b, sync) & sel;
+  }
+  return (__popc(acc) & 1u);
+}
+
+// One CTA (4 warps = 4 alignments) per resync chunk: errors over bits 256..511 of the chunk.
+__global__ void __launch_bounds__(128) k_hs_errors(HsDeconvArgs a, uint64_t first_resync, uint32_t ngroups) {
+  const uint32_t g = blockIdx.x;
+  if (g >= ngroups) return;
+  const int sync = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)first_resync + (int64_t)g * a.resync_period;
+  uint32_t err = 0;
+  for (int k = 0; k < 8; ++k) err += hs_fir_bit(a, c * 512 + 256 + lane * 8 + k, sync, 0x38f70u, 9);
+  for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+  if (lane == 0) a.errors[g * 4 + sync] = err;
+}
+
+// The lock chain (dvb.h:640-657): chunk c is decoded with the alignment locked BEFORE its own vote.
+__global__ void k_hs_lock(HsDeconvArgs a, uint64_t first_resync) {
+  if (threadIdx.x || blockIdx.x) return;
+  int locked = a.locked;
+  uint64_t g = 0;
+  for (uint64_t c = 0; c < a.nchunks; ++c) {
+    a.lock_of_chunk[c] = (uint8_t)locked;
+    if (c >= first_resync && (c - first_resync) % (uint64_t)a.resync_period == 0) {
+      const uint32_t *e = a.errors + g * 4;
+      int best = 0; uint32_t eb = e[0];
+      for (int s = 1; s < 4; ++s) if (e[s] < eb) { eb = e[s]; best = s; }
+      locked = best;
+      ++g;
+    }
+  }
+  a.state_out[0] = locked;
+}
+
+__global__ void __launch_bounds__(256) k_hs_decode(HsDeconvArgs a) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.nchunks * 64) return;
+  const int sync = a.lock_of_chunk[j >> 6];
+  uint32_t byte = 0;
+  for (int k = 0; k < 8; ++k) byte = (byte << 1) | hs_fir_bit(a, (int64_t)(8 * j + k), sync, 0x3bau, 5);
+  a.out[j] = (uint8_t)byte;
+}
+
 // ================================================================= MPEG sync
 // mpeg_sync (dvb.h:742-874).  Locked tracking is data parallel (k_sync_flags +
 // a word-wise scan of the bad-sync mask); acquisition (run_searching,
@@ -565,6 +638,18 @@ k_derand_out(DerandArgs a) {
 }
 
 }  // namespace
+
+cudaError_t launch_hs_deconv(const HsDeconvArgs &a, cudaStream_t st, int *launches) {
+  *launches = 0;
+  if (!a.nchunks) return cudaSuccess;
+  // first chunk of the batch on which all alignments vote (resync_phase == 0)
+  const uint64_t first = (uint64_t)((a.resync_period - a.resync_phase) % a.resync_period);
+  const uint32_t ngroups = first < a.nchunks ? (uint32_t)((a.nchunks - first + a.resync_period - 1) / a.resync_period) : 0;
+  if (ngroups) { k_hs_errors<<<ngroups, 128, 0, st>>>(a, first, ngroups); ++*launches; }
+  k_hs_lock<<<1, 32, 0, st>>>(a, first); ++*launches;
+  k_hs_decode<<<(unsigned)((a.nchunks * 64 + 255) / 256), 256, 0, st>>>(a); ++*launches;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_deconv_carry(const DeconvArgs &a, uint64_t nsym, uint64_t *carry_out, cudaStream_t st) {
   if (a.nbytes) k_deconv_tiled<<<(unsigned)((a.nbytes + kDcBytes - 1) / kDcBytes), 256, 0, st>>>(a, nsym);

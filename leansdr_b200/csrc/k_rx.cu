@@ -160,6 +160,58 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
   return emitted;
 }
 
+// One input sample of fast_qpsk_receiver::run()'s inner loop (sdr.h:1024-1111).  Integer
+// arithmetic as in the reference (u_angle = uint16_t, signed long = 64 bits); the state lives in
+// RxRun's float fields as exactly representable integers.  cur/nxt are the u8 samples as the
+// front end converted them (value - 128, exact).
+__device__ __forceinline__ bool rx_sample_hs(const RxParams &p, RxRun &r, float2 cur, float2 nxt, uint32_t &word,
+                                             float &mu_emit) {
+  bool emitted = false;
+  int phase = (int)r.phase;
+  long long freqw = (long long)r.freqw;
+  if (r.mu < 1.0f) {
+    const uint32_t i0 = (uint32_t)((int)cur.x + 128) * 256u + (uint32_t)((int)cur.y + 128);
+    const uint32_t i1 = (uint32_t)((int)nxt.x + 128) * 256u + (uint32_t)((int)nxt.y + 128);
+    const uint32_t p0 = __ldg(p.hs_polar + i0), p1 = __ldg(p.hs_polar + i1);
+    const uint32_t a0 = (((p0 & 0xffffu) - (uint32_t)phase) & 0xffffu) >> 8;                        // sdr.h:1040
+    const uint32_t a1 = ((uint32_t)((long long)(p1 & 0xffffu) - ((long long)phase + freqw)) & 0xffffu) >> 8;
+    const uint32_t r0 = __ldg(p.hs_rect + a0 * 256u + ((p0 >> 16) >> 1));
+    const uint32_t r1 = __ldg(p.hs_rect + a1 * 256u + ((p1 >> 16) >> 1));
+    const int p0re = (int)(r0 & 0xffu), p0im = (int)(r0 >> 8), p1re = (int)(r1 & 0xffu), p1im = (int)(r1 >> 8);
+    // s.re = (int)(p0r->re + (p1r->re - p0r->re)*mu), stored in a u8 (sdr.h:1045-1046)
+    const uint32_t sre = (uint32_t)f2i_trunc(fadd((float)p0re, fmul((float)(p1re - p0re), r.mu))) & 0xffu;
+    const uint32_t sim = (uint32_t)f2i_trunc(fadd((float)p0im, fmul((float)(p1im - p0im), r.mu))) & 0xffu;
+    const uint32_t symbol_arg = __ldg(p.hs_polar + sre * 256u + sim) & 0xffffu;
+    const uint32_t q2s = 0x1320u;                                 // quadrant_to_symbol {0,2,3,1}, one nibble each
+    const uint32_t sym = (q2s >> (4 * (symbol_arg >> 14))) & 0xfu;
+    word = sym << 16;
+    mu_emit = r.mu;
+    emitted = true;
+    const long long pe = (long long)(int)(symbol_arg & 16383u) - 8192;                               // sdr.h:1063
+    phase = (int)(((long long)phase + ((pe * 2621 + 32768) >> 16)) & 0xffff);                        // freq_alpha = 0.04*65536
+    freqw += (pe * p.hs_freq_beta + 32768 * 256) >> 24;
+    r.h2pr = r.h1pr; r.h2pi = r.h1pi; r.h2cr = r.h1cr; r.h2ci = r.h1ci;
+    r.h1pr = r.h0pr; r.h1pi = r.h0pi; r.h1cr = r.h0cr; r.h1ci = r.h0ci;
+    const uint32_t cp = __ldg(p.hs_sincos + (((symbol_arg & 49152u) + 8192u) & 0xffffu));
+    r.h0pr = (float)sre; r.h0pi = (float)sim; r.h0cr = (float)(cp & 0xffu); r.h0ci = (float)(cp >> 8);
+    const int h0pr = (int)sre, h0pi = (int)sim, h0cr = (int)(cp & 0xffu), h0ci = (int)(cp >> 8);
+    const int h1pr = (int)r.h1pr, h1pi = (int)r.h1pi, h1cr = (int)r.h1cr, h1ci = (int)r.h1ci;
+    const int h2pr = (int)r.h2pr, h2pi = (int)r.h2pi, h2cr = (int)r.h2cr, h2ci = (int)r.h2ci;
+    const int muerr = ((int)(signed char)(h0pr - h2pr) * (h1cr - 128) + (int)(signed char)(h0pi - h2pi) * (h1ci - 128)) -
+                      ((int)(signed char)(h0cr - h2cr) * (h1pr - 128) + (int)(signed char)(h0ci - h2ci) * (h1pi - 128));
+    float mucorr = fmul((float)muerr, p.gain_mu);
+    if (mucorr < -0.1f) mucorr = -0.1f;
+    if (mucorr > 0.1f) mucorr = 0.1f;
+    r.mu = fadd(r.mu, mucorr);
+    r.mu = fadd(r.mu, p.omega);
+  }
+  r.mu = fsub(r.mu, 1.0f);
+  phase = (int)(((long long)phase + freqw) & 0xffff);
+  r.phase = (float)phase;
+  r.freqw = (float)freqw;
+  return emitted;
+}
+
 __device__ __forceinline__ void rx_chunk_begin(const RxParams &p, RxRun &r, int sampler) {
   if (sampler == 1) r.samp_freqw = r.freqw;  // linear_sampler::update_freq (sdr.h:620)
   if (sampler == 2) {                        // fir_sampler::update_freq (sdr.h:667-675)
@@ -170,6 +222,15 @@ __device__ __forceinline__ void rx_chunk_begin(const RxParams &p, RxRun &r, int 
     }
   }
   r.have_point = 0;
+}
+
+// End-of-chunk bookkeeping of fast_qpsk_receiver::run() (sdr.h:1122-1125): integer limits.
+__device__ __forceinline__ void rx_chunk_end_hs(const RxParams &p, RxRun &r) {
+  if (!p.allow_drift) {
+    const long long f = (long long)r.freqw, lo = (long long)p.min_freqw, hi = (long long)p.max_freqw;
+    if (f < lo || f > hi) r.freqw = (float)((hi + lo) / 2);
+  }
+  r.freq_tap = __fdiv_rn(r.freqw, 65536.0f);   // what freq_out reports (sdr.h:1133)
 }
 
 // End-of-chunk bookkeeping of cstln_receiver::run() (sdr.h:849-902).
@@ -330,7 +391,10 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
         if ((n & 1) == 0) { w = rp[(n >> 1) + 1]; nxt2 = make_float2(w.x, w.y); }
         else nxt2 = make_float2(w.z, w.w);
         uint32_t word; float mu_e;
-        if (rx_sample<SAMPLER>(p, r, cur, nxt, reinterpret_cast<const float2 *>(rp) + n, word, mu_e)) {
+        bool em;
+        if (SAMPLER == kRxSamplerHs) em = rx_sample_hs(p, r, cur, nxt, word, mu_e);
+        else em = rx_sample<SAMPLER>(p, r, cur, nxt, reinterpret_cast<const float2 *>(rp) + n, word, mu_e);
+        if (em) {
           if (phase_of_run == 1) {
             if (n_out < cap) out[n_out] = word;
             ++n_out;
@@ -357,7 +421,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
           a.sampled_flag[c] = r.have_point ? 1u : 0u;
           if (r.have_point) a.sampled[c] = make_float2(r.s_re, r.s_im);
         }
-        rx_chunk_end(p, r);
+        if (SAMPLER == kRxSamplerHs) rx_chunk_end_hs(p, r); else rx_chunk_end(p, r);
         // Measurements (sdr.h:904-913)
         r.meas_count += kRxChunk;
         while (r.meas_count >= p.meas_decimation) {
@@ -392,6 +456,7 @@ k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
   extern __shared__ __align__(128) unsigned char smem[];
   if (a.p.sampler == 0) rx_warp<0, TILE>(a, span_list, nlist, smem);
   else if (a.p.sampler == 1) rx_warp<1, TILE>(a, span_list, nlist, smem);
+  else if (a.p.sampler == kRxSamplerHs) rx_warp<kRxSamplerHs, TILE>(a, span_list, nlist, smem);
   else rx_warp<2, TILE>(a, span_list, nlist, smem);
 }
 

@@ -135,7 +135,27 @@ struct RxParams {
   uint32_t meas_decimation;
   // rrc sampler
   const float *rrc_coeffs; int rrc_n, rrc_sub;
+  // --hs: fast_qpsk_receiver (sampler == kRxSamplerHs).  The integer loop state travels in the
+  // float fields of RxState (phase: u16, freqw and the limits: integers below 2^24, hist: u8) --
+  // every value is exactly representable, so carry / warm-up / seam plumbing is shared.
+  const uint32_t *hs_polar; const uint16_t *hs_rect; const uint16_t *hs_sincos;
+  long long hs_freq_beta;    // (signed long)(0.0012*256*65536/omega*pll_adjustment), sdr.h:1002
 };
+constexpr int kRxSamplerHs = 3;
+
+// dvb_deconvol_sync_hard (dvb.h:612-707): per 64-byte chunk; see k_fec.cu.
+struct HsDeconvArgs {
+  const uint32_t *symbols;   // softsymbol words, hard symbol in bits 16..17
+  uint64_t nchunks;          // chunks of 512 symbols / 64 bytes
+  uint64_t hist;             // the 32 symbols in front of symbols[0], 2 bits each, newest in the LSBs
+  int hist_valid;            // how many of them exist (0 at the start of a stream)
+  int resync_phase, resync_period, locked;
+  uint32_t *errors;          // [ngroups][4] scratch
+  uint8_t *lock_of_chunk;    // [nchunks + 1] scratch: alignment each chunk is decoded with
+  uint8_t *out;              // nchunks * 64 bytes
+  int32_t *state_out;        // {locked after the batch}
+};
+cudaError_t launch_hs_deconv(const HsDeconvArgs &a, cudaStream_t st, int *launches);
 
 // 22 words, same layout as ldvb_get_rx_state (include/leandvb_b200.h).
 struct RxState {

@@ -123,6 +123,10 @@ struct ldvb_handle {
   double rx_sym_per_sample = 1;
   HypState hyp[4];
   HypState hyp2[4];          // --fastlock: auxiliary registers in2/n_in2/n_out2 (dvb.h:303-306)
+  // --hs: dvb_deconvol_sync_hard carry (dvb.h:662-672): the last 32 hard symbols (2 bits each, newest
+  // in the LSBs; every alignment's shift registers are a remapping of them), vote phase, lock
+  uint64_t hs_hist = 0; int hs_hist_valid = 0, hs_resync_phase = 0, hs_locked = 0;
+  DevBuf d_hs_polar, d_hs_rect, d_hs_sincos, d_hs_errors, d_hs_lock, d_hs_state;
   int locked = 0, skip = 0;
   DevBuf d_deconv_carry;
   // Viterbi (viterbi_sync)
@@ -357,6 +361,12 @@ void reset_carry(ldvb_handle *h) {
   rx_reset_state(h);
   h->rx_state.freqw = freqw;
   h->rx_state.freq_tap = freqw / 65536;
+  if (h->cfg.hs) {   // fast_qpsk_receiver: integer loop state, no AGC (sdr.h:957-987)
+    const long fw = h->cfg.Ftune ? (long)((h->cfg.Ftune / h->cfg.Fs) * 65536) : 0;
+    h->rx_state.est_insp = 0; h->rx_state.agc_gain = 0;
+    h->rx_state.freqw = (float)fw;
+    h->rx_state.freq_tap = (float)fw / 65536;
+  }
   if (h->use_fir && h->fir_current_freq != 0) {
     h->fir_shifted = shift_taps(h->fir_coeffs, 0);
     h->fir_current_freq = 0;
@@ -372,8 +382,9 @@ void reset_carry(ldvb_handle *h) {
   memset(&h->sync, 0, sizeof h->sync);
   h->sync.report_state = 1;
   h->sync.phase8 = -1;
-  h->sync.fastlock = h->cfg.fastlock ? 1 : 0;    // leandvb.cc:565
-  h->sync.resync_period = 1;                     // dvb.h:729 (and leandvb.cc:553 with --fastlock)
+  h->sync.fastlock = (h->cfg.fastlock || h->cfg.hs) ? 1 : 0;             // leandvb.cc:565, 862
+  h->sync.resync_period = (h->cfg.hs && !h->cfg.fastlock) ? 32 : 1;      // dvb.h:729, leandvb.cc:553, 863
+  h->hs_hist = 0; h->hs_hist_valid = 0; h->hs_resync_phase = 0; h->hs_locked = 0;
   h->derand_pos = 0;
   h->ts_queue_rd = h->ts_queue_wr = 0;
   memset(&h->meas, 0, sizeof h->meas);
@@ -430,6 +441,23 @@ void rx_setup(ldvb_handle *h) {
     p.rrc_n = (int)h->rrc_coeffs.size();
     p.rrc_sub = steps;
     h->readahead = p.rrc_n - 1;       // sdr.h:645
+  }
+  if (c.hs) {
+    // fast_qpsk_receiver (sdr.h:977-1005): set_omega(Fs/Fm), set_freq(Ftune/Fs), limits +-65536/max_omega/8
+    // in `signed long` arithmetic, freq_beta truncated to a long; all of them exact in a float.
+    p.sampler = kRxSamplerHs;
+    long fw = 0;
+    if (c.Ftune) fw = (long)((c.Ftune / c.Fs) * 65536);           // set_freq: freqw = freq * 65536
+    const long lo = (long)(fw - 65536 / max_omega / 8), hi = (long)(fw + 65536 / max_omega / 8);
+    p.min_freqw = (float)lo; p.max_freqw = (float)hi;
+    p.hs_freq_beta = (long long)(signed long)(0.0012 * 256 * 65536 / omega * 1.0f);
+    int mdh = (int)(c.Fs / c.Finfo);
+    p.meas_decimation = (uint32_t)std::max(mdh, 1);
+    rx_reset_state(h);
+    h->rx_state.est_insp = 0; h->rx_state.agc_gain = 0;
+    h->rx_state.freqw = (float)fw;
+    h->rx_state.freq_tap = (float)fw / 65536;
+    h->readahead = 1;                                                // sdr.h:1010: chunk_size + 1
   }
 }
 
@@ -489,7 +517,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
                     &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
-                    &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam,
+                    &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam, &h->d_hs_polar, &h->d_hs_rect, &h->d_hs_sincos, &h->d_hs_errors, &h->d_hs_lock, &h->d_hs_state,
                     &h->m_cnr.d_avg, &h->m_cnr.d_have, &h->m_spec.d_avg, &h->m_spec.d_have, &h->d_meas_carry[0], &h->d_meas_carry[1],
                     &h->d_meas_points, &h->d_meas_power, &h->d_meas_sums, &h->d_meas_rows};
   for (DevBuf *b : bufs) b->release();
@@ -524,6 +552,15 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     return code;
   };
   if (c.input_format < 0 || c.input_format > LDVB_FMT_F32) return bail(LDVB_EINVAL, "bad input_format");
+  if (c.hs) {
+    // run_highspeed (leandvb.cc:727-969): u8 input (:771-772), code rate 1/2 only (:845-846), QPSK by
+    // construction; that graph has no notch, rotator, filter, CNR or spectrum blocks.
+    if (c.input_format != LDVB_FMT_U8) return bail(LDVB_EINVAL, "--hs requires --u8");
+    if (c.fec != LDVB_FEC12) return bail(LDVB_EINVAL, "--hs currently supports code rate 1/2 only");
+    if (c.constellation != LDVB_CSTLN_QPSK || c.viterbi || c.resample || c.decim > 1 || c.Fderot != 0)
+      return bail(LDVB_EINVAL, "--hs: QPSK without --viterbi/--resample/--decim/--derotate");
+    h->cfg.anf = 0; h->cfg.cnr = 0; h->cfg.spectrum = 0; h->cfg.sampler = LDVB_SAMP_LINEAR; h->cfg.hard_metric = 0;
+  }
   if (c.cnr && c.Fm / c.Fs > 0.25f) return bail(LDVB_EINVAL, "CNR estimator requires Fsampling > 4x Fsignal");   // sdr.h:1283-1284
   if (c.sampler < 0 || c.sampler > 2) return bail(LDVB_EINVAL, "bad sampler");
   if (c.anf < 0 || c.anf > kNotchMaxSlots) return bail(LDVB_EINVAL, "anf must be 0..4");
@@ -604,6 +641,16 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   }
   h->Fs_rx = Fs;
   rx_setup(h);
+  if (c.hs) {
+    const HsTables ht = make_hs_tables();
+    if (upload(h->d_hs_polar, ht.polar.data(), ht.polar.size() * 4) != cudaSuccess ||
+        upload(h->d_hs_rect, ht.rect.data(), ht.rect.size() * 2) != cudaSuccess ||
+        upload(h->d_hs_sincos, ht.sincos.data(), ht.sincos.size() * 2) != cudaSuccess)
+      return bail(LDVB_ECUDA, "--hs tables upload");
+    h->rxp.hs_polar = h->d_hs_polar.as<uint32_t>();
+    h->rxp.hs_rect = h->d_hs_rect.as<uint16_t>();
+    h->rxp.hs_sincos = h->d_hs_sincos.as<uint16_t>();
+  }
   if (c.sampler == LDVB_SAMP_RRC) {
     if ((h->rxp.rrc_n + h->rxp.rrc_sub - 1) / h->rxp.rrc_sub > 6) return bail(LDVB_EINVAL, "RRC sampler: more than 6 taps per symbol");
     if (upload(h->d_rrc, h->rrc_coeffs.data(), h->rrc_coeffs.size() * 4) != cudaSuccess) return bail(LDVB_ECUDA, "rrc upload");
@@ -1495,7 +1542,55 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
       if (rc == 0) break;
     }
   }
-  for (int guard = 0; guard < (c.fastlock ? 4096 : 64) && !c.viterbi; ++guard) {
+  if (c.hs) {
+    // dvb_deconvol_sync_hard (dvb.h:633-660): whole 64-byte chunks, then mpeg_sync (fast search)
+    Stream &in = h->s_sym;
+    uint64_t nchunks = in.count / 512;
+    nchunks = std::min<uint64_t>(nchunks, (h->s_bytes.cap - h->s_bytes.count) / 64);
+    if (nchunks) {
+      const int period = c.fastlock ? 1 : 32;                       // leandvb.cc:853
+      const uint64_t ngroups = nchunks / period + 2;
+      if (h->d_hs_errors.bytes < ngroups * 16) { h->d_hs_errors.release(); CK(h->d_hs_errors.alloc(ngroups * 16 + 4096)); }
+      if (h->d_hs_lock.bytes < nchunks + 1) { h->d_hs_lock.release(); CK(h->d_hs_lock.alloc(nchunks + 4096)); }
+      if (!h->d_hs_state.p) CK(h->d_hs_state.alloc(64));
+      HsDeconvArgs a;
+      a.symbols = reinterpret_cast<const uint32_t *>(in.at(0));
+      a.nchunks = nchunks; a.hist = h->hs_hist; a.hist_valid = h->hs_hist_valid;
+      a.resync_phase = h->hs_resync_phase; a.resync_period = period; a.locked = h->hs_locked;
+      a.errors = h->d_hs_errors.as<uint32_t>(); a.lock_of_chunk = h->d_hs_lock.as<uint8_t>();
+      a.out = h->s_bytes.at(h->s_bytes.count);
+      a.state_out = h->d_hs_state.as<int32_t>();
+      int nl = 0;
+      KL("hs_deconv", launch_hs_deconv(a, h->st, &nl));
+      h->launches += (nl > 0 ? nl - 1 : 0);
+      // carry: lock, vote phase, the last 32 symbols of what was consumed
+      int32_t locked = 0;
+      uint32_t last[32];
+      const uint64_t used = nchunks * 512;
+      CK(cudaMemcpyAsync(&locked, h->d_hs_state.p, 4, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaMemcpyAsync(last, in.at(used - 32), sizeof last, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      h->hs_locked = locked;
+      h->hs_resync_phase = (int)((h->hs_resync_phase + nchunks) % (uint64_t)period);
+      uint64_t hist = 0;
+      for (int i = 0; i < 32; ++i) hist = (hist << 2) | ((last[i] >> 16) & 3u);
+      h->hs_hist = hist; h->hs_hist_valid = 32;
+      const uint64_t produced = nchunks * 64;
+      if (c.keep_taps) {
+        tap_bytes.resize(produced);
+        CK(cudaMemcpy(tap_bytes.data(), h->s_bytes.at(h->s_bytes.count), produced, cudaMemcpyDeviceToHost));
+      }
+      h->s_bytes.count += produced;
+      h->s_bytes.fresh += produced;
+      if ((rc = stream_consume(h, in, used, h->d_scratch))) return rc;
+    }
+    for (int guard = 0; guard < 1 << 20; ++guard) {
+      rc = run_sync(h);
+      if (rc < 0) return rc;
+      if (rc == 0) break;
+    }
+  }
+  for (int guard = 0; guard < (c.fastlock ? 4096 : 64) && !c.viterbi && !c.hs; ++guard) {
     if (h->skip) {  // dvb.h:415-416
       if (h->s_sym.count < (uint64_t)h->skip) break;
       if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
@@ -1854,7 +1949,7 @@ int shard_check(ldvb_handle *h, const ldvb_shard *s) {
   if (!h || !s) return LDVB_EINVAL;
   if (h->cfg.rx_mode != LDVB_RX_FAST) return fail(h, LDVB_EINVAL, "time sharding needs rx_mode = LDVB_RX_FAST");
   if (h->cfg.sampler == LDVB_SAMP_RRC) return fail(h, LDVB_EINVAL, "time sharding: RRC sampler not supported yet");
-  if (h->cfg.fastlock) return fail(h, LDVB_EINVAL, "time sharding: --fastlock not supported");
+  if (h->cfg.fastlock || h->cfg.hs) return fail(h, LDVB_EINVAL, "time sharding: --fastlock / --hs not supported");
   const uint64_t u = shard_unit(h);
   if (s->n_halo % u || s->n_chunk % u || s->abs_raw0 % u || s->n_halo_next % u)
     return fail(h, LDVB_EINVAL, "time sharding: abs_raw0, n_halo, n_chunk must be multiples of lcm(4096, 128*decimation)");

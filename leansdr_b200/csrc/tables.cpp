@@ -381,6 +381,30 @@ bool make_deconv(int fec, DeconvPolys *out) {
   return true;
 }
 
+HsTables make_hs_tables() {
+  HsTables t;
+  t.polar.resize(65536); t.rect.resize(65536); t.sincos.resize(65536);
+  for (int i = 0; i < 256; ++i)
+    for (int q = 0; q < 256; ++q) {
+      // (s_angle)(double) then assigned to a u_angle; (int)hypotf() assigned to an unsigned char
+      const uint16_t a = (uint16_t)(int16_t)(int32_t)(atan2f(q - 128, i - 128) * 65536 / (2 * M_PI));
+      const uint8_t r = (uint8_t)(int)hypotf(i - 128, q - 128);
+      t.polar[i * 256 + q] = (uint32_t)a | ((uint32_t)r << 16);
+    }
+  for (unsigned long a = 0; a < 65536; ++a) {
+    float f = 2 * M_PI * a / 65536;
+    const uint8_t re = (uint8_t)(128 + 75 * cosf(f)), im = (uint8_t)(128 + 75 * sinf(f));   // cstln_amp (sdr.h:287)
+    t.sincos[a] = (uint16_t)(re | (im << 8));
+  }
+  for (int a = 0; a < 256; ++a)
+    for (int r = 0; r < 256; ++r) {
+      const uint8_t re = (uint8_t)(int)(128 + r * cos(2 * M_PI * a / 256));
+      const uint8_t im = (uint8_t)(int)(128 + r * sin(2 * M_PI * a / 256));
+      t.rect[a * 256 + r] = (uint16_t)(re | (im << 8));
+    }
+  return t;
+}
+
 // ------------------------------------------------------------------- Viterbi
 
 bool make_trellis(int fec, Trellis *t) {

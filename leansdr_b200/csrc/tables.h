@@ -41,6 +41,12 @@ std::vector<float> shift_taps_resampler(const std::vector<float> &coeffs, float 
 // sdr.h:1231-1241: 65536 x cos then 65536 x sin.
 std::vector<float> make_rotator_lut(float freq);
 
+// fast_qpsk_receiver::init_lookup_tables (sdr.h:1144-1164), index = (u8)re * 256 + (u8)im:
+//   polar[i] = angle (u16) | magnitude (u8) << 16; rect[angle8 * 256 + r] = re | im << 8;
+//   sincos[angle16] = re | im << 8.
+struct HsTables { std::vector<uint32_t> polar; std::vector<uint16_t> rect, sincos; };
+HsTables make_hs_tables();
+
 struct DeconvPolys {
   int punctperiod = 0, punctweight = 0;
   uint64_t deconv[8] = {0}, deconv2[8] = {0};

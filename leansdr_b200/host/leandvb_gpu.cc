@@ -73,6 +73,7 @@ int main(int argc, const char *argv[]) {
     else if ( !strcmp(a,"--roll-off") && more ) cfg.rolloff = atof(argv[++i]);
     else if ( !strcmp(a,"--hard-metric") ) cfg.hard_metric = 1;
     else if ( !strcmp(a,"--fastlock") ) cfg.fastlock = 1;
+    else if ( !strcmp(a,"--hs") ) cfg.hs = 1;
     else if ( !strcmp(a,"--viterbi") ) cfg.viterbi = 1;
     else if ( !strcmp(a,"--standard") && more ) ++i;       // DVB-S only
     else if ( !strcmp(a,"--cr") && more ) {

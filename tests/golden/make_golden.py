@@ -5,6 +5,8 @@ where /root/reference is mounted and `make -C oracle ref` has built oracle/_ref)
   c1_160.ts            leandvb --u8 -f 2400e3 --sr 2000e3 --cr 1/2          < c1_160.u8
   c1_160_resample.ts   leandvb --u8 ... --resample                           < c1_160.u8
   c1_160_anf0.ts       leandvb --u8 ... --anf 0                              < c1_160.u8
+  c1_160_hs.ts         leandvb --u8 ... --hs                                 < c1_160.u8
+                       (`python make_golden.py hs` regenerates only this file)
   c1_160_taps.json     sha256 + sizes of every stream tapped by oracle/_ref/ref_tap (default flags)
   tables.json          sha256 of the constant tables dumped by oracle/_ref/ref_tables
   c1_160_spectrum_fs100k.f32  spectrum rows (p_spectrum) of ref_tap --u8 -f 100000 --sr 83333 < c1_160.u8
@@ -40,7 +42,15 @@ def tx_golden():
         kat[name] = {"samples": len(out) // 8, "sha256": sha(out), "cmd": " ".join(["leantsgen -c %d |" % npk, "leandvbtx"] + args[1:])}
     json.dump(kat, open(os.path.join(HERE, "tx_kat.json"), "w"), indent=1)
 
+def hs_golden():
+    iq = np.fromfile(os.path.join(HERE, "c1_160.u8"), np.uint8)
+    V.ref_leandvb(iq, ["--u8", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--hs"]).tofile(os.path.join(HERE, "c1_160_hs.ts"))
+
 def main():
+    if sys.argv[1:] == ["hs"]:
+        hs_golden()
+        print("hs golden regenerated")
+        return
     if sys.argv[1:] == ["tx"]:
         tx_golden()
         print("tx golden regenerated")
@@ -60,6 +70,7 @@ def main():
         taps[f] = {"bytes": len(b), "sha256": sha(b)}
     json.dump(taps, open(os.path.join(HERE, "c1_160_taps.json"), "w"), indent=1)
     spectrum_golden(iq)
+    hs_golden()
     d2 = tempfile.mkdtemp()
     subprocess.run([O.ref_bin("ref_tables"), d2], check=True)
     tabs = {f: {"bytes": os.path.getsize(os.path.join(d2, f)), "sha256": sha(open(os.path.join(d2, f), "rb").read())}

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "leandvb_gpu")),
                     reason="oracle/_ref/leandvb_gpu not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("fmt,flags", [("f32", ["--resample"]), ("u8", []), ("f32", ["--anf", "0", "--gpu-exact"])])
+@pytest.mark.parametrize("fmt,flags", [("f32", ["--resample"]), ("u8", []), ("f32", ["--anf", "0", "--gpu-exact"]),
+                                       ("u8", ["--hs", "--gpu-exact"]), ("u8", ["--hs"]), ("f32", ["--fastlock"])])
 def test_reference_scheduler_runs_gpu_runnable(product, oracle, fmt, flags):
     O = oracle
     raw = V.ref_iq(1500, fmt=fmt)

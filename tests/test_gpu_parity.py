@@ -397,3 +397,25 @@ def test_vber_rate_estimator(product, oracle):
     assert len(want) >= 4 and any(w > 0 for w in want)
     assert got.size in (len(want), len(want) + 1)          # the product drains one more packet at the end
     assert np.array_equal(got[: len(want)], np.array(want, np.float32))
+
+
+@pytest.mark.parametrize("mode,npk,noise,fastlock", [("exact", 300, None, False), ("exact", 300, 22, False),
+                                                     ("exact", 300, None, True), ("fast", 1500, None, False),
+                                                     ("fast", 1500, 22, False)])
+def test_hs_path(product, oracle, mode, npk, noise, fastlock):
+    """--hs (leandvb.cc:727-969): fast_qpsk_receiver<u8> (integer PLL, table-driven interpolation),
+    dvb_deconvol_sync_hard (bit-sliced deconvolution, alignment voted on every resync_period-th chunk),
+    mpeg_sync's fast search.  EXACT receiver mode: hard symbols, bytes, aligned bytes, RS packets and
+    TS bit-identical to the oracle (itself pinned to the reference runnables).  FAST mode: TS."""
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt="u8", noise_db=noise)
+    ref = O.hs_chain(raw, fastlock=fastlock)
+    got = run_product(P, raw, fmt="u8", hs=True, fastlock=fastlock, rx_mode=P.RX_EXACT if mode == "exact" else P.RX_FAST)
+    if mode == "exact":
+        sym = got["symbols"].reshape(-1, 4)[:, 2]
+        assert_prefix(sym, ref["symbols"], "hard symbols", slack=256)
+        assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=64)
+        assert_prefix(got["mpegbytes"], ref["mpegbytes"], "aligned bytes", slack=204)
+        assert_prefix(got["rspackets"], ref["rspackets"], "RS packets", slack=204)
+    assert_prefix(got["ts"], ref["ts"], "TS", slack=188)
+    assert len(got["ts"]) > npk - 80

@@ -271,3 +271,31 @@ def test_fastlock_chain_vs_reference_leandvb(oracle, cr, ratio, Fs, vit, exact):
     gw, gg = good(want), good(got)
     assert len(gg) > 300 and gg == list(range(gg[0], gg[-1] + 1))       # contiguous numbered packets
     assert gw[-1] == gg[-1] and gg[0] - gw[0] < 64                       # same end, start within the schedule slack
+
+
+# ------------------------------------------------------------------ --hs
+
+def test_hs_oracle_equals_reference_golden(oracle):
+    """`leandvb --hs` (fast_qpsk_receiver + dvb_deconvol_sync_hard, leandvb.cc:727-969) on the committed
+    fixture: the oracle's TS equals the golden made by the unmodified reference binary."""
+    want = np.fromfile(os.path.join(GOLDEN, "c1_160_hs.ts"), dtype=np.uint8).reshape(-1, 188)
+    got = oracle.hs_chain(_golden_iq())["ts"]
+    assert len(want) > 100 and len(got) == len(want) and np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not V.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("noise", [None, 22])
+def test_hs_oracle_equals_tapped_reference_runnables(oracle, noise):
+    """Hard symbols, bytes, aligned bytes (oracle/_ref/ref_hs taps the UNMODIFIED runnables) and the
+    TS of `leandvb --hs`, bit for bit including the lengths."""
+    O = oracle
+    raw = V.ref_iq(300, fmt="u8", noise_db=noise)
+    want_ts = V.ref_leandvb(raw, ["--u8", "--hs", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2"])
+    d = tempfile.mkdtemp()
+    subprocess.run([O.ref_bin("ref_hs"), "2400e3", "2000e3", "32", os.path.join(d, "o")], input=raw.tobytes(),
+                   stdout=subprocess.DEVNULL, check=True)
+    t = O.hs_chain(raw)
+    for key, ext in (("symbols", "symbols"), ("bytes", "bytes"), ("mpegbytes", "mpeg")):
+        ref = np.fromfile(os.path.join(d, "o." + ext), np.uint8)
+        assert ref.size == t[key].size and np.array_equal(ref, t[key].reshape(-1)), key
+    assert len(want_ts) > 200 and len(t["ts"]) == len(want_ts) and np.array_equal(t["ts"], want_ts)
