@@ -100,7 +100,7 @@ def gen_vector_device(npackets: int, dev, torch, P):
     return out
 
 
-def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int):
+def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int, flags=None):
     """Times oracle/_ref/leandvb on `raw` (page-cached file), `replicas` processes at once.
     Returns (MS/s aggregate, TS bytes of one replica)."""
     from oracle import oracle as O
@@ -115,7 +115,7 @@ def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int):
             procs = []
             for r in range(replicas):
                 out = subprocess.PIPE if r == 0 else subprocess.DEVNULL
-                procs.append(subprocess.Popen([O.ref_bin("leandvb"), *REF_FLAGS], stdin=open(path, "rb"),
+                procs.append(subprocess.Popen([O.ref_bin("leandvb"), *(flags or REF_FLAGS)], stdin=open(path, "rb"),
                                               stdout=out, stderr=subprocess.DEVNULL))
             ts0 = procs[0].stdout.read()
             for p in procs:
@@ -285,6 +285,9 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", default="f32", choices=["f32", "u8", "hs"],
+                    help="side measurements (N = 1): 'u8' = the same chain fed complex<u8> IQ (leandvb --u8), 'hs' = leandvb --u8 --hs "
+                         "(fast_qpsk_receiver path).  The default 'f32' is BASELINE.json's configuration.")
     ap.add_argument("--cpu-gen", action="store_true", help="synthesise the IQ with the reference binaries on the host "
                     "instead of the B200 transmit chain (N = 1)")
     ap.add_argument("--shard", default="time", choices=["time", "streams"],
@@ -300,6 +303,15 @@ def main():
     workload = {"workload": "C2: leantsgen|leandvbtx -f 6/5 --power 37.5 --agc -> leandvb --f32 --resample "
                             "-f 2400e3 --sr 2000e3 --cr 1/2 (QPSK, 1.2 samples/symbol, 5-tap FIR, anf=%d)" % a.anf,
                 "packets": a.packets}
+
+    ref_flags = list(REF_FLAGS)
+    rx_kw = dict(fmt="f32", resample=True)
+    if a.variant != "f32":
+        if a.impl == "reference" or world > 1:
+            raise SystemExit("--variant is a single-GPU side measurement of the b200 arm")
+        ref_flags = ["--u8", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--standard", "DVB-S"] + (["--hs"] if a.variant == "hs" else ["--resample"])
+        rx_kw = dict(fmt="u8", hs=True) if a.variant == "hs" else dict(fmt="u8", resample=True)
+        workload["workload"] = "SIDE MEASUREMENT, not BASELINE.json's configuration: same waveform as complex<u8> IQ -> leandvb " + " ".join(ref_flags)
 
     # ---------------------------------------------------------------- reference arm
     if a.impl == "reference":
@@ -356,9 +368,13 @@ def main():
         if rank == 0:
             head = gen_vector(min(a.packets, 2048))          # the unmodified reference transmitter, same packets
             vector_check = bool(head.size > 1000000 and np.array_equal(head.view(np.uint32), raw[: head.size].view(np.uint32)))
+    if a.variant != "f32":
+        # leanchansim --ou8 = cconverter<f32,0,u8,128,1,1> (dsp.h:33-54): (u8)(128 + x), truncating
+        iq_dev = (iq_dev + 128.0).to(torch.uint8)
+        raw = iq_dev.cpu().numpy()
     n = raw.size // 2
     mode = P.RX_FAST if a.mode == "fast" else P.RX_EXACT
-    rx = P.Receiver(fmt="f32", resample=True, anf=a.anf, rx_mode=mode, max_batch=n, device=local)
+    rx = P.Receiver(anf=a.anf, rx_mode=mode, max_batch=n, device=local, **rx_kw)
     stream = torch.cuda.current_stream()
     rx.set_stream(stream.cuda_stream)
     cap = n // 1900 + 64
@@ -431,8 +447,8 @@ def main():
     sym = meas["symbols"]
     omega = 1.2
     alg_bytes = {                      # per launch, see DESIGN.md "Kernels"
-        "frontend": n * (8 + 8),                      # cf32 in + cf32 out (FIR, D=1)
-        "notch_apply": n * (8 + 8),
+        "frontend": n * ((8 if a.variant == "f32" else 2) + 8),   # IQ in + cf32 out (FIR, D=1)
+        "notch_apply": n * ((8 if a.variant == "f32" else 2) + 8),
         "rx": n * 8 + sym * 4,                        # cf32 in + softsymbol out
         "rx_compact": sym * 8,
         "deconv_carry": sym * 4 + sym // 8,
@@ -463,19 +479,19 @@ def main():
     if not a.no_cpu:
         sample_pk = min(a.packets, 16384)
         sample = raw[: 2 * min(n, sample_pk * 1958)]
-        v, ts_ref = run_reference_cpu(sample, 1, 3)
+        v, ts_ref = run_reference_cpu(sample, 1, 3, ref_flags)
         ref_pk = np.frombuffer(ts_ref, dtype=np.uint8).reshape(-1, 188)
         k = min(len(ref_pk), len(ts_gpu))
         ts_match = bool(k > 0 and np.array_equal(ref_pk[:k], ts_gpu[:k]) and
                         (len(ts_gpu) >= len(ref_pk) if sample.size == raw.size else True))
         cpu = {"value": v, "unit": "MS/s", "cores": 1, "kind": "reference",
-               "sample": f"oracle/_ref/leandvb {' '.join(REF_FLAGS)} on the first {sample.size // 2} samples of the same "
+               "sample": f"oracle/_ref/leandvb {' '.join(ref_flags)} on the first {sample.size // 2} samples of the same "
                          f"vector (best of 3, file in page cache); host has {os.cpu_count()} cores, the reference uses 1"}
 
     line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {**workload, "samples_per_step_per_gpu": n, "rx_mode": a.mode,
+            "dtype": "f32" if a.variant != "hs" else "int (u8/u16 angles, 64-bit PLL)", "data": "synthetic",
+            "config": {**workload, "samples_per_step_per_gpu": n, "rx_mode": a.mode, "variant": a.variant,
                        "l2": "input batch (%d MB) larger than L2, re-read every step" % (raw.nbytes >> 20),
                        "parallelism": "time spans inside one GPU; one independent stream per GPU"},
             "clocks": clk,

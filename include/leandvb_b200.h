@@ -111,7 +111,7 @@ typedef struct ldvb_config {
   uint32_t span_chunks;      /* FAST: 128-sample chunks per span (0 = auto)  */
   uint32_t warmup_chunks;    /* FAST: warm-up chunks before a span (0 = auto)*/
   int32_t  keep_taps;        /* keep intermediate streams for ldvb_tap()     */
-  int32_t  push_sub_batch;   /* ldvb_push: samples per pipelined sub-batch (0 = 24 Mi) */
+  int32_t  push_sub_batch;   /* ldvb_push: samples per pipelined sub-batch (0 = 192 MiB of input) */
   int32_t  cnr;              /* --cnr: cnr_fft (sdr.h:1273-1345), needs Fs > 4 Fm */
   int32_t  spectrum;         /* spectrum (sdr.h:1347-1404); leandvb always runs it
                                 (leandvb.cc:333-343), ldvb_config_default sets 1 */

@@ -206,30 +206,67 @@ __global__ void __launch_bounds__(128) k_hs_errors(HsDeconvArgs a, uint64_t firs
   if (lane == 0) a.errors[g * 4 + sync] = err;
 }
 
-// The lock chain (dvb.h:640-657): chunk c is decoded with the alignment locked BEFORE its own vote.
-__global__ void k_hs_lock(HsDeconvArgs a, uint64_t first_resync) {
+// The lock chain (dvb.h:640-657), walked over the resync chunks only: lock_of_chunk[g] = alignment
+// in force AFTER the vote of group g (the chunks behind the voting chunk, up to the next vote).
+__global__ void k_hs_lock(HsDeconvArgs a, uint32_t ngroups) {
   if (threadIdx.x || blockIdx.x) return;
   int locked = a.locked;
-  uint64_t g = 0;
-  for (uint64_t c = 0; c < a.nchunks; ++c) {
-    a.lock_of_chunk[c] = (uint8_t)locked;
-    if (c >= first_resync && (c - first_resync) % (uint64_t)a.resync_period == 0) {
-      const uint32_t *e = a.errors + g * 4;
-      int best = 0; uint32_t eb = e[0];
-      for (int s = 1; s < 4; ++s) if (e[s] < eb) { eb = e[s]; best = s; }
-      locked = best;
-      ++g;
-    }
+  for (uint32_t g = 0; g < ngroups; ++g) {
+    const uint32_t *e = a.errors + (size_t)g * 4;
+    int best = 0; uint32_t eb = e[0];
+    for (int s = 1; s < 4; ++s) if (e[s] < eb) { eb = e[s]; best = s; }
+    locked = best;
+    a.lock_of_chunk[g] = (uint8_t)locked;
   }
   a.state_out[0] = locked;
 }
 
-__global__ void __launch_bounds__(256) k_hs_decode(HsDeconvArgs a) {
+// Thread per output byte: the 12 symbols 8j-4 .. 8j+7 are remapped once into two bit strings, the
+// eight decoded bits are parities of shifted windows (taps b = 0..4 of poly 0x3ba).
+__global__ void __launch_bounds__(256) k_hs_decode(HsDeconvArgs a, uint64_t first_resync) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.nchunks * 64) return;
-  const int sync = a.lock_of_chunk[j >> 6];
+  // chunk c is decoded with the alignment locked BEFORE its own vote
+  const uint64_t c = j >> 6;
+  int sync = a.locked;
+  if (c >= first_resync) {
+    const uint64_t g = (c - first_resync) / (uint64_t)a.resync_period;
+    const bool voting = (c - first_resync) % (uint64_t)a.resync_period == 0;
+    if (!voting) sync = a.lock_of_chunk[g];
+    else if (g) sync = a.lock_of_chunk[g - 1];
+  }
+  uint32_t I = 0, Q = 0;      // bit i = symbol 8j - 4 + i
+  if (j) {
+    const uint4 *w = reinterpret_cast<const uint4 *>(a.symbols + 8 * j - 4);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const uint4 v = __ldg(w + q);
+      const uint32_t sy[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t iq = kHsLut[sync][(sy[t] >> 16) & 3u];
+        I |= (iq >> 1) << (4 * q + t); Q |= (iq & 1u) << (4 * q + t);
+      }
+    }
+  } else {
+    for (int i = 0; i < 12; ++i) {
+      const uint32_t iq = hs_iq(a, (int64_t)i - 4, sync);
+      I |= (iq >> 1) << i; Q |= (iq & 1u) << i;
+    }
+  }
+  // decoded bit k (position 8j + k) = XOR_b PD_I[b] & I[k + 4 - b] ^ PD_Q[b] & Q[k + 4 - b]
   uint32_t byte = 0;
-  for (int k = 0; k < 8; ++k) byte = (byte << 1) | hs_fir_bit(a, (int64_t)(8 * j + k), sync, 0x3bau, 5);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const uint32_t sel = (0x3bau >> (2 * b)) & 3u;
+      if (sel & 2u) acc ^= (I >> (k + 4 - b)) & 1u;
+      if (sel & 1u) acc ^= (Q >> (k + 4 - b)) & 1u;
+    }
+    byte = (byte << 1) | acc;
+  }
   a.out[j] = (uint8_t)byte;
 }
 
@@ -646,8 +683,8 @@ cudaError_t launch_hs_deconv(const HsDeconvArgs &a, cudaStream_t st, int *launch
   const uint64_t first = (uint64_t)((a.resync_period - a.resync_phase) % a.resync_period);
   const uint32_t ngroups = first < a.nchunks ? (uint32_t)((a.nchunks - first + a.resync_period - 1) / a.resync_period) : 0;
   if (ngroups) { k_hs_errors<<<ngroups, 128, 0, st>>>(a, first, ngroups); ++*launches; }
-  k_hs_lock<<<1, 32, 0, st>>>(a, first); ++*launches;
-  k_hs_decode<<<(unsigned)((a.nchunks * 64 + 255) / 256), 256, 0, st>>>(a); ++*launches;
+  k_hs_lock<<<1, 32, 0, st>>>(a, ngroups); ++*launches;
+  k_hs_decode<<<(unsigned)((a.nchunks * 64 + 255) / 256), 256, 0, st>>>(a, first); ++*launches;
   return cudaGetLastError();
 }
 

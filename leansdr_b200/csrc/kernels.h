@@ -151,7 +151,7 @@ struct HsDeconvArgs {
   int hist_valid;            // how many of them exist (0 at the start of a stream)
   int resync_phase, resync_period, locked;
   uint32_t *errors;          // [ngroups][4] scratch
-  uint8_t *lock_of_chunk;    // [nchunks + 1] scratch: alignment each chunk is decoded with
+  uint8_t *lock_of_chunk;    // [ngroups] scratch: alignment in force after the vote of group g
   uint8_t *out;              // nchunks * 64 bytes
   int32_t *state_out;        // {locked after the batch}
 };

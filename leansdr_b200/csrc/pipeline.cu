@@ -657,7 +657,9 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     h->rxp.rrc_coeffs = h->d_rrc.as<float>();
   }
   // Host batches larger than this are pipelined (copy/compute overlap); push_sub_batch overrides.
-  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : (uint64_t)24 << 20;
+  // Default: 192 MiB of input per sub-batch (24 Mi cf32 samples, 96 Mi complex<u8> samples): the copy of a
+  // sub-batch has to outlast the chain on the previous one, whose cost per sample does not depend on the format.
+  h->sub_batch = c.push_sub_batch > 0 ? (uint64_t)c.push_sub_batch : ((uint64_t)192 << 20) / h->bps_in;
 
   // ---- stream buffers
   const uint64_t M = c.max_batch;
