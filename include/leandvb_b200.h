@@ -58,7 +58,12 @@ enum {
  * (sdr.h:305-311), code_rate (dvb.h:36-40), config::sampler (leandvb.cc:70). */
 enum { LDVB_FMT_U8 = 0, LDVB_FMT_S8 = 1, LDVB_FMT_U16 = 2, LDVB_FMT_S16 = 3,
        LDVB_FMT_F32 = 4 };
-enum { LDVB_CSTLN_BPSK = 0, LDVB_CSTLN_QPSK = 1, LDVB_CSTLN_8PSK = 2 };
+/* cstln_lut<256>::predef (sdr.h:305-311).  The APSK ring ratios follow the code rate
+ * (make_dvbs2_constellation, dvb.h:45-81): 16APSK needs 2/3, 3/4 or 5/6, 32APSK 3/4 or 5/6;
+ * other combinations are LDVB_EINVAL where the reference fail()s. */
+enum { LDVB_CSTLN_BPSK = 0, LDVB_CSTLN_QPSK = 1, LDVB_CSTLN_8PSK = 2,
+       LDVB_CSTLN_16APSK = 3, LDVB_CSTLN_32APSK = 4, LDVB_CSTLN_64APSKE = 5,
+       LDVB_CSTLN_16QAM = 6, LDVB_CSTLN_64QAM = 7, LDVB_CSTLN_256QAM = 8 };
 enum { LDVB_FEC12 = 0, LDVB_FEC23 = 1, LDVB_FEC46 = 2, LDVB_FEC34 = 3,
        LDVB_FEC56 = 4, LDVB_FEC78 = 5 };
 enum { LDVB_SAMP_NEAREST = 0, LDVB_SAMP_LINEAR = 1, LDVB_SAMP_RRC = 2 };

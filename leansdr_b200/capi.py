@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("LDVB_LIB") or os.path.join(_HERE, "libleandvb_b200.so
 ABI_VERSION = 1
 FMT = {"u8": 0, "s8": 1, "u16": 2, "s16": 3, "f32": 4}
 FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16, "f32": np.float32}
-CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2}
+CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2, "16APSK": 3, "32APSK": 4, "64APSKe": 5,
+         "16QAM": 6, "64QAM": 7, "256QAM": 8}
 FEC = {"1/2": 0, "2/3": 1, "4/6": 2, "3/4": 3, "5/6": 4, "7/8": 5}
 SAMPLER = {"nearest": 0, "linear": 1, "rrc": 2}
 RX_EXACT, RX_FAST = 0, 1

@@ -127,7 +127,7 @@ struct CstlnCellDev { int16_t cost, symbol, phase_error, pad; };
 struct RxParams {
   const CstlnCellDev *cstln;   // [65536]
   const float2 *trig;          // [65536]
-  int8_t sym_re[32], sym_im[32];
+  int8_t sym_re[256], sym_im[256];
   int nsymbols, sampler;
   float omega, min_freqw, max_freqw;
   float freq_alpha, freq_beta, gain_mu, kest;

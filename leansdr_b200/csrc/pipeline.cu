@@ -402,7 +402,7 @@ void rx_setup(ldvb_handle *h) {
   const ldvb_config &c = h->cfg;
   RxParams &p = h->rxp;
   memset(&p, 0, sizeof p);
-  for (int s = 0; s < h->cst.nsymbols && s < 32; ++s) {
+  for (int s = 0; s < h->cst.nsymbols && s < 256; ++s) {
     p.sym_re[s] = h->cst.sym_re[s];
     p.sym_im[s] = h->cst.sym_im[s];
   }
@@ -414,7 +414,8 @@ void rx_setup(ldvb_handle *h) {
   const float tol = 10e-6;
   const float max_omega = omega * (1 + tol);
   int n = 4;
-  switch (h->cst.nsymbols) { case 2: n = 2; break; case 4: n = 4; break; case 8: n = 8; break; default: n = 4; }
+  switch (h->cst.nsymbols) { case 2: n = 2; break; case 4: n = 4; break; case 8: n = 8; break;
+                             case 16: n = 12; break; case 32: n = 16; break; default: n = 4; }
   float freqw = 0;
   if (c.Ftune) freqw = (c.Ftune / h->Fs_rx) * 65536;  // set_freq (sdr.h:745-749)
   // The constructor's set_freq(0)/set_omega(1) are overwritten by these calls;
@@ -569,10 +570,10 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return bail(LDVB_ECUDA, "stream");
 
   // ---- tables
-  h->cst = make_cstln(c.constellation, c.hard_metric != 0);
+  h->cst = make_cstln(c.constellation, c.fec, c.hard_metric != 0);
   if (h->cst.nsymbols == 0) return bail(LDVB_EINVAL, "constellation not supported");
   int fec = c.fec;
-  if (c.viterbi && fec == LDVB_FEC23 && h->cst.nsymbols == 4) fec = LDVB_FEC46;  // leandvb.cc:533-537
+  if (c.viterbi && fec == LDVB_FEC23 && (h->cst.nsymbols == 4 || h->cst.nsymbols == 64)) fec = LDVB_FEC46;  // leandvb.cc:533-537
   if (!c.viterbi && !make_deconv(fec, &h->dec)) return bail(LDVB_EINVAL, "code rate not supported");
   if (c.viterbi) {
     if (!make_trellis(fec, &h->trellis)) return bail(LDVB_EINVAL, "code rate not supported by the Viterbi decoder");
@@ -2433,7 +2434,7 @@ static int host_table(const ldvb_config &c, int which, std::vector<uint8_t> &blo
   else if (c.decim > 1) Fs /= c.decim;
   switch (which) {
     case LDVB_TABLE_CSTLN: {
-      Cstln cs = make_cstln(c.constellation, c.hard_metric != 0);
+      Cstln cs = make_cstln(c.constellation, c.fec, c.hard_metric != 0);
       if (!cs.nsymbols) return LDVB_EINVAL;
       put(cs.cells.data(), cs.cells.size() * sizeof(CstlnCell));
       break;
@@ -2463,7 +2464,7 @@ static int host_table(const ldvb_config &c, int which, std::vector<uint8_t> &blo
     }
     case LDVB_TABLE_VITMAP: {
       Trellis t;
-      Cstln cs = make_cstln(c.constellation, c.hard_metric != 0);
+      Cstln cs = make_cstln(c.constellation, c.fec, c.hard_metric != 0);
       if (!cs.nsymbols || !make_trellis(c.fec, &t)) return LDVB_EINVAL;
       VitSyncs v = make_vitsyncs(cs, t);
       blob.push_back((uint8_t)v.nsyncs); blob.push_back((uint8_t)v.nshifts);

@@ -28,12 +28,68 @@ void put_point(Cstln &c, int s, float r, int n, float i) {
   c.sym_im[s] = (int8_t)(r * sinf(a) * kCstlnAmp);
 }
 
+// polar2() (sdr.h:497-504): four points at angles a*pi (float angle, double M_PI).
+void put_polar2(Cstln &c, int i, float r, float a0, float a1, float a2, float a3) {
+  const float a[4] = {a0, a1, a2, a3};
+  for (int j = 0; j < 4; ++j) {
+    float phi = (float)((double)a[j] * M_PI);
+    c.sym_re[i + j] = (int8_t)(r * cosf(phi) * kCstlnAmp);
+    c.sym_im[i + j] = (int8_t)(r * sinf(phi) * kCstlnAmp);
+  }
+}
+
+// make_qam() (sdr.h:505-528): m x m grid, x-major, unit average power.
+void put_qam(Cstln &c, int n) {
+  c.nsymbols = n; c.nrotations = 4;
+  int m = (int)sqrtl((long double)n);
+  float scale;
+  {
+    int q = m / 2;
+    float avgpower = (float)(2 * (q * 0.25 + (q - 1) * q / 2 + (q - 1) * q * (2 * q - 1) / 6) / q);
+    scale = (float)(1.0 / sqrtf(avgpower));
+  }
+  int s = 0;
+  for (int x = 0; x < m; ++x)
+    for (int y = 0; y < m; ++y) {
+      float I = x - (float)(m - 1) / 2;
+      float Q = y - (float)(m - 1) / 2;
+      c.sym_re[s] = (int8_t)(I * scale * kCstlnAmp);
+      c.sym_im[s] = (int8_t)(Q * scale * kCstlnAmp);
+      ++s;
+    }
+}
+
+// make_dvbs2_constellation (dvb.h:45-81): APSK ring ratios per code rate.  Only the DVB-S
+// rates exist behind this ABI; a rate the reference rejects returns false.
+bool apsk_gammas(int kind, int fec, float *g1, float *g2, float *g3) {
+  *g1 = *g2 = *g3 = 1;
+  if (kind == 3) {         // APSK16, EN 302 307 table 9
+    switch (fec) {
+      case 1: case 2: *g1 = 3.15; return true;   // 2/3, 4/6
+      case 3: *g1 = 2.85; return true;           // 3/4
+      case 4: *g1 = 2.70; return true;           // 5/6
+      default: return false;
+    }
+  }
+  if (kind == 4) {         // APSK32, table 10
+    switch (fec) {
+      case 3: *g1 = 2.84; *g2 = 5.27; return true;
+      case 4: *g1 = 2.64; *g2 = 4.64; return true;
+      default: return false;
+    }
+  }
+  if (kind == 5) { *g1 = 2.4; *g2 = 4.3; *g3 = 7; }   // APSK64E, EN 302 307-2 table 13f
+  return true;
+}
+
 }  // namespace
 
-Cstln make_cstln(int kind, bool harden) {
+Cstln make_cstln(int kind, int fec, bool harden) {
   Cstln c;
   c.sym_re.assign(256, 0);
   c.sym_im.assign(256, 0);
+  float g1, g2, g3;
+  if (!apsk_gammas(kind, fec, &g1, &g2, &g3)) return c;
   switch (kind) {
     case 0:  // BPSK at 45 degrees (sdr.h:315-327)
       c.nsymbols = 2; c.nrotations = 2;
@@ -51,6 +107,56 @@ Cstln make_cstln(int kind, bool harden) {
       for (int s = 0; s < 8; ++s) put_point(c, s, 1, 8, (float)o[s]);
       break;
     }
+    case 3: {  // 16APSK (sdr.h:355-381): 12 points on the outer ring, 4 inside
+      static const float o[12] = {1.5f, 10.5f, 4.5f, 7.5f, 0.5f, 11.5f, 5.5f, 6.5f, 2.5f, 9.5f, 3.5f, 8.5f};
+      static const float q[4] = {0.5f, 3.5f, 1.5f, 2.5f};
+      float r1 = sqrtf(4 / (1 + 3 * g1 * g1));
+      float r2 = g1 * r1;
+      c.nsymbols = 16; c.nrotations = 4;
+      for (int s = 0; s < 12; ++s) put_point(c, s, r2, 12, o[s]);
+      for (int s = 0; s < 4; ++s) put_point(c, 12 + s, r1, 4, q[s]);
+      break;
+    }
+    case 4: {  // 32APSK (sdr.h:382-424): rings of 4, 12 and 16 points
+      // {ring (1..3), position}; ring 1 has 4 positions, ring 2 twelve, ring 3 sixteen.
+      static const struct { int ring; float i; } t[32] = {
+        {2, 1.5f}, {2, 2.5f}, {2, 10.5f}, {2, 9.5f}, {2, 4.5f}, {2, 3.5f}, {2, 7.5f}, {2, 8.5f},
+        {3, 1}, {3, 3}, {3, 14}, {3, 12}, {3, 6}, {3, 4}, {3, 9}, {3, 11},
+        {2, 0.5f}, {1, 0.5f}, {2, 11.5f}, {1, 3.5f}, {2, 5.5f}, {1, 1.5f}, {2, 6.5f}, {1, 2.5f},
+        {3, 0}, {3, 2}, {3, 15}, {3, 13}, {3, 7}, {3, 5}, {3, 8}, {3, 10}};
+      float r1 = sqrtf(8 / (1 + 3 * g1 * g1 + 4 * g2 * g2));
+      float r2 = g1 * r1;
+      float r3 = g2 * r1;
+      c.nsymbols = 32; c.nrotations = 4;
+      for (int s = 0; s < 32; ++s) {
+        if (t[s].ring == 1) put_point(c, s, r1, 4, t[s].i);
+        else if (t[s].ring == 2) put_point(c, s, r2, 12, t[s].i);
+        else put_point(c, s, r3, 16, t[s].i);
+      }
+      break;
+    }
+    case 5: {  // 64APSK "E" (sdr.h:425-452): rings of 4, 12, 20 and 28 points
+      float r1 = sqrtf(64 / (4 + 12 * g1 * g1 + 20 * g2 * g2 + 28 * g3 * g3));
+      float r2 = g1 * r1;
+      float r3 = g2 * r1;
+      float r4 = g3 * r1;
+      c.nsymbols = 64; c.nrotations = 4;
+      // Groups of four points that are mirror images of each other: the first angle (in
+      // units of pi/den) fixes the other three (2 - a, 1 - a, 1 + a).
+      static const struct { int ring; int num, den; } t[16] = {
+        {4, 1, 4}, {4, 13, 28}, {4, 1, 28}, {1, 1, 4}, {4, 9, 28}, {4, 11, 28}, {3, 1, 20}, {2, 1, 12},
+        {4, 5, 28}, {3, 9, 20}, {4, 3, 28}, {2, 5, 12}, {3, 1, 4}, {3, 7, 20}, {3, 3, 20}, {2, 1, 4}};
+      const float rr[5] = {0, r1, r2, r3, r4};
+      for (int g = 0; g < 16; ++g) {
+        const double n = t[g].num, d = t[g].den;
+        put_polar2(c, 4 * g, rr[t[g].ring], (float)(n / d), (float)((2 * d - n) / d),
+                   (float)((d - n) / d), (float)((d + n) / d));
+      }
+      break;
+    }
+    case 6: put_qam(c, 16); break;
+    case 7: put_qam(c, 64); break;
+    case 8: put_qam(c, 256); break;
     default:
       return c;  // nsymbols == 0 signals "unsupported"
   }

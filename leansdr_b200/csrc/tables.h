@@ -21,7 +21,8 @@ struct Cstln {
   std::vector<std::vector<uint8_t>> rot;
 };
 
-Cstln make_cstln(int kind, bool harden);                 // sdr.h:313-573
+// kind = LDVB_CSTLN_*, fec = LDVB_FEC* (APSK ring ratios depend on it, dvb.h:45-81).
+Cstln make_cstln(int kind, int fec, bool harden);        // sdr.h:313-573
 std::vector<float> make_trig16();                        // math.h:95-111, 65536 x {cos,sin}
 void make_rs_tables(uint8_t exp512[512], uint8_t log256[256]);  // rs.h:49-60
 std::vector<uint8_t> make_derand_pattern();              // dvb.h:1116-1129

@@ -541,12 +541,12 @@ int ldvbtx_create(const ldvbtx_config *cfg, ldvbtx_handle **out) {
   if (!h) return LDVB_ENOMEM;
   h->cfg = *cfg;
   h->cfg.power_db[sizeof h->cfg.power_db - 1] = 0;
-  const Cstln cs = make_cstln(cfg->constellation, false);
+  const Cstln cs = make_cstln(cfg->constellation, cfg->fec, false);
   h->nsymbols = cs.nsymbols;
   h->bps = 0; while ((1 << h->bps) < cs.nsymbols) ++h->bps;
   h->fec = cfg->fec;
-  if (h->fec == LDVB_FEC23 && cs.nsymbols == 4) h->fec = LDVB_FEC46;     // leandvbtx.cc:115-119
-  if (!tx_fec_spec(h->fec, &h->bits_in, &h->bits_out, h->polys) || h->bits_out % h->bps) {   // dvb.h:582-584
+  if (h->fec == LDVB_FEC23 && (cs.nsymbols == 4 || cs.nsymbols == 64)) h->fec = LDVB_FEC46;     // leandvbtx.cc:115-119
+  if (cs.nsymbols == 0 || !tx_fec_spec(h->fec, &h->bits_in, &h->bits_out, h->polys) || h->bits_out % h->bps) {   // dvb.h:582-584
     delete h;
     return LDVB_EINVAL;
   }

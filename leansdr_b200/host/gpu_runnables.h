@@ -16,8 +16,17 @@
 #define LEANSDR_B200_GPU_RUNNABLES_H
 
 #include <stdio.h>
+#include <string.h>
 #include "leandvb_b200.h"
 #include "leandvb_b200_tx.h"
+
+// --const STRING as leandvb / leandvbtx spell it (leandvb.cc:1089-1112, leandvbtx.cc:256-277).
+static inline int ldvb_cstln_from_name(const char *v) {
+  static const char *names[] = { "BPSK", "QPSK", "8PSK", "16APSK", "32APSK", "64APSKe",
+				 "16QAM", "64QAM", "256QAM" };
+  for ( int k=0; k<9; ++k ) if ( !strcmp(v, names[k]) ) return k;   // = LDVB_CSTLN_*
+  return -1;
+}
 
 namespace leansdr {
 

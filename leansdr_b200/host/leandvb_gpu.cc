@@ -76,6 +76,7 @@ int main(int argc, const char *argv[]) {
     else if ( !strcmp(a,"--hs") ) cfg.hs = 1;
     else if ( !strcmp(a,"--viterbi") ) cfg.viterbi = 1;
     else if ( !strcmp(a,"--standard") && more ) ++i;       // DVB-S only
+    else if ( !strcmp(a,"--const") && more ) cfg.constellation = ldvb_cstln_from_name(argv[++i]);
     else if ( !strcmp(a,"--cr") && more ) {
       const char *v = argv[++i];
       cfg.fec = !strcmp(v,"1/2") ? LDVB_FEC12 : !strcmp(v,"2/3") ? LDVB_FEC23 : !strcmp(v,"3/4") ? LDVB_FEC34 :

@@ -27,9 +27,7 @@ int main(int argc, const char *argv[]) {
     const char *a = argv[i];
     bool more = i+1 < argc;
     if ( !strcmp(a,"--const") && more ) {
-      const char *v = argv[++i];
-      cfg.constellation = !strcmp(v,"BPSK") ? LDVB_CSTLN_BPSK : !strcmp(v,"QPSK") ? LDVB_CSTLN_QPSK :
-	!strcmp(v,"8PSK") ? LDVB_CSTLN_8PSK : -1;
+      cfg.constellation = ldvb_cstln_from_name(argv[++i]);
     }
     else if ( !strcmp(a,"--cr") && more ) {
       const char *v = argv[++i];

@@ -48,28 +48,132 @@ static void polar(float r, int n, float i, int8_t *re, int8_t *im) {
   *im = (int8_t)(r * sinf(a) * 75.0f);
 }
 
-void orc_cstln_build(orc_cstln *c, int kind, int harden) {
+/* sdr.h:497-504: four points at the angles a*pi */
+static void polar2(orc_cstln *c, int i, float r, float a0, float a1, float a2, float a3) {
+  float a[] = { a0, a1, a2, a3 };
+  for ( int j = 0; j < 4; ++j ) {
+    float phi = a[j] * M_PI;
+    c->sym_re[i+j] = (int8_t)(r*cosf(phi)*75.0f);
+    c->sym_im[i+j] = (int8_t)(r*sinf(phi)*75.0f);
+  }
+}
+
+/* sdr.h:505-528 */
+static void make_qam(orc_cstln *c, int n) {
+  c->nrotations = 4;
+  c->nsymbols = n;
+  int m = sqrtl(n);
+  float scale;
+  {
+    int q = m / 2;
+    float avgpower = 2*(q*0.25+(q-1)*q/2+(q-1)*q*(2*q-1)/6) / q;
+    scale = 1.0 / sqrtf(avgpower);
+  }
+  int s = 0;
+  for ( int x = 0; x < m; ++x )
+    for ( int y = 0; y < m; ++y ) {
+      float I = x - (float)(m-1)/2;
+      float Q = y - (float)(m-1)/2;
+      c->sym_re[s] = (int8_t)(I * scale * 75.0f);
+      c->sym_im[s] = (int8_t)(Q * scale * 75.0f);
+      ++s;
+    }
+}
+
+#define P(s, r, n, i) polar(r, n, i, &c->sym_re[s], &c->sym_im[s])
+
+int orc_cstln_build2(orc_cstln *c, int kind, int fec, int harden) {
   memset(c, 0, sizeof(*c));
+  /* make_dvbs2_constellation, dvb.h:45-81 (DVB-S code rates only) */
+  float gamma1 = 1, gamma2 = 1, gamma3 = 1;
+  switch ( kind ) {
+  case ORC_16APSK:
+    switch ( fec ) {
+    case ORC_FEC23: case ORC_FEC46: gamma1 = 3.15; break;
+    case ORC_FEC34: gamma1 = 2.85; break;
+    case ORC_FEC56: gamma1 = 2.70; break;
+    default: return -1;
+    }
+    break;
+  case ORC_32APSK:
+    switch ( fec ) {
+    case ORC_FEC34: gamma1 = 2.84; gamma2 = 5.27; break;
+    case ORC_FEC56: gamma1 = 2.64; gamma2 = 4.64; break;
+    default: return -1;
+    }
+    break;
+  case ORC_64APSKE:
+    gamma1 = 2.4; gamma2 = 4.3; gamma3 = 7;
+    break;
+  default: break;
+  }
   switch ( kind ) {
   case ORC_BPSK:                               /* sdr.h:315-327 */
     c->nrotations = 2; c->nsymbols = 2;
-    polar(1, 8, 1, &c->sym_re[0], &c->sym_im[0]);
-    polar(1, 8, 5, &c->sym_re[1], &c->sym_im[1]);
+    P(0, 1, 8, 1); P(1, 1, 8, 5);
     break;
   case ORC_QPSK:                               /* sdr.h:328-339 */
     c->nrotations = 4; c->nsymbols = 4;
-    polar(1, 4, 0.5f, &c->sym_re[0], &c->sym_im[0]);
-    polar(1, 4, 3.5f, &c->sym_re[1], &c->sym_im[1]);
-    polar(1, 4, 1.5f, &c->sym_re[2], &c->sym_im[2]);
-    polar(1, 4, 2.5f, &c->sym_re[3], &c->sym_im[3]);
+    P(0, 1, 4, 0.5f); P(1, 1, 4, 3.5f); P(2, 1, 4, 1.5f); P(3, 1, 4, 2.5f);
     break;
   case ORC_8PSK: {                             /* sdr.h:340-354 */
     static const int idx[8] = { 1, 0, 4, 5, 2, 7, 3, 6 };
     c->nrotations = 8; c->nsymbols = 8;
-    for ( int s = 0; s < 8; ++s )
-      polar(1, 8, (float)idx[s], &c->sym_re[s], &c->sym_im[s]);
+    for ( int s = 0; s < 8; ++s ) P(s, 1, 8, (float)idx[s]);
     break;
   }
+  case ORC_16APSK: {                           /* sdr.h:355-381 */
+    float r1 = sqrtf(4 / (1+3*gamma1*gamma1));
+    float r2 = gamma1 * r1;
+    c->nrotations = 4; c->nsymbols = 16;
+    P(0, r2, 12, 1.5f);  P(1, r2, 12, 10.5f); P(2, r2, 12, 4.5f);  P(3, r2, 12, 7.5f);
+    P(4, r2, 12, 0.5f);  P(5, r2, 12, 11.5f); P(6, r2, 12, 5.5f);  P(7, r2, 12, 6.5f);
+    P(8, r2, 12, 2.5f);  P(9, r2, 12, 9.5f);  P(10, r2, 12, 3.5f); P(11, r2, 12, 8.5f);
+    P(12, r1, 4, 0.5f);  P(13, r1, 4, 3.5f);  P(14, r1, 4, 1.5f);  P(15, r1, 4, 2.5f);
+    break;
+  }
+  case ORC_32APSK: {                           /* sdr.h:382-424 */
+    float r1 = sqrtf(8 / (1+3*gamma1*gamma1+4*gamma2*gamma2));
+    float r2 = gamma1 * r1;
+    float r3 = gamma2 * r1;
+    c->nrotations = 4; c->nsymbols = 32;
+    P(0, r2, 12, 1.5f);  P(1, r2, 12, 2.5f);  P(2, r2, 12, 10.5f); P(3, r2, 12, 9.5f);
+    P(4, r2, 12, 4.5f);  P(5, r2, 12, 3.5f);  P(6, r2, 12, 7.5f);  P(7, r2, 12, 8.5f);
+    P(8, r3, 16, 1);     P(9, r3, 16, 3);     P(10, r3, 16, 14);   P(11, r3, 16, 12);
+    P(12, r3, 16, 6);    P(13, r3, 16, 4);    P(14, r3, 16, 9);    P(15, r3, 16, 11);
+    P(16, r2, 12, 0.5f); P(17, r1, 4, 0.5f);  P(18, r2, 12, 11.5f); P(19, r1, 4, 3.5f);
+    P(20, r2, 12, 5.5f); P(21, r1, 4, 1.5f);  P(22, r2, 12, 6.5f); P(23, r1, 4, 2.5f);
+    P(24, r3, 16, 0);    P(25, r3, 16, 2);    P(26, r3, 16, 15);   P(27, r3, 16, 13);
+    P(28, r3, 16, 7);    P(29, r3, 16, 5);    P(30, r3, 16, 8);    P(31, r3, 16, 10);
+    break;
+  }
+  case ORC_64APSKE: {                          /* sdr.h:425-452 */
+    float r1 = sqrtf(64 / (4+12*gamma1*gamma1+20*gamma2*gamma2+28*gamma3*gamma3));
+    float r2 = gamma1 * r1;
+    float r3 = gamma2 * r1;
+    float r4 = gamma3 * r1;
+    c->nrotations = 4; c->nsymbols = 64;
+    polar2(c,  0, r4,  1.0/ 4,  7.0/ 4,  3.0/ 4,  5.0/ 4);
+    polar2(c,  4, r4, 13.0/28, 43.0/28, 15.0/28, 41.0/28);
+    polar2(c,  8, r4,  1.0/28, 55.0/28, 27.0/28, 29.0/28);
+    polar2(c, 12, r1,  1.0/ 4,  7.0/ 4,  3.0/ 4,  5.0/ 4);
+    polar2(c, 16, r4,  9.0/28, 47.0/28, 19.0/28, 37.0/28);
+    polar2(c, 20, r4, 11.0/28, 45.0/28, 17.0/28, 39.0/28);
+    polar2(c, 24, r3,  1.0/20, 39.0/20, 19.0/20, 21.0/20);
+    polar2(c, 28, r2,  1.0/12, 23.0/12, 11.0/12, 13.0/12);
+    polar2(c, 32, r4,  5.0/28, 51.0/28, 23.0/28, 33.0/28);
+    polar2(c, 36, r3,  9.0/20, 31.0/20, 11.0/20, 29.0/20);
+    polar2(c, 40, r4,  3.0/28, 53.0/28, 25.0/28, 31.0/28);
+    polar2(c, 44, r2,  5.0/12, 19.0/12,  7.0/12, 17.0/12);
+    polar2(c, 48, r3,  1.0/ 4,  7.0/ 4,  3.0/ 4,  5.0/ 4);
+    polar2(c, 52, r3,  7.0/20, 33.0/20, 13.0/20, 27.0/20);
+    polar2(c, 56, r3,  3.0/20, 37.0/20, 17.0/20, 23.0/20);
+    polar2(c, 60, r2,  1.0/ 4,  7.0/ 4,  3.0/ 4,  5.0/ 4);
+    break;
+  }
+  case ORC_16QAM:  make_qam(c, 16);  break;
+  case ORC_64QAM:  make_qam(c, 64);  break;
+  case ORC_256QAM: make_qam(c, 256); break;
   default:
     fprintf(stderr, "orc_cstln_build: constellation not implemented\n");
     abort();
@@ -104,6 +208,12 @@ void orc_cstln_build(orc_cstln *c, int kind, int harden) {
 	if ( c->cell[i][q].cost < 0 ) c->cell[i][q].cost = -1;
 	if ( c->cell[i][q].cost > 0 ) c->cell[i][q].cost = 1;
       }
+  return 0;
+}
+#undef P
+
+void orc_cstln_build(orc_cstln *c, int kind, int harden) {
+  if ( orc_cstln_build2(c, kind, ORC_FEC34, harden) ) abort();
 }
 
 void orc_trig16_build(float *lut) {            /* math.h:97-103 */

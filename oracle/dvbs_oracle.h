@@ -24,7 +24,8 @@ extern "C" {
 
 /* ---------------------------------------------------------------- tables */
 
-enum { ORC_BPSK = 0, ORC_QPSK = 1, ORC_8PSK = 2 };
+enum { ORC_BPSK = 0, ORC_QPSK = 1, ORC_8PSK = 2, ORC_16APSK = 3, ORC_32APSK = 4, ORC_64APSKE = 5,
+       ORC_16QAM = 6, ORC_64QAM = 7, ORC_256QAM = 8 };
 enum { ORC_FEC12 = 0, ORC_FEC23 = 1, ORC_FEC46 = 2, ORC_FEC34 = 3,
        ORC_FEC56 = 4, ORC_FEC78 = 5 };
 
@@ -42,7 +43,10 @@ typedef struct {
   int nsymbols, nrotations;
 } orc_cstln;
 
-void orc_cstln_build(orc_cstln *c, int kind, int harden);
+/* fec (ORC_FEC*) selects the APSK ring ratios (dvb.h:45-81); returns 0, or -1 where the
+   reference fail()s ("Code rate not supported with APSK16/32"). */
+int orc_cstln_build2(orc_cstln *c, int kind, int fec, int harden);
+void orc_cstln_build(orc_cstln *c, int kind, int harden);   /* fec = 3/4 for the APSKs */
 void orc_trig16_build(float *lut /* [65536][2] = cos,sin */);
 void orc_rs_tables(uint8_t *exp511, uint8_t *log256, uint8_t *gen17);
 void orc_derand_pattern(uint8_t *pat1504);

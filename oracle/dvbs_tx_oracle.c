@@ -181,9 +181,9 @@ size_t orc_tx_chain(const uint8_t *ts, size_t npk, int cstln_kind, int fec, int 
 		    float *out, size_t cap_samples,
 		    uint8_t *tap_mpegbytes, size_t *n_mpegbytes, uint8_t *tap_symbols, size_t *n_symbols) {
   orc_cstln *c = malloc(sizeof *c);
-  orc_cstln_build(c, cstln_kind, 0);
+  if ( orc_cstln_build2(c, cstln_kind, fec, 0) ) { free(c); return 0; }   /* leandvbtx.cc:112 */
   int bps = 0; while ( (1 << bps) < c->nsymbols ) ++bps;
-  if ( fec == ORC_FEC23 && c->nsymbols == 4 ) fec = ORC_FEC46;   /* leandvbtx.cc:115-119 */
+  if ( fec == ORC_FEC23 && (c->nsymbols == 4 || c->nsymbols == 64) ) fec = ORC_FEC46;   /* leandvbtx.cc:115-119 */
   uint8_t *r = malloc(npk*188 + 1), *rs = malloc(npk*204 + 1), *mb = malloc(npk*204 + 1);
   orc_tx_randomize(ts, npk, r);
   orc_tx_rs_encode(r, npk, rs);

@@ -24,7 +24,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 FEC = {"1/2": 0, "2/3": 1, "4/6": 2, "3/4": 3, "5/6": 4, "7/8": 5}
-CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2}
+CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2, "16APSK": 3, "32APSK": 4, "64APSKe": 5,
+         "16QAM": 6, "64QAM": 7, "256QAM": 8}
 SAMPLER = {"nearest": 0, "linear": 1, "rrc": 2}
 FMT = {"u8": 0, "s8": 1, "u16": 2, "s16": 3, "f32": 4}
 FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16,
@@ -64,6 +65,8 @@ def lib():
         L.orc_deconv_polys.restype = C.c_int
         L.orc_deconv_polys.argtypes = [C.c_int, vp, vp, C.POINTER(C.c_int)]
         L.orc_cstln_build.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_cstln_build2.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.orc_cstln_build2.restype = C.c_int
         L.orc_trig16_build.argtypes = [vp]
         L.orc_rs_tables.argtypes = [vp, vp, vp]
         L.orc_derand_pattern.argtypes = [vp]
@@ -176,10 +179,12 @@ class _Obj:
 
 # ----------------------------------------------------------------- tables
 
-def cstln_table(kind: str = "QPSK", harden: bool = False):
-    """-> (cells int16[256,256,4] = cost,symbol,phase_error,0 ; symbols int8[n,2])"""
+def cstln_table(kind: str = "QPSK", harden: bool = False, fec: str = "3/4"):
+    """-> (cells int16[256,256,4] = cost,symbol,phase_error,0 ; symbols int8[n,2]).
+    fec only matters for the APSK ring ratios (make_dvbs2_constellation, dvb.h:45-81)."""
     o = _Obj(0)
-    lib().orc_cstln_build(o.p, CSTLN[kind], int(harden))
+    if lib().orc_cstln_build2(o.p, CSTLN[kind], FEC[fec], int(harden)):
+        raise ValueError(f"Code rate {fec} not supported with {kind}")
     cells = o.buf[:256 * 256 * 8].view(np.int16).reshape(256, 256, 4).copy()
     off = 256 * 256 * 8
     sre = o.buf[off:off + 256].view(np.int8)
@@ -556,7 +561,7 @@ class Chain:
     def __init__(self, cfg: Config):
         self.cfg = cfg
         f32 = np.float32
-        self.cells, self.syms, self.cst = cstln_table(cfg.cstln, cfg.hard_metric)
+        self.cells, self.syms, self.cst = cstln_table(cfg.cstln, cfg.hard_metric, cfg.fec)
         self.trig = trig16_table()
         self.notch = Notch(cfg.anf) if cfg.anf else None
         Fs = f32(cfg.Fs)
@@ -586,7 +591,7 @@ class Chain:
             pll = f32(pll / f32(6))
         self.rx.config(pll, cfg.allow_drift, _idecim(Fs, cfg.Finfo))
         fec = cfg.fec
-        if cfg.viterbi and fec == "2/3" and cfg.cstln == "QPSK":
+        if cfg.viterbi and fec == "2/3" and self.syms.shape[0] in (4, 64):   # leandvb.cc:533-537
             fec = "4/6"
         self.vit = Viterbi(self.cst, fec) if cfg.viterbi else None
         if self.vit and cfg.fastlock:

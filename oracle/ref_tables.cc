@@ -69,7 +69,10 @@ static void dump_trellis(const char *name, const uint16_t *polys, int nstates, i
   FILE *f = out(std::string("trellis_")+name+".bin");
   for ( int s=0; s<nstates; ++s )
     for ( int cs=0; cs<ncs; ++cs ) {
+      // `us` of a branch that does not exist (pred == NOSTATE) is never written by the
+      // reference (viterbi.h:54-58): dump 0 there so that the file is reproducible.
       unsigned char rec[2] = { t->states[s].branches[cs].pred, t->states[s].branches[cs].us };
+      if ( rec[0] == TR::NOSTATE ) rec[1] = 0;
       fwrite(rec, 1, 2, f);
     }
   fclose(f);
@@ -144,6 +147,16 @@ int main(int argc, char **argv) {
   dump_cstln("qpsk_hard", cstln_lut<256>::QPSK, FEC12, true);
   dump_cstln("bpsk", cstln_lut<256>::BPSK, FEC12);
   dump_cstln("8psk", cstln_lut<256>::PSK8, FEC12);
+  dump_cstln("16apsk23", cstln_lut<256>::APSK16, FEC23);
+  dump_cstln("16apsk34", cstln_lut<256>::APSK16, FEC34);
+  dump_cstln("16apsk56", cstln_lut<256>::APSK16, FEC56);
+  dump_cstln("32apsk34", cstln_lut<256>::APSK32, FEC34);
+  dump_cstln("32apsk56", cstln_lut<256>::APSK32, FEC56);
+  dump_cstln("64apske", cstln_lut<256>::APSK64E, FEC34);
+  dump_cstln("16qam", cstln_lut<256>::QAM16, FEC12);
+  dump_cstln("64qam", cstln_lut<256>::QAM64, FEC12);
+  dump_cstln("256qam", cstln_lut<256>::QAM256, FEC12);
+  dump_cstln("16apsk34_hard", cstln_lut<256>::APSK16, FEC34, true);
 
   { trig16 *t = new trig16();
     FILE *f = out("trig16.f32"); fwrite(t->lut, 8, 65536, f); fclose(f); }
@@ -167,6 +180,11 @@ int main(int argc, char **argv) {
   dump_vitmap("qpsk12", cstln_lut<256>::QPSK, FEC12);
   dump_vitmap("qpsk34", cstln_lut<256>::QPSK, FEC34);
   dump_vitmap("qpsk78", cstln_lut<256>::QPSK, FEC78);
+  dump_vitmap("8psk23", cstln_lut<256>::PSK8, FEC23);
+  dump_vitmap("16apsk34", cstln_lut<256>::APSK16, FEC34);
+  dump_vitmap("16qam34", cstln_lut<256>::QAM16, FEC34);
+  dump_vitmap("64qam46", cstln_lut<256>::QAM64, FEC46);
+  dump_vitmap("256qam78", cstln_lut<256>::QAM256, FEC78);
 
   { scheduler sch;
     pipebuf<tspacket> a(&sch, "a", 4), b(&sch, "b", 4);

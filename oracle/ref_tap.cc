@@ -133,8 +133,11 @@ int main(int argc, const char *argv[]) {
     }
     else if ( a=="--const" && more ) {
       std::string s = argv[++i];
-      o.cstln = (s=="BPSK")?cstln_lut<256>::BPSK:(s=="8PSK")?cstln_lut<256>::PSK8:
-	cstln_lut<256>::QPSK;
+      static const char *names[] = { "BPSK", "QPSK", "8PSK", "16APSK", "32APSK", "64APSKe",
+				     "16QAM", "64QAM", "256QAM" };   // order of cstln_lut<256>::predef
+      o.cstln = cstln_lut<256>::QPSK;
+      for ( int k=0; k<9; ++k )
+	if ( s == names[k] ) o.cstln = (cstln_lut<256>::predef)k;
     }
     else if ( a=="--tap-dir" && more ) o.tapdir = argv[++i];
     else { fprintf(stderr, "ref_tap: bad option %s\n", argv[i]); return 2; }
@@ -280,7 +283,7 @@ int main(int argc, const char *argv[]) {
   deconvol_sync_simple *r_deconv = NULL;
   code_rate fec = o.fec;
   if ( o.viterbi ) {
-    if ( fec==FEC23 && demod.cstln->nsymbols==4 ) fec = FEC46;
+    if ( fec==FEC23 && (demod.cstln->nsymbols==4 || demod.cstln->nsymbols==64) ) fec = FEC46;
     viterbi_sync *r = new viterbi_sync(&sch, p_symbols, p_bytes, demod.cstln, fec);
     if ( o.fastlock ) r->resync_period = 1;
   } else {

@@ -9,6 +9,7 @@ where /root/reference is mounted and `make -C oracle ref` has built oracle/_ref)
                        (`python make_golden.py hs` regenerates only this file)
   c1_160_taps.json     sha256 + sizes of every stream tapped by oracle/_ref/ref_tap (default flags)
   tables.json          sha256 of the constant tables dumped by oracle/_ref/ref_tables
+                       (`python make_golden.py tables` regenerates only this file and the small verbatim tables)
   c1_160_spectrum_fs100k.f32  spectrum rows (p_spectrum) of ref_tap --u8 -f 100000 --sr 83333 < c1_160.u8
   kat.json             known answers quoted in SURVEY.md 8(c)
   tx_kat.json          sha256 + length of oracle/_ref/leandvbtx's cf32 output for tests/tx_cases.py
@@ -46,7 +47,23 @@ def hs_golden():
     iq = np.fromfile(os.path.join(HERE, "c1_160.u8"), np.uint8)
     V.ref_leandvb(iq, ["--u8", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--hs"]).tofile(os.path.join(HERE, "c1_160_hs.ts"))
 
+def tables_golden():
+    d2 = tempfile.mkdtemp()
+    subprocess.run([O.ref_bin("ref_tables"), d2], check=True)
+    tabs = {f: {"bytes": os.path.getsize(os.path.join(d2, f)), "sha256": sha(open(os.path.join(d2, f), "rb").read())}
+            for f in sorted(os.listdir(d2))}
+    json.dump(tabs, open(os.path.join(HERE, "tables.json"), "w"), indent=1)
+    # Small tables are committed verbatim (libm independent).
+    for f in ("rs_exp.u8", "rs_log.u8", "rs_gen.u8", "derand.u8", "deconv_12.u64", "deconv_34.u64", "deconv_78.u64",
+              "trellis_12.bin", "vitmap_qpsk12.u8", "cstln_qpsk_symbols.s8", "cstln_16apsk34_symbols.s8",
+              "cstln_64apske_symbols.s8", "cstln_256qam_symbols.s8", "vitmap_16apsk34.u8"):
+        open(os.path.join(HERE, f), "wb").write(open(os.path.join(d2, f), "rb").read())
+
 def main():
+    if sys.argv[1:] == ["tables"]:
+        tables_golden()
+        print("tables golden regenerated")
+        return
     if sys.argv[1:] == ["hs"]:
         hs_golden()
         print("hs golden regenerated")
@@ -71,15 +88,7 @@ def main():
     json.dump(taps, open(os.path.join(HERE, "c1_160_taps.json"), "w"), indent=1)
     spectrum_golden(iq)
     hs_golden()
-    d2 = tempfile.mkdtemp()
-    subprocess.run([O.ref_bin("ref_tables"), d2], check=True)
-    tabs = {f: {"bytes": os.path.getsize(os.path.join(d2, f)), "sha256": sha(open(os.path.join(d2, f), "rb").read())}
-            for f in sorted(os.listdir(d2))}
-    json.dump(tabs, open(os.path.join(HERE, "tables.json"), "w"), indent=1)
-    # Small tables are committed verbatim (libm independent).
-    for f in ("rs_exp.u8", "rs_log.u8", "rs_gen.u8", "derand.u8", "deconv_12.u64", "deconv_34.u64", "deconv_78.u64",
-              "trellis_12.bin", "vitmap_qpsk12.u8", "cstln_qpsk_symbols.s8"):
-        open(os.path.join(HERE, f), "wb").write(open(os.path.join(d2, f), "rb").read())
+    tables_golden()
     kat = {"deconv_fec12": "0x3ba", "rs_gen": "01 3b 0d 68 bd 44 d1 1e 08 a3 41 29 e5 62 32 24 3b",
            "qpsk_points": [[53, 53], [53, -53], [-53, 53], [-53, -53]],
            "lookup_53_53": [-11236, 0, 0], "lookup_10_m3": [-636, 1, 5151]}

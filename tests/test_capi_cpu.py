@@ -94,6 +94,24 @@ def test_host_tables_match_reference_dumps(product):
     assert _sha(P.host_table(P.default_config(sampler="rrc", Fs=4e6), "rrc")) == g["rrc_fs4_sr2.f32"]["sha256"]
     assert _sha(P.host_table(c, "vitmap")) == g["vitmap_qpsk12.u8"]["sha256"]
     assert _sha(P.host_table(P.default_config(fec="7/8"), "vitmap")) == g["vitmap_qpsk78.u8"]["sha256"]
+    # every constellation of cstln_lut<256>::predef (sdr.h:305-311); APSK radii per code rate (dvb.h:45-81)
+    for cst, fec, f in (("16APSK", "2/3", "16apsk23"), ("16APSK", "3/4", "16apsk34"), ("16APSK", "5/6", "16apsk56"),
+                        ("32APSK", "3/4", "32apsk34"), ("32APSK", "5/6", "32apsk56"), ("64APSKe", "3/4", "64apske"),
+                        ("16QAM", "1/2", "16qam"), ("64QAM", "1/2", "64qam"), ("256QAM", "1/2", "256qam")):
+        assert _sha(P.host_table(P.default_config(cstln=cst, fec=fec), "cstln")) == g[f"cstln_{f}.bin"]["sha256"], cst
+    assert _sha(P.host_table(P.default_config(cstln="16APSK", fec="3/4", hard_metric=True), "cstln")) == \
+        g["cstln_16apsk34_hard.bin"]["sha256"]
+    for cst, fec, f in (("8PSK", "2/3", "8psk23"), ("16APSK", "3/4", "16apsk34"), ("16QAM", "3/4", "16qam34"),
+                        ("64QAM", "4/6", "64qam46"), ("256QAM", "7/8", "256qam78")):
+        assert _sha(P.host_table(P.default_config(cstln=cst, fec=fec), "vitmap")) == g[f"vitmap_{f}.u8"]["sha256"], cst
+    for fec, f in (("3/4", "34"), ("4/6", "46"), ("5/6", "56"), ("7/8", "78")):
+        t = P.host_table(P.default_config(fec=fec), "trellis").reshape(-1, 2).copy()
+        t[t[:, 0] == 65, 1] = 0          # `us` of absent branches: not written by the reference
+        assert _sha(t) == g[f"trellis_{f}.bin"]["sha256"], fec
+    # combinations the reference fail()s on (dvb.h:59, 70)
+    for cst, fec in (("16APSK", "1/2"), ("32APSK", "1/2"), ("32APSK", "2/3"), ("16APSK", "7/8")):
+        with pytest.raises(P.LdvbError):
+            P.host_table(P.default_config(cstln=cst, fec=fec), "cstln")
 
 
 def test_known_answers(product):

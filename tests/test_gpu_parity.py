@@ -75,13 +75,15 @@ def test_exact_mode_every_stream_bit_exact(product, oracle, name, kw, gkw, npk):
     assert got["meas"]["kernel_launches"] > 0
 
 
-@pytest.mark.parametrize("cst", ["BPSK", "8PSK"])
-def test_exact_mode_other_constellation_tables(product, oracle, cst):
-    """The slicer/PLL with the BPSK and 8PSK tables (and --hard-metric): soft symbols only
-    (a QPSK test signal does not frame-lock under another constellation)."""
+@pytest.mark.parametrize("cst,fec", [("BPSK", "1/2"), ("8PSK", "1/2"), ("32APSK", "5/6"), ("64APSKe", "1/2"),
+                                     ("64QAM", "1/2"), ("256QAM", "1/2")])
+def test_exact_mode_other_constellation_tables(product, oracle, cst, fec):
+    """The slicer/PLL with the other constellation tables (and --hard-metric): soft symbols only
+    (a QPSK test signal does not frame-lock under another constellation; the ones that have a
+    working loop-back are in VIT_CASES below)."""
     P, O = product, oracle
     raw = V.ref_iq(120, fmt="f32")
-    kw = dict(fmt="f32", anf=0, cstln=cst, hard_metric=True)
+    kw = dict(fmt="f32", anf=0, cstln=cst, fec=fec, hard_metric=(cst in ("BPSK", "8PSK")))
     ref = O.Chain(O.Config(**kw)).run(raw)
     rx = P.Receiver(keep_taps=1, max_batch=raw.size // 2, **kw)
     rx.push(raw)
@@ -127,6 +129,8 @@ FAST_CASES = [
     ("rrc", dict(fmt="f32", sampler="rrc"), {}, 1200),
     ("noise22", dict(fmt="f32", resample=True), dict(noise_db=22), 1200),
     ("u8", dict(fmt="u8"), {}, 1200),
+    ("8psk23-viterbi", dict(fmt="f32", viterbi=True, cstln="8PSK", fec="2/3", Fs=4e6), dict(cr="2/3", ratio="2", cst="8PSK"), 1200),
+    ("16apsk34-viterbi", dict(fmt="f32", viterbi=True, cstln="16APSK", fec="3/4", Fs=4e6), dict(cr="3/4", ratio="2", cst="16APSK"), 1600),
 ]
 
 
@@ -152,6 +156,13 @@ VIT_CASES = [
     ("vit12-u8", dict(fmt="u8", viterbi=True, resample=True), {}, 300),
     ("vit78", dict(fmt="f32", viterbi=True, fec="7/8", Fs=55e6, Fm=27.5e6), dict(cr="7/8", ratio="2"), 260),
     ("vit34", dict(fmt="f32", viterbi=True, fec="3/4", Fs=4e6, Fm=2e6), dict(cr="3/4", ratio="2"), 260),
+    # the other constellations through the same kernels (tables differ), real loop-backs
+    ("bpsk12", dict(fmt="f32", viterbi=True, cstln="BPSK", Fs=4e6), dict(ratio="2", cst="BPSK"), 260),
+    ("8psk23", dict(fmt="f32", viterbi=True, cstln="8PSK", fec="2/3", Fs=4e6), dict(cr="2/3", ratio="2", cst="8PSK"), 400),
+    ("16apsk34-noise", dict(fmt="f32", viterbi=True, cstln="16APSK", fec="3/4", Fs=4e6),
+     dict(cr="3/4", ratio="2", cst="16APSK", noise_db=18), 400),
+    ("16qam34-hard", dict(fmt="f32", viterbi=True, hard_metric=True, cstln="16QAM", fec="3/4", Fs=4e6),
+     dict(cr="3/4", ratio="2", cst="16QAM"), 400),
 ]
 
 

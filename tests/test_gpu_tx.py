@@ -108,3 +108,12 @@ def test_device_resident_tx_into_rx_loopback(product, oracle):
     assert k > npk - 100      # 11 packets stay in the interleaver, ~50 go into acquisition
     assert np.array_equal(ts[3:], V.ts_packets(k - 3, int(ctr[3])))
     rx.close(); tx.close()
+
+
+def test_tx_rejects_unsuitable_code_rate(product):
+    """leandvbtx fail()s with "Code rate not suitable for this constellation" (dvb.h:582-584) or
+    "Code rate not supported with APSK16" (dvb.h:59); the handle refuses the same combinations."""
+    from tests.tx_cases import TX_REJECTED
+    for cst, cr in TX_REJECTED:
+        with pytest.raises(product.LdvbError):
+            product.Transmitter(cstln=cst, fec=cr, ratio="2", power="37.5", agc=False, max_packets=16)

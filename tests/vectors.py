@@ -38,11 +38,11 @@ def ts_packets(n: int, start: int = 0) -> np.ndarray:
 
 def ref_iq(npackets: int, ratio: str = "6/5", cr: str = "1/2", power: float = 37.5,
            noise_db: float | None = None, extra_chansim: list[str] | None = None,
-           fmt: str = "f32") -> np.ndarray:
-    """leantsgen -c N | leandvbtx --cr CR -f RATIO --power P --agc [| leanchansim ...]."""
+           fmt: str = "f32", cst: str = "QPSK") -> np.ndarray:
+    """leantsgen -c N | leandvbtx --const CST --cr CR -f RATIO --power P --agc [| leanchansim ...]."""
     ts = subprocess.run([O.ref_bin("leantsgen"), "-c", str(npackets)], stdout=subprocess.PIPE,
                         check=True).stdout
-    iq = subprocess.run([O.ref_bin("leandvbtx"), "--cr", cr, "-f", ratio, "--power", str(power), "--agc"],
+    iq = subprocess.run([O.ref_bin("leandvbtx"), "--const", cst, "--cr", cr, "-f", ratio, "--power", str(power), "--agc"],
                         input=ts, stdout=subprocess.PIPE, check=True).stdout
     if noise_db is not None or extra_chansim or fmt == "u8":
         args = [O.ref_bin("leanchansim"), "--if32"]
