@@ -433,8 +433,9 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
               m[0] = (float)c;
               m[1] = r.freq_tap;
               m[2] = __fsqrt_rn(r.est_insp);
-              // telemetry only: the exact MER is recomputed on the host from (sp, ep)
-              m[3] = (r.est_ep != 0.0f) ? 10.0f * logf(__fdiv_rn(r.est_sp, r.est_ep)) / logf(10.0f) : 0.0f;
+              // est_sp / est_ep (or -1 when est_ep == 0): the host turns it into dB with glibc's
+              // logf, like the reference (sdr.h:910-911), so that p_mer is bit-identical.
+              m[3] = (r.est_ep != 0.0f) ? __fdiv_rn(r.est_sp, r.est_ep) : -1.0f;
             }
           }
         }

@@ -1291,7 +1291,9 @@ int run_receiver(ldvb_handle *h) {
       for (auto &o : order) {
         h->meas_log.push_back(m[4 * o.second + 1]);
         h->meas_log.push_back(m[4 * o.second + 2]);
-        h->meas_log.push_back(m[4 * o.second + 3]);
+        const float q = m[4 * o.second + 3];                               // est_sp / est_ep, -1: est_ep == 0
+        h->meas_log.push_back(q < 0 ? 0.0f : 10 * logf(q) / logf(10));     // sdr.h:910-911
+
       }
     }
   }

@@ -19,7 +19,7 @@ def run_product(P, raw, n_batch=None, **kw):
     n = raw.size // 2
     step = n_batch or n
     rx = P.Receiver(keep_taps=1, max_batch=step, **kw)
-    taps = {k: [] for k in ("pp", "symbols", "bytes", "mpegbytes", "rspackets", "rtspackets", "rsflags", "sampled")}
+    taps = {k: [] for k in ("pp", "symbols", "bytes", "mpegbytes", "rspackets", "rtspackets", "rsflags", "sampled", "meas")}
     ts = []
     for s in range(0, n, step):
         rx.push(raw[2 * s: 2 * min(n, s + step)])
@@ -28,6 +28,7 @@ def run_product(P, raw, n_batch=None, **kw):
             taps[k].append(rx.tap(k))
     out = {k: np.concatenate(v) for k, v in taps.items()}
     out["ts"] = np.concatenate(ts)
+    out["telemetry"] = out["meas"]
     out["meas"] = rx.meas()
     out["rx_state"] = rx.rx_state()
     rx.close()
@@ -73,6 +74,12 @@ def test_exact_mode_every_stream_bit_exact(product, oracle, name, kw, gkw, npk):
     fl = got["rsflags"].view(np.int32).reshape(-1, 2)
     assert np.array_equal(fl[:, 0] != 0, ref["rs_bad"]) and np.array_equal(fl[:, 1], ref["rs_nerr"])
     assert got["meas"]["kernel_launches"] > 0
+    # p_freq / p_ss / p_mer (sdr.h:904-913): one {freq_tap, ss, mer} row per meas_decimation samples, bit for bit
+    tel = got["telemetry"].view(np.float32).reshape(-1, 3)
+    want = np.asarray(ref["meas"], np.float32).reshape(-1, 3)
+    assert len(tel) == len(want) and np.array_equal(tel.view(np.uint32), want.view(np.uint32))
+    if name in ("f32-default", "f32-resample", "u8-default", "f32-noise", "f32-rrc"):
+        assert len(want) >= 1                     # 300 packets = 587 k samples > Fs / 5 = 480 k
 
 
 @pytest.mark.parametrize("cst,fec", [("BPSK", "1/2"), ("8PSK", "1/2"), ("32APSK", "5/6"), ("64APSKe", "1/2"),

@@ -131,6 +131,12 @@ def test_oracle_stages_equal_reference_taps(oracle, name, fmt, flags, okw, gkw):
             continue                      # this short vector never frame-locks, in either implementation
         assert n > 0 and np.array_equal(a[:n], b[:n]), f"{name}: {key} differs"
         assert a.size >= b.size and a.size - b.size <= 64 * max(1, a.itemsize), f"{name}: {key} length"
+    # telemetry rows p_freq / p_ss / p_mer (sdr.h:904-913), bit for bit
+    meas = np.asarray(t["meas"], np.float32).reshape(-1, 3)
+    for col, f in enumerate(("freq.f32", "ss.f32", "mer.f32")):
+        b = np.fromfile(os.path.join(d, f), dtype=np.float32)
+        assert (b.size >= 1 or "-f" in flags) and np.array_equal(meas[:b.size, col].view(np.uint32), b.view(np.uint32)), f"{name}: {f}"
+        assert meas.shape[0] - b.size in (0, 1)
     # RS output: identical on packets the decoder accepts; packets it gives up on depend on
     # an uninitialised table entry in the reference (rs.h:53-60 never writes lut_log[0]).
     ref_rts = np.fromfile(os.path.join(d, "rtspackets.u8"), dtype=np.uint8).reshape(-1, 188)
