@@ -151,6 +151,13 @@ struct ldvb_handle {
   uint64_t meas_carry_count = 0;   // samples kept from the previous batch (< 4096)
   uint64_t meas_abs_next = 0;      // absolute index of the next new sample
   std::vector<float> cnr_queue, spec_queue;
+  // Telemetry results still on their way to the host: the band sums / averaged rows are copied
+  // asynchronously into page-locked memory and turned into dB (glibc logf / log10f, like the
+  // reference) by meas_finish(), which run_chain calls while the receiver kernel is running.
+  struct MeasPending { bool is_cnr; int np, n; size_t off; };
+  std::vector<MeasPending> meas_pending;
+  float *meas_host = nullptr; size_t meas_host_cap = 0, meas_host_used = 0;
+  cudaEvent_t meas_ev = nullptr;
   // rate_estimator<float> (generic.h:272-305) on the RS counts: accumulators and queued ratios
   std::vector<float> vber_queue;
   int64_t vber_num = 0, vber_den = 0;
@@ -394,6 +401,7 @@ void reset_carry(ldvb_handle *h) {
   }
   h->meas_carry_count = 0; h->meas_abs_next = 0;
   h->cnr_queue.clear(); h->spec_queue.clear();
+  h->meas_pending.clear(); h->meas_host_used = 0;      // (callers have synchronised the stream)
   h->vber_queue.clear(); h->vber_num = h->vber_den = 0;
   h->vber_sample = std::max(50000, (int)(h->cfg.Fm / 2));   // leandvb.cc:585-587
 }
@@ -526,6 +534,8 @@ int ldvb_destroy(ldvb_handle *h) {
   for (int i = 0; i < 2; ++i) { h->d_stage[i].release(); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
   if (h->copy_st) cudaStreamDestroy(h->copy_st);
   if (h->ts_queue) cudaFreeHost(h->ts_queue);
+  if (h->meas_host) cudaFreeHost(h->meas_host);
+  if (h->meas_ev) cudaEventDestroy(h->meas_ev);
   for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto &e : h->prof_free) cudaEventDestroy(e);
   if (h->st && h->own_stream) cudaStreamDestroy(h->st);
@@ -668,7 +678,9 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   const uint64_t pp_max = M / h->decim + 4096 + 512;
   const double sym_per_sample = 1.0 / std::max(1.0f, h->rxp.omega - 0.15f);
   const uint64_t sym_max = (uint64_t)(pp_max * sym_per_sample) + 4096;
-  const uint64_t bytes_max = sym_max * 2 / 8 + 4096;  // <= 2 bits per symbol out
+  int bits_per_sym = 2;                                // QPSK / deconvol_sync: <= 2 bits per symbol out
+  while ((1 << bits_per_sym) < h->cst.nsymbols) ++bits_per_sym;   // viterbi_sync: < log2(nsymbols) (code rate < 1)
+  const uint64_t bytes_max = sym_max * bits_per_sym / 8 + 4096;
   const uint64_t pk_max = bytes_max / 204 + 16;
   int rc;
   if ((rc = stream_alloc(h, h->s_raw, h->bps_in, M + carry_raw))) return bail(rc, h->err.c_str());
@@ -802,6 +814,10 @@ int ldvb_get_profile(ldvb_handle *h, ldvb_kernel_stat *stats, int cap, int *n) {
 }  // extern "C"
 
 namespace {
+
+int meas_finish(ldvb_handle *h);
+int meas_host_reserve(ldvb_handle *h, size_t need, float **dst);
+
 
 // ------------------------------------------------------------------------- notch
 
@@ -1059,6 +1075,8 @@ int rx_fast_launch(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, uint64_t nchunks
     sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
     sa.seams = h->d_rx_seams.as<RxSeam>();
     KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
+  // The device is busy with the spans for a while: finish the telemetry of this batch now.
+  { int rcm = meas_finish(h); if (rcm) return rcm; }
   return LDVB_OK;
 }
 
@@ -1678,6 +1696,61 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
 // ------------------------------------------------------------ cnr_fft / spectrum
 
 // One telemetry runnable over the samples [abs0, abs0 + avail) held in `src`.
+// Waits for the telemetry copies queued by run_meas_unit and finishes the measurements on the
+// host: cnr_fft::do_cnr (sdr.h:1326-1330) and spectrum::do_spectrum (sdr.h:1390-1394) take the
+// logarithms with glibc, like the reference.  Idempotent; called where the device is busy anyway
+// and before anything reads the queues.
+int meas_finish(ldvb_handle *h) {
+  if (h->meas_pending.empty()) return LDVB_OK;
+  CK(cudaEventSynchronize(h->meas_ev));
+  for (const auto &m : h->meas_pending) {
+    const float *src = h->meas_host + m.off;
+    if (m.is_cnr) {
+      for (int p = 0; p < m.np; ++p) {
+        const float c2plusn2 = src[3 * p];
+        const float n2 = (src[3 * p + 1] + src[3 * p + 2]) / 2;
+        const float c2 = c2plusn2 - n2;
+        const float cnr = (c2 > 0 && n2 > 0) ? 10 * logf(c2 / n2) / logf(10) : -50;
+        h->cnr_queue.push_back(cnr);
+      }
+    } else {
+      const int n = m.n;
+      const size_t o = h->spec_queue.size();
+      h->spec_queue.resize(o + (size_t)m.np * n);
+      for (int p = 0; p < m.np; ++p) {
+        const float *avg = src + (size_t)p * n;
+        float *row = h->spec_queue.data() + o + (size_t)p * n;
+        for (int i = 0; i < n / 2; ++i) {
+          row[i] = 10 * log10f(avg[n / 2 + i]);
+          row[n / 2 + i] = 10 * log10f(avg[i]);
+        }
+      }
+    }
+  }
+  h->meas_pending.clear();
+  h->meas_host_used = 0;
+  return LDVB_OK;
+}
+
+// `need` floats of page-locked host memory for one asynchronous telemetry read-back.
+int meas_host_reserve(ldvb_handle *h, size_t need, float **dst) {
+  if (!h->meas_ev) CK(cudaEventCreateWithFlags(&h->meas_ev, cudaEventDisableTiming));
+  if (h->meas_host_used + need > h->meas_host_cap) {
+    int rc = meas_finish(h);                       // drains: nothing points into the buffer any more
+    if (rc) return rc;
+    if (need > h->meas_host_cap) {
+      if (h->meas_host) cudaFreeHost(h->meas_host);
+      h->meas_host = nullptr; h->meas_host_cap = 0;
+      const size_t cap = std::max<size_t>(2 * need, (size_t)kMeasGroup * 1024);
+      if (cudaMallocHost(&h->meas_host, cap * 4) != cudaSuccess) return fail(h, LDVB_ENOMEM, "telemetry host buffer");
+      h->meas_host_cap = cap;
+    }
+  }
+  *dst = h->meas_host + h->meas_host_used;
+  h->meas_host_used += need;
+  return LDVB_OK;
+}
+
 int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, uint64_t abs0, uint64_t avail) {
   if (!u.on) return LDVB_OK;
   const int64_t n = (int64_t)1 << u.logn;
@@ -1713,33 +1786,14 @@ int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, 
     e.bwslots = bwslots; e.icf = icf; e.sums = h->d_meas_sums.as<float>();
     e.rows = is_cnr ? nullptr : h->d_meas_rows.as<float>();
     KL("meas_ema", launch_meas_ema(e, h->st));
-    if (is_cnr) {
-      if (!bwslots) continue;                                    // sdr.h:1324
-      std::vector<float> sums(3 * (size_t)np);
-      CK(cudaMemcpyAsync(sums.data(), e.sums, sums.size() * 4, cudaMemcpyDeviceToHost, h->st));
-      CK(cudaStreamSynchronize(h->st));
-      for (int p = 0; p < np; ++p) {                             // sdr.h:1326-1330 (glibc logf)
-        const float c2plusn2 = sums[3 * p];
-        const float n2 = (sums[3 * p + 1] + sums[3 * p + 2]) / 2;
-        const float c2 = c2plusn2 - n2;
-        const float cnr = (c2 > 0 && n2 > 0) ? 10 * logf(c2 / n2) / logf(10) : -50;
-        h->cnr_queue.push_back(cnr);
-      }
-    } else {
-      std::vector<float> rows((size_t)np * n);
-      CK(cudaMemcpyAsync(rows.data(), e.rows, rows.size() * 4, cudaMemcpyDeviceToHost, h->st));
-      CK(cudaStreamSynchronize(h->st));
-      const size_t o = h->spec_queue.size();
-      h->spec_queue.resize(o + rows.size());
-      for (int p = 0; p < np; ++p) {                             // sdr.h:1390-1394 (glibc log10f)
-        const float *avg = rows.data() + (size_t)p * n;
-        float *row = h->spec_queue.data() + o + (size_t)p * n;
-        for (int i = 0; i < n / 2; ++i) {
-          row[i] = 10 * log10f(avg[n / 2 + i]);
-          row[n / 2 + i] = 10 * log10f(avg[i]);
-        }
-      }
-    }
+    if (is_cnr && !bwslots) continue;                            // sdr.h:1324
+    // Results travel to the host asynchronously; meas_finish() turns them into dB later.
+    const size_t need = is_cnr ? 3 * (size_t)np : (size_t)np * (size_t)n;
+    float *dst = nullptr;
+    { int rcr = meas_host_reserve(h, need, &dst); if (rcr) return rcr; }
+    CK(cudaMemcpyAsync(dst, is_cnr ? e.sums : e.rows, need * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaEventRecord(h->meas_ev, h->st));
+    h->meas_pending.push_back({is_cnr, np, (int)n, (size_t)(dst - h->meas_host)});
   }
   return LDVB_OK;
 }
@@ -1861,6 +1915,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   // ---- receiver
   delete wt; wt = new WallTimer(h, "wall:rx");
   if ((rc = run_receiver(h))) return rc;
+  if ((rc = meas_finish(h))) return rc;            // (already done in FAST mode, while the spans ran)
   if ((rc = tap_store(h, LDVB_TAP_SYMBOLS, h->s_sym.at(h->s_sym.count - h->s_sym.fresh), h->s_sym.fresh * 4))) return rc;
   if (h->cfg.keep_taps && !h->meas_log.empty()) {
     Tap &t = h->taps[LDVB_TAP_MEAS];
@@ -2554,6 +2609,7 @@ int ldvb_set_state(ldvb_handle *h, const void *blob, size_t size) {
 
 int ldvb_pull_cnr(ldvb_handle *h, float *dst, size_t cap, size_t *n) {
   if (!h || !n) return LDVB_EINVAL;
+  { int rc = meas_finish(h); if (rc) return rc; }
   const size_t k = std::min(cap, h->cnr_queue.size());
   if (k && dst) memcpy(dst, h->cnr_queue.data(), k * 4);
   h->cnr_queue.erase(h->cnr_queue.begin(), h->cnr_queue.begin() + k);
@@ -2572,6 +2628,7 @@ int ldvb_pull_vber(ldvb_handle *h, float *dst, size_t cap, size_t *n) {
 
 int ldvb_pull_spectrum(ldvb_handle *h, float *dst, size_t cap_rows, size_t *n_rows) {
   if (!h || !n_rows) return LDVB_EINVAL;
+  { int rc = meas_finish(h); if (rc) return rc; }
   const size_t k = std::min(cap_rows, h->spec_queue.size() / 1024);
   if (k && dst) memcpy(dst, h->spec_queue.data(), k * 1024 * 4);
   h->spec_queue.erase(h->spec_queue.begin(), h->spec_queue.begin() + k * 1024);

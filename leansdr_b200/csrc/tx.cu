@@ -531,7 +531,7 @@ int ldvbtx_create(const ldvbtx_config *cfg, ldvbtx_handle **out) {
   *out = nullptr;
   if (cfg->abi_version != LDVB_ABI_VERSION) return LDVB_EINVAL;
   if (cfg->interp < 1 || cfg->decim < 1 || cfg->max_packets < 1 || cfg->rrc_rej <= 0) return LDVB_EINVAL;
-  if (cfg->constellation < LDVB_CSTLN_BPSK || cfg->constellation > LDVB_CSTLN_8PSK) return LDVB_EINVAL;
+  if (cfg->constellation < LDVB_CSTLN_BPSK || cfg->constellation > LDVB_CSTLN_256QAM) return LDVB_EINVAL;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) return LDVB_ENODEV;
   cudaDeviceProp prop;
