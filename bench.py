@@ -42,6 +42,17 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic(kernel: str, n_samples: int):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of this bench command (profiles/ncu_traffic.json), scaled by samples per launch
+    when the batch differs from the captured one.  None if that kernel was not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(t["kernels"][kernel]["bytes_per_sample"]) * n_samples
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -242,7 +253,7 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     ab = alg_bytes.get(dom, nloc * 8)
     ach = ab / (kern[dom] * 1e-3) / 1e9
     roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind, "ms_per_launch": kern[dom],
+            "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(dom, nloc), "peak_source": peak_kind, "ms_per_launch": kern[dom],
             "algorithmic_bytes_per_launch": ab, "share_of_step": per_step[dom] / (ms / a.steps), "rank": 0}
     fir = None
     if "frontend" in kern:
@@ -463,10 +474,13 @@ def main():
     if dom:
         ab = alg_bytes.get(dom, n * 8)
         ach = ab / (kern[dom] * 1e-3) / 1e9
+        traffic = ncu_traffic(dom, n) if a.variant == "f32" else None
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                 "ms_per_launch": kern[dom], "algorithmic_bytes_per_launch": ab,
-                "share_of_step": per_step[dom] / (ms / a.steps)}
+                "share_of_step": per_step[dom] / (ms / a.steps),
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram read + write per launch)" if traffic else None,
+                "dram_frac": (traffic / (kern[dom] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None}
     fir = None
     if "frontend" in kern:
         ach = alg_bytes["frontend"] / (kern["frontend"] * 1e-3) / 1e9

@@ -77,7 +77,12 @@ enum { LDVB_SAMP_NEAREST = 0, LDVB_SAMP_LINEAR = 1, LDVB_SAMP_RRC = 2 };
  *          ambiguity is resolved against the previous span, and every seam is
  *          verified on hard decisions (failed seams are re-run exactly).
  *          TS output is bit-identical whenever the seams verify; soft costs
- *          may differ by one table cell (hard part 1). */
+ *          may differ by one table cell (hard part 1).
+ *          Constant-envelope constellations only (BPSK, QPSK, 8PSK: the slicer
+ *          looks at the angle alone).  The ring / grid decisions of the APSK and
+ *          QAM constellations depend on the AGC estimate, which remembers ~100
+ *          chunks (sdr.h:863-869) -- more than a span's warm-up can reproduce --
+ *          so a handle for those constellations runs EXACT whatever is asked. */
 enum { LDVB_RX_EXACT = 0, LDVB_RX_FAST = 1 };
 
 /* ------------------------------------------------------------------ config

@@ -582,6 +582,11 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   // ---- tables
   h->cst = make_cstln(c.constellation, c.fec, c.hard_metric != 0);
   if (h->cst.nsymbols == 0) return bail(LDVB_EINVAL, "constellation not supported");
+  // FAST spans restart the loops from the carried state a few chunks early.  That reproduces the
+  // decisions of constant-envelope constellations (the slicer of BPSK/QPSK/8PSK looks at the angle
+  // only), but the AGC estimate (sdr.h:863-869) remembers ~100 chunks and the ring / grid
+  // decisions of APSK and QAM depend on it: those constellations always run the exact receiver.
+  if (h->cfg.rx_mode == LDVB_RX_FAST && h->cst.nsymbols > 8) h->cfg.rx_mode = LDVB_RX_EXACT;
   int fec = c.fec;
   if (c.viterbi && fec == LDVB_FEC23 && (h->cst.nsymbols == 4 || h->cst.nsymbols == 64)) fec = LDVB_FEC46;  // leandvb.cc:533-537
   if (!c.viterbi && !make_deconv(fec, &h->dec)) return bail(LDVB_EINVAL, "code rate not supported");

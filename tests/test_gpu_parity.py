@@ -149,6 +149,11 @@ def test_fast_mode_ts_bit_exact(product, oracle, name, kw, gkw, npk):
     got = run_product(P, raw, rx_mode=P.RX_FAST, **kw)
     assert_prefix(got["ts"], ref["ts"], "TS")
     m = got["meas"]
+    if kw.get("cstln") == "16APSK":
+        # amplitude-sensitive slicer: the handle runs the exact receiver whatever is asked (leandvb_b200.h)
+        assert m["seams_total"] == 0
+        assert np.array_equal(got["symbols"].reshape(-1, 4)[:, :3], ref["symbols"][:len(got["symbols"]) // 4, :3])
+        return
     assert m["seams_total"] > 10
     # hard decisions: count symbol mismatches (reported, not assumed)
     a = got["symbols"].reshape(-1, 4)[:, 2]
