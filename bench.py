@@ -487,6 +487,16 @@ def main():
         fir = {"kernel": "frontend(FIR)", "achieved": ach, "frac": ach / peaks["hbm_gbs"], "unit": "GB/s",
                "ms_per_launch": kern["frontend"]}
 
+    # every kernel that was captured with ncu --set full: algorithmic and DRAM-traffic bandwidth against the peak
+    roof_all = []
+    for k in ("frontend", "notch_guess", "notch_apply", "rx"):
+        if k in kern and a.variant == "f32":
+            tr = ncu_traffic(k, n)
+            ab = alg_bytes.get(k, n * 8)
+            roof_all.append({"kernel": k, "ms_per_launch": kern[k], "achieved": ab / (kern[k] * 1e-3) / 1e9,
+                             "frac": ab / (kern[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": tr,
+                             "dram_frac": (tr / (kern[k] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tr else None})
+
     # ---- CPU baseline: the unmodified reference on this box, same vector, in the same run
     cpu = None
     ts_match = None
@@ -512,7 +522,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": int(raw.nbytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches),
-            "roofline": roof, "roofline_fir": fir,
+            "roofline": roof, "roofline_fir": fir, "roofline_kernels": roof_all,
             "kernel_ms_per_step": per_step, "stage_wall_ms_per_step": wall,
             "cpu_baseline": cpu,
             "ts_packets_per_step": int(npk), "ts_bit_exact_vs_reference": ts_match,
