@@ -296,9 +296,10 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", default="f32", choices=["f32", "u8", "hs"],
+    ap.add_argument("--variant", default="f32", choices=["f32", "u8", "hs", "viterbi"],
                     help="side measurements (N = 1): 'u8' = the same chain fed complex<u8> IQ (leandvb --u8), 'hs' = leandvb --u8 --hs "
-                         "(fast_qpsk_receiver path).  The default 'f32' is BASELINE.json's configuration.")
+                         "(fast_qpsk_receiver path), 'viterbi' = leandvb --f32 --resample --viterbi (viterbi_sync instead of deconvol_sync).  "
+                         "The default 'f32' is BASELINE.json's configuration.")
     ap.add_argument("--cpu-gen", action="store_true", help="synthesise the IQ with the reference binaries on the host "
                     "instead of the B200 transmit chain (N = 1)")
     ap.add_argument("--shard", default="time", choices=["time", "streams"],
@@ -320,9 +321,14 @@ def main():
     if a.variant != "f32":
         if a.impl == "reference" or world > 1:
             raise SystemExit("--variant is a single-GPU side measurement of the b200 arm")
-        ref_flags = ["--u8", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--standard", "DVB-S"] + (["--hs"] if a.variant == "hs" else ["--resample"])
-        rx_kw = dict(fmt="u8", hs=True) if a.variant == "hs" else dict(fmt="u8", resample=True)
-        workload["workload"] = "SIDE MEASUREMENT, not BASELINE.json's configuration: same waveform as complex<u8> IQ -> leandvb " + " ".join(ref_flags)
+        if a.variant == "viterbi":
+            ref_flags = list(REF_FLAGS) + ["--viterbi"]
+            rx_kw = dict(fmt="f32", resample=True, viterbi=True)
+            workload["workload"] = "SIDE MEASUREMENT, not BASELINE.json's configuration: same f32 waveform -> leandvb " + " ".join(ref_flags)
+        else:
+            ref_flags = ["--u8", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--standard", "DVB-S"] + (["--hs"] if a.variant == "hs" else ["--resample"])
+            rx_kw = dict(fmt="u8", hs=True) if a.variant == "hs" else dict(fmt="u8", resample=True)
+            workload["workload"] = "SIDE MEASUREMENT, not BASELINE.json's configuration: same waveform as complex<u8> IQ -> leandvb " + " ".join(ref_flags)
 
     # ---------------------------------------------------------------- reference arm
     if a.impl == "reference":
@@ -379,7 +385,7 @@ def main():
         if rank == 0:
             head = gen_vector(min(a.packets, 2048))          # the unmodified reference transmitter, same packets
             vector_check = bool(head.size > 1000000 and np.array_equal(head.view(np.uint32), raw[: head.size].view(np.uint32)))
-    if a.variant != "f32":
+    if a.variant in ("u8", "hs"):
         # leanchansim --ou8 = cconverter<f32,0,u8,128,1,1> (dsp.h:33-54): (u8)(128 + x), truncating
         iq_dev = (iq_dev + 128.0).to(torch.uint8)
         raw = iq_dev.cpu().numpy()
@@ -458,8 +464,9 @@ def main():
     sym = meas["symbols"]
     omega = 1.2
     alg_bytes = {                      # per launch, see DESIGN.md "Kernels"
-        "frontend": n * ((8 if a.variant == "f32" else 2) + 8),   # IQ in + cf32 out (FIR, D=1)
-        "notch_apply": n * ((8 if a.variant == "f32" else 2) + 8),
+        "frontend": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),   # IQ in + cf32 out (FIR, D=1)
+        "notch_apply": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),
+        "viterbi": sym * 4 + sym // 8,
         "rx": n * 8 + sym * 4,                        # cf32 in + softsymbol out
         "rx_compact": sym * 8,
         "deconv_carry": sym * 4 + sym // 8,
@@ -528,7 +535,8 @@ def main():
             "ts_packets_per_step": int(npk), "ts_bit_exact_vs_reference": ts_match,
             "e2e_ts_equals_device_resident_ts": e2e_ts_ok,
             "vector_equals_reference_transmitter_prefix": vector_check,
-            "seams": {"total": meas["seams_total"], "repaired": meas["seams_repaired"], "notch_repaired": meas["notch_repaired"]}}
+            "seams": {"total": meas["seams_total"], "repaired": meas["seams_repaired"], "notch_repaired": meas["notch_repaired"],
+                      "viterbi_segments": meas["vit_segments"], "viterbi_repaired": meas["vit_repaired"]}}
     print(json.dumps(line))
 
 

@@ -130,7 +130,10 @@ typedef struct ldvb_config {
   int32_t  hs;               /* --hs (leandvb.cc:727-969): fast_qpsk_receiver<u8> + dvb_deconvol_sync_hard +
                                 mpeg_sync with fastlock; needs u8 input, QPSK, code rate 1/2; no notch,
                                 filter, CNR or spectrum blocks exist on that path                  */
-  int32_t  reserved[2];
+  int32_t  vit_segments;     /* --viterbi: target number of concurrent time segments per batch
+                                (0 = 2048; 1 = one serial pass, the reference's own schedule)    */
+  int32_t  vit_warm_chunks;  /* --viterbi: warm-up of a cold segment, 128-block chunks (0 = 2; -1 = none at
+                                all: a test knob, every segment then fails verification and is re-run) */
 } ldvb_config;
 
 typedef struct ldvb_handle ldvb_handle;
@@ -153,6 +156,9 @@ typedef struct ldvb_meas {
   uint32_t seams_repaired;   /* FAST: seams that failed verification and were re-run exactly */
   uint32_t notch_repaired;   /* notch segments re-run after a carry mismatch */
   uint32_t kernel_launches;  /* CUDA kernels launched by this handle so far  */
+  uint32_t vit_segments;     /* --viterbi: time segments decoded concurrently (cold start + warm-up,
+                                entry state verified bit for bit against the predecessor's exit)  */
+  uint32_t vit_repaired;     /* --viterbi: segments that had not merged and were re-run exactly  */
 } ldvb_meas;
 
 /* Intermediate streams readable with ldvb_tap() when keep_taps != 0; names

@@ -46,7 +46,7 @@ class Config(C.Structure):
         ("allow_drift", C.c_int32), ("Ftune", C.c_float), ("Finfo", C.c_float),
         ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
         ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
-        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("hs", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("hs", C.c_int32), ("vit_segments", C.c_int32), ("vit_warm_chunks", C.c_int32),
     ]
 
 
@@ -57,6 +57,7 @@ class Meas(C.Structure):
         ("ts_packets", C.c_uint64), ("ts_dropped", C.c_uint64), ("samples_in", C.c_uint64),
         ("symbols", C.c_uint64), ("seams_total", C.c_uint32), ("seams_repaired", C.c_uint32),
         ("notch_repaired", C.c_uint32), ("kernel_launches", C.c_uint32),
+        ("vit_segments", C.c_uint32), ("vit_repaired", C.c_uint32),
     ]
 
     def asdict(self):

@@ -15,8 +15,25 @@
 // The current decoder runs on every 128-block chunk, the others only on every
 // `resync_period`-th chunk with the state they had 32 chunks earlier; the best
 // sum of quality over blocks >= discr_delay becomes current (dvb.h:1386-1411).
-// This kernel follows the reference order exactly (serial in time, parallel
-// over states and hypotheses), so the output is bit-identical.
+//
+// Rescan without the dead labels.  All rescan candidates of one predecessor carry
+// the same metric, and among equal metrics the LAST label wins: per state only
+// (pred, us) of the largest label of every distinct predecessor matters, in
+// increasing order of that label.  The CTA builds these lists from the full
+// trellis when it starts (7/8: 64 entries per state instead of 256 labels); the
+// selected branch is the one the reference selects, tie for tie.
+//
+// Time parallelism.  The recurrence is serial, but a Viterbi decoder forgets: once all
+// survivors descend from one state, the normalised metrics and the path registers no longer
+// depend on where the decoder started.  The stream is cut into segments (whole re-sync
+// groups); one CTA per segment starts its decoders COLD a little earlier -- all of them on the
+// previous re-sync chunk, which is the only data the non-current ones see between two votes
+// anyway, with that chunk's vote; then the current one again, cold, on the last `warm_chunks`
+// chunks -- and records the state with which it enters its segment.  k_vit_verify compares entry(g) with exit(g-1) bit for bit (64 metrics, 64 path
+// registers per decoder, the current decoder and the re-sync phase); a segment that did not
+// merge is re-run from its predecessor's exit state (list mode).  Exactness therefore holds by
+// induction, as for the notch segments and the receiver spans; segment 0 always starts from
+// the carried state.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,13 +43,116 @@ namespace {
 
 constexpr int kVitChunk = 128;
 
+struct VitWarp {
+  int32_t *cost;        // [2][64]
+  uint64_t *path;       // [2][64]
+  const uint8_t *map;
+  int shift, bank;
+};
+
+// One chunk of 128 FEC blocks for this warp's decoder (update_sync + viterbi_dec::update,
+// dvb.h:1353-1364, viterbi.h:196-263).  Returns the sum of quality over blocks >= discr_delay.
+__device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const uint8_t *t_pred, const uint8_t *t_us,
+                                             const uint8_t *l_pred, const uint8_t *l_us, int nb, uint64_t chunk,
+                                             bool write_out, int lane) {
+  const int discr_delay = 64 / a.bits_in;   // dvb.h:1369
+  const uint64_t path_mask = (1ull << a.path_nbits) - 1;
+  const int read_shift = (a.path_depth - 1) * a.path_nbits;
+  const int bytes_per_chunk = kVitChunk * a.bits_in / 8;
+  int32_t td = 0;
+  uint64_t outstream = 0; int nout = 0;
+  uint8_t *outp = a.out + chunk * bytes_per_chunk;
+  const uint32_t *pin = a.symbols + chunk * (uint64_t)kVitChunk * a.nshifts + w.shift;
+  int bank = w.bank;
+  for (int blk = 0; blk < kVitChunk; ++blk, pin += a.nshifts) {
+    // update_sync (dvb.h:1353-1364): coded symbol and cost of this FEC block
+    unsigned cs = 0; int32_t bcost = 0;
+    for (int i = 0; i < a.nshifts; ++i) {
+      const uint32_t sw = __ldg(pin + i);
+      cs = ((cs << a.bps) | w.map[(sw >> 16) & 0xffu]) & 0xffu;
+      bcost += (int32_t)(int16_t)(sw & 0xffffu);
+    }
+    const int32_t *cc = w.cost + bank * 64;
+    const uint64_t *pc = w.path + bank * 64;
+    int32_t *cn = w.cost + (bank ^ 1) * 64;
+    uint64_t *pn = w.path + (bank ^ 1) * 64;
+    int32_t my_m[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = lane + 32 * h;
+      int32_t best_m = 0x7fffffff; int best_pred = 0, best_us = 0;
+      {
+        const int p = t_pred[s * a.ncs + cs];
+        if (p != 65) {
+          const int32_t m = cc[p] + bcost;
+          if (m <= best_m) { best_m = m; best_pred = p; best_us = t_us[s * a.ncs + cs]; }
+        }
+      }
+      if (a.ncs != 1) {
+        const uint8_t *lp = l_pred + s * nb, *lu = l_us + s * nb;
+        for (int k = 0; k < nb; ++k) {
+          const int p = lp[k];
+          const int32_t m = cc[p];
+          if (m <= best_m) { best_m = m; best_pred = p; best_us = lu[k]; }
+        }
+      }
+      uint64_t np = pc[best_pred];
+      if (a.path32) np = (uint64_t)(uint32_t)(((uint32_t)np << a.path_nbits) | (uint32_t)best_us);
+      else np = (np << a.path_nbits) | (uint64_t)best_us;
+      pn[s] = np; cn[s] = best_m; my_m[h] = best_m;
+    }
+    // best state: minimum, first index wins (viterbi.h:239-243)
+    int32_t bm; int bs;
+    if (my_m[1] < my_m[0]) { bm = my_m[1]; bs = lane + 32; } else { bm = my_m[0]; bs = lane; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const int32_t om = __shfl_xor_sync(0xffffffffu, bm, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (om < bm || (om == bm && os < bs)) { bm = om; bs = os; }
+    }
+    // second best: minimum over all states except the best one (duplicates count)
+    int32_t b2 = 0x7fffffff;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) if (lane + 32 * h != bs && my_m[h] < b2) b2 = my_m[h];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const int32_t v = __shfl_xor_sync(0xffffffffu, b2, o); if (v < b2) b2 = v; }
+    __syncwarp();
+    bank ^= 1;
+    // normalise (viterbi.h:249)
+    cn[lane] -= bm; cn[lane + 32] -= bm;
+    __syncwarp();
+    const int32_t quality = b2 - bm;
+    if (blk >= discr_delay) td += quality;
+    if (write_out) {
+      const unsigned result = (unsigned)((pn[bs] >> read_shift) & path_mask);
+      outstream = (outstream << a.bits_in) | result;
+      nout += a.bits_in;
+      while (nout >= 8) {
+        if (lane == 0) *outp = (uint8_t)(outstream >> (nout - 8));
+        ++outp; nout -= 8;
+      }
+    }
+  }
+  w.bank = bank;
+  return td;
+}
+
+__device__ __forceinline__ void vit_store(VitDecState *dst, const VitWarp &w, int lane) {
+  for (int s = lane; s < 64; s += 32) { dst->cost[s] = w.cost[w.bank * 64 + s]; dst->path[s] = w.path[w.bank * 64 + s]; }
+  if (lane == 0) { dst->bank = 0; dst->pad = 0; }   // the bank is re-based to 0 on store
+}
+
 __global__ void __launch_bounds__(512)
-k_viterbi(VitArgs a) {
+k_viterbi(VitArgs a, VitSegArgs sg) {
   extern __shared__ __align__(16) unsigned char smem[];
-  // Layout: trellis pred[64*ncs], us[64*ncs]; per warp: cost[2][64] int32, path[2][64] u64.
+  // Layout: trellis pred[64*ncs], us[64*ncs]; rescan lists pred[64*nb], us[64*nb];
+  // per warp: cost[2][64] int32, path[2][64] u64.
+  const int nb = sg.nb;
   uint8_t *t_pred = smem;
   uint8_t *t_us = t_pred + 64 * a.ncs;
-  size_t off = ((size_t)128 * a.ncs + 15) & ~(size_t)15;
+  uint8_t *l_pred = t_us + 64 * a.ncs;
+  uint8_t *l_us = l_pred + 64 * nb;
+  size_t off = ((size_t)128 * a.ncs + (size_t)128 * nb + 15) & ~(size_t)15;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = a.nsyncs;
   int32_t *cost_all = reinterpret_cast<int32_t *>(smem + off);
@@ -41,134 +161,173 @@ k_viterbi(VitArgs a) {
   off += (size_t)nw * 2 * 64 * 8;
   int32_t *totaldiscr = reinterpret_cast<int32_t *>(smem + off);
   off += (size_t)nw * 4;
-  int *s_ctl = reinterpret_cast<int *>(smem + off);   // [0] current_sync, [1] resync_phase
+  int *s_ctl = reinterpret_cast<int *>(smem + off);   // [0] current_sync
+
+  const uint32_t g = sg.list ? sg.list[blockIdx.x] : blockIdx.x;
+  const bool repair = sg.list != nullptr;
+  const bool cold = !repair && g != 0;
+  const uint64_t c0 = sg.seg_start[g], c1 = sg.seg_start[g + 1];
+  const int P = a.resync_period;
 
   for (int i = threadIdx.x; i < 64 * a.ncs; i += blockDim.x) { t_pred[i] = a.trellis_pred[i]; t_us[i] = a.trellis_us[i]; }
-  int32_t *cost = cost_all + (size_t)warp * 128;
-  uint64_t *path = path_all + (size_t)warp * 128;
-  VitDecState *st = a.state + warp;
-  int bank = st->bank;
-  for (int s = lane; s < 64; s += 32) { cost[bank * 64 + s] = st->cost[s]; path[bank * 64 + s] = st->path[s]; }
-  if (threadIdx.x == 0) { s_ctl[0] = a.ctl->current_sync; s_ctl[1] = a.ctl->resync_phase; }
+  __syncthreads();
+  // Rescan lists: per state, (pred, us) of the largest label of every distinct predecessor,
+  // by increasing label.  Walk the labels downwards, keep first sightings, then reverse.
+  for (int s = threadIdx.x; s < 64 && a.ncs != 1; s += blockDim.x) {
+    unsigned long long seen = 0;
+    int k = nb;
+    for (int c = a.ncs - 1; c >= 0; --c) {
+      const int p = t_pred[s * a.ncs + c];
+      if (p == 65 || ((seen >> p) & 1ull)) continue;
+      seen |= 1ull << p;
+      if (k > 0) { --k; l_pred[s * nb + k] = (uint8_t)p; l_us[s * nb + k] = t_us[s * a.ncs + c]; }
+    }
+    // (k == 0 here for a regular code: every state has exactly nb distinct predecessors;
+    //  unused slots would repeat the first real entry, which changes nothing)
+    for (int j = 0; j < k; ++j) { l_pred[s * nb + j] = l_pred[s * nb + k]; l_us[s * nb + j] = l_us[s * nb + k]; }
+  }
+
+  VitWarp w;
+  w.cost = cost_all + (size_t)warp * 128;
+  w.path = path_all + (size_t)warp * 128;
+  w.map = a.maps + (size_t)warp * a.nsymbols;
+  w.shift = a.shifts[warp];
+  w.bank = 0;
+  const VitDecState *src = nullptr;
+  if (g == 0) src = a.state + warp;
+  else if (repair) src = sg.exit + (size_t)(g - 1) * nw + warp;
+  if (src) { for (int s = lane; s < 64; s += 32) { w.cost[s] = src->cost[s]; w.path[s] = src->path[s]; } }
+  else { for (int s = lane; s < 64; s += 32) { w.cost[s] = 0; w.path[s] = 0; } }   // viterbi.h:133-145
+  if (threadIdx.x == 0) {
+    if (g == 0) s_ctl[0] = a.ctl->current_sync;
+    else if (repair) s_ctl[0] = sg.ctl_exit[g - 1].current_sync;
+    else s_ctl[0] = a.ctl->current_sync;       // speculation: the current decoder does not change
+  }
   __syncthreads();
 
-  const uint8_t *map = a.maps + (size_t)warp * a.nsymbols;
-  const int shift = a.shifts[warp];
-  const int discr_delay = 64 / a.bits_in;   // dvb.h:1369
-  const uint64_t path_mask = (1ull << a.path_nbits) - 1;
-  const int read_shift = (a.path_depth - 1) * a.path_nbits;
-  const int bytes_per_chunk = kVitChunk * a.bits_in / 8;
-
-  for (uint64_t chunk = 0; chunk < a.nchunks; ++chunk) {
-    const int current = s_ctl[0];
-    const bool resync = (s_ctl[1] == 0);
-    const bool mine = (warp == current);
-    if (mine || resync) {
-      int32_t td = 0;
-      uint64_t outstream = 0; int nout = 0;
-      uint8_t *outp = a.out + chunk * bytes_per_chunk;
-      const uint32_t *pin = a.symbols + chunk * (uint64_t)kVitChunk * a.nshifts + shift;
-      for (int blk = 0; blk < kVitChunk; ++blk, pin += a.nshifts) {
-        // update_sync (dvb.h:1353-1364): coded symbol and cost of this FEC block
-        unsigned cs = 0; int32_t bcost = 0;
-        for (int i = 0; i < a.nshifts; ++i) {
-          const uint32_t w = pin[i];
-          cs = ((cs << a.bps) | map[(w >> 16) & 0xffu]) & 0xffu;
-          bcost += (int32_t)(int16_t)(w & 0xffffu);
-        }
-        const int32_t *cc = cost + bank * 64;
-        const uint64_t *pc = path + bank * 64;
-        int32_t *cn = cost + (bank ^ 1) * 64;
-        uint64_t *pn = path + (bank ^ 1) * 64;
-        int32_t my_m[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int s = lane + 32 * h;
-          const uint8_t *row_p = t_pred + s * a.ncs, *row_u = t_us + s * a.ncs;
-          int32_t best_m = 0x7fffffff; int best_pred = 0, best_us = 0;
-          {
-            const int p = row_p[cs];
-            if (p != 65) {
-              const int32_t m = cc[p] + bcost;
-              if (m <= best_m) { best_m = m; best_pred = p; best_us = row_u[cs]; }
-            }
-          }
-          if (a.ncs != 1) {
-            for (int c = 0; c < a.ncs; ++c) {
-              const int p = row_p[c];
-              if (p == 65) continue;
-              const int32_t m = cc[p];
-              if (m <= best_m) { best_m = m; best_pred = p; best_us = row_u[c]; }
-            }
-          }
-          uint64_t np = pc[best_pred];
-          if (a.path32) np = (uint64_t)(uint32_t)(((uint32_t)np << a.path_nbits) | (uint32_t)best_us);
-          else np = (np << a.path_nbits) | (uint64_t)best_us;
-          pn[s] = np; cn[s] = best_m; my_m[h] = best_m;
-        }
-        // best state: minimum, first index wins (viterbi.h:239-243)
-        int32_t bm; int bs;
-        if (my_m[1] < my_m[0]) { bm = my_m[1]; bs = lane + 32; } else { bm = my_m[0]; bs = lane; }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          const int32_t om = __shfl_xor_sync(0xffffffffu, bm, o);
-          const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-          if (om < bm || (om == bm && os < bs)) { bm = om; bs = os; }
-        }
-        // second best: minimum over all states except the best one (duplicates count)
-        int32_t b2 = 0x7fffffff;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) if (lane + 32 * h != bs && my_m[h] < b2) b2 = my_m[h];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { const int32_t v = __shfl_xor_sync(0xffffffffu, b2, o); if (v < b2) b2 = v; }
-        __syncwarp();
-        bank ^= 1;
-        // normalise (viterbi.h:249)
-        cn[lane] -= bm; cn[lane + 32] -= bm;
-        __syncwarp();
-        const int32_t quality = b2 - bm;
-        if (blk >= discr_delay) td += quality;
-        if (mine) {
-          const unsigned result = (unsigned)((pn[bs] >> read_shift) & path_mask);
-          outstream = (outstream << a.bits_in) | result;
-          nout += a.bits_in;
-          while (nout >= 8) {
-            if (lane == 0) *outp = (uint8_t)(outstream >> (nout - 8));
-            ++outp; nout -= 8;
-          }
-        }
-      }
-      if (lane == 0) totaldiscr[warp] = td;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (resync) {   // dvb.h:1402-1411
-        int best = current;
+  if (cold && (sg.warm_chunks || sg.warm_others)) {
+    // Warm-up: nothing is written.  Votes ARE taken, from cold decoders: which hypothesis is
+    // current at c0 is the outcome of the last vote before c0, and a cold decoder's quality sum
+    // over a chunk differs from the true one only in its first few blocks.
+    auto vote = [&]() {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int best = s_ctl[0];
         for (int s = 0; s < a.nsyncs; ++s) if (totaldiscr[s] > totaldiscr[best]) best = s;
         s_ctl[0] = best;
       }
-      if (++s_ctl[1] >= a.resync_period) s_ctl[1] = 0;
+      __syncthreads();
+    };
+    if (P > 1) {
+      // A: every decoder on the previous re-sync chunk (all the other decoders ever see between
+      //    two votes), then the vote of that chunk.
+      const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - (uint64_t)P, false, lane);
+      if (lane == 0) totaldiscr[warp] = td;
+      vote();
+      // B: the decoder that is current now restarts cold on the last warm_chunks chunks.
+      if (warp == s_ctl[0]) {
+        for (int s = lane; s < 64; s += 32) { w.cost[s] = 0; w.path[s] = 0; }
+        w.bank = 0;
+        __syncwarp();
+        for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, lane);
+      }
+    } else {
+      for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) {
+        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, lane);
+        if (lane == 0) totaldiscr[warp] = td;
+        vote();
+      }
     }
     __syncthreads();
   }
-  for (int s = lane; s < 64; s += 32) { st->cost[s] = cost[bank * 64 + s]; st->path[s] = path[bank * 64 + s]; }
-  if (lane == 0) st->bank = 0;
-  // bank is re-based to 0 on store
-  if (threadIdx.x == 0) { a.ctl->current_sync = s_ctl[0]; a.ctl->resync_phase = s_ctl[1]; }
+  vit_store(sg.entry + (size_t)g * nw + warp, w, lane);
+  if (threadIdx.x == 0) {
+    VitCtl ce; ce.current_sync = s_ctl[0]; ce.resync_phase = (int)(((uint64_t)sg.phase0 + c0) % (uint64_t)P);
+    sg.ctl_entry[g] = ce;
+  }
+
+  for (uint64_t chunk = c0; chunk < c1; ++chunk) {
+    const int current = s_ctl[0];
+    const bool resync = (((uint64_t)sg.phase0 + chunk) % (uint64_t)P) == 0;
+    const bool mine = (warp == current);
+    if (mine || resync) {
+      const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, chunk, mine, lane);
+      if (lane == 0) totaldiscr[warp] = td;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && resync) {   // dvb.h:1402-1411
+      int best = current;
+      for (int s = 0; s < a.nsyncs; ++s) if (totaldiscr[s] > totaldiscr[best]) best = s;
+      s_ctl[0] = best;
+    }
+    __syncthreads();
+  }
+  vit_store(sg.exit + (size_t)g * nw + warp, w, lane);
+  if (threadIdx.x == 0) {
+    VitCtl ce; ce.current_sync = s_ctl[0]; ce.resync_phase = (int)(((uint64_t)sg.phase0 + c1) % (uint64_t)P);
+    sg.ctl_exit[g] = ce;
+  }
+}
+
+// entry(g) == exit(g-1), bit for bit, for every decoder; ok[g] and the number of failures.
+__global__ void __launch_bounds__(64)
+k_vit_verify(VitSegArgs sg, int nsyncs, uint8_t *ok, uint32_t *nfail) {
+  const uint32_t g = blockIdx.x + 1;
+  if (g >= sg.nseg) return;
+  const int s = threadIdx.x;
+  bool same = true;
+  for (int d = 0; d < nsyncs; ++d) {
+    const VitDecState &e = sg.entry[(size_t)g * nsyncs + d];
+    const VitDecState &x = sg.exit[(size_t)(g - 1) * nsyncs + d];
+    same = same && e.cost[s] == x.cost[s] && e.path[s] == x.path[s];
+  }
+  if (s == 0)
+    same = same && sg.ctl_entry[g].current_sync == sg.ctl_exit[g - 1].current_sync &&
+           sg.ctl_entry[g].resync_phase == sg.ctl_exit[g - 1].resync_phase;
+  const int all = __syncthreads_and(same ? 1 : 0);
+  if (s == 0) {
+    ok[g] = (uint8_t)all;
+    if (!all) atomicAdd(nfail, 1u);
+  }
+}
+
+// The last segment's exit state becomes the carried state.
+__global__ void k_vit_commit(VitArgs a, VitSegArgs sg) {
+  const VitDecState *src = sg.exit + (size_t)(sg.nseg - 1) * a.nsyncs;
+  for (int i = threadIdx.x; i < a.nsyncs * 64; i += blockDim.x) {
+    a.state[i / 64].cost[i % 64] = src[i / 64].cost[i % 64];
+    a.state[i / 64].path[i % 64] = src[i / 64].path[i % 64];
+  }
+  if (threadIdx.x < a.nsyncs) { a.state[threadIdx.x].bank = 0; a.state[threadIdx.x].pad = 0; }
+  if (threadIdx.x == 0) *a.ctl = sg.ctl_exit[sg.nseg - 1];
 }
 
 }  // namespace
 
-cudaError_t launch_viterbi(const VitArgs &a, cudaStream_t st) {
-  if (!a.nchunks) return cudaSuccess;
-  size_t smem = (((size_t)128 * a.ncs + 15) & ~(size_t)15) + (size_t)a.nsyncs * (2 * 64 * 4 + 2 * 64 * 8 + 4) + 64;
+int vit_rescan_entries(int bits_in) { return bits_in >= 6 ? 64 : (1 << bits_in); }
+
+cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st) {
+  if (!a.nchunks || !nblocks) return cudaSuccess;
+  size_t smem = (((size_t)128 * a.ncs + (size_t)128 * sg.nb + 15) & ~(size_t)15) +
+                (size_t)a.nsyncs * (2 * 64 * 4 + 2 * 64 * 8 + 4) + 64;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  k_viterbi<<<1, 32 * a.nsyncs, smem, st>>>(a);
+  k_viterbi<<<nblocks, 32 * a.nsyncs, smem, st>>>(a, sg);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vit_verify(const VitSegArgs &sg, int nsyncs, uint8_t *ok, uint32_t *nfail, cudaStream_t st) {
+  if (sg.nseg < 2) return cudaSuccess;
+  k_vit_verify<<<sg.nseg - 1, 64, 0, st>>>(sg, nsyncs, ok, nfail);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vit_commit(const VitArgs &a, const VitSegArgs &sg, cudaStream_t st) {
+  k_vit_commit<<<1, 256, 0, st>>>(a, sg);
   return cudaGetLastError();
 }
 

@@ -282,7 +282,25 @@ struct VitArgs {
   VitCtl *ctl;
   uint8_t *out;              // nchunks * 128 * bits_in / 8 bytes
 };
-cudaError_t launch_viterbi(const VitArgs &a, cudaStream_t st);
+// Time segments of the Viterbi stage (see k_viterbi.cu): segment g covers chunks
+// [seg_start[g], seg_start[g+1]); every boundary but the first is a re-sync chunk.
+struct VitSegArgs {
+  const uint64_t *seg_start;   // [nseg + 1] (device)
+  uint32_t nseg;
+  const uint32_t *list;        // null: all segments (g > 0 start cold, warmed up); else the segments to re-run
+  uint32_t nlist;              //       exactly from exit[g-1]
+  uint32_t warm_chunks;        // warm-up of the current decoder (of all decoders when resync_period == 1)
+  uint32_t warm_others;        // 0: no warm-up at all (test knob: every cold segment fails verification)
+  int phase0;                  // resync_phase at chunk 0
+  int nb;                      // rescan entries per state = vit_rescan_entries(bits_in)
+  VitDecState *entry, *exit;   // [nseg][nsyncs]
+  VitCtl *ctl_entry, *ctl_exit;// [nseg]
+};
+int vit_rescan_entries(int bits_in);
+// nblocks = nseg (list == null) or nlist.
+cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st);
+cudaError_t launch_vit_verify(const VitSegArgs &sg, int nsyncs, uint8_t *ok, uint32_t *nfail, cudaStream_t st);
+cudaError_t launch_vit_commit(const VitArgs &a, const VitSegArgs &sg, cudaStream_t st);
 
 // ---------------------------------------------------------------- K6/K7 framing
 struct SyncState {

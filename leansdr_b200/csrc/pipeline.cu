@@ -132,6 +132,7 @@ struct ldvb_handle {
   // Viterbi (viterbi_sync)
   Trellis trellis; VitSyncs vsyncs;
   DevBuf d_vit_pred, d_vit_us, d_vit_maps, d_vit_shifts, d_vit_state, d_vit_ctl;
+  DevBuf d_vit_entry, d_vit_exit, d_vit_aux;   // per time segment: entry / exit states, ctl, lists
   SyncState sync;
   DevBuf d_sync_state, d_sync_res;
   int derand_pos = 0;
@@ -525,7 +526,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
-                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
+                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_vit_entry, &h->d_vit_exit, &h->d_vit_aux, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
                     &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam, &h->d_hs_polar, &h->d_hs_rect, &h->d_hs_sincos, &h->d_hs_errors, &h->d_hs_lock, &h->d_hs_state,
                     &h->m_cnr.d_avg, &h->m_cnr.d_have, &h->m_spec.d_avg, &h->m_spec.d_have, &h->d_meas_carry[0], &h->d_meas_carry[1],
                     &h->d_meas_points, &h->d_meas_power, &h->d_meas_sums, &h->d_meas_rows};
@@ -1445,7 +1446,71 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
   a.maps = h->d_vit_maps.as<uint8_t>(); a.shifts = h->d_vit_shifts.as<int32_t>();
   a.state = h->d_vit_state.as<VitDecState>(); a.ctl = h->d_vit_ctl.as<VitCtl>();
   a.out = h->s_bytes.at(h->s_bytes.count);
-  KL("viterbi", launch_viterbi(a, h->st));
+  {
+    // Time segments (k_viterbi.cu): whole re-sync groups, cold start + warm-up, verified bit for bit.
+    const uint64_t P = (uint64_t)a.resync_period;
+    const bool no_warm = h->cfg.vit_warm_chunks < 0;
+    const uint32_t warm = no_warm ? 0 : h->cfg.vit_warm_chunks ? (uint32_t)h->cfg.vit_warm_chunks : 2;
+    VitCtl ctl0;
+    CK(cudaMemcpyAsync(&ctl0, h->d_vit_ctl.p, sizeof ctl0, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    const uint64_t target = h->cfg.vit_segments > 0 ? (uint64_t)h->cfg.vit_segments : 2048;
+    const uint64_t minL = std::max<uint64_t>(P, 16);
+    uint64_t L = std::max<uint64_t>(minL, (nchunks + target - 1) / target);
+    L = (L + P - 1) / P * P;
+    std::vector<uint64_t> start;
+    start.push_back(0);
+    // first boundary: a re-sync chunk, at least one group (and the warm-up) into the batch
+    uint64_t b = (P - (uint64_t)ctl0.resync_phase % P) % P;
+    while (b < std::max<uint64_t>(P, warm) || b < L / 2) b += P;
+    if (target > 1) for (; b + L / 2 < nchunks; b += L) start.push_back(b);
+    start.push_back(nchunks);
+    const uint32_t nseg = (uint32_t)start.size() - 1;
+    const size_t st_bytes = (size_t)nseg * a.nsyncs * sizeof(VitDecState);
+    if (h->d_vit_entry.bytes < st_bytes) {
+      h->d_vit_entry.release(); h->d_vit_exit.release();
+      CK(h->d_vit_entry.alloc(st_bytes + 4096)); CK(h->d_vit_exit.alloc(st_bytes + 4096));
+    }
+    const size_t aux = (size_t)nseg * (2 * sizeof(VitCtl) + 1 + 4) + (start.size()) * 8 + 256;
+    if (h->d_vit_aux.bytes < aux) { h->d_vit_aux.release(); CK(h->d_vit_aux.alloc(aux + 4096)); }
+    uint8_t *ax = h->d_vit_aux.as<uint8_t>();
+    VitSegArgs sg;
+    memset(&sg, 0, sizeof sg);
+    sg.seg_start = reinterpret_cast<const uint64_t *>(ax); ax += start.size() * 8;
+    sg.ctl_entry = reinterpret_cast<VitCtl *>(ax); ax += (size_t)nseg * sizeof(VitCtl);
+    sg.ctl_exit = reinterpret_cast<VitCtl *>(ax); ax += (size_t)nseg * sizeof(VitCtl);
+    uint32_t *d_list = reinterpret_cast<uint32_t *>(ax); ax += (size_t)nseg * 4;
+    uint32_t *d_nfail = reinterpret_cast<uint32_t *>(ax); ax += 8;
+    uint8_t *d_ok = ax;
+    sg.nseg = nseg; sg.list = nullptr; sg.nlist = 0; sg.warm_chunks = warm; sg.warm_others = no_warm ? 0 : 1;
+    sg.phase0 = ctl0.resync_phase; sg.nb = vit_rescan_entries(bits_in);
+    sg.entry = h->d_vit_entry.as<VitDecState>(); sg.exit = h->d_vit_exit.as<VitDecState>();
+    CK(cudaMemcpyAsync(const_cast<uint64_t *>(sg.seg_start), start.data(), start.size() * 8, cudaMemcpyHostToDevice, h->st));
+    KL("viterbi", launch_viterbi(a, sg, nseg, h->st));
+    h->meas.vit_segments += nseg;
+    std::vector<uint8_t> ok(nseg);
+    for (uint32_t round = 0; nseg > 1 && round <= nseg; ++round) {
+      uint32_t nfail = 0;
+      CK(cudaMemsetAsync(d_nfail, 0, 4, h->st));
+      KL("vit_verify", launch_vit_verify(sg, a.nsyncs, d_ok, d_nfail, h->st));
+      CK(cudaMemcpyAsync(&nfail, d_nfail, 4, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      if (!nfail) break;
+      CK(cudaMemcpyAsync(ok.data(), d_ok, nseg, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      ok[0] = 1;
+      std::vector<uint32_t> todo;
+      for (uint32_t g = 1; g < nseg; ++g) if (!ok[g] && ok[g - 1]) todo.push_back(g);
+      if (todo.empty()) return fail(h, LDVB_ESTATE, "viterbi segment repair made no progress");
+      h->meas.vit_repaired += (uint32_t)todo.size();
+      CK(cudaMemcpyAsync(d_list, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, h->st));
+      VitSegArgs rp = sg;
+      rp.list = d_list; rp.nlist = (uint32_t)todo.size();
+      KL("viterbi", launch_viterbi(a, rp, rp.nlist, h->st));
+      CK(cudaStreamSynchronize(h->st));      // `todo` is a local buffer
+    }
+    KL("vit_commit", launch_vit_commit(a, sg, h->st));
+  }
   *produced = nchunks * bpc;
   h->s_bytes.count += *produced;
   h->s_bytes.fresh += *produced;

@@ -196,6 +196,30 @@ def test_viterbi_bit_exact(product, oracle, name, kw, gkw, npk):
     assert len(ref["ts"]) > npk - 120
 
 
+@pytest.mark.parametrize("name,kw,gkw,npk", [VIT_CASES[0], VIT_CASES[2], VIT_CASES[5]], ids=["vit12-noise", "vit78", "8psk23"])
+def test_viterbi_time_segments(product, oracle, name, kw, gkw, npk):
+    """The Viterbi stage decodes time segments concurrently from a cold start plus warm-up and verifies every
+    segment's entry state against its predecessor's exit state (k_viterbi.cu).  Same bytes whatever the cut:
+    default segments, one serial pass (the reference's schedule), many short segments, and segments without any
+    warm-up (every one of them fails verification and is re-run exactly: the repair path)."""
+    P, O = product, oracle
+    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    runs = {}
+    for label, extra in (("default", {}), ("serial", dict(vit_segments=1)), ("short", dict(vit_segments=100000)),
+                         ("no-warmup", dict(vit_segments=100000, vit_warm_chunks=-1))):
+        got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw, **extra)
+        assert_prefix(got["bytes"], ref["bytes"], f"Viterbi bytes ({label})")
+        assert_prefix(got["ts"], ref["ts"], f"TS ({label})")
+        runs[label] = got["meas"]
+    assert runs["serial"]["vit_segments"] == 1 and runs["serial"]["vit_repaired"] == 0
+    assert runs["default"]["vit_segments"] > 4
+    assert runs["short"]["vit_segments"] >= runs["default"]["vit_segments"]
+    assert runs["no-warmup"]["vit_repaired"] > 0
+    # with the warm-up, segments merge: at most a few repairs while the hypothesis is still being chosen
+    assert runs["default"]["vit_repaired"] <= 4, runs["default"]
+
+
 def _freq_shift(raw, f_rel, phase0=0.3):
     x = raw.view(np.float32).reshape(-1, 2).astype(np.float64)
     z = (x[:, 0] + 1j * x[:, 1]) * np.exp(1j * (2 * np.pi * f_rel * np.arange(x.shape[0]) + phase0))
