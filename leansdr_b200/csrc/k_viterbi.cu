@@ -27,9 +27,9 @@
 // survivors descend from one state, the normalised metrics and the path registers no longer
 // depend on where the decoder started.  The stream is cut into segments (whole re-sync
 // groups); one CTA per segment starts its decoders COLD a little earlier -- all of them on the
-// previous re-sync chunk, which is the only data the non-current ones see between two votes
-// anyway, with that chunk's vote; then the current one again, cold, on the last `warm_chunks`
-// chunks -- and records the state with which it enters its segment.  k_vit_verify compares entry(g) with exit(g-1) bit for bit (64 metrics, 64 path
+// previous `warm_others` re-sync chunks, which is the only data the non-current ones see
+// between two votes anyway, with those chunks' votes; then the current one again, cold, on the
+// last `warm_chunks` chunks -- and records the state with which it enters its segment.  k_vit_verify compares entry(g) with exit(g-1) bit for bit (64 metrics, 64 path
 // registers per decoder, the current decoder and the re-sync phase); a segment that did not
 // merge is re-run from its predecessor's exit state (list mode).  Exactness therefore holds by
 // induction, as for the notch segments and the receiver spans; segment 0 always starts from
@@ -219,11 +219,15 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
       __syncthreads();
     };
     if (P > 1) {
-      // A: every decoder on the previous re-sync chunk (all the other decoders ever see between
-      //    two votes), then the vote of that chunk.
-      const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - (uint64_t)P, false, lane);
-      if (lane == 0) totaldiscr[warp] = td;
-      vote();
+      // A: every decoder on the previous warm_others re-sync chunks (all the other decoders ever
+      //    see between two votes), with their votes.  A decoder of a WRONG hypothesis is fed noise:
+      //    its 64 survivors coalesce like a random genealogy (time scale ~64 blocks, exponential
+      //    tail), so it needs ~1000 blocks where the right one needs a few dozen.
+      for (uint32_t j = sg.warm_others; j >= 1; --j) {
+        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - (uint64_t)j * (uint64_t)P, false, lane);
+        if (lane == 0) totaldiscr[warp] = td;
+        vote();
+      }
       // B: the decoder that is current now restarts cold on the last warm_chunks chunks.
       if (warp == s_ctl[0]) {
         for (int s = lane; s < 64; s += 32) { w.cost[s] = 0; w.path[s] = 0; }

@@ -290,7 +290,8 @@ struct VitSegArgs {
   const uint32_t *list;        // null: all segments (g > 0 start cold, warmed up); else the segments to re-run
   uint32_t nlist;              //       exactly from exit[g-1]
   uint32_t warm_chunks;        // warm-up of the current decoder (of all decoders when resync_period == 1)
-  uint32_t warm_others;        // 0: no warm-up at all (test knob: every cold segment fails verification)
+  uint32_t warm_others;        // resync_period > 1: re-sync chunks every decoder warms up on (0 with warm_chunks == 0:
+                               // no warm-up at all, a test knob: every cold segment fails verification)
   int phase0;                  // resync_phase at chunk 0
   int nb;                      // rescan entries per state = vit_rescan_entries(bits_in)
   VitDecState *entry, *exit;   // [nseg][nsyncs]

@@ -1450,19 +1450,22 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
     // Time segments (k_viterbi.cu): whole re-sync groups, cold start + warm-up, verified bit for bit.
     const uint64_t P = (uint64_t)a.resync_period;
     const bool no_warm = h->cfg.vit_warm_chunks < 0;
-    const uint32_t warm = no_warm ? 0 : h->cfg.vit_warm_chunks ? (uint32_t)h->cfg.vit_warm_chunks : 2;
+    // Warm-up: 2 chunks bring the current decoder (right hypothesis) back; the decoders of wrong hypotheses
+    // decode noise and need ~1000 blocks = 8 chunks (they only run on re-sync chunks: 8 of those).
+    const uint32_t warm_others = no_warm ? 0 : 8;
+    const uint32_t warm = no_warm ? 0 : h->cfg.vit_warm_chunks ? (uint32_t)h->cfg.vit_warm_chunks : (P > 1 ? 2 : 8);
     VitCtl ctl0;
     CK(cudaMemcpyAsync(&ctl0, h->d_vit_ctl.p, sizeof ctl0, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     const uint64_t target = h->cfg.vit_segments > 0 ? (uint64_t)h->cfg.vit_segments : 2048;
-    const uint64_t minL = std::max<uint64_t>(P, 16);
+    const uint64_t minL = std::max<uint64_t>(P, 64);
     uint64_t L = std::max<uint64_t>(minL, (nchunks + target - 1) / target);
     L = (L + P - 1) / P * P;
     std::vector<uint64_t> start;
     start.push_back(0);
     // first boundary: a re-sync chunk, at least one group (and the warm-up) into the batch
     uint64_t b = (P - (uint64_t)ctl0.resync_phase % P) % P;
-    while (b < std::max<uint64_t>(P, warm) || b < L / 2) b += P;
+    while (b < std::max<uint64_t>(P * std::max<uint32_t>(warm_others, 1), warm) || b < L / 2) b += P;
     if (target > 1) for (; b + L / 2 < nchunks; b += L) start.push_back(b);
     start.push_back(nchunks);
     const uint32_t nseg = (uint32_t)start.size() - 1;
@@ -1482,7 +1485,7 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
     uint32_t *d_list = reinterpret_cast<uint32_t *>(ax); ax += (size_t)nseg * 4;
     uint32_t *d_nfail = reinterpret_cast<uint32_t *>(ax); ax += 8;
     uint8_t *d_ok = ax;
-    sg.nseg = nseg; sg.list = nullptr; sg.nlist = 0; sg.warm_chunks = warm; sg.warm_others = no_warm ? 0 : 1;
+    sg.nseg = nseg; sg.list = nullptr; sg.nlist = 0; sg.warm_chunks = warm; sg.warm_others = P > 1 ? warm_others : 0;
     sg.phase0 = ctl0.resync_phase; sg.nb = vit_rescan_entries(bits_in);
     sg.entry = h->d_vit_entry.as<VitDecState>(); sg.exit = h->d_vit_exit.as<VitDecState>();
     CK(cudaMemcpyAsync(const_cast<uint64_t *>(sg.seg_start), start.data(), start.size() * 8, cudaMemcpyHostToDevice, h->st));

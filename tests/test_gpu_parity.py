@@ -213,11 +213,11 @@ def test_viterbi_time_segments(product, oracle, name, kw, gkw, npk):
         assert_prefix(got["ts"], ref["ts"], f"TS ({label})")
         runs[label] = got["meas"]
     assert runs["serial"]["vit_segments"] == 1 and runs["serial"]["vit_repaired"] == 0
-    assert runs["default"]["vit_segments"] > 4
+    assert runs["default"]["vit_segments"] >= 4
     assert runs["short"]["vit_segments"] >= runs["default"]["vit_segments"]
     assert runs["no-warmup"]["vit_repaired"] > 0
     # with the warm-up, segments merge: at most a few repairs while the hypothesis is still being chosen
-    assert runs["default"]["vit_repaired"] <= 4, runs["default"]
+    assert runs["default"]["vit_repaired"] <= max(2, runs["default"]["vit_segments"] // 20), runs["default"]
 
 
 def _freq_shift(raw, f_rel, phase0=0.3):
