@@ -46,15 +46,21 @@ constexpr int kVitChunk = 128;
 struct VitWarp {
   int32_t *cost;        // [2][64]
   uint64_t *path;       // [2][64]
+  int32_t *blk_cost;    // [128] branch cost of the blocks of the chunk being decoded
+  uint8_t *blk_cs;      // [128] their coded symbols
   const uint8_t *map;
   int shift, bank;
 };
 
 // One chunk of 128 FEC blocks for this warp's decoder (update_sync + viterbi_dec::update,
-// dvb.h:1353-1364, viterbi.h:196-263).  Returns the sum of quality over blocks >= discr_delay.
+// dvb.h:1353-1364, viterbi.h:196-263).  Returns the sum of quality over blocks >= discr_delay
+// (only computed when need_td: the votes look at it on re-sync chunks only).
+// The coded symbol and the branch cost of the 128 blocks do not depend on the decoder state:
+// the lanes prepare them in parallel (4 blocks each) before the serial walk, which then touches
+// shared memory only.
 __device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const uint8_t *t_pred, const uint8_t *t_us,
                                              const uint8_t *l_pred, const uint8_t *l_us, int nb, uint64_t chunk,
-                                             bool write_out, int lane) {
+                                             bool write_out, bool need_td, int lane) {
   const int discr_delay = 64 / a.bits_in;   // dvb.h:1369
   const uint64_t path_mask = (1ull << a.path_nbits) - 1;
   const int read_shift = (a.path_depth - 1) * a.path_nbits;
@@ -62,16 +68,28 @@ __device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const
   int32_t td = 0;
   uint64_t outstream = 0; int nout = 0;
   uint8_t *outp = a.out + chunk * bytes_per_chunk;
-  const uint32_t *pin = a.symbols + chunk * (uint64_t)kVitChunk * a.nshifts + w.shift;
-  int bank = w.bank;
-  for (int blk = 0; blk < kVitChunk; ++blk, pin += a.nshifts) {
-    // update_sync (dvb.h:1353-1364): coded symbol and cost of this FEC block
-    unsigned cs = 0; int32_t bcost = 0;
-    for (int i = 0; i < a.nshifts; ++i) {
-      const uint32_t sw = __ldg(pin + i);
-      cs = ((cs << a.bps) | w.map[(sw >> 16) & 0xffu]) & 0xffu;
-      bcost += (int32_t)(int16_t)(sw & 0xffffu);
+  {
+    // update_sync (dvb.h:1353-1364): coded symbol and cost of every FEC block of the chunk
+    const uint32_t *pin = a.symbols + chunk * (uint64_t)kVitChunk * a.nshifts + w.shift;
+#pragma unroll
+    for (int q = 0; q < kVitChunk / 32; ++q) {
+      const int blk = lane + 32 * q;
+      const uint32_t *pb = pin + (size_t)blk * a.nshifts;
+      unsigned cs = 0; int32_t bcost = 0;
+      for (int i = 0; i < a.nshifts; ++i) {
+        const uint32_t sw = __ldg(pb + i);
+        cs = ((cs << a.bps) | __ldg(w.map + ((sw >> 16) & 0xffu))) & 0xffu;
+        bcost += (int32_t)(int16_t)(sw & 0xffffu);
+      }
+      w.blk_cs[blk] = (uint8_t)cs;
+      w.blk_cost[blk] = bcost;
     }
+    __syncwarp();
+  }
+  int bank = w.bank;
+  for (int blk = 0; blk < kVitChunk; ++blk) {
+    const unsigned cs = w.blk_cs[blk];
+    const int32_t bcost = w.blk_cost[blk];
     const int32_t *cc = w.cost + bank * 64;
     const uint64_t *pc = w.path + bank * 64;
     int32_t *cn = w.cost + (bank ^ 1) * 64;
@@ -99,30 +117,24 @@ __device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const
       uint64_t np = pc[best_pred];
       if (a.path32) np = (uint64_t)(uint32_t)(((uint32_t)np << a.path_nbits) | (uint32_t)best_us);
       else np = (np << a.path_nbits) | (uint64_t)best_us;
-      pn[s] = np; cn[s] = best_m; my_m[h] = best_m;
+      pn[s] = np; my_m[h] = best_m;
     }
     // best state: minimum, first index wins (viterbi.h:239-243)
-    int32_t bm; int bs;
-    if (my_m[1] < my_m[0]) { bm = my_m[1]; bs = lane + 32; } else { bm = my_m[0]; bs = lane; }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const int32_t om = __shfl_xor_sync(0xffffffffu, bm, o);
-      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-      if (om < bm || (om == bm && os < bs)) { bm = om; bs = os; }
-    }
-    // second best: minimum over all states except the best one (duplicates count)
-    int32_t b2 = 0x7fffffff;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) if (lane + 32 * h != bs && my_m[h] < b2) b2 = my_m[h];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { const int32_t v = __shfl_xor_sync(0xffffffffu, b2, o); if (v < b2) b2 = v; }
-    __syncwarp();
-    bank ^= 1;
+    const int32_t bm = __reduce_min_sync(0xffffffffu, min(my_m[0], my_m[1]));
+    const unsigned e0 = __ballot_sync(0xffffffffu, my_m[0] == bm);
+    const unsigned e1 = __ballot_sync(0xffffffffu, my_m[1] == bm);
+    const int bs = e0 ? (__ffs((int)e0) - 1) : (32 + __ffs((int)e1) - 1);
     // normalise (viterbi.h:249)
-    cn[lane] -= bm; cn[lane + 32] -= bm;
+    cn[lane] = my_m[0] - bm; cn[lane + 32] = my_m[1] - bm;
+    bank ^= 1;
+    if (need_td) {
+      // second best: minimum over all states except the best one (duplicates count)
+      const int32_t x0 = (lane == bs) ? 0x7fffffff : my_m[0];
+      const int32_t x1 = (lane + 32 == bs) ? 0x7fffffff : my_m[1];
+      const int32_t b2 = __reduce_min_sync(0xffffffffu, min(x0, x1));
+      if (blk >= discr_delay) td += b2 - bm;
+    }
     __syncwarp();
-    const int32_t quality = b2 - bm;
-    if (blk >= discr_delay) td += quality;
     if (write_out) {
       const unsigned result = (unsigned)((pn[bs] >> read_shift) & path_mask);
       outstream = (outstream << a.bits_in) | result;
@@ -161,6 +173,11 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
   off += (size_t)nw * 2 * 64 * 8;
   int32_t *totaldiscr = reinterpret_cast<int32_t *>(smem + off);
   off += (size_t)nw * 4;
+  int32_t *blk_cost_all = reinterpret_cast<int32_t *>(smem + off);
+  off += (size_t)nw * kVitChunk * 4;
+  uint8_t *blk_cs_all = smem + off;
+  off += (size_t)nw * kVitChunk;
+  off = (off + 15) & ~(size_t)15;
   int *s_ctl = reinterpret_cast<int *>(smem + off);   // [0] current_sync
 
   const uint32_t g = sg.list ? sg.list[blockIdx.x] : blockIdx.x;
@@ -190,6 +207,8 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
   VitWarp w;
   w.cost = cost_all + (size_t)warp * 128;
   w.path = path_all + (size_t)warp * 128;
+  w.blk_cost = blk_cost_all + (size_t)warp * kVitChunk;
+  w.blk_cs = blk_cs_all + (size_t)warp * kVitChunk;
   w.map = a.maps + (size_t)warp * a.nsymbols;
   w.shift = a.shifts[warp];
   w.bank = 0;
@@ -224,7 +243,7 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
       //    its 64 survivors coalesce like a random genealogy (time scale ~64 blocks, exponential
       //    tail), so it needs ~1000 blocks where the right one needs a few dozen.
       for (uint32_t j = sg.warm_others; j >= 1; --j) {
-        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - (uint64_t)j * (uint64_t)P, false, lane);
+        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - (uint64_t)j * (uint64_t)P, false, true, lane);
         if (lane == 0) totaldiscr[warp] = td;
         vote();
       }
@@ -233,11 +252,11 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
         for (int s = lane; s < 64; s += 32) { w.cost[s] = 0; w.path[s] = 0; }
         w.bank = 0;
         __syncwarp();
-        for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, lane);
+        for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, false, lane);
       }
     } else {
       for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) {
-        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, lane);
+        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, true, lane);
         if (lane == 0) totaldiscr[warp] = td;
         vote();
       }
@@ -255,7 +274,7 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
     const bool resync = (((uint64_t)sg.phase0 + chunk) % (uint64_t)P) == 0;
     const bool mine = (warp == current);
     if (mine || resync) {
-      const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, chunk, mine, lane);
+      const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, chunk, mine, resync, lane);
       if (lane == 0) totaldiscr[warp] = td;
     }
     __syncthreads();
@@ -313,7 +332,7 @@ int vit_rescan_entries(int bits_in) { return bits_in >= 6 ? 64 : (1 << bits_in);
 cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st) {
   if (!a.nchunks || !nblocks) return cudaSuccess;
   size_t smem = (((size_t)128 * a.ncs + (size_t)128 * sg.nb + 15) & ~(size_t)15) +
-                (size_t)a.nsyncs * (2 * 64 * 4 + 2 * 64 * 8 + 4) + 64;
+                (size_t)a.nsyncs * (2 * 64 * 4 + 2 * 64 * 8 + 4 + kVitChunk * 5) + 96;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
