@@ -92,12 +92,12 @@ def gen_vector(npackets: int) -> np.ndarray:
     return V.ref_iq(npackets, fmt="f32")
 
 
-def gen_vector_device(npackets: int, dev, torch, P):
+def gen_vector_device(npackets: int, dev, torch, P, ratio="6/5", fec="1/2"):
     """The same waveform synthesised in HBM by the B200 transmit chain (include/leandvb_b200_tx.h;
     bit-identical to leantsgen | leandvbtx, tests/test_gpu_tx.py): numbered TS packets ->
     randomizer, RS, interleaver, convolutional code, QPSK, RRC x6/5, AGC.  Returns a float32 device
     tensor of interleaved I/Q."""
-    tx = P.Transmitter(ratio="6/5", power="37.5", agc=True, max_packets=npackets, device=dev.index or 0)
+    tx = P.Transmitter(ratio=ratio, fec=fec, power="37.5", agc=True, max_packets=npackets, device=dev.index or 0)
     ts = torch.empty(npackets * 188, dtype=torch.uint8, device=dev)
     tx.tsgen_device(0, npackets, ts.data_ptr())
     cap = tx.max_samples(npackets)
@@ -296,7 +296,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", default="f32", choices=["f32", "u8", "hs", "viterbi"],
+    ap.add_argument("--variant", default="f32", choices=["f32", "u8", "hs", "viterbi", "viterbi78"],
                     help="side measurements (N = 1): 'u8' = the same chain fed complex<u8> IQ (leandvb --u8), 'hs' = leandvb --u8 --hs "
                          "(fast_qpsk_receiver path), 'viterbi' = leandvb --f32 --resample --viterbi (viterbi_sync instead of deconvol_sync).  "
                          "The default 'f32' is BASELINE.json's configuration.")
@@ -318,10 +318,18 @@ def main():
 
     ref_flags = list(REF_FLAGS)
     rx_kw = dict(fmt="f32", resample=True)
+    tx_kw = {}
     if a.variant != "f32":
         if a.impl == "reference" or world > 1:
             raise SystemExit("--variant is a single-GPU side measurement of the b200 arm")
-        if a.variant == "viterbi":
+        if a.variant == "viterbi78":
+            # BASELINE.json configs[2]: broadcast rate, 2 samples per symbol
+            ref_flags = ["--f32", "-f", "55e6", "--sr", "27.5e6", "--cr", "7/8", "--standard", "DVB-S", "--viterbi"]
+            rx_kw = dict(fmt="f32", Fs=55e6, Fm=27.5e6, fec="7/8", viterbi=True)
+            tx_kw = dict(ratio="2", fec="7/8")
+            workload["workload"] = ("SIDE MEASUREMENT (BASELINE.json configs[2]): leantsgen|leandvbtx --cr 7/8 -f 2 --power 37.5 --agc -> leandvb "
+                                    + " ".join(ref_flags))
+        elif a.variant == "viterbi":
             ref_flags = list(REF_FLAGS) + ["--viterbi"]
             rx_kw = dict(fmt="f32", resample=True, viterbi=True)
             workload["workload"] = "SIDE MEASUREMENT, not BASELINE.json's configuration: same f32 waveform -> leandvb " + " ".join(ref_flags)
@@ -379,10 +387,10 @@ def main():
         iq_dev = torch.from_numpy(raw).to(dev)
         workload["synthesis"] = "oracle/_ref leantsgen | leandvbtx on the host"
     else:
-        iq_dev = gen_vector_device(a.packets, dev, torch, P)
+        iq_dev = gen_vector_device(a.packets, dev, torch, P, **tx_kw)
         raw = iq_dev.cpu().numpy()
         workload["synthesis"] = "B200 transmit chain (ldvbtx_*), bit-identical to leantsgen | leandvbtx"
-        if rank == 0:
+        if rank == 0 and not tx_kw:
             head = gen_vector(min(a.packets, 2048))          # the unmodified reference transmitter, same packets
             vector_check = bool(head.size > 1000000 and np.array_equal(head.view(np.uint32), raw[: head.size].view(np.uint32)))
     if a.variant in ("u8", "hs"):
@@ -394,7 +402,7 @@ def main():
     rx = P.Receiver(anf=a.anf, rx_mode=mode, max_batch=n, device=local, **rx_kw)
     stream = torch.cuda.current_stream()
     rx.set_stream(stream.cuda_stream)
-    cap = n // 1900 + 64
+    cap = n // 900 + 64
     ts_dev = torch.empty(cap * 188, dtype=torch.uint8, device=dev)
 
     def barrier():

@@ -131,7 +131,7 @@ typedef struct ldvb_config {
                                 mpeg_sync with fastlock; needs u8 input, QPSK, code rate 1/2; no notch,
                                 filter, CNR or spectrum blocks exist on that path                  */
   int32_t  vit_segments;     /* --viterbi: target number of concurrent time segments per batch
-                                (0 = 2048; 1 = one serial pass, the reference's own schedule)    */
+                                (0 = one full wave of CTAs; 1 = one serial pass, the reference's own schedule)    */
   int32_t  vit_warm_chunks;  /* --viterbi: warm-up of a cold segment, 128-block chunks (0 = 2; -1 = none at
                                 all: a test knob, every segment then fails verification and is re-run) */
 } ldvb_config;

@@ -329,16 +329,38 @@ __global__ void k_vit_commit(VitArgs a, VitSegArgs sg) {
 
 int vit_rescan_entries(int bits_in) { return bits_in >= 6 ? 64 : (1 << bits_in); }
 
-cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st) {
-  if (!a.nchunks || !nblocks) return cudaSuccess;
-  size_t smem = (((size_t)128 * a.ncs + (size_t)128 * sg.nb + 15) & ~(size_t)15) +
-                (size_t)a.nsyncs * (2 * 64 * 4 + 2 * 64 * 8 + 4 + kVitChunk * 5) + 96;
+static size_t vit_smem_bytes(int ncs, int nb, int nsyncs) {
+  return (((size_t)128 * ncs + (size_t)128 * nb + 15) & ~(size_t)15) +
+         (size_t)nsyncs * (2 * 64 * 4 + 2 * 64 * 8 + 4 + kVitChunk * 5) + 96;
+}
+
+static cudaError_t vit_configure(size_t smem) {
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
+  return cudaSuccess;
+}
+
+// Segments (CTAs) that are resident at the same time on the current device: one full wave.
+int vit_resident_segments(int ncs, int bits_in, int nsyncs) {
+  const size_t smem = vit_smem_bytes(ncs, vit_rescan_entries(bits_in), nsyncs);
+  if (vit_configure(smem) != cudaSuccess) return 0;
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_viterbi, 32 * nsyncs, smem) != cudaSuccess)
+    return 0;
+  return sms * per_sm;
+}
+
+cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st) {
+  if (!a.nchunks || !nblocks) return cudaSuccess;
+  const size_t smem = vit_smem_bytes(a.ncs, sg.nb, a.nsyncs);
+  cudaError_t e = vit_configure(smem);
+  if (e != cudaSuccess) return e;
   k_viterbi<<<nblocks, 32 * a.nsyncs, smem, st>>>(a, sg);
   return cudaGetLastError();
 }

@@ -298,6 +298,7 @@ struct VitSegArgs {
   VitCtl *ctl_entry, *ctl_exit;// [nseg]
 };
 int vit_rescan_entries(int bits_in);
+int vit_resident_segments(int ncs, int bits_in, int nsyncs);   // CTAs of one full wave on the current device (0: unknown)
 // nblocks = nseg (list == null) or nlist.
 cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st);
 cudaError_t launch_vit_verify(const VitSegArgs &sg, int nsyncs, uint8_t *ok, uint32_t *nfail, cudaStream_t st);

@@ -132,6 +132,7 @@ struct ldvb_handle {
   // Viterbi (viterbi_sync)
   Trellis trellis; VitSyncs vsyncs;
   DevBuf d_vit_pred, d_vit_us, d_vit_maps, d_vit_shifts, d_vit_state, d_vit_ctl;
+  int vit_wave = 0;                            // CTAs of k_viterbi resident at once on this device
   DevBuf d_vit_entry, d_vit_exit, d_vit_aux;   // per time segment: entry / exit states, ctl, lists
   SyncState sync;
   DevBuf d_sync_state, d_sync_res;
@@ -1457,7 +1458,9 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
     VitCtl ctl0;
     CK(cudaMemcpyAsync(&ctl0, h->d_vit_ctl.p, sizeof ctl0, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    const uint64_t target = h->cfg.vit_segments > 0 ? (uint64_t)h->cfg.vit_segments : 2048;
+    // Default: one full wave of CTAs (every segment resident at once, no tail).
+    if (!h->vit_wave) h->vit_wave = std::max(1, vit_resident_segments(a.ncs, bits_in, a.nsyncs));
+    const uint64_t target = h->cfg.vit_segments > 0 ? (uint64_t)h->cfg.vit_segments : (uint64_t)h->vit_wave;
     const uint64_t minL = std::max<uint64_t>(P, 64);
     uint64_t L = std::max<uint64_t>(minL, (nchunks + target - 1) / target);
     L = (L + P - 1) / P * P;
