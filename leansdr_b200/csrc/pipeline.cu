@@ -1452,16 +1452,17 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
     const uint64_t P = (uint64_t)a.resync_period;
     const bool no_warm = h->cfg.vit_warm_chunks < 0;
     // Warm-up: 2 chunks bring the current decoder (right hypothesis) back; the decoders of wrong hypotheses
-    // decode noise and need ~1000 blocks = 8 chunks (they only run on re-sync chunks: 8 of those).
-    const uint32_t warm_others = no_warm ? 0 : 8;
-    const uint32_t warm = no_warm ? 0 : h->cfg.vit_warm_chunks ? (uint32_t)h->cfg.vit_warm_chunks : (P > 1 ? 2 : 8);
+    // decode noise and need ~2000 blocks = 16 chunks (they only run on re-sync chunks: 16 of those; with 8,
+    // 11-13 of ~1100-2000 segments still failed, and a repair round costs a whole segment time).
+    const uint32_t warm_others = no_warm ? 0 : 16;
+    const uint32_t warm = no_warm ? 0 : h->cfg.vit_warm_chunks ? (uint32_t)h->cfg.vit_warm_chunks : (P > 1 ? 2 : 16);
     VitCtl ctl0;
     CK(cudaMemcpyAsync(&ctl0, h->d_vit_ctl.p, sizeof ctl0, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     // Default: one full wave of CTAs (every segment resident at once, no tail).
     if (!h->vit_wave) h->vit_wave = std::max(1, vit_resident_segments(a.ncs, bits_in, a.nsyncs));
     const uint64_t target = h->cfg.vit_segments > 0 ? (uint64_t)h->cfg.vit_segments : (uint64_t)h->vit_wave;
-    const uint64_t minL = std::max<uint64_t>(P, 64);
+    const uint64_t minL = std::max<uint64_t>(P, 128);
     uint64_t L = std::max<uint64_t>(minL, (nchunks + target - 1) / target);
     L = (L + P - 1) / P * P;
     std::vector<uint64_t> start;
