@@ -203,7 +203,7 @@ def test_viterbi_time_segments(product, oracle, name, kw, gkw, npk):
     default segments, one serial pass (the reference's schedule), many short segments, and segments without any
     warm-up (every one of them fails verification and is re-run exactly: the repair path)."""
     P, O = product, oracle
-    raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
+    raw = V.ref_iq(max(npk, 800), fmt=kw["fmt"], **gkw)     # >= 16 re-sync groups of warm-up + a few segments at 7/8
     ref = O.Chain(O.Config(**kw)).run(raw)
     runs = {}
     for label, extra in (("default", {}), ("serial", dict(vit_segments=1)), ("short", dict(vit_segments=100000)),
