@@ -242,8 +242,21 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
       //    see between two votes), with their votes.  A decoder of a WRONG hypothesis is fed noise:
       //    its 64 survivors coalesce like a random genealogy (time scale ~64 blocks, exponential
       //    tail), so it needs ~1000 blocks where the right one needs a few dozen.
-      for (uint32_t j = sg.warm_others; j >= 1; --j) {
-        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - (uint64_t)j * (uint64_t)P, false, true, lane);
+      //    A segment that starts fewer than warm_others re-sync chunks into the batch does better:
+      //    the other decoders only ever run on re-sync chunks, so their state at c0 follows EXACTLY
+      //    from the carried state and the (few) re-sync chunks in front of c0.
+      const uint64_t first_resync = (uint64_t)((P - sg.phase0 % P) % P);
+      uint64_t nres = (c0 - first_resync) / (uint64_t)P;          // re-sync chunks in [0, c0)
+      if (nres < sg.warm_others) {
+        const VitDecState *cs0 = a.state + warp;
+        for (int s = lane; s < 64; s += 32) { w.cost[s] = cs0->cost[s]; w.path[s] = cs0->path[s]; }
+        w.bank = 0;
+        __syncwarp();
+      } else {
+        nres = sg.warm_others;
+      }
+      for (uint64_t j = nres; j >= 1; --j) {
+        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - j * (uint64_t)P, false, true, lane);
         if (lane == 0) totaldiscr[warp] = td;
         vote();
       }

@@ -1469,7 +1469,9 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
     start.push_back(0);
     // first boundary: a re-sync chunk, at least one group (and the warm-up) into the batch
     uint64_t b = (P - (uint64_t)ctl0.resync_phase % P) % P;
-    while (b < std::max<uint64_t>(P * std::max<uint32_t>(warm_others, 1), warm) || b < L / 2) b += P;
+    // (P > 1: a segment closer than warm_others re-sync chunks to the start takes the other decoders exactly
+    //  from the carried state, so only the current decoder's warm-up has to fit in front of it)
+    while (b < std::max<uint64_t>(P > 1 ? P : 1, warm) || b < L / 2) b += P;
     if (target > 1) for (; b + L / 2 < nchunks; b += L) start.push_back(b);
     start.push_back(nchunks);
     const uint32_t nseg = (uint32_t)start.size() - 1;
