@@ -58,9 +58,13 @@ struct VitWarp {
 // The coded symbol and the branch cost of the 128 blocks do not depend on the decoder state:
 // the lanes prepare them in parallel (4 blocks each) before the serial walk, which then touches
 // shared memory only.
-__device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const uint8_t *t_pred, const uint8_t *t_us,
-                                             const uint8_t *l_pred, const uint8_t *l_us, int nb, uint64_t chunk,
-                                             bool write_out, bool need_td, int lane) {
+// R12: rate 1/2 (4 labels, 2 predecessors per state): the trellis rows of the lane's two states
+// live in registers (they do not change from block to block), so the serial chain of a block is
+// metric loads -> compare/select -> path load -> store.
+template <bool R12>
+__device__ __forceinline__ int32_t vit_chunk_t(const VitArgs &a, VitWarp &w, const uint8_t *t_pred, const uint8_t *t_us,
+                                               const uint8_t *l_pred, const uint8_t *l_us, int nb, uint64_t chunk,
+                                               bool write_out, bool need_td, int lane) {
   const int discr_delay = 64 / a.bits_in;   // dvb.h:1369
   const uint64_t path_mask = (1ull << a.path_nbits) - 1;
   const int read_shift = (a.path_depth - 1) * a.path_nbits;
@@ -86,6 +90,18 @@ __device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const
     }
     __syncwarp();
   }
+  uint32_t r_tp[2] = {0, 0}, r_tu[2] = {0, 0};
+  int r_lp[2][2] = {{0, 0}, {0, 0}}, r_lu[2][2] = {{0, 0}, {0, 0}};
+  if (R12) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = lane + 32 * h;
+      r_tp[h] = *reinterpret_cast<const uint32_t *>(t_pred + s * 4);
+      r_tu[h] = *reinterpret_cast<const uint32_t *>(t_us + s * 4);
+      r_lp[h][0] = l_pred[s * 2]; r_lp[h][1] = l_pred[s * 2 + 1];
+      r_lu[h][0] = l_us[s * 2]; r_lu[h][1] = l_us[s * 2 + 1];
+    }
+  }
   int bank = w.bank;
   for (int blk = 0; blk < kVitChunk; ++blk) {
     const unsigned cs = w.blk_cs[blk];
@@ -99,6 +115,13 @@ __device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const
     for (int h = 0; h < 2; ++h) {
       const int s = lane + 32 * h;
       int32_t best_m = 0x7fffffff; int best_pred = 0, best_us = 0;
+      if (R12) {
+        const int p = (int)((r_tp[h] >> (8 * cs)) & 0xffu);
+        const int32_t m0 = cc[r_lp[h][0]], m1 = cc[r_lp[h][1]];
+        if (p != 65) { best_m = cc[p] + bcost; best_pred = p; best_us = (int)((r_tu[h] >> (8 * cs)) & 0xffu); }
+        if (m0 <= best_m) { best_m = m0; best_pred = r_lp[h][0]; best_us = r_lu[h][0]; }
+        if (m1 <= best_m) { best_m = m1; best_pred = r_lp[h][1]; best_us = r_lu[h][1]; }
+      } else {
       {
         const int p = t_pred[s * a.ncs + cs];
         if (p != 65) {
@@ -113,6 +136,7 @@ __device__ __forceinline__ int32_t vit_chunk(const VitArgs &a, VitWarp &w, const
           const int32_t m = cc[p];
           if (m <= best_m) { best_m = m; best_pred = p; best_us = lu[k]; }
         }
+      }
       }
       uint64_t np = pc[best_pred];
       if (a.path32) np = (uint64_t)(uint32_t)(((uint32_t)np << a.path_nbits) | (uint32_t)best_us);
@@ -154,7 +178,9 @@ __device__ __forceinline__ void vit_store(VitDecState *dst, const VitWarp &w, in
   if (lane == 0) { dst->bank = 0; dst->pad = 0; }   // the bank is re-based to 0 on store
 }
 
-__global__ void __launch_bounds__(512)
+// R12 instances are rate 1/2: at most 4 decoders (QPSK: 4, BPSK: 2) = 128 threads, 8 CTAs per SM.
+template <bool R12>
+__global__ void __launch_bounds__(R12 ? 128 : 512, R12 ? 8 : 2)
 k_viterbi(VitArgs a, VitSegArgs sg) {
   extern __shared__ __align__(16) unsigned char smem[];
   // Layout: trellis pred[64*ncs], us[64*ncs]; rescan lists pred[64*nb], us[64*nb];
@@ -224,79 +250,73 @@ k_viterbi(VitArgs a, VitSegArgs sg) {
   }
   __syncthreads();
 
+  // One loop over "steps" (a single instance of the block walk in the code):
+  //   A  (cold, P > 1)  every decoder on the re-sync chunks in front of c0, with their votes.  A decoder
+  //      of a WRONG hypothesis is fed noise: its 64 survivors coalesce like a random genealogy (time scale
+  //      ~64 blocks, exponential tail), so it needs ~2000 blocks where the right one needs a few dozen.
+  //      A segment that starts fewer than warm_others re-sync chunks into the batch does better: the other
+  //      decoders only ever run on re-sync chunks, so their state at c0 follows EXACTLY from the carried
+  //      state and the (few) re-sync chunks in front of c0.
+  //   B  (cold)  the decoder that is current after A restarts cold on the last warm_chunks chunks
+  //      (P == 1: every decoder, with the votes).  Nothing is written during A and B; votes ARE taken, from
+  //      cold decoders: which hypothesis is current at c0 is the outcome of the last vote before c0.
+  //   M  the segment's own chunks.
+  uint64_t nA = 0, nB = 0;
   if (cold && (sg.warm_chunks || sg.warm_others)) {
-    // Warm-up: nothing is written.  Votes ARE taken, from cold decoders: which hypothesis is
-    // current at c0 is the outcome of the last vote before c0, and a cold decoder's quality sum
-    // over a chunk differs from the true one only in its first few blocks.
-    auto vote = [&]() {
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int best = s_ctl[0];
-        for (int s = 0; s < a.nsyncs; ++s) if (totaldiscr[s] > totaldiscr[best]) best = s;
-        s_ctl[0] = best;
-      }
-      __syncthreads();
-    };
+    nB = sg.warm_chunks;
     if (P > 1) {
-      // A: every decoder on the previous warm_others re-sync chunks (all the other decoders ever
-      //    see between two votes), with their votes.  A decoder of a WRONG hypothesis is fed noise:
-      //    its 64 survivors coalesce like a random genealogy (time scale ~64 blocks, exponential
-      //    tail), so it needs ~1000 blocks where the right one needs a few dozen.
-      //    A segment that starts fewer than warm_others re-sync chunks into the batch does better:
-      //    the other decoders only ever run on re-sync chunks, so their state at c0 follows EXACTLY
-      //    from the carried state and the (few) re-sync chunks in front of c0.
       const uint64_t first_resync = (uint64_t)((P - sg.phase0 % P) % P);
-      uint64_t nres = (c0 - first_resync) / (uint64_t)P;          // re-sync chunks in [0, c0)
-      if (nres < sg.warm_others) {
+      nA = (c0 - first_resync) / (uint64_t)P;                     // re-sync chunks in [0, c0)
+      if (nA < sg.warm_others) {
         const VitDecState *cs0 = a.state + warp;
         for (int s = lane; s < 64; s += 32) { w.cost[s] = cs0->cost[s]; w.path[s] = cs0->path[s]; }
         w.bank = 0;
-        __syncwarp();
       } else {
-        nres = sg.warm_others;
+        nA = sg.warm_others;
       }
-      for (uint64_t j = nres; j >= 1; --j) {
-        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c0 - j * (uint64_t)P, false, true, lane);
-        if (lane == 0) totaldiscr[warp] = td;
-        vote();
-      }
-      // B: the decoder that is current now restarts cold on the last warm_chunks chunks.
-      if (warp == s_ctl[0]) {
+    }
+  }
+  __syncthreads();
+  const uint64_t nsteps = nA + nB + (c1 - c0);
+  for (uint64_t it = 0; it < nsteps; ++it) {
+    uint64_t chunk; bool runs, vote, out, need_td;
+    const int current = s_ctl[0];
+    if (it < nA) {
+      chunk = c0 - (nA - it) * (uint64_t)P; runs = true; vote = true; out = false; need_td = true;
+    } else if (it < nA + nB) {
+      if (it == nA && P > 1 && warp == current) {
         for (int s = lane; s < 64; s += 32) { w.cost[s] = 0; w.path[s] = 0; }
         w.bank = 0;
         __syncwarp();
-        for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, false, lane);
       }
+      chunk = c0 - (nA + nB - it); runs = (P == 1) || warp == current; vote = (P == 1); out = false; need_td = vote;
     } else {
-      for (uint64_t c = c0 - sg.warm_chunks; c < c0; ++c) {
-        const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, c, false, true, lane);
-        if (lane == 0) totaldiscr[warp] = td;
-        vote();
+      if (it == nA + nB) {
+        vit_store(sg.entry + (size_t)g * nw + warp, w, lane);
+        if (threadIdx.x == 0) {
+          VitCtl ce; ce.current_sync = current; ce.resync_phase = (int)(((uint64_t)sg.phase0 + c0) % (uint64_t)P);
+          sg.ctl_entry[g] = ce;
+        }
       }
+      chunk = c0 + (it - nA - nB);
+      const bool resync = (((uint64_t)sg.phase0 + chunk) % (uint64_t)P) == 0;
+      const bool mine = (warp == current);
+      runs = mine || resync; vote = resync; out = mine; need_td = resync;
     }
-    __syncthreads();
-  }
-  vit_store(sg.entry + (size_t)g * nw + warp, w, lane);
-  if (threadIdx.x == 0) {
-    VitCtl ce; ce.current_sync = s_ctl[0]; ce.resync_phase = (int)(((uint64_t)sg.phase0 + c0) % (uint64_t)P);
-    sg.ctl_entry[g] = ce;
-  }
-
-  for (uint64_t chunk = c0; chunk < c1; ++chunk) {
-    const int current = s_ctl[0];
-    const bool resync = (((uint64_t)sg.phase0 + chunk) % (uint64_t)P) == 0;
-    const bool mine = (warp == current);
-    if (mine || resync) {
-      const int32_t td = vit_chunk(a, w, t_pred, t_us, l_pred, l_us, nb, chunk, mine, resync, lane);
+    if (runs) {
+      const int32_t td = vit_chunk_t<R12>(a, w, t_pred, t_us, l_pred, l_us, nb, chunk, out, need_td, lane);
       if (lane == 0) totaldiscr[warp] = td;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && resync) {   // dvb.h:1402-1411
+    if (threadIdx.x == 0 && vote) {   // dvb.h:1402-1411
       int best = current;
       for (int s = 0; s < a.nsyncs; ++s) if (totaldiscr[s] > totaldiscr[best]) best = s;
       s_ctl[0] = best;
     }
     __syncthreads();
+  }
+  if (c1 == c0) {   // (cannot happen: every segment owns at least one chunk)
+    vit_store(sg.entry + (size_t)g * nw + warp, w, lane);
   }
   vit_store(sg.exit + (size_t)g * nw + warp, w, lane);
   if (threadIdx.x == 0) {
@@ -350,7 +370,7 @@ static size_t vit_smem_bytes(int ncs, int nb, int nsyncs) {
 static cudaError_t vit_configure(size_t smem) {
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_viterbi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -364,7 +384,8 @@ int vit_resident_segments(int ncs, int bits_in, int nsyncs) {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_viterbi, 32 * nsyncs, smem) != cudaSuccess)
+      (ncs == 4 && nsyncs <= 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_viterbi<true>, 32 * nsyncs, smem)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_viterbi<false>, 32 * nsyncs, smem)) != cudaSuccess)
     return 0;
   return sms * per_sm;
 }
@@ -374,7 +395,9 @@ cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblo
   const size_t smem = vit_smem_bytes(a.ncs, sg.nb, a.nsyncs);
   cudaError_t e = vit_configure(smem);
   if (e != cudaSuccess) return e;
-  k_viterbi<<<nblocks, 32 * a.nsyncs, smem, st>>>(a, sg);
+  // rate 1/2 (4 labels, 2 predecessors per state) has its trellis rows in registers
+  if (a.ncs == 4 && sg.nb == 2 && a.nsyncs <= 4) k_viterbi<true><<<nblocks, 32 * a.nsyncs, smem, st>>>(a, sg);
+  else k_viterbi<false><<<nblocks, 32 * a.nsyncs, smem, st>>>(a, sg);
   return cudaGetLastError();
 }
 

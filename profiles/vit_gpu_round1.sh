@@ -2,7 +2,7 @@
 # Viterbi time-segment kernel: parity tests + side measurements.
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -k "viterbi or shard or integration" > gpurun_out/pytest_gpu3.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -k "viterbi or time_sharded_ts_bit_exact" > gpurun_out/pytest_gpu3.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu3.log
 tail -4 gpurun_out/pytest_gpu3.log
 for v in viterbi viterbi78; do
