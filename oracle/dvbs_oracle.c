@@ -1618,6 +1618,55 @@ size_t orc_viterbi_run(orc_viterbi *v, const uint8_t *symbols4, size_t n_in,
   return wr;
 }
 
+/* ---- model-checking hooks for the time-segment schedule of the CUDA Viterbi stage (k_viterbi.cu):
+   the same block update as above (pinned to the reference), driven one chunk at a time by the test. */
+
+/* One chunk (128 FEC blocks) at symbols4 for the decoders in run_mask; returns the bytes of decoder
+   `out_sync` (or nothing when out_sync < 0); totals[s] = sum of quality over blocks >= discr_delay. */
+size_t orc_viterbi_chunk(orc_viterbi *v, const uint8_t *symbols4, uint32_t run_mask, int out_sync,
+			 uint8_t *out, int32_t *totals) {
+  const int chunk_size = 128;
+  int discr_delay = 64 / v->bits_in;
+  size_t wr = 0;
+  for ( int s = 0; s < v->nsyncs; ++s ) {
+    totals[s] = 0;
+    if ( !((run_mask >> s) & 1) ) continue;
+    uint64_t outstream = 0;
+    int nout = 0;
+    const uint8_t *pin = symbols4;
+    for ( int blocknum = 0; blocknum < chunk_size; ++blocknum, pin += 4*v->nshifts ) {
+      int32_t discr;
+      uint8_t result = vit_update_sync(v, s, pin, &discr);
+      if ( blocknum >= discr_delay ) totals[s] += discr;
+      if ( s == out_sync ) {
+	outstream = (outstream << v->bits_in) | result;
+	nout += v->bits_in;
+	while ( nout >= 8 ) { out[wr++] = (uint8_t)(outstream >> (nout-8)); nout -= 8; }
+      }
+    }
+  }
+  return wr;
+}
+
+/* Normalised metrics and path registers of one decoder, as the CUDA stage stores them (bank re-based). */
+void orc_viterbi_get_dec(const orc_viterbi *v, int s, int32_t *cost64, uint64_t *path64) {
+  const vdec *d = &v->syncs[s].dec;
+  memcpy(cost64, d->cost[d->bank], sizeof(int32_t)*64);
+  memcpy(path64, d->path[d->bank], sizeof(uint64_t)*64);
+}
+void orc_viterbi_set_dec(orc_viterbi *v, int s, const int32_t *cost64, const uint64_t *path64) {
+  vdec *d = &v->syncs[s].dec;
+  d->bank = 0;
+  memcpy(d->cost[0], cost64, sizeof(int32_t)*64);
+  memcpy(d->path[0], path64, sizeof(uint64_t)*64);
+}
+void orc_viterbi_set_ctl(orc_viterbi *v, int current_sync, int resync_phase) {
+  v->current_sync = current_sync; v->resync_phase = resync_phase;
+}
+int orc_viterbi_resync_phase(const orc_viterbi *v) { return v->resync_phase; }
+int orc_viterbi_nshifts(const orc_viterbi *v) { return v->nshifts; }
+int orc_viterbi_bits_in(const orc_viterbi *v) { return v->bits_in; }
+
 /* ===================================================== binding helpers */
 /* Flat accessors so that the Python test harness (oracle/oracle.py) can
    allocate and inspect stage state without mirroring struct layouts. */

@@ -266,6 +266,15 @@ void   orc_viterbi_set_resync_period(orc_viterbi *v, int p);
 int    orc_viterbi_nsyncs(const orc_viterbi *v);
 int    orc_viterbi_current_sync(const orc_viterbi *v);
 /* dvb.h:1353-1414. Returns bytes written. */
+/* model-checking hooks for the time-segment schedule of the CUDA Viterbi stage */
+size_t orc_viterbi_chunk(orc_viterbi *v, const uint8_t *symbols4, uint32_t run_mask, int out_sync,
+			 uint8_t *out, int32_t *totals);
+void   orc_viterbi_get_dec(const orc_viterbi *v, int s, int32_t *cost64, uint64_t *path64);
+void   orc_viterbi_set_dec(orc_viterbi *v, int s, const int32_t *cost64, const uint64_t *path64);
+void   orc_viterbi_set_ctl(orc_viterbi *v, int current_sync, int resync_phase);
+int    orc_viterbi_resync_phase(const orc_viterbi *v);
+int    orc_viterbi_nshifts(const orc_viterbi *v);
+int    orc_viterbi_bits_in(const orc_viterbi *v);
 size_t orc_viterbi_run(orc_viterbi *v, const uint8_t *symbols4, size_t n_in,
 		       uint8_t *out, size_t out_cap, size_t *consumed);
 
