@@ -216,6 +216,29 @@ def test_oracle_more_flag_sets_equal_reference_taps(oracle, name, fmt, flags, ok
 
 
 @needs_ref
+def test_oracle_wideband_resample_equals_reference_taps(oracle):
+    """BASELINE.json configs[4], reading 5b of SURVEY 8(d): a carrier oversampled 120x (leandvbtx -f 120), decoded with
+    --resample: 313-tap low-pass, decimation 30, then a 4 samples/symbol receiver (leandvb.cc:353-384)."""
+    O = oracle
+    raw = V.ref_iq(120, ratio="120", fmt="f32")
+    d = tempfile.mkdtemp()
+    ts_ref = subprocess.run([O.ref_bin("ref_tap"), "--f32", "--resample", "-f", "240e6", "--tap-dir", d], input=raw.tobytes(),
+                            stdout=subprocess.PIPE, check=True).stdout
+    ch = O.Chain(O.Config(fmt="f32", resample=True, Fs=240e6))
+    assert ch.decim == 30 and len(ch.fir_taps) == 313
+    t = ch.run(raw)
+    for key, f in (("pp", "pp.cf32"), ("symbols", "symbols.bin"), ("bytes", "bytes.u8"), ("mpegbytes", "mpegbytes.u8")):
+        a = np.ascontiguousarray(t[key]).reshape(-1).view(np.uint8)
+        b = np.fromfile(os.path.join(d, f), dtype=np.uint8)
+        n = min(a.size, b.size)
+        assert n > 0 and np.array_equal(a[:n], b[:n]), key
+        assert a.size >= b.size and a.size - b.size <= 64 * max(1, a.itemsize), key
+    ts = t["ts"].tobytes()
+    n = min(len(ts), len(ts_ref))
+    assert n >= 40 * 188 and ts[:n] == ts_ref[:n]
+
+
+@needs_ref
 def test_oracle_notch_detect_path(oracle):
     """>4 Mi samples so that auto_notch::detect() (sdr.h:76-118) runs once."""
     O = oracle
