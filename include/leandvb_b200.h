@@ -82,7 +82,10 @@ enum { LDVB_SAMP_NEAREST = 0, LDVB_SAMP_LINEAR = 1, LDVB_SAMP_RRC = 2 };
  *          looks at the angle alone).  The ring / grid decisions of the APSK and
  *          QAM constellations depend on the AGC estimate, which remembers ~100
  *          chunks (sdr.h:863-869) -- more than a span's warm-up can reproduce --
- *          so a handle for those constellations runs EXACT whatever is asked. */
+ *          so a handle for those constellations runs EXACT whatever is asked.
+ *          The same holds for receivers fed more than 2 samples per symbol
+ *          (after decimation): the spans' warm-up is 4 chunks of samples,
+ *          validated at 1.2 and 2 samples per symbol only. */
 enum { LDVB_RX_EXACT = 0, LDVB_RX_FAST = 1 };
 
 /* ------------------------------------------------------------------ config
