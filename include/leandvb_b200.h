@@ -84,8 +84,11 @@ enum { LDVB_SAMP_NEAREST = 0, LDVB_SAMP_LINEAR = 1, LDVB_SAMP_RRC = 2 };
  *          chunks (sdr.h:863-869) -- more than a span's warm-up can reproduce --
  *          so a handle for those constellations runs EXACT whatever is asked.
  *          The same holds for receivers fed more than 2 samples per symbol
- *          (after decimation): the spans' warm-up is 4 chunks of samples,
- *          validated at 1.2 and 2 samples per symbol only. */
+ *          (after decimation; validated at 1.2 and 2 only).
+ *          FAST also assumes that the carried AGC state is settled: every span
+ *          restarts from the batch-entry AGC estimate, so a stream whose level is
+ *          far from the nominal amplitude (RMS ~70 in front of the receiver; use
+ *          float_scale) must start in EXACT mode -- see DESIGN.md section 3. */
 enum { LDVB_RX_EXACT = 0, LDVB_RX_FAST = 1 };
 
 /* ------------------------------------------------------------------ config

@@ -658,10 +658,12 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     Fs /= h->decim;
   }
   h->Fs_rx = Fs;
-  // FAST spans warm up for 4 chunks of SAMPLES (512): ~430 symbols at the bench's 1.2 samples per symbol, 256 at 2
-  // (both validated: seams verify, TS bit-exact), but only 128 at 4 samples per symbol, where the first GPU run
-  // of the wideband configuration produced no TS at all in FAST mode (EXACT: every stream bit-exact).  Until
-  // the warm-up is expressed in symbols, receivers fed more than 2 samples per symbol run EXACT.
+  // FAST is validated at 1.2 and 2 samples per symbol with input near the nominal amplitude.  The first GPU run of
+  // the wideband configuration (4 samples per symbol after the decimation) produced no TS in FAST mode (EXACT:
+  // every stream bit-exact).  Cause, found on the oracle: that waveform reaches the receiver with RMS 6 instead of
+  // ~70, the AGC needs a few hundred chunks to pull the gain from 1 to 11, and FAST spans all restart from the
+  // batch-entry AGC state, so it never gets there.  Until FAST has a settling pass,
+  // receivers fed more than 2 samples per symbol -- the heavily decimated wideband case -- run EXACT.
   if (h->cfg.rx_mode == LDVB_RX_FAST && h->Fs_rx / c.Fm > 2.05f) h->cfg.rx_mode = LDVB_RX_EXACT;
   rx_setup(h);
   if (c.hs) {
