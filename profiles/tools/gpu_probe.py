@@ -1,7 +1,7 @@
 """Ad-hoc GPU bring-up probe (not a pytest): product vs oracle on a generated vector."""
 import os, subprocess, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle as O
 import leansdr_b200 as P
 
