@@ -192,7 +192,11 @@ enum {
   LDVB_TABLE_RRC     = 6,    /* ncoeffs float (filtergen.h:68-92)            */
   LDVB_TABLE_DECONV  = 7,    /* punctperiod x uint64 (dvb.h:205-292)         */
   LDVB_TABLE_TRELLIS = 8,    /* 64 x NCS x {pred, us} bytes (viterbi.h:61-92) */
-  LDVB_TABLE_VITMAP  = 9     /* nsyncs x {shift, map[nsymbols]} (dvb.h:1336-1351) */
+  LDVB_TABLE_VITMAP  = 9,    /* nsyncs x {shift, map[nsymbols]} (dvb.h:1336-1351) */
+  /* fast_qpsk_receiver::init_lookup_tables (sdr.h:1144-1164), ldvb_host_table only: */
+  LDVB_TABLE_HS_POLAR  = 10, /* 65536 x u32: angle | radius << 16, index (u8)re * 256 + (u8)im */
+  LDVB_TABLE_HS_RECT   = 11, /* 65536 x u16: re | im << 8, index angle8 * 256 + radius     */
+  LDVB_TABLE_HS_SINCOS = 12  /* 65536 x u16: re | im << 8, index angle16                    */
 };
 
 /* --------------------------------------------------------------- lifecycle */

@@ -2618,6 +2618,9 @@ static int host_table(const ldvb_config &c, int which, std::vector<uint8_t> &blo
       }
       break;
     }
+    case LDVB_TABLE_HS_POLAR: { const HsTables t = make_hs_tables(); put(t.polar.data(), t.polar.size() * 4); break; }
+    case LDVB_TABLE_HS_RECT: { const HsTables t = make_hs_tables(); put(t.rect.data(), t.rect.size() * 2); break; }
+    case LDVB_TABLE_HS_SINCOS: { const HsTables t = make_hs_tables(); put(t.sincos.data(), t.sincos.size() * 2); break; }
     default: return LDVB_EINVAL;
   }
   return LDVB_OK;

@@ -191,6 +191,33 @@ int main(int argc, char **argv) {
     derandomizer *d = new derandomizer(&sch, a, b);
     FILE *f = out("derand.u8"); fwrite(d->pattern, 1, 188*8, f); fclose(f); }
 
+  { // fast_qpsk_receiver<u8>::init_lookup_tables (sdr.h:1144-1164), packed like the B200 library uploads them:
+    // polar = angle | radius << 16 (u32), rect / sincos = re | im << 8 (u16)
+    scheduler sch;
+    pipebuf<cu8> pi(&sch, "i", 4096);
+    pipebuf<u8> po(&sch, "o", 4096);
+    fast_qpsk_receiver<u8> *r = new fast_qpsk_receiver<u8>(&sch, pi, po);
+    FILE *f = out("hs_polar.u32");
+    for ( int i=0; i<256; ++i )
+      for ( int q=0; q<256; ++q ) {
+	uint32_t w = (uint32_t)r->lut_polar[i][q].a | ((uint32_t)r->lut_polar[i][q].r << 16);
+	fwrite(&w, 4, 1, f);
+      }
+    fclose(f);
+    f = out("hs_rect.u16");
+    for ( int a=0; a<256; ++a )
+      for ( int k=0; k<256; ++k ) {
+	uint16_t w = (uint16_t)(r->lut_rect[a][k].re | (r->lut_rect[a][k].im << 8));
+	fwrite(&w, 2, 1, f);
+      }
+    fclose(f);
+    f = out("hs_sincos.u16");
+    for ( int a=0; a<65536; ++a ) {
+      uint16_t w = (uint16_t)(r->lut_sincos[a].re | (r->lut_sincos[a].im << 8));
+      fwrite(&w, 2, 1, f);
+    }
+    fclose(f); }
+
   dump_lowpass("fs2.4_sr2", 2.4e6, 2e6, 0.35, 10);
   dump_lowpass("fs9.6_sr2", 9.6e6, 2e6, 0.35, 10);
   dump_lowpass("fs240_sr2", 240e6, 2e6, 0.35, 10);

@@ -94,6 +94,9 @@ def test_host_tables_match_reference_dumps(product):
     assert _sha(P.host_table(P.default_config(sampler="rrc", Fs=4e6), "rrc")) == g["rrc_fs4_sr2.f32"]["sha256"]
     assert _sha(P.host_table(c, "vitmap")) == g["vitmap_qpsk12.u8"]["sha256"]
     assert _sha(P.host_table(P.default_config(fec="7/8"), "vitmap")) == g["vitmap_qpsk78.u8"]["sha256"]
+    # --hs: fast_qpsk_receiver's three look-up tables (sdr.h:1144-1164)
+    for name, f in (("hs_polar", "hs_polar.u32"), ("hs_rect", "hs_rect.u16"), ("hs_sincos", "hs_sincos.u16")):
+        assert _sha(P.host_table(c, name)) == g[f]["sha256"], name
     # every constellation of cstln_lut<256>::predef (sdr.h:305-311); APSK radii per code rate (dvb.h:45-81)
     for cst, fec, f in (("16APSK", "2/3", "16apsk23"), ("16APSK", "3/4", "16apsk34"), ("16APSK", "5/6", "16apsk56"),
                         ("32APSK", "3/4", "32apsk34"), ("32APSK", "5/6", "32apsk56"), ("64APSKe", "3/4", "64apske"),
