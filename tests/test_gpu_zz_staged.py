@@ -1,0 +1,49 @@
+"""Parity cases written after this round's GPU budget was spent: the oracle side of each is pinned to the reference on
+the CPU (tests/test_oracle_cpu.py, MORE_CASES), the CUDA side has NOT been run on a B200 yet.  They are marked xfail
+(non-strict) so that the first GPU run reports them as XPASS / xfailed instead of masking the verified suite; the
+marker goes away once they have been seen green."""
+import numpy as np
+import pytest
+
+from tests import vectors as V
+from tests.test_gpu_parity import assert_prefix, run_product
+from tests.test_oracle_cpu import _as_format
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="staged: written after the round's GPU budget was spent, not yet run on a B200", strict=False)]
+
+FORMAT_CASES = [
+    ("s16-scale", "s16", dict(fmt="s16", float_scale=0.015625)),
+    ("u16-scale-resample", "u16", dict(fmt="u16", float_scale=0.015625, resample=True)),
+    ("s8-anf0", "s8", dict(fmt="s8", anf=0)),
+]
+
+
+@pytest.mark.parametrize("name,fmt,kw", FORMAT_CASES, ids=[c[0] for c in FORMAT_CASES])
+def test_other_input_formats_every_stream_bit_exact(product, oracle, name, fmt, kw):
+    """cconverter<s16|u16|s8> + scaler (leandvb.cc:204-260) in front of the chain."""
+    P, O = product, oracle
+    raw = _as_format(V.ref_iq(300, fmt="f32"), fmt)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["pp"], ref["pp"], "preprocessed IQ")
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=8)
+    assert_prefix(got["ts"], ref["ts"], "TS")
+    assert len(ref["ts"]) > 200
+
+
+@pytest.mark.parametrize("name,kw,gkw", [
+    ("cr34", dict(fmt="f32", fec="3/4", Fs=4e6), dict(ratio="2", cr="3/4")),
+    ("tune-drift", dict(fmt="f32", Ftune=15000.0, allow_drift=True), {}),
+    ("resample-4.8sps", dict(fmt="f32", resample=True, Fs=9.6e6), dict(ratio="24/5")),
+], ids=lambda v: v if isinstance(v, str) else None)
+def test_more_flag_sets_bit_exact(product, oracle, name, kw, gkw):
+    P, O = product, oracle
+    raw = V.ref_iq(300, fmt="f32", **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["pp"], ref["pp"], "preprocessed IQ")
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=8)
+    assert_prefix(got["ts"], ref["ts"], "TS")
