@@ -141,3 +141,17 @@ def test_known_answers(product):
     assert np.array_equal(got[m, 1], ref[m, 1])
     gexp = np.fromfile(os.path.join(GOLDEN, "rs_exp.u8"), dtype=np.uint8)
     assert np.array_equal(P.host_table(c, "rs_exp")[:511], gexp)
+
+
+def test_qpsk_table_cells_follow_from_arithmetic(product):
+    """Ground for a lighter critical path in k_rx: over ALL 65536 cells of the QPSK table the
+    symbol is the pair of sign bits of the truncated (I, Q) and the cost is sat(d_nearest) - sat(d_second) with
+    d_second = d_nearest + 212 min(abs I, abs Q) -- only phase_error (glibc atan2f) needs a table."""
+    P = product
+    cells = P.host_table(P.default_config(), "cstln").view(np.int16).reshape(256, 256, 4).astype(np.int32)
+    v = np.arange(256).astype(np.uint8).view(np.int8).astype(np.int32)
+    I, Q = v[:, None] * np.ones((1, 256), np.int32), v[None, :] * np.ones((256, 1), np.int32)
+    assert np.array_equal(cells[:, :, 1], ((I < 0).astype(np.int32) << 1) | (Q < 0).astype(np.int32))
+    d1 = (np.abs(I) - 53) ** 2 + (np.abs(Q) - 53) ** 2
+    d2 = d1 + 212 * np.minimum(np.abs(I), np.abs(Q))
+    assert np.array_equal(cells[:, :, 0], np.minimum(d1, 32767) - np.minimum(d2, 32767))
