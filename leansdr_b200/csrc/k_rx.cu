@@ -114,7 +114,7 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
       }
       const float2 sg = cmul(e0, make_float2(acc_re, acc_im));
       r.sg_re = sg.x; r.sg_im = sg.y;
-    } else if (SAMPLER == 1) {
+    } else if (SAMPLER == 1 || SAMPLER == kRxSamplerLinArith) {
       const float2 e1 = expi(p.trig, -fadd(r.phase, r.samp_freqw));
       const float2 s1 = cmul(nxt, e1);
       const float a = fsub(1.0f, r.mu);
@@ -128,11 +128,25 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
     // --- constellation look-up (sdr.h:470-486)
     float I = r.s_re, Q = r.s_im;
     while (I < -128.f || I > 127.f || Q < -128.f || Q > 127.f) { I = fmul(I, 0.5f); Q = fmul(Q, 0.5f); }
-    const uint32_t ci = ((uint32_t)f2i_trunc(I) & 0xffu) * 256u + ((uint32_t)f2i_trunc(Q) & 0xffu);
-    const uint2 cellw = __ldg(reinterpret_cast<const uint2 *>(p.cstln) + ci);
-    const int symbol = (int)(cellw.x >> 16) & 0xff;
-    const int pe = (int)(short)(cellw.y & 0xffffu);
-    word = (cellw.x & 0xffffu) | ((uint32_t)symbol << 16);
+    int symbol, pe;
+    if (SAMPLER == kRxSamplerLinArith) {
+      // QPSK: the cell's symbol and cost follow from the truncated (I, Q); only the phase error is looked up.
+      const int Ii = f2i_trunc(I), Qi = f2i_trunc(Q);
+      const uint32_t ci = ((uint32_t)Ii & 0xffu) * 256u + ((uint32_t)Qi & 0xffu);
+      pe = (int)__ldg(p.pe16 + ci);
+      symbol = ((Ii < 0) ? 2 : 0) | ((Qi < 0) ? 1 : 0);
+      const int aI = abs(Ii), aQ = abs(Qi);
+      const int d1 = (aI - 53) * (aI - 53) + (aQ - 53) * (aQ - 53);
+      const int d2 = d1 + 212 * min(aI, aQ);
+      const int cost = min(d1, 32767) - min(d2, 32767);
+      word = ((uint32_t)cost & 0xffffu) | ((uint32_t)symbol << 16);
+    } else {
+      const uint32_t ci = ((uint32_t)f2i_trunc(I) & 0xffu) * 256u + ((uint32_t)f2i_trunc(Q) & 0xffu);
+      const uint2 cellw = __ldg(reinterpret_cast<const uint2 *>(p.cstln) + ci);
+      symbol = (int)(cellw.x >> 16) & 0xff;
+      pe = (int)(short)(cellw.y & 0xffffu);
+      word = (cellw.x & 0xffffu) | ((uint32_t)symbol << 16);
+    }
     mu_emit = r.mu;
     emitted = true;
     // --- PLL (sdr.h:814-816)
@@ -143,7 +157,8 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
     r.h2pr = r.h1pr; r.h2pi = r.h1pi; r.h2cr = r.h1cr; r.h2ci = r.h1ci;
     r.h1pr = r.h0pr; r.h1pi = r.h0pi; r.h1cr = r.h0cr; r.h1ci = r.h0ci;
     r.h0pr = r.s_re; r.h0pi = r.s_im;
-    r.cp_re = (float)p.sym_re[symbol]; r.cp_im = (float)p.sym_im[symbol];
+    if (SAMPLER == kRxSamplerLinArith) { r.cp_re = (symbol & 2) ? -53.0f : 53.0f; r.cp_im = (symbol & 1) ? -53.0f : 53.0f; }
+    else { r.cp_re = (float)p.sym_re[symbol]; r.cp_im = (float)p.sym_im[symbol]; }
     r.have_point = 1;
     r.h0cr = r.cp_re; r.h0ci = r.cp_im;
     const float t1 = fadd(fmul(fsub(r.h0pr, r.h2pr), r.h1cr), fmul(fsub(r.h0pi, r.h2pi), r.h1ci));
@@ -213,7 +228,7 @@ __device__ __forceinline__ bool rx_sample_hs(const RxParams &p, RxRun &r, float2
 }
 
 __device__ __forceinline__ void rx_chunk_begin(const RxParams &p, RxRun &r, int sampler) {
-  if (sampler == 1) r.samp_freqw = r.freqw;  // linear_sampler::update_freq (sdr.h:620)
+  if (sampler == 1 || sampler == kRxSamplerLinArith) r.samp_freqw = r.freqw;  // linear_sampler::update_freq (sdr.h:620)
   if (sampler == 2) {                        // fir_sampler::update_freq (sdr.h:667-675)
     r.rrc_update_phase -= kRxChunk;
     if (r.rrc_update_phase <= 0) {
@@ -461,6 +476,14 @@ k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
   else rx_warp<2, TILE>(a, span_list, nlist, smem);
 }
 
+// EXPERIMENT (kRxSamplerLinArith, see kernels.h): a kernel of its own, so that k_rx's code is what was measured.
+template <int TILE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_rx_arith(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  rx_warp<kRxSamplerLinArith, TILE>(a, span_list, nlist, smem);
+}
+
 // ---------------------------------------------------------------- seam stitching
 
 // One warp per seam: lanes stride over the logged symbols.
@@ -624,6 +647,19 @@ cudaError_t launch_rx_t(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     if (e != cudaSuccess) return e;
     configured = true;
+  }
+  if (a.p.sampler == kRxSamplerLinArith) {   // EXPERIMENT: same launch geometry, its own kernel
+    static bool configured_arith = false;
+    if (!configured_arith) {
+      cudaError_t e = cudaFuncSetAttribute(k_rx_arith<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+      if (e != cudaSuccess) return e;
+      configured_arith = true;
+    }
+    const unsigned pb = kWarpsPerBlock * 32;
+    const unsigned ln = span_list ? nlist : a.nspans;
+    const size_t sm = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<1, TILE>::kBytes;
+    k_rx_arith<TILE><<<(ln + pb - 1) / pb, pb, sm, st>>>(a, span_list, nlist);
+    return cudaGetLastError();
   }
   const unsigned per_block = kWarpsPerBlock * 32;
   const unsigned lanes = span_list ? nlist : a.nspans;

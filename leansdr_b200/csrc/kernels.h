@@ -139,9 +139,14 @@ struct RxParams {
   // float fields of RxState (phase: u16, freqw and the limits: integers below 2^24, hist: u8) --
   // every value is exactly representable, so carry / warm-up / seam plumbing is shared.
   const uint32_t *hs_polar; const uint16_t *hs_rect; const uint16_t *hs_sincos;
+  const int16_t *pe16;       // kRxSamplerLinArith: phase_error of every cell, same index as cstln
   long long hs_freq_beta;    // (signed long)(0.0012*256*65536/omega*pll_adjustment), sdr.h:1002
 };
 constexpr int kRxSamplerHs = 3;
+// EXPERIMENT (off unless LDVB_RX_ARITH=1; not yet run on a B200): linear sampler + QPSK slicer whose symbol and
+// cost are computed (tests/test_capi_cpu.py::test_qpsk_table_cells_follow_from_arithmetic) and whose phase error
+// comes from a 128 KB int16 table instead of the 512 KB cell table.  Its own kernel: k_rx itself is untouched.
+constexpr int kRxSamplerLinArith = 4;
 
 // dvb_deconvol_sync_hard (dvb.h:612-707): per 64-byte chunk; see k_fec.cu.
 struct HsDeconvArgs {

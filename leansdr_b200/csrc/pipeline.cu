@@ -97,6 +97,7 @@ struct ldvb_handle {
 
   // ---- device tables
   DevBuf d_rrc;
+  DevBuf d_pe16;             // EXPERIMENT LDVB_RX_ARITH: phase_error of every constellation cell
   DevBuf d_cstln, d_trig, d_rot, d_taps, d_gfexp, d_gflog, d_derand, d_rotperm, d_twiddle;
 
   // ---- streams
@@ -520,7 +521,7 @@ int ldvb_destroy(ldvb_handle *h) {
   if (!h) return LDVB_OK;
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
-  DevBuf *bufs[] = {&h->d_rrc, &h->d_cstln, &h->d_trig, &h->d_rot, &h->d_taps, &h->d_gfexp, &h->d_gflog, &h->d_derand,
+  DevBuf *bufs[] = {&h->d_pe16, &h->d_rrc, &h->d_cstln, &h->d_trig, &h->d_rot, &h->d_taps, &h->d_gfexp, &h->d_gflog, &h->d_derand,
                     &h->d_rotperm, &h->d_twiddle, &h->s_raw.buf, &h->s_notched.buf, &h->s_pp.buf, &h->s_sym.buf,
                     &h->s_bytes.buf, &h->s_mpeg.buf, &h->d_rts, &h->d_rsflags, &h->d_ts, &h->d_scratch,
                     &h->d_badwords, &h->d_rs204, &h->d_notch_tables, &h->d_notch_state, &h->d_notch_epochs,
@@ -666,6 +667,18 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   // receivers fed more than 2 samples per symbol -- the heavily decimated wideband case -- run EXACT.
   if (h->cfg.rx_mode == LDVB_RX_FAST && h->Fs_rx / c.Fm > 2.05f) h->cfg.rx_mode = LDVB_RX_EXACT;
   rx_setup(h);
+  {
+    // EXPERIMENT, off by default, not yet run on a B200 (kernels.h, kRxSamplerLinArith): QPSK + linear sampler with
+    // the slicer's symbol / cost computed and the phase error in a 128 KB table.  LDVB_RX_ARITH=1 turns it on.
+    const char *e = getenv("LDVB_RX_ARITH");
+    if (e && atoi(e) == 1 && c.constellation == LDVB_CSTLN_QPSK && !c.hard_metric && c.sampler == LDVB_SAMP_LINEAR && !c.hs) {
+      std::vector<int16_t> pe(h->cst.cells.size());
+      for (size_t i = 0; i < pe.size(); ++i) pe[i] = h->cst.cells[i].phase_error;
+      if (upload(h->d_pe16, pe.data(), pe.size() * 2) != cudaSuccess) return bail(LDVB_ECUDA, "pe16 upload");
+      h->rxp.pe16 = h->d_pe16.as<int16_t>();
+      h->rxp.sampler = kRxSamplerLinArith;
+    }
+  }
   if (c.hs) {
     const HsTables ht = make_hs_tables();
     if (upload(h->d_hs_polar, ht.polar.data(), ht.polar.size() * 4) != cudaSuccess ||
