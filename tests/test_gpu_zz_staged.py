@@ -47,3 +47,18 @@ def test_more_flag_sets_bit_exact(product, oracle, name, kw, gkw):
     assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
     assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=8)
     assert_prefix(got["ts"], ref["ts"], "TS")
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_experimental_arithmetic_qpsk_slicer(product, oracle, mode, monkeypatch):
+    """LDVB_RX_ARITH=1 (kernels.h, kRxSamplerLinArith): symbol and cost computed, phase error from a 128 KB table.
+    Must give the same soft symbols (EXACT) / TS (FAST) as the table path."""
+    P, O = product, oracle
+    monkeypatch.setenv("LDVB_RX_ARITH", "1")
+    kw = dict(fmt="f32", resample=True)
+    raw = V.ref_iq(1200 if mode == "fast" else 300, fmt="f32", noise_db=22)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT if mode == "exact" else P.RX_FAST, **kw)
+    if mode == "exact":
+        assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["ts"], ref["ts"], "TS")
