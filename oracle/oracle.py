@@ -621,6 +621,16 @@ class Chain:
             t["cnr"], _ = Meas(4096, float(bw), 0.1, dec1).run(x, 0.0)
         t["spectrum"], _ = Meas(1024, 0.0, 0.5, dec1).run(x)
         if self.fir:
+            # fir_filter::run (dsp.h:236-244) follows the demodulator's freq_tap when it is further than
+            # freq_tol from the frequency the taps are shifted for (leandvb.cc:505-510).  One-shot schedule:
+            # sampled once, before the batch (the reference samples it at every run() call) -- with --tune
+            # the very first call already retunes.
+            f32 = np.float32
+            freq_tap = f32(self.rx.get_state().view(f32)[20])
+            new_freq = f32(freq_tap * f32(1.0 / self.decim))
+            tol = f32(np.float64(f32(cfg.Fm) / (f32(self.Fs_rx) * f32(self.decim))) * 0.1)
+            if abs(np.float64(f32(0.0) - new_freq)) > tol:
+                self.fir.set_freq(float(new_freq))
             x, _ = self.fir.run(x)
         elif self.decim > 1:
             x, _ = decimate(x, self.decim)

@@ -62,3 +62,17 @@ def test_experimental_arithmetic_qpsk_slicer(product, oracle, mode, monkeypatch)
     if mode == "exact":
         assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
     assert_prefix(got["ts"], ref["ts"], "TS")
+
+
+def test_resample_follows_tune(product, oracle):
+    """fir_filter retune from freq_tap at the start of the batch (dsp.h:236-244): --resample --tune 216000 on a carrier
+    moved by 0.09 cycles per sample; oracle side pinned to the reference in tests/test_oracle_cpu.py."""
+    from tests.test_oracle_cpu import _shift
+    P, O = product, oracle
+    raw = _shift(V.ref_iq(300, fmt="f32"), 0.09)
+    kw = dict(fmt="f32", resample=True, Ftune=216000.0)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["pp"], ref["pp"], "preprocessed IQ")
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["ts"], ref["ts"], "TS")

@@ -215,6 +215,37 @@ def test_oracle_more_flag_sets_equal_reference_taps(oracle, name, fmt, flags, ok
     assert 0 <= len(ts) - len(ts_ref) <= 188
 
 
+def _shift(raw_f32, f_rel):
+    x = raw_f32.reshape(-1, 2).astype(np.float64)
+    z = (x[:, 0] + 1j * x[:, 1]) * np.exp(2j * np.pi * f_rel * np.arange(x.shape[0]))
+    out = np.empty((z.size, 2), np.float32)
+    out[:, 0] = z.real; out[:, 1] = z.imag
+    return out.reshape(-1)
+
+
+@needs_ref
+def test_oracle_resample_follows_tune_like_the_reference(oracle):
+    """fir_filter retunes its taps to the demodulator's freq_tap (dsp.h:236-244, 270-280; leandvb.cc:505-510): with
+    --tune 216 kHz at 2.4 MS/s (0.09 > freq_tol 0.083) the first run() already shifts the low-pass.  Carrier moved by
+    the same 0.09 cycles per sample; preprocessed IQ and soft symbols bit for bit, TS identical."""
+    O = oracle
+    raw = _shift(V.ref_iq(300, fmt="f32"), 0.09)
+    d = tempfile.mkdtemp()
+    ts_ref = subprocess.run([O.ref_bin("ref_tap"), "--f32", "--resample", "--tune", "216000", "--tap-dir", d],
+                            input=raw.tobytes(), stdout=subprocess.PIPE, check=True).stdout
+    t = O.Chain(O.Config(fmt="f32", resample=True, Ftune=216000.0)).run(raw)
+    for key, f in (("pp", "pp.cf32"), ("symbols", "symbols.bin")):
+        a = np.ascontiguousarray(t[key]).reshape(-1).view(np.uint8)
+        b = np.fromfile(os.path.join(d, f), dtype=np.uint8)
+        assert a.size == b.size and np.array_equal(a, b), key
+    ts = t["ts"].tobytes()
+    n = min(len(ts), len(ts_ref))
+    assert n >= 30 * 188 and ts[:n] == ts_ref[:n]
+    # without the retune the filter would sit 216 kHz off the carrier: the streams differ from the first sample
+    t0 = O.Chain(O.Config(fmt="f32", resample=True)).run(raw)
+    assert not np.array_equal(t0["pp"][:1000], t["pp"][:1000])
+
+
 @needs_ref
 def test_oracle_wideband_resample_equals_reference_taps(oracle):
     """BASELINE.json configs[4], reading 5b of SURVEY 8(d): a carrier oversampled 120x (leandvbtx -f 120), decoded with
