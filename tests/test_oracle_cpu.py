@@ -181,6 +181,20 @@ MORE_CASES = [
     # --tune / --drift (sdr.h:745-770, leandvb.cc:483-497), wider low-pass (13 taps at Fs/Fm = 4.8)
     ("search-tune-drift", "f32", ["--tune", "15000", "--drift"], dict(fmt="f32", Ftune=15000.0, allow_drift=True), {}),
     ("f32-resample-4.8sps", "f32", ["--resample", "-f", "9.6e6"], dict(fmt="f32", resample=True, Fs=9.6e6), dict(ratio="24/5")),
+    # filter design knobs, explicit decimation, metric and scale options
+    ("f32-resample-decim2", "f32", ["--resample", "--decim", "2", "-f", "9.6e6"], dict(fmt="f32", resample=True, decim=2, Fs=9.6e6), dict(ratio="24/5")),
+    ("f32-resample-rej20", "f32", ["--resample", "--resample-rej", "20"], dict(fmt="f32", resample=True, resample_rej=20.0), {}),
+    ("f32-resample-rolloff02", "f32", ["--resample", "--roll-off", "0.2"], dict(fmt="f32", resample=True, rolloff=0.2), {}),
+    ("f32-rrc-viterbi", "f32", ["--sampler", "rrc", "--viterbi"], dict(fmt="f32", sampler="rrc", viterbi=True), {}),
+    ("f32-rrc-steps2-rej5", "f32", ["--sampler", "rrc", "--rrc-steps", "2", "--rrc-rej", "5", "-f", "4e6"],
+     dict(fmt="f32", sampler="rrc", rrc_steps=2, rrc_rej=5.0, Fs=4e6), dict(ratio="2")),
+    ("f32-hard-metric", "f32", ["--hard-metric"], dict(fmt="f32", hard_metric=True), {}),
+    ("f32-viterbi-hard-noise", "f32", ["--viterbi", "--hard-metric"], dict(fmt="f32", viterbi=True, hard_metric=True), dict(noise_db=25)),
+    ("f32-float-scale2", "f32", ["--float-scale", "2.0"], dict(fmt="f32", float_scale=2.0), {}),
+    ("f32-drift", "f32", ["--drift"], dict(fmt="f32", allow_drift=True), {}),
+    ("f32-anf3", "f32", ["--anf", "3"], dict(fmt="f32", anf=3), {}),
+    ("search-derot-minus30k", "f32", ["--derotate", "-30000", "--anf", "0"], dict(fmt="f32", Fderot=-30000.0, anf=0), {}),
+    ("search-nearest-1.2sps", "f32", ["--sampler", "nearest"], dict(fmt="f32", sampler="nearest"), {}),
 ]
 
 
