@@ -223,5 +223,10 @@ int main(int argc, char **argv) {
   dump_lowpass("fs240_sr2", 240e6, 2e6, 0.35, 10);
   dump_rrc("fs2.4_sr2", 2.4e6, 2e6, 0.35, 10);
   dump_rrc("fs4_sr2", 4e6, 2e6, 0.35, 10);
+  dump_lowpass("fs9.6_sr2_rej20", 9.6e6, 2e6, 0.35, 20);
+  dump_lowpass("fs2.4_sr2_ro02", 2.4e6, 2e6, 0.2, 10);
+  dump_lowpass("fs55_sr27.5", 55e6, 27.5e6, 0.35, 10);
+  dump_rrc("fs2.4_sr2_ro02", 2.4e6, 2e6, 0.2, 10);
+  dump_rrc("fs8_sr2_rej5", 8e6, 2e6, 0.35, 5);
   return 0;
 }

@@ -94,6 +94,13 @@ def test_host_tables_match_reference_dumps(product):
     assert _sha(P.host_table(P.default_config(sampler="rrc", Fs=4e6), "rrc")) == g["rrc_fs4_sr2.f32"]["sha256"]
     assert _sha(P.host_table(c, "vitmap")) == g["vitmap_qpsk12.u8"]["sha256"]
     assert _sha(P.host_table(P.default_config(fec="7/8"), "vitmap")) == g["vitmap_qpsk78.u8"]["sha256"]
+    # more filter designs (filtergen.h:45-92 through leandvb.cc:353-378, 437-456)
+    for kw, kind, f in ((dict(resample=True, Fs=9.6e6, resample_rej=20.0), "fir", "lowpass_fs9.6_sr2_rej20.f32"),
+                        (dict(resample=True, rolloff=0.2), "fir", "lowpass_fs2.4_sr2_ro02.f32"),
+                        (dict(resample=True, Fs=55e6, Fm=27.5e6), "fir", "lowpass_fs55_sr27.5.f32"),
+                        (dict(sampler="rrc", rolloff=0.2), "rrc", "rrc_fs2.4_sr2_ro02.f32"),
+                        (dict(sampler="rrc", Fs=8e6, rrc_rej=5.0), "rrc", "rrc_fs8_sr2_rej5.f32")):
+        assert _sha(P.host_table(P.default_config(**kw), kind)) == g[f]["sha256"], f
     # --hs: fast_qpsk_receiver's three look-up tables (sdr.h:1144-1164)
     for name, f in (("hs_polar", "hs_polar.u32"), ("hs_rect", "hs_rect.u16"), ("hs_sincos", "hs_sincos.u16")):
         assert _sha(P.host_table(c, name)) == g[f]["sha256"], name
