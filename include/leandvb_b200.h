@@ -196,7 +196,9 @@ enum {
   /* fast_qpsk_receiver::init_lookup_tables (sdr.h:1144-1164), ldvb_host_table only: */
   LDVB_TABLE_HS_POLAR  = 10, /* 65536 x u32: angle | radius << 16, index (u8)re * 256 + (u8)im */
   LDVB_TABLE_HS_RECT   = 11, /* 65536 x u16: re | im << 8, index angle8 * 256 + radius     */
-  LDVB_TABLE_HS_SINCOS = 12  /* 65536 x u16: re | im << 8, index angle16                    */
+  LDVB_TABLE_HS_SINCOS = 12, /* 65536 x u16: re | im << 8, index angle16                    */
+  LDVB_TABLE_FIR_SHIFTED = 13 /* ncoeffs x {re, im} float: the low-pass taps as fir_filter::set_freq shifts them
+                                 for the first batch (dsp.h:236-244, 270-280), ldvb_host_table only */
 };
 
 /* --------------------------------------------------------------- lifecycle */

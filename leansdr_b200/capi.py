@@ -26,7 +26,8 @@ RX_EXACT, RX_FAST = 0, 1
 TAP = {"pp": 0, "symbols": 1, "bytes": 2, "mpegbytes": 3, "rspackets": 4, "rtspackets": 5,
        "rsflags": 6, "sampled": 7, "meas": 8}
 TABLE = {"cstln": 0, "trig16": 1, "rs_exp": 2, "rs_log": 3, "derand": 4, "fir": 5, "rrc": 6,
-         "deconv": 7, "trellis": 8, "vitmap": 9, "hs_polar": 10, "hs_rect": 11, "hs_sincos": 12}
+         "deconv": 7, "trellis": 8, "vitmap": 9, "hs_polar": 10, "hs_rect": 11, "hs_sincos": 12,
+         "fir_shifted": 13}
 
 
 class LdvbError(RuntimeError):

@@ -648,7 +648,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     h->use_fir = true;
     Fs /= d;
     h->fir_tap_mult = 1.0f / d;                     // leandvb.cc:508
-    h->fir_tol = c.Fm / (Fs * d) * 0.1f;            // leandvb.cc:509 (Fs already divided)
+    h->fir_tol = (float)((double)(c.Fm / (Fs * d)) * 0.1);   // leandvb.cc:509 (Fs already divided; 0.1 is a double there)
     h->fir_shifted = shift_taps(h->fir_coeffs, 0);
     h->fir_current_freq = 0;
     if (upload(h->d_taps, h->fir_shifted.data(), h->fir_shifted.size() * 4) != cudaSuccess)
@@ -2600,6 +2600,18 @@ static int host_table(const ldvb_config &c, int which, std::vector<uint8_t> &blo
     case LDVB_TABLE_RS_LOG: { uint8_t e[512], l[256]; make_rs_tables(e, l); put(l, 256); break; }
     case LDVB_TABLE_DERAND: { auto t = make_derand_pattern(); put(t.data(), t.size()); break; }
     case LDVB_TABLE_FIR: put(fir.data(), fir.size() * 4); break;
+    case LDVB_TABLE_FIR_SHIFTED: {
+      // The complex taps in force for the first batch: fir_filter::set_freq (dsp.h:270-280) at the frequency
+      // run() picks up from the demodulator's initial freq_tap (dsp.h:236-244, leandvb.cc:483-486, 505-510).
+      if (!c.resample) return LDVB_EINVAL;
+      const float freqw = c.Ftune ? (c.Ftune / Fs) * 65536 : 0.0f;          // set_freq (sdr.h:745-749)
+      const float freq_tap = freqw / 65536;
+      const float new_freq = freq_tap * (1.0f / decim);
+      const float tol = (float)((double)(c.Fm / (Fs * decim)) * 0.1);
+      const std::vector<float> sh = shift_taps(fir, fabsf(0.0f - new_freq) > tol ? new_freq : 0.0f);
+      put(sh.data(), sh.size() * 4);
+      break;
+    }
     case LDVB_TABLE_DECONV: {
       DeconvPolys d;
       if (!make_deconv(c.fec, &d)) return LDVB_EINVAL;

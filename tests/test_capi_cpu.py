@@ -162,3 +162,20 @@ def test_qpsk_table_cells_follow_from_arithmetic(product):
     d1 = (np.abs(I) - 53) ** 2 + (np.abs(Q) - 53) ** 2
     d2 = d1 + 212 * np.minimum(np.abs(I), np.abs(Q))
     assert np.array_equal(cells[:, :, 0], np.minimum(d1, 32767) - np.minimum(d2, 32767))
+
+
+def test_first_batch_fir_taps_follow_tune(product, oracle):
+    """fir_filter::set_freq at the frequency its first run() picks up from the demodulator (dsp.h:236-244, 270-280):
+    the library's host code against the oracle, whose output with these taps equals the tapped reference
+    (tests/test_oracle_cpu.py::test_oracle_resample_follows_tune_like_the_reference)."""
+    P, O = product, oracle
+    for Ftune, expect_shift in ((216000.0, True), (20000.0, False), (0.0, False)):
+        got = P.host_table(P.default_config(fmt="f32", resample=True, Ftune=Ftune), "fir_shifted").view(np.float32).reshape(-1, 2)
+        ch = O.Chain(O.Config(fmt="f32", resample=True, Ftune=Ftune))
+        f = O.Fir(ch.fir_taps, ch.decim)
+        if expect_shift:
+            f.set_freq(float(np.float32(np.float32(Ftune) / np.float32(2.4e6))))
+        want = f.shifted()
+        assert got.shape == want.shape == (5, 2)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), Ftune
+        assert bool(np.any(got[:, 1] != 0)) == expect_shift
