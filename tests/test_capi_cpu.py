@@ -179,3 +179,49 @@ def test_first_batch_fir_taps_follow_tune(product, oracle):
         assert got.shape == want.shape == (5, 2)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), Ftune
         assert bool(np.any(got[:, 1] != 0)) == expect_shift
+
+
+@pytest.mark.parametrize("fec", ["1/2", "2/3", "4/6", "3/4", "5/6", "7/8"])
+def test_viterbi_rescan_over_distinct_predecessors_selects_the_same_branch(product, fec):
+    """k_viterbi.cu replaces the reference's rescan over ALL labels (viterbi.h:221-234, `<=`: the last label among
+    equal metrics wins) by a scan over the largest label of every distinct predecessor, in increasing label order.
+    Same winner (metric, predecessor, uncoded symbol) for every state, received label and metric vector -- including
+    vectors full of ties -- on all six trellises."""
+    P = product
+    t = P.host_table(P.default_config(fec=fec), "trellis").reshape(64, -1, 2).astype(np.int32)
+    ncs = t.shape[1]
+    pred, us = t[:, :, 0], t[:, :, 1]
+    # the compact lists, built like the kernel does: labels downwards, first sighting of a predecessor, reversed
+    lists = []
+    for s in range(64):
+        seen, l = set(), []
+        for c in range(ncs - 1, -1, -1):
+            p = pred[s, c]
+            if p == 65 or p in seen:
+                continue
+            seen.add(p)
+            l.append((p, us[s, c]))
+        lists.append(l[::-1])
+    nb = len(lists[0])
+    assert all(len(l) == nb for l in lists) and nb == min(64, 1 << int(fec[0]) if fec != "4/6" else 16)
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        cc = rng.integers(0, 3 if trial % 2 else 1000, 64)          # every other trial: metrics full of ties
+        bcost = -int(rng.integers(0, 3 if trial % 2 else 500))
+        cs = int(rng.integers(0, ncs))
+        for s in range(64):
+            # reference order: the received label first (metric + cost), then every existing label ascending, `<=`
+            best = (0x7fffffff, 0, 0)
+            p = pred[s, cs]
+            if p != 65 and cc[p] + bcost <= best[0]:
+                best = (cc[p] + bcost, p, us[s, cs])
+            full = best
+            for c in range(ncs):
+                p = pred[s, c]
+                if p != 65 and cc[p] <= full[0]:
+                    full = (cc[p], p, us[s, c])
+            compact = best
+            for p, u in lists[s]:
+                if cc[p] <= compact[0]:
+                    compact = (cc[p], p, u)
+            assert tuple(int(v) for v in full) == tuple(int(v) for v in compact), (fec, s, cs, trial)
