@@ -76,3 +76,21 @@ def test_resample_follows_tune(product, oracle):
     assert_prefix(got["pp"], ref["pp"], "preprocessed IQ")
     assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
     assert_prefix(got["ts"], ref["ts"], "TS")
+
+
+@pytest.mark.parametrize("name,kw,gkw", [
+    ("vit23as46", dict(fmt="f32", fec="2/3", viterbi=True, Fs=4e6), dict(ratio="2", cr="2/3")),
+    ("vit56-noise", dict(fmt="f32", fec="5/6", viterbi=True, Fs=4e6), dict(ratio="2", cr="5/6", noise_db=18)),
+], ids=lambda v: v if isinstance(v, str) else None)
+def test_viterbi_remaining_trellises(product, oracle, name, kw, gkw):
+    """The 4/6 (QPSK 2/3 runs as 4/6, leandvb.cc:533-537) and 5/6 trellises; oracle side pinned to the reference in
+    tests/test_oracle_cpu.py (f32-vit23as46, f32-vit56-noise), the kernel's rescan lists by
+    tests/test_capi_cpu.py::test_viterbi_rescan_over_distinct_predecessors_selects_the_same_branch."""
+    P, O = product, oracle
+    raw = V.ref_iq(500, fmt="f32", **gkw)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_EXACT, **kw)
+    assert_prefix(got["symbols"], ref["symbols"], "soft symbols")
+    assert_prefix(got["bytes"], ref["bytes"], "Viterbi bytes")
+    assert_prefix(got["ts"], ref["ts"], "TS")
+    assert len(ref["ts"]) > 300
