@@ -32,6 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "IQ MS/s end-to-end leandvb DVB-S QPSK CR1/2; TS bytes bit-exact vs CPU"
+# What bounds each kernel.  The HBM fraction is reported for all of them; for the serial
+# recurrences it says how far the kernel is from being a streaming kernel, not how well it uses the memory system.
+BOUND = {"frontend": "hbm", "notch_guess": "hbm", "front_fused": "hbm", "rx": "latency", "notch_apply": "latency",
+         "viterbi": "latency", "rx_compact": "hbm", "deconv_carry": "hbm"}
 REF_FLAGS = ["--f32", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--standard", "DVB-S", "--resample"]
 
 
@@ -138,6 +142,73 @@ def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int, flags=None):
         os.unlink(path)
     n = raw.size // 2
     return replicas * n / best / 1e6, ts
+
+
+def awgn(raw: np.ndarray, mer_db: float) -> np.ndarray:
+    """The reference's own channel simulator (apps/leanchansim.cc: wgn_c + adder, --deterministic seed) on an f32
+    vector: `leanchansim --if32 --awgn DB --deterministic --of32`, the generator the parity tests use."""
+    from oracle import oracle as O
+    out = subprocess.run([O.ref_bin("leanchansim"), "--if32", "--awgn", str(mer_db), "--deterministic", "--of32"],
+                         input=raw.tobytes(), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    return np.frombuffer(out, dtype=np.float32).copy()
+
+
+def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: int, sample_packets: int):
+    """FAST-mode parity, MEASURED: on a bounded prefix of the bench vector, clean and with the
+    reference's AWGN at 22 dB and 10 dB, the FAST receiver against the EXACT receiver (symbol by symbol: hard decision
+    and soft cost) and both against the unmodified reference binary (TS packets)."""
+    from tests import vectors as V
+    n = min(raw.size // 2, sample_packets * 1958)
+    base = np.ascontiguousarray(raw[: 2 * n])
+    sent = V.ts_packets(sample_packets + 64)
+
+    def run(x, mode):
+        rx = P.Receiver(anf=anf, rx_mode=mode, max_batch=x.size // 2, device=device, keep_taps=1, **rx_kw)
+        rx.push(x)
+        ts = rx.pull_all()
+        sym = rx.tap("symbols").view(np.uint32).copy()
+        m = rx.meas()
+        rx.close()
+        return sym, ts, m
+
+    def ids(ts):
+        """numbered packets -> set of counters of the packets that are bit-correct transmitted packets"""
+        if not len(ts):
+            return set(), 0
+        c = (ts[:, 5].astype(np.int64) << 16) | (ts[:, 6].astype(np.int64) << 8) | ts[:, 7]
+        ok = (c < len(sent))
+        good = ok & (ts == sent[np.minimum(c, len(sent) - 1)]).all(axis=1)
+        return set(c[good].tolist()), int((~good).sum())
+
+    out = {"sample_samples": int(n)}
+    for name, db in (("clean", None), ("awgn22", 22.0), ("awgn10", 10.0)):
+        x = base if db is None else awgn(base, db)
+        se, te, me = run(x, P.RX_EXACT)
+        sf, tf, mf = run(x, P.RX_FAST)
+        tr = np.frombuffer(subprocess.run([_ref_bin("leandvb"), *ref_flags], input=x.tobytes(), stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, check=True).stdout, dtype=np.uint8).reshape(-1, 188)
+        k = min(se.size, sf.size)
+        ie, be = ids(te); i_f, bf = ids(tf); ir, br = ids(tr)
+        kk = min(len(te), len(tr))
+        out[name] = {
+            "symbols": int(k), "symbol_count_diff": int(sf.size) - int(se.size),
+            "hard_symbol_mismatch": int(((se[:k] >> 16) != (sf[:k] >> 16)).sum()),
+            "cost_mismatch": int(((se[:k] & 0xffff) != (sf[:k] & 0xffff)).sum()),
+            "ts_packets": {"reference": int(len(tr)), "exact": int(len(te)), "fast": int(len(tf))},
+            "exact_ts_bit_identical_to_reference_prefix": bool(kk > 0 and np.array_equal(te[:kk], tr[:kk]) and abs(len(te) - len(tr)) <= 1),
+            "ts_packets_differing": {"fast_vs_reference": len(i_f ^ ir), "fast_vs_exact": len(i_f ^ ie), "exact_vs_reference": len(ie ^ ir)},
+            "wrong_packets_delivered": {"reference": br, "exact": be, "fast": bf},
+            "seams": {"total": mf["seams_total"], "repaired": mf["seams_repaired"],
+                      "accepted_with_mismatch": mf["seams_mismatch_accepted"], "settle_passes": mf["settle_passes"],
+                      "max_dphase": mf["seam_max_dphase"], "max_dfreqw": mf["seam_max_dfreqw"], "max_dmu": mf["seam_max_dmu"]},
+            "reference_mer_db": me["mer"],
+        }
+    return out
+
+
+def _ref_bin(name):
+    from oracle import oracle as O
+    return O.ref_bin(name)
 
 
 def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
@@ -252,8 +323,9 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     dom = max(per_step, key=per_step.get)
     ab = alg_bytes.get(dom, nloc * 8)
     ach = ab / (kern[dom] * 1e-3) / 1e9
-    roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roof = {"kernel": dom, "bound": BOUND.get(dom, "hbm"), "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(dom, nloc), "peak_source": peak_kind, "ms_per_launch": kern[dom],
+            "ns_per_sample": kern[dom] * 1e6 / nloc,
             "algorithmic_bytes_per_launch": ab, "share_of_step": per_step[dom] / (ms / a.steps), "rank": 0}
     fir = None
     if "frontend" in kern:
@@ -263,11 +335,10 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {**workload, "samples_per_step_per_gpu": C, "stream_samples_per_step": C * world, "rx_mode": "fast",
-                       "l2": "per-GPU chunk (%d MB) larger than L2, re-read every step" % (C * 8 >> 20),
-                       "parallelism": "ONE stream time-sharded over %d GPUs: chunk k on GPU k; per step and boundary one NCCL "
-                                      "send/recv of %d halo samples (%d KB), 16 B of notch bins and a %d-byte EDGE (carry state); "
-                                      "front stages concurrent, back stages chained" % (world, H, H * 8 >> 10, engine.edge_size)},
+            "config": dict(workload),
+            "run": {"samples_per_step_per_gpu": C, "stream_samples_per_step": C * world, "rx_mode": "fast",
+                    "exchange": "per step and boundary one NCCL send/recv of %d halo samples (%d KB), 16 B of notch bins and a "
+                                "%d-byte EDGE (carry state); front stages concurrent, back stages chained" % (H, H * 8 >> 10, engine.edge_size)},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": int(C * 8 * world),
                     "d2h_bytes_per_step": int(allv[:, 6].sum() * 188), "ms_per_step": e2e_ms / a.steps},
@@ -296,6 +367,9 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--anf", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fast_vs_exact parity measurement")
+    ap.add_argument("--parity-packets", type=int, default=2048, help="packets of the bench vector the fast_vs_exact leg decodes "
+                    "(three noise levels x EXACT + FAST + the reference binary)")
     ap.add_argument("--variant", default="f32", choices=["f32", "u8", "hs", "viterbi", "viterbi78"],
                     help="side measurements (N = 1): 'u8' = the same chain fed complex<u8> IQ (leandvb --u8), 'hs' = leandvb --u8 --hs "
                          "(fast_qpsk_receiver path), 'viterbi' = leandvb --f32 --resample --viterbi (viterbi_sync instead of deconvol_sync).  "
@@ -312,9 +386,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
+    # `config` is the same dictionary in both arms (the driver compares them); what is specific to a run goes to `run`.
     workload = {"workload": "C2: leantsgen|leandvbtx -f 6/5 --power 37.5 --agc -> leandvb --f32 --resample "
                             "-f 2400e3 --sr 2000e3 --cr 1/2 (QPSK, 1.2 samples/symbol, 5-tap FIR, anf=%d)" % a.anf,
-                "packets": a.packets}
+                "packets": a.packets, "variant": a.variant, "shard": a.shard if a.gpus > 1 else "none",
+                "l2": "b200 arm: the per-GPU input batch (packets x 1958 samples x 8 B, 1 GB at the default size) is larger "
+                      "than L2 and re-read every step; reference arm: host CPU",
+                "parallelism": "b200 arm: N = 1 time spans inside one GPU, N > 1 ONE stream time-sharded over N GPUs (chunk k on "
+                               "GPU k; halo, notch bins and EDGE carry state over NCCL send/recv); reference arm: one "
+                               "single-threaded leandvb process per host core (the reference has no threads)"}
 
     ref_flags = list(REF_FLAGS)
     rx_kw = dict(fmt="f32", resample=True)
@@ -343,7 +423,7 @@ def main():
         if rank != 0:
             return
         ncores = os.cpu_count() or 1
-        sample_pk = min(a.packets, 4096)           # bounded sample: ~8 Mi samples per replica
+        sample_pk = min(a.packets, 16384)          # bounded sample: the same 32 M-sample prefix the b200 arm's cpu_baseline leg decodes
         raw = gen_vector(sample_pk)
         n = raw.size // 2
         for _ in range(a.warmup):
@@ -356,7 +436,7 @@ def main():
         line = {"metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {**workload, "sample_packets": sample_pk},
+                "config": dict(workload), "run": {"sample_packets": sample_pk, "samples_per_process_per_step": n},
                 "cpu_baseline": {"value": v, "unit": "MS/s", "cores": ncores, "kind": "reference",
                                  "sample": f"{ncores} concurrent single-threaded leandvb processes (the reference has no "
                                            f"threads), each on the same {n} samples from page cache; one process alone: "
@@ -490,9 +570,9 @@ def main():
         ab = alg_bytes.get(dom, n * 8)
         ach = ab / (kern[dom] * 1e-3) / 1e9
         traffic = ncu_traffic(dom, n) if a.variant == "f32" else None
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        roof = {"kernel": dom, "bound": BOUND.get(dom, "hbm"), "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                "ms_per_launch": kern[dom], "algorithmic_bytes_per_launch": ab,
+                "ms_per_launch": kern[dom], "ns_per_sample": kern[dom] * 1e6 / n, "algorithmic_bytes_per_launch": ab,
                 "share_of_step": per_step[dom] / (ms / a.steps),
                 "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram read + write per launch)" if traffic else None,
                 "dram_frac": (traffic / (kern[dom] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None}
@@ -508,7 +588,8 @@ def main():
         if k in kern and a.variant == "f32":
             tr = ncu_traffic(k, n)
             ab = alg_bytes.get(k, n * 8)
-            roof_all.append({"kernel": k, "ms_per_launch": kern[k], "achieved": ab / (kern[k] * 1e-3) / 1e9,
+            roof_all.append({"kernel": k, "bound": BOUND.get(k, "hbm"), "ms_per_launch": kern[k], "ns_per_sample": kern[k] * 1e6 / n,
+                             "achieved": ab / (kern[k] * 1e-3) / 1e9,
                              "frac": ab / (kern[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": tr,
                              "dram_frac": (tr / (kern[k] * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tr else None})
 
@@ -527,12 +608,18 @@ def main():
                "sample": f"oracle/_ref/leandvb {' '.join(ref_flags)} on the first {sample.size // 2} samples of the same "
                          f"vector (best of 3, file in page cache); host has {os.cpu_count()} cores, the reference uses 1"}
 
+    parity = None
+    if not a.no_cpu and not a.no_parity and a.variant == "f32" and a.mode == "fast":
+        del iq_dev
+        torch.cuda.empty_cache()
+        parity = fast_vs_exact(P, raw, rx_kw, ref_flags, a.anf, local, min(a.packets, a.parity_packets))
+
     line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.variant != "hs" else "int (u8/u16 angles, 64-bit PLL)", "data": "synthetic",
-            "config": {**workload, "samples_per_step_per_gpu": n, "rx_mode": a.mode, "variant": a.variant,
-                       "l2": "input batch (%d MB) larger than L2, re-read every step" % (raw.nbytes >> 20),
-                       "parallelism": "time spans inside one GPU; one independent stream per GPU"},
+            "config": {k: v for k, v in workload.items() if k != "synthesis"},
+            "run": {"samples_per_step_per_gpu": n, "rx_mode": a.mode, "input_bytes_per_step": int(raw.nbytes),
+                    "synthesis": workload.get("synthesis")},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": int(raw.nbytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / a.steps},
@@ -541,6 +628,7 @@ def main():
             "kernel_ms_per_step": per_step, "stage_wall_ms_per_step": wall,
             "cpu_baseline": cpu,
             "ts_packets_per_step": int(npk), "ts_bit_exact_vs_reference": ts_match,
+            "fast_vs_exact": parity,
             "e2e_ts_equals_device_resident_ts": e2e_ts_ok,
             "vector_equals_reference_transmitter_prefix": vector_check,
             "seams": {"total": meas["seams_total"], "repaired": meas["seams_repaired"], "notch_repaired": meas["notch_repaired"],

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LDVB_LIB") or os.path.join(_HERE, "libleandvb_b200.so")   # LDVB_LIB: experiment builds only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FMT = {"u8": 0, "s8": 1, "u16": 2, "s16": 3, "f32": 4}
 FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16, "f32": np.float32}
 CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2, "16APSK": 3, "32APSK": 4, "64APSKe": 5,
@@ -48,6 +48,7 @@ class Config(C.Structure):
         ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
         ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
         ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("hs", C.c_int32), ("vit_segments", C.c_int32), ("vit_warm_chunks", C.c_int32),
+        ("settle_chunks", C.c_int32), ("seam_mode", C.c_int32),
     ]
 
 
@@ -59,6 +60,8 @@ class Meas(C.Structure):
         ("symbols", C.c_uint64), ("seams_total", C.c_uint32), ("seams_repaired", C.c_uint32),
         ("notch_repaired", C.c_uint32), ("kernel_launches", C.c_uint32),
         ("vit_segments", C.c_uint32), ("vit_repaired", C.c_uint32),
+        ("seams_mismatch_accepted", C.c_uint32), ("settle_passes", C.c_uint32),
+        ("seam_max_dphase", C.c_float), ("seam_max_dfreqw", C.c_float), ("seam_max_dmu", C.c_float),
     ]
 
     def asdict(self):

@@ -1,9 +1,24 @@
 // common.cuh -- shared device helpers for the sm_100a DVB-S kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 
 namespace ldvb {
+
+// ---------------------------------------------------------- per-device opt-ins
+// cudaFuncSetAttribute is per device (context): a process may hold handles on several GPUs,
+// possibly on different threads, so "already configured" is remembered per device ordinal.
+// need(v) returns true when this device has not been configured for at least `v` yet (the caller then
+// sets the attribute and calls commit(v)); racing threads at worst set the same attribute twice.
+struct PerDeviceMark {
+  static constexpr int kMaxDev = 64;
+  std::atomic<size_t> mark[kMaxDev];
+  PerDeviceMark() { for (auto &m : mark) m.store(0); }
+  int dev() const { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDev) d = kMaxDev - 1; return d; }
+  bool need(size_t v) const { return mark[dev()].load(std::memory_order_acquire) < v; }
+  void commit(size_t v) { auto &m = mark[dev()]; size_t cur = m.load(); while (cur < v && !m.compare_exchange_weak(cur, v)) {} }
+};
 
 // ----------------------------------------------------------------- arithmetic
 // Every float operation on the bit-exact path goes through the _rn intrinsics:

@@ -219,11 +219,11 @@ cudaError_t launch_frontend(FrontendArgs a, cudaStream_t st) {
   a.max_raw_bytes = (span_max * a.bytes_per_sample + 15u) & ~15u;
   size_t smem = (((size_t)N * 8 + 127) & ~(size_t)127) + (((size_t)a.max_raw_bytes + 127) & ~(size_t)127);
   if (a.fmt < 4) smem += (size_t)span_max * 8;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDeviceMark configured;   // per device: a process may hold handles on several GPUs
+  if (smem > 48 * 1024 && configured.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured.commit(smem);
   }
   const uint64_t tiles = (a.count + tile - 1) / tile;
   k_frontend<<<(unsigned)tiles, kThreads, smem, st>>>(a);

@@ -582,8 +582,8 @@ constexpr size_t kNotchSmem = kNotchSmemIn + (size_t)kNWarps * 32 * kNPitch;   /
 template <int FMT, int NSLOTS>
 cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, uint32_t nlist,
                            const float2 *guess, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceMark configured;   // per device (function attributes belong to the context)
+  if (configured.need(1)) {
     cudaError_t e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kNotchSmem);
     if (e != cudaSuccess) return e;
@@ -594,7 +594,7 @@ cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, ui
       e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
       if (e != cudaSuccess) return e;
     }
-    configured = true;
+    configured.commit(1);
   }
   const unsigned per_block = kNWarps * 32;
   const uint32_t lanes = seg_list ? nlist : a.nsegs;

@@ -40,6 +40,14 @@ namespace {
 // sampler (304 B, up to 6 taps).  Both pitches are 16 B mod 128-friendly: any 8 consecutive
 // lanes read 16 B each from distinct banks.
 template <int SAMPLER, int TILE> struct RowCfg { static constexpr int kBytes = (TILE + (SAMPLER == 2 ? 6 : 2)) * 8; };
+// Slicer variants (template parameter SLICER of rx_sample / rx_warp):
+//   0  cstln_lut<256>::lookup as a gather into the 512 KB cell table in global memory (any constellation);
+//   1  QPSK: symbol and cost follow from the truncated (I, Q) by arithmetic
+//      (tests/test_capi_cpu.py::test_qpsk_table_cells_follow_from_arithmetic checks all 65536 cells of the
+//      host-built table), and the phase error -- glibc atan2f, so it stays a table -- is read from a 128 KB
+//      int16 copy of that column held in SHARED memory: the constellation look-up leaves the L1/L2 path
+//      altogether (round 1, ncu: one lane of every warp-wide gather missed L1, so every symbol waited for L2).
+constexpr int kPe16Bytes = 65536 * 2;
 #ifndef LDVB_RX_CA
 #define LDVB_RX_CA 0
 #endif
@@ -48,7 +56,6 @@ constexpr bool kRxCa = LDVB_RX_CA != 0;
 #define LDVB_RX_STAGES 2
 #endif
 constexpr int kStages = LDVB_RX_STAGES;   // tiles in flight per lane (kStages - 1 ahead of the one in use)
-constexpr int kWarpsPerBlock = 4;
 
 struct RxRun {
   float mu, phase, freqw, est_insp, agc_gain, est_sp, est_ep;
@@ -83,6 +90,13 @@ __device__ __forceinline__ void store_state(RxState &s, const RxRun &r) {
   s.rrc_update_phase = r.rrc_update_phase; s.rrc_f = r.rrc_f;
 }
 
+// Signed 16-bit load from a shared-space byte address (no generic-address conversion on the dependent path).
+__device__ __forceinline__ int lds_s16(uint32_t addr) {
+  short v;
+  asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return (int)v;
+}
+
 // trig16::expi(float) (math.h:104-110): index = (uint16)(int16)(int32)a.
 __device__ __forceinline__ float2 expi(const float2 *__restrict__ trig, float a) {
   return __ldg(trig + ((uint32_t)f2i_trunc(a) & 0xffffu));
@@ -90,9 +104,9 @@ __device__ __forceinline__ float2 expi(const float2 *__restrict__ trig, float a)
 
 // One input sample of cstln_receiver::run()'s inner loop (sdr.h:800-847).
 // cur = pin[0], nxt = pin[1].  Returns true and fills `word` when a symbol is emitted.
-template <int SAMPLER>
+template <int SAMPLER, int SLICER>
 __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cur, float2 nxt,
-                                          const float2 *pin, uint32_t &word, float &mu_emit) {
+                                          const float2 *pin, uint32_t s_pe, uint32_t &word, float &mu_emit) {
   bool emitted = false;
   if (r.mu < 1.0f) {
     // --- sampler (sdr.h:595-597, 609-618, 647-665)
@@ -114,7 +128,7 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
       }
       const float2 sg = cmul(e0, make_float2(acc_re, acc_im));
       r.sg_re = sg.x; r.sg_im = sg.y;
-    } else if (SAMPLER == 1 || SAMPLER == kRxSamplerLinArith) {
+    } else if (SAMPLER == 1) {
       const float2 e1 = expi(p.trig, -fadd(r.phase, r.samp_freqw));
       const float2 s1 = cmul(nxt, e1);
       const float a = fsub(1.0f, r.mu);
@@ -127,13 +141,21 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
     r.s_im = fmul(r.sg_im, r.agc_gain);
     // --- constellation look-up (sdr.h:470-486)
     float I = r.s_re, Q = r.s_im;
-    while (I < -128.f || I > 127.f || Q < -128.f || Q > 127.f) { I = fmul(I, 0.5f); Q = fmul(Q, 0.5f); }
+    // The truncations are issued before the range test resolves (the halving loop is rare): the recurrence
+    // is one long dependent chain, so the test must not sit in front of the conversions.
+    int Ii, Qi;
+    asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(Ii) : "f"(I));   // (volatile: keeps them in front of the test)
+    asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(Qi) : "f"(Q));
+    if (I < -128.f || I > 127.f || Q < -128.f || Q > 127.f) {
+      do { I = fmul(I, 0.5f); Q = fmul(Q, 0.5f); } while (I < -128.f || I > 127.f || Q < -128.f || Q > 127.f);
+      Ii = f2i_trunc(I); Qi = f2i_trunc(Q);
+    }
     int symbol, pe;
-    if (SAMPLER == kRxSamplerLinArith) {
-      // QPSK: the cell's symbol and cost follow from the truncated (I, Q); only the phase error is looked up.
-      const int Ii = f2i_trunc(I), Qi = f2i_trunc(Q);
-      const uint32_t ci = ((uint32_t)Ii & 0xffu) * 256u + ((uint32_t)Qi & 0xffu);
-      pe = (int)__ldg(p.pe16 + ci);
+    if (SLICER == 1) {
+      // QPSK: the cell's symbol and cost follow from the truncated (I, Q); only the phase error is looked up
+      // (shared memory: a 2-byte gather, ~3 bank wavefronts for 32 random lanes).
+      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040);   // (Ii & 0xff) << 8 | (Qi & 0xff)
+      pe = lds_s16(s_pe + 2u * ci);
       symbol = ((Ii < 0) ? 2 : 0) | ((Qi < 0) ? 1 : 0);
       const int aI = abs(Ii), aQ = abs(Qi);
       const int d1 = (aI - 53) * (aI - 53) + (aQ - 53) * (aQ - 53);
@@ -141,7 +163,7 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
       const int cost = min(d1, 32767) - min(d2, 32767);
       word = ((uint32_t)cost & 0xffffu) | ((uint32_t)symbol << 16);
     } else {
-      const uint32_t ci = ((uint32_t)f2i_trunc(I) & 0xffu) * 256u + ((uint32_t)f2i_trunc(Q) & 0xffu);
+      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040);
       const uint2 cellw = __ldg(reinterpret_cast<const uint2 *>(p.cstln) + ci);
       symbol = (int)(cellw.x >> 16) & 0xff;
       pe = (int)(short)(cellw.y & 0xffffu);
@@ -157,7 +179,7 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
     r.h2pr = r.h1pr; r.h2pi = r.h1pi; r.h2cr = r.h1cr; r.h2ci = r.h1ci;
     r.h1pr = r.h0pr; r.h1pi = r.h0pi; r.h1cr = r.h0cr; r.h1ci = r.h0ci;
     r.h0pr = r.s_re; r.h0pi = r.s_im;
-    if (SAMPLER == kRxSamplerLinArith) { r.cp_re = (symbol & 2) ? -53.0f : 53.0f; r.cp_im = (symbol & 1) ? -53.0f : 53.0f; }
+    if (SLICER == 1) { r.cp_re = (symbol & 2) ? -53.0f : 53.0f; r.cp_im = (symbol & 1) ? -53.0f : 53.0f; }
     else { r.cp_re = (float)p.sym_re[symbol]; r.cp_im = (float)p.sym_im[symbol]; }
     r.have_point = 1;
     r.h0cr = r.cp_re; r.h0ci = r.cp_im;
@@ -228,7 +250,7 @@ __device__ __forceinline__ bool rx_sample_hs(const RxParams &p, RxRun &r, float2
 }
 
 __device__ __forceinline__ void rx_chunk_begin(const RxParams &p, RxRun &r, int sampler) {
-  if (sampler == 1 || sampler == kRxSamplerLinArith) r.samp_freqw = r.freqw;  // linear_sampler::update_freq (sdr.h:620)
+  if (sampler == 1) r.samp_freqw = r.freqw;  // linear_sampler::update_freq (sdr.h:620)
   if (sampler == 2) {                        // fir_sampler::update_freq (sdr.h:667-675)
     r.rrc_update_phase -= kRxChunk;
     if (r.rrc_update_phase <= 0) {
@@ -281,14 +303,129 @@ __device__ __forceinline__ void rx_chunk_end(const RxParams &p, RxRun &r) {
   r.freq_tap = __fdiv_rn(r.freqw, 65536.0f);  // sdr.h:917-919
 }
 
-template <int SAMPLER, int TILE>
-__device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_all) {
+// Where the symbols of a lane go.  All counters are per lane.
+struct RxEmit {
+  uint32_t *out;            // the span's region of sym_out
+  RxSeamSym *hlog, *tlog;   // seam logs of the span (or null)
+  uint32_t n_out, n_tail, n_head, cap;
+};
+
+// What a lane does with the symbols of the chunk it is walking.
+//   kWarm   warm-up in front of the span: loops run, nothing is kept
+//   kOwned  owned chunk: symbols are appended to the span's output
+//   kHead   first owned chunk(s): as kOwned + (time, hard symbol) into the head log
+//   kTail   verification overlap behind the span: symbols stored after the owned ones + tail log
+enum { kWarm = 0, kOwned = 1, kHead = 2, kTail = 3 };
+
+// One staged tile (TILE samples + look-ahead, at `rp`) of one lane.  MODE is a template parameter so that the
+// per-symbol bookkeeping of the three output flavours is not evaluated symbol by symbol (the recurrence is
+// latency bound: every predicate in its way costs issue slots of the only instruction stream the lane has).
+template <int SAMPLER, int SLICER, int TILE, int MODE>
+__device__ __forceinline__ void rx_tile(const RxParams &p, RxRun &r, const float4 *rp, uint32_t s_pe, RxEmit &e,
+                                        float t0 /* time of the tile's first sample relative to the seam */) {
+  float4 w = rp[0];
+  float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
+#pragma unroll
+  for (int n = 0; n < TILE; ++n) {
+    float2 nxt2;
+    if ((n & 1) == 0) { w = rp[(n >> 1) + 1]; nxt2 = make_float2(w.x, w.y); }
+    else nxt2 = make_float2(w.z, w.w);
+    uint32_t word; float mu_e;
+    bool em;
+    if (SAMPLER == kRxSamplerHs) em = rx_sample_hs(p, r, cur, nxt, word, mu_e);
+    else em = rx_sample<SAMPLER, SLICER>(p, r, cur, nxt, reinterpret_cast<const float2 *>(rp) + n, s_pe, word, mu_e);
+    if (MODE != kWarm && em) {
+      if (MODE == kOwned || MODE == kHead) {
+        if (e.n_out < e.cap) e.out[e.n_out] = word;
+        ++e.n_out;
+        if (MODE == kHead && e.hlog && e.n_head < kRxSeamLog) {
+          e.hlog[e.n_head].t = t0 + (float)n + mu_e;
+          e.hlog[e.n_head].sym = word >> 16;
+          ++e.n_head;
+        }
+      } else {
+        // Verification overlap: stored right after the owned symbols so that the
+        // stitcher can extend this span by one symbol when needed.
+        if (e.n_out + e.n_tail < e.cap) e.out[e.n_out + e.n_tail] = word;
+        if (e.tlog && e.n_tail < kRxSeamLog) {
+          e.tlog[e.n_tail].t = t0 + (float)n + mu_e;
+          e.tlog[e.n_tail].sym = word >> 16;
+        }
+        ++e.n_tail;
+      }
+    }
+    cur = nxt; nxt = nxt2;
+  }
+}
+
+// End of a chunk: AGC / estimators / limits, measurement rows, end-of-span state.
+template <int SAMPLER>
+__device__ __forceinline__ void rx_chunk_close(const RxArgs &a, RxRun &r, uint64_t c, bool owned, uint32_t span,
+                                               uint64_t own_end) {
+  const RxParams &p = a.p;
+  if (a.sampled && owned) {
+    a.sampled_flag[c] = r.have_point ? 1u : 0u;
+    if (r.have_point) a.sampled[c] = make_float2(r.s_re, r.s_im);
+  }
+  if (SAMPLER == kRxSamplerHs) rx_chunk_end_hs(p, r); else rx_chunk_end(p, r);
+  // Measurements (sdr.h:904-913)
+  r.meas_count += kRxChunk;
+  while (r.meas_count >= p.meas_decimation) {
+    r.meas_count -= p.meas_decimation;
+    if (a.meas && owned) {
+      const uint32_t k = atomicAdd(a.meas_count, 1u);
+      if (k < a.max_meas) {
+        float *m = a.meas + 4 * (size_t)k;
+        m[0] = (float)c;
+        m[1] = r.freq_tap;
+        m[2] = __fsqrt_rn(r.est_insp);
+        // est_sp / est_ep (or -1 when est_ep == 0): the host turns it into dB with glibc's
+        // logf, like the reference (sdr.h:910-911), so that p_mer is bit-identical.
+        m[3] = (r.est_ep != 0.0f) ? __fdiv_rn(r.est_sp, r.est_ep) : -1.0f;
+      }
+    }
+  }
+  if (c + 1 == own_end) store_state(a.state_end[span], r);
+}
+
+// Start state of a span that is warmed up: the carried loop state (frequency, AGC) with the timing / phase
+// registers cleared; counters that are pure functions of the position are set for `run_begin`.
+template <int SAMPLER>
+__device__ __forceinline__ void rx_warm_state(const RxArgs &a, RxRun &r, uint64_t run_begin) {
+  const RxParams &p = a.p;
+  load_state(r, *a.warm_in);
+  r.mu = 0.f; r.phase = 0.f;
+  r.h0pr = r.h0pi = r.h0cr = r.h0ci = 0.f;
+  r.h1pr = r.h1pi = r.h1cr = r.h1ci = 0.f;
+  r.h2pr = r.h2pi = r.h2cr = r.h2ci = 0.f;
+  // Position counters: state_in is valid at chunk a.state_chunk (0 unless a settling pass ran in front).
+  const int64_t rel = (int64_t)run_begin - (int64_t)a.state_chunk;
+  const int64_t dec = (int64_t)p.meas_decimation;
+  int64_t mc = ((int64_t)a.state_in->meas_count + (rel % dec) * kRxChunk) % dec;
+  if (mc < 0) mc += dec;
+  r.meas_count = (uint32_t)mc;
+  if (SAMPLER == 2) {
+    // The tap-update throttle is a pure function of the position: first update at
+    // chunk i0, then every ceil(n*16/128) chunks.
+    const int R = p.rrc_n * 16, P = (R + kRxChunk - 1) / kRxChunk;
+    const int p0 = a.state_in->rrc_update_phase;
+    const int64_t i0 = (p0 <= kRxChunk) ? 0 : (p0 + kRxChunk - 1) / kRxChunk - 1;
+    const int64_t rb = rel > 0 ? rel : 0;
+    if (rb <= i0) r.rrc_update_phase = p0 - kRxChunk * (int)rb;
+    else r.rrc_update_phase = R - kRxChunk * (int)((rb - i0 - 1) % P);
+    r.rrc_f = __fdiv_rn(r.freqw, (float)p.rrc_sub);
+  }
+}
+
+template <int SAMPLER, int SLICER, int TILE>
+__device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, unsigned char *smem_rows,
+                        uint32_t s_pe) {
   constexpr int kTile = TILE;
   constexpr int kTilesPerChunk = kRxChunk / kTile;
   constexpr int kRowBytes = RowCfg<SAMPLER, TILE>::kBytes;
   const RxParams &p = a.p;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t warp_global = blockIdx.x * nwarps + warp;
   // Span of this lane.  Repair mode (span_list): lane g re-runs span span_list[g] exactly,
   // from the end state of its predecessor (a.state_end[span - 1]).
   const bool repair = (span_list != nullptr);
@@ -300,11 +437,12 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   const RxState *forced = nullptr;
   if (repair && have_span) forced = span ? a.state_end + (span - 1) : a.prev_end;
 
-  const uint64_t S = a.span_chunks, W = a.warm_chunks;
+  const uint32_t S = a.span_chunks, W = a.warm_chunks;
   uint64_t own_begin = 0, own_end = 0, run_begin = 0, run_end = 0;
   RxRun r;
   load_state(r, *a.state_in);
   r.sg_re = r.sg_im = r.s_re = r.s_im = r.cp_re = r.cp_im = 0.f; r.have_point = 0;
+  bool log_head_span = false;
   if (have_span) {
     own_begin = a.chunk0 + (uint64_t)span * S;
     own_end = own_begin + S;
@@ -317,54 +455,44 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     if (forced) {
       load_state(r, *forced);
       run_begin = own_begin;
-    } else if (run_begin > 0 || !a.first_exact) {
-      // Warm-up: the carried loop state (frequency, AGC) with the timing / phase registers cleared.
-      load_state(r, *a.warm_in);
-      r.mu = 0.f; r.phase = 0.f;
-      r.h0pr = r.h0pi = r.h0cr = r.h0ci = 0.f;
-      r.h1pr = r.h1pi = r.h1cr = r.h1ci = 0.f;
-      r.h2pr = r.h2pi = r.h2cr = r.h2ci = 0.f;
-      r.meas_count = (uint32_t)(((uint64_t)a.state_in->meas_count + run_begin * (uint64_t)kRxChunk) % p.meas_decimation);
-      if (SAMPLER == 2) {
-        // The tap-update throttle is a pure function of the position: first update at
-        // chunk i0, then every ceil(n*16/128) chunks.
-        const int R = p.rrc_n * 16, P = (R + kRxChunk - 1) / kRxChunk;
-        const int p0 = a.state_in->rrc_update_phase;
-        const int64_t i0 = (p0 <= kRxChunk) ? 0 : (p0 + kRxChunk - 1) / kRxChunk - 1;
-        if ((int64_t)run_begin <= i0) r.rrc_update_phase = p0 - kRxChunk * (int)run_begin;
-        else r.rrc_update_phase = R - kRxChunk * (int)(((int64_t)run_begin - i0 - 1) % P);
-        r.rrc_f = __fdiv_rn(r.freqw, (float)p.rrc_sub);
-      }
+    } else if (span == 0 && a.first_exact) {
+      run_begin = own_begin;                 // the true state at chunk0 (batch start, or end of the settling pass)
+    } else {
+      rx_warm_state<SAMPLER>(a, r, run_begin);
     }
-    // run_begin == 0: the true state at the start of the batch (exact).
+    log_head_span = a.head_log && (span > 0 || !a.first_exact);
   }
   // Common iteration space of the warp: local chunk index i, chunk c = base + i.
   // Lanes outside [run_begin, run_end) idle but keep the barrier protocol.
   int64_t base;          // chunk index of local iteration 0 for this lane
-  uint64_t iters;
+  uint32_t iters;
   if (repair) { base = (int64_t)run_begin; iters = S + kRxVerifyChunks; }
   else { base = (int64_t)(a.chunk0 + (uint64_t)span * S) - (int64_t)W; iters = W + S + kRxVerifyChunks; }
+  // Local chunk indices (relative to base): [lb, le) is run, [ob, oe) is owned.
+  const int lb = (int)((int64_t)run_begin - base), le = have_span ? (int)((int64_t)run_end - base) : lb;
+  const int ob = (int)((int64_t)own_begin - base), oe = (int)((int64_t)own_end - base);
 
   // This lane's private row in each stage (shared-memory window of the warp).
-  const uint32_t row_off = (uint32_t)((threadIdx.x >> 5) * kStages * 32 * kRowBytes + lane * kRowBytes);
-  const uint64_t total_tiles = iters * kTilesPerChunk;
+  unsigned char *warp_rows = smem_rows + (size_t)warp * kStages * 32 * kRowBytes;
+  const uint32_t total_tiles = iters * kTilesPerChunk;
   constexpr int kChunks16 = kRowBytes / 16;
   // Rows are fetched by the WARP: the 32 x kChunks16 16-byte pieces of a tile are dealt to the lanes
-  // in row-major order, so one LDGSTS covers 32 / kChunks16 (~3.5) consecutive rows -- a few whole
+  // in row-major order, so one LDGSTS covers 32 / kChunks16 consecutive rows -- a few whole
   // 128-byte lines -- instead of 32 different lines (the per-lane version kept the L1 -> crossbar
   // request path 45 % busy, ncu round 1).  Row addresses travel by shuffle.
-  auto issue = [&](uint64_t tile) {
+  const float2 *lane_x = a.x + base * (int64_t)kRxChunk;     // sample 0 of local chunk 0 (never dereferenced outside [lb, le))
+  auto issue = [&](uint32_t tile) {
     const int st = (int)(tile % kStages);
-    const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
-    const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
+    const int i = (int)(tile / kTilesPerChunk);
+    const bool active = i >= lb && i < le;
     const unsigned act = __ballot_sync(0xffffffffu, active);
     if (act) {
-      const uintptr_t src = active ? reinterpret_cast<uintptr_t>(a.x + (uint64_t)c * kRxChunk + (tile % kTilesPerChunk) * kTile) : 0;
+      const uintptr_t src = reinterpret_cast<uintptr_t>(lane_x + (size_t)tile * kTile);
       const uint32_t slo = (uint32_t)src, shi = (uint32_t)(src >> 32);
-      unsigned char *stage_base = smem_all + (size_t)(threadIdx.x >> 5) * kStages * 32 * kRowBytes + (size_t)st * 32 * kRowBytes;
+      unsigned char *stage_base = warp_rows + (size_t)st * 32 * kRowBytes;
 #pragma unroll
-      for (int i = 0; i < kChunks16; ++i) {
-        const int piece = i * 32 + lane, row = piece / kChunks16, q = piece % kChunks16;
+      for (int k = 0; k < kChunks16; ++k) {
+        const int piece = k * 32 + lane, row = piece / kChunks16, q = piece % kChunks16;
         const uint32_t lo = __shfl_sync(0xffffffffu, slo, row), hi = __shfl_sync(0xffffffffu, shi, row);
         if ((act >> row) & 1u) {
           const unsigned char *rs = reinterpret_cast<const unsigned char *>(((uintptr_t)hi << 32) | lo);
@@ -376,121 +504,148 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     cp_async_commit();
   };
 
-  uint32_t *out = a.sym_out + (size_t)span * a.span_cap;
-  RxSeamSym *hlog = (a.head_log && have_span) ? a.head_log + (size_t)span * kRxSeamLog : nullptr;
-  RxSeamSym *tlog = (a.tail_log && have_span) ? a.tail_log + (size_t)span * kRxSeamLog : nullptr;
-  uint32_t n_out = 0, n_tail = 0, n_head = 0;
-  const uint32_t cap = a.span_cap;
+  RxEmit e;
+  e.out = a.sym_out + (size_t)span * a.span_cap;
+  e.hlog = (log_head_span && have_span) ? a.head_log + (size_t)span * kRxSeamLog : nullptr;
+  e.tlog = (a.tail_log && have_span) ? a.tail_log + (size_t)span * kRxSeamLog : nullptr;
+  e.n_out = e.n_tail = e.n_head = 0;
+  e.cap = a.span_cap;
 
-  for (int s = 0; s < kStages - 1; ++s) { if ((uint64_t)s < total_tiles) issue(s); else cp_async_commit(); }
-  for (uint64_t tile = 0; tile < total_tiles; ++tile) {
+  for (int s = 0; s < kStages - 1; ++s) { if ((uint32_t)s < total_tiles) issue(s); else cp_async_commit(); }
+  for (uint32_t tile = 0; tile < total_tiles; ++tile) {
     if (tile + kStages - 1 < total_tiles) issue(tile + kStages - 1); else cp_async_commit();
     cp_async_wait<kStages - 1>();
     __syncwarp();                           // rows were copied by other lanes
     const int st = (int)(tile % kStages);
-    const int64_t c = base + (int64_t)(tile / kTilesPerChunk);
+    const int i = (int)(tile / kTilesPerChunk);
     const int tic = (int)(tile % kTilesPerChunk);
-    const bool active = have_span && c >= (int64_t)run_begin && c < (int64_t)run_end;
-    if (active) {
-      const int phase_of_run = ((uint64_t)c < own_begin) ? 0 : ((uint64_t)c < own_end ? 1 : 2);
-      if (tic == 0) rx_chunk_begin(p, r, SAMPLER);
-      const float4 *rp = reinterpret_cast<const float4 *>(smem_all + row_off + (size_t)st * 32 * kRowBytes);
-      float4 w = rp[0];
-      float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
-      const float t_head = (float)(((int64_t)c - (int64_t)own_begin) * kRxChunk + tic * kTile);
-      const float t_tail = (float)(((int64_t)c - (int64_t)own_end) * kRxChunk + tic * kTile);
-      const bool log_head = hlog && (span > 0 || !a.first_exact) && phase_of_run == 1 && ((uint64_t)c - own_begin) < kRxVerifyChunks;
-#pragma unroll 2
-      for (int n = 0; n < kTile; ++n) {
-        float2 nxt2;
-        if ((n & 1) == 0) { w = rp[(n >> 1) + 1]; nxt2 = make_float2(w.x, w.y); }
-        else nxt2 = make_float2(w.z, w.w);
-        uint32_t word; float mu_e;
-        bool em;
-        if (SAMPLER == kRxSamplerHs) em = rx_sample_hs(p, r, cur, nxt, word, mu_e);
-        else em = rx_sample<SAMPLER>(p, r, cur, nxt, reinterpret_cast<const float2 *>(rp) + n, word, mu_e);
-        if (em) {
-          if (phase_of_run == 1) {
-            if (n_out < cap) out[n_out] = word;
-            ++n_out;
-            if (log_head && n_head < kRxSeamLog) {
-              hlog[n_head].t = t_head + (float)n + mu_e;
-              hlog[n_head].sym = word >> 16;
-              ++n_head;
-            }
-          } else if (phase_of_run == 2) {
-            // Verification overlap: stored right after the owned symbols so that the
-            // stitcher can extend this span by one symbol when needed.
-            if (n_out + n_tail < cap) out[n_out + n_tail] = word;
-            if (tlog && n_tail < kRxSeamLog) {
-              tlog[n_tail].t = t_tail + (float)n + mu_e;
-              tlog[n_tail].sym = word >> 16;
-            }
-            ++n_tail;
-          }
-        }
-        cur = nxt; nxt = nxt2;
+    if (i >= lb && i < le) {
+      const int mode = (i < ob) ? kWarm : (i < oe ? ((e.hlog && i - ob < kRxVerifyChunks) ? kHead : kOwned) : kTail);
+      if (tic == 0) {
+        if (i == ob && a.state_begin) store_state(a.state_begin[span], r);   // state the span enters its own chunks with
+        rx_chunk_begin(p, r, SAMPLER);
       }
-      if (tic == kTilesPerChunk - 1) {
-        if (a.sampled && phase_of_run == 1) {
-          a.sampled_flag[c] = r.have_point ? 1u : 0u;
-          if (r.have_point) a.sampled[c] = make_float2(r.s_re, r.s_im);
-        }
-        if (SAMPLER == kRxSamplerHs) rx_chunk_end_hs(p, r); else rx_chunk_end(p, r);
-        // Measurements (sdr.h:904-913)
-        r.meas_count += kRxChunk;
-        while (r.meas_count >= p.meas_decimation) {
-          r.meas_count -= p.meas_decimation;
-          if (a.meas && phase_of_run == 1) {
-            const uint32_t k = atomicAdd(a.meas_count, 1u);
-            if (k < a.max_meas) {
-              float *m = a.meas + 4 * (size_t)k;
-              m[0] = (float)c;
-              m[1] = r.freq_tap;
-              m[2] = __fsqrt_rn(r.est_insp);
-              // est_sp / est_ep (or -1 when est_ep == 0): the host turns it into dB with glibc's
-              // logf, like the reference (sdr.h:910-911), so that p_mer is bit-identical.
-              m[3] = (r.est_ep != 0.0f) ? __fdiv_rn(r.est_sp, r.est_ep) : -1.0f;
-            }
-          }
-        }
-        if ((uint64_t)c + 1 == own_end) store_state(a.state_end[span], r);
+      const float4 *rp = reinterpret_cast<const float4 *>(warp_rows + (size_t)st * 32 * kRowBytes + (size_t)lane * kRowBytes);
+      switch (mode) {                        // warp-uniform except at the ends of the stream
+        case kWarm: rx_tile<SAMPLER, SLICER, TILE, kWarm>(p, r, rp, s_pe, e, 0.f); break;
+        case kOwned: rx_tile<SAMPLER, SLICER, TILE, kOwned>(p, r, rp, s_pe, e, 0.f); break;
+        case kHead: rx_tile<SAMPLER, SLICER, TILE, kHead>(p, r, rp, s_pe, e, (float)((i - ob) * kRxChunk + tic * kTile)); break;
+        default: rx_tile<SAMPLER, SLICER, TILE, kTail>(p, r, rp, s_pe, e, (float)((i - oe) * kRxChunk + tic * kTile)); break;
       }
+      if (tic == kTilesPerChunk - 1)
+        rx_chunk_close<SAMPLER>(a, r, (uint64_t)(base + i), mode == kOwned || mode == kHead, span, own_end);
     }
     __syncwarp();  // every lane is done with this stage before it is refilled
   }
   if (have_span) {
     RxSpanInfo inf;
-    inf.n_out = n_out; inf.n_tail = n_tail; inf.n_head_logged = n_head; inf.pad = 0;
+    inf.n_out = e.n_out; inf.n_tail = e.n_tail; inf.n_head_logged = e.n_head; inf.pad = 0;
     a.info[span] = inf;
   }
 }
 
-template <int TILE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  if (a.p.sampler == 0) rx_warp<0, TILE>(a, span_list, nlist, smem);
-  else if (a.p.sampler == 1) rx_warp<1, TILE>(a, span_list, nlist, smem);
-  else if (a.p.sampler == kRxSamplerHs) rx_warp<kRxSamplerHs, TILE>(a, span_list, nlist, smem);
-  else rx_warp<2, TILE>(a, span_list, nlist, smem);
+// The 128 KB phase-error column into shared memory (SLICER 1), by the whole CTA.
+__device__ __forceinline__ void load_pe16(int16_t *s_pe, const int16_t *g_pe) {
+  const int4 *src = reinterpret_cast<const int4 *>(g_pe);
+  int4 *dst = reinterpret_cast<int4 *>(s_pe);
+  for (int i = threadIdx.x; i < kPe16Bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
 }
 
-// EXPERIMENT (kRxSamplerLinArith, see kernels.h): a kernel of its own, so that k_rx's code is what was measured.
-template <int TILE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_rx_arith(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
+template <int TILE, int SLICER>
+__global__ void __launch_bounds__(SLICER ? 640 : 128)
+k_rx(RxArgs a, const uint32_t *span_list, uint32_t nlist) {
   extern __shared__ __align__(128) unsigned char smem[];
-  rx_warp<kRxSamplerLinArith, TILE>(a, span_list, nlist, smem);
+  uint32_t s_pe = 0;                         // shared-space byte address of the phase-error column
+  unsigned char *rows = smem;
+  if (SLICER == 1) {
+    load_pe16(reinterpret_cast<int16_t *>(smem), a.p.pe16);
+    s_pe = smem_u32(smem);
+    rows = smem + kPe16Bytes;
+  }
+  if (a.p.sampler == 0) rx_warp<0, SLICER, TILE>(a, span_list, nlist, rows, s_pe);
+  else if (a.p.sampler == 1) rx_warp<1, SLICER, TILE>(a, span_list, nlist, rows, s_pe);
+  else if (SLICER == 0 && a.p.sampler == kRxSamplerHs) rx_warp<kRxSamplerHs, 0, TILE>(a, span_list, nlist, rows, s_pe);
+  else rx_warp<2, SLICER, TILE>(a, span_list, nlist, rows, s_pe);
+}
+
+// ------------------------------------------------------------------ the serial lane
+// EXACT mode, the AGC settling pass of FAST mode and every other single-span run: ONE lane walks the chunks in
+// the reference's order; the other 31 lanes of its warp only move data (whole chunks, 16 bytes per lane and
+// copy, double buffered), so the recurrence never waits for memory and owns every issue slot of its scheduler.
+constexpr int kSerialChunkBytes = (kRxChunk + 8) * 8;   // one chunk + look-ahead (<= 6 samples), 16-byte multiple
+
+template <int SAMPLER, int SLICER>
+__device__ void rx_serial(const RxArgs &a, unsigned char *bufs, uint32_t s_pe) {
+  constexpr int TILE = 8;
+  constexpr int kTilesPerChunk = kRxChunk / TILE;
+  const RxParams &p = a.p;
+  const int lane = threadIdx.x & 31;
+  const uint64_t c0 = a.chunk0, c1 = a.nchunks;
+  RxRun r;
+  load_state(r, *a.state_in);
+  r.sg_re = r.sg_im = r.s_re = r.s_im = r.cp_re = r.cp_im = 0.f; r.have_point = 0;
+  if (!a.first_exact) rx_warm_state<SAMPLER>(a, r, c0);
+  RxEmit e;
+  e.out = a.sym_out; e.hlog = nullptr; e.tlog = nullptr;
+  e.n_out = e.n_tail = e.n_head = 0; e.cap = a.span_cap;
+  constexpr int kPieces = (kRxChunk + (SAMPLER == 2 ? 6 : 2)) * 8 / 16;
+  auto issue = [&](uint64_t c) {
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + c * kRxChunk);
+    unsigned char *dst = bufs + (size_t)(c & 1) * kSerialChunkBytes;
+    for (int q = lane; q < kPieces; q += 32) cp_async16(dst + q * 16, src + q * 16);
+    cp_async_commit();
+  };
+  if (c0 < c1) issue(c0);
+  for (uint64_t c = c0; c < c1; ++c) {
+    if (c + 1 < c1) issue(c + 1); else cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    if (lane == 0) {
+      if (c == c0 && a.state_begin) store_state(a.state_begin[0], r);
+      rx_chunk_begin(p, r, SAMPLER);
+      const unsigned char *row = bufs + (size_t)(c & 1) * kSerialChunkBytes;
+#pragma unroll 1
+      for (int tic = 0; tic < kTilesPerChunk; ++tic)
+        rx_tile<SAMPLER, SLICER, TILE, kOwned>(p, r, reinterpret_cast<const float4 *>(row + tic * TILE * 8), s_pe, e, 0.f);
+      rx_chunk_close<SAMPLER>(a, r, c, true, 0, c1);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    RxSpanInfo inf;
+    inf.n_out = e.n_out; inf.n_tail = 0; inf.n_head_logged = 0; inf.pad = 0;
+    a.info[0] = inf;
+  }
+}
+
+template <int SLICER>
+__global__ void __launch_bounds__(128)
+k_rx_serial(RxArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t s_pe = 0;
+  unsigned char *bufs = smem;
+  if (SLICER == 1) {
+    load_pe16(reinterpret_cast<int16_t *>(smem), a.p.pe16);
+    s_pe = smem_u32(smem);
+    bufs = smem + kPe16Bytes;
+  }
+  if (threadIdx.x >= 32) return;             // warps 1..3 only helped to load the table
+  if (a.p.sampler == 0) rx_serial<0, SLICER>(a, bufs, s_pe);
+  else if (a.p.sampler == 1) rx_serial<1, SLICER>(a, bufs, s_pe);
+  else if (SLICER == 0 && a.p.sampler == kRxSamplerHs) rx_serial<kRxSamplerHs, 0>(a, bufs, s_pe);
+  else rx_serial<2, SLICER>(a, bufs, s_pe);
 }
 
 // ---------------------------------------------------------------- seam stitching
 
-// One warp per seam: lanes stride over the logged symbols.
+// One warp per seam: lanes stride over the logged symbols.  sb / se: state of the later span entering its own
+// chunks and end state of the earlier span (or null).
 __device__ RxSeam stitch_seam(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t nt, const RxSeamSym *head,
-                              uint32_t nh, int lane) {
+                              uint32_t nh, const RxState *sb, const RxState *se, int lane) {
   RxSeam s;
-  s.ok = 0; s.rot = 0; s.extend_prev = 0; s.skip_next = 0; s.compared = 0; s.mismatches = 0;
+  s.ok = 0; s.rot = 0; s.extend_prev = 0; s.skip_next = 0; s.compared = 0; s.mismatches = 0; s.ok_loose = 0;
+  s.dphase = 0.f; s.dfreqw = 0.f; s.dmu = 0.f;
   if (nt >= 8 && nh >= 8) {
     // Align on symbol time: tail[it0 + i] <-> head[ih0 + i].
     const float half = 0.5f * a.omega;
@@ -515,10 +670,24 @@ __device__ RxSeam stitch_seam(const RxStitchArgs &a, const RxSeamSym *tail, uint
     }
     time_ok = __all_sync(0xffffffffu, time_ok);
     s.rot = best_rot; s.compared = n; s.mismatches = best_mis;
-    // Isolated disagreements are noise-level decision flips between two converged
-    // loops (either span may be the one that differs from the serial reference);
-    // an unconverged or rotated span disagrees on half or more of the symbols.
-    s.ok = (time_ok && n >= 8 && best_mis * 16 <= n) ? 1 : 0;
+    // Tolerant rule: isolated disagreements are noise-level decision flips between two converged
+    // loops (either span may be the one that differs from the serial reference); an unconverged or
+    // rotated span disagrees on half or more of the symbols.
+    s.ok_loose = (time_ok && n >= 8 && best_mis * 16 <= n) ? 1 : 0;
+    bool state_ok = true;
+    if (sb && se) {
+      // Loop states on both sides: the later span's phase is in its own frame (rot * 65536/nrot away).
+      const float sector = 65536.0f / (float)a.nrot;
+      float dp = fmodf(sb->phase - se->phase - (float)best_rot * sector, sector);
+      if (dp > 0.5f * sector) dp -= sector;
+      if (dp < -0.5f * sector) dp += sector;
+      s.dphase = dp;
+      s.dfreqw = sb->freqw - se->freqw;
+      s.dmu = sb->mu - se->mu - (float)(s.extend_prev - s.skip_next) * a.omega;
+      if (a.tol_phase > 0.f && fabsf(dp) > a.tol_phase) state_ok = false;
+      if (a.tol_freqw > 0.f && fabsf(s.dfreqw) > a.tol_freqw) state_ok = false;
+    }
+    s.ok = a.strict ? (s.ok_loose && best_mis == 0 && state_ok) : s.ok_loose;
   }
   return s;
 }
@@ -529,15 +698,18 @@ k_rx_stitch(RxStitchArgs a, const uint32_t *seam_list, uint32_t nlist) {
   uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (seam_list) { if (j >= nlist) return; j = seam_list[j]; }
   if (j + 1 >= a.nspans) return;
+  const bool st = a.state_begin && a.state_end;
   const RxSeam s = stitch_seam(a, a.tail_log + (size_t)j * kRxSeamLog, min(a.info[j].n_tail, (uint32_t)kRxSeamLog),
                                a.head_log + (size_t)(j + 1) * kRxSeamLog,
-                               min(a.info[j + 1].n_head_logged, (uint32_t)kRxSeamLog), lane);
+                               min(a.info[j + 1].n_head_logged, (uint32_t)kRxSeamLog),
+                               st ? a.state_begin + (j + 1) : nullptr, st ? a.state_end + j : nullptr, lane);
   if (lane == 0) a.seams[j] = s;
 }
 
-__global__ void k_rx_stitch_pair(RxStitchArgs a, const RxSeamSym *tail, uint32_t n_tail, RxSeam *out) {
+__global__ void k_rx_stitch_pair(RxStitchArgs a, const RxSeamSym *tail, uint32_t n_tail, const RxState *prev_end, RxSeam *out) {
   const RxSeam s = stitch_seam(a, tail, min(n_tail, (uint32_t)kRxSeamLog), a.head_log,
-                               min(a.info[0].n_head_logged, (uint32_t)kRxSeamLog), threadIdx.x & 31);
+                               min(a.info[0].n_head_logged, (uint32_t)kRxSeamLog),
+                               (a.state_begin && prev_end) ? a.state_begin : nullptr, prev_end, threadIdx.x & 31);
   if (threadIdx.x == 0) *out = s;
 }
 
@@ -569,9 +741,9 @@ k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t
   __shared__ int s_rot[32];
   __shared__ unsigned long long carry_sum;
   __shared__ int carry_rot;
-  __shared__ unsigned int nfail, overflow;
+  __shared__ unsigned int nfail, overflow, nmis, mx_phase, mx_freqw, mx_mu, nfail_loose;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { carry_sum = 0; carry_rot = 0; nfail = 0; overflow = 0; }
+  if (tid == 0) { carry_sum = 0; carry_rot = 0; nfail = 0; overflow = 0; nmis = 0; mx_phase = 0; mx_freqw = 0; mx_mu = 0; nfail_loose = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < nspans; base += 1024) {
     const uint32_t j = base + tid;
@@ -583,6 +755,13 @@ k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t
       if (j > 0) {
         const RxSeam sm = seams[j - 1];
         if (!sm.ok) atomicAdd(&nfail, 1u);
+        else if (sm.mismatches) atomicAdd(&nmis, 1u);
+        if (!sm.ok_loose) atomicAdd(&nfail_loose, 1u);
+        if (sm.ok) {   // (non-negative floats order like their bit patterns)
+          atomicMax(&mx_phase, __float_as_uint(fabsf(sm.dphase)));
+          atomicMax(&mx_freqw, __float_as_uint(fabsf(sm.dfreqw)));
+          atomicMax(&mx_mu, __float_as_uint(fabsf(sm.dmu)));
+        }
         skip = (uint32_t)sm.skip_next; rot = sm.rot;
       } else {
         skip = skip0; rot = rot0;   // seam in front of span 0 (previous rank), 0 otherwise
@@ -625,63 +804,106 @@ k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t
   if (tid == 0) {
     span_offset[0] = 0;
     result[0] = nfail; result[1] = carry_sum; result[2] = (uint64_t)carry_rot; result[3] = overflow;
+    result[4] = nmis; result[5] = mx_phase; result[6] = mx_freqw; result[7] = mx_mu; result[8] = nfail_loose;
   }
 }
 
 
+// Mean |x|^2 of the first n samples.
+__global__ void __launch_bounds__(256)
+k_rx_power(const float2 *x, uint32_t n, float *out) {
+  __shared__ float part[8];
+  float acc = 0.f;
+  for (uint32_t i = threadIdx.x; i < n; i += 256) { const float2 v = x[i]; acc += v.x * v.x + v.y * v.y; }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *out = n ? t / (float)n : 0.f;
+  }
+}
+
 }  // namespace
 
-namespace {
-template <int TILE>
-cudaError_t launch_rx_t(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, int carveout, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    constexpr size_t smem_max = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<2, TILE>::kBytes;
-    cudaError_t e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-    if (e != cudaSuccess) return e;
-    // Leave most of the SM's unified cache to L1: the two 512 KB tables are read through it,
-    // and their hot lines (current carrier phase, constellation clusters) must stay resident --
-    // table latency is what bounds this kernel.  Measured (round 1): 8-sample tiles (20 KB of rows
-    // per CTA, 3 CTAs per SM) with a 30-40 % shared-memory carve-out beat 16-sample tiles at 50 %
-    // by 4 %; every split that gives L1 less than half is 30-130 % slower.
-    e = cudaFuncSetAttribute(k_rx<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  if (a.p.sampler == kRxSamplerLinArith) {   // EXPERIMENT: same launch geometry, its own kernel
-    static bool configured_arith = false;
-    if (!configured_arith) {
-      cudaError_t e = cudaFuncSetAttribute(k_rx_arith<TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-      if (e != cudaSuccess) return e;
-      configured_arith = true;
-    }
-    const unsigned pb = kWarpsPerBlock * 32;
-    const unsigned ln = span_list ? nlist : a.nspans;
-    const size_t sm = (size_t)kWarpsPerBlock * kStages * 32 * RowCfg<1, TILE>::kBytes;
-    k_rx_arith<TILE><<<(ln + pb - 1) / pb, pb, sm, st>>>(a, span_list, nlist);
-    return cudaGetLastError();
-  }
-  const unsigned per_block = kWarpsPerBlock * 32;
-  const unsigned lanes = span_list ? nlist : a.nspans;
-  const size_t smem = (size_t)kWarpsPerBlock * kStages * 32 *
-                      (a.p.sampler == 2 ? RowCfg<2, TILE>::kBytes : RowCfg<1, TILE>::kBytes);
-  k_rx<TILE><<<(lanes + per_block - 1) / per_block, per_block, smem, st>>>(a, span_list, nlist);
+cudaError_t launch_rx_power(const float2 *x, uint32_t n, float *out, cudaStream_t st) {
+  k_rx_power<<<1, 256, 0, st>>>(x, n, out);
   return cudaGetLastError();
 }
+
+namespace {
+constexpr int kTile = 8;   // samples per staged tile (16 was measured 4 % slower in round 1)
+
+int env_int(const char *name, int dflt, int lo, int hi) {
+  const char *e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return (v < lo || v > hi) ? dflt : v;
+}
+
+size_t rx_row_bytes(int sampler) { return sampler == 2 ? RowCfg<2, kTile>::kBytes : RowCfg<1, kTile>::kBytes; }
 }  // namespace
 
-// Tuning knobs (read once): LDVB_RX_TILE = 8 | 16 samples per staged tile,
-// LDVB_RX_CARVEOUT = shared-memory share of the unified cache in percent.
-int rx_tile_config() {
-  static int tile = [] { const char *e = getenv("LDVB_RX_TILE"); int t = e ? atoi(e) : 8; return t == 16 ? 16 : 8; }();
-  return tile;
+// Warps per CTA of the span kernel.  Slicer 1 (QPSK, phase-error column in shared memory): one fat CTA per SM,
+// LDVB_RX_WARPS warps (default 16: 128 KB of table + 80 KB of rows); slicer 0: 4 warps, three CTAs per SM.
+int rx_warps_per_cta(int slicer) {
+  static const int w1 = env_int("LDVB_RX_WARPS", 16, 1, 20);
+  return slicer == 1 ? w1 : 4;
+}
+
+// Lanes (spans) of one full wave of the span kernel on the current device.
+uint64_t rx_resident_lanes(int slicer) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (uint64_t)sms * (slicer == 1 ? rx_warps_per_cta(1) : 12) * 32;
 }
 
 cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st) {
   if (a.nspans == 0 || (span_list && !nlist)) return cudaSuccess;
-  static int carveout = [] { const char *e = getenv("LDVB_RX_CARVEOUT"); int c = e ? atoi(e) : 35; return (c < 0 || c > 100) ? 35 : c; }();
-  if (rx_tile_config() == 8) return launch_rx_t<8>(a, span_list, nlist, carveout, st);
-  return launch_rx_t<16>(a, span_list, nlist, carveout, st);
+  const int slicer = a.p.slicer;
+  if (slicer == 1 && !a.p.pe16) return cudaErrorInvalidValue;
+  // One span, no warm-up: the serial lane (EXACT mode, settling pass).
+  if (!span_list && a.nspans == 1 && a.warm_chunks == 0 && !a.head_log && !a.tail_log) {
+    const size_t smem = (slicer == 1 ? (size_t)kPe16Bytes : 0) + 2 * (size_t)kSerialChunkBytes;
+    static PerDeviceMark configured;
+    if (slicer == 1 && configured.need(1)) {
+      cudaError_t e = cudaFuncSetAttribute(k_rx_serial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured.commit(1);
+    }
+    if (slicer == 1) k_rx_serial<1><<<1, 128, smem, st>>>(a);
+    else k_rx_serial<0><<<1, 32, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+  const int warps = rx_warps_per_cta(slicer);
+  const unsigned per_block = (unsigned)warps * 32;
+  const unsigned lanes = span_list ? nlist : a.nspans;
+  const size_t rows = (size_t)warps * kStages * 32 * rx_row_bytes(a.p.sampler);
+  if (slicer == 1) {
+    const size_t smem = (size_t)kPe16Bytes + rows;
+    static PerDeviceMark configured;
+    if (configured.need(smem)) {
+      cudaError_t e = cudaFuncSetAttribute(k_rx<kTile, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured.commit(smem);
+    }
+    k_rx<kTile, 1><<<(lanes + per_block - 1) / per_block, per_block, smem, st>>>(a, span_list, nlist);
+    return cudaGetLastError();
+  }
+  static PerDeviceMark configured0;
+  if (configured0.need(1)) {
+    // Leave most of the SM's unified cache to L1: the two 512 KB tables are read through it,
+    // and their hot lines (current carrier phase, constellation clusters) must stay resident.
+    // Measured (round 1): 8-sample tiles (20 KB of rows per CTA, 3 CTAs per SM) with a 30-40 %
+    // shared-memory carve-out; every split that gives L1 less than half is 30-130 % slower.
+    static const int carveout = env_int("LDVB_RX_CARVEOUT", 35, 0, 100);
+    cudaError_t e = cudaFuncSetAttribute(k_rx<kTile, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    if (e != cudaSuccess) return e;
+    configured0.commit(1);
+  }
+  k_rx<kTile, 0><<<(lanes + per_block - 1) / per_block, per_block, rows, st>>>(a, span_list, nlist);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st) {
@@ -691,9 +913,9 @@ cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, u
   return cudaGetLastError();
 }
 
-cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, RxSeam *out,
-                                  cudaStream_t st) {
-  k_rx_stitch_pair<<<1, 32, 0, st>>>(a, tail, n_tail, out);
+cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, const RxState *prev_end,
+                                  RxSeam *out, cudaStream_t st) {
+  k_rx_stitch_pair<<<1, 32, 0, st>>>(a, tail, n_tail, prev_end, out);
   return cudaGetLastError();
 }
 

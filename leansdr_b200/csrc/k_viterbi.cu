@@ -368,11 +368,11 @@ static size_t vit_smem_bytes(int ncs, int nb, int nsyncs) {
 }
 
 static cudaError_t vit_configure(size_t smem) {
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDeviceMark configured;   // per device (function attributes belong to the context)
+  if (smem > 48 * 1024 && configured.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(k_viterbi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    configured.commit(smem);
   }
   return cudaSuccess;
 }

@@ -139,14 +139,11 @@ struct RxParams {
   // float fields of RxState (phase: u16, freqw and the limits: integers below 2^24, hist: u8) --
   // every value is exactly representable, so carry / warm-up / seam plumbing is shared.
   const uint32_t *hs_polar; const uint16_t *hs_rect; const uint16_t *hs_sincos;
-  const int16_t *pe16;       // kRxSamplerLinArith: phase_error of every cell, same index as cstln
+  const int16_t *pe16;       // slicer 1: phase_error of every cell, same index as cstln (copied to shared memory)
+  int slicer;                // 0: cell table gather (any constellation); 1: QPSK arithmetic + pe16 (k_rx.cu)
   long long hs_freq_beta;    // (signed long)(0.0012*256*65536/omega*pll_adjustment), sdr.h:1002
 };
 constexpr int kRxSamplerHs = 3;
-// EXPERIMENT (off unless LDVB_RX_ARITH=1; not yet run on a B200): linear sampler + QPSK slicer whose symbol and
-// cost are computed (tests/test_capi_cpu.py::test_qpsk_table_cells_follow_from_arithmetic) and whose phase error
-// comes from a 128 KB int16 table instead of the 512 KB cell table.  Its own kernel: k_rx itself is untouched.
-constexpr int kRxSamplerLinArith = 4;
 
 // dvb_deconvol_sync_hard (dvb.h:612-707): per 64-byte chunk; see k_fec.cu.
 struct HsDeconvArgs {
@@ -191,17 +188,19 @@ struct RxArgs {
   uint64_t nchunks;          // end of the owned chunks (spans cover [chunk0, nchunks))
   uint64_t avail_chunks;     // chunks present in x (>= nchunks; == nchunks outside time-sharded mode)
   uint64_t chunk0;           // first owned chunk (time-sharded mode: chunks before it are halo)
-  int first_exact;           // span 0 starts from the exact carried state (state_in)
+  int first_exact;           // span 0 starts at chunk0 from the exact carried state (state_in), without warm-up
   const RxState *prev_end;   // repair mode: end state of the span before span 0 (previous rank), or null
   uint32_t span_chunks;      // owned chunks per span (exact mode: >= nchunks)
   uint32_t warm_chunks;      // warm-up chunks (0 in exact mode)
   uint32_t nspans;
   uint32_t span_cap;         // symbol capacity of one span's output region
-  const RxState *state_in;   // exact/carried state at chunk 0
+  const RxState *state_in;   // exact/carried state at chunk `state_chunk` (span 0 starts from it when first_exact)
+  uint64_t state_chunk;      // chunk at which state_in's position counters (meas_count, rrc phase) are valid
   const RxState *warm_in;    // loop state (freqw, AGC) that warm-ups start from; usually == state_in
   uint32_t *sym_out;         // [nspans][span_cap] softsymbols {cost:16, symbol:8, 0}
   RxSpanInfo *info;          // [nspans]
   RxState *state_end;        // [nspans] state at the span's nominal end
+  RxState *state_begin;      // optional [nspans]: state with which the span enters its own chunks (after the warm-up)
   RxSeamSym *head_log;       // [nspans][kRxSeamLog]
   RxSeamSym *tail_log;       // [nspans][kRxSeamLog]
   float2 *sampled;           // optional [nchunks] tap (exact mode), may be null
@@ -213,14 +212,19 @@ struct RxArgs {
 // span_list == nullptr: all spans.  Otherwise the listed spans are re-run exactly from the end
 // state of their predecessors (a.state_end[span - 1]) -- seam repair.
 cudaError_t launch_rx(const RxArgs &a, const uint32_t *span_list, uint32_t nlist, cudaStream_t st);
+int rx_warps_per_cta(int slicer);
+uint64_t rx_resident_lanes(int slicer);   // lanes (spans) of one full wave of the span kernel on the current device
 
 struct RxSeam {
-  int32_t ok;              // verification passed
+  int32_t ok;              // verification passed (rule in force: strict or tolerant, see RxStitchArgs)
   int32_t rot;             // rotation of span j+1 relative to span j (units of 360/nrot)
   int32_t extend_prev;     // span j keeps this many tail symbols (0/1)
   int32_t skip_next;       // span j+1 drops this many head symbols (0/1)
   int32_t compared;        // symbols compared
-  int32_t mismatches;
+  int32_t mismatches;      // hard decisions that differ in the overlap (after de-rotation)
+  int32_t ok_loose;        // the tolerant rule alone: aligned in time and <= 1/16 mismatches
+  float dphase, dfreqw, dmu;  // state of span j+1 entering its chunks minus end state of span j (phase modulo the
+                              // rotational ambiguity, phase units / freqw units / samples); 0 when not recorded
 };
 struct RxStitchArgs {
   const RxSpanInfo *info; const RxSeamSym *head_log; const RxSeamSym *tail_log;
@@ -228,15 +232,22 @@ struct RxStitchArgs {
   const uint8_t *rot_perm;   // [nrot][nsymbols] device
   float omega;
   RxSeam *seams;             // [nspans-1]
+  // strict: a seam verifies only when EVERY compared hard decision agrees (and the loop states agree within the
+  // tolerances below); otherwise the tolerant rule (<= 1/16 mismatches) decides.
+  int strict;
+  const RxState *state_begin, *state_end;   // [nspans] or null: loop states on both sides of each seam
+  float tol_phase, tol_freqw;               // |dphase|, |dfreqw| bounds for `ok` (0: not checked)
 };
 cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, uint32_t nlist, cudaStream_t st);
 // One seam between an imported tail log (previous rank) and span 0's head log.
-cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, RxSeam *out,
-                                  cudaStream_t st);
+cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, const RxState *prev_end,
+                                  RxSeam *out, cudaStream_t st);
 
 // One-CTA scan over the seams: offsets / skips / cumulative rotations of every span.
 // result[0] = seams that failed verification, [1] = symbols kept, [2] = rotation of the
-// last span, [3] = spans that overflowed their capacity.
+// last span, [3] = spans that overflowed their capacity, [4] = verified seams with at least one
+// mismatching hard decision (tolerant rule), [5..7] = max |dphase|, |dfreqw|, |dmu| over the seams (float bits),
+// [8] = seams that fail the tolerant rule too (spans that did not converge).
 cudaError_t launch_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
                            int rot0, uint32_t skip0, uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot,
                            uint64_t *result, cudaStream_t st);
@@ -252,6 +263,9 @@ struct RxCompactArgs {
   uint32_t *sym_out;             // appended after the carried symbols
 };
 cudaError_t launch_rx_compact(const RxCompactArgs &a, uint64_t total, cudaStream_t st);
+
+// Mean |x|^2 of the first n samples (one CTA): the level check in front of the FAST spans.
+cudaError_t launch_rx_power(const float2 *x, uint32_t n, float *out, cudaStream_t st);
 
 // -------------------------------------------------------------- K4 deconvolution
 struct DeconvArgs {

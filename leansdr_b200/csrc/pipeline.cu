@@ -63,7 +63,6 @@ struct Stream {
 struct HypState { uint64_t reg = 0, acc = 0; int n_in = 0, n_out = 0; };
 
 constexpr int kMeasGroup = 256;                 // cnr/spectrum measurements per launch
-constexpr uint64_t kRxTargetSpans = 56 * 1024;  // ~ resident lanes of k_rx on 148 SMs
 
 struct Tap {
   DevBuf buf;
@@ -97,7 +96,7 @@ struct ldvb_handle {
 
   // ---- device tables
   DevBuf d_rrc;
-  DevBuf d_pe16;             // EXPERIMENT LDVB_RX_ARITH: phase_error of every constellation cell
+  DevBuf d_pe16;             // slicer 1 (QPSK): phase_error column of the constellation table
   DevBuf d_cstln, d_trig, d_rot, d_taps, d_gfexp, d_gflog, d_derand, d_rotperm, d_twiddle;
 
   // ---- streams
@@ -119,8 +118,9 @@ struct ldvb_handle {
   uint32_t rot_index = 0;
   RxState rx_state;            // host mirror of the exact/carried receiver state
   DevBuf d_rx_state, d_rx_info, d_rx_end, d_rx_head, d_rx_tail, d_rx_seams, d_rx_spans;
-  DevBuf d_rx_off, d_rx_skip, d_rx_rot, d_rx_meas, d_rx_measn, d_rx_forced;
+  DevBuf d_rx_off, d_rx_skip, d_rx_rot, d_rx_meas, d_rx_measn, d_rx_forced, d_rx_begin, d_rx_power, d_rx_settled;
   uint32_t rx_max_spans = 1;
+  uint64_t rx_target_spans = 0;   // lanes of one full wave of k_rx (set at the first FAST launch)
   double rx_sym_per_sample = 1;
   HypState hyp[4];
   HypState hyp2[4];          // --fastlock: auxiliary registers in2/n_in2/n_out2 (dvb.h:303-306)
@@ -175,6 +175,7 @@ struct ldvb_handle {
     // geometry (absolute units unless noted)
     uint64_t R0 = 0, base_chunk = 0, own_begin = 0, own_end = 0, avail_end = 0, notch_b0 = 0;
     bool first = false;
+    uint64_t settle_syms = 0;             // symbols the first chunk's settling pass put at the front of s_sym
     RxArgs a; RxStitchArgs sa; NotchApplyArgs na;
     const float2 *pp = nullptr;
   } shard;
@@ -515,6 +516,8 @@ void ldvb_config_default(ldvb_config *c) {
   c->device = 0;
   c->max_batch = 1u << 22;
   c->spectrum = 1;   // leandvb.cc:333-343: always instantiated
+  c->settle_chunks = 0;   // auto (512)
+  c->seam_mode = 0;       // strict seams
 }
 
 int ldvb_destroy(ldvb_handle *h) {
@@ -528,7 +531,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
-                    &h->d_rx_forced, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_vit_entry, &h->d_vit_exit, &h->d_vit_aux, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
+                    &h->d_rx_forced, &h->d_rx_begin, &h->d_rx_power, &h->d_rx_settled, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_vit_entry, &h->d_vit_exit, &h->d_vit_aux, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
                     &h->d_edge_tail, &h->d_edge_state, &h->d_edge_seam, &h->d_hs_polar, &h->d_hs_rect, &h->d_hs_sincos, &h->d_hs_errors, &h->d_hs_lock, &h->d_hs_state,
                     &h->m_cnr.d_avg, &h->m_cnr.d_have, &h->m_spec.d_avg, &h->m_spec.d_have, &h->d_meas_carry[0], &h->d_meas_carry[1],
                     &h->d_meas_points, &h->d_meas_power, &h->d_meas_sums, &h->d_meas_rows};
@@ -659,24 +662,19 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     Fs /= h->decim;
   }
   h->Fs_rx = Fs;
-  // FAST is validated at 1.2 and 2 samples per symbol with input near the nominal amplitude.  The first GPU run of
-  // the wideband configuration (4 samples per symbol after the decimation) produced no TS in FAST mode (EXACT:
-  // every stream bit-exact).  Cause, found on the oracle: that waveform reaches the receiver with RMS 6 instead of
-  // ~70, the AGC needs a few hundred chunks to pull the gain from 1 to 11, and FAST spans all restart from the
-  // batch-entry AGC state, so it never gets there.  Until FAST has a settling pass,
-  // receivers fed more than 2 samples per symbol -- the heavily decimated wideband case -- run EXACT.
-  if (h->cfg.rx_mode == LDVB_RX_FAST && h->Fs_rx / c.Fm > 2.05f) h->cfg.rx_mode = LDVB_RX_EXACT;
   rx_setup(h);
   {
-    // EXPERIMENT, off by default, not yet run on a B200 (kernels.h, kRxSamplerLinArith): QPSK + linear sampler with
-    // the slicer's symbol / cost computed and the phase error in a 128 KB table.  LDVB_RX_ARITH=1 turns it on.
-    const char *e = getenv("LDVB_RX_ARITH");
-    if (e && atoi(e) == 1 && c.constellation == LDVB_CSTLN_QPSK && !c.hard_metric && c.sampler == LDVB_SAMP_LINEAR && !c.hs) {
+    // QPSK with the soft metric (the headline configuration): the slicer's symbol and cost are computed and the
+    // phase error comes from a 128 KB int16 column that k_rx keeps in shared memory (kernels.h: slicer 1).
+    // LDVB_RX_SLICER=0 forces the cell-table gather (A/B measurements); other constellations always use it.
+    const char *e = getenv("LDVB_RX_SLICER");
+    const bool want = !(e && atoi(e) == 0);
+    if (want && c.constellation == LDVB_CSTLN_QPSK && !c.hard_metric && !c.hs) {
       std::vector<int16_t> pe(h->cst.cells.size());
       for (size_t i = 0; i < pe.size(); ++i) pe[i] = h->cst.cells[i].phase_error;
       if (upload(h->d_pe16, pe.data(), pe.size() * 2) != cudaSuccess) return bail(LDVB_ECUDA, "pe16 upload");
       h->rxp.pe16 = h->d_pe16.as<int16_t>();
-      h->rxp.sampler = kRxSamplerLinArith;
+      h->rxp.slicer = 1;
     }
   }
   if (c.hs) {
@@ -742,8 +740,10 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
       h->d_rx_off.alloc(8 * ((size_t)nsp + 1)) == cudaSuccess && h->d_rx_skip.alloc(4 * (size_t)nsp) == cudaSuccess &&
       h->d_rx_rot.alloc(nsp) == cudaSuccess && h->d_rx_meas.alloc(16 * 4096) == cudaSuccess &&
       h->d_rx_measn.alloc(4) == cudaSuccess && h->d_rx_forced.alloc(sizeof(RxState)) == cudaSuccess &&
+      h->d_rx_begin.alloc(sizeof(RxState) * nsp) == cudaSuccess && h->d_rx_power.alloc(16) == cudaSuccess &&
+      h->d_rx_settled.alloc(sizeof(RxState) + sizeof(RxSpanInfo) + 64) == cudaSuccess &&
       h->d_deconv_carry.alloc(256) == cudaSuccess && h->d_sync_state.alloc(sizeof(SyncState)) == cudaSuccess &&
-      h->d_sync_res.alloc(sizeof(SyncResult)) == cudaSuccess && h->d_counts.alloc(64) == cudaSuccess;
+      h->d_sync_res.alloc(sizeof(SyncResult)) == cudaSuccess && h->d_counts.alloc(128) == cudaSuccess;
   if (!aok) return bail(LDVB_ENOMEM, "device allocation failed");
   // cnr_fft / spectrum (leandvb.cc:322-343)
   {
@@ -1084,7 +1084,9 @@ int rx_fast_launch(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, uint64_t nchunks
     // least 4 chunks; 4 chunks of warm-up (timing and carrier loops re-converge
     // within ~200 symbols when freqw and the AGC are carried).
     uint32_t S = c.span_chunks;
-    static const uint64_t target = [] { const char *e = getenv("LDVB_RX_SPANS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : kRxTargetSpans; }();
+    static const uint64_t target_env = [] { const char *e = getenv("LDVB_RX_SPANS"); return e ? strtoull(e, nullptr, 10) : 0ull; }();
+    if (!h->rx_target_spans) h->rx_target_spans = rx_resident_lanes(h->rxp.slicer);   // one full wave of k_rx on this device
+    const uint64_t target = target_env ? target_env : h->rx_target_spans;
     if (!S) S = (uint32_t)std::max<uint64_t>(4, (nchunks + target - 1) / target);
     const uint32_t W = c.warmup_chunks ? c.warmup_chunks : 4;
     a.span_chunks = S;
@@ -1096,11 +1098,20 @@ int rx_fast_launch(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, uint64_t nchunks
     a.sym_out = h->d_rx_spans.as<uint32_t>();
     a.head_log = h->d_rx_head.as<RxSeamSym>();
     a.tail_log = h->d_rx_tail.as<RxSeamSym>();
+    a.state_begin = h->d_rx_begin.as<RxState>();
     KL("rx", launch_rx(a, nullptr, 0, h->st));
+    memset(&sa, 0, sizeof sa);
     sa.info = a.info; sa.head_log = a.head_log; sa.tail_log = a.tail_log;
     sa.nspans = a.nspans; sa.nrot = h->cst.nrotations; sa.nsymbols = h->cst.nsymbols;
     sa.rot_perm = h->d_rotperm.as<uint8_t>(); sa.omega = h->rxp.omega;
     sa.seams = h->d_rx_seams.as<RxSeam>();
+    // Seam rule (include/leandvb_b200.h, "Receiver scheduling mode"): strict = every hard decision of the overlap
+    // agrees and the loop states on both sides agree: phase within 1/16 of the ambiguity sector (5.6 degrees for
+    // QPSK; converged loops differ by a few phase units), NCO frequency within 1/64 of the lock range.
+    sa.strict = (c.seam_mode == 0) ? 1 : 0;
+    sa.state_begin = a.state_begin; sa.state_end = a.state_end;
+    sa.tol_phase = c.hs ? 0.f : 65536.0f / (float)h->cst.nrotations / 16.0f;
+    sa.tol_freqw = c.hs ? 0.f : (h->rxp.max_freqw - h->rxp.min_freqw) / 64.0f;
     KL("rx_stitch", launch_rx_stitch(sa, nullptr, 0, h->st));
   // The device is busy with the spans for a while: finish the telemetry of this batch now.
   { int rcm = meas_finish(h); if (rcm) return rcm; }
@@ -1126,7 +1137,7 @@ int rx_fast_reseed(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, std::vector<RxSe
                    std::vector<RxSpanInfo> &info) {
   for (int attempt = 0; attempt < 6 && a.nspans > 8; ++attempt) {
     uint32_t nfail = 0;
-    for (uint32_t j = 0; j + 1 < a.nspans; ++j) nfail += seams[j].ok ? 0 : 1;
+    for (uint32_t j = 0; j + 1 < a.nspans; ++j) nfail += seams[j].ok_loose ? 0 : 1;   // spans that did not converge
     if (nfail <= std::max<uint32_t>(4, a.nspans / 32)) break;
     std::vector<RxState> ends(a.nspans);
     CK(cudaMemcpyAsync(ends.data(), a.state_end, sizeof(RxState) * a.nspans, cudaMemcpyDeviceToHost, h->st));
@@ -1162,12 +1173,19 @@ int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint3
     KL("rx_plan", launch_rx_plan(a.info, sa.seams, a.nspans, a.span_cap, h->cst.nrotations, rot0, skip0,
                                  h->d_rx_off.as<uint64_t>(), h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(),
                                  h->d_counts.as<uint64_t>(), h->st));
-    uint64_t plan[4];
+    uint64_t plan[8];
     CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     int cum = (int)plan[2];
     const bool slow = (plan[0] != 0 || plan[3] != 0);
     h->meas.seams_total += slow ? 0 : a.nspans - 1;
+    auto note_deviation = [&](const uint64_t *pl) {
+      float f; uint32_t u;
+      u = (uint32_t)pl[5]; memcpy(&f, &u, 4); h->meas.seam_max_dphase = std::max(h->meas.seam_max_dphase, f);
+      u = (uint32_t)pl[6]; memcpy(&f, &u, 4); h->meas.seam_max_dfreqw = std::max(h->meas.seam_max_dfreqw, f);
+      u = (uint32_t)pl[7]; memcpy(&f, &u, 4); h->meas.seam_max_dmu = std::max(h->meas.seam_max_dmu, f);
+    };
+    if (!slow) { h->meas.seams_mismatch_accepted += (uint32_t)plan[4]; note_deviation(plan); }
     produced = plan[1];
     if (slow) {
     std::vector<RxSeam> seams(a.nspans);
@@ -1180,12 +1198,17 @@ int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint3
     // Repair failed seams: span j+1 is re-run exactly from the end state of span j.  All
     // failed spans whose predecessor is final are repaired in ONE launch per round; the
     // seam behind each repaired span is stitched again (its tail changed).
+    // Strict mode: after kStrictRounds rounds the seams that still carry isolated mismatches are judged
+    // by the tolerant rule (low SNR: two converged loops flip different noise-level decisions, and every
+    // round costs a span time); seams that fail that rule too are repaired to the end.
+    constexpr int kStrictRounds = 2;
     std::vector<uint8_t> fixed(a.nspans, 0);   // seam j resolved by an exact re-run of span j+1
     for (int round = 0; round < 1 << 20; ++round) {
       std::vector<uint32_t> spans, restitch;
       bool prev_bad = false;
+      const bool loose = sa.strict && round >= kStrictRounds;
       for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
-        const bool bad = !seams[j].ok && !fixed[j];
+        const bool bad = !(loose ? seams[j].ok_loose : seams[j].ok) && !fixed[j];
         if (bad && !prev_bad) spans.push_back(j + 1);
         prev_bad = bad;
       }
@@ -1205,6 +1228,14 @@ int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint3
       }
       rc = fetch();
       if (rc) return rc;
+    }
+    for (uint32_t j = 0; j + 1 < a.nspans; ++j) {
+      if (!fixed[j]) {
+        if (seams[j].mismatches) ++h->meas.seams_mismatch_accepted;
+        h->meas.seam_max_dphase = std::max(h->meas.seam_max_dphase, fabsf(seams[j].dphase));
+        h->meas.seam_max_dfreqw = std::max(h->meas.seam_max_dfreqw, fabsf(seams[j].dfreqw));
+        h->meas.seam_max_dmu = std::max(h->meas.seam_max_dmu, fabsf(seams[j].dmu));
+      }
     }
     for (uint32_t j = 0; j + 1 < a.nspans; ++j)
       if (fixed[j]) { seams[j].ok = 1; seams[j].rot = 0; seams[j].extend_prev = 0; seams[j].skip_next = 0; }
@@ -1253,6 +1284,49 @@ int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint3
     }
     *produced_out = produced;
   *cum_out = cum;
+  return LDVB_OK;
+}
+
+// Level check in front of the FAST spans (include/leandvb_b200.h, "AGC settling"): mean |x|^2 of the first samples
+// of the batch against the carried AGC estimate (sdr.h:863-869 tracks the power of the sampled symbols).
+// *far = the estimate is more than a factor 2 away, i.e. the spans' warm-ups would start with loop gains
+// (proportional to the squared amplitude) that are off by more than that.
+int rx_level_check(ldvb_handle *h, const float2 *x, uint64_t nsamples, float *power, bool *far) {
+  *far = false; *power = 0;
+  if (h->cfg.hs || h->cfg.settle_chunks < 0 || !nsamples) return LDVB_OK;   // --hs: no AGC in that receiver
+  KL("rx_power", launch_rx_power(x, (uint32_t)std::min<uint64_t>(nsamples, 16384), h->d_rx_power.as<float>(), h->st));
+  CK(cudaMemcpyAsync(power, h->d_rx_power.p, 4, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  const float est = h->rx_state.est_insp;
+  *far = (*power > 0.f) && (est > 2.0f * *power || est < 0.5f * *power);
+  return LDVB_OK;
+}
+
+uint64_t rx_settle_chunks(const ldvb_handle *h) { return h->cfg.settle_chunks > 0 ? (uint64_t)h->cfg.settle_chunks : 512; }
+
+// The settling pass: chunks [a.chunk0, a.chunk0 + K) are walked by the serial lane from the exact carried state
+// (a.state_in), symbols go straight to sym_dst.  On return `a` describes the rest of the batch: it starts at
+// chunk0 + K from the state reached there (kept on the device), exactly, like span 0 of an ordinary batch.
+int rx_settle(ldvb_handle *h, RxArgs &a, uint64_t K, uint32_t *sym_dst, uint64_t room, uint64_t *n0) {
+  RxArgs s = a;
+  RxState *d_state = h->d_rx_settled.as<RxState>();
+  RxSpanInfo *d_info = reinterpret_cast<RxSpanInfo *>(h->d_rx_settled.as<uint8_t>() + ((sizeof(RxState) + 15) & ~(size_t)15));
+  s.nchunks = a.chunk0 + K; s.avail_chunks = s.nchunks;
+  s.span_chunks = (uint32_t)K; s.warm_chunks = 0; s.nspans = 1;
+  s.span_cap = (uint32_t)std::min<uint64_t>(room, 0xffffffffu);
+  s.sym_out = sym_dst; s.info = d_info; s.state_end = d_state;
+  s.head_log = nullptr; s.tail_log = nullptr; s.state_begin = nullptr; s.sampled = nullptr; s.sampled_flag = nullptr;
+  KL("rx_settle", launch_rx(s, nullptr, 0, h->st));
+  RxSpanInfo inf;
+  CK(cudaMemcpyAsync(&inf, d_info, sizeof inf, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&h->rx_state, d_state, sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (inf.n_out > s.span_cap) return fail(h, LDVB_EOVERFLOW, "symbol stream overflow");
+  *n0 = inf.n_out;
+  ++h->meas.settle_passes;
+  a.chunk0 += K;
+  a.state_in = d_state; a.warm_in = d_state; a.state_chunk = a.chunk0;
+  a.first_exact = 1;
   return LDVB_OK;
 }
 
@@ -1316,11 +1390,25 @@ int run_receiver(ldvb_handle *h) {
       smp.release(); smpf.release();
     }
   } else {
-    RxStitchArgs sa;
-    int rcf = rx_fast_launch(h, a, sa, nchunks);
-    if (rcf) return rcf;
-    int cum = 0;
-    if ((rcf = rx_fast_resolve(h, a, sa, 0, 0, sym_dst, room, &produced, &cum))) return rcf;
+    int rcf;
+    // AGC settling: an estimate far from the input level is pulled in by a serial (exact) pass first.
+    float power = 0; bool far = false;
+    if ((rcf = rx_level_check(h, a.x, nchunks * kRxChunk, &power, &far))) return rcf;
+    uint64_t n0 = 0, K = 0;
+    if (far) {
+      K = std::min(nchunks, rx_settle_chunks(h));
+      if (nchunks - K < 8) K = nchunks;                  // too little left for spans
+      if ((rcf = rx_settle(h, a, K, sym_dst, room, &n0))) return rcf;
+    }
+    produced = n0;
+    if (K < nchunks) {
+      RxStitchArgs sa;
+      if ((rcf = rx_fast_launch(h, a, sa, nchunks - K))) return rcf;
+      int cum = 0;
+      uint64_t n1 = 0;
+      if ((rcf = rx_fast_resolve(h, a, sa, 0, 0, sym_dst + n0, room - n0, &n1, &cum))) return rcf;
+      produced += n1;
+    }
   }
   // Measurements recorded by the kernel: {chunk, freq_tap, ss, mer}
   {
@@ -1712,7 +1800,16 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
       if (rc == 0) break;
     }
   }
-  for (int guard = 0; guard < (c.fastlock ? 4096 : 64) && !c.viterbi && !c.hs; ++guard) {
+  // The loop ends when the symbols are drained below what the deconvolver needs (dvb.h:419-426); every pass
+  // consumes symbols, a skipped symbol or at least moves to the next hypothesis, so the bound below (one pass per
+  // 256 symbols + a constant) is never reached by a correct run: running into it is reported, not hidden.
+  // While mpeg_sync is searching, one pass deconvolves only what a search can look at before it calls
+  // next_sync() (3 sweeps x 8 bit phases x 1632 bytes, dvb.h:758-778) instead of the whole batch: on a stream that
+  // never locks the cost is one pass over the symbols, not one pass per hypothesis switch.
+  constexpr uint64_t kSearchWindow = 3 * 8 * 1632 + 4096;
+  const uint64_t max_passes = c.viterbi || c.hs ? 0 : h->s_sym.count / 256 + 4096;
+  uint64_t pass = 0;
+  for (; pass < max_passes; ++pass) {
     if (h->skip) {  // dvb.h:415-416
       if (h->s_sym.count < (uint64_t)h->skip) break;
       if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
@@ -1750,7 +1847,9 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
       }
       continue;                                          // more windows while symbols remain
     }
-    if ((rc = deconv_launch(h, ~0ull, &run))) return rc;
+    const uint64_t limit = h->sync.synchronized ? ~0ull : kSearchWindow;
+    if ((rc = deconv_launch(h, limit, &run))) return rc;
+    if (!run.produced) break;                            // fewer symbols left than one run needs (dvb.h:419-426)
     const size_t tap_at = tap_bytes.size();
     if (c.keep_taps && run.produced) {
       tap_bytes.resize(tap_at + run.produced);
@@ -1762,7 +1861,8 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
     if (rc < 0) return rc;
     if (rc == 0) {
       if ((rc = deconv_commit(h, run))) return rc;
-      break;
+      if (run.produced < limit) break;                   // everything the symbols allow has been deconvolved
+      continue;                                          // a search window: more symbols are waiting
     }
     // Third fruitless sweep: mpeg_sync calls deconv->next_sync().  Bytes of this
     // run that the search has not consumed are void (their symbols are re-read by
@@ -1779,6 +1879,7 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
     if ((rc = deconv_commit(h, kept))) return rc;
     if (++h->locked == 4) { h->locked = 0; h->skip = 1; }  // dvb.h:185-193
   }
+  if (max_passes && pass == max_passes) return fail(h, LDVB_ESTATE, "deconvolution/sync search did not drain the symbol stream");
   if (c.keep_taps) {
     Tap &t = h->taps[LDVB_TAP_BYTES];
     if (t.buf.bytes < tap_bytes.size()) { t.buf.release(); CK(t.buf.alloc(tap_bytes.size() + 4096)); }
@@ -2259,16 +2360,36 @@ int shard_run_front(ldvb_handle *h, const NotchState *exact_notch) {
   a.info = h->d_rx_info.as<RxSpanInfo>();
   a.state_end = h->d_rx_end.as<RxState>();
   a.meas = nullptr; a.meas_count = nullptr; a.max_meas = 0;
-  if ((rc = rx_fast_launch(h, a, sh.sa, sh.own_end - sh.own_begin))) return rc;
+  // AGC settling (see run_receiver).  The first chunk of the stream has the exact start state: a serial pass, its
+  // symbols open the symbol stream.  Later chunks have no exact state to start from before the EDGE arrives (the
+  // seam to the previous chunk is verified then): their warm-ups are seeded with the measured power instead.
+  sh.settle_syms = 0;
+  uint64_t owned = sh.own_end - sh.own_begin;
+  {
+    float power = 0; bool far = false;
+    if ((rc = rx_level_check(h, a.x + a.chunk0 * kRxChunk, owned * kRxChunk, &power, &far))) return rc;
+    if (far && sh.first) {
+      const uint64_t K = std::min(owned - 8, rx_settle_chunks(h));
+      if ((rc = rx_settle(h, a, K, reinterpret_cast<uint32_t *>(h->s_sym.at(0)), h->s_sym.cap, &sh.settle_syms))) return rc;
+      owned -= K;
+    } else if (far) {
+      st0.est_insp = power;
+      st0.agc_gain = 75.0f / sqrtf(power);
+      CK(cudaMemcpyAsync(h->d_rx_state.p, &st0, sizeof st0, cudaMemcpyHostToDevice, h->st));
+      CK(cudaStreamSynchronize(h->st));   // st0 is a local
+      ++h->meas.settle_passes;
+    }
+  }
+  if ((rc = rx_fast_launch(h, a, sh.sa, owned))) return rc;
   // Cold start (carrier offset): most warm-ups fail; pull the loops in before the back stage.
   if (a.nspans > 8) {
     KL("rx_plan", launch_rx_plan(a.info, sh.sa.seams, a.nspans, a.span_cap, h->cst.nrotations, 0, 0,
                                  h->d_rx_off.as<uint64_t>(), h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(),
                                  h->d_counts.as<uint64_t>(), h->st));
-    uint64_t plan[4];
+    uint64_t plan[9];
     CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    if (plan[0] > std::max<uint32_t>(4, a.nspans / 32)) {
+    if (plan[8] > std::max<uint32_t>(4, a.nspans / 32)) {
       std::vector<RxSeam> seams; std::vector<RxSpanInfo> info;
       if ((rc = rx_fetch(h, a, sh.sa, seams, info))) return rc;
       if ((rc = rx_fast_reseed(h, a, sh.sa, seams, info))) return rc;
@@ -2362,7 +2483,12 @@ int shard_back(ldvb_handle *h, const EdgeBlob *in, uint8_t *ts_dst, uint64_t ts_
     memset(&seam, 0, sizeof seam);
     if (in->have_tail) {
       CK(cudaMemcpyAsync(h->d_edge_tail.p, in->tail_log, sizeof in->tail_log, cudaMemcpyHostToDevice, h->st));
-      KL("rx_stitch", launch_rx_stitch_pair(sh.sa, h->d_edge_tail.as<RxSeamSym>(), in->n_tail, h->d_edge_seam.as<RxSeam>(), h->st));
+      // the previous chunk's end state, in ITS last span's frame (in->rx_end is in the reference frame)
+      RxState pe = in->rx_end;
+      if (in->cum_rot) pe.phase = fmodf(pe.phase + (float)in->cum_rot * (65536.0f / h->cst.nrotations), 65536.0f);
+      CK(cudaMemcpyAsync(h->d_edge_state.p, &pe, sizeof pe, cudaMemcpyHostToDevice, h->st));
+      KL("rx_stitch", launch_rx_stitch_pair(sh.sa, h->d_edge_tail.as<RxSeamSym>(), in->n_tail, h->d_edge_state.as<RxState>(),
+                                            h->d_edge_seam.as<RxSeam>(), h->st));
       CK(cudaMemcpyAsync(&seam, h->d_edge_seam.p, sizeof seam, cudaMemcpyDeviceToHost, h->st));
       CK(cudaStreamSynchronize(h->st));
     }
@@ -2388,7 +2514,8 @@ int shard_back(ldvb_handle *h, const EdgeBlob *in, uint8_t *ts_dst, uint64_t ts_
       }
     }
   } else {
-    sym.count = 0; h->s_bytes.count = 0; h->s_mpeg.count = 0;
+    sym.count = sh.settle_syms; h->s_bytes.count = 0; h->s_mpeg.count = 0;
+    h->meas.symbols += sh.settle_syms;
   }
   uint64_t produced = 0;
   int cum = 0;

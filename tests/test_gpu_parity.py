@@ -469,3 +469,101 @@ def test_hs_path(product, oracle, mode, npk, noise, fastlock):
         assert_prefix(got["rspackets"], ref["rspackets"], "RS packets", slack=204)
     assert_prefix(got["ts"], ref["ts"], "TS", slack=188)
     assert len(got["ts"]) > npk - 80
+
+
+# ------------------------------------------------------------------ round 2: FAST-mode envelope
+
+def _scaled(raw, g):
+    return (raw.astype(np.float32) * np.float32(g)).astype(np.float32)
+
+
+@pytest.mark.parametrize("gain", [0.1, 6.0])
+def test_fast_mode_off_nominal_level_settles(product, oracle, gain):
+    """A stream 20 dB below / 15 dB above the nominal level: the reference's AGC (sdr.h:863-869) needs a few
+    hundred chunks to pull the gain in.  FAST walks those chunks serially first (ldvb_config::settle_chunks),
+    then cuts spans: the settling pass is bit-exact, the TS equals the oracle's."""
+    P, O = product, oracle
+    raw = _scaled(V.ref_iq(1500, fmt="f32"), gain)
+    kw = dict(fmt="f32", resample=True)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_FAST, **kw)
+    m = got["meas"]
+    assert m["settle_passes"] == 1 and m["seams_total"] > 10, m
+    sym = got["symbols"].reshape(-1, 4)
+    k = 512 * 128 * 5 // 6 - 64                      # symbols of the 512-chunk settling pass at 1.2 samples per symbol
+    assert np.array_equal(sym[:k, :3], ref["symbols"][:k, :3]), "settling pass: every softsymbol field"
+    n = min(sym.shape[0], ref["symbols"].shape[0])
+    assert abs(sym.shape[0] - ref["symbols"].shape[0]) <= 2
+    assert int((sym[:n, 2] != ref["symbols"][:n, 2]).sum()) == 0, "hard decisions"
+    assert_prefix(got["ts"], ref["ts"], "TS")
+
+
+@pytest.mark.parametrize("seam_mode", [0, 1])
+def test_fast_mode_seam_rules(product, oracle, seam_mode):
+    """seam_mode 0 (default): a seam stands only with ZERO mismatching hard decisions in the overlap and agreeing
+    loop states, else the span is re-run exactly; 1: the tolerant rule of round 1 (<= 1/16).  On a clean signal both
+    give the serial hard decisions and no seam is accepted with a mismatch."""
+    P, O = product, oracle
+    kw = dict(fmt="f32", resample=True)
+    raw = V.ref_iq(1200, fmt="f32")
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_FAST, seam_mode=seam_mode, **kw)
+    m = got["meas"]
+    assert m["seams_total"] > 10 and m["seams_mismatch_accepted"] == 0, m
+    assert m["seam_max_dphase"] < 65536 / 4 / 16 and m["seam_max_dfreqw"] < 200, m
+    a, b = got["symbols"].reshape(-1, 4)[:, 2], ref["symbols"][:, 2]
+    assert a.size == b.size and int((a != b).sum()) == 0
+    assert_prefix(got["ts"], ref["ts"], "TS")
+
+
+def test_fast_mode_low_snr_strict_seams_repair(product, oracle):
+    """MER ~10 dB: noise-level decision flips make strict seams fail; they are re-run exactly (bounded rounds),
+    the rest is judged by the tolerant rule and COUNTED.  Every delivered packet must be a transmitted packet and
+    the packet sets of product and oracle differ by a few packets at most."""
+    P, O = product, oracle
+    raw = V.ref_iq(1500, fmt="f32", noise_db=10)
+    kw = dict(fmt="f32", resample=True)
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    got = run_product(P, raw, rx_mode=P.RX_FAST, **kw)
+    m = got["meas"]
+    assert m["seams_repaired"] > 0, m
+    sent = V.ts_packets(1500)
+
+    def ctrs(ts):
+        ts = ts[8:]
+        c = (ts[:, 5].astype(np.int64) << 16) | (ts[:, 6].astype(np.int64) << 8) | ts[:, 7]
+        assert (c < 1500).all() and np.array_equal(ts, sent[c])
+        return set(c.tolist())
+    cg, co = ctrs(got["ts"]), ctrs(ref["ts"])
+    assert len(co) > 1000 and len(cg ^ co) <= 0.03 * len(co), (len(cg), len(co), len(cg ^ co), m)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_noise_only_large_batches_drain(product, mode):
+    """A stream that never locks: the deconvolution/sync search must drain every batch -- no leftover
+    symbols piling up until 'symbol stream overflow' -- at a cost of one pass, whatever the batch size."""
+    P = product
+    rng = np.random.default_rng(7)
+    n = 1 << 21
+    raw = (rng.standard_normal(2 * n) * 50).astype(np.float32)
+    rx = P.Receiver(fmt="f32", resample=True, rx_mode=P.RX_EXACT if mode == "exact" else P.RX_FAST, max_batch=n)
+    for _ in range(3):
+        rx.push(raw)
+        assert rx.pull_all().shape[0] == 0
+    assert rx.meas()["lock"] == 0
+    rx.close()
+
+
+def test_two_devices_in_one_process(product, oracle):
+    """Function attributes (dynamic shared memory opt-in) are per device: a second handle on another GPU of the same
+    process must work (Viterbi 7/8 needs ~75 KB, the QPSK receiver ~208 KB)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    P, O = product, oracle
+    kw = dict(fmt="f32", viterbi=True, fec="7/8", Fs=55e6, Fm=27.5e6)
+    raw = V.ref_iq(260, fmt="f32", cr="7/8", ratio="2")
+    ref = O.Chain(O.Config(**kw)).run(raw)
+    for dev in (0, 1):
+        got = run_product(P, raw, rx_mode=P.RX_FAST, device=dev, **kw)
+        assert_prefix(got["ts"], ref["ts"], f"TS on device {dev}")

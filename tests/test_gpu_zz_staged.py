@@ -1,7 +1,7 @@
-"""Parity cases written after this round's GPU budget was spent: the oracle side of each is pinned to the reference on
-the CPU (tests/test_oracle_cpu.py, MORE_CASES), the CUDA side has NOT been run on a B200 yet.  They are marked xfail
-(non-strict) so that the first GPU run reports them as XPASS / xfailed instead of masking the verified suite; the
-marker goes away once they have been seen green."""
+"""More parity cases (s16/u16/s8 input, extra flag sets, `--resample --tune`, the 4/6 and 5/6 Viterbi trellises, the
+arithmetic QPSK slicer).  The oracle side of each is pinned to the reference on the CPU (tests/test_oracle_cpu.py,
+MORE_CASES).  They were staged as non-strict xfail at the end of round 1 and all passed on a B200 (GPUTEST_r01:
+11 xpassed); since round 2 they are ordinary tests: a regression here fails the suite."""
 import numpy as np
 import pytest
 
@@ -9,8 +9,7 @@ from tests import vectors as V
 from tests.test_gpu_parity import assert_prefix, run_product
 from tests.test_oracle_cpu import _as_format
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="staged: written after the round's GPU budget was spent, not yet run on a B200", strict=False)]
+pytestmark = pytest.mark.gpu
 
 FORMAT_CASES = [
     ("s16-scale", "s16", dict(fmt="s16", float_scale=0.015625)),
@@ -49,12 +48,15 @@ def test_more_flag_sets_bit_exact(product, oracle, name, kw, gkw):
     assert_prefix(got["ts"], ref["ts"], "TS")
 
 
+@pytest.mark.parametrize("slicer", ["table", "arith-smem"])
 @pytest.mark.parametrize("mode", ["exact", "fast"])
-def test_experimental_arithmetic_qpsk_slicer(product, oracle, mode, monkeypatch):
-    """LDVB_RX_ARITH=1 (kernels.h, kRxSamplerLinArith): symbol and cost computed, phase error from a 128 KB table.
-    Must give the same soft symbols (EXACT) / TS (FAST) as the table path."""
+def test_qpsk_slicer_variants(product, oracle, mode, slicer, monkeypatch):
+    """kernels.h, RxParams::slicer.  1 (default for QPSK with the soft metric): symbol and cost computed, phase error
+    from a 128 KB int16 column in shared memory; 0 (LDVB_RX_SLICER=0, and every other constellation): the 512 KB cell
+    table gathered from global memory.  Both must give the oracle's soft symbols (EXACT) / TS (FAST)."""
     P, O = product, oracle
-    monkeypatch.setenv("LDVB_RX_ARITH", "1")
+    if slicer == "table":
+        monkeypatch.setenv("LDVB_RX_SLICER", "0")
     kw = dict(fmt="f32", resample=True)
     raw = V.ref_iq(1200 if mode == "fast" else 300, fmt="f32", noise_db=22)
     ref = O.Chain(O.Config(**kw)).run(raw)

@@ -22,6 +22,17 @@ def test_wideband_resample_chain(product, oracle, mode):
         assert_prefix(got["bytes"], ref["bytes"], "deconvolved bytes", slack=8)
     assert_prefix(got["ts"], ref["ts"], "TS")
     assert len(ref["ts"]) >= 40
-    # 4 samples per symbol after the decimation: the handle runs the exact receiver whatever is asked
-    # (include/leandvb_b200.h, "Receiver scheduling mode")
-    assert got["meas"]["seams_total"] == 0
+    m = got["meas"]
+    if mode == "fast":
+        # This waveform reaches the receiver ~11x below the nominal level (the transmitter normalises the power of the
+        # 120x oversampled carrier): the carried AGC estimate (75^2) is far off, so the first chunks are walked
+        # serially (the settling pass, bit-exact) and the spans start from the settled state.
+        assert m["settle_passes"] == 1 and m["seams_total"] > 0, m
+        nset = 512 * 128 // 4                                  # >= symbols of the settling pass (4 samples per symbol)
+        a = got["symbols"].reshape(-1, 4)[:nset // 2, :3]
+        assert np.array_equal(a, ref["symbols"][:a.shape[0], :3]), "settling pass: soft symbols"
+        hard_a, hard_b = got["symbols"].reshape(-1, 4)[:, 2], ref["symbols"][:, 2]
+        n = min(hard_a.size, hard_b.size)
+        assert abs(hard_a.size - hard_b.size) <= 2 and int((hard_a[:n] != hard_b[:n]).sum()) <= n // 1000
+    else:
+        assert m["seams_total"] == 0
