@@ -146,7 +146,9 @@ def run_reference_cpu(raw: np.ndarray, replicas: int, repeats: int, flags=None):
 
 def awgn(raw: np.ndarray, mer_db: float) -> np.ndarray:
     """The reference's own channel simulator (apps/leanchansim.cc: wgn_c + adder, --deterministic seed) on an f32
-    vector: `leanchansim --if32 --awgn DB --deterministic --of32`, the generator the parity tests use."""
+    vector: `leanchansim --if32 --awgn DB --deterministic --of32`, the generator the parity tests use.  DB is the
+    noise standard deviation in dB (leanchansim.cc:248-249); the bench signal's RMS is ~68 = 36.7 dB, and its MER
+    without any noise is ~14 dB already (linear interpolation at 1.2 samples per symbol, no matched filter)."""
     from oracle import oracle as O
     out = subprocess.run([O.ref_bin("leanchansim"), "--if32", "--awgn", str(mer_db), "--deterministic", "--of32"],
                          input=raw.tobytes(), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
@@ -181,7 +183,7 @@ def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: 
         return set(c[good].tolist()), int((~good).sum())
 
     out = {"sample_samples": int(n)}
-    for name, db in (("clean", None), ("awgn22", 22.0), ("awgn10", 10.0)):
+    for name, db in (("clean", None), ("awgn_stddev_22dB", 22.0), ("awgn_stddev_25dB", 25.0)):
         x = base if db is None else awgn(base, db)
         se, te, me = run(x, P.RX_EXACT)
         sf, tf, mf = run(x, P.RX_FAST)
@@ -194,6 +196,10 @@ def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: 
             "symbols": int(k), "symbol_count_diff": int(sf.size) - int(se.size),
             "hard_symbol_mismatch": int(((se[:k] >> 16) != (sf[:k] >> 16)).sum()),
             "cost_mismatch": int(((se[:k] & 0xffff) != (sf[:k] & 0xffff)).sum()),
+            # soft cost = int16 difference of two squared distances (sdr.h:529-560); its scale is ~|cost| ~ 212 * 53
+            "cost_abs_diff_mean": float(np.abs((se[:k] & 0xffff).astype(np.int16).astype(np.int32) - (sf[:k] & 0xffff).astype(np.int16).astype(np.int32)).mean()) if k else None,
+            "cost_abs_diff_max": int(np.abs((se[:k] & 0xffff).astype(np.int16).astype(np.int32) - (sf[:k] & 0xffff).astype(np.int16).astype(np.int32)).max()) if k else None,
+            "cost_abs_mean": float(np.abs((se[:k] & 0xffff).astype(np.int16).astype(np.int32)).mean()) if k else None,
             "ts_packets": {"reference": int(len(tr)), "exact": int(len(te)), "fast": int(len(tf))},
             "exact_ts_bit_identical_to_reference_prefix": bool(kk > 0 and np.array_equal(te[:kk], tr[:kk]) and abs(len(te) - len(tr)) <= 1),
             "ts_packets_differing": {"fast_vs_reference": len(i_f ^ ir), "fast_vs_exact": len(i_f ^ ie), "exact_vs_reference": len(ie ^ ir)},
@@ -201,7 +207,7 @@ def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: 
             "seams": {"total": mf["seams_total"], "repaired": mf["seams_repaired"],
                       "accepted_with_mismatch": mf["seams_mismatch_accepted"], "settle_passes": mf["settle_passes"],
                       "max_dphase": mf["seam_max_dphase"], "max_dfreqw": mf["seam_max_dfreqw"], "max_dmu": mf["seam_max_dmu"]},
-            "reference_mer_db": me["mer"],
+            "mer_db": me["mer"],
         }
     return out
 

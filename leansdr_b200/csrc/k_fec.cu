@@ -53,7 +53,10 @@ k_deconv_tiled(DeconvArgs a, uint64_t nsym) {
   const int64_t g1 = (bit_last >= a.n_out) ? (bit_last - a.n_out) / pp : -1;
   // Extended symbol stream E: E[0..31] = the carried register, E[32+s] = symbol s.
   // The register of group g is E[K_g .. K_g+32), K_g = k0 + g*half.
-  const int64_t e_base = (k0 + g0 * half) & ~(int64_t)15;
+  // e_base: at or below the first register, and such that symbols + (e_base - 32) is 16-byte aligned whatever the
+  // alignment of `symbols` itself (the stream's read position advances by arbitrary symbol counts).
+  const int mis = (int)((reinterpret_cast<uintptr_t>(a.symbols) >> 2) & 3u);
+  const int64_t e_base = ((k0 + g0 * half + mis) & ~(int64_t)15) - mis;
   const int64_t e_end = (g1 >= 0) ? k0 + g1 * half + 32 : e_base;
   const int nwords = (int)((e_end - e_base + 15) / 16) + 2;
   for (int w = threadIdx.x; w < nwords && w < kDcWords; w += blockDim.x) {
@@ -73,7 +76,8 @@ k_deconv_tiled(DeconvArgs a, uint64_t nsym) {
       for (int i = 0; i < 16; ++i) {
         const int64_t e = e0 + i;
         uint32_t code = 0;
-        if (e < 32) code = (uint32_t)(a.reg_in >> (2 * (31 - e))) & 3u;
+        if (e < 0) code = 0;                       // (in front of the carried register: never part of a group)
+        else if (e < 32) code = (uint32_t)(a.reg_in >> (2 * (31 - e))) & 3u;
         else if ((uint64_t)(e - 32) < nsym) code = a.hyp[(a.symbols[e - 32] >> 16) & 3u];
         word |= code << (30 - 2 * i);
       }

@@ -154,7 +154,7 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
     if (SLICER == 1) {
       // QPSK: the cell's symbol and cost follow from the truncated (I, Q); only the phase error is looked up
       // (shared memory: a 2-byte gather, ~3 bank wavefronts for 32 random lanes).
-      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040);   // (Ii & 0xff) << 8 | (Qi & 0xff)
+      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040) & 0xffffu;   // (Ii & 0xff) << 8 | (Qi & 0xff)
       pe = lds_s16(s_pe + 2u * ci);
       symbol = ((Ii < 0) ? 2 : 0) | ((Qi < 0) ? 1 : 0);
       const int aI = abs(Ii), aQ = abs(Qi);
@@ -163,7 +163,7 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
       const int cost = min(d1, 32767) - min(d2, 32767);
       word = ((uint32_t)cost & 0xffffu) | ((uint32_t)symbol << 16);
     } else {
-      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040);
+      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040) & 0xffffu;
       const uint2 cellw = __ldg(reinterpret_cast<const uint2 *>(p.cstln) + ci);
       symbol = (int)(cellw.x >> 16) & 0xff;
       pe = (int)(short)(cellw.y & 0xffffu);
@@ -325,7 +325,9 @@ __device__ __forceinline__ void rx_tile(const RxParams &p, RxRun &r, const float
                                         float t0 /* time of the tile's first sample relative to the seam */) {
   float4 w = rp[0];
   float2 cur = make_float2(w.x, w.y), nxt = make_float2(w.z, w.w);
-#pragma unroll
+  // (unrolled by two -- one 16-byte row read per pair of samples -- and no further: the body is ~140
+  //  instructions per sample, and four modes x three samplers of it have to stay in the instruction cache)
+#pragma unroll 2
   for (int n = 0; n < TILE; ++n) {
     float2 nxt2;
     if ((n & 1) == 0) { w = rp[(n >> 1) + 1]; nxt2 = make_float2(w.x, w.y); }
@@ -846,9 +848,10 @@ size_t rx_row_bytes(int sampler) { return sampler == 2 ? RowCfg<2, kTile>::kByte
 }  // namespace
 
 // Warps per CTA of the span kernel.  Slicer 1 (QPSK, phase-error column in shared memory): one fat CTA per SM,
-// LDVB_RX_WARPS warps (default 16: 128 KB of table + 80 KB of rows); slicer 0: 4 warps, three CTAs per SM.
+// LDVB_RX_WARPS warps (default 12: 128 KB of table + 60 KB of rows; measured 1.60 ms against 2.35 ms with 16 warps, whose
+// 208 KB of shared memory leave the trig16 gathers only 28 KB of L1); slicer 0: 4 warps, three CTAs per SM.
 int rx_warps_per_cta(int slicer) {
-  static const int w1 = env_int("LDVB_RX_WARPS", 16, 1, 20);
+  static const int w1 = env_int("LDVB_RX_WARPS", 12, 1, 19);
   return slicer == 1 ? w1 : 4;
 }
 

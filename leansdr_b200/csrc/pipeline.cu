@@ -57,7 +57,8 @@ struct Stream {
   uint64_t cap = 0;     // items
   uint64_t count = 0;   // items currently held (carry + new)
   uint64_t fresh = 0;   // items appended by the current batch (for taps)
-  uint8_t *at(uint64_t i) const { return buf.as<uint8_t>() + i * elem; }
+  uint64_t head = 0;    // read position: items in front of it were consumed lazily (stream_consume_lazy)
+  uint8_t *at(uint64_t i) const { return buf.as<uint8_t>() + (head + i) * elem; }
 };
 
 struct HypState { uint64_t reg = 0, acc = 0; int n_in = 0, n_out = 0; };
@@ -339,6 +340,25 @@ int stream_consume(ldvb_handle *h, Stream &s, uint64_t n, DevBuf &tmp) {
   return LDVB_OK;
 }
 
+// Consume without moving the remainder: only the read position advances.  For streams that are drained in
+// several passes per batch (the symbols, while mpeg_sync is searching); stream_compact brings the (then small)
+// remainder back to the front of the buffer.
+int stream_consume_lazy(ldvb_handle *h, Stream &s, uint64_t n) {
+  if (n > s.count) return fail(h, LDVB_ESTATE, "stream underflow");
+  s.head += n;
+  s.count -= n;
+  if (!s.count) s.head = 0;
+  return LDVB_OK;
+}
+
+int stream_compact(ldvb_handle *h, Stream &s, DevBuf &tmp) {
+  if (!s.head) return LDVB_OK;
+  const uint64_t n = s.head, left = s.count;
+  s.head = 0;
+  s.count = left + n;                    // view the buffer from its start again, then drop the consumed items
+  return stream_consume(h, s, n, tmp);
+}
+
 int tap_store(ldvb_handle *h, int which, const void *dev, uint64_t bytes) {
   if (!h->cfg.keep_taps) return LDVB_OK;
   Tap &t = h->taps[which];
@@ -363,7 +383,7 @@ void rx_reset_state(ldvb_handle *h) {
 // Everything a fresh handle starts from (also ldvb_reset).
 void reset_carry(ldvb_handle *h) {
   Stream *ss[] = {&h->s_raw, &h->s_notched, &h->s_pp, &h->s_sym, &h->s_bytes, &h->s_mpeg};
-  for (Stream *s : ss) { s->count = 0; s->fresh = 0; }
+  for (Stream *s : ss) { s->count = 0; s->fresh = 0; s->head = 0; }
   memset(&h->notch, 0, sizeof h->notch);
   h->notch.gain = 1;
   for (int s = 0; s < kNotchMaxSlots; ++s) h->notch.slot[s].bin = -1;
@@ -1529,7 +1549,7 @@ int fastlock_evaluate(ldvb_handle *h, uint64_t n, uint64_t *errors_best) {
 
 int deconv_commit(ldvb_handle *h, const DeconvRun &run) {
   h->hyp[h->locked] = run.after;
-  return stream_consume(h, h->s_sym, run.consumed, h->d_scratch);
+  return stream_consume_lazy(h, h->s_sym, run.consumed);
 }
 
 // viterbi_sync::run (dvb.h:1366-1414): whole chunks of 128 FEC blocks.
@@ -1637,7 +1657,6 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
 int run_sync(ldvb_handle *h) {
   Stream &in = h->s_bytes;
   Stream &out = h->s_mpeg;
-  out.fresh = 0;
   for (int guard = 0; guard < 1000000; ++guard) {
     uint64_t npk = 0;
     CK(cudaMemcpyAsync(h->d_sync_state.p, &h->sync, sizeof(SyncState), cudaMemcpyHostToDevice, h->st));
@@ -1734,6 +1753,7 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
   WallTimer *wt = nullptr;
   struct WtGuard { WallTimer *&p; ~WtGuard() { delete p; } } wt_guard{wt};
   delete wt; wt = new WallTimer(h, "wall:deconv_sync");
+  h->s_mpeg.fresh = 0;   // (run_sync may be called several times per batch: the tap covers all of them)
   // ---- deconvolution <-> sync (with the backward next_sync edge, dvb.h:771-778)
   std::vector<uint8_t> tap_bytes;  // bytes that stay in the stream, for the tap
   if (c.viterbi) {
@@ -1812,7 +1832,7 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
   for (; pass < max_passes; ++pass) {
     if (h->skip) {  // dvb.h:415-416
       if (h->s_sym.count < (uint64_t)h->skip) break;
-      if ((rc = stream_consume(h, h->s_sym, h->skip, h->d_scratch))) return rc;
+      if ((rc = stream_consume_lazy(h, h->s_sym, h->skip))) return rc;
       h->skip = 0;
     }
     DeconvRun run;
@@ -1880,6 +1900,7 @@ int run_backend(ldvb_handle *h, uint8_t *ts_dst, uint64_t ts_cap, uint64_t *ts_o
     if (++h->locked == 4) { h->locked = 0; h->skip = 1; }  // dvb.h:185-193
   }
   if (max_passes && pass == max_passes) return fail(h, LDVB_ESTATE, "deconvolution/sync search did not drain the symbol stream");
+  if ((rc = stream_compact(h, h->s_sym, h->d_scratch))) return rc;
   if (c.keep_taps) {
     Tap &t = h->taps[LDVB_TAP_BYTES];
     if (t.buf.bytes < tap_bytes.size()) { t.buf.release(); CK(t.buf.alloc(tap_bytes.size() + 4096)); }
