@@ -239,6 +239,17 @@ int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n_samples);
 int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets,
 	      size_t *n_packets);
 
+/* Page-locks a host buffer the caller owns, once, so that every later
+ * ldvb_push from inside it is a direct DMA transfer.  Meant for the reference's
+ * pipebuf: framework.h:133-146 allocates it once with `new T[size]` (pageable
+ * memory) and hands out pointers into it for the life of the process
+ * (pipereader::rd(), framework.h:219-221); a pageable source makes the driver
+ * stage every copy through its own bounce buffer, synchronously.  ldvb_push
+ * accepts pageable memory too (it is only slower).  Returns LDVB_ECUDA when the
+ * range cannot be locked (the caller may carry on unregistered). */
+int ldvb_host_register(void *ptr, size_t bytes);
+int ldvb_host_unregister(void *ptr);
+
 /* ------------------------------------------------------- device-resident I/O
  * Same processing with the IQ batch already in HBM and the TS packets left in
  * HBM: iq_dev and ts_dev are device pointers on cfg.device.  *n_packets is
@@ -281,7 +292,12 @@ int ldvb_host_table(const ldvb_config *cfg, int which, void *dst_host,
 
 /* Carry state of the serial stages: what rank r hands
  * to rank r+1 in a time-sharded run, and what tests use to compare with the
- * reference's private members.  Opaque blob of ldvb_state_size() bytes. */
+ * reference's private members.  Opaque blob of ldvb_state_size() bytes.
+ * PARTIAL by design: the notch / rotator / receiver loop / deconvolver /
+ * mpeg_sync / derandomizer registers and the fir_filter retune.  It does NOT
+ * hold the Viterbi decoders, the --hs carry or the unread stream remainders
+ * (use it between batches of a drained handle); the complete hand-over between
+ * handles is the EDGE blob of ldvb_shard_back(). */
 size_t ldvb_state_size(const ldvb_handle *h);
 int    ldvb_get_state(ldvb_handle *h, void *blob, size_t cap);
 int    ldvb_set_state(ldvb_handle *h, const void *blob, size_t size);

@@ -70,7 +70,7 @@ class Meas(C.Structure):
 
 EXPORTS = [
     "ldvb_abi_version", "ldvb_strerror", "ldvb_last_error", "ldvb_config_default", "ldvb_create",
-    "ldvb_destroy", "ldvb_push", "ldvb_pull", "ldvb_process_device", "ldvb_get_meas", "ldvb_tap",
+    "ldvb_destroy", "ldvb_push", "ldvb_pull", "ldvb_host_register", "ldvb_host_unregister", "ldvb_process_device", "ldvb_get_meas", "ldvb_tap",
     "ldvb_table", "ldvb_host_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
     "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
     "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
@@ -113,6 +113,8 @@ def load():
     L.ldvb_destroy.argtypes = [vp]
     L.ldvb_push.argtypes = [vp, vp, sz]
     L.ldvb_pull.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.ldvb_host_register.argtypes = [vp, sz]
+    L.ldvb_host_unregister.argtypes = [vp]
     L.ldvb_process_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
     L.ldvb_get_meas.argtypes = [vp, C.POINTER(Meas)]
     L.ldvb_tap.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]

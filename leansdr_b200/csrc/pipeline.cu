@@ -428,6 +428,9 @@ void reset_carry(ldvb_handle *h) {
   h->meas_pending.clear(); h->meas_host_used = 0;      // (callers have synchronised the stream)
   h->vber_queue.clear(); h->vber_num = h->vber_den = 0;
   h->vber_sample = std::max(50000, (int)(h->cfg.Fm / 2));   // leandvb.cc:585-587
+  // The clears above went to the legacy default stream, which the handle's non-blocking stream does not
+  // synchronise with: make them visible before anything is launched on h->st.
+  cudaDeviceSynchronize();
 }
 
 void rx_setup(ldvb_handle *h) {
@@ -2687,6 +2690,20 @@ int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n) {
   return LDVB_OK;
 }
 
+int ldvb_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return LDVB_EINVAL;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return LDVB_OK; }
+  if (e != cudaSuccess) { cudaGetLastError(); return LDVB_ECUDA; }
+  return LDVB_OK;
+}
+
+int ldvb_host_unregister(void *ptr) {
+  if (!ptr) return LDVB_EINVAL;
+  if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return LDVB_ECUDA; }
+  return LDVB_OK;
+}
+
 int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets, size_t *n_packets) {
   if (!h || !n_packets) return LDVB_EINVAL;
   const size_t avail = (h->ts_queue_wr - h->ts_queue_rd) / 188;
@@ -2864,6 +2881,13 @@ int ldvb_set_state(ldvb_handle *h, const void *blob, size_t size) {
   h->notch = b.notch; h->rot_index = b.rot_index; h->rx_state = b.rx;
   for (int i = 0; i < 4; ++i) h->hyp[i] = b.hyp[i];
   h->locked = b.locked; h->skip = b.skip; h->sync = b.sync; h->derand_pos = b.derand_pos;
+  if (h->use_fir && h->fir_current_freq != b.fir_current_freq) {   // the low-pass follows the saved retune
+    CK(cudaStreamSynchronize(h->st));
+    h->fir_shifted = shift_taps(h->fir_coeffs, b.fir_current_freq);
+    h->fir_current_freq = b.fir_current_freq;
+    CK(cudaMemcpyAsync(h->d_taps.p, h->fir_shifted.data(), h->fir_shifted.size() * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
   return LDVB_OK;
 }
 

@@ -60,6 +60,11 @@ struct gpu_dvbs_receiver : runnable {
     int rc = ldvb_create(&cfg, &handle);
     if ( rc ) { fprintf(stderr, "ldvb_create: %s\n", ldvb_strerror(rc)); fail("gpu_dvbs_receiver"); }
     max_batch = cfg.max_batch;
+    // The pipebufs are allocated once with new T[] (framework.h:139-141): page-lock them so that
+    // the copies of ldvb_push are DMA transfers straight from in.rd().  Failure is not fatal.
+    if ( ldvb_host_register(_in.buf, (size_t)(_in.end-_in.buf)*sizeof(Tin)) )
+      fprintf(stderr, "gpu_dvbs_receiver: input pipebuf stays pageable (slower copies)\n");
+    else registered = _in.buf;
   }
 
   void run() {
@@ -78,10 +83,12 @@ struct gpu_dvbs_receiver : runnable {
   }
 
   void shutdown() {
+    if ( registered ) { ldvb_host_unregister(registered); registered = NULL; }
     if ( handle ) { ldvb_destroy(handle); handle = NULL; }
   }
 
 private:
+  void *registered = NULL;
   void drain() {
     while ( 1 ) {
       unsigned long w = out.writable();
