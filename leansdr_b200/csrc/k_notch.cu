@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "notch_common.cuh"
 
 namespace ldvb {
 
@@ -141,53 +142,6 @@ k_notch_detect(NotchDetectArgs a) {
 // (measured: median 1000 samples, max < 3000).  Every segment is
 // still verified against its predecessor and re-run when it did not merge.
 
-template <int FMT>
-__device__ __forceinline__ float2 ld_raw(const RawSrc &src, uint64_t idx, float scale) {
-  const void *raw = src.head;
-  if (src.main && idx >= src.c0) { raw = src.main; idx -= src.c0; }
-  if (FMT == 0) { uchar2 v = reinterpret_cast<const uchar2 *>(raw)[idx];
-    return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
-  if (FMT == 1) { char2 v = reinterpret_cast<const char2 *>(raw)[idx];
-    return make_float2((float)(int)v.x, (float)(int)v.y); }
-  if (FMT == 2) { ushort2 v = reinterpret_cast<const ushort2 *>(raw)[idx];
-    return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768)); }
-  if (FMT == 3) { short2 v = reinterpret_cast<const short2 *>(raw)[idx];
-    return make_float2((float)(int)v.x, (float)(int)v.y); }
-  float2 v = __ldg(reinterpret_cast<const float2 *>(raw) + idx);
-  if (FMT == 4) v = make_float2(fmul(v.x, scale), fmul(v.y, scale));
-  return v;
-}
-
-// Segment geometry shared by the guess and apply kernels.
-struct SegPlan {
-  uint64_t own_begin, own_end, run_begin;  // blocks
-  int epoch;                               // epoch of run_begin
-  int start_kind;                          // 0 exact carried state, 1 exact zero (full reset), 2 guess
-};
-
-__device__ __forceinline__ SegPlan plan_segment(const NotchApplyArgs &a, uint32_t seg) {
-  SegPlan p;
-  p.own_begin = a.block0 + (uint64_t)seg * a.seg_blocks;
-  p.own_end = p.own_begin + a.seg_blocks;
-  if (p.own_end > a.nblocks) p.own_end = a.nblocks;
-  int ep = 0;
-  while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= p.own_begin) ++ep;
-  p.epoch = ep;
-  if (seg == 0 && a.first_exact) { p.run_begin = p.own_begin; p.start_kind = 0; return p; }
-  // One warm-up block, never across an epoch start (tables / resets change there).
-  uint64_t wb = (p.own_begin > a.warm_blocks) ? p.own_begin - a.warm_blocks : 0;
-  if (wb < a.epochs[ep].first_block) wb = a.epochs[ep].first_block;
-  p.run_begin = wb;
-  if (wb == 0 && ep == 0 && a.first_exact) { p.start_kind = 0; return p; }   // reaches the carried state
-  if (a.epochs[ep].first_block == wb) {
-    bool all = true;
-    for (int s = 0; s < a.nslots; ++s) all = all && (a.epochs[ep].reset[s] != 0);
-    if (all) { p.start_kind = 1; return p; }
-  }
-  p.start_kind = 2;
-  return p;
-}
-
 // Block sums: S_b = sum over the samples i of block b of bb[i]*k*(1-k)^(4095-i), i.e. what
 // block b alone contributes to the estimate at its end.  One CTA per block, every sample of
 // the stream is read once (coalesced); the start state of a segment is then assembled from
@@ -198,6 +152,11 @@ k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][
   __shared__ float2 part[4][kNotchMaxSlots];
   const uint64_t b = first_block + blockIdx.x;
   if (b >= a.nblocks) return;
+  if (a.seg_blocks > 2) {
+    // Only the two blocks in front of a segment's warm-up are ever asked for (guess_from_sums): with long
+    // segments most blocks are skipped (b + warm + 2 >= block0 by the choice of first_block).
+    if ((b + a.warm_blocks + 2 - a.block0) % a.seg_blocks > 1) return;
+  }
   int ep = 0;
   while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= b) ++ep;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,26 +188,6 @@ k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][
   }
 }
 
-// Start state of a segment whose exact run begins at block p.run_begin (start_kind 2): the
-// estimate forgets with (1-k)^n, so the two blocks in front of it (8192 samples, weight of
-// anything older < 1e-7) decide it.  History never reaches across the start of the epoch
-// (tables change there); at the very start of the stream it runs into the carried state.
-__device__ __forceinline__ float2 guess_from_sums(const NotchApplyArgs &a, const SegPlan &p, const float2 *sums, int s) {
-  const uint64_t floor_b = a.epochs[p.epoch].first_block;
-  const uint64_t rb = p.run_begin;
-  const uint64_t nh = (rb - floor_b) < 2 ? (rb - floor_b) : 2;     // history blocks available
-  const float w4096 = a.w_block;                                     // (1-k)^4096
-  float2 g = make_float2(0.f, 0.f);
-  if (nh >= 1) g = sums[(rb - 1) * kNotchMaxSlots + s];
-  if (nh >= 2) { const float2 o = sums[(rb - 2) * kNotchMaxSlots + s]; g.x += o.x * w4096; g.y += o.y * w4096; }
-  if (nh < 2 && !a.epochs[p.epoch].reset[s] && p.epoch == 0 && floor_b == 0 && a.first_exact) {
-    const float w = nh ? w4096 : 1.0f;
-    g.x += a.state_in->slot[s].est_re * w;
-    g.y += a.state_in->slot[s].est_im * w;
-  }
-  return g;
-}
-
 // One lane = one segment.  The 32 lanes of a warp walk 32 segments in lock step;
 // per tile the warp stages every lane's next 64 raw samples in a private
 // shared-memory row (cooperative 16-byte cp.async copies, contiguous within a
@@ -269,21 +208,6 @@ constexpr int kNWarps = LDVB_NOTCH_WARPS;
 static_assert(kNPitch % 128 == 16 && kNotchN % kNTile == 0 && kNStages >= 2, "row geometry");
 // dynamic shared memory: [input rows: warps x stages x 32 x pitch | table tiles: warps x stages x slots x tile | output tiles]
 constexpr size_t kNotchSmemIn = (size_t)kNWarps * kNStages * 32 * kNPitch + (size_t)kNWarps * kNStages * 4 * kNTile * 8;
-
-template <int FMT>
-__device__ __forceinline__ float2 row_sample(const unsigned char *row, uint32_t idx, float scale) {
-  if (FMT == 0) { uchar2 v = reinterpret_cast<const uchar2 *>(row)[idx];
-    return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
-  if (FMT == 1) { char2 v = reinterpret_cast<const char2 *>(row)[idx];
-    return make_float2((float)(int)v.x, (float)(int)v.y); }
-  if (FMT == 2) { ushort2 v = reinterpret_cast<const ushort2 *>(row)[idx];
-    return make_float2((float)((int)v.x - 32768), (float)((int)v.y - 32768)); }
-  if (FMT == 3) { short2 v = reinterpret_cast<const short2 *>(row)[idx];
-    return make_float2((float)(int)v.x, (float)(int)v.y); }
-  float2 v = reinterpret_cast<const float2 *>(row)[idx];
-  if (FMT == 4 && scale != 1.0f) v = make_float2(fmul(v.x, scale), fmul(v.y, scale));  // x*1 == x
-  return v;
-}
 
 template <int FMT, int NSLOTS>
 __global__ void __launch_bounds__(kNWarps * 32)

@@ -44,10 +44,11 @@ template <int SAMPLER, int TILE> struct RowCfg { static constexpr int kBytes = (
 //   0  cstln_lut<256>::lookup as a gather into the 512 KB cell table in global memory (any constellation);
 //   1  QPSK: symbol and cost follow from the truncated (I, Q) by arithmetic
 //      (tests/test_capi_cpu.py::test_qpsk_table_cells_follow_from_arithmetic checks all 65536 cells of the
-//      host-built table), and the phase error -- glibc atan2f, so it stays a table -- is read from a 128 KB
-//      int16 copy of that column held in SHARED memory: the constellation look-up leaves the L1/L2 path
+//      host-built table), and the phase error -- glibc atan2f, so it stays a table -- is read from a 66 KB
+//      int16 copy of that column (folded over Q) held in SHARED memory: the constellation look-up leaves the L1/L2 path
 //      altogether (round 1, ncu: one lane of every warp-wide gather missed L1, so every symbol waited for L2).
-constexpr int kPe16Bytes = 65536 * 2;
+constexpr int kPe16Bytes = 256 * kPeFoldPitch * 2;   // folded over Q (kernels.h): 66 KB
+static_assert(kPe16Bytes % 16 == 0, "copied 16 bytes at a time");
 #ifndef LDVB_RX_CA
 #define LDVB_RX_CA 0
 #endif
@@ -98,8 +99,19 @@ __device__ __forceinline__ int lds_s16(uint32_t addr) {
 }
 
 // trig16::expi(float) (math.h:104-110): index = (uint16)(int16)(int32)a.
+#ifndef LDVB_RX_TRIG_EVICT_LAST
+#define LDVB_RX_TRIG_EVICT_LAST 1
+#endif
 __device__ __forceinline__ float2 expi(const float2 *__restrict__ trig, float a) {
-  return __ldg(trig + ((uint32_t)f2i_trunc(a) & 0xffffu));
+  const float2 *p = trig + ((uint32_t)f2i_trunc(a) & 0xffffu);
+#if LDVB_RX_TRIG_EVICT_LAST
+  // The table lines around the current carrier phase are the only data of this kernel that L1 should keep.
+  float2 v;
+  asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
 }
 
 // One input sample of cstln_receiver::run()'s inner loop (sdr.h:800-847).
@@ -154,10 +166,11 @@ __device__ __forceinline__ bool rx_sample(const RxParams &p, RxRun &r, float2 cu
     if (SLICER == 1) {
       // QPSK: the cell's symbol and cost follow from the truncated (I, Q); only the phase error is looked up
       // (shared memory: a 2-byte gather, ~3 bank wavefronts for 32 random lanes).
-      const uint32_t ci = __byte_perm((uint32_t)Qi, (uint32_t)Ii, 0x0040) & 0xffffu;   // (Ii & 0xff) << 8 | (Qi & 0xff)
-      pe = lds_s16(s_pe + 2u * ci);
-      symbol = ((Ii < 0) ? 2 : 0) | ((Qi < 0) ? 1 : 0);
       const int aI = abs(Ii), aQ = abs(Qi);
+      // folded column: [I & 0xff][|Q|], pe(I, -Q) = -pe(I, Q)
+      pe = lds_s16(s_pe + 2u * (((uint32_t)Ii & 0xffu) * (uint32_t)kPeFoldPitch + (uint32_t)aQ));
+      if (Qi < 0) pe = -pe;
+      symbol = ((Ii < 0) ? 2 : 0) | ((Qi < 0) ? 1 : 0);
       const int d1 = (aI - 53) * (aI - 53) + (aQ - 53) * (aQ - 53);
       const int d2 = d1 + 212 * min(aI, aQ);
       const int cost = min(d1, 32767) - min(d2, 32767);
@@ -308,7 +321,39 @@ struct RxEmit {
   uint32_t *out;            // the span's region of sym_out
   RxSeamSym *hlog, *tlog;   // seam logs of the span (or null)
   uint32_t n_out, n_tail, n_head, cap;
+  uint32_t w0, w1, w2;      // symbols waiting for the fourth one of their 16-byte group (vec mode)
+  bool vec;                 // out is 16-byte aligned and cap a multiple of 4: symbols leave four at a time
 };
+
+// 16-byte / 4-byte stores that do not allocate in L1 (the symbols are read by a later kernel; in L1 they would
+// only evict the trig16 lines -- ncu, round 2: 139 M store sectors per launch went through L1 next to 322 M
+// table sectors, table hit rate 74 %).
+__device__ __forceinline__ void st_cg(uint4 *p, uint4 v) { __stcg(p, v); }
+__device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
+
+// Symbol `word` goes to position pos of the span's output (owned symbols, then the verification overlap).
+// Each lane writes its own span: one 4-byte store per symbol is a 32-byte sector per lane and instruction;
+// in vec mode the lane keeps three words in registers and writes 16 bytes with the fourth.
+__device__ __forceinline__ void emit_word(RxEmit &e, uint32_t pos, uint32_t word) {
+  if (!e.vec) { if (pos < e.cap) st_cg(e.out + pos, word); return; }
+  const uint32_t r = pos & 3u;
+  if (r == 0) e.w0 = word;
+  else if (r == 1) e.w1 = word;
+  else if (r == 2) e.w2 = word;
+  else if (pos < e.cap) st_cg(reinterpret_cast<uint4 *>(e.out + (pos - 3u)), make_uint4(e.w0, e.w1, e.w2, word));
+}
+// The words of the last, incomplete group.
+__device__ __forceinline__ void emit_flush(RxEmit &e) {
+  if (!e.vec) return;
+  const uint32_t pos = e.n_out + e.n_tail, r = pos & 3u, b = pos - r;
+  if (r > 0 && b < e.cap) st_cg(e.out + b, e.w0);
+  if (r > 1 && b + 1 < e.cap) st_cg(e.out + b + 1, e.w1);
+  if (r > 2 && b + 2 < e.cap) st_cg(e.out + b + 2, e.w2);
+}
+__device__ __forceinline__ void emit_init(RxEmit &e) {
+  e.n_out = e.n_tail = e.n_head = 0; e.w0 = e.w1 = e.w2 = 0;
+  e.vec = ((reinterpret_cast<uintptr_t>(e.out) & 15u) == 0) && ((e.cap & 3u) == 0);
+}
 
 // What a lane does with the symbols of the chunk it is walking.
 //   kWarm   warm-up in front of the span: loops run, nothing is kept
@@ -338,7 +383,7 @@ __device__ __forceinline__ void rx_tile(const RxParams &p, RxRun &r, const float
     else em = rx_sample<SAMPLER, SLICER>(p, r, cur, nxt, reinterpret_cast<const float2 *>(rp) + n, s_pe, word, mu_e);
     if (MODE != kWarm && em) {
       if (MODE == kOwned || MODE == kHead) {
-        if (e.n_out < e.cap) e.out[e.n_out] = word;
+        emit_word(e, e.n_out, word);
         ++e.n_out;
         if (MODE == kHead && e.hlog && e.n_head < kRxSeamLog) {
           e.hlog[e.n_head].t = t0 + (float)n + mu_e;
@@ -348,7 +393,7 @@ __device__ __forceinline__ void rx_tile(const RxParams &p, RxRun &r, const float
       } else {
         // Verification overlap: stored right after the owned symbols so that the
         // stitcher can extend this span by one symbol when needed.
-        if (e.n_out + e.n_tail < e.cap) e.out[e.n_out + e.n_tail] = word;
+        emit_word(e, e.n_out + e.n_tail, word);
         if (e.tlog && e.n_tail < kRxSeamLog) {
           e.tlog[e.n_tail].t = t0 + (float)n + mu_e;
           e.tlog[e.n_tail].sym = word >> 16;
@@ -510,8 +555,8 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
   e.out = a.sym_out + (size_t)span * a.span_cap;
   e.hlog = (log_head_span && have_span) ? a.head_log + (size_t)span * kRxSeamLog : nullptr;
   e.tlog = (a.tail_log && have_span) ? a.tail_log + (size_t)span * kRxSeamLog : nullptr;
-  e.n_out = e.n_tail = e.n_head = 0;
   e.cap = a.span_cap;
+  emit_init(e);
 
   for (int s = 0; s < kStages - 1; ++s) { if ((uint32_t)s < total_tiles) issue(s); else cp_async_commit(); }
   for (uint32_t tile = 0; tile < total_tiles; ++tile) {
@@ -540,6 +585,7 @@ __device__ void rx_warp(const RxArgs &a, const uint32_t *span_list, uint32_t nli
     __syncwarp();  // every lane is done with this stage before it is refilled
   }
   if (have_span) {
+    emit_flush(e);
     RxSpanInfo inf;
     inf.n_out = e.n_out; inf.n_tail = e.n_tail; inf.n_head_logged = e.n_head; inf.pad = 0;
     a.info[span] = inf;
@@ -590,7 +636,8 @@ __device__ void rx_serial(const RxArgs &a, unsigned char *bufs, uint32_t s_pe) {
   if (!a.first_exact) rx_warm_state<SAMPLER>(a, r, c0);
   RxEmit e;
   e.out = a.sym_out; e.hlog = nullptr; e.tlog = nullptr;
-  e.n_out = e.n_tail = e.n_head = 0; e.cap = a.span_cap;
+  e.cap = a.span_cap;
+  emit_init(e);
   constexpr int kPieces = (kRxChunk + (SAMPLER == 2 ? 6 : 2)) * 8 / 16;
   auto issue = [&](uint64_t c) {
     const unsigned char *src = reinterpret_cast<const unsigned char *>(a.x + c * kRxChunk);
@@ -615,6 +662,7 @@ __device__ void rx_serial(const RxArgs &a, unsigned char *bufs, uint32_t s_pe) {
     __syncwarp();
   }
   if (lane == 0) {
+    emit_flush(e);
     RxSpanInfo inf;
     inf.n_out = e.n_out; inf.n_tail = 0; inf.n_head_logged = 0; inf.pad = 0;
     a.info[0] = inf;
@@ -851,7 +899,7 @@ size_t rx_row_bytes(int sampler) { return sampler == 2 ? RowCfg<2, kTile>::kByte
 // LDVB_RX_WARPS warps (default 12: 128 KB of table + 60 KB of rows; measured 1.60 ms against 2.35 ms with 16 warps, whose
 // 208 KB of shared memory leave the trig16 gathers only 28 KB of L1); slicer 0: 4 warps, three CTAs per SM.
 int rx_warps_per_cta(int slicer) {
-  static const int w1 = env_int("LDVB_RX_WARPS", 12, 1, 19);
+  static const int w1 = env_int("LDVB_RX_WARPS", 12, 1, 20);
   return slicer == 1 ? w1 : 4;
 }
 

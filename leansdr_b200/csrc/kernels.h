@@ -94,6 +94,29 @@ cudaError_t launch_notch_verify(const NotchApplyArgs &a, uint32_t *nfail, cudaSt
 cudaError_t launch_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist,
                                const float2 *guess, cudaStream_t st);
 
+// Fused auto_notch + fir_filter (k_notchfir.cu): the notch chain of a CTA's 32 segments is walked by one warp,
+// the data-parallel work around it by eight others, and -- when the low-pass that follows has decimation 1 and at
+// most kFirFuseMaxTaps taps -- the FIR is applied on the store path, so that the notched stream never reaches HBM.
+constexpr int kFirFuseMaxTaps = 32;
+constexpr int kNotchEdge = 2 * kFirFuseMaxTaps;   // float2 per segment: [first N-1 | (at kFirFuseMaxTaps) last N] notched samples
+struct NotchFirArgs {
+  NotchApplyArgs n;             // n.out is used only when fir_n == 0 (plain notch)
+  int fir_n;                    // 0: no FIR
+  int real_taps;                // every tap has a zero imaginary part (no retune in force)
+  const float2 *taps;           // [fir_n] shifted taps (dsp.h:270-280)
+  float2 *y;                    // y[k], k = 0 .. carry + nblocks*4096 - fir_n - 1 (dsp.h:250-256)
+  uint32_t carry;               // notched samples carried in front of the batch: 0 (first batch) or fir_n
+  const float2 *carry_in;       // [carry]
+  float2 *carry_out;            // [fir_n] the last fir_n notched samples of this batch (may alias carry_in)
+  float2 *edge;                 // [nsegs][kNotchEdge]
+  const uint64_t *dump_blocks;  // [ndump] sorted: blocks whose notched samples cnr_fft / spectrum will read
+  int ndump;
+  float2 *dump;                 // [ndump][4096]
+};
+cudaError_t launch_notch_fir(const NotchFirArgs &a, const uint32_t *seg_list, uint32_t nlist, const float2 *guess, cudaStream_t st);
+// The fir_n - 1 outputs across every segment boundary (and the batch start), then the new carry.
+cudaError_t launch_fir_edges(const NotchFirArgs &a, cudaStream_t st);
+
 // ------------------------------------------------------- K8 cnr_fft / spectrum
 // [carry | rest]: `carry` holds cf32 samples (converted, not rotated) kept from the previous
 // batch, `rest` is the batch in its input format starting at element rest_off.
@@ -124,6 +147,7 @@ cudaError_t launch_meas_save(const MeasSrc &src, uint64_t start, uint32_t count,
 // ------------------------------------------------------------------ K3 receiver
 struct CstlnCellDev { int16_t cost, symbol, phase_error, pad; };
 
+constexpr int kPeFoldPitch = 129;   // |Q| = 0..128
 struct RxParams {
   const CstlnCellDev *cstln;   // [65536]
   const float2 *trig;          // [65536]
@@ -139,7 +163,8 @@ struct RxParams {
   // float fields of RxState (phase: u16, freqw and the limits: integers below 2^24, hist: u8) --
   // every value is exactly representable, so carry / warm-up / seam plumbing is shared.
   const uint32_t *hs_polar; const uint16_t *hs_rect; const uint16_t *hs_sincos;
-  const int16_t *pe16;       // slicer 1: phase_error of every cell, same index as cstln (copied to shared memory)
+  const int16_t *pe16;       // slicer 1: phase_error column folded over Q, [I & 0xff][|Q|] with pitch kPeFoldPitch
+                             // (pe(I, -Q) == -pe(I, Q), verified at create time); copied to shared memory
   int slicer;                // 0: cell table gather (any constellation); 1: QPSK arithmetic + pe16 (k_rx.cu)
   long long hs_freq_beta;    // (signed long)(0.0012*256*65536/omega*pll_adjustment), sdr.h:1002
 };

@@ -115,6 +115,9 @@ struct ldvb_handle {
   std::map<int, uint32_t> notch_table_of_bin;
   DevBuf d_notch_tables; uint32_t notch_tables_used = 0, notch_tables_cap = 0;
   DevBuf d_notch_guess, d_notch_weights, d_notch_list;
+  DevBuf d_notch_edge, d_notch_dump, d_notch_dumpblocks;   // k_notchfir.cu: segment edges, telemetry blocks
+  bool notch_v2 = false, notch_fused = false;
+  uint64_t notch_target_segs = 0;
   DevBuf d_notch_state, d_notch_epochs, d_notch_entry, d_notch_exit, d_notch_exact, d_notch_bins, d_notch_blocks;
   uint32_t rot_index = 0;
   RxState rx_state;            // host mirror of the exact/carried receiver state
@@ -551,7 +554,7 @@ int ldvb_destroy(ldvb_handle *h) {
                     &h->d_rotperm, &h->d_twiddle, &h->s_raw.buf, &h->s_notched.buf, &h->s_pp.buf, &h->s_sym.buf,
                     &h->s_bytes.buf, &h->s_mpeg.buf, &h->d_rts, &h->d_rsflags, &h->d_ts, &h->d_scratch,
                     &h->d_badwords, &h->d_rs204, &h->d_notch_tables, &h->d_notch_state, &h->d_notch_epochs,
-                    &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
+                    &h->d_notch_edge, &h->d_notch_dump, &h->d_notch_dumpblocks, &h->d_notch_entry, &h->d_notch_exit, &h->d_notch_guess, &h->d_notch_weights, &h->d_notch_list, &h->d_notch_exact, &h->d_notch_bins, &h->d_notch_blocks,
                     &h->d_rx_state, &h->d_rx_info, &h->d_rx_end, &h->d_rx_head, &h->d_rx_tail, &h->d_rx_seams,
                     &h->d_rx_spans, &h->d_rx_off, &h->d_rx_skip, &h->d_rx_rot, &h->d_rx_meas, &h->d_rx_measn,
                     &h->d_rx_forced, &h->d_rx_begin, &h->d_rx_power, &h->d_rx_settled, &h->d_deconv_carry, &h->d_vit_pred, &h->d_vit_us, &h->d_vit_maps, &h->d_vit_shifts, &h->d_vit_state, &h->d_vit_ctl, &h->d_vit_entry, &h->d_vit_exit, &h->d_vit_aux, &h->d_sync_state, &h->d_sync_res, &h->d_counts,
@@ -693,11 +696,29 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     const char *e = getenv("LDVB_RX_SLICER");
     const bool want = !(e && atoi(e) == 0);
     if (want && c.constellation == LDVB_CSTLN_QPSK && !c.hard_metric && !c.hs) {
-      std::vector<int16_t> pe(h->cst.cells.size());
-      for (size_t i = 0; i < pe.size(); ++i) pe[i] = h->cst.cells[i].phase_error;
-      if (upload(h->d_pe16, pe.data(), pe.size() * 2) != cudaSuccess) return bail(LDVB_ECUDA, "pe16 upload");
-      h->rxp.pe16 = h->d_pe16.as<int16_t>();
-      h->rxp.slicer = 1;
+      // Folded over Q: phase_error(I, -Q) == -phase_error(I, Q) holds for every cell of the host-built table
+      // (the I reflection does not: 18 cells differ by one unit), so the column shrinks to 256 x 129 entries
+      // [I & 0xff][|Q|], 66 KB instead of 128 KB of shared memory -- room for more resident warps.  The
+      // identity is CHECKED here over all 65536 cells; if it ever failed the generic cell-table gather stays.
+      std::vector<int16_t> pe((size_t)256 * kPeFoldPitch, 0);
+      for (int ib = 0; ib < 256; ++ib)
+        for (int q = 0; q <= 128; ++q) {
+          const int qb = (q == 128) ? 0x80 : q;                    // |Q| = 128 only exists as Q = -128
+          const int v = h->cst.cells[(size_t)ib * 256 + qb].phase_error;
+          pe[(size_t)ib * kPeFoldPitch + q] = (int16_t)((q == 128) ? -v : v);
+        }
+      bool folds = true;
+      for (int ib = 0; ib < 256 && folds; ++ib)
+        for (int qb = 0; qb < 256; ++qb) {
+          const int Q = (int)(int8_t)qb, aq = Q < 0 ? -Q : Q;
+          const int v = pe[(size_t)ib * kPeFoldPitch + aq];
+          if ((Q < 0 ? -v : v) != h->cst.cells[(size_t)ib * 256 + qb].phase_error) { folds = false; break; }
+        }
+      if (folds) {
+        if (upload(h->d_pe16, pe.data(), pe.size() * 2) != cudaSuccess) return bail(LDVB_ECUDA, "pe16 upload");
+        h->rxp.pe16 = h->d_pe16.as<int16_t>();
+        h->rxp.slicer = 1;
+      }
     }
   }
   if (c.hs) {
@@ -746,7 +767,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     const uint64_t nch = pp_max / kRxChunk + 1;
     const uint32_t smin = c.span_chunks ? c.span_chunks : 4;
     nsp = (uint32_t)(nch / smin + 2);
-    const double cap_min = (smin + kRxVerifyChunks + 1) * kRxChunk * sym_per_sample + 64;
+    const double cap_min = (smin + kRxVerifyChunks + 1) * kRxChunk * sym_per_sample + 64 + 4;   // (+4: span_cap is rounded up to 16-byte groups)
     span_bytes = (size_t)(std::max((double)nsp * cap_min, 1.25 * sym_max) * 4) + 4096;
   }
   h->rx_max_spans = nsp;
@@ -809,6 +830,17 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     // Table 0 is all zeros: slots that never detected (bin -1) use it (sdr.h:57-63).
     cudaMemset(h->d_notch_tables.p, 0, (size_t)kNotchN * 8);
     h->notch_tables_used = 1;
+    // Kernel choice.  Default: the lane-per-segment kernel (k_notch.cu) followed by k_frontend.  LDVB_NOTCH_V2=1
+    // selects the warp-specialised kernel of k_notchfir.cu, which (unless LDVB_NOTCH_FUSE=0) applies the low-pass on
+    // its store path so that the notched stream never reaches HBM (decimation 1, <= kFirFuseMaxTaps taps, no
+    // rotator).  It is bit-exact (the whole GPU suite passes with it) and halves the DRAM traffic of the two
+    // stages, but measured 3.1 ms against 1.0 + 0.3 ms per 128 M samples (profiles/r02_*): ~790 instructions per
+    // warp and tile step where the arithmetic needs ~300, so it stays opt-in.  Time-sharded handles always run
+    // the default path.
+    const char *e2 = getenv("LDVB_NOTCH_V2"), *ef = getenv("LDVB_NOTCH_FUSE");
+    h->notch_v2 = (e2 && atoi(e2) != 0);
+    h->notch_fused = h->notch_v2 && !(ef && atoi(ef) == 0) && h->use_fir && h->decim == 1 && !h->use_rot &&
+                     h->fir_n >= 2 && h->fir_n <= kFirFuseMaxTaps;
   }
   reset_carry(h);
   *out = h;
@@ -867,6 +899,9 @@ namespace {
 
 int meas_finish(ldvb_handle *h);
 int meas_host_reserve(ldvb_handle *h, size_t need, float **dst);
+int fir_retune(ldvb_handle *h, int *real_taps);
+void meas_plan(ldvb_handle::MeasUnit &u, uint64_t abs0, uint64_t avail, std::vector<uint64_t> &points);
+int meas_launch(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, const std::vector<uint64_t> &points);
 
 
 // ------------------------------------------------------------------------- notch
@@ -902,7 +937,7 @@ int notch_table_for_bin(ldvb_handle *h, int bin, uint32_t *index) {
 // Verifies entry(j) == exit(j-1) for every segment (device-side count first) and re-runs the
 // segments that did not merge, all of them in one launch per round.  exitv receives the exit
 // states (at least the last one).
-int notch_verify_repair(ldvb_handle *h, NotchApplyArgs &a, std::vector<float2> &exitv_out) {
+int notch_verify_repair(ldvb_handle *h, NotchApplyArgs &a, std::vector<float2> &exitv_out, NotchFirArgs *fa = nullptr) {
   const ldvb_config &c = h->cfg;
   // Device-side check first: the host only reads a counter and the last exit state.
   CK(cudaMemsetAsync(h->d_counts.p, 0, 4, h->st));
@@ -933,7 +968,8 @@ int notch_verify_repair(ldvb_handle *h, NotchApplyArgs &a, std::vector<float2> &
     }
     if (todo.empty()) break;
     CK(cudaMemcpyAsync(h->d_notch_list.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, h->st));
-    KL("notch_apply", launch_notch_apply(a, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st));
+    if (fa) { fa->n = a; KL("notch_fir", launch_notch_fir(*fa, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st)); }
+    else KL("notch_apply", launch_notch_apply(a, h->d_notch_list.as<uint32_t>(), (uint32_t)todo.size(), nullptr, h->st));
     h->meas.notch_repaired += (uint32_t)todo.size();
     for (uint32_t j : todo)   // by construction the repaired segment entered with exit(j-1)
       memcpy(&entry[(size_t)j * kNotchMaxSlots], &exitv[(size_t)(j - 1) * kNotchMaxSlots], 8 * kNotchMaxSlots);
@@ -948,7 +984,10 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   *consumed = nblocks * kNotchN;
   h->s_notched.fresh = 0;
   if (!nblocks) return LDVB_OK;
-  if (h->s_notched.count + nblocks * kNotchN > h->s_notched.cap) return fail(h, LDVB_EOVERFLOW, "notched stream overflow");
+  // v2: the warp-specialised kernel (k_notchfir.cu); fused: the low-pass is applied on its store path and the
+  // notched stream stays on the chip (s_notched only holds the fir_n samples carried between batches).
+  const bool v2 = h->notch_v2, fused = h->notch_fused;
+  if (!fused && h->s_notched.count + nblocks * kNotchN > h->s_notched.cap) return fail(h, LDVB_EOVERFLOW, "notched stream overflow");
   const int fmt = c.input_format;
   // Detect points (sdr.h:64-71): phase advances by 4096 before the test.
   std::vector<uint64_t> dblocks;
@@ -1026,6 +1065,16 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // estimate the float trajectories merge bit for bit after 4..10 Ki samples
   // (0.998^n decay below one ulp), measured in DESIGN.md.
   a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 32767) / 32768));
+  if (v2) {
+    // One CTA = 32 segments; as many segments as fit in one wave (two CTAs per SM with one slot, else one): the
+    // chain warp needs ~8 cycles per sample, so longer segments cost little and dilute the warm-up blocks.
+    if (!h->notch_target_segs) {
+      int dev = 0, sms = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      h->notch_target_segs = (uint64_t)32 * sms * (c.anf == 1 ? 2 : 1);
+    }
+    a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + h->notch_target_segs - 1) / h->notch_target_segs));
+  }
   a.warm_blocks = 2;   // exact blocks after the parallel weighted-sum guess (merge: median 1 Ki, max ~3 Ki samples)
   {  // tuning knobs (experiments): LDVB_NOTCH_SEG = blocks per segment, LDVB_NOTCH_WARM = warm-up blocks
     static const int seg_env = [] { const char *e = getenv("LDVB_NOTCH_SEG"); return e ? atoi(e) : 0; }();
@@ -1039,16 +1088,87 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   a.seg_exit = h->d_notch_exit.as<float2>();
   a.seg_exact = h->d_notch_exact.as<uint8_t>();
   KL("notch_guess", launch_notch_guess(a, h->d_notch_guess.as<float2>(), h->d_notch_weights.as<float>(), h->st));
-  KL("notch_apply", launch_notch_apply(a, nullptr, 0, h->d_notch_guess.as<float2>(), h->st));
+  NotchFirArgs fa;
+  memset(&fa, 0, sizeof fa);
+  uint64_t ycount = 0;
+  std::vector<uint64_t> pts_cnr, pts_spec;
+  if (v2) {
+    if (fused) {
+      int real = 1;
+      { int rcr = fir_retune(h, &real); if (rcr) return rcr; }
+      const uint64_t carry = h->s_notched.count;                       // 0 (first batch) or fir_n
+      if (carry != 0 && carry != (uint64_t)h->fir_n) return fail(h, LDVB_ESTATE, "notched carry");
+      ycount = carry + nblocks * kNotchN - (uint64_t)h->fir_n;         // dsp.h:246-247, decimation 1
+      if (h->s_pp.count + ycount > h->s_pp.cap) return fail(h, LDVB_EOVERFLOW, "preprocessed stream overflow");
+      if ((size_t)a.nsegs * kNotchEdge * 8 > h->d_notch_edge.bytes) {
+        h->d_notch_edge.release();
+        CK(h->d_notch_edge.alloc((size_t)a.nsegs * kNotchEdge * 8 + 65536));
+      }
+      fa.fir_n = h->fir_n; fa.real_taps = real; fa.taps = h->d_taps.as<float2>();
+      fa.y = reinterpret_cast<float2 *>(h->s_pp.at(h->s_pp.count));
+      fa.carry = (uint32_t)carry;
+      fa.carry_in = reinterpret_cast<const float2 *>(h->s_notched.at(0));
+      fa.carry_out = reinterpret_cast<float2 *>(h->s_notched.at(0));
+      fa.edge = h->d_notch_edge.as<float2>();
+      // cnr_fft / spectrum look at the notched stream (leandvb.cc:296-343): the blocks they will measure are
+      // known in advance (sdr.h:1294-1302, 1362-1370) and are the only ones written out.
+      if (h->m_cnr.on || h->m_spec.on) {
+        if (h->meas_carry_count) return fail(h, LDVB_ESTATE, "telemetry carry in fused mode");
+        const uint64_t abs0 = h->meas_abs_next;
+        if (h->m_cnr.on) meas_plan(h->m_cnr, abs0, nblocks * kNotchN, pts_cnr);
+        if (h->m_spec.on) meas_plan(h->m_spec, abs0, nblocks * kNotchN, pts_spec);
+        std::vector<uint64_t> blocks;
+        for (uint64_t pnt : pts_cnr) blocks.push_back(pnt / kNotchN);
+        for (uint64_t pnt : pts_spec) blocks.push_back(pnt / kNotchN);
+        std::sort(blocks.begin(), blocks.end());
+        blocks.erase(std::unique(blocks.begin(), blocks.end()), blocks.end());
+        if (!blocks.empty()) {
+          if (blocks.size() * 8 > h->d_notch_dumpblocks.bytes) { h->d_notch_dumpblocks.release(); CK(h->d_notch_dumpblocks.alloc(blocks.size() * 8 + 1024)); }
+          if (blocks.size() * kNotchN * 8 > h->d_notch_dump.bytes) { h->d_notch_dump.release(); CK(h->d_notch_dump.alloc((blocks.size() + 16) * kNotchN * 8)); }
+          CK(cudaMemcpyAsync(h->d_notch_dumpblocks.p, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice, h->st));
+          fa.dump_blocks = h->d_notch_dumpblocks.as<uint64_t>(); fa.ndump = (int)blocks.size(); fa.dump = h->d_notch_dump.as<float2>();
+          auto remap = [&](std::vector<uint64_t> &pts) {
+            for (uint64_t &pnt : pts) {
+              const size_t slot = std::lower_bound(blocks.begin(), blocks.end(), pnt / kNotchN) - blocks.begin();
+              pnt = slot * kNotchN + pnt % kNotchN;
+            }
+          };
+          remap(pts_cnr); remap(pts_spec);
+        }
+        h->meas_abs_next = abs0 + nblocks * kNotchN;
+      }
+    }
+    fa.n = a;
+    KL("notch_fir", launch_notch_fir(fa, nullptr, 0, h->d_notch_guess.as<float2>(), h->st));
+  } else {
+    KL("notch_apply", launch_notch_apply(a, nullptr, 0, h->d_notch_guess.as<float2>(), h->st));
+  }
   // Verify entry(j) == exit(j-1) bit for bit.  Segments whose warm-up had not merged
   // with the true trajectory are re-run exactly from their predecessor's exit state,
   // all of them in one launch per round (a segment whose predecessor is also being
   // repaired waits for the next round).
   std::vector<float2> exitv;
-  { int rcv = notch_verify_repair(h, a, exitv); if (rcv) return rcv; }
+  { int rcv = notch_verify_repair(h, a, exitv, v2 ? &fa : nullptr); if (rcv) return rcv; }
   for (int s = 0; s < c.anf; ++s) {
     h->notch.slot[s].est_re = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].x;
     h->notch.slot[s].est_im = exitv[(size_t)(a.nsegs - 1) * kNotchMaxSlots + s].y;
+  }
+  if (fused) {
+    KL("fir_edges", launch_fir_edges(fa, h->st));
+    h->s_notched.count = (uint64_t)h->fir_n;
+    h->s_notched.fresh = 0;
+    h->s_pp.count += ycount;
+    h->s_pp.fresh = ycount;
+    if (!pts_cnr.empty() || !pts_spec.empty()) {
+      MeasSrc msrc;
+      memset(&msrc, 0, sizeof msrc);
+      msrc.rest.head = fa.dump; msrc.rest.head_count = (uint64_t)fa.ndump * kNotchN;
+      msrc.fmt = 5; msrc.scale = 1.0f;
+      int rcm;
+      if (!pts_cnr.empty() && (rcm = meas_launch(h, h->m_cnr, msrc, pts_cnr))) return rcm;
+      if (!pts_spec.empty() && (rcm = meas_launch(h, h->m_spec, msrc, pts_spec))) return rcm;
+    }
+    return LDVB_OK;
   }
   h->s_notched.count += nblocks * kNotchN;
   h->s_notched.fresh = nblocks * kNotchN;
@@ -1056,6 +1176,25 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
 }
 
 // --------------------------------------------------------------------- front end
+
+// fir_filter retune from the demodulator's freq_tap (dsp.h:236-244), sampled once per batch (the reference
+// samples it once per run() call).  *real_taps: every shifted tap has a zero imaginary part.
+int fir_retune(ldvb_handle *h, int *real_taps) {
+  if (h->use_fir) {
+    const float new_freq = h->rx_state.freq_tap * h->fir_tap_mult;
+    if (fabsf(h->fir_current_freq - new_freq) > h->fir_tol) {
+      h->fir_shifted = shift_taps(h->fir_coeffs, new_freq);
+      h->fir_current_freq = new_freq;
+      CK(cudaMemcpyAsync(h->d_taps.p, h->fir_shifted.data(), h->fir_shifted.size() * 4, cudaMemcpyHostToDevice, h->st));
+      CK(cudaStreamSynchronize(h->st));
+    }
+  }
+  if (real_taps) {
+    *real_taps = 1;
+    for (int i = 0; i < h->fir_n; ++i) if (h->fir_shifted[2 * i + 1] != 0.0f) *real_taps = 0;
+  }
+  return LDVB_OK;
+}
 
 int run_frontend(ldvb_handle *h, const RawSrc &src, int fmt, uint64_t avail, uint64_t *consumed) {
   const ldvb_config &c = h->cfg;
@@ -1068,17 +1207,7 @@ int run_frontend(ldvb_handle *h, const RawSrc &src, int fmt, uint64_t avail, uin
   h->s_pp.fresh = 0;
   if (!count) return LDVB_OK;
   if (h->s_pp.count + count > h->s_pp.cap) return fail(h, LDVB_EOVERFLOW, "preprocessed stream overflow");
-  if (h->use_fir) {
-    // fir_filter retune from the demodulator's freq_tap (dsp.h:236-244), sampled
-    // once per batch (the reference samples it once per run() call).
-    const float new_freq = h->rx_state.freq_tap * h->fir_tap_mult;
-    if (fabsf(h->fir_current_freq - new_freq) > h->fir_tol) {
-      h->fir_shifted = shift_taps(h->fir_coeffs, new_freq);
-      h->fir_current_freq = new_freq;
-      CK(cudaMemcpyAsync(h->d_taps.p, h->fir_shifted.data(), h->fir_shifted.size() * 4, cudaMemcpyHostToDevice, h->st));
-      CK(cudaStreamSynchronize(h->st));
-    }
-  }
+  { int rcr = fir_retune(h, nullptr); if (rcr) return rcr; }
   FrontendArgs a;
   memset(&a, 0, sizeof a);
   a.src = src; a.fmt = fmt; a.scale = c.float_scale;
@@ -1115,7 +1244,7 @@ int rx_fast_launch(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, uint64_t nchunks
     a.span_chunks = S;
     a.warm_chunks = W;
     a.nspans = (uint32_t)((nchunks + S - 1) / S);
-    a.span_cap = (uint32_t)((S + kRxVerifyChunks + 1) * kRxChunk * h->rx_sym_per_sample) + 64;
+    a.span_cap = ((uint32_t)((S + kRxVerifyChunks + 1) * kRxChunk * h->rx_sym_per_sample) + 64 + 3u) & ~3u;   // 16-byte groups (k_rx: emit_word)
     if (a.nspans > h->rx_max_spans || (uint64_t)a.nspans * a.span_cap * 4 > h->d_rx_spans.bytes)
       return fail(h, LDVB_EOVERFLOW, "receiver span buffers too small for this batch");
     a.sym_out = h->d_rx_spans.as<uint32_t>();
@@ -1975,13 +2104,12 @@ int meas_host_reserve(ldvb_handle *h, size_t need, float **dst) {
   return LDVB_OK;
 }
 
-int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, uint64_t abs0, uint64_t avail) {
-  if (!u.on) return LDVB_OK;
+// Measured blocks of one unit over the samples [abs0, abs0 + avail): start positions relative to abs0.
+// Phase advances by n per block, a block is measured when it reaches the decimation (sdr.h:1294-1302,
+// 1362-1370).  Closed form instead of a walk over every block.
+void meas_plan(ldvb_handle::MeasUnit &u, uint64_t abs0, uint64_t avail, std::vector<uint64_t> &points) {
   const int64_t n = (int64_t)1 << u.logn;
   const uint64_t abs_end = abs0 + avail;
-  // Measured blocks: phase advances by n per block, a block is measured when it reaches the
-  // decimation (sdr.h:1294-1302, 1362-1370).  Closed form instead of a walk over every block.
-  std::vector<uint64_t> points;
   while (u.pos + (uint64_t)n <= abs_end) {
     int64_t k = (u.decimation - u.phase + n - 1) / n;
     if (k < 1) k = 1;
@@ -1991,6 +2119,10 @@ int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, 
     u.pos += (uint64_t)k * (uint64_t)n;
     points.push_back(u.pos - (uint64_t)n - abs0);
   }
+}
+
+int meas_launch(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, const std::vector<uint64_t> &points) {
+  const int64_t n = (int64_t)1 << u.logn;
   const bool is_cnr = u.bandwidth > 0;
   // do_cnr (sdr.h:1306-1308, 1322): centre bin from freq_tap as of the start of the batch
   const float tap_multiplier = (float)(1.0 / h->decim);          // leandvb.cc:514
@@ -2020,6 +2152,13 @@ int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, 
     h->meas_pending.push_back({is_cnr, np, (int)n, (size_t)(dst - h->meas_host)});
   }
   return LDVB_OK;
+}
+
+int run_meas_unit(ldvb_handle *h, ldvb_handle::MeasUnit &u, const MeasSrc &src, uint64_t abs0, uint64_t avail) {
+  if (!u.on) return LDVB_OK;
+  std::vector<uint64_t> points;
+  meas_plan(u, abs0, avail, points);
+  return meas_launch(h, u, src, points);
 }
 
 // cnr_fft and spectrum on the new samples of this batch: `rest` at element rest_off holds
@@ -2089,6 +2228,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
   uint64_t raw_consumed = 0;
   if (c.anf) {
     if ((rc = run_notch(h, src, avail, &raw_consumed))) return rc;
+    if (!h->notch_fused) {   // (fused: run_notch produced the preprocessed stream and the telemetry)
     {   // cnr_fft / spectrum read the notched stream (leandvb.cc:296-343); the rotator is applied on load
       RawSrc fresh;
       fresh.head = h->s_notched.at(0); fresh.head_count = h->s_notched.count; fresh.main = nullptr; fresh.c0 = 0;
@@ -2107,6 +2247,7 @@ int run_chain(ldvb_handle *h, const void *src_dev, bool src_is_user_dev, uint64_
       if (k) CK(cudaMemcpyAsync(h->s_pp.at(h->s_pp.count), h->s_notched.at(0), k * 8, cudaMemcpyDeviceToDevice, h->st));
       h->s_pp.count += k; h->s_pp.fresh = k;
       h->s_notched.count = 0;
+    }
     }
   } else {
     if ((rc = run_meas(h, src, c0, c.input_format, n))) return rc;
