@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LDVB_ABI_VERSION 2
+#define LDVB_ABI_VERSION 3
 
 /* ------------------------------------------------------------ error codes */
 enum {
@@ -151,6 +151,12 @@ typedef struct ldvb_config {
   int32_t  settle_chunks;    /* FAST: chunks of the serial AGC settling pass (0 = 512, -1 = never)  */
   int32_t  seam_mode;        /* FAST: 0 = strict seams (equality in the overlap, else exact re-run),
                                 1 = tolerant (<= 1/16 mismatching hard decisions)                  */
+  /* ---- ABI 3 ---- */
+  int32_t  async_push;       /* 1: ldvb_push returns as soon as the samples have left the caller's buffer;
+                                the chain runs on a thread of the handle and the packets reach ldvb_pull
+                                when they are done (ldvb_flush waits for them).  Keeps the copy engine busy
+                                across push calls.  0 (default): push returns with its packets ready.  */
+  int32_t  reserved0;
 } ldvb_config;
 
 typedef struct ldvb_handle ldvb_handle;
@@ -238,6 +244,11 @@ int         ldvb_abi_version(void);
 int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n_samples);
 int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets,
 	      size_t *n_packets);
+
+/* Waits until everything pushed so far has been processed (async_push) and
+ * reports an error of the background chain, if any.  A no-op otherwise.  Every
+ * entry point except ldvb_push / ldvb_pull does this implicitly. */
+int ldvb_flush(ldvb_handle *h);
 
 /* Page-locks a host buffer the caller owns, once, so that every later
  * ldvb_push from inside it is a direct DMA transfer.  Meant for the reference's

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LDVB_LIB") or os.path.join(_HERE, "libleandvb_b200.so")   # LDVB_LIB: experiment builds only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FMT = {"u8": 0, "s8": 1, "u16": 2, "s16": 3, "f32": 4}
 FMT_DTYPE = {"u8": np.uint8, "s8": np.int8, "u16": np.uint16, "s16": np.int16, "f32": np.float32}
 CSTLN = {"BPSK": 0, "QPSK": 1, "8PSK": 2, "16APSK": 3, "32APSK": 4, "64APSKe": 5,
@@ -48,7 +48,7 @@ class Config(C.Structure):
         ("rx_mode", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_uint64),
         ("span_chunks", C.c_uint32), ("warmup_chunks", C.c_uint32), ("keep_taps", C.c_int32),
         ("push_sub_batch", C.c_int32), ("cnr", C.c_int32), ("spectrum", C.c_int32), ("vber", C.c_int32), ("hs", C.c_int32), ("vit_segments", C.c_int32), ("vit_warm_chunks", C.c_int32),
-        ("settle_chunks", C.c_int32), ("seam_mode", C.c_int32),
+        ("settle_chunks", C.c_int32), ("seam_mode", C.c_int32), ("async_push", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -70,7 +70,7 @@ class Meas(C.Structure):
 
 EXPORTS = [
     "ldvb_abi_version", "ldvb_strerror", "ldvb_last_error", "ldvb_config_default", "ldvb_create",
-    "ldvb_destroy", "ldvb_push", "ldvb_pull", "ldvb_host_register", "ldvb_host_unregister", "ldvb_process_device", "ldvb_get_meas", "ldvb_tap",
+    "ldvb_destroy", "ldvb_push", "ldvb_pull", "ldvb_flush", "ldvb_host_register", "ldvb_host_unregister", "ldvb_process_device", "ldvb_get_meas", "ldvb_tap",
     "ldvb_table", "ldvb_host_table", "ldvb_state_size", "ldvb_get_state", "ldvb_set_state", "ldvb_get_rx_state",
     "ldvb_set_rx_state", "ldvb_fir_cf32", "ldvb_deint_rs", "ldvb_rs_decode",
     "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
@@ -113,6 +113,7 @@ def load():
     L.ldvb_destroy.argtypes = [vp]
     L.ldvb_push.argtypes = [vp, vp, sz]
     L.ldvb_pull.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.ldvb_flush.argtypes = [vp]
     L.ldvb_host_register.argtypes = [vp, sz]
     L.ldvb_host_unregister.argtypes = [vp]
     L.ldvb_process_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
@@ -160,7 +161,7 @@ def default_config(**kw) -> Config:
             cfg.sampler = SAMPLER[v] if isinstance(v, str) else v
         elif k == "sub_batch":
             cfg.push_sub_batch = int(v)
-        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps", "vber", "hs"):
+        elif k in ("resample", "viterbi", "hard_metric", "fastlock", "allow_drift", "keep_taps", "vber", "hs", "async_push"):
             setattr(cfg, k, int(v))
         else:
             setattr(cfg, k, v)
@@ -235,7 +236,12 @@ class Receiver:
         self._ck(self.L.ldvb_pull(self.h, C.c_void_p(host_ptr), cap_packets, C.byref(n)), "ldvb_pull")
         return n.value
 
+    def flush(self) -> None:
+        """Waits for everything pushed so far (async_push); a no-op otherwise."""
+        self._ck(self.L.ldvb_flush(self.h), "ldvb_flush")
+
     def pull_all(self) -> np.ndarray:
+        self.flush()
         parts = []
         while True:
             p = self.pull(1 << 16)

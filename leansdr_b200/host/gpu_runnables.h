@@ -57,7 +57,11 @@ struct gpu_dvbs_receiver : runnable {
     vber_out = opt_writer(_vber_out);
     cnr_out = opt_writer(_cnr_out);
     spectrum_out = _spectrum_out ? new pipewriter<float[1024]>(*_spectrum_out) : NULL;
-    int rc = ldvb_create(&cfg, &handle);
+    // async_push: run() returns as soon as the samples have left the pipebuf, the chain works on the
+    // previous batch while file_reader refills the pipe; packets are drained on later steps.
+    ldvb_config c2 = cfg;
+    c2.async_push = 1;
+    int rc = ldvb_create(&c2, &handle);
     if ( rc ) { fprintf(stderr, "ldvb_create: %s\n", ldvb_strerror(rc)); fail("gpu_dvbs_receiver"); }
     max_batch = cfg.max_batch;
     // The pipebufs are allocated once with new T[] (framework.h:139-141): page-lock them so that
@@ -74,7 +78,14 @@ struct gpu_dvbs_receiver : runnable {
     //    (framework.h:96-113 detects the fixpoint on the pipe counters).
     unsigned long n = in.readable();
     if ( n > max_batch ) n = max_batch;
-    if ( !n ) return;
+    if ( !n ) {
+      // Starved (end of input): wait for the work in flight so that this step still makes progress
+      // on the output pipe; a step in which nothing moves ends scheduler::run() (framework.h:96-104).
+      // (no telemetry here: writing p_freq / p_ss / p_mer on a starved step would move pipe counters for ever)
+      if ( ldvb_flush(handle) ) fail("ldvb_flush");
+      drain();
+      return;
+    }
     int rc = ldvb_push(handle, in.rd(), n);
     if ( rc ) { fprintf(stderr, "ldvb_push: %s (%s)\n", ldvb_strerror(rc), ldvb_last_error(handle)); fail("gpu_dvbs_receiver"); }
     in.read(n);

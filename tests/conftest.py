@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # No test of this suite needs more than a couple of minutes: a hang (a deadlocked worker thread, a scheduler
+    # that never reaches its fixpoint) must fail, not eat the GPU box's time.  pytest-timeout is in the image.
+    if config.pluginmanager.hasplugin("timeout") and not getattr(config.option, "timeout", None):
+        config.option.timeout = 300
 
 
 @pytest.fixture(scope="session")

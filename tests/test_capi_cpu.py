@@ -45,7 +45,7 @@ def test_tx_defaults_and_no_device(product):
 
 def test_abi_and_defaults(product):
     L = product.load()
-    assert L.ldvb_abi_version() == 2
+    assert L.ldvb_abi_version() == 3
     c = product.default_config()
     # leandvb.cc:88-135 defaults
     assert (c.input_format, c.anf, c.sampler, c.constellation, c.fec) == (0, 1, 1, 1, 0)

@@ -24,7 +24,7 @@ def test_reference_scheduler_runs_gpu_runnable(product, oracle, fmt, flags):
     ref_flags = [f for f in flags if not f.startswith("--gpu")]
     want = V.ref_leandvb(raw, base + ref_flags)
     out = subprocess.run([O.ref_bin("leandvb_gpu"), *base, *flags, "--gpu-batch", str(1 << 20)],
-                         input=raw.tobytes(), stdout=subprocess.PIPE, check=True).stdout
+                         input=raw.tobytes(), stdout=subprocess.PIPE, check=True, timeout=120).stdout
     got = np.frombuffer(out, dtype=np.uint8).reshape(-1, 188)
     n = min(len(got), len(want))
     assert n > 1400
@@ -44,6 +44,6 @@ def test_reference_scheduler_runs_gpu_transmitter(product, oracle, flags, batch)
     ts = subprocess.run([O.ref_bin("leantsgen"), "-c", "1500"], stdout=subprocess.PIPE, check=True).stdout
     want = subprocess.run([O.ref_bin("leandvbtx"), *flags], input=ts, stdout=subprocess.PIPE, check=True).stdout
     got = subprocess.run([O.ref_bin("leandvbtx_gpu"), *flags, "--gpu-batch", str(batch)], input=ts,
-                         stdout=subprocess.PIPE, check=True).stdout
+                         stdout=subprocess.PIPE, check=True, timeout=120).stdout
     assert len(got) == len(want) and len(got) > 1000000
     assert got == want

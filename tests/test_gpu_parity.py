@@ -568,3 +568,36 @@ def test_two_devices_in_one_process(product, oracle):
     for dev in (0, 1):
         got = run_product(P, raw, rx_mode=P.RX_FAST, device=dev, **kw)
         assert_prefix(got["ts"], ref["ts"], f"TS on device {dev}")
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_async_push_equals_synchronous_push(product, mode):
+    """ldvb_config.async_push: pushes return once the samples have left the caller's buffer, the chain runs on the
+    handle's worker thread.  Same packets as the synchronous handle fed the same pieces; ldvb_pull never waits,
+    ldvb_flush does; telemetry pulls do not wait either."""
+    P = product
+    raw = V.ref_iq(1500, fmt="f32")
+    n = raw.size // 2
+    kw = dict(fmt="f32", resample=True, rx_mode=P.RX_EXACT if mode == "exact" else P.RX_FAST, max_batch=n)
+    pieces = [(0, 700001), (700001, 700001 + 4096 * 300 + 17), (700001 + 4096 * 300 + 17, n)]
+    sync = P.Receiver(**kw)
+    want = []
+    for a, b in pieces:
+        sync.push(raw[2 * a: 2 * b])
+        want.append(sync.pull_all())
+    want = np.concatenate(want)
+    sync.close()
+    rx = P.Receiver(async_push=True, sub_batch=262144, **kw)
+    got = []
+    for a, b in pieces:
+        piece = raw[2 * a: 2 * b].copy()
+        rx.push(piece)
+        piece[:] = 0                         # the caller's buffer is free again when push returns
+        got.append(rx.pull())                # whatever is ready, never blocks
+        rx.meas()                            # telemetry of the finished sub-batches, no wait
+    got.append(rx.pull_all())                # flush + everything
+    got = np.concatenate(got)
+    m = rx.meas()
+    rx.close()
+    assert len(want) > 1300 and np.array_equal(got, want)
+    assert m["ts_packets"] == len(want) and m["samples_in"] == n
