@@ -213,14 +213,22 @@ def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: 
     base = np.ascontiguousarray(raw[: 2 * n])
     sent = V.ts_packets(sample_packets + 64)
 
-    def run(x, mode):
+    def run(x, mode, pieces=1):
+        """-> symbols, TS, meas, seconds of the pushes.  pieces = 2: the vector arrives in two pushes, so that the
+        second one starts from a carried (settled) loop state -- the steady state of a stream."""
         rx = P.Receiver(anf=anf, rx_mode=mode, max_batch=x.size // 2, device=device, keep_taps=1, **rx_kw)
-        rx.push(x)
-        ts = rx.pull_all()
-        sym = rx.tap("symbols").view(np.uint32).copy()
-        m = rx.meas()
+        m = x.size // 2
+        cuts = [0, m] if pieces == 1 else [0, (m // 2) // 4096 * 4096, m]
+        syms, tss, dt = [], [], 0.0
+        for a0, a1 in zip(cuts[:-1], cuts[1:]):
+            t0 = time.perf_counter()
+            rx.push(x[2 * a0: 2 * a1])
+            dt += time.perf_counter() - t0
+            tss.append(rx.pull_all())
+            syms.append(rx.tap("symbols").view(np.uint32).copy())
+        meas = rx.meas()
         rx.close()
-        return sym, ts, m
+        return np.concatenate(syms), np.concatenate(tss), meas, dt, [s.size for s in syms]
 
     def ids(ts):
         """numbered packets -> set of counters of the packets that are bit-correct transmitted packets"""
@@ -234,8 +242,9 @@ def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: 
     out = {"sample_samples": int(n)}
     for name, db in (("clean", None), ("awgn_stddev_22dB", 22.0), ("awgn_stddev_25dB", 25.0)):
         x = base if db is None else awgn(base, db)
-        se, te, me = run(x, P.RX_EXACT)
-        sf, tf, mf = run(x, P.RX_FAST)
+        se, te, me, dte, _ = run(x, P.RX_EXACT)
+        sf, tf, mf, _, _ = run(x, P.RX_FAST)
+        s2, t2, m2, _, sizes2 = run(x, P.RX_FAST, pieces=2)
         tr = np.frombuffer(subprocess.run([_ref_bin("leandvb"), *ref_flags], input=x.tobytes(), stdout=subprocess.PIPE,
                                           stderr=subprocess.DEVNULL, check=True).stdout, dtype=np.uint8).reshape(-1, 188)
         k = min(se.size, sf.size)
@@ -257,6 +266,16 @@ def fast_vs_exact(P, raw: np.ndarray, rx_kw: dict, ref_flags, anf: int, device: 
                       "accepted_with_mismatch": mf["seams_mismatch_accepted"], "settle_passes": mf["settle_passes"],
                       "max_dphase": mf["seam_max_dphase"], "max_dfreqw": mf["seam_max_dfreqw"], "max_dmu": mf["seam_max_dmu"]},
             "mer_db": me["mer"],
+            # the same vector in two pushes: the symbols of the SECOND push come from spans that started from a carried,
+            # settled AGC / frequency state (what every batch but the first of a stream sees)
+            "steady_state": (lambda h0, kk2: {
+                "symbols": int(kk2 - h0),
+                "hard_symbol_mismatch": int(((se[h0:kk2] >> 16) != (s2[h0:kk2] >> 16)).sum()),
+                "cost_mismatch": int(((se[h0:kk2] & 0xffff) != (s2[h0:kk2] & 0xffff)).sum()),
+                "cost_abs_diff_mean": float(np.abs((se[h0:kk2] & 0xffff).astype(np.int16).astype(np.int32) -
+                                                   (s2[h0:kk2] & 0xffff).astype(np.int16).astype(np.int32)).mean()) if kk2 > h0 else None,
+                "ts_packets_differing_vs_reference": len(ids(t2)[0] ^ ir)})(sizes2[0], min(se.size, s2.size)),
+            "exact_mode_MSps": (x.size // 2) / dte / 1e6,
         }
     return out
 
@@ -288,7 +307,33 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     cap = C // 1900 + 64
     ts_dev = torch.empty(cap * 188, dtype=torch.uint8, device=dev)
     engine = S.GpuEngine(rx, ts_dev.data_ptr(), cap)
-    ring = S.Ring(dist, dev)
+    # The ring: inside the library (ldvb_ring_*: ncclSend / ncclRecv between neighbours, C ABI) unless --ring py
+    # asks for the torch.distributed transport of leansdr_b200/shard.py (the same three shard calls underneath).
+    use_lib = (a.ring == "lib")
+    if use_lib:
+        from leansdr_b200 import capi
+        ids = torch.zeros(256, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            ids.copy_(torch.frombuffer(bytearray(capi.ring_unique_id() + capi.ring_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ids, 0)
+        idb = ids.cpu().numpy().tobytes()
+        ok = 1.0
+        try:
+            rx.ring_init(idb[:128], idb[128:], rank, world)
+        except Exception as e:                       # e.g. no libnccl.so.2 for the library: all ranks fall back together
+            sys.stderr.write(f"[bench] rank {rank}: ldvb_ring_init failed ({e}); using the torch.distributed ring\n")
+            ok = 0.0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag[0]) < 1.0:
+            use_lib = False
+            try:
+                rx.ring_destroy()
+            except Exception:
+                pass
+    ring = None if use_lib else S.Ring(dist, dev)
+    if False:
+        pass
     halo_send = buf[buf.numel() - 2 * ch.n_halo_next:] if ch.n_halo_next else None
     halo_recv = buf[: 2 * ch.n_halo] if ch.n_halo else None
     tl = {}
@@ -297,14 +342,27 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
         dist.barrier()
         torch.cuda.synchronize()
 
-    def step(timeline=None):
-        return S.run_round(engine, ring, ch, buf.data_ptr(), halo_send, halo_recv, timeline)
+    def ring_flush():
+        if use_lib:
+            rx.ring_flush()
+        else:
+            ring.flush()
+
+    def step(timeline=None, b=None):
+        b = buf if b is None else b
+        if use_lib:
+            sh = rx.shard(b.data_ptr(), ch.abs_raw0, ch.n_halo, ch.n_chunk, ch.n_halo_next, ch.last)
+            return rx.ring_round(sh, ts_dev.data_ptr(), cap)
+        return S.run_round(engine, ring, ch, b.data_ptr(), b[b.numel() - 2 * ch.n_halo_next:] if ch.n_halo_next else None,
+                           b[: 2 * ch.n_halo] if ch.n_halo else None, timeline)
 
     for _ in range(W):
         npk = step()
-    ring.flush()
+    ring_flush()
     torch.cuda.synchronize()
     halo_ok = bool(torch.equal(buf[: 2 * ch.n_halo], own_halo))
+    if use_lib:
+        rx.ring_stats(reset=True)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
@@ -316,34 +374,53 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     t0 = time.perf_counter()
     for _ in range(a.steps):
         npk = step(tl)
-    ring.flush()
+    ring_flush()
     e1.record(stream)
     barrier()
     ms = max(e0.elapsed_time(e1), 0.0)
     ms_host = (time.perf_counter() - t0) * 1e3
+    if use_lib:
+        tl = rx.ring_stats(reset=True)
     prof = rx.get_profile()
     rx.profile(False)
     meas = rx.meas()
     launches = meas["kernel_launches"] - l0
     ts_gpu = ts_dev[: npk * 188].cpu().numpy().reshape(-1, 188)
 
-    # ---- e2e: the chunk comes from pinned host memory every step, the TS goes back to the host
+    # ---- e2e: the chunk comes from pinned host memory every step, the TS goes back to the host.  Two chunk buffers:
+    # the samples of step s+1 arrive (side stream) while step s is being demodulated, like consecutive chunks of a
+    # live stream; every step waits for its own samples, and the last TS copy lies inside the timed region.
     pinned = torch.from_numpy(raw[2 * ch.n_halo:]).pin_memory()
     ts_host = torch.empty(cap * 188, dtype=torch.uint8).pin_memory()
+    bufs = [buf, torch.empty_like(buf)]
+    side = torch.cuda.Stream()
+    arrived = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        buf[2 * ch.n_halo:].copy_(pinned, non_blocking=True)
-        k = step()
-        ts_host[: k * 188].copy_(ts_dev[: k * 188], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def fetch(i):
+        side.wait_stream(torch.cuda.current_stream())          # the buffer's previous step is done with it
+        with torch.cuda.stream(side):
+            bufs[i][2 * ch.n_halo:].copy_(pinned, non_blocking=True)
+            arrived[i].record(side)
+
+    def e2e_run(nsteps):
+        k = 0
+        fetch(0)
+        for i in range(nsteps):
+            cur = i & 1
+            if i + 1 < nsteps:
+                fetch(cur ^ 1)     # (its outgoing halo of two steps ago has left: ldvb_ring_round waits for that first)
+            arrived[cur].synchronize()
+            torch.cuda.current_stream().wait_event(arrived[cur])
+            k = step(b=bufs[cur])
+            ts_host[: k * 188].copy_(ts_dev[: k * 188], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         return k
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
+    ring_flush()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        k = e2e_step()
-    ring.flush()
+    k = e2e_run(a.steps)
+    ring_flush()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clk = clocks.summary()
@@ -352,6 +429,14 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     ctr = (ts_gpu[:, 1].astype(np.int64) << 16) | (ts_gpu[:, 2].astype(np.int64) << 8) | ts_gpu[:, 3]
     i0 = 3 if rank == 0 else 0                     # the stream opens with the interleaver's fill
     ok = len(ts_gpu) > i0 + 8 and np.array_equal(ts_gpu[i0:], V.ts_packets(len(ts_gpu) - i0, int(ctr[i0])))
+    # rank 0 also decodes the first samples of the stream (= of its own chunk) with the unmodified reference
+    ref_match = None
+    if rank == 0 and not a.no_cpu:
+        nref = min(C, 8 << 20)
+        tsr = np.frombuffer(subprocess.run([_ref_bin("leandvb"), *REF_FLAGS], input=raw[: 2 * nref].tobytes(), stdout=subprocess.PIPE,
+                                           stderr=subprocess.DEVNULL, check=True).stdout, dtype=np.uint8).reshape(-1, 188)
+        kk = min(len(tsr), len(ts_gpu))
+        ref_match = bool(kk > 100 and np.array_equal(tsr[:kk], ts_gpu[:kk]))
     mine = torch.tensor([float(ms), float(e2e_ms), float(ms_host), float(ctr[i0]) if len(ctr) > i0 else -1.0,
                          float(ctr[-1]) if len(ctr) else -1.0, float(ok), float(len(ts_gpu)), float(launches), float(halo_ok),
                          tl.get("early", 0.0), tl.get("front", 0.0), tl.get("wait_edge", 0.0), tl.get("back", 0.0),
@@ -402,7 +487,9 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
             "kernel_ms_per_step": per_step, "stage_wall_ms_per_step": wall,
             "cpu_baseline": None,
             "ts_packets_per_step": int(allv[:, 6].sum()),
-            "ts_bit_exact_vs_reference": None,
+            "ts_bit_exact_vs_reference": ref_match,
+            "ts_bit_exact_vs_reference_how": "rank 0: oracle/_ref/leandvb on the first %d samples of the stream against the packets of chunk 0" % min(C, 8 << 20),
+            "ring": "library (ldvb_ring_round: ncclSend/ncclRecv, two communicators)" if use_lib else "python (torch.distributed isend/recv)",
             "ts_equals_transmitted_packets_contiguous_over_ranks": ts_ok,
             "halo_received_equals_own_generation": bool(allv[:, 8].all()),
             "shard_timeline_ms_per_step": [{"rank": k, "early": allv[k, 9] / a.steps, "front": allv[k, 10] / a.steps,
@@ -431,6 +518,8 @@ def main():
                          "The default 'f32' is BASELINE.json's configuration.")
     ap.add_argument("--cpu-gen", action="store_true", help="synthesise the IQ with the reference binaries on the host "
                     "instead of the B200 transmit chain (N = 1)")
+    ap.add_argument("--ring", default="lib", choices=["lib", "py"], help="time-sharded transport: ldvb_ring_* inside the library "
+                    "(NCCL from C) or leansdr_b200/shard.py over torch.distributed")
     ap.add_argument("--shard", default="time", choices=["time", "streams"],
                     help="N > 1: 'time' = ONE stream cut into N time chunks (halo + EDGE over NCCL), "
                          "'streams' = N independent streams (replicas)")

@@ -377,6 +377,27 @@ int ldvb_shard_front(ldvb_handle *h, const ldvb_shard *s);
 int ldvb_shard_back(ldvb_handle *h, const void *edge_in, uint8_t *ts_dev, size_t cap_packets,
 		    size_t *n_packets, void *edge_out);
 
+/* The ring around those three calls, inside the library: NCCL point-to-point between neighbouring
+ * ranks (ncclSend / ncclRecv on two communicators: halo + notch bins, and the EDGE), one process per
+ * GPU.  libnccl.so.2 is resolved at run time; LDVB_ENODEV when it is absent.
+ *   ldvb_ring_unique_id  one rank creates two ids (ncclGetUniqueId) and hands their bytes to the
+ *                        others by whatever means the host has (MPI, a file, torch.distributed ...)
+ *   ldvb_ring_init       collective: every rank, same two ids
+ *   ldvb_ring_round      this rank's turn for chunk s (s->iq_dev = [halo | chunk] in HBM, the halo
+ *                        region is filled by the call; bins_before / bins_after are filled too):
+ *                        receive halo + bins, detect, send halo + bins, front, receive EDGE, back,
+ *                        send EDGE.  Chunks must be presented in stream order, chunk k on rank k mod N.
+ *                        The caller may refill the chunk buffer after the NEXT call has started or
+ *                        after ldvb_ring_flush (the outgoing halo is read from it asynchronously).
+ *   ldvb_ring_stats      host wall clock per phase {early, front, wait_edge, back}, ms, accumulated */
+#define LDVB_RING_ID_BYTES 128
+int ldvb_ring_unique_id(void *id, size_t cap_bytes);
+int ldvb_ring_init(ldvb_handle *h, const void *id_early, const void *id_edge, int rank, int nranks);
+int ldvb_ring_round(ldvb_handle *h, ldvb_shard *s, uint8_t *ts_dev, size_t cap_packets, size_t *n_packets);
+int ldvb_ring_flush(ldvb_handle *h);
+int ldvb_ring_stats(ldvb_handle *h, double ms4[4], int reset);
+int ldvb_ring_destroy(ldvb_handle *h);
+
 /* ------------------------------------------------- stand-alone stage kernels
  * Host in, host out; used by the parity tests and by callers that only need
  * one block.  Each runs the same kernel the chain uses. */

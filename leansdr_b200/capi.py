@@ -76,6 +76,7 @@ EXPORTS = [
     "ldvb_reset", "ldvb_set_stream", "ldvb_profile", "ldvb_get_profile",
     "ldvb_pull_cnr", "ldvb_pull_spectrum", "ldvb_pull_vber",
     "ldvb_edge_size", "ldvb_shard_min_halo", "ldvb_shard_detect", "ldvb_shard_front", "ldvb_shard_back",
+    "ldvb_ring_unique_id", "ldvb_ring_init", "ldvb_ring_round", "ldvb_ring_flush", "ldvb_ring_stats", "ldvb_ring_destroy",
 ]
 
 
@@ -143,6 +144,12 @@ def load():
     L.ldvb_shard_detect.argtypes = [vp, C.POINTER(Shard)]
     L.ldvb_shard_front.argtypes = [vp, C.POINTER(Shard)]
     L.ldvb_shard_back.argtypes = [vp, vp, vp, sz, C.POINTER(sz), vp]
+    L.ldvb_ring_unique_id.argtypes = [vp, sz]
+    L.ldvb_ring_init.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    L.ldvb_ring_round.argtypes = [vp, C.POINTER(Shard), vp, sz, C.POINTER(sz)]
+    L.ldvb_ring_flush.argtypes = [vp]
+    L.ldvb_ring_stats.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    L.ldvb_ring_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -170,6 +177,15 @@ def default_config(**kw) -> Config:
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def ring_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (one rank calls it, the bytes go to the others)."""
+    b = np.zeros(128, np.uint8)
+    rc = load().ldvb_ring_unique_id(_p(b), b.size)
+    if rc:
+        raise LdvbError(rc, "ldvb_ring_unique_id", load().ldvb_strerror(rc).decode())
+    return b.tobytes()
 
 
 def host_table(cfg: Config, name: str) -> np.ndarray:
@@ -354,6 +370,27 @@ class Receiver:
         self._ck(self.L.ldvb_shard_back(self.h, _p(edge_in) if edge_in is not None else None, ts_ptr, cap_packets,
                                         C.byref(n), _p(edge_out) if edge_out is not None else None), "ldvb_shard_back")
         return int(n.value)
+
+    # ---- the ring inside the library (NCCL send/recv between neighbouring ranks)
+    def ring_init(self, id_early: bytes, id_edge: bytes, rank: int, nranks: int):
+        a = np.frombuffer(bytes(id_early), np.uint8).copy(); b = np.frombuffer(bytes(id_edge), np.uint8).copy()
+        self._ck(self.L.ldvb_ring_init(self.h, _p(a), _p(b), rank, nranks), "ldvb_ring_init")
+
+    def ring_round(self, s: Shard, ts_ptr: int, cap_packets: int) -> int:
+        n = C.c_size_t(0)
+        self._ck(self.L.ldvb_ring_round(self.h, C.byref(s), ts_ptr, cap_packets, C.byref(n)), "ldvb_ring_round")
+        return int(n.value)
+
+    def ring_flush(self):
+        self._ck(self.L.ldvb_ring_flush(self.h), "ldvb_ring_flush")
+
+    def ring_stats(self, reset: bool = False) -> dict:
+        v = (C.c_double * 4)()
+        self._ck(self.L.ldvb_ring_stats(self.h, v, 1 if reset else 0), "ldvb_ring_stats")
+        return dict(zip(("early", "front", "wait_edge", "back"), (float(x) for x in v)))
+
+    def ring_destroy(self):
+        self._ck(self.L.ldvb_ring_destroy(self.h), "ldvb_ring_destroy")
 
     def get_state(self) -> np.ndarray:
         n = self.L.ldvb_state_size(self.h)

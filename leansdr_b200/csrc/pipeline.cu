@@ -79,6 +79,7 @@ struct ProfSpanRec { int id; cudaEvent_t a, b; };
 
 }  // namespace
 
+struct RingState;
 struct ldvb_handle {
   ldvb_config cfg;
   cudaStream_t st = nullptr;
@@ -213,6 +214,7 @@ struct ldvb_handle {
   uint64_t stage_next = 0;
   double dbg_stage_wait_ms = 0, dbg_copy_wait_ms = 0, dbg_chain_ms = 0; uint64_t dbg_jobs = 0;   // LDVB_ASYNC_DEBUG
   std::mutex qmu;                       // ts_queue, ts_queue_cap, rd, wr, ready
+  struct RingState *ring = nullptr;     // ldvb_ring_*: the NCCL transport of the time-sharded mode
   // telemetry as of the last finished job (amu): what ldvb_get_meas / ldvb_pull_{cnr,vber,spectrum} serve while
   // the worker owns the live copies
   ldvb_meas meas_pub;
@@ -585,6 +587,7 @@ void ldvb_config_default(ldvb_config *c) {
 int ldvb_destroy(ldvb_handle *h) {
   if (!h) return LDVB_OK;
   cudaSetDevice(h->cfg.device);
+  if (h->ring) ldvb_ring_destroy(h);
   if (h->worker_started) {
     { std::unique_lock<std::mutex> lk(h->amu); h->acv_done.wait(lk, [&] { return h->pending == 0; }); h->worker_stop = true; }
     h->acv_job.notify_all();
@@ -3294,6 +3297,213 @@ int ldvb_shard_back(ldvb_handle *h, const void *edge_in, uint8_t *ts_dev, size_t
 }
 
 // ------------------------------------------------------------ stand-alone stages
+
+// ---------------------------------------------------------------- the ring (NCCL)
+// "a single NCCL send/recv over NVLink carrying only the chunk-edge samples and Viterbi/PLL carry
+// state".  ldvb_ring_round is one rank's turn: halo and notch bins in (early communicator), detect, halo and bins
+// out, the speculative front stage, EDGE in (edge communicator), the exact back stage, EDGE out.  Two
+// communicators = two NCCL streams, so that the early messages of the next round travel while an EDGE is still
+// awaited.  Messages between two neighbours are matched in issue order and every rank issues them in chunk order,
+// all dependencies point forward in the stream (the wrap-around N-1 -> 0 included), so the schedule cannot lock.
+// NCCL is resolved at run time (dlopen): a single-GPU user of the library does not need it.
+}  // extern "C"
+
+#include <dlfcn.h>
+
+namespace ldvb {
+namespace {
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclUint8 = 1;   // ncclUint8 (nccl.h: ncclInt8 = 0, ncclUint8 = 1)
+
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *lib = nullptr;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return;
+    auto sym = [&](const char *n) { return dlsym(lib, n); };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+  });
+  return &api;
+}
+}  // namespace
+}  // namespace ldvb
+
+struct RingState {
+  void *comm_early = nullptr, *comm_edge = nullptr;
+  cudaStream_t st_early = nullptr, st_edge = nullptr;
+  int rank = 0, n = 1;
+  DevBuf d_bins_in, d_bins_out, d_edge_in, d_edge_out;
+  uint8_t *h_edge_in = nullptr, *h_edge_out = nullptr;
+  int32_t *h_bins = nullptr;          // [8] pinned: bins in, bins out
+  double ms[4] = {0, 0, 0, 0};        // early, front, wait_edge, back (host wall clock, accumulated)
+};
+
+namespace {
+int ring_fail(ldvb_handle *h, int nccl_rc, const char *what) {
+  ldvb::NcclApi *api = ldvb::nccl_api();
+  std::string msg = std::string("NCCL ") + what + ": " + (api->GetErrorString ? api->GetErrorString(nccl_rc) : "error");
+  return fail(h, LDVB_ECUDA, msg.c_str());
+}
+#define NK(call, what) do { int rcn_ = (call); if (rcn_ != 0) return ring_fail(h, rcn_, what); } while (0)
+}  // namespace
+
+extern "C" {
+
+int ldvb_ring_unique_id(void *id, size_t cap) {
+  ldvb::NcclApi *api = ldvb::nccl_api();
+  if (!id || cap < sizeof(ldvb::NcclApi::UniqueId)) return LDVB_EINVAL;
+  if (!api->ok) return LDVB_ENODEV;
+  ldvb::NcclApi::UniqueId u;
+  if (api->GetUniqueId(&u) != 0) return LDVB_ECUDA;
+  memcpy(id, &u, sizeof u);
+  return LDVB_OK;
+}
+
+int ldvb_ring_init(ldvb_handle *h, const void *id_early, const void *id_edge, int rank, int nranks) {
+  using namespace ldvb;
+  if (!h || !id_early || !id_edge || nranks < 1 || rank < 0 || rank >= nranks) return LDVB_EINVAL;
+  { int rcw = async_wait(h); if (rcw) return rcw; }
+  NcclApi *api = nccl_api();
+  if (!api->ok) return fail(h, LDVB_ENODEV, "libnccl.so.2 not found");
+  if (h->ring) return fail(h, LDVB_ESTATE, "ring already initialised");
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  RingState *r = new RingState();
+  r->rank = rank; r->n = nranks;
+  h->ring = r;
+  NcclApi::UniqueId a, b;
+  memcpy(&a, id_early, sizeof a); memcpy(&b, id_edge, sizeof b);
+  NK(api->CommInitRank(&r->comm_early, nranks, a, rank), "ncclCommInitRank (early)");
+  NK(api->CommInitRank(&r->comm_edge, nranks, b, rank), "ncclCommInitRank (edge)");
+  CK(cudaStreamCreateWithFlags(&r->st_early, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&r->st_edge, cudaStreamNonBlocking));
+  CK(r->d_bins_in.alloc(64)); CK(r->d_bins_out.alloc(64));
+  CK(r->d_edge_in.alloc(sizeof(EdgeBlob) + 256)); CK(r->d_edge_out.alloc(sizeof(EdgeBlob) + 256));
+  CK(cudaHostAlloc((void **)&r->h_edge_in, sizeof(EdgeBlob), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void **)&r->h_edge_out, sizeof(EdgeBlob), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void **)&r->h_bins, 64, cudaHostAllocDefault));
+  return LDVB_OK;
+}
+
+int ldvb_ring_flush(ldvb_handle *h) {
+  using namespace ldvb;
+  if (!h || !h->ring) return LDVB_EINVAL;
+  CK(cudaStreamSynchronize(h->ring->st_early));
+  CK(cudaStreamSynchronize(h->ring->st_edge));
+  return LDVB_OK;
+}
+
+int ldvb_ring_round(ldvb_handle *h, ldvb_shard *s, uint8_t *ts_dev, size_t cap_packets, size_t *n_packets) {
+  using namespace ldvb;
+  if (!h || !s || !ts_dev || !n_packets) return LDVB_EINVAL;
+  RingState *r = h->ring;
+  if (!r) return fail(h, LDVB_ESTATE, "ldvb_ring_init first");
+  { int rcw = async_wait(h); if (rcw) return rcw; }
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
+  NcclApi *api = nccl_api();
+  const bool first = (s->n_halo == 0 && s->abs_raw0 == 0), last = s->last != 0;
+  const int prv = (r->rank + r->n - 1) % r->n, nxt = (r->rank + 1) % r->n;
+  const size_t bps = h->s_raw.elem;
+  uint8_t *iq = static_cast<uint8_t *>(const_cast<void *>(s->iq_dev));
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  auto t0 = now();
+  // The halo of the previous round has left the caller's buffer (the caller refills it between rounds).
+  CK(cudaStreamSynchronize(r->st_early));
+  // ---- early: halo + notch bins from the previous chunk
+  for (int k = 0; k < 4; ++k) s->bins_before[k] = -1;
+  if (!first) {
+    NK(api->GroupStart(), "ncclGroupStart");
+    NK(api->Recv(iq, s->n_halo * bps, kNcclUint8, prv, r->comm_early, r->st_early), "ncclRecv (halo)");
+    NK(api->Recv(r->d_bins_in.p, 16, kNcclUint8, prv, r->comm_early, r->st_early), "ncclRecv (bins)");
+    NK(api->GroupEnd(), "ncclGroupEnd");
+    CK(cudaMemcpyAsync(r->h_bins, r->d_bins_in.p, 16, cudaMemcpyDeviceToHost, r->st_early));
+    CK(cudaStreamSynchronize(r->st_early));
+    for (int k = 0; k < 4; ++k) s->bins_before[k] = r->h_bins[k];
+  }
+  int rc = shard_check(h, s);
+  if (rc) return rc;
+  if ((rc = shard_detect(h, s))) return rc;
+  if (!last) {
+    for (int k = 0; k < 4; ++k) r->h_bins[4 + k] = s->bins_after[k];
+    CK(cudaMemcpyAsync(r->d_bins_out.p, r->h_bins + 4, 16, cudaMemcpyHostToDevice, r->st_early));
+    NK(api->GroupStart(), "ncclGroupStart");
+    NK(api->Send(iq + (s->n_halo + s->n_chunk - s->n_halo_next) * bps, s->n_halo_next * bps, kNcclUint8, nxt, r->comm_early, r->st_early), "ncclSend (halo)");
+    NK(api->Send(r->d_bins_out.p, 16, kNcclUint8, nxt, r->comm_early, r->st_early), "ncclSend (bins)");
+    NK(api->GroupEnd(), "ncclGroupEnd");
+  }
+  r->ms[0] += ms_since(t0); t0 = now();
+  // ---- front (speculative, concurrent on all ranks)
+  if ((rc = shard_front(h, s))) return rc;
+  r->ms[1] += ms_since(t0); t0 = now();
+  // ---- EDGE of the previous chunk
+  if (!first) {
+    NK(api->Recv(r->d_edge_in.p, sizeof(EdgeBlob), kNcclUint8, prv, r->comm_edge, r->st_edge), "ncclRecv (EDGE)");
+    CK(cudaMemcpyAsync(r->h_edge_in, r->d_edge_in.p, sizeof(EdgeBlob), cudaMemcpyDeviceToHost, r->st_edge));
+  }
+  CK(cudaStreamSynchronize(r->st_edge));      // (also: the previous round's EDGE has left h_edge_out / d_edge_out)
+  r->ms[2] += ms_since(t0); t0 = now();
+  // ---- back (exact, chained) and the EDGE for the next chunk
+  uint64_t got = 0;
+  rc = shard_back(h, first ? nullptr : reinterpret_cast<const EdgeBlob *>(r->h_edge_in), ts_dev, cap_packets, &got,
+                  last ? nullptr : reinterpret_cast<EdgeBlob *>(r->h_edge_out));
+  *n_packets = (size_t)got;
+  if (rc) return rc;
+  if (!last) {
+    CK(cudaMemcpyAsync(r->d_edge_out.p, r->h_edge_out, sizeof(EdgeBlob), cudaMemcpyHostToDevice, r->st_edge));
+    NK(api->Send(r->d_edge_out.p, sizeof(EdgeBlob), kNcclUint8, nxt, r->comm_edge, r->st_edge), "ncclSend (EDGE)");
+  }
+  r->ms[3] += ms_since(t0);
+  return LDVB_OK;
+}
+
+int ldvb_ring_stats(ldvb_handle *h, double ms4[4], int reset) {
+  if (!h || !h->ring || !ms4) return LDVB_EINVAL;
+  for (int k = 0; k < 4; ++k) { ms4[k] = h->ring->ms[k]; if (reset) h->ring->ms[k] = 0; }
+  return LDVB_OK;
+}
+
+int ldvb_ring_destroy(ldvb_handle *h) {
+  using namespace ldvb;
+  if (!h) return LDVB_EINVAL;
+  RingState *r = h->ring;
+  if (!r) return LDVB_OK;
+  cudaSetDevice(h->cfg.device);
+  if (r->st_early) cudaStreamSynchronize(r->st_early);
+  if (r->st_edge) cudaStreamSynchronize(r->st_edge);
+  NcclApi *api = nccl_api();
+  if (r->comm_early) api->CommDestroy(r->comm_early);
+  if (r->comm_edge) api->CommDestroy(r->comm_edge);
+  if (r->st_early) cudaStreamDestroy(r->st_early);
+  if (r->st_edge) cudaStreamDestroy(r->st_edge);
+  r->d_bins_in.release(); r->d_bins_out.release(); r->d_edge_in.release(); r->d_edge_out.release();
+  if (r->h_edge_in) cudaFreeHost(r->h_edge_in);
+  if (r->h_edge_out) cudaFreeHost(r->h_edge_out);
+  if (r->h_bins) cudaFreeHost(r->h_bins);
+  delete r;
+  h->ring = nullptr;
+  return LDVB_OK;
+}
 
 int ldvb_fir_cf32(int device, const float *x, size_t n_in, const float *taps, uint32_t ntaps, uint32_t decim,
                   float *y, size_t cap_out, size_t *n_out) {

@@ -12,7 +12,7 @@ from tests.test_gpu_parity import _freq_shift
 pytestmark = pytest.mark.gpu
 
 
-def run_sharded(P, raw, n_chunks, n_engines, halo_units=None, **kw):
+def run_sharded(P, raw, n_chunks, n_engines, halo_units=None, unit=4096, **kw):
     import torch
     from leansdr_b200 import shard as S
     n = raw.size // 2
@@ -26,7 +26,7 @@ def run_sharded(P, raw, n_chunks, n_engines, halo_units=None, **kw):
         ts = torch.empty(cap * 188, dtype=torch.uint8, device=dev)
         rxs.append(rx); ts_bufs.append(ts)
         engines.append(S.GpuEngine(rx, ts.data_ptr(), cap))
-    unit = 4096       # a multiple of lcm(4096, 128 * decimation) for decimation 1 and 2
+    # unit: a multiple of lcm(4096, 128 * decimation); 4096 for decimation 1 and 2
     halo = -(-rxs[0].shard_min_halo() // unit) * unit if halo_units is None else halo_units * unit
     chunks = S.plan_stream(n, n_chunks, unit, halo)
     out = []
@@ -76,6 +76,21 @@ def test_time_sharded_ts_bit_exact(product, oracle, name, kw, gkw, npk, nch, nen
     got, meas, chunks = run_sharded(P, raw, nch, neng, **kw)
     check_ts(got, want, lost_tail=_tail(raw, chunks))
     assert sum(m["seams_total"] for m in meas) > nch
+
+
+def test_time_sharded_wideband_resample_chain(product, oracle):
+    """BASELINE.json configs[4], reading 5b: a carrier oversampled 120x (Fs/Fm = 120), `--resample` = 313-tap low-pass
+    with decimation 30, then the 4 samples/symbol receiver -- time-sharded over three handles.  The waveform arrives
+    ~11x below the nominal level: the first chunk settles its AGC serially, the later chunks seed their warm-ups with
+    the measured power; alignment unit lcm(4096, 128 * 30) = 61440 samples."""
+    P, O = product, oracle
+    raw = V.ref_iq(120, ratio="120", fmt="f32")
+    kw = dict(fmt="f32", resample=True, Fs=240e6)
+    want = O.Chain(O.Config(**kw)).run(raw)["ts"]
+    got, meas, chunks = run_sharded(P, raw, 3, 3, unit=61440, **kw)
+    assert len(want) >= 40
+    check_ts(got, want, lost_tail=_tail(raw, chunks))
+    assert sum(m["seams_total"] for m in meas) > 3 and sum(m["settle_passes"] for m in meas) >= 1
 
 
 def test_time_sharded_cold_start_with_carrier_offset(product, oracle):
