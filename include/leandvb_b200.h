@@ -245,6 +245,10 @@ int ldvb_push(ldvb_handle *h, const void *iq_host, size_t n_samples);
 int ldvb_pull(ldvb_handle *h, uint8_t *ts_host, size_t cap_packets,
 	      size_t *n_packets);
 
+/* Threads: a handle has ONE caller at a time, with one exception made for streaming hosts: on an async_push
+ * handle ldvb_pull may be called from a second thread while another one is inside ldvb_push / ldvb_flush (a
+ * producer and a consumer); ldvb_pull only touches the packet queue, under its own lock. */
+
 /* Waits until everything pushed so far has been processed (async_push) and
  * reports an error of the background chain, if any.  A no-op otherwise.  Every
  * entry point except ldvb_push / ldvb_pull does this implicitly. */

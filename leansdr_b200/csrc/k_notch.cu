@@ -163,12 +163,17 @@ k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][
   float accr[kNotchMaxSlots], acci[kNotchMaxSlots];
   for (int s = 0; s < kNotchMaxSlots; ++s) { accr[s] = 0.f; acci[s] = 0.f; }
   const uint64_t base = b * (uint64_t)kNotchN;
+  const float2 *tab[kNotchMaxSlots];
+  for (int s = 0; s < kNotchMaxSlots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s < a.nslots ? s : 0] * kNotchN;
+  // Plain streaming: every load of the block is issued before the first use (8 independent iterations in flight
+  // per thread), so that the kernel is bound by the one pass over the samples and not by load latency.
+#pragma unroll 8
   for (int j = 0; j < kNotchN / 128; ++j) {
     const int i = j * 128 + tid;
     const float2 x = ld_raw<FMT>(a.src, base + i, a.scale);
     const float w = __ldg(weights + (kNotchN - 1 - i)) * a.k;
     for (int s = 0; s < a.nslots; ++s) {
-      const float2 e = __ldg(a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + i);
+      const float2 e = __ldg(tab[s] + i);
       accr[s] += (x.x * e.x + x.y * e.y) * w;
       acci[s] += (-x.x * e.y + x.y * e.x) * w;
     }
@@ -207,7 +212,12 @@ constexpr int kNStages = LDVB_NOTCH_STAGES;        // tiles in flight per lane: 
 constexpr int kNWarps = LDVB_NOTCH_WARPS;
 static_assert(kNPitch % 128 == 16 && kNotchN % kNTile == 0 && kNStages >= 2, "row geometry");
 // dynamic shared memory: [input rows: warps x stages x 32 x pitch | table tiles: warps x stages x slots x tile | output tiles]
-constexpr size_t kNotchSmemIn = (size_t)kNWarps * kNStages * 32 * kNPitch + (size_t)kNWarps * kNStages * 4 * kNTile * 8;
+// (two table sets per stage and slot, see k_notch_apply; sized by the number of slots so that the one-slot kernel
+//  still fits four CTAs per SM)
+template <int NSLOTS> struct NotchSmem {
+  static constexpr size_t in = (size_t)kNWarps * kNStages * 32 * kNPitch + (size_t)kNWarps * kNStages * 2 * NSLOTS * kNTile * 8;
+  static constexpr size_t total = in + (size_t)kNWarps * 32 * kNPitch;   // + one output tile per warp
+};
 
 template <int FMT, int NSLOTS>
 __global__ void __launch_bounds__(kNWarps * 32)
@@ -275,8 +285,13 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   // tile is staged once per warp with the rows (kNTile * 8 bytes per slot, 16 B per lane) and
   // read back as shared-memory broadcasts: the table leaves the dependent-load path (ncu: the
   // products waiting on these LDGs were 45 % of the kernel's stall samples).
+  // Up to TWO table sets per stage: a warp that straddles a bin change (an epoch boundary, 30 per 128 M samples on
+  // a flat spectrum) has lanes on the old tables and lanes on the new ones; with one set it fell back to per-lane
+  // global loads for all its three blocks and, the kernel being one wave of latency-bound warps, set the kernel's
+  // duration (1.39 ms against 1.00 ms, continuous-stream bench of round 2).
   float2 *wtab = reinterpret_cast<float2 *>(smem + (size_t)kNWarps * kNStages * 32 * kNPitch) +
-                 (size_t)warp * kNStages * kNotchMaxSlots * kNTile;
+                 (size_t)warp * kNStages * 2 * NSLOTS * kNTile;
+  uint32_t set_mask = 0;              // bit st: this LANE reads set 1 of stage st
   uint32_t staged_mask = 0;           // bit st: stage st holds a valid table tile (warp uniform)
   int epi = p.epoch;                  // epoch cursor of the issue stream
   uint32_t tixi[NSLOTS];
@@ -323,27 +338,48 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
       if (active && (lead + kNTile) * bps > (uint32_t)kRowChunks * 16u)
         cp_async16(stage_base + (size_t)lane * kNPitch + kRowChunks * 16, src + kRowChunks * 16);
     }
-    // Same tables on every active lane?  (all lanes of the warp are here: no divergence)
-    bool uniform = act != 0;
-    uint32_t lead_tix[NSLOTS];
+    // Which tables do the active lanes use?  One set (always, except in a warp that straddles a bin change) or two
+    // are staged; three or more (never seen) fall back to per-lane global loads.  (All lanes of the warp are here.)
+    bool stage_ok = act != 0;
+    bool two = false;
+    uint32_t lead_tix[NSLOTS], alt_tix[NSLOTS];
+    bool mine_alt = false;
     if (act) {
       const int leader = __ffs(act) - 1;
       bool same = true;
 #pragma unroll
       for (int s = 0; s < NSLOTS; ++s) {
         lead_tix[s] = __shfl_sync(0xffffffffu, tixi[s], leader);
+        alt_tix[s] = lead_tix[s];
         same = same && (!active || tixi[s] == lead_tix[s]);
       }
-      uniform = __all_sync(0xffffffffu, same);
+      const unsigned diff = __ballot_sync(0xffffffffu, !same);
+      if (diff) {
+        const int l2 = __ffs(diff) - 1;
+        bool same2 = true;
+#pragma unroll
+        for (int s = 0; s < NSLOTS; ++s) {
+          alt_tix[s] = __shfl_sync(0xffffffffu, tixi[s], l2);
+          same2 = same2 && (tixi[s] == alt_tix[s]);
+        }
+        mine_alt = !same;
+        two = true;
+        stage_ok = __all_sync(0xffffffffu, same || same2);
+      }
     }
-    if (uniform) {
+    if (stage_ok) {
       staged_mask |= 1u << st;
+      if (mine_alt) set_mask |= 1u << st; else set_mask &= ~(1u << st);
       constexpr int kChunks = kNTile * 8 / 16;       // 16-byte pieces per slot
 #pragma unroll
       for (int s = 0; s < NSLOTS; ++s)
-        for (int q = lane; q < kChunks; q += 32)
-          cp_async16_ca(reinterpret_cast<unsigned char *>(wtab + ((size_t)st * kNotchMaxSlots + s) * kNTile) + q * 16,
+        for (int q = lane; q < kChunks; q += 32) {
+          cp_async16_ca(reinterpret_cast<unsigned char *>(wtab + (((size_t)st * 2 + 0) * NSLOTS + s) * kNTile) + q * 16,
                         reinterpret_cast<const unsigned char *>(a.expj_tables + (size_t)lead_tix[s] * kNotchN + (size_t)tibi * kNTile) + q * 16);
+          if (two)
+            cp_async16_ca(reinterpret_cast<unsigned char *>(wtab + (((size_t)st * 2 + 1) * NSLOTS + s) * kNTile) + q * 16,
+                          reinterpret_cast<const unsigned char *>(a.expj_tables + (size_t)alt_tix[s] * kNotchN + (size_t)tibi * kNTile) + q * 16);
+        }
     } else {
       staged_mask &= ~(1u << st);
     }
@@ -365,7 +401,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
     const bool active = have && blk >= (int64_t)run_begin && blk < (int64_t)own_end;
     const bool write = active && ((uint64_t)blk >= own_begin);
     float2 *outp = a.out + (uint64_t)(active ? blk : 0) * kNotchN + (uint64_t)tib * kNTile;
-    unsigned char *orow_base = smem + kNotchSmemIn + (size_t)warp * 32 * kNPitch;   // the warp's output tile
+    unsigned char *orow_base = smem + NotchSmem<NSLOTS>::in + (size_t)warp * 32 * kNPitch;   // the warp's output tile
     if (active) {
       if (tib == 0) {
         // Block start: entry snapshot, epoch switch / resets (sdr.h:97-109).
@@ -388,7 +424,7 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
 #pragma unroll
         for (int s = 0; s < NSLOTS; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN + tib * kNTile;
       }
-      const float4 *stab = reinterpret_cast<const float4 *>(wtab + (size_t)st * kNotchMaxSlots * kNTile);   // shared
+      const float4 *stab = reinterpret_cast<const float4 *>(wtab + ((size_t)st * 2 + ((set_mask >> st) & 1u)) * NSLOTS * kNTile);   // shared: this lane's set
       float4 *myout = reinterpret_cast<float4 *>(orow_base + (size_t)lane * kNPitch);
       uint32_t lead; { const unsigned char *unused; locate((uint64_t)blk * kNotchN + (uint64_t)tib * kNTile, unused, lead); }
       const unsigned char *myrow = smem + row_off + (size_t)st * 32 * kNPitch;
@@ -501,7 +537,6 @@ k_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint32_t nlist, const 
   }
 }
 
-constexpr size_t kNotchSmem = kNotchSmemIn + (size_t)kNWarps * 32 * kNPitch;   // + one output tile per warp
 
 template <int FMT, int NSLOTS>
 cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, uint32_t nlist,
@@ -509,7 +544,7 @@ cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, ui
   static PerDeviceMark configured;   // per device (function attributes belong to the context)
   if (configured.need(1)) {
     cudaError_t e = cudaFuncSetAttribute(k_notch_apply<FMT, NSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kNotchSmem);
+                                         (int)NotchSmem<NSLOTS>::total);
     if (e != cudaSuccess) return e;
     // Four resident CTAs per SM (4 x 55 KB of rows, table tiles and output tiles) cover the whole
     // grid at the bench size; the e^{j theta} tables are staged in shared memory, so L1 is not needed.
@@ -523,7 +558,7 @@ cudaError_t launch_apply_t(const NotchApplyArgs &a, const uint32_t *seg_list, ui
   const unsigned per_block = kNWarps * 32;
   const uint32_t lanes = seg_list ? nlist : a.nsegs;
   if (!lanes) return cudaSuccess;
-  k_notch_apply<FMT, NSLOTS><<<(lanes + per_block - 1) / per_block, per_block, kNotchSmem, st>>>(a, seg_list, nlist, guess);
+  k_notch_apply<FMT, NSLOTS><<<(lanes + per_block - 1) / per_block, per_block, NotchSmem<NSLOTS>::total, st>>>(a, seg_list, nlist, guess);
   return cudaGetLastError();
 }
 

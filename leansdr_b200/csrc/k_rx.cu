@@ -771,14 +771,23 @@ __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
   const uint32_t *src = a.sym_in + (size_t)span * a.span_cap + a.span_skip[span];
   const uint8_t *perm = a.rot_perm + (size_t)a.span_rot[span] * a.nsymbols;
   const bool identity = (a.span_rot[span] == 0);
-  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    uint32_t w = src[i];
-    if (!identity) {
-      uint32_t sym = (w >> 16) & 0xffu;
-      w = (w & 0xffffu) | ((uint32_t)perm[sym] << 16);
-    }
-    a.sym_out[base + i] = w;
+  auto fix = [&](uint32_t w) {
+    if (identity) return w;
+    const uint32_t sym = (w >> 16) & 0xffu;
+    return (w & 0xffffu) | ((uint32_t)perm[sym] << 16);
+  };
+  uint32_t *dst = a.sym_out + base;
+  // Head up to the first 16-byte boundary of the destination, then 16-byte stores (the source is only 4-byte
+  // aligned relative to it: four 4-byte loads per thread, still contiguous across the warp), then the tail.
+  const uint64_t head = min((uint64_t)((16u - ((uint32_t)reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) / 4u, n);
+  for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = fix(src[i]);
+  const uint64_t nvec = (n - head) / 4;
+  for (uint64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint64_t i = head + 4 * v;
+    const uint4 w = make_uint4(fix(__ldcs(src + i)), fix(__ldcs(src + i + 1)), fix(__ldcs(src + i + 2)), fix(__ldcs(src + i + 3)));
+    *reinterpret_cast<uint4 *>(dst + i) = w;
   }
+  for (uint64_t i = head + 4 * nvec + threadIdx.x; i < n; i += blockDim.x) dst[i] = fix(src[i]);
 }
 
 // Seam resolution on the device: kept symbol counts, skips, cumulative rotations and

@@ -13,6 +13,7 @@
 #include <string.h>
 #include <math.h>
 #include <fcntl.h>
+#include <time.h>
 
 #include "leansdr/framework.h"
 #include "leansdr/generic.h"
@@ -24,7 +25,7 @@
 using namespace leansdr;
 
 template<typename Tin>
-static int run_chain(const ldvb_config &cfg, unsigned long inbuf, bool info) {
+static int run_chain(const ldvb_config &cfg, unsigned long inbuf, bool info, bool timing) {
   scheduler sch;
   pipebuf<Tin> p_stdin(&sch, "stdin", inbuf);
   pipebuf<tspacket> p_ts(&sch, "TS packets", 1<<16);
@@ -41,7 +42,14 @@ static int run_chain(const ldvb_config &cfg, unsigned long inbuf, bool info) {
     new file_printer<int>(&sch, "LOCK %d\n", p_lock, 2);
     new file_printer<float>(&sch, "VBER %.6f\n", p_vber, 2);
   }
+  // --gpu-timing: wall clock of the scheduler loop alone (CUDA start-up and ldvb_create lie in front of it)
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   sch.run();
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if ( timing )
+    fprintf(stderr, "LDVB_TIMING samples=%lu seconds=%.6f\n", (unsigned long)p_stdin.total_written,
+	    (t1.tv_sec-t0.tv_sec) + 1e-9*(t1.tv_nsec-t0.tv_nsec));
   sch.shutdown();
   return 0;
 }
@@ -51,7 +59,7 @@ int main(int argc, const char *argv[]) {
   ldvb_config_default(&cfg);
   cfg.max_batch = 1<<24;
   cfg.rx_mode = LDVB_RX_FAST;
-  bool info = false;
+  bool info = false, timing = false;
   for ( int i=1; i<argc; ++i ) {
     const char *a = argv[i];
     bool more = i+1 < argc;
@@ -89,15 +97,16 @@ int main(int argc, const char *argv[]) {
     else if ( !strcmp(a,"--gpu-exact") ) cfg.rx_mode = LDVB_RX_EXACT;
     else if ( !strcmp(a,"--gpu-batch") && more ) cfg.max_batch = strtoull(argv[++i], NULL, 0);
     else if ( !strcmp(a,"--gpu-device") && more ) cfg.device = atoi(argv[++i]);
+    else if ( !strcmp(a,"--gpu-timing") ) timing = true;
     else if ( !strcmp(a,"--fd-info") && more ) { info = (atoi(argv[++i]) == 2); cfg.vber = 1; }
     else { fprintf(stderr, "leandvb_gpu: unsupported option %s\n", a); return 1; }
   }
   unsigned long inbuf = cfg.max_batch;
   switch ( cfg.input_format ) {
-  case LDVB_FMT_U8:  return run_chain< complex<u8> >(cfg, inbuf, info);
-  case LDVB_FMT_S8:  return run_chain< complex<s8> >(cfg, inbuf, info);
-  case LDVB_FMT_U16: return run_chain< complex<u16> >(cfg, inbuf, info);
-  case LDVB_FMT_S16: return run_chain< complex<s16> >(cfg, inbuf, info);
-  default:           return run_chain< complex<f32> >(cfg, inbuf, info);
+  case LDVB_FMT_U8:  return run_chain< complex<u8> >(cfg, inbuf, info, timing);
+  case LDVB_FMT_S8:  return run_chain< complex<s8> >(cfg, inbuf, info, timing);
+  case LDVB_FMT_U16: return run_chain< complex<u16> >(cfg, inbuf, info, timing);
+  case LDVB_FMT_S16: return run_chain< complex<s16> >(cfg, inbuf, info, timing);
+  default:           return run_chain< complex<f32> >(cfg, inbuf, info, timing);
   }
 }
