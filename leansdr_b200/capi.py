@@ -179,6 +179,19 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def host_register(arr: np.ndarray) -> None:
+    """ldvb_host_register: page-locks a host array the caller owns (what the runnable does with its pipebuf)."""
+    rc = load().ldvb_host_register(_p(arr), arr.nbytes)
+    if rc:
+        raise LdvbError(rc, "ldvb_host_register", load().ldvb_strerror(rc).decode())
+
+
+def host_unregister(arr: np.ndarray) -> None:
+    rc = load().ldvb_host_unregister(_p(arr))
+    if rc:
+        raise LdvbError(rc, "ldvb_host_unregister", load().ldvb_strerror(rc).decode())
+
+
 def ring_unique_id() -> bytes:
     """ncclGetUniqueId through the library (one rank calls it, the bytes go to the others)."""
     b = np.zeros(128, np.uint8)

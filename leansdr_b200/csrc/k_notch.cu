@@ -146,10 +146,10 @@ k_notch_detect(NotchDetectArgs a) {
 // block b alone contributes to the estimate at its end.  One CTA per block, every sample of
 // the stream is read once (coalesced); the start state of a segment is then assembled from
 // the two block sums in front of its warm-up (guess_from_sums).
-template <int FMT>
+template <int FMT, int NSLOTS>
 __global__ void __launch_bounds__(128)
 k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][kNotchMaxSlots] */, const float *weights) {
-  __shared__ float2 part[4][kNotchMaxSlots];
+  __shared__ float2 part[4][NSLOTS];
   const uint64_t b = first_block + blockIdx.x;
   if (b >= a.nblocks) return;
   if (a.seg_blocks > 2) {
@@ -160,25 +160,54 @@ k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][
   int ep = 0;
   while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= b) ++ep;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float accr[kNotchMaxSlots], acci[kNotchMaxSlots];
-  for (int s = 0; s < kNotchMaxSlots; ++s) { accr[s] = 0.f; acci[s] = 0.f; }
+  float accr[NSLOTS], acci[NSLOTS];
+  const float2 *tab[NSLOTS];
+#pragma unroll
+  for (int s = 0; s < NSLOTS; ++s) { accr[s] = 0.f; acci[s] = 0.f; tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s] * kNotchN; }
+  // The block lies in ONE part of the two-part stream unless it is the block that holds the carry boundary.
   const uint64_t base = b * (uint64_t)kNotchN;
-  const float2 *tab[kNotchMaxSlots];
-  for (int s = 0; s < kNotchMaxSlots; ++s) tab[s] = a.expj_tables + (size_t)a.epochs[ep].table_index[s < a.nslots ? s : 0] * kNotchN;
-  // Plain streaming: every load of the block is issued before the first use (8 independent iterations in flight
-  // per thread), so that the kernel is bound by the one pass over the samples and not by load latency.
-#pragma unroll 8
-  for (int j = 0; j < kNotchN / 128; ++j) {
-    const int i = j * 128 + tid;
-    const float2 x = ld_raw<FMT>(a.src, base + i, a.scale);
-    const float w = __ldg(weights + (kNotchN - 1 - i)) * a.k;
-    for (int s = 0; s < a.nslots; ++s) {
-      const float2 e = __ldg(tab[s] + i);
-      accr[s] += (x.x * e.x + x.y * e.y) * w;
-      acci[s] += (-x.x * e.y + x.y * e.x) * w;
+  const bool split = a.src.main && base < a.src.c0 && base + kNotchN > a.src.c0;
+  const float k = a.k;
+  if (FMT >= 4 && !split) {
+    // cf32: two samples per 16-byte load when the block starts on a 16-byte boundary of its part, all loads of an
+    // iteration group issued before their first use (plain streaming, bound by the one pass over the samples).
+    const bool in_main = a.src.main && base >= a.src.c0;
+    const float2 *xs = in_main ? reinterpret_cast<const float2 *>(a.src.main) + (base - a.src.c0)
+                               : reinterpret_cast<const float2 *>(a.src.head) + base;
+    const bool al16 = (reinterpret_cast<uintptr_t>(xs) & 15u) == 0;
+#pragma unroll 4
+    for (int j = 0; j < kNotchN / 256; ++j) {
+      const int i = 2 * (j * 128 + tid);
+      float2 x0, x1;
+      if (al16) { const float4 v = __ldcs(reinterpret_cast<const float4 *>(xs + i)); x0 = make_float2(v.x, v.y); x1 = make_float2(v.z, v.w); }
+      else { x0 = __ldcs(xs + i); x1 = __ldcs(xs + i + 1); }
+      if (FMT == 4 && a.scale != 1.0f) { x0.x = fmul(x0.x, a.scale); x0.y = fmul(x0.y, a.scale); x1.x = fmul(x1.x, a.scale); x1.y = fmul(x1.y, a.scale); }
+      // weights[m] = (1-k)^m, m = 4095 - i: the pair (i, i+1) reads weights[4094 - i], weights[4095 - i]
+      const float2 wv = __ldg(reinterpret_cast<const float2 *>(weights + (kNotchN - 2 - i)));
+      const float w0 = wv.y * k, w1 = wv.x * k;
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) {
+        const float4 e = __ldg(reinterpret_cast<const float4 *>(tab[s] + i));
+        accr[s] += (x0.x * e.x + x0.y * e.y) * w0 + (x1.x * e.z + x1.y * e.w) * w1;
+        acci[s] += (-x0.x * e.y + x0.y * e.x) * w0 + (-x1.x * e.w + x1.y * e.z) * w1;
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < kNotchN / 128; ++j) {
+      const int i = j * 128 + tid;
+      const float2 x = ld_raw<FMT>(a.src, base + i, a.scale);
+      const float w = __ldg(weights + (kNotchN - 1 - i)) * k;
+#pragma unroll
+      for (int s = 0; s < NSLOTS; ++s) {
+        const float2 e = __ldg(tab[s] + i);
+        accr[s] += (x.x * e.x + x.y * e.y) * w;
+        acci[s] += (-x.x * e.y + x.y * e.x) * w;
+      }
     }
   }
-  for (int s = 0; s < a.nslots; ++s) {
+#pragma unroll
+  for (int s = 0; s < NSLOTS; ++s) {
     for (int o = 16; o; o >>= 1) {
       accr[s] += __shfl_xor_sync(0xffffffffu, accr[s], o);
       acci[s] += __shfl_xor_sync(0xffffffffu, acci[s], o);
@@ -186,7 +215,7 @@ k_notch_guess(NotchApplyArgs a, uint64_t first_block, float2 *sums /* [nblocks][
     if (lane == 0) part[warp][s] = make_float2(accr[s], acci[s]);
   }
   __syncthreads();
-  if (tid < a.nslots) {
+  if (tid < NSLOTS) {
     float2 t = part[0][tid];
     for (int w = 1; w < 4; ++w) { t.x += part[w][tid].x; t.y += part[w][tid].y; }
     sums[b * kNotchMaxSlots + tid] = t;
@@ -603,19 +632,31 @@ cudaError_t launch_notch_detect(NotchDetectArgs a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+namespace {
+template <int FMT>
+void guess_launch_f(const NotchApplyArgs &a, unsigned blocks, uint64_t first, float2 *sums, const float *weights, cudaStream_t st) {
+  switch (a.nslots) {
+    case 1: k_notch_guess<FMT, 1><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 2: k_notch_guess<FMT, 2><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 3: k_notch_guess<FMT, 3><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    default: k_notch_guess<FMT, 4><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+  }
+}
+}  // namespace
+
 cudaError_t launch_notch_guess(const NotchApplyArgs &a, float2 *sums, const float *weights, cudaStream_t st) {
   // Blocks whose sums can be asked for: from two blocks in front of the first warm-up on.
   const uint64_t lead = (uint64_t)a.warm_blocks + 2;
   const uint64_t first = a.block0 > lead ? a.block0 - lead : 0;
-  if (a.nblocks <= first) return cudaSuccess;
+  if (a.nblocks <= first || a.nslots < 1) return cudaSuccess;
   const unsigned blocks = (unsigned)(a.nblocks - first);
   switch (a.fmt) {
-    case 0: k_notch_guess<0><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
-    case 1: k_notch_guess<1><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
-    case 2: k_notch_guess<2><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
-    case 3: k_notch_guess<3><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
-    case 4: k_notch_guess<4><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
-    default: k_notch_guess<5><<<blocks, 128, 0, st>>>(a, first, sums, weights); break;
+    case 0: guess_launch_f<0>(a, blocks, first, sums, weights, st); break;
+    case 1: guess_launch_f<1>(a, blocks, first, sums, weights, st); break;
+    case 2: guess_launch_f<2>(a, blocks, first, sums, weights, st); break;
+    case 3: guess_launch_f<3>(a, blocks, first, sums, weights, st); break;
+    case 4: guess_launch_f<4>(a, blocks, first, sums, weights, st); break;
+    default: guess_launch_f<5>(a, blocks, first, sums, weights, st); break;
   }
   return cudaGetLastError();
 }

@@ -26,6 +26,7 @@
 #include "../../include/leandvb_b200.h"
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -80,6 +81,15 @@ struct ProfSpanRec { int id; cudaEvent_t a, b; };
 }  // namespace
 
 struct RingState;
+// Page-locked mailbox of the receiver stage: everything the host reads back after the spans ran arrives with ONE
+// stream synchronisation (seam plan, the carried loop state, the level check, the telemetry rows).
+struct RxMail {
+  uint64_t plan[16];
+  RxState last;
+  float power;
+  uint32_t nm;
+  float rows[4 * 4096];
+};
 struct ldvb_handle {
   ldvb_config cfg;
   cudaStream_t st = nullptr;
@@ -124,6 +134,7 @@ struct ldvb_handle {
   DevBuf d_notch_guess, d_notch_weights, d_notch_list;
   DevBuf d_notch_edge, d_notch_dump, d_notch_dumpblocks;   // k_notchfir.cu: segment edges, telemetry blocks
   bool rx_cold = true;                  // no FAST batch has settled the AGC of this stream yet
+  RxMail *rx_mail = nullptr;            // page-locked
   bool notch_v2 = false, notch_fused = false;
   uint64_t notch_target_segs = 0;
   DevBuf d_notch_state, d_notch_epochs, d_notch_entry, d_notch_exit, d_notch_exact, d_notch_bins, d_notch_blocks;
@@ -613,6 +624,7 @@ int ldvb_destroy(ldvb_handle *h) {
   for (int i = 0; i < ldvb_handle::kStages; ++i) { h->d_stage[i].release(); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
   if (h->copy_st) cudaStreamDestroy(h->copy_st);
   if (h->ts_queue) cudaFreeHost(h->ts_queue);
+  if (h->rx_mail) cudaFreeHost(h->rx_mail);
   if (h->notch_stage) cudaFreeHost(h->notch_stage);
   if (h->notch_stage_ev) cudaEventDestroy(h->notch_stage_ev);
   if (h->meas_host) cudaFreeHost(h->meas_host);
@@ -859,7 +871,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   for (int s = 0; s < kNotchMaxSlots; ++s) h->notch.slot[s].bin = -1;
   if (c.anf) {
     const uint64_t nblk = M / kNotchN + 2;
-    h->notch_tables_cap = 1024;        // 32 MB: a flat spectrum visits a new bin at almost every detect point
+    h->notch_tables_cap = 4096;        // 128 MB: a flat spectrum visits a new bin at almost every detect point; 4096 = all of them
     bool nok = h->d_notch_tables.alloc((size_t)h->notch_tables_cap * kNotchN * 8) == cudaSuccess &&
                h->d_notch_epochs.alloc(sizeof(NotchEpoch) * (nblk / 1024 + 4)) == cudaSuccess &&
                h->d_notch_entry.alloc(8 * kNotchMaxSlots * (nblk + 1)) == cudaSuccess &&
@@ -1422,16 +1434,23 @@ int rx_fast_reseed(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, std::vector<RxSe
 // contiguous symbol stream at sym_dst and carry the loop state.  rot0 / skip0 describe the
 // seam in front of span 0 (time-sharded mode; 0 otherwise).
 int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint32_t skip0, uint32_t *sym_dst,
-                    uint64_t room, uint64_t *produced_out, int *cum_out) {
+                    uint64_t room, uint64_t *produced_out, int *cum_out, const std::function<int()> *pre_sync = nullptr) {
   uint64_t produced = 0;
+  if (!h->rx_mail && cudaHostAlloc((void **)&h->rx_mail, sizeof(RxMail), cudaHostAllocDefault) != cudaSuccess)
+    return fail(h, LDVB_ENOMEM, "receiver mailbox");
+  RxMail *mail = h->rx_mail;
     // Fast path: offsets / skips / rotations are resolved on the device; the host reads back
     // four numbers.  Only when a seam failed (or a span overflowed) the seams are fetched
     // and repaired below.
     KL("rx_plan", launch_rx_plan(a.info, sa.seams, a.nspans, a.span_cap, h->cst.nrotations, rot0, skip0,
                                  h->d_rx_off.as<uint64_t>(), h->d_rx_skip.as<uint32_t>(), h->d_rx_rot.as<uint8_t>(),
                                  h->d_counts.as<uint64_t>(), h->st));
-    uint64_t plan[8];
-    CK(cudaMemcpyAsync(plan, h->d_counts.p, sizeof plan, cudaMemcpyDeviceToHost, h->st));
+    // One synchronisation for the plan, the end state of the last span (final unless a seam has to be repaired) and
+    // whatever else the caller wants to read back with them.
+    uint64_t *plan = mail->plan;
+    CK(cudaMemcpyAsync(plan, h->d_counts.p, 9 * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&mail->last, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
+    if (pre_sync) { int rcp = (*pre_sync)(); if (rcp) return rcp; }
     CK(cudaStreamSynchronize(h->st));
     int cum = (int)plan[2];
     const bool slow = (plan[0] != 0 || plan[3] != 0);
@@ -1530,8 +1549,11 @@ int rx_fast_resolve(ldvb_handle *h, RxArgs &a, RxStitchArgs &sa, int rot0, uint3
     KL("rx_compact", launch_rx_compact(ca, produced, h->st));
     // Carry: the end state of the last span.  Its phase is rotated back by the
     // cumulative rotation so that the next batch continues in span 0's frame.
-    CK(cudaMemcpyAsync(&h->rx_state, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    if (slow) {      // spans were re-run: fetch the state again
+      CK(cudaMemcpyAsync(&mail->last, a.state_end + (a.nspans - 1), sizeof(RxState), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+    }
+    h->rx_state = mail->last;
     if (cum) {
       // Span frames differ by cum*65536/nrot phase units: symbols of the last span
       // were de-rotated by `cum`; adding the same angle to the PLL phase makes the
@@ -1615,6 +1637,7 @@ int run_receiver(ldvb_handle *h) {
   const uint64_t room = h->s_sym.cap - h->s_sym.count;
   uint64_t produced = 0;
   const bool fast = (c.rx_mode == LDVB_RX_FAST) && nchunks >= 4;
+  bool fast_rows_done = false;
   if (!fast) {
     a.span_chunks = (uint32_t)std::min<uint64_t>(nchunks, 0xffffffffu);
     a.warm_chunks = 0;
@@ -1648,34 +1671,92 @@ int run_receiver(ldvb_handle *h) {
     }
   } else {
     int rcf;
+    bool rows_fetched = false;
+    // What is read back together with the seam plan (one synchronisation): the telemetry rows of the kernel and,
+    // in the steady state, the level check.
+    const std::function<int()> fetch_rows = [&]() -> int {
+      RxMail *mail = h->rx_mail;
+      CK(cudaMemcpyAsync(&mail->nm, h->d_rx_measn.p, 4, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaMemcpyAsync(mail->rows, h->d_rx_meas.p, sizeof mail->rows, cudaMemcpyDeviceToHost, h->st));
+      if (h->d_rx_power.p) CK(cudaMemcpyAsync(&mail->power, h->d_rx_power.p, 4, cudaMemcpyDeviceToHost, h->st));
+      rows_fetched = true;
+      return LDVB_OK;
+    };
+    const float est_carried = h->rx_state.est_insp;      // (the estimate the spans of this batch start from)
+    auto is_far = [&](float power) {
+      return (power > 0.f) && (est_carried > 2.0f * power || est_carried < 0.5f * power);
+    };
+    const bool settle_on = !c.hs && c.settle_chunks >= 0;
     // AGC settling: an estimate far from the input level is pulled in by a serial (exact) pass first.
-    float power = 0; bool far = false;
-    if ((rcf = rx_level_check(h, a.x, nchunks * kRxChunk, &power, &far))) return rcf;
-    uint64_t n0 = 0, K = 0;
     // The first FAST batch of a stream always settles: spans restart from the carried AGC estimate and move it by
     // only ~9 % per batch (S + W chunks at k = 0.01), so an estimate that starts at the constructor's 75^2
     // (sdr.h:727) would stay 10-20 % off the serial one for many batches -- hard decisions do not care, soft
     // costs (proportional to the gain squared) do: measured 13 % mean cost deviation without this (bench.py,
     // fast_vs_exact.steady_state).
-    if (h->rx_cold && !c.hs && c.settle_chunks >= 0) far = true;
-    if (far) {
-      h->rx_cold = false;
-      K = std::min(nchunks, rx_settle_chunks(h));
-      if (nchunks - K < 8) K = nchunks;                  // too little left for spans
-      if ((rcf = rx_settle(h, a, K, sym_dst, room, &n0))) return rcf;
-    }
-    produced = n0;
-    if (K < nchunks) {
+    // Steady state (the stream has settled): the level check does not gate the launch.  The power of the batch head
+    // is measured on the device, the spans are launched from the carried state, and the verdict comes back with the
+    // seam plan; in the rare case that the level has jumped by more than a factor 2 the batch is redone the slow way.
+    bool redo = false;
+    const RxState carried = h->rx_state;
+    const ldvb_meas meas_before = h->meas;
+    if (settle_on && !h->rx_cold && nchunks >= 16) {
+      KL("rx_power", launch_rx_power(a.x, (uint32_t)std::min<uint64_t>(nchunks * kRxChunk, 16384), h->d_rx_power.as<float>(), h->st));
+      RxArgs a2 = a;
       RxStitchArgs sa;
-      if ((rcf = rx_fast_launch(h, a, sa, nchunks - K))) return rcf;
+      if ((rcf = rx_fast_launch(h, a2, sa, nchunks))) return rcf;
       int cum = 0;
       uint64_t n1 = 0;
-      if ((rcf = rx_fast_resolve(h, a, sa, 0, 0, sym_dst + n0, room - n0, &n1, &cum))) return rcf;
-      produced += n1;
+      if ((rcf = rx_fast_resolve(h, a2, sa, 0, 0, sym_dst, room, &n1, &cum, &fetch_rows))) return rcf;
+      if (is_far(h->rx_mail->power)) {
+        redo = true;                                   // nothing is committed yet: symbols are overwritten below
+        h->rx_state = carried;
+        h->meas = meas_before;
+        rows_fetched = false;
+        CK(cudaMemsetAsync(h->d_rx_measn.p, 0, 4, h->st));
+      } else {
+        produced = n1;
+      }
+    } else {
+      redo = true;
     }
+    if (redo) {
+      float power = 0; bool far = false;
+      if ((rcf = rx_level_check(h, a.x, nchunks * kRxChunk, &power, &far))) return rcf;
+      uint64_t n0 = 0, K = 0;
+      if (h->rx_cold && settle_on) far = true;
+      if (far) {
+        h->rx_cold = false;
+        K = std::min(nchunks, rx_settle_chunks(h));
+        if (nchunks - K < 8) K = nchunks;                  // too little left for spans
+        if ((rcf = rx_settle(h, a, K, sym_dst, room, &n0))) return rcf;
+      }
+      produced = n0;
+      if (K < nchunks) {
+        RxStitchArgs sa;
+        if ((rcf = rx_fast_launch(h, a, sa, nchunks - K))) return rcf;
+        int cum = 0;
+        uint64_t n1 = 0;
+        if ((rcf = rx_fast_resolve(h, a, sa, 0, 0, sym_dst + n0, room - n0, &n1, &cum, &fetch_rows))) return rcf;
+        produced += n1;
+      }
+    }
+    if (rows_fetched) {
+      const uint32_t nm = std::min(h->rx_mail->nm, 4096u);
+      const float *m = h->rx_mail->rows;
+      std::vector<std::pair<float, int>> order;
+      for (uint32_t i = 0; i < nm; ++i) order.push_back({m[4 * i], (int)i});
+      std::sort(order.begin(), order.end());
+      for (auto &o : order) {
+        h->meas_log.push_back(m[4 * o.second + 1]);
+        h->meas_log.push_back(m[4 * o.second + 2]);
+        const float q = m[4 * o.second + 3];                               // est_sp / est_ep, -1: est_ep == 0
+        h->meas_log.push_back(q < 0 ? 0.0f : 10 * logf(q) / logf(10));     // sdr.h:910-911
+      }
+    }
+    fast_rows_done = rows_fetched;
   }
   // Measurements recorded by the kernel: {chunk, freq_tap, ss, mer}
-  {
+  if (!fast_rows_done) {
     uint32_t nm = 0;
     CK(cudaMemcpy(&nm, h->d_rx_measn.p, 4, cudaMemcpyDeviceToHost));
     nm = std::min(nm, 4096u);

@@ -32,7 +32,9 @@ timeout 600 ncu --set full --clock-control none --import-source on \
 fi
 if has variants; then
 for v in ${VARIANTS:-u8 hs viterbi viterbi78}; do
-  timeout 300 python bench.py --variant $v --steps 3 ${VARIANT_ARGS} > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
+  extra=""
+  case $v in viterbi) extra="--cpu-sample-packets 2048";; viterbi78) extra="--cpu-sample-packets 512";; esac
+  timeout 400 python bench.py --variant $v --steps 3 $extra ${VARIANT_ARGS} > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
 done
 fi
 if has smoke; then
@@ -43,7 +45,7 @@ python - <<'PY'
 import json
 for f in ("bench_n1", "bench_ref_n1", "bench_u8", "bench_hs", "bench_viterbi", "bench_viterbi78"):
     try:
-        b = json.load(open(f"gpurun_out/{f}.json"))
+        b = json.loads([l for l in open(f"gpurun_out/{f}.json") if l.startswith("{")][-1])
         print(f, "value=%.0f" % b["value"], "ms=%.2f" % b["ms_per_step"], "e2e=%.0f" % b["e2e"]["value"], b.get("seams"), b.get("ts_bit_exact_vs_reference"))
         if "kernel_ms_per_step" in b: print("   ", {k: round(v, 3) for k, v in b["kernel_ms_per_step"].items()}); print("   ", b.get("fast_vs_exact"))
     except Exception as e:

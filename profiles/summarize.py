@@ -49,7 +49,7 @@ def launch_list():
         sel = [t for g, t in v if gsize(g) == gmax]
         full[k] = sum(sel) / len(sel)
     full_sum = sum(full.values())
-    bench = json.load(open(os.path.join(src, "bench_n1.json")))
+    bench = json.loads([l for l in open(os.path.join(src, "bench_n1.json")) if l.startswith("{")][-1])
     live = bench["kernel_ms_per_step"]; step = bench["ms_per_step"]
     allms = sum(tot.values())
     out = [f"# {tag} -- ncu launch list of the bench command (per-kernel device time)", "",
@@ -105,11 +105,11 @@ def ncu_full():
     ix = {h: i for i, h in enumerate(hdr)}
     n = 128324096
     out = [f"# {tag} -- `ncu --set full --clock-control none --import-source on` of the four heaviest kernels at the bench size", "",
-           "Command (gpurun, 1 GPU, profiles/run_gpu_round1.sh): `ncu --set full --clock-control none --import-source on -k "
+           "Command (gpurun, 1 GPU, profiles/run_gpu_round2.sh): `ncu --set full --clock-control none --import-source on -k "
            "regex:'k_rx$|k_notch_apply|k_frontend|k_notch_guess' -s 8 -c 4 python bench.py --steps 1 --warmup 3 --no-cpu` "
            f"({n} f32 samples per launch).  Per launch, under the profiler (cold, serialised): use shares and ratios, not absolutes.", ""]
     traffic = {"_source": "ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 --no-cpu (%d f32 samples per launch), "
-                          "profiles/run_gpu_round1.sh; dram__bytes_read.sum + dram__bytes_write.sum per launch" % n,
+                          "profiles/run_gpu_round2.sh; dram__bytes_read.sum + dram__bytes_write.sum per launch" % n,
                "samples_per_launch": n, "kernels": {}}
     mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
     for r in rows[2:]:

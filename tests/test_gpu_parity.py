@@ -601,3 +601,26 @@ def test_async_push_equals_synchronous_push(product, mode):
     rx.close()
     assert len(want) > 1300 and np.array_equal(got, want)
     assert m["ts_packets"] == len(want) and m["samples_in"] == n
+
+
+def test_push_from_a_registered_pipebuf(product):
+    """ldvb_host_register: the caller's own buffer (the reference's pipebuf, `new T[size]`) is page-locked once and every
+    push out of it -- at any offset, like pipereader::rd() -- is a direct DMA transfer; same packets as from pageable
+    memory, and registering twice or unregistering is harmless."""
+    P = product
+    raw = V.ref_iq(1200, fmt="f32")
+    n = raw.size // 2
+    kw = dict(fmt="f32", resample=True, rx_mode=P.RX_FAST, max_batch=n)
+    a = P.Receiver(**kw); a.push(raw); want = a.pull_all(); a.close()
+    pipe = np.zeros(raw.size + 4096, np.float32)
+    P.host_register(pipe)
+    P.host_register(pipe)                        # already registered: not an error
+    pipe[2 * 77: 2 * 77 + raw.size] = raw        # (data does not start at the beginning of the registered range)
+    b = P.Receiver(async_push=True, **kw)
+    half = (n // 2) * 2
+    b.push(pipe[2 * 77: 2 * 77 + half])
+    b.push(pipe[2 * 77 + half: 2 * 77 + raw.size])
+    got = b.pull_all()
+    b.close()
+    P.host_unregister(pipe)
+    assert len(want) > 1000 and np.array_equal(got, want)
