@@ -5,14 +5,14 @@
 // operations per sample and component); the products in front of it (bb*k) and everything behind it
 // (out = x - estim*e, the FIR) are data parallel.  k_notch_apply (k_notch.cu) lets every lane do all of it for
 // its own segment, so the whole kernel runs at the speed of 1-2 warps per scheduler.  Here the roles are split
-// inside a CTA of 32 segments ("rows"):
+// inside a CTA of 16 segments ("rows"):
 //
-//   worker warps (8 x 4 rows, lane = sample of a 32-sample tile):
+//   worker warps (8 x 2 rows, lane = TWO consecutive samples of a 64-sample tile: 16-byte accesses throughout):
 //     LOAD(t+2)  the rows' next raw tile by 16-byte cp.async (each warp loads the rows it works on)
 //     A(t)       convert, bk = (x * conj(e)) * k                        -> shared tile bk[t & 1]
 //     CD(t-2)    out = gain * (x - sum estim*e); FIR over the row        <- shared tile est[t & 1]
 //   chain warp (lane = row):
-//     B(t-1)     estim = bk + estim*(1-k), 32 steps per tile, both tiles as conflict-free float4 columns
+//     B(t-1)     estim = bk + estim*(1-k), 64 steps per tile, both tiles as conflict-free float4 columns
 //
 // one __syncthreads per tile step.  Same arithmetic, same order, same rounding as the reference; segments,
 // warm-up from the weighted-sum guess, bit-for-bit verification of entry(j) == exit(j-1) and the repair path
@@ -34,15 +34,17 @@ namespace ldvb {
 
 namespace {
 
-constexpr int kFT = 32;                         // samples per tile = lanes along a row
-constexpr int kFRows = 32;                      // segments per CTA
+constexpr int kFT = 64;                         // samples per tile: every worker lane handles TWO consecutive samples of a row
+constexpr int kFRows = kNotchFirRows;           // 16 segments per CTA (the chain warp uses 16 of its lanes)
 constexpr int kFWorkers = 8;                    // worker warps, kFRows / kFWorkers rows each
 constexpr int kFRowsPerWarp = kFRows / kFWorkers;
 constexpr int kFThreads = (kFWorkers + 1) * 32; // + the chain warp (warp 0)
 constexpr int kFRawStages = 5;                  // raw tiles t+2 (in flight) ... t-2 (read again by CD)
-constexpr int kFPitch = (kFT + 2) * 8;          // cf32 tiles: 272 B rows, 16 (mod 128): float4 columns are conflict-free
+constexpr int kFPitch = (kFT + 2) * 8;          // cf32 tiles: 528 B rows, 16 (mod 128): float4 columns are conflict-free
 constexpr int kFTilesPerBlock = kNotchN / kFT;
+constexpr int kFTileShift = 6;                  // log2(kFTilesPerBlock)
 static_assert(kFirFuseMaxTaps <= kFT, "the FIR history of a tile must fit in the previous tile");
+static_assert((1 << kFTileShift) == kFTilesPerBlock && kFT == 64, "tile geometry");
 
 struct FRow {
   int64_t base;                                 // block of local tile 0
@@ -92,7 +94,7 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
   for (int s = 0; s < NSLOTS; ++s) { er[s] = 0.f; ei[s] = 0.f; }
   bool forced = false;
   int start_kind = 0;
-  if (warp == 0) {
+  if (warp == 0 && lane < kFRows) {
     const uint32_t g = blockIdx.x * kFRows + lane;
     uint32_t seg; bool have;
     if (repair) { have = g < nlist; seg = have ? seg_list[g] : 0; }
@@ -135,23 +137,28 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
 
   if (warp == 0) {
     // ================================================================ chain warp
-    const FRow r = s_row[lane];
+    FRow r;
+    if (lane < kFRows) r = s_row[lane];
+    else { r.base = 0; r.own_begin = r.own_end = r.run_begin = 0; r.seg = 0; r.have = 0; r.ep0 = 0; r.pad = 0; }
     int ep = r.ep0;
+    const int lb_run = r.have ? (int)((int64_t)r.run_begin - r.base) : 0;
+    const int lb_end = r.have ? (int)((int64_t)r.own_end - r.base) : 0;
     for (int64_t s = 0; s < total + 2; ++s) {
       const int64_t t = s - 1;
       if (t >= 0 && t < total) {
-        const int64_t blk = r.base + t / kFTilesPerBlock;
-        const int tib = (int)(t % kFTilesPerBlock);
-        const bool active = r.have && blk >= (int64_t)r.run_begin && blk < (int64_t)r.own_end;
+        const int lb = (int)(t >> kFTileShift);
+        const int tib = (int)(t & (kFTilesPerBlock - 1));
+        const bool active = lb >= lb_run && lb < lb_end;
         if (active) {
           if (tib == 0) {
             // Block start: entry snapshot, epoch switch / resets (sdr.h:97-109).
-            while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= (uint64_t)blk) ++ep;
-            if ((uint64_t)blk == r.own_begin && a.seg_entry && !forced) {
+            const uint64_t blk = (uint64_t)(r.base + lb);
+            while (ep + 1 < a.nepochs && a.epochs[ep + 1].first_block <= blk) ++ep;
+            if (blk == r.own_begin && a.seg_entry && !forced) {
 #pragma unroll
               for (int sl = 0; sl < NSLOTS; ++sl) a.seg_entry[(size_t)r.seg * kNotchMaxSlots + sl] = make_float2(er[sl], ei[sl]);
             }
-            if (a.epochs[ep].first_block == (uint64_t)blk) {
+            if (a.epochs[ep].first_block == blk) {
 #pragma unroll
               for (int sl = 0; sl < NSLOTS; ++sl)
                 if (a.epochs[ep].reset[sl]) { er[sl] = 0.f; ei[sl] = 0.f; }
@@ -159,14 +166,30 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
           }
           const unsigned char *bk = s_bk + (size_t)(t & 1) * SM::tile + (size_t)lane * kFPitch;
           unsigned char *es = s_est + (size_t)(t & 1) * SM::tile + (size_t)lane * kFPitch;
+          // 16 samples (8 float4) per slot at a time; the loads of the next group are issued in front of the stores of
+          // this one (the compiler cannot move them there: both go through the same shared array)
+          constexpr int G = 8;
 #pragma unroll
-          for (int n = 0; n < kFT; n += 2) {
+          for (int sl = 0; sl < NSLOTS; ++sl) {
+            const float4 *bp = reinterpret_cast<const float4 *>(bk + (size_t)sl * kFRows * kFPitch);
+            float4 *ep4 = reinterpret_cast<float4 *>(es + (size_t)sl * kFRows * kFPitch);
+            float4 b[G], nb[G];
 #pragma unroll
-            for (int sl = 0; sl < NSLOTS; ++sl) {
-              const float4 b = *reinterpret_cast<const float4 *>(bk + (size_t)sl * kFRows * kFPitch + n * 8);
-              const float r0 = fadd(b.x, fmul(er[sl], omk)), i0 = fadd(b.y, fmul(ei[sl], omk));
-              er[sl] = fadd(b.z, fmul(r0, omk)); ei[sl] = fadd(b.w, fmul(i0, omk));
-              *reinterpret_cast<float4 *>(es + (size_t)sl * kFRows * kFPitch + n * 8) = make_float4(r0, i0, er[sl], ei[sl]);
+            for (int q = 0; q < G; ++q) b[q] = bp[q];
+#pragma unroll
+            for (int c = 0; c < kFT / 2 / G; ++c) {
+              if (c + 1 < kFT / 2 / G) {
+#pragma unroll
+                for (int q = 0; q < G; ++q) nb[q] = bp[(c + 1) * G + q];
+              }
+#pragma unroll
+              for (int q = 0; q < G; ++q) {
+                const float r0 = fadd(b[q].x, fmul(er[sl], omk)), i0 = fadd(b[q].y, fmul(ei[sl], omk));
+                er[sl] = fadd(b[q].z, fmul(r0, omk)); ei[sl] = fadd(b[q].w, fmul(i0, omk));
+                ep4[c * G + q] = make_float4(r0, i0, er[sl], ei[sl]);
+              }
+#pragma unroll
+              for (int q = 0; q < G; ++q) b[q] = nb[q];
             }
           }
         }
@@ -185,8 +208,9 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
 
   // ================================================================== worker warps
   // Everything that depends on (row, block) only -- is the row active there, where do its samples lie, which
-  // tables are in force, where do its outputs go -- is worked out once per 4096-sample block (128 tiles) and kept
-  // in registers; a tile step then costs a handful of instructions per row besides the arithmetic.
+  // tables are in force, where do its outputs go -- is worked out once per 4096-sample block (64 tiles) and kept
+  // in registers; a tile step then costs a handful of instructions per row besides the arithmetic.  A lane handles
+  // the samples 2*lane and 2*lane + 1 of a row-tile: 16-byte shared-memory and table accesses.
   const int w = warp - 1;
   const int row0 = w * kFRowsPerWarp;
   const int N = FIR ? fa.fir_n : 0, L = N > 0 ? N - 1 : 0;
@@ -194,7 +218,6 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
   constexpr int kLoadIters = (kFRowsPerWarp * kPieces + 31) / 32;
   constexpr uint32_t kStageBytes = (uint32_t)kFRows * kRawPitch;
 
-  // row geometry in local block indices (tile t lies in local block t / 128)
   int lb_run[kFRowsPerWarp], lb_own[kFRowsPerWarp], lb_end[kFRowsPerWarp];
 #pragma unroll
   for (int rr = 0; rr < kFRowsPerWarp; ++rr) {
@@ -203,8 +226,6 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
     lb_own[rr] = r.have ? (int)((int64_t)r.own_begin - r.base) : 0;
     lb_end[rr] = r.have ? (int)((int64_t)r.own_end - r.base) : 0;
   }
-  // Element offset in front of the rows of a block (rows in the user's buffer start `lead_main` elements after a
-  // 16-byte boundary) and the byte address of the block's first sample, aligned down.
   auto block_src = [&](int rr, int lb, uint32_t &lead) -> const unsigned char * {
     uint64_t idx = (uint64_t)(s_row[row0 + rr].base + lb) * kNotchN;
     const unsigned char *part = static_cast<const unsigned char *>(a.src.head);
@@ -213,7 +234,7 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
     return part + (idx - lead) * bps;
   };
 
-  // ---- LOAD state: this lane's pieces of the warp's four rows
+  // ---- LOAD state: this lane's pieces of the warp's rows
   const unsigned char *ld_src[kLoadIters];
   uint32_t ld_dst[kLoadIters];
   uint32_t ld_ok = 0;
@@ -225,8 +246,7 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
       const int rr = piece / kPieces, q = piece % kPieces;
       ld_src[i] = nullptr; ld_dst[i] = 0;
       if (rr < kFRowsPerWarp) {
-        // (rr is a per-lane value here: plain shared-memory reads instead of the register copies)
-        const FRow &r = s_row[row0 + rr];
+        const FRow &r = s_row[row0 + rr];          // (rr is a per-lane value here)
         const int64_t blk = r.base + lb;
         if (r.have && blk >= (int64_t)r.run_begin && blk < (int64_t)r.own_end) {
           uint32_t lead;
@@ -244,7 +264,7 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
   auto load = [&](int64_t t) {
     if (t < total) {
       const int tib = (int)(t & (kFTilesPerBlock - 1));
-      if (tib == 0) load_block((int)(t >> 7));
+      if (tib == 0) load_block((int)(t >> kFTileShift));
       unsigned char *stage = s_raw + stL * kStageBytes;
       const uint32_t toff = (uint32_t)tib * kFT * bps;
 #pragma unroll
@@ -254,20 +274,19 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
     stL = (stL + 1 == kFRawStages) ? 0 : stL + 1;
     cp_async_commit();
   };
-  static_assert(kFTilesPerBlock == 128, "t >> 7");
 
-  // ---- A state
+  // ---- A / CD state
   uint32_t actA = 0, xoffA[kFRowsPerWarp];
   const float2 *tabA[kFRowsPerWarp][NSLOTS];
   int epA[kFRowsPerWarp];
-  // ---- CD state
   uint32_t actC = 0, firstC = 0, lastC = 0, dumpC = 0, xoffC[kFRowsPerWarp];
   const float2 *tabC[kFRowsPerWarp][NSLOTS];
-  float2 *yC[kFRowsPerWarp];             // FIR: fa.y + (carry + g - N) of this lane at tile 0 of the block; else a.out + g
+  float2 *yC[kFRowsPerWarp];             // FIR: fa.y + (carry + g - N) of this lane's first sample at tile 0 of the block; else a.out + g
+  float2 *dmpC[kFRowsPerWarp];
   int epC[kFRowsPerWarp];
 #pragma unroll
   for (int rr = 0; rr < kFRowsPerWarp; ++rr) {
-    epA[rr] = epC[rr] = s_row[row0 + rr].ep0; xoffA[rr] = xoffC[rr] = 0; yC[rr] = nullptr;
+    epA[rr] = epC[rr] = s_row[row0 + rr].ep0; xoffA[rr] = xoffC[rr] = 0; yC[rr] = nullptr; dmpC[rr] = nullptr;
 #pragma unroll
     for (int sl = 0; sl < NSLOTS; ++sl) tabA[rr][sl] = tabC[rr][sl] = a.expj_tables;
   }
@@ -280,9 +299,9 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
       const uint64_t blk = (uint64_t)(s_row[row0 + rr].base + lb);
       while (epA[rr] + 1 < a.nepochs && a.epochs[epA[rr] + 1].first_block <= blk) ++epA[rr];
 #pragma unroll
-      for (int sl = 0; sl < NSLOTS; ++sl) tabA[rr][sl] = a.expj_tables + (size_t)a.epochs[epA[rr]].table_index[sl] * kNotchN + lane;
+      for (int sl = 0; sl < NSLOTS; ++sl) tabA[rr][sl] = a.expj_tables + (size_t)a.epochs[epA[rr]].table_index[sl] * kNotchN + 2 * lane;
       uint32_t lead; block_src(rr, lb, lead);
-      xoffA[rr] = (uint32_t)(row0 + rr) * kRawPitch + (lead + lane) * bps;
+      xoffA[rr] = (uint32_t)(row0 + rr) * kRawPitch + (lead + 2 * lane) * bps;
     }
   };
   auto block_C = [&](int lb) {
@@ -297,21 +316,35 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
       if (lb == lb_own[rr]) firstC |= 1u << rr;
       if (lb == lb_end[rr] - 1) lastC |= 1u << rr;
 #pragma unroll
-      for (int sl = 0; sl < NSLOTS; ++sl) tabC[rr][sl] = a.expj_tables + (size_t)a.epochs[epC[rr]].table_index[sl] * kNotchN + lane;
+      for (int sl = 0; sl < NSLOTS; ++sl) tabC[rr][sl] = a.expj_tables + (size_t)a.epochs[epC[rr]].table_index[sl] * kNotchN + 2 * lane;
       uint32_t lead; block_src(rr, lb, lead);
-      xoffC[rr] = (uint32_t)(row0 + rr) * kRawPitch + (lead + lane) * bps;
-      const uint64_t g0 = blk * kNotchN + lane;
+      xoffC[rr] = (uint32_t)(row0 + rr) * kRawPitch + (lead + 2 * lane) * bps;
+      const uint64_t g0 = blk * kNotchN + 2 * lane;
       if (FIR) yC[rr] = fa.y + ((int64_t)fa.carry + (int64_t)g0 - N);   // (may point in front of y for the first samples of the first batch: guarded below)
       else yC[rr] = a.out + g0;
       // telemetry: is this block one that cnr_fft / spectrum will look at?  (sorted list, a few entries)
       if (fa.ndump) {
         int lo = 0, hi = fa.ndump;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (fa.dump_blocks[mid] < blk) lo = mid + 1; else hi = mid; }
-        if (lo < fa.ndump && fa.dump_blocks[lo] == blk) dumpC |= 1u << rr;
+        if (lo < fa.ndump && fa.dump_blocks[lo] == blk) { dumpC |= 1u << rr; dmpC[rr] = fa.dump + (size_t)lo * kNotchN + 2 * lane; }
       }
     }
   };
   const bool first_batch = FIR && fa.carry < (uint32_t)N;            // outputs with kk < 0 do not exist
+  // two consecutive samples of a staged raw row
+  auto raw_pair = [&](const unsigned char *p, float2 &x0, float2 &x1) {
+    if (FMT >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+      const float4 v = *reinterpret_cast<const float4 *>(p);
+      x0 = make_float2(v.x, v.y); x1 = make_float2(v.z, v.w);
+      if (FMT == 4 && a.scale != 1.0f) { x0.x = fmul(x0.x, a.scale); x0.y = fmul(x0.y, a.scale); x1.x = fmul(x1.x, a.scale); x1.y = fmul(x1.y, a.scale); }
+    } else {
+      x0 = row_sample<FMT>(p, 0, a.scale); x1 = row_sample<FMT>(p, 1, a.scale);
+    }
+  };
+  auto store_pair = [&](float2 *dst, float2 v0, float2 v1) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) st_stream(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v0.y, v1.x, v1.y));
+    else { st_stream(dst, v0); st_stream(dst + 1, v1); }
+  };
 
   load(0);
   load(1);
@@ -323,21 +356,25 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
     // ------------------------------------------------------------------ A(s)
     if (s < total) {
       const int tib = (int)(s & (kFTilesPerBlock - 1));
-      if (tib == 0) block_A((int)(s >> 7));
+      if (tib == 0) block_A((int)(s >> kFTileShift));
       if (actA) {
         const unsigned char *stage = s_raw + stA * kStageBytes;
-        unsigned char *bkt = s_bk + (uint32_t)(s & 1) * (uint32_t)SM::tile + (uint32_t)row0 * kFPitch + lane * 8;
+        unsigned char *bkt = s_bk + (uint32_t)(s & 1) * (uint32_t)SM::tile + (uint32_t)row0 * kFPitch + lane * 16;
         const uint32_t eoff = (uint32_t)tib * kFT;
 #pragma unroll
         for (int rr = 0; rr < kFRowsPerWarp; ++rr) {
           if (!((actA >> rr) & 1u)) continue;
-          const float2 x = row_sample<FMT>(stage + xoffA[rr], 0, a.scale);
+          float2 x0, x1;
+          raw_pair(stage + xoffA[rr], x0, x1);
 #pragma unroll
           for (int sl = 0; sl < NSLOTS; ++sl) {
-            const float2 e = __ldg(tabA[rr][sl] + eoff);
-            const float br = fmul(fadd(fmul(x.x, e.x), fmul(x.y, e.y)), k);
-            const float bi = fmul(fadd(fmul(-x.x, e.y), fmul(x.y, e.x)), k);
-            *reinterpret_cast<float2 *>(bkt + (uint32_t)sl * kFRows * kFPitch + rr * kFPitch) = make_float2(br, bi);
+            const float4 e = __ldg(reinterpret_cast<const float4 *>(tabA[rr][sl] + eoff));
+            float4 b;
+            b.x = fmul(fadd(fmul(x0.x, e.x), fmul(x0.y, e.y)), k);
+            b.y = fmul(fadd(fmul(-x0.x, e.y), fmul(x0.y, e.x)), k);
+            b.z = fmul(fadd(fmul(x1.x, e.z), fmul(x1.y, e.w)), k);
+            b.w = fmul(fadd(fmul(-x1.x, e.w), fmul(x1.y, e.z)), k);
+            *reinterpret_cast<float4 *>(bkt + (uint32_t)sl * kFRows * kFPitch + rr * kFPitch) = b;
           }
         }
       }
@@ -346,84 +383,94 @@ k_notch_fir(NotchFirArgs fa, const uint32_t *seg_list, uint32_t nlist, const flo
     const int64_t t = s - 2;
     if (t >= 0) {
       const int tib = (int)(t & (kFTilesPerBlock - 1));
-      if (tib == 0) block_C((int)(t >> 7));
+      if (tib == 0) block_C((int)(t >> kFTileShift));
       if (actC) {
         const unsigned char *stage = s_raw + stC * kStageBytes;
-        const unsigned char *estt = s_est + (uint32_t)(t & 1) * (uint32_t)SM::tile + (uint32_t)row0 * kFPitch + lane * 8;
+        const unsigned char *estt = s_est + (uint32_t)(t & 1) * (uint32_t)SM::tile + (uint32_t)row0 * kFPitch + lane * 16;
         const uint32_t eoff = (uint32_t)tib * kFT;
-        float2 out[kFRowsPerWarp];
+        float2 o0[kFRowsPerWarp], o1[kFRowsPerWarp];
 #pragma unroll
         for (int rr = 0; rr < kFRowsPerWarp; ++rr) {
-          out[rr] = make_float2(0.f, 0.f);
+          o0[rr] = o1[rr] = make_float2(0.f, 0.f);
           if (!((actC >> rr) & 1u)) continue;
-          const float2 x = row_sample<FMT>(stage + xoffC[rr], 0, a.scale);
-          float outr = x.x, outi = x.y;
+          float2 x0, x1;
+          raw_pair(stage + xoffC[rr], x0, x1);
+          float r0 = x0.x, i0 = x0.y, r1 = x1.x, i1 = x1.y;
 #pragma unroll
           for (int sl = 0; sl < NSLOTS; ++sl) {
-            const float2 e = __ldg(tabC[rr][sl] + eoff);
-            const float2 es = *reinterpret_cast<const float2 *>(estt + (uint32_t)sl * kFRows * kFPitch + rr * kFPitch);
-            outr = fsub(outr, fsub(fmul(es.x, e.x), fmul(es.y, e.y)));
-            outi = fsub(outi, fadd(fmul(es.x, e.y), fmul(es.y, e.x)));
+            const float4 e = __ldg(reinterpret_cast<const float4 *>(tabC[rr][sl] + eoff));
+            const float4 es = *reinterpret_cast<const float4 *>(estt + (uint32_t)sl * kFRows * kFPitch + rr * kFPitch);
+            r0 = fsub(r0, fsub(fmul(es.x, e.x), fmul(es.y, e.y)));
+            i0 = fsub(i0, fadd(fmul(es.x, e.y), fmul(es.y, e.x)));
+            r1 = fsub(r1, fsub(fmul(es.z, e.z), fmul(es.w, e.w)));
+            i1 = fsub(i1, fadd(fmul(es.z, e.w), fmul(es.w, e.z)));
           }
-          if (!unit_gain) { outr = fmul(gain, outr); outi = fmul(gain, outi); }
-          out[rr] = make_float2(outr, outi);
-        }
-        if (dumpC) {                                 // rare: a block the telemetry reads
-#pragma unroll
-          for (int rr = 0; rr < kFRowsPerWarp; ++rr) {
-            if (!((dumpC >> rr) & 1u)) continue;
-            const uint64_t blk = (uint64_t)(s_row[row0 + rr].base + (t >> 7));
-            int lo = 0, hi = fa.ndump;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fa.dump_blocks[mid] < blk) lo = mid + 1; else hi = mid; }
-            fa.dump[(size_t)lo * kNotchN + tib * kFT + lane] = out[rr];
-          }
+          if (!unit_gain) { r0 = fmul(gain, r0); i0 = fmul(gain, i0); r1 = fmul(gain, r1); i1 = fmul(gain, i1); }
+          o0[rr] = make_float2(r0, i0); o1[rr] = make_float2(r1, i1);
+          if ((dumpC >> rr) & 1u)                  // rare: a block the telemetry reads
+            *reinterpret_cast<float4 *>(dmpC[rr] + eoff) = make_float4(r0, i0, r1, i1);
         }
         if constexpr (!FIR) {
 #pragma unroll
           for (int rr = 0; rr < kFRowsPerWarp; ++rr)
-            if ((actC >> rr) & 1u) st_stream(yC[rr] + eoff, out[rr]);
+            if ((actC >> rr) & 1u) store_pair(yC[rr] + eoff, o0[rr], o1[rr]);
         } else {
           // notched tiles of the warp's rows: [previous | current] alternate between the two halves of s_nt
-          unsigned char *curb = s_nt + (uint32_t)(t & 1) * (kFRows * kFPitch) + (uint32_t)row0 * kFPitch;
+          unsigned char *curb = s_nt + (uint32_t)(t & 1) * (kFRows * kFPitch) + (uint32_t)row0 * kFPitch + lane * 16;
           const int32_t prev_delta = ((t & 1) ? -1 : 1) * (int32_t)(kFRows * kFPitch) + kFT * 8;   // &prev[kFT + j] - &cur[j]
 #pragma unroll
           for (int rr = 0; rr < kFRowsPerWarp; ++rr)
-            if ((actC >> rr) & 1u) *reinterpret_cast<float2 *>(curb + rr * kFPitch + lane * 8) = out[rr];
+            if ((actC >> rr) & 1u) *reinterpret_cast<float4 *>(curb + rr * kFPitch) = make_float4(o0[rr].x, o0[rr].y, o1[rr].x, o1[rr].y);
           __syncwarp();
 #pragma unroll
           for (int rr = 0; rr < kFRowsPerWarp; ++rr) {
             if (!((actC >> rr) & 1u)) continue;
-            // the output whose newest input is this lane's sample; not for the first N-1 samples of a segment
-            // (k_fir_edges), not for outputs in front of the stream
-            bool doit = true;
-            if (tib == 0) {
-              if (((firstC >> rr) & 1u) && lane < L) doit = false;
-              if (first_batch && s_row[row0 + rr].base + (t >> 7) == 0 && lane < N) doit = false;
-            }
-            if (doit) {
-              const unsigned char *me = curb + rr * kFPitch + lane * 8;
-              float2 acc = make_float2(0.f, 0.f);
-              if (fa.real_taps) {
+            // Outputs whose newest inputs are this lane's two samples (2 lane, 2 lane + 1): a sliding pair over the taps,
+            //   y1 = sum_i c_i v[2l+1-i],  y0 = sum_i c_i v[2l-i]   (accumulated in the reference's order, i = 0 .. N-1)
+            const unsigned char *me = curb + rr * kFPitch;      // &cur[2 lane]
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+            float2 prev = o1[rr], cur = o0[rr];
+            if (fa.real_taps) {
 #pragma unroll 5
-                for (int i = 0; i < N; ++i) {
-                  const float2 v = *reinterpret_cast<const float2 *>(me - i * 8 + ((lane < i) ? prev_delta : 0));
-                  const float c = s_taps[i].x;
-                  acc.x = fadd(acc.x, fmul(c, v.x)); acc.y = fadd(acc.y, fmul(c, v.y));
-                }
-              } else {
-                for (int i = 0; i < N; ++i) {
-                  const float2 v = *reinterpret_cast<const float2 *>(me - i * 8 + ((lane < i) ? prev_delta : 0));
-                  const float2 pr = cmul(s_taps[i], v);
-                  acc.x = fadd(acc.x, pr.x); acc.y = fadd(acc.y, pr.y);
-                }
+              for (int i = 0; i < N; ++i) {
+                const float c = s_taps[i].x;
+                a1.x = fadd(a1.x, fmul(c, prev.x)); a1.y = fadd(a1.y, fmul(c, prev.y));
+                a0.x = fadd(a0.x, fmul(c, cur.x));  a0.y = fadd(a0.y, fmul(c, cur.y));
+                prev = cur;
+                const int j = 2 * lane - (i + 1);                  // the next older sample
+                cur = *reinterpret_cast<const float2 *>(me - (i + 1) * 8 + ((j < 0) ? prev_delta : 0));
               }
-              st_stream(yC[rr] + eoff, acc);
+            } else {
+              for (int i = 0; i < N; ++i) {
+                const float2 c = s_taps[i];
+                const float2 p1 = cmul(c, prev), p0 = cmul(c, cur);
+                a1.x = fadd(a1.x, p1.x); a1.y = fadd(a1.y, p1.y);
+                a0.x = fadd(a0.x, p0.x); a0.y = fadd(a0.y, p0.y);
+                prev = cur;
+                const int j = 2 * lane - (i + 1);
+                cur = *reinterpret_cast<const float2 *>(me - (i + 1) * 8 + ((j < 0) ? prev_delta : 0));
+              }
             }
+            // not for the first N-1 samples of a segment (k_fir_edges), not for outputs in front of the stream
+            bool ok0 = true, ok1 = true;
+            if (tib == 0) {
+              if ((firstC >> rr) & 1u) { ok0 = 2 * lane >= L; ok1 = 2 * lane + 1 >= L; }
+              if (first_batch && s_row[row0 + rr].base + (t >> kFTileShift) == 0) { ok0 = ok0 && 2 * lane >= N; ok1 = ok1 && 2 * lane + 1 >= N; }
+            }
+            float2 *yp = yC[rr] + eoff;
+            if (ok0 && ok1) store_pair(yp, a0, a1);
+            else { if (ok0) st_stream(yp, a0); if (ok1) st_stream(yp + 1, a1); }
             // what k_fir_edges needs: the first N-1 and the last N notched samples of the segment
-            if (tib == 0 && ((firstC >> rr) & 1u) && lane < L)
-              fa.edge[(size_t)s_row[row0 + rr].seg * kNotchEdge + lane] = out[rr];
-            if (tib == kFTilesPerBlock - 1 && ((lastC >> rr) & 1u) && lane >= kFT - N)
-              fa.edge[(size_t)s_row[row0 + rr].seg * kNotchEdge + kFirFuseMaxTaps + (lane - (kFT - N))] = out[rr];
+            if (tib == 0 && ((firstC >> rr) & 1u)) {
+              float2 *ed = fa.edge + (size_t)s_row[row0 + rr].seg * kNotchEdge;
+              if (2 * lane < L) ed[2 * lane] = o0[rr];
+              if (2 * lane + 1 < L) ed[2 * lane + 1] = o1[rr];
+            }
+            if (tib == kFTilesPerBlock - 1 && ((lastC >> rr) & 1u)) {
+              float2 *ed = fa.edge + (size_t)s_row[row0 + rr].seg * kNotchEdge + kFirFuseMaxTaps - (kFT - N);
+              if (2 * lane >= kFT - N) ed[2 * lane] = o0[rr];
+              if (2 * lane + 1 >= kFT - N) ed[2 * lane + 1] = o1[rr];
+            }
           }
         }
       }

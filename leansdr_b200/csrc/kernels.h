@@ -98,6 +98,7 @@ cudaError_t launch_notch_apply(NotchApplyArgs a, const uint32_t *seg_list, uint3
 // the data-parallel work around it by eight others, and -- when the low-pass that follows has decimation 1 and at
 // most kFirFuseMaxTaps taps -- the FIR is applied on the store path, so that the notched stream never reaches HBM.
 constexpr int kFirFuseMaxTaps = 32;
+constexpr int kNotchFirRows = 16;               // segments per CTA of k_notch_fir
 constexpr int kNotchEdge = 2 * kFirFuseMaxTaps;   // float2 per segment: [first N-1 | (at kFirFuseMaxTaps) last N] notched samples
 struct NotchFirArgs {
   NotchApplyArgs n;             // n.out is used only when fir_n == 0 (plain notch)

@@ -891,15 +891,14 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
     // Table 0 is all zeros: slots that never detected (bin -1) use it (sdr.h:57-63).
     cudaMemset(h->d_notch_tables.p, 0, (size_t)kNotchN * 8);
     h->notch_tables_used = 1;
-    // Kernel choice.  Default: the lane-per-segment kernel (k_notch.cu) followed by k_frontend.  LDVB_NOTCH_V2=1
-    // selects the warp-specialised kernel of k_notchfir.cu, which (unless LDVB_NOTCH_FUSE=0) applies the low-pass on
-    // its store path so that the notched stream never reaches HBM (decimation 1, <= kFirFuseMaxTaps taps, no
-    // rotator).  It is bit-exact (the whole GPU suite passes with it) and halves the DRAM traffic of the two
-    // stages, but measured 3.1 ms against 1.0 + 0.3 ms per 128 M samples (profiles/r02_*): ~790 instructions per
-    // warp and tile step where the arithmetic needs ~300, so it stays opt-in.  Time-sharded handles always run
-    // the default path.
+    // Kernel choice.  Default: the warp-specialised kernel of k_notchfir.cu, which -- when the low-pass that follows has
+    // decimation 1, at most kFirFuseMaxTaps taps and no rotator in front -- applies the FIR on its store path, so that the
+    // notched stream never reaches HBM (LDVB_NOTCH_FUSE=0: plain notch, then k_frontend).  Measured at the bench size
+    // (profiles/r02_*): 1.20 ms + 0.06 ms of start-state sums against 0.90 + 0.32 + 0.17 ms for the lane-per-segment
+    // kernel, k_frontend and the sums of 1-block segments, and 2.5 GB instead of 7.1 GB of DRAM traffic.
+    // LDVB_NOTCH_V2=0 selects the lane-per-segment kernel of k_notch.cu (round 1); time-sharded handles always run it.
     const char *e2 = getenv("LDVB_NOTCH_V2"), *ef = getenv("LDVB_NOTCH_FUSE");
-    h->notch_v2 = (e2 && atoi(e2) != 0);
+    h->notch_v2 = !(e2 && atoi(e2) == 0);
     h->notch_fused = h->notch_v2 && !(ef && atoi(ef) == 0) && h->use_fir && h->decim == 1 && !h->use_rot &&
                      h->fir_n >= 2 && h->fir_n <= kFirFuseMaxTaps;
   }
@@ -1183,12 +1182,12 @@ int run_notch(ldvb_handle *h, const RawSrc &src, uint64_t avail, uint64_t *consu
   // (0.998^n decay below one ulp), measured in DESIGN.md.
   a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + 32767) / 32768));
   if (v2) {
-    // One CTA = 32 segments; as many segments as fit in one wave (two CTAs per SM with one slot, else one): the
+    // One CTA = kNotchFirRows segments; as many segments as fit in one wave (two CTAs per SM with one slot, else one): the
     // chain warp needs ~8 cycles per sample, so longer segments cost little and dilute the warm-up blocks.
     if (!h->notch_target_segs) {
       int dev = 0, sms = 148;
       if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      h->notch_target_segs = (uint64_t)32 * sms * (c.anf == 1 ? 2 : 1);
+      h->notch_target_segs = (uint64_t)kNotchFirRows * sms * (c.anf == 1 ? 2 : 1);
     }
     a.seg_blocks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (nblocks + h->notch_target_segs - 1) / h->notch_target_segs));
   }

@@ -1,7 +1,8 @@
-"""The opt-in warp-specialised auto_notch kernel (k_notchfir.cu, LDVB_NOTCH_V2=1): plain notch and notch + fir_filter fused
-on the store path (the notched stream never reaches HBM).  Same bytes as the oracle in every stream, like the default
-kernels; batches chosen so that segment boundaries, the carried FIR history between batches and the telemetry blocks
-(cnr_fft / spectrum read the notched stream) are all exercised."""
+"""The two auto_notch kernels side by side: the warp-specialised one of k_notchfir.cu (the default: plain notch, and notch +
+fir_filter fused on the store path so that the notched stream never reaches HBM) and the lane-per-segment one of k_notch.cu
+(LDVB_NOTCH_V2=0, what time-sharded handles run).  Same bytes as the oracle in every stream; batches chosen so that segment
+boundaries, the carried FIR history between batches and the telemetry blocks (cnr_fft / spectrum read the notched stream)
+are all exercised."""
 import numpy as np
 import pytest
 
@@ -18,10 +19,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("v2", ["1", "0"])
 @pytest.mark.parametrize("name,kw,gkw,npk,batch", CASES, ids=[c[0] for c in CASES])
-def test_notchfir_kernel_every_stream_bit_exact(product, oracle, monkeypatch, name, kw, gkw, npk, batch):
+def test_notchfir_kernel_every_stream_bit_exact(product, oracle, monkeypatch, name, kw, gkw, npk, batch, v2):
     P, O = product, oracle
-    monkeypatch.setenv("LDVB_NOTCH_V2", "1")           # read by ldvb_create
+    monkeypatch.setenv("LDVB_NOTCH_V2", v2)            # read by ldvb_create
     raw = V.ref_iq(npk, fmt=kw["fmt"], **gkw)
     ref = O.Chain(O.Config(**kw)).run(raw)
     got = run_product(P, raw, n_batch=batch, rx_mode=P.RX_EXACT, **kw)
@@ -31,13 +33,14 @@ def test_notchfir_kernel_every_stream_bit_exact(product, oracle, monkeypatch, na
     assert len(ref["ts"]) > npk - 80
 
 
+@pytest.mark.parametrize("v2", ["1", "0"])
 @pytest.mark.parametrize("batch", [None, 3_000_001])
-def test_notchfir_spectrum_rows(product, oracle, monkeypatch, batch):
+def test_notchfir_spectrum_rows(product, oracle, monkeypatch, batch, v2):
     """spectrum (always on, leandvb.cc:333-343) reads the notched stream, which the fused kernel only writes out for the
     blocks that will be measured (known in advance: sdr.h:1362-1370)."""
     from tests.test_gpu_parity import _telemetry
     P, O = product, oracle
-    monkeypatch.setenv("LDVB_NOTCH_V2", "1")
+    monkeypatch.setenv("LDVB_NOTCH_V2", v2)
     raw = V.ref_iq(4000, fmt="f32")
     kw = dict(fmt="f32", resample=True)
     ref = O.Chain(O.Config(**kw)).run(raw)
