@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(HERE), "gpurun_out")
 tag = sys.argv[2] if len(sys.argv) > 2 else "r01"
 
-PROFILE_NAME = {"k_rx": "rx", "k_notch_apply": "notch_apply", "k_notch_guess": "notch_guess", "k_notch_detect": "notch_detect",
+PROFILE_NAME = {"k_rx": "rx", "k_notch_fir": "notch_fir", "k_fir_edges": "fir_edges", "k_notch_apply": "notch_apply", "k_notch_guess": "notch_guess", "k_notch_detect": "notch_detect",
                 "k_notch_verify": "notch_verify", "k_frontend": "frontend", "k_rx_stitch": "rx_stitch", "k_rx_plan": "rx_plan",
                 "k_rx_compact": "rx_compact", "k_deconv_tiled": "deconv_carry", "k_deconv": "deconv_carry", "k_sync_track": "sync_track",
                 "k_sync_flags": "sync_flags", "k_realign": "realign", "k_rs": "deint_rs", "k_derand_scan": "derand",
@@ -32,13 +32,16 @@ def launch_list():
     lines = [l for l in open(p) if l.startswith('"')]
     rows = list(csv.DictReader(io.StringIO("".join(lines))))
     shutil.copy(p, os.path.join(HERE, f"{tag}_launches.csv"))
-    tot = defaultdict(float); cnt = defaultdict(int); per = defaultdict(list)
+    tot = defaultdict(float); cnt = defaultdict(int); per = defaultdict(list); serial = []
     for r in rows:
         if r["Metric Name"] != "gpu__time_duration.sum":
             continue
         k = base(r["Kernel Name"])
         if k.startswith("k_tx"):
             continue                                   # input synthesis, outside the timed region
+        if k == "k_rx_serial":
+            serial.append(float(r["Metric Value"]) / 1e6)   # cold-start AGC settling passes: once per stream, outside the timed steps
+            continue
         tot[k] += float(r["Metric Value"]) / 1e6; cnt[k] += 1
         per[k].append((r["Grid Size"], float(r["Metric Value"]) / 1e6))
     # the device-resident steps (whole 128 M-sample batch): per kernel, the launches with the largest grid
@@ -59,10 +62,10 @@ def launch_list():
            "kernels that synthesise the input are left out).",
            "Times under ncu are cold-cache and serialised: compare SHARES with the live CUDA-event numbers of `bench.py` "
            f"(right-hand columns, un-profiled run of the same commit: value {bench['value']/1e3:.1f} GS/s, {step:.2f} ms/step).", "",
-           "The list mixes whole-batch launches (the `value` steps) with the six pipelined sub-batch launches of every `e2e` step; the "
-           "latency-bound kernels (`k_notch_apply`: one lane walks 3 blocks whatever the batch size) take as long on a sub-batch as on the "
-           "whole batch, so the share over ALL launches over-weights them.  The column to compare with the live share is the one over the "
-           "whole-batch launches only (largest grid per kernel).", "",
+           "The list covers the fresh check pass, the warm-up and the timed steps of the device-resident loop and the pushes of the e2e leg "
+           "(one staged piece per push since round 2, i.e. whole batches everywhere).  Left out of the shares: `k_rx_serial`, the cold-start "
+           f"AGC settling pass, which runs once per STREAM ({len(serial)} launches here, {sum(serial)/max(len(serial),1):.2f} ms each: the two handles "
+           "of the bench, one fresh pass + one stream each) and never inside the timed steps.", "",
            "| kernel | launches | total ms (ncu, all) | share (all) | ms per whole-batch launch (ncu) | share (whole-batch) | ms/step live (bench.py CUDA events) | share live |",
            "|---|---|---|---|---|---|---|---|"]
     live_sum = sum(live.values())
@@ -104,9 +107,9 @@ def ncu_full():
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     n = 128324096
-    out = [f"# {tag} -- `ncu --set full --clock-control none --import-source on` of the four heaviest kernels at the bench size", "",
+    out = [f"# {tag} -- `ncu --set full --clock-control none --import-source on` of the heaviest kernels at the bench size", "",
            "Command (gpurun, 1 GPU, profiles/run_gpu_round2.sh): `ncu --set full --clock-control none --import-source on -k "
-           "regex:'k_rx$|k_notch_apply|k_frontend|k_notch_guess' -s 8 -c 4 python bench.py --steps 1 --warmup 3 --no-cpu` "
+           "regex:'^k_rx$|^k_notch_fir$|^k_notch_guess$|^k_rx_compact$' -s 8 -c 4 python bench.py --steps 1 --warmup 3 --no-cpu` "
            f"({n} f32 samples per launch).  Per launch, under the profiler (cold, serialised): use shares and ratios, not absolutes.", ""]
     traffic = {"_source": "ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 --no-cpu (%d f32 samples per launch), "
                           "profiles/run_gpu_round2.sh; dram__bytes_read.sum + dram__bytes_write.sum per launch" % n,
