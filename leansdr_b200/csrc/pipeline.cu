@@ -560,6 +560,8 @@ extern "C" {
 
 int ldvb_abi_version(void) { return LDVB_ABI_VERSION; }
 
+static int stage_init(ldvb_handle *h);   // (defined with ldvb_push)
+
 const char *ldvb_strerror(int code) {
   switch (code) {
     case LDVB_OK: return "ok";
@@ -903,6 +905,16 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
                      h->fir_n >= 2 && h->fir_n <= kFirFuseMaxTaps;
   }
   reset_carry(h);
+  if (c.async_push) {
+    // A streaming host: the staging buffers and the page-locked packet queue are set up here, not inside the first
+    // push (three cudaMallocs of up to 1 GiB and a cudaHostAlloc took 0.1-0.6 s of the first scheduler step,
+    // depending on the box: bench.py e2e_runnable).
+    int rcs = stage_init(h);
+    if (rcs) return bail(rcs, h->err.c_str());
+    const size_t cap = 2 * (size_t)h->ts_cap * 188;
+    if (cudaHostAlloc((void **)&h->ts_queue, cap, cudaHostAllocDefault) != cudaSuccess) return bail(LDVB_ENOMEM, "TS queue");
+    h->ts_queue_cap = cap;
+  }
   *out = h;
   return LDVB_OK;
 }
