@@ -91,11 +91,15 @@ enum { LDVB_SAMP_NEAREST = 0, LDVB_SAMP_LINEAR = 1, LDVB_SAMP_RRC = 2 };
  *          QAM constellations depend on the AGC estimate, which remembers ~100
  *          chunks (sdr.h:863-869) -- more than a span's warm-up can reproduce --
  *          so a handle for those constellations runs EXACT whatever is asked.
- *          AGC settling: spans restart from the batch-entry AGC estimate.  When the
- *          measured input power is more than a factor 2 away from it (cold start
- *          on a stream that is not at the nominal level, e.g. after a heavy
- *          decimation), the first `settle_chunks` chunks of the batch are walked
- *          serially (exactly) and the spans start from the state reached there. */
+ *          AGC settling: spans restart from the batch-entry AGC estimate.  On the
+ *          first FAST batch of a stream (after create / reset), and whenever the
+ *          measured input power is more than a factor 2 away from the carried
+ *          estimate (a stream that is not at the nominal level, e.g. after a heavy
+ *          decimation; a level jump), the first `settle_chunks` chunks of the batch
+ *          are walked serially (exactly, ~14 ms for the default 512 chunks) and the
+ *          spans start from the state reached there.  settle_chunks = -1 disables it:
+ *          hard decisions of BPSK/QPSK/8PSK do not depend on the estimate, soft costs
+ *          then stay ~10 % off the serial ones for many batches. */
 enum { LDVB_RX_EXACT = 0, LDVB_RX_FAST = 1 };
 
 /* ------------------------------------------------------------------ config
