@@ -832,7 +832,11 @@ def main():
     if not a.no_cpu:
         sample_pk = min(a.packets, a.cpu_sample_packets)
         sample = raw[: 2 * min(n, sample_pk * 1958)]
-        v, ts_ref = run_reference_cpu(sample, 1, 3, ref_flags)
+        try:
+            v, ts_ref = run_reference_cpu(sample, 1, 3, ref_flags)
+        except Exception as e:
+            sys.stderr.write(f"[bench] cpu_baseline leg failed: {e!r}\n")
+            v, ts_ref = float("nan"), b""
         ref_pk = np.frombuffer(ts_ref, dtype=np.uint8).reshape(-1, 188)
         k = min(len(ref_pk), len(ts_gpu))
         ts_match = bool(k > 0 and np.array_equal(ref_pk[:k], ts_gpu[:k]) and
@@ -852,7 +856,10 @@ def main():
     if not a.no_cpu and not a.no_parity and a.variant == "f32" and a.mode == "fast":
         del iq_all
         torch.cuda.empty_cache()
-        parity = fast_vs_exact(P, raw, rx_kw, ref_flags, a.anf, local, min(a.packets, a.parity_packets))
+        try:
+            parity = fast_vs_exact(P, raw, rx_kw, ref_flags, a.anf, local, min(a.packets, a.parity_packets))
+        except Exception as e:                                  # never lose the bench line to a side measurement
+            parity = {"error": repr(e)[:300]}
 
     line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

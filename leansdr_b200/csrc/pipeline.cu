@@ -930,7 +930,8 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
 
 int ldvb_reset(ldvb_handle *h) {
   if (!h) return LDVB_EINVAL;
-  { int rcw = async_wait(h); if (rcw) return rcw; }
+  async_wait(h);                         // (an error of the background chain does not outlive a reset)
+  if (h->worker_started) { std::lock_guard<std::mutex> lk(h->amu); h->worker_rc = 0; }
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, LDVB_ECUDA, "cudaSetDevice");
   CK(cudaStreamSynchronize(h->st));
   reset_carry(h);
