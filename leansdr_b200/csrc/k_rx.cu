@@ -790,82 +790,7 @@ __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
   for (uint64_t i = head + 4 * nvec + threadIdx.x; i < n; i += blockDim.x) dst[i] = fix(src[i]);
 }
 
-// Seam resolution on the device: kept symbol counts, skips, cumulative rotations and
-// output offsets of every span (one CTA, block-wide scans), so that the host only
-// reads back two numbers when every seam verified.
-__global__ void __launch_bounds__(1024)
-k_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
-          int rot0, uint32_t skip0, uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot, uint64_t *result /* [4] */) {
-  __shared__ unsigned long long s_sum[32];
-  __shared__ int s_rot[32];
-  __shared__ unsigned long long carry_sum;
-  __shared__ int carry_rot;
-  __shared__ unsigned int nfail, overflow, nmis, mx_phase, mx_freqw, mx_mu, nfail_loose;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { carry_sum = 0; carry_rot = 0; nfail = 0; overflow = 0; nmis = 0; mx_phase = 0; mx_freqw = 0; mx_mu = 0; nfail_loose = 0; }
-  __syncthreads();
-  for (uint32_t base = 0; base < nspans; base += 1024) {
-    const uint32_t j = base + tid;
-    unsigned long long keep = 0; int rot = 0; uint32_t skip = 0;
-    if (j < nspans) {
-      const RxSpanInfo inf = info[j];
-      if (inf.n_out + inf.n_tail > span_cap) atomicAdd(&overflow, 1u);
-      keep = inf.n_out;
-      if (j > 0) {
-        const RxSeam sm = seams[j - 1];
-        if (!sm.ok) atomicAdd(&nfail, 1u);
-        else if (sm.mismatches) atomicAdd(&nmis, 1u);
-        if (!sm.ok_loose) atomicAdd(&nfail_loose, 1u);
-        if (sm.ok) {   // (non-negative floats order like their bit patterns)
-          atomicMax(&mx_phase, __float_as_uint(fabsf(sm.dphase)));
-          atomicMax(&mx_freqw, __float_as_uint(fabsf(sm.dfreqw)));
-          atomicMax(&mx_mu, __float_as_uint(fabsf(sm.dmu)));
-        }
-        skip = (uint32_t)sm.skip_next; rot = sm.rot;
-      } else {
-        skip = skip0; rot = rot0;   // seam in front of span 0 (previous rank), 0 otherwise
-      }
-      keep -= skip;
-      if (j + 1 < nspans) keep += (unsigned long long)seams[j].extend_prev;
-    }
-    // inclusive scans (sum of keep, sum of rot mod nrot) across the block
-    unsigned long long ks = keep; int rs = rot;
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long a = __shfl_up_sync(0xffffffffu, ks, o);
-      const int b = __shfl_up_sync(0xffffffffu, rs, o);
-      if (lane >= o) { ks += a; rs += b; }
-    }
-    if (lane == 31) { s_sum[warp] = ks; s_rot[warp] = rs; }
-    __syncthreads();
-    if (warp == 0) {
-      unsigned long long a = s_sum[lane]; int b = s_rot[lane];
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long a2 = __shfl_up_sync(0xffffffffu, a, o);
-        const int b2 = __shfl_up_sync(0xffffffffu, b, o);
-        if (lane >= o) { a += a2; b += b2; }
-      }
-      s_sum[lane] = a; s_rot[lane] = b;
-    }
-    __syncthreads();
-    const unsigned long long wbase = warp ? s_sum[warp - 1] : 0;
-    const int wrot = warp ? s_rot[warp - 1] : 0;
-    const unsigned long long incl = carry_sum + wbase + ks;
-    const int rincl = (carry_rot + wrot + rs) % nrot;
-    if (j < nspans) {
-      span_offset[j + 1] = incl;
-      span_skip[j] = skip;
-      span_rot[j] = (uint8_t)rincl;
-    }
-    __syncthreads();
-    if (tid == 1023) { carry_sum = incl; carry_rot = rincl; }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    span_offset[0] = 0;
-    result[0] = nfail; result[1] = carry_sum; result[2] = (uint64_t)carry_rot; result[3] = overflow;
-    result[4] = nmis; result[5] = mx_phase; result[6] = mx_freqw; result[7] = mx_mu; result[8] = nfail_loose;
-  }
-}
+#include "k_ctl_rx.cuh"   // k_rx_plan
 
 
 // Mean |x|^2 of the first n samples.

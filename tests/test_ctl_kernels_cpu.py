@@ -1,0 +1,37 @@
+"""The control kernels of the byte stages and of the receiver's seam resolution, run on the HOST.
+
+`leansdr_b200/csrc/k_ctl_fec.cuh` / `k_ctl_rx.cuh` hold device code only; nvcc compiles them into the library, and
+here g++ compiles the same text against `tests/emu/cuda_emu.h` (one OS thread per CUDA thread, barriers for
+`__syncthreads`, exchange slots for shuffles and ballots).  `tests/emu/emu_ctl.cpp` feeds every kernel and its
+predecessor (`tests/emu/ctl_v1.cuh`: the kernels as they passed the GPU parity suite on B200) the same seeded inputs
+and compares every output word.  This is how a rewrite of these integer programs is checked where there is no GPU;
+the GPU parity tests then check them again against the oracle through the C ABI.
+"""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+
+@pytest.fixture(scope="module")
+def emu_bin(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    out = str(tmp_path_factory.mktemp("emu") / "emu_ctl")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-w", "-I", CUDA_INC,
+                           os.path.join(ROOT, "tests", "emu", "emu_ctl.cpp"), "-o", out])
+    return out
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("case,seeds", [("plan", (1, 2)), ("derand", (1,)), ("sync_locked", (1, 2, 3)),
+                                        ("sync_search", (1, 2, 3, 4)), ("deconv", (1, 2, 3, 4))])
+def test_control_kernel_equals_its_predecessor(emu_bin, case, seeds):
+    for seed in seeds:
+        r = subprocess.run([emu_bin, case, str(seed)], capture_output=True, text=True, timeout=800)
+        assert r.returncode == 0, f"{case} seed {seed}:\n{r.stderr[-2000:]}"
+        assert "identical" in r.stdout
