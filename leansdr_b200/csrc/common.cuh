@@ -4,6 +4,12 @@
 #include <atomic>
 #include <cstdint>
 
+// Dynamic shared memory of a kernel whose text is also compiled on the host by the test shim (tests/emu/cuda_emu.h
+// defines its own LDVB_DYN_SMEM).
+#ifndef LDVB_DYN_SMEM
+#define LDVB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace ldvb {
 
 // ---------------------------------------------------------- per-device opt-ins

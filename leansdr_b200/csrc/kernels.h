@@ -339,10 +339,12 @@ struct VitSegArgs {
                                // no warm-up at all, a test knob: every cold segment fails verification)
   int phase0;                  // resync_phase at chunk 0
   int nb;                      // rescan entries per state = vit_rescan_entries(bits_in)
+  int full;                    // every state is a predecessor of every state (vit_trellis_is_full): k_viterbi<kVitFull>
   VitDecState *entry, *exit;   // [nseg][nsyncs]
   VitCtl *ctl_entry, *ctl_exit;// [nseg]
 };
 int vit_rescan_entries(int bits_in);
+bool vit_trellis_is_full(const uint8_t *pred /* [64][ncs] host */, int ncs, int bits_in);
 int vit_resident_segments(int ncs, int bits_in, int nsyncs);   // CTAs of one full wave on the current device (0: unknown)
 // nblocks = nseg (list == null) or nlist.
 cudaError_t launch_viterbi(const VitArgs &a, const VitSegArgs &sg, uint32_t nblocks, cudaStream_t st);

@@ -2008,6 +2008,7 @@ int run_viterbi(ldvb_handle *h, uint64_t *produced) {
     uint8_t *d_ok = ax;
     sg.nseg = nseg; sg.list = nullptr; sg.nlist = 0; sg.warm_chunks = warm; sg.warm_others = P > 1 ? warm_others : 0;
     sg.phase0 = ctl0.resync_phase; sg.nb = vit_rescan_entries(bits_in);
+    sg.full = vit_trellis_is_full(h->trellis.pred.data(), a.ncs, bits_in) ? 1 : 0;
     sg.entry = h->d_vit_entry.as<VitDecState>(); sg.exit = h->d_vit_exit.as<VitDecState>();
     CK(cudaMemcpyAsync(const_cast<uint64_t *>(sg.seg_start), start.data(), start.size() * 8, cudaMemcpyHostToDevice, h->st));
     KL("viterbi", launch_viterbi(a, sg, nseg, h->st));

@@ -25,8 +25,10 @@
 #define __shared__ static
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#define LDVB_DYN_SMEM(name) unsigned char *name = emu::g_dyn_smem
 
 namespace emu {
+inline unsigned char *g_dyn_smem = nullptr;   // dynamic shared memory of the block being run (set by the harness)
 struct Warp {
   std::barrier<> bar;
   uint64_t slot[32];
@@ -54,6 +56,15 @@ inline int __syncthreads_or(int pred) {
   if (pred) __atomic_fetch_or(&emu::g_blk->red[0], 1ull, __ATOMIC_SEQ_CST);
   __syncthreads();
   const int r = (int)emu::g_blk->red[0];
+  __syncthreads();
+  return r;
+}
+inline int __syncthreads_and(int pred) {
+  if (threadIdx.x == 0) emu::g_blk->red[1] = 1;
+  __syncthreads();
+  if (!pred) __atomic_store_n(&emu::g_blk->red[1], 0ull, __ATOMIC_SEQ_CST);
+  __syncthreads();
+  const int r = (int)emu::g_blk->red[1];
   __syncthreads();
   return r;
 }

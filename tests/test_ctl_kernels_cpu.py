@@ -35,3 +35,29 @@ def test_control_kernel_equals_its_predecessor(emu_bin, case, seeds):
         r = subprocess.run([emu_bin, case, str(seed)], capture_output=True, text=True, timeout=800)
         assert r.returncode == 0, f"{case} seed {seed}:\n{r.stderr[-2000:]}"
         assert "identical" in r.stdout
+
+
+@pytest.fixture(scope="module")
+def emu_vit_bin(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    out = str(tmp_path_factory.mktemp("emu") / "emu_vit")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-w", "-I", CUDA_INC,
+                           os.path.join(ROOT, "tests", "emu", "emu_vit.cpp"),
+                           os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp"), "-o", out])
+    return out
+
+
+# (fec, kernel, seed, stream, layout): fec 5 = 7/8 through k_viterbi<kVitFull> (the rescan replaced by the minimum of the
+# metrics + the tie rule), fec 0 = 1/2 through k_viterbi_ws (one warp per time segment); streams with a decodable
+# hypothesis and pure noise; segments far from / close to the start of the batch, and resync_period 1 (--fastlock).
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("args", [(5, "full", 1, "signal", 0), (5, "full", 2, "noise", 1), (5, "full", 3, "noise", 2),
+                                  (0, "ws", 1, "signal", 0), (0, "ws", 2, "noise", 1), (0, "ws", 3, "signal", 2)])
+def test_viterbi_kernel_equals_its_predecessor(emu_vit_bin, args):
+    """k_vit_dev.cuh (the text nvcc compiles) on the host: output bytes, entry / exit states of every time segment and
+    the elected hypothesis equal those of the kernel that passed the GPU parity suite (tests/emu/vit_v1.cuh), on cold
+    segments, exact segments and the repair path."""
+    r = subprocess.run([emu_vit_bin, *map(str, args)], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, f"{args}:\n{r.stderr[-2000:]}"
+    assert "identical" in r.stdout
