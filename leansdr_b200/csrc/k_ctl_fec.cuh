@@ -6,8 +6,9 @@
 //
 // What they have in common: each one used to be a single CTA (or thread) walking the batch in 1024-element rounds,
 // one global-load latency and several block barriers per round (k_derand_scan 0.18 ms, k_sync_track 0.19 ms of a
-// 4.4 ms step for a few hundred KB of data).  Here every thread owns a contiguous run, the block-wide scans happen
-// once per 65 536 elements, and the all-good case of the lock tracker is a reduction.
+// 4.4 ms step for a few hundred KB of data).  Here the lock tracker stages its mask in shared memory and takes the
+// all-good case as a reduction (0.19 -> 0.01 ms on B200), and the de-randomiser scan is spread over tiles of 1024
+// packets on as many CTAs with a one-CTA chain step in between.
 
 // =============================================================== deconvolution
 // deconvol_sync::readbyte (dvb.h:369-389) as a position-indexed computation.
@@ -300,13 +301,24 @@ k_sync_track(const uint8_t *bytes, uint64_t nbytes, const SyncState *st_in,
 }
 
 // ============================================================ de-randomiser
-// derandomizer::run (dvb.h:1131-1158).  pos_p = 188*((p - r_p) mod 8) with r_p
-// the last packet <= p whose first byte is an inverted sync (0xB8 or 0xB8^0x55);
-// before the first reset the carried position keeps cycling.  One CTA: every thread reads the heads of a run of
-// 64 consecutive packets into registers (64 independent loads in flight, where round 2 took one load latency and
-// four barriers per 1024 packets), a block-wide max-scan hands each run the last reset in front of it, a block-wide
-// sum-scan the number of packets kept in front of it; a second kernel XORs and writes the kept packets.
-constexpr int kDrRun = 64;
+// derandomizer::run (dvb.h:1131-1158).  pos_p = 188*((p - r_p) mod 8) with r_p the last packet <= p whose first byte
+// is an inverted sync (0xB8 or 0xB8^0x55); before the first reset the carried position keeps cycling.  A packet is kept
+// when its de-randomised head is 0x47; kept packets are written back to back.
+//
+// Three small grids over tiles of 1024 packets (one thread per packet, consecutive threads on consecutive packets):
+//   k_derand_tiles  per tile: the last reset, the RS error sum, the packets kept after the tile's first reset, and --
+//                   for the packets in front of it, whose pattern position depends on earlier tiles -- the number
+//                   kept under each of the 8 possible positions of the tile's first packet;
+//   k_derand_chain  one CTA: the position of every tile's first packet (max-scan of the resets), hence its kept
+//                   count and its base in the output (sum-scan); the batch totals;
+//   k_derand_index  per tile again: output index and pattern position of every packet.
+// History: one CTA walking 1024 packets per round took 0.18 ms per 65 536 packets (a load latency and four barriers
+// per round); one CTA with a contiguous run of 64 packets per thread 0.16 ms on B200 (a quarter of a million
+// uncoalesced accesses through one SM's load/store unit).  Tile records: kDrRec words per tile in a.scratch behind
+// the 2 * npackets per-packet words: [0] last reset in the tile + 1 (0: none), [1] kept after the first reset,
+// [2..9] kept in front of it by position, [10] RS errors, [11] position of the first packet, [12] output base.
+constexpr int kDrTile = 1024;
+constexpr int kDrRec = 16;
 
 // inclusive block scans over 1024 threads (s_a / s_b: 32 entries each); every thread must call
 __device__ __forceinline__ void block_scan_max_sum(long long &mx, unsigned &sum, long long *s_a, unsigned *s_b) {
@@ -332,84 +344,85 @@ __device__ __forceinline__ void block_scan_max_sum(long long &mx, unsigned &sum,
   if (warp > 0) { if (s_a[warp - 1] > mx) mx = s_a[warp - 1]; sum += s_b[warp - 1]; }
 }
 
+__device__ __forceinline__ uint32_t *derand_rec(const DerandArgs &a, uint64_t tile) { return a.scratch + 2 * a.npackets + kDrRec * tile; }
+
 __global__ void __launch_bounds__(1024)
-k_derand_scan(DerandArgs a) {
+k_derand_tiles(DerandArgs a) {
   __shared__ long long s_last[32];
   __shared__ unsigned s_cnt[32];
   __shared__ unsigned s_pat[8];
-  __shared__ long long carry_last;   // last reset index so far, -1: none yet
-  __shared__ unsigned long long carry_kept, carry_errs;
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) { carry_last = -1; carry_kept = 0; carry_errs = 0; }
-  if (tid < 8) s_pat[tid] = a.pattern[188 * tid];
+  __shared__ unsigned s_front[8], s_err;
+  const int tid = threadIdx.x;
+  if (tid < 8) { s_pat[tid] = a.pattern[188 * tid]; s_front[tid] = 0; }
+  if (tid == 8) s_err = 0;
   __syncthreads();
-  const long long start_phase = a.pos_in / 188;  // packets since the (virtual) last reset
-  for (uint64_t base = 0; base < a.npackets; base += (uint64_t)1024 * kDrRun) {
-    const uint64_t p0 = base + (uint64_t)tid * kDrRun;
-    const int n = p0 < a.npackets ? (int)min((uint64_t)kDrRun, a.npackets - p0) : 0;
-    // heads of the run, four per register
-    uint32_t hw[kDrRun / 4];
-#pragma unroll
-    for (int i = 0; i < kDrRun / 4; ++i) hw[i] = 0;
-#pragma unroll
-    for (int i = 0; i < kDrRun; ++i)
-      if (i < n) hw[i >> 2] |= (uint32_t)a.rts[188 * (p0 + i)] << (8 * (i & 3));
-    unsigned long long resets = 0;
-#pragma unroll
-    for (int i = 0; i < kDrRun; ++i) {
-      const unsigned head = (hw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-      if (i < n && (head == 0xb8u || head == (0xb8u ^ 0x55u))) resets |= 1ull << i;
-    }
-    int nerr = 0;
-    if (a.flags) for (int i = 0; i < n; ++i) nerr += a.flags[2 * (p0 + i) + 1];
-    for (int o = 16; o; o >>= 1) nerr += __shfl_xor_sync(0xffffffffu, nerr, o);
-    // last reset at or before the end of every run
-    const long long my_last = resets ? (long long)p0 + (63 - __clzll((long long)resets)) : -1;
-    long long last_incl = my_last; unsigned dummy = 0;
-    block_scan_max_sum(last_incl, dummy, s_last, s_cnt);
-    long long last = __shfl_up_sync(0xffffffffu, last_incl, 1);   // exclusive: the runs in front of this one
-    if (lane == 0) last = (tid >= 32) ? s_last[(tid >> 5) - 1] : -1;
-    if (carry_last > last) last = carry_last;
-    // which packets of the run are kept
-    unsigned long long keeps = 0;
-    {
-      long long cur = last;
-#pragma unroll
-      for (int i = 0; i < kDrRun; ++i) {
-        const long long p = (long long)p0 + i;
-        if ((resets >> i) & 1) cur = p;
-        const int ph = (int)((cur >= 0 ? p - cur : p + start_phase) & 7);
-        const unsigned head = (hw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-        if (i < n && (head ^ s_pat[ph]) == 0x47u) keeps |= 1ull << i;
-      }
-    }
-    long long unused = -1; unsigned kept_incl = (unsigned)__popcll(keeps);
-    block_scan_max_sum(unused, kept_incl, s_last, s_cnt);
-    unsigned long long out = carry_kept + kept_incl - (unsigned)__popcll(keeps);   // kept packets in front of the run
-    {
-      // scratch[p] = output index (0xffffffff when dropped), pattern position in scratch[npackets + p]
-      long long cur = last;
-      for (int i = 0; i < n; ++i) {
-        const long long p = (long long)p0 + i;
-        if ((resets >> i) & 1) cur = p;
-        const int ph = (int)((cur >= 0 ? p - cur : p + start_phase) & 7);
-        const bool keep = (keeps >> i) & 1;
-        a.scratch[p] = keep ? (unsigned)out : 0xffffffffu;
-        a.scratch[a.npackets + p] = (unsigned)(188 * ph);
-        out += keep;
-      }
-    }
-    if (lane == 0 && nerr) atomicAdd(&carry_errs, (unsigned long long)nerr);
-    __syncthreads();   // (every thread has read carry_last / carry_kept)
-    if (tid == 1023) {
-      const long long tile_last = my_last > last ? my_last : last;   // = the inclusive scan's last element or the carry
-      carry_last = tile_last;
-      carry_kept += kept_incl;
+  const uint64_t p = (uint64_t)blockIdx.x * kDrTile + tid;
+  const bool valid = p < a.npackets;
+  const unsigned head = valid ? a.rts[188 * p] : 0u;
+  const bool reset = valid && (head == 0xb8u || head == (0xb8u ^ 0x55u));
+  unsigned err = (valid && a.flags) ? (unsigned)a.flags[2 * p + 1] : 0u;
+  for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+  if ((tid & 31) == 0 && err) atomicAdd(&s_err, err);
+  long long lr = reset ? (long long)tid : -1;   // last reset of the tile at or before this packet
+  unsigned unused = 0;
+  block_scan_max_sum(lr, unused, s_last, s_cnt);
+  unsigned kept = 0;
+  if (valid && lr >= 0) {
+    kept = ((head ^ s_pat[(tid - (int)lr) & 7]) == 0x47u) ? 1u : 0u;
+  } else if (valid) {
+    for (int f = 0; f < 8; ++f)
+      if ((head ^ s_pat[(tid + f) & 7]) == 0x47u) atomicAdd(&s_front[f], 1u);
+  }
+  long long none = -1;
+  block_scan_max_sum(none, kept, s_last, s_cnt);   // (also orders the atomics above before the reads below)
+  __syncthreads();
+  if (tid == 1023) {
+    uint32_t *rec = derand_rec(a, blockIdx.x);
+    rec[0] = (uint32_t)(lr + 1);
+    rec[1] = kept;
+    for (int f = 0; f < 8; ++f) rec[2 + f] = s_front[f];
+    rec[10] = s_err;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k_derand_chain(DerandArgs a, uint32_t ntiles) {
+  __shared__ long long s_last[32];
+  __shared__ unsigned s_cnt[32];
+  __shared__ long long carry_last;                 // last reset so far (packet index), -1: none yet
+  __shared__ unsigned long long carry_kept, carry_errs;
+  const int tid = threadIdx.x;
+  if (tid == 0) { carry_last = -1; carry_kept = 0; carry_errs = 0; }
+  __syncthreads();
+  const long long start_phase = a.pos_in / 188;    // packets since the (virtual) last reset
+  for (uint32_t base = 0; base < ntiles; base += blockDim.x) {   // (any whole number of warps; 1024 threads in the library)
+    const uint32_t i = base + (uint32_t)tid;
+    const bool valid = i < ntiles;
+    uint32_t *rec = derand_rec(a, valid ? i : 0);
+    const long long first = (long long)i * kDrTile;
+    const long long mine = (valid && rec[0]) ? first + (long long)rec[0] - 1 : -1;
+    unsigned err = valid ? rec[10] : 0u;
+    long long incl = mine;
+    block_scan_max_sum(incl, err, s_last, s_cnt);          // err: inclusive sum of the tiles' error counts
+    long long prev = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive: the tiles in front of this one
+    if ((tid & 31) == 0) prev = (tid >= 32) ? s_last[(tid >> 5) - 1] : -1;
+    if (carry_last > prev) prev = carry_last;
+    const int phi = (int)((prev >= 0 ? first - prev : first + start_phase) & 7);
+    unsigned kept = valid ? rec[1] + rec[2 + phi] : 0u;
+    const unsigned mykept = kept;
+    long long none = -1;
+    block_scan_max_sum(none, kept, s_last, s_cnt);
+    if (valid) { rec[11] = (uint32_t)phi; rec[12] = (uint32_t)(carry_kept + kept - mykept); }
+    __syncthreads();   // (every thread has read the carries)
+    if (tid == (int)blockDim.x - 1) {
+      carry_last = incl > carry_last ? incl : carry_last;
+      carry_kept += kept;
+      carry_errs += err;
     }
     __syncthreads();
   }
   if (tid == 0) {
-    long long last = carry_last;
+    const long long last = carry_last;
     int pos_out;
     if (last >= 0) pos_out = (int)(((long long)a.npackets - last) & 7) * 188;
     else pos_out = (int)(((long long)a.npackets + start_phase) & 7) * 188;
@@ -417,5 +430,35 @@ k_derand_scan(DerandArgs a) {
     a.counts[1] = a.npackets - carry_kept;
     a.counts[2] = (uint64_t)pos_out;
     a.counts[3] = carry_errs;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k_derand_index(DerandArgs a) {
+  __shared__ long long s_last[32];
+  __shared__ unsigned s_cnt[32];
+  __shared__ unsigned s_pat[8];
+  const int tid = threadIdx.x;
+  if (tid < 8) s_pat[tid] = a.pattern[188 * tid];
+  __syncthreads();
+  const uint32_t *rec = derand_rec(a, blockIdx.x);
+  const int phi = (int)rec[11];
+  const unsigned base = rec[12];
+  const uint64_t p = (uint64_t)blockIdx.x * kDrTile + tid;
+  const bool valid = p < a.npackets;
+  const unsigned head = valid ? a.rts[188 * p] : 0u;
+  const bool reset = valid && (head == 0xb8u || head == (0xb8u ^ 0x55u));
+  long long lr = reset ? (long long)tid : -1;
+  unsigned unused = 0;
+  block_scan_max_sum(lr, unused, s_last, s_cnt);
+  const int ph = (lr >= 0 ? tid - (int)lr : tid + phi) & 7;
+  const bool keep = valid && (head ^ s_pat[ph]) == 0x47u;
+  unsigned incl = keep ? 1u : 0u;
+  long long none = -1;
+  block_scan_max_sum(none, incl, s_last, s_cnt);
+  if (valid) {
+    // scratch[p] = output index (0xffffffff when dropped), pattern position in scratch[npackets + p]
+    a.scratch[p] = keep ? base + incl - 1u : 0xffffffffu;
+    a.scratch[a.npackets + p] = (unsigned)(188 * ph);
   }
 }

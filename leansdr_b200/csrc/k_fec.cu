@@ -31,7 +31,7 @@ __device__ __forceinline__ uint64_t deconv_reg(const DeconvArgs &a, int64_t K) {
   return reg;
 }
 
-#include "k_ctl_fec.cuh"   // k_deconv_tiled, sync_search_window, k_sync_track, k_derand_scan
+#include "k_ctl_fec.cuh"   // k_deconv_tiled, sync_search_window, k_sync_track, k_derand_tiles / _chain / _index
 
 // Carry for the next batch (register, leftover bits, symbols consumed): one thread.
 __global__ void k_deconv(DeconvArgs a, uint64_t *carry_out) {
@@ -426,9 +426,12 @@ cudaError_t launch_derand(const DerandArgs &a, cudaStream_t st, int *launches) {
     uint64_t z[4] = {0, 0, (uint64_t)a.pos_in, 0};
     return cudaMemcpyAsync(a.counts, z, sizeof(z), cudaMemcpyHostToDevice, st);
   }
-  k_derand_scan<<<1, 1024, 0, st>>>(a);
+  const uint32_t ntiles = (uint32_t)((a.npackets + kDrTile - 1) / kDrTile);
+  k_derand_tiles<<<ntiles, 1024, 0, st>>>(a);
+  k_derand_chain<<<1, 1024, 0, st>>>(a, ntiles);
+  k_derand_index<<<ntiles, 1024, 0, st>>>(a);
   k_derand_out<<<(unsigned)((a.npackets + 3) / 4), 256, 0, st>>>(a);
-  if (launches) *launches += 2;
+  if (launches) *launches += 4;
   return cudaGetLastError();
 }
 

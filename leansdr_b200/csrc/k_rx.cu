@@ -790,7 +790,7 @@ __global__ void k_rx_compact(RxCompactArgs a, uint64_t total) {
   for (uint64_t i = head + 4 * nvec + threadIdx.x; i < n; i += blockDim.x) dst[i] = fix(src[i]);
 }
 
-#include "k_ctl_rx.cuh"   // k_rx_plan
+#include "k_ctl_rx.cuh"   // k_rx_plan_local, k_rx_plan_apply
 
 
 // Mean |x|^2 of the first n samples.
@@ -907,7 +907,14 @@ cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, 
 cudaError_t launch_rx_plan(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, uint32_t span_cap, int nrot,
                            int rot0, uint32_t skip0, uint64_t *span_offset, uint32_t *span_skip, uint8_t *span_rot,
                            uint64_t *result, cudaStream_t st) {
-  k_rx_plan<<<1, 1024, 0, st>>>(info, seams, nspans, span_cap, nrot, rot0, skip0, span_offset, span_skip, span_rot, result);
+  // (the CTA totals live behind the nspans + 1 offsets: the handle allocates span_offset with room for them)
+  const uint32_t nblk = std::max(1u, (nspans + 1023u) / 1024u);
+  unsigned long long *totals = reinterpret_cast<unsigned long long *>(span_offset + (size_t)nspans + 1);
+  unsigned long long *res = reinterpret_cast<unsigned long long *>(result);
+  cudaError_t e = cudaMemsetAsync(result, 0, 9 * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return e;
+  k_rx_plan_local<<<nblk, 1024, 0, st>>>(info, seams, nspans, span_cap, nrot, rot0, skip0, span_offset, span_skip, span_rot, totals, res);
+  k_rx_plan_apply<<<nblk, 1024, 0, st>>>(nspans, nrot, span_offset, span_rot, totals, res);
   return cudaGetLastError();
 }
 

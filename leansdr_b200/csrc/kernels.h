@@ -406,7 +406,7 @@ struct DerandArgs {
   uint8_t *ts_out; uint64_t ts_cap;
   uint64_t *counts;          // device [4]: kept, dropped, pos_out, rs_errs_sum
   const int32_t *flags;      // RS flags for the error sum (may be null)
-  uint32_t *scratch;         // [npackets + 64]
+  uint32_t *scratch;         // [2 * npackets + 16 * (npackets / 1024 + 1)]: per-packet index and position, tile records
 };
 cudaError_t launch_derand(const DerandArgs &a, cudaStream_t st, int *launches);
 

@@ -844,7 +844,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
   h->rx_max_spans = nsp;
   bool aok =
       h->d_rts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_rsflags.alloc(pk_max * 8 + 64) == cudaSuccess &&
-      h->d_ts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_scratch.alloc(std::max<uint64_t>(pk_max * 8 + 4096, 1 << 20)) == cudaSuccess &&
+      h->d_ts.alloc(pk_max * 188 + 256) == cudaSuccess && h->d_scratch.alloc(std::max<uint64_t>(pk_max * 8 + pk_max / 16 + 8192, 1 << 20)) == cudaSuccess &&
       h->d_badwords.alloc(pk_max / 8 + 4096) == cudaSuccess && h->d_rs204.alloc(c.keep_taps ? pk_max * 204 + 256 : 16) == cudaSuccess &&
       h->d_notch_state.alloc(sizeof(NotchState)) == cudaSuccess && h->d_rx_state.alloc(sizeof(RxState)) == cudaSuccess &&
       h->d_rx_info.alloc(sizeof(RxSpanInfo) * nsp) == cudaSuccess && h->d_rx_end.alloc(sizeof(RxState) * nsp) == cudaSuccess &&
@@ -852,7 +852,7 @@ int ldvb_create(const ldvb_config *cfg, ldvb_handle **out) {
       h->d_rx_tail.alloc(sizeof(RxSeamSym) * kRxSeamLog * (size_t)nsp) == cudaSuccess &&
       h->d_rx_seams.alloc(sizeof(RxSeam) * nsp) == cudaSuccess &&
       h->d_rx_spans.alloc(span_bytes) == cudaSuccess &&
-      h->d_rx_off.alloc(8 * ((size_t)nsp + 1)) == cudaSuccess && h->d_rx_skip.alloc(4 * (size_t)nsp) == cudaSuccess &&
+      h->d_rx_off.alloc(8 * ((size_t)nsp + 1) + 16 * ((size_t)nsp / 1024 + 2)) == cudaSuccess && h->d_rx_skip.alloc(4 * (size_t)nsp) == cudaSuccess &&
       h->d_rx_rot.alloc(nsp) == cudaSuccess && h->d_rx_meas.alloc(16 * 4096) == cudaSuccess &&
       h->d_rx_measn.alloc(4) == cudaSuccess && h->d_rx_forced.alloc(sizeof(RxState)) == cudaSuccess &&
       h->d_rx_begin.alloc(sizeof(RxState) * nsp) == cudaSuccess && h->d_rx_power.alloc(16) == cudaSuccess &&

@@ -28,7 +28,7 @@ def emu_bin(tmp_path_factory):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("case,seeds", [("plan", (1, 2)), ("derand", (1,)), ("sync_locked", (1, 2, 3)),
+@pytest.mark.parametrize("case,seeds", [("plan", (1, 2)), ("derand", (1, 2)), ("sync_locked", (1, 2, 3)),
                                         ("sync_search", (1, 2, 3, 4)), ("deconv", (1, 2, 3, 4))])
 def test_control_kernel_equals_its_predecessor(emu_bin, case, seeds):
     for seed in seeds:
