@@ -19,7 +19,8 @@ PROFILE_NAME = {"k_rx": "rx", "k_notch_fir": "notch_fir", "k_fir_edges": "fir_ed
                 "k_notch_verify": "notch_verify", "k_frontend": "frontend", "k_rx_stitch": "rx_stitch", "k_rx_plan": "rx_plan",
                 "k_rx_compact": "rx_compact", "k_deconv_tiled": "deconv_carry", "k_deconv": "deconv_carry", "k_sync_track": "sync_track",
                 "k_sync_flags": "sync_flags", "k_realign": "realign", "k_rs": "deint_rs", "k_derand_scan": "derand",
-                "k_derand_out": "derand", "k_meas_power": "meas_power", "k_meas_ema": "meas_ema"}
+                "k_derand_out": "derand", "k_derand_tiles": "derand", "k_derand_chain": "derand", "k_derand_index": "derand",
+                "k_rx_plan_local": "rx_plan", "k_rx_plan_apply": "rx_plan", "k_meas_power": "meas_power", "k_meas_ema": "meas_ema"}
 
 def base(kn):
     m = re.search(r"(k_[a-z0-9_]+)", kn)
@@ -57,7 +58,7 @@ def launch_list():
     allms = sum(tot.values())
     out = [f"# {tag} -- ncu launch list of the bench command (per-kernel device time)", "",
            "Command (gpurun, 1 GPU): `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file "
-           "gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu` (bench.py raises the warm-up to 3; the list covers "
+           "gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-parity` ( the list covers "
            f"the device-resident steps and the pipelined host-push steps: {sum(cnt.values())} launches of the receive path; the transmit-chain "
            "kernels that synthesise the input are left out).",
            "Times under ncu are cold-cache and serialised: compare SHARES with the live CUDA-event numbers of `bench.py` "
