@@ -356,7 +356,7 @@ k_derand_tiles(DerandArgs a) {
   if (tid < 8) { s_pat[tid] = a.pattern[188 * tid]; s_front[tid] = 0; }
   if (tid == 8) s_err = 0;
   __syncthreads();
-  const uint64_t p = (uint64_t)blockIdx.x * kDrTile + tid;
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + tid;   // (tile = the CTA: kDrTile threads in the library)
   const bool valid = p < a.npackets;
   const unsigned head = valid ? a.rts[188 * p] : 0u;
   const bool reset = valid && (head == 0xb8u || head == (0xb8u ^ 0x55u));
@@ -376,7 +376,7 @@ k_derand_tiles(DerandArgs a) {
   long long none = -1;
   block_scan_max_sum(none, kept, s_last, s_cnt);   // (also orders the atomics above before the reads below)
   __syncthreads();
-  if (tid == 1023) {
+  if (tid == (int)blockDim.x - 1) {
     uint32_t *rec = derand_rec(a, blockIdx.x);
     rec[0] = (uint32_t)(lr + 1);
     rec[1] = kept;
@@ -386,7 +386,7 @@ k_derand_tiles(DerandArgs a) {
 }
 
 __global__ void __launch_bounds__(1024)
-k_derand_chain(DerandArgs a, uint32_t ntiles) {
+k_derand_chain(DerandArgs a, uint32_t ntiles, uint32_t tile /* packets per tile */) {
   __shared__ long long s_last[32];
   __shared__ unsigned s_cnt[32];
   __shared__ long long carry_last;                 // last reset so far (packet index), -1: none yet
@@ -399,7 +399,7 @@ k_derand_chain(DerandArgs a, uint32_t ntiles) {
     const uint32_t i = base + (uint32_t)tid;
     const bool valid = i < ntiles;
     uint32_t *rec = derand_rec(a, valid ? i : 0);
-    const long long first = (long long)i * kDrTile;
+    const long long first = (long long)i * tile;
     const long long mine = (valid && rec[0]) ? first + (long long)rec[0] - 1 : -1;
     unsigned err = valid ? rec[10] : 0u;
     long long incl = mine;
@@ -444,7 +444,7 @@ k_derand_index(DerandArgs a) {
   const uint32_t *rec = derand_rec(a, blockIdx.x);
   const int phi = (int)rec[11];
   const unsigned base = rec[12];
-  const uint64_t p = (uint64_t)blockIdx.x * kDrTile + tid;
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + tid;   // (tile = the CTA: kDrTile threads in the library)
   const bool valid = p < a.npackets;
   const unsigned head = valid ? a.rts[188 * p] : 0u;
   const bool reset = valid && (head == 0xb8u || head == (0xb8u ^ 0x55u));

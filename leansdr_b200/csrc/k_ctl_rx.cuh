@@ -20,7 +20,7 @@ k_rx_plan_local(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, ui
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { nfail = 0; overflow = 0; nmis = 0; mx_phase = 0; mx_freqw = 0; mx_mu = 0; nfail_loose = 0; }
   __syncthreads();
-  const uint32_t j = blockIdx.x * 1024u + (uint32_t)tid;
+  const uint32_t j = blockIdx.x * blockDim.x + (uint32_t)tid;   // (1024 threads in the library; any whole number of warps)
   unsigned long long keep = 0; int rot = 0; uint32_t skip = 0;
   if (j < nspans) {
     const RxSpanInfo inf = info[j];
@@ -69,7 +69,7 @@ k_rx_plan_local(const RxSpanInfo *info, const RxSeam *seams, uint32_t nspans, ui
     span_skip[j] = skip;
     span_rot[j] = (uint8_t)(rincl % nrot);
   }
-  if (tid == 1023) { totals[2 * blockIdx.x] = incl; totals[2 * blockIdx.x + 1] = (unsigned long long)rincl; }
+  if (tid == (int)blockDim.x - 1) { totals[2 * blockIdx.x] = incl; totals[2 * blockIdx.x + 1] = (unsigned long long)rincl; }
   if (tid == 0) {
     if (nfail) atomicAdd(result + 0, (unsigned long long)nfail);
     if (overflow) atomicAdd(result + 3, (unsigned long long)overflow);
@@ -94,7 +94,7 @@ k_rx_plan_apply(uint32_t nspans, int nrot, uint64_t *span_offset, uint8_t *span_
   }
   __syncthreads();
   const unsigned long long base = s_base, rbase = s_rbase;
-  const uint32_t j = blockIdx.x * 1024u + (uint32_t)tid;
+  const uint32_t j = blockIdx.x * blockDim.x + (uint32_t)tid;   // (1024 threads in the library; any whole number of warps)
   if (j < nspans) {
     span_offset[j + 1] += base;
     span_rot[j] = (uint8_t)(((unsigned long long)span_rot[j] + rbase) % (unsigned long long)nrot);

@@ -427,9 +427,9 @@ cudaError_t launch_derand(const DerandArgs &a, cudaStream_t st, int *launches) {
     return cudaMemcpyAsync(a.counts, z, sizeof(z), cudaMemcpyHostToDevice, st);
   }
   const uint32_t ntiles = (uint32_t)((a.npackets + kDrTile - 1) / kDrTile);
-  k_derand_tiles<<<ntiles, 1024, 0, st>>>(a);
-  k_derand_chain<<<1, 1024, 0, st>>>(a, ntiles);
-  k_derand_index<<<ntiles, 1024, 0, st>>>(a);
+  k_derand_tiles<<<ntiles, kDrTile, 0, st>>>(a);
+  k_derand_chain<<<1, 1024, 0, st>>>(a, ntiles, kDrTile);
+  k_derand_index<<<ntiles, kDrTile, 0, st>>>(a);
   k_derand_out<<<(unsigned)((a.npackets + 3) / 4), 256, 0, st>>>(a);
   if (launches) *launches += 4;
   return cudaGetLastError();

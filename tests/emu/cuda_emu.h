@@ -5,7 +5,7 @@
 // shuffles and ballots) are integer programs whose whole risk is in their indexing, so their SOURCE
 // (`leansdr_b200/csrc/k_ctl_*.cuh`, the very text nvcc compiles) is also compiled by g++ against this
 // shim and checked against the kernels they replace on the CPU (`tests/emu/emu_ctl.cpp`,
-// `tests/test_ctl_kernels_cpu.py`).  One OS thread per CUDA thread, std::barrier for
+// `tests/test_ctl_kernels_cpu.py`).  One OS thread per CUDA thread, a sleeping barrier for
 // __syncthreads(), a per-warp exchange slot + barrier for shuffles and ballots, GCC __atomic
 // builtins for atomics.  Blocks of a grid run one after the other (so `__shared__` can be a
 // function-local static).  Nothing here is ever linked into the product.
@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>   // vector types, cudaError_t (host-side declarations only)
 
 #include <barrier>
+#include <condition_variable>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -29,13 +31,36 @@
 
 namespace emu {
 inline unsigned char *g_dyn_smem = nullptr;   // dynamic shared memory of the block being run (set by the harness)
+// Block barrier that SLEEPS (mutex + condition variable): warps that wait for the rest of the block must not spin --
+// std::barrier spins and yields first, and with a few dozen waiting host threads per core the one working warp of a
+// kernel like k_viterbi crawls.
+class SleepBarrier {
+ public:
+  explicit SleepBarrier(std::ptrdiff_t n) : expected_(n), waiting_(0), gen_(0) {}
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    if (++waiting_ == expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); return; }
+    const unsigned long g = gen_;
+    cv_.wait(lk, [&] { return gen_ != g; });
+  }
+  void arrive_and_drop() {
+    std::unique_lock<std::mutex> lk(m_);
+    --expected_;
+    if (expected_ > 0 && waiting_ == expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+  }
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::ptrdiff_t expected_, waiting_;
+  unsigned long gen_;
+};
 struct Warp {
   std::barrier<> bar;
   uint64_t slot[32];
   explicit Warp(int n) : bar(n) {}
 };
 struct BlockCtx {
-  std::unique_ptr<std::barrier<>> bar;
+  std::unique_ptr<SleepBarrier> bar;
   std::vector<std::unique_ptr<Warp>> warps;
   uint64_t red[3];   // __syncthreads_or / _and / _count
 };
@@ -153,7 +178,7 @@ namespace emu {
 inline void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
   for (unsigned b = 0; b < grid; ++b) {
     BlockCtx ctx;
-    ctx.bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)block);
+    ctx.bar = std::make_unique<SleepBarrier>((std::ptrdiff_t)block);
     const unsigned nwarps = (block + 31) / 32;
     for (unsigned w = 0; w < nwarps; ++w) ctx.warps.push_back(std::make_unique<Warp>((int)std::min(32u, block - 32 * w)));
     std::vector<std::thread> th;

@@ -59,7 +59,7 @@ int main(int argc, char **argv) {
   if (!make_trellis(fec, &tr)) { fprintf(stderr, "no trellis\n"); return 2; }
   const Cstln cst = make_cstln(LDVB_CSTLN_QPSK, fec, false);
   const VitSyncs vs = make_vitsyncs(cst, tr);
-  const int nsyncs = std::min(vs.nsyncs, 4);   // (one OS thread per CUDA thread: four decoders are enough)
+  const int nsyncs = std::min(vs.nsyncs, mode == "ws" ? 4 : 3);   // (one OS thread per CUDA thread: a few decoders are enough)
   const int nsh = vs.nshifts, bps = vs.bps, ncs = tr.ncs;
   const int nb = vit_rescan_entries(tr.bits_in);
   bool full = nb == 64;
@@ -76,7 +76,7 @@ int main(int argc, char **argv) {
   std::vector<int> inv(1 << bps, 0);   // coded bits -> symbol index under hypothesis 0
   for (int sym = 0; sym < cst.nsymbols; ++sym) inv[vs.map[0][sym] & ((1 << bps) - 1)] = sym;
 
-  const uint64_t nchunks = 48;
+  const uint64_t nchunks = 32;
   const uint64_t nblocks = nchunks * 128;
   std::vector<uint32_t> symbols(nblocks * nsh + 64, 0);
   {
@@ -99,9 +99,9 @@ int main(int argc, char **argv) {
   for (int d = 0; d < nsyncs; ++d) maps.insert(maps.end(), vs.map[d].begin(), vs.map[d].end());
   std::vector<int32_t> shifts(vs.shift.begin(), vs.shift.begin() + nsyncs);
 
-  const std::vector<uint64_t> seg_start = layout == 1 ? std::vector<uint64_t>{0, 8, 32, nchunks}
-                                        : layout == 2 ? std::vector<uint64_t>{0, 13, 29, nchunks}
-                                                      : std::vector<uint64_t>{0, 24, 32, nchunks};   // P = 8: boundaries on re-sync chunks
+  const std::vector<uint64_t> seg_start = layout == 1 ? std::vector<uint64_t>{0, 8, 24, nchunks}
+                                        : layout == 2 ? std::vector<uint64_t>{0, 9, 20, nchunks}
+                                                      : std::vector<uint64_t>{0, 16, 24, nchunks};   // P = 8: boundaries on re-sync chunks
   const uint32_t nseg = (uint32_t)seg_start.size() - 1;
   const size_t smem = smem_bytes(ncs, nb, nsyncs);
 

@@ -29,7 +29,7 @@ def emu_bin(tmp_path_factory):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("case,seeds", [("plan", (1, 2)), ("derand", (1, 2)), ("sync_locked", (1, 2, 3)),
-                                        ("sync_search", (1, 2, 3, 4)), ("deconv", (1, 2, 3, 4))])
+                                        ("sync_search", (1, 2)), ("deconv", (1, 2))])
 def test_control_kernel_equals_its_predecessor(emu_bin, case, seeds):
     for seed in seeds:
         r = subprocess.run([emu_bin, case, str(seed)], capture_output=True, text=True, timeout=800)
@@ -52,8 +52,8 @@ def emu_vit_bin(tmp_path_factory):
 # metrics + the tie rule), fec 0 = 1/2 through k_viterbi_ws (one warp per time segment); streams with a decodable
 # hypothesis and pure noise; segments far from / close to the start of the batch, and resync_period 1 (--fastlock).
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("args", [(5, "full", 1, "signal", 0), (5, "full", 2, "noise", 1), (5, "full", 3, "noise", 2),
-                                  (0, "ws", 1, "signal", 0), (0, "ws", 2, "noise", 1), (0, "ws", 3, "signal", 2)])
+@pytest.mark.parametrize("args", [(5, "full", 1, "signal", 1), (5, "full", 3, "noise", 2),
+                                  (0, "ws", 1, "signal", 0), (0, "ws", 2, "noise", 1)])
 def test_viterbi_kernel_equals_its_predecessor(emu_vit_bin, args):
     """k_vit_dev.cuh (the text nvcc compiles) on the host: output bytes, entry / exit states of every time segment and
     the elected hypothesis equal those of the kernel that passed the GPU parity suite (tests/emu/vit_v1.cuh), on cold
