@@ -225,3 +225,65 @@ def test_viterbi_rescan_over_distinct_predecessors_selects_the_same_branch(produ
                 if cc[p] <= compact[0]:
                     compact = (cc[p], p, u)
             assert tuple(int(v) for v in full) == tuple(int(v) for v in compact), (fec, s, cs, trial)
+
+
+def test_viterbi_full_trellis_shortcut_selects_the_same_branch(product):
+    """k_viterbi<kVitFull> (7/8): every state is a predecessor of every state, so the reference's rescan
+    (viterbi.h:221-234) is not walked at all: its outcome is the minimum g of the current metrics, taken unless the
+    labelled branch is STRICTLY smaller, and among the states that attain g the one whose entry comes last in this
+    state's label order.  Same (metric, predecessor, uncoded symbol) as the reference's scan over all 256 labels for
+    every state, received label and metric vector: unique minima, ties, the all-equal cold start, negative, zero and
+    positive branch costs."""
+    P = product
+    t = P.host_table(P.default_config(fec="7/8"), "trellis").reshape(64, -1, 2).astype(np.int32)
+    ncs = t.shape[1]
+    pred, us = t[:, :, 0], t[:, :, 1]
+    assert ncs == 256
+    # the precondition the host checks before it selects the kernel (vit_trellis_is_full)
+    for s in range(64):
+        assert set(int(p) for p in pred[s] if p != 65) == set(range(64))
+    # per state: position of predecessor p in the list "largest label of every distinct predecessor, ascending" and
+    # the uncoded symbol of that entry -- the two transposed tables of the kernel
+    pos = np.zeros((64, 64), np.int32)
+    usp = np.zeros((64, 64), np.int32)
+    for s in range(64):
+        seen, k = set(), 64
+        for c in range(ncs - 1, -1, -1):
+            p = int(pred[s, c])
+            if p == 65 or p in seen:
+                continue
+            seen.add(p)
+            k -= 1
+            pos[s, p], usp[s, p] = k, us[s, c]
+        assert k == 0
+    rng = np.random.default_rng(11)
+    for trial in range(80):
+        kind = trial % 4
+        if kind == 0:
+            cc = rng.integers(0, 1000, 64)                          # a unique minimum, almost surely
+        elif kind == 1:
+            cc = rng.integers(0, 3, 64)                             # many ties
+        elif kind == 2:
+            cc = np.zeros(64, np.int64)                             # cold start: all tied
+        else:
+            cc = rng.integers(0, 1000, 64); cc[rng.integers(0, 64, 3)] = 0   # a few tied minima (normalised metrics)
+        bcost = int(rng.integers(-500, 1)) if trial % 5 else int(rng.integers(0, 3))
+        cs = int(rng.integers(0, ncs))
+        g = int(cc.min())
+        tied = [p for p in range(64) if cc[p] == g]
+        for s in range(64):
+            ref = (0x7fffffff, 0, 0)                                # viterbi.h:207-234
+            p = int(pred[s, cs])
+            if p != 65 and cc[p] + bcost <= ref[0]:
+                ref = (int(cc[p]) + bcost, p, int(us[s, cs]))
+            for c in range(ncs):
+                p = int(pred[s, c])
+                if p != 65 and cc[p] <= ref[0]:
+                    ref = (int(cc[p]), p, int(us[s, c]))
+            p = int(pred[s, cs])                                    # the kernel
+            if p != 65 and cc[p] + bcost < g:
+                got = (int(cc[p]) + bcost, p, int(us[s, cs]))
+            else:
+                q = tied[0] if len(tied) == 1 else max(tied, key=lambda x: pos[s, x])
+                got = (g, q, int(usp[s, q]))
+            assert ref == got, (s, cs, trial, ref, got)
