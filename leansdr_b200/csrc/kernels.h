@@ -269,7 +269,9 @@ cudaError_t launch_rx_stitch(const RxStitchArgs &a, const uint32_t *seam_list, u
 cudaError_t launch_rx_stitch_pair(const RxStitchArgs &a, const RxSeamSym *tail, uint32_t n_tail, const RxState *prev_end,
                                   RxSeam *out, cudaStream_t st);
 
-// One-CTA scan over the seams: offsets / skips / cumulative rotations of every span.
+// Scan over the seams: offsets / skips / cumulative rotations of every span (two grids of 1024-span CTAs,
+// k_ctl_rx.cuh).  span_offset holds nspans + 1 offsets AND, behind them, 2 * ceil(nspans / 1024) words of CTA totals:
+// allocate 8 * (nspans + 1) + 16 * (nspans / 1024 + 2) bytes.  result: [9] words, zeroed by the launcher.
 // result[0] = seams that failed verification, [1] = symbols kept, [2] = rotation of the
 // last span, [3] = spans that overflowed their capacity, [4] = verified seams with at least one
 // mismatching hard decision (tolerant rule), [5..7] = max |dphase|, |dfreqw|, |dmu| over the seams (float bits),
