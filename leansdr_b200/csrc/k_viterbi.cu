@@ -34,6 +34,14 @@
 // merge is re-run from its predecessor's exit state (list mode).  Exactness therefore holds by
 // induction, as for the notch segments and the receiver spans; segment 0 always starts from
 // the carried state.
+//
+// Instances (device code in k_vit_dev.cuh, which the host shim of tests/emu compiles too):
+//   k_viterbi<kVitGeneric>  any trellis: CTA per segment, warp per hypothesis, rescan lists;
+//   k_viterbi<kVitFull>     every state a predecessor of every state (7/8): no rescan walk at all, its outcome is the
+//                           minimum of the current metrics plus the tie rule (2.3 GS/s against 0.24 on B200);
+//   k_viterbi<kVitR12>      rate 1/2, trellis rows in registers (LDVB_VIT_WS=0);
+//   k_viterbi_ws            rate 1/2, one WARP per segment, its decoders side by side in shared memory: every resident
+//                           warp walks a decoder (4.2 GS/s against 2.1).
 #include <cstdlib>
 
 #include "common.cuh"
