@@ -1,0 +1,68 @@
+"""The packet kernels of `leansdr_b200/csrc/k_fec.cu` run on the HOST and checked against the oracle.
+
+The device text of the file (everything inside its anonymous namespace: the launchers stay behind) is cut out here and
+compiled by g++ against `tests/emu/cuda_emu.h` together with `tests/emu/emu_fec.cpp`: the Reed-Solomon decoder with
+and without the fused de-interleaver gather (0..10 byte errors per packet: flags, corrected-bit counts and bytes equal
+the oracle's `rs_decoder`), byte re-alignment and sync flags (equal mpeg_sync's definition), and the de-randomiser's
+scan + output grids (equal the oracle's `derandomizer`, dropped packets and carried position included).  The same
+binary built with -fsanitize=thread is the race check of these kernels (see test_ctl_kernels_cpu.py).  The GPU parity
+tests check the same kernels through the C ABI; this is what can be said about them where there is no GPU.
+"""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+CASES = ["rs", "rs_deint", "realign", "derand"]
+
+
+def _build(tmp, oracle_lib, tsan):
+    src = open(os.path.join(ROOT, "leansdr_b200", "csrc", "k_fec.cu")).read()
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("}  // namespace\n")
+    body = src[i:j].replace('#include "k_ctl_fec.cuh"', '#include "%s"' % os.path.join(ROOT, "leansdr_b200", "csrc", "k_ctl_fec.cuh"))
+    assert "<<<" not in body and "k_rs" in body and "k_derand_out" in body
+    inc = str(tmp / "k_fec_dev.inc")
+    open(inc, "w").write(body)
+    out = str(tmp / ("emu_fec_tsan" if tsan else "emu_fec"))
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-w", "-I", CUDA_INC, '-DFEC_DEV_INC="%s"' % inc,
+           os.path.join(ROOT, "tests", "emu", "emu_fec.cpp"), os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp"),
+           oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib), "-o", out]
+    if tsan:
+        cmd[1:1] = ["-g", "-fsanitize=thread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and tsan:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out
+
+
+@pytest.fixture(scope="module")
+def oracle_lib(oracle):
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    p = os.path.join(ROOT, "oracle", "liboracle.so")
+    assert os.path.exists(p)
+    return p
+
+
+@pytest.mark.timeout(600)
+def test_packet_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    exe = _build(tmp_path_factory.mktemp("emu_fec"), oracle_lib, tsan=False)
+    for case in CASES:
+        for seed in (1, 2, 3):
+            r = subprocess.run([exe, case, str(seed)], capture_output=True, text=True, timeout=500)
+            assert r.returncode == 0 and "equal" in r.stdout, f"{case} seed {seed}:\n{r.stderr[-2000:]}"
+
+
+@pytest.mark.timeout(900)
+def test_packet_kernels_are_race_free_under_thread_sanitizer(oracle_lib, tmp_path_factory):
+    exe = _build(tmp_path_factory.mktemp("emu_fec_tsan"), oracle_lib, tsan=True)
+    for case in CASES:
+        r = subprocess.run([exe, case, "4"], capture_output=True, text=True, timeout=800,
+                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+        n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+        assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{case}: {n} reports\n{(r.stdout + r.stderr)[-3000:]}"
