@@ -4,7 +4,10 @@
 // own host trellis (tables.cpp): a random walk through the code for hypothesis 0 with symbol errors and random
 // (negative) costs -- signal for one decoder, noise for the others -- so that labelled branches, rescan winners,
 // unique best states, ties and the all-tied cold start all occur; with `noise` every decoder sees noise.
-// Usage: emu_vit <fec 0..5> <mode: full|generic|r12|ws> <seed> [noise|signal] [layout 0..2]; exit code 0 = identical.
+// With a sixth argument "oracle" the checker is the ORACLE instead (oracle/dvbs_oracle.c, pinned to the reference's
+// viterbi_sync): every hypothesis of the configuration, one serial segment from the constructor state; output bytes,
+// the metrics and path registers of every decoder at the end and the elected hypothesis must equal orc_viterbi_run's.
+// Usage: emu_vit <fec 0..5> <mode: full|generic|r12|ws> <seed> [noise|signal] [layout 0..2] [oracle]; exit code 0 = identical.
 #include "cuda_emu.h"
 
 #include <cstdio>
@@ -15,6 +18,9 @@
 #include "../../leansdr_b200/csrc/kernels.h"
 #include "../../leansdr_b200/csrc/tables.h"
 #include "../../include/leandvb_b200.h"
+extern "C" {
+#include "../../oracle/dvbs_oracle.h"
+}
 
 namespace ldvb {
 namespace v1 {
@@ -52,6 +58,7 @@ int main(int argc, char **argv) {
   // warm_others re-sync chunks into the batch (other decoders exactly from the carried state); 2: resync_period 1
   // (--fastlock: every decoder on every chunk, a vote per chunk)
   const int layout = argc > 5 ? atoi(argv[5]) : 0;
+  const bool vs_oracle = argc > 6 && std::string(argv[6]) == "oracle";
   const int P = layout == 2 ? 1 : 8;
   std::mt19937_64 rng(seed);
 
@@ -59,7 +66,7 @@ int main(int argc, char **argv) {
   if (!make_trellis(fec, &tr)) { fprintf(stderr, "no trellis\n"); return 2; }
   const Cstln cst = make_cstln(LDVB_CSTLN_QPSK, fec, false);
   const VitSyncs vs = make_vitsyncs(cst, tr);
-  const int nsyncs = std::min(vs.nsyncs, mode == "ws" ? 4 : 3);   // (one OS thread per CUDA thread: a few decoders are enough)
+  const int nsyncs = vs_oracle ? vs.nsyncs : std::min(vs.nsyncs, mode == "ws" ? 4 : 3);   // (one OS thread per CUDA thread: a few decoders are enough)
   const int nsh = vs.nshifts, bps = vs.bps, ncs = tr.ncs;
   const int nb = vit_rescan_entries(tr.bits_in);
   bool full = nb == 64;
@@ -146,6 +153,55 @@ int main(int argc, char **argv) {
     rp.list = list.data() + 1;
     launch(1, rp);
   };
+  if (vs_oracle) {
+    // the current text, one serial segment from the constructor state (metrics and paths 0, hypothesis 0, phase 0)
+    Run r;
+    r.out.assign(nchunks * 16 * tr.bits_in, 0xee);
+    r.entry.assign(nsyncs, VitDecState{}); r.exit = r.entry; r.state.assign(nsyncs, VitDecState{});
+    r.ctl_entry.assign(1, VitCtl{}); r.ctl_exit = r.ctl_entry; r.ctl = VitCtl{};
+    VitArgs a{};
+    a.symbols = symbols.data(); a.nchunks = nchunks;
+    a.bits_in = tr.bits_in; a.bits_out = tr.bits_out; a.bps = bps; a.nshifts = nsh; a.nsyncs = nsyncs; a.ncs = ncs; a.nsymbols = cst.nsymbols;
+    a.path_nbits = tr.path_nbits; a.path_depth = tr.path_depth; a.path32 = tr.path32 ? 1 : 0; a.resync_period = P;
+    a.trellis_pred = tr.pred.data(); a.trellis_us = tr.us.data(); a.maps = maps.data(); a.shifts = shifts.data();
+    a.state = r.state.data(); a.ctl = &r.ctl; a.out = r.out.data();
+    const std::vector<uint64_t> one = {0, nchunks};
+    VitSegArgs sg{};
+    sg.seg_start = one.data(); sg.nseg = 1; sg.warm_chunks = 2; sg.warm_others = 2; sg.phase0 = 0; sg.nb = nb; sg.full = full ? 1 : 0;
+    sg.entry = r.entry.data(); sg.exit = r.exit.data(); sg.ctl_entry = r.ctl_entry.data(); sg.ctl_exit = r.ctl_exit.data();
+    const size_t ws_smem = (((size_t)128 * ncs + (size_t)128 * nb + 15) & ~(size_t)15) + (size_t)4 * ((size_t)nsyncs * 1536 + 128 * 4 + 64 + 128);
+    std::vector<unsigned char> dyn(std::max(smem, ws_smem) + 64);
+    emu::g_dyn_smem = dyn.data();
+    if (mode == "ws") emu::launch(1, 32 * v2::kVitWsWarps, [&] { v2::k_viterbi_ws(a, sg, 1); });
+    else if (mode == "r12") emu::launch(1, 32 * nsyncs, [&] { v2::k_viterbi<v2::kVitR12>(a, sg); });
+    else if (mode == "full") emu::launch(1, 32 * nsyncs, [&] { v2::k_viterbi<v2::kVitFull>(a, sg); });
+    else emu::launch(1, 32 * nsyncs, [&] { v2::k_viterbi<v2::kVitGeneric>(a, sg); });
+    // the oracle on the same softsymbols (4 bytes each: cost in the low half, symbol above it: sdr.h:455-458)
+    static orc_cstln oc;
+    if (orc_cstln_build2(&oc, ORC_QPSK, fec, 0)) { fprintf(stderr, "oracle: constellation\n"); return 2; }
+    orc_viterbi *ov = orc_viterbi_new(&oc, fec);
+    orc_viterbi_set_resync_period(ov, P);
+    CHECK(orc_viterbi_nsyncs(ov) == nsyncs && orc_viterbi_nshifts(ov) == nsh && orc_viterbi_bits_in(ov) == tr.bits_in, "oracle configuration");
+    std::vector<uint8_t> want(r.out.size(), 0xee);
+    size_t consumed = 0;
+    const size_t nw = orc_viterbi_run(ov, reinterpret_cast<const uint8_t *>(symbols.data()), nblocks * nsh + (nsh - 1), want.data(), want.size(), &consumed);
+    CHECK(nw == want.size() && consumed == nblocks * nsh, "oracle decoded %zu bytes from %zu symbols", nw, consumed);
+    CHECK(r.out == want, "output bytes differ from the oracle");
+    for (size_t i = 0; i < want.size() && g_fail < 5; ++i) CHECK(r.out[i] == want[i], "out[%zu] (chunk %zu): %02x vs oracle %02x", i, i / (16 * tr.bits_in), r.out[i], want[i]);
+    CHECK(r.ctl_exit[0].current_sync == orc_viterbi_current_sync(ov), "elected hypothesis %d vs oracle %d", r.ctl_exit[0].current_sync, orc_viterbi_current_sync(ov));
+    CHECK(r.ctl_exit[0].resync_phase == orc_viterbi_resync_phase(ov), "re-sync phase");
+    for (int d = 0; d < nsyncs; ++d) {
+      int32_t cost[64]; uint64_t path[64];
+      orc_viterbi_get_dec(ov, d, cost, path);
+      for (int st = 0; st < 64; ++st) CHECK(r.exit[d].cost[st] == cost[st] && r.exit[d].path[st] == path[st], "decoder %d state %d at the end", d, st);
+    }
+    if (!noise_only) CHECK(r.ctl_exit[0].current_sync == 0, "hypothesis 0 was not elected");
+    orc_viterbi_free(ov);
+    if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }
+    printf("identical to the oracle (fec %d, %s, %d decoders, %llu chunks, resync_period %d, current %d)\n", fec, mode.c_str(), nsyncs,
+           (unsigned long long)nchunks, P, r.ctl_exit[0].current_sync);
+    return 0;
+  }
   Run r1, r2;
   run(1, r1);
   run(2, r2);

@@ -37,14 +37,17 @@ def test_control_kernel_equals_its_predecessor(emu_bin, case, seeds):
         assert "identical" in r.stdout
 
 
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+EMU_VIT_SRC = [os.path.join(ROOT, "tests", "emu", "emu_vit.cpp"), os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp"),
+               ORACLE_LIB, "-Wl,-rpath," + os.path.dirname(ORACLE_LIB)]
+
+
 @pytest.fixture(scope="module")
-def emu_vit_bin(tmp_path_factory):
+def emu_vit_bin(tmp_path_factory, oracle):
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("g++ or the CUDA headers are not available")
     out = str(tmp_path_factory.mktemp("emu") / "emu_vit")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-w", "-I", CUDA_INC,
-                           os.path.join(ROOT, "tests", "emu", "emu_vit.cpp"),
-                           os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp"), "-o", out])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-w", "-I", CUDA_INC, *EMU_VIT_SRC, "-o", out])
     return out
 
 
@@ -61,6 +64,22 @@ def test_viterbi_kernel_equals_its_predecessor(emu_vit_bin, args):
     r = subprocess.run([emu_vit_bin, *map(str, args)], capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, f"{args}:\n{r.stderr[-2000:]}"
     assert "identical" in r.stdout
+
+
+# (fec, kernel, seed, stream, layout): 0 = 1/2, 2 = 4/6, 3 = 3/4, 4 = 5/6, 5 = 7/8; layout 2 = resync_period 1 (--fastlock)
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("args", [(0, "ws", 1, "signal", 0), (0, "ws", 2, "noise", 2), (0, "r12", 1, "signal", 0),
+                                  (5, "full", 1, "signal", 0), (5, "full", 2, "noise", 2), (5, "generic", 1, "signal", 0),
+                                  (2, "generic", 1, "signal", 0), (3, "generic", 1, "signal", 0), (4, "generic", 2, "noise", 0)])
+def test_viterbi_kernel_equals_the_oracle_on_the_host(emu_vit_bin, args):
+    """The Viterbi kernels (the text nvcc compiles) against the ORACLE's viterbi_sync, which is pinned to the
+    reference's: every hypothesis of the configuration (4 at QPSK 1/2, 16 at 7/8), one serial segment from the
+    constructor state; output bytes, the 64 metrics and 64 path registers of every decoder at the end, the elected
+    hypothesis and the re-sync phase are the oracle's -- on a decodable stream and on noise, for all five trellises
+    QPSK takes, with resync_period 32-style voting and with a vote per chunk."""
+    r = subprocess.run([emu_vit_bin, *map(str, args), "oracle"], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, f"{args}:\n{r.stderr[-2000:]}"
+    assert "identical to the oracle" in r.stdout
 
 
 def _tsan_build(tmp_path_factory, name, sources):
@@ -81,7 +100,7 @@ def _tsan_warnings(cmd, timeout):
 
 
 @pytest.mark.timeout(3600)
-def test_emulated_kernels_are_race_free_under_thread_sanitizer(tmp_path_factory):
+def test_emulated_kernels_are_race_free_under_thread_sanitizer(tmp_path_factory, oracle):
     """The host shim runs one OS thread per CUDA thread with real barriers behind __syncthreads / __syncwarp / the warp
     collectives, so ThreadSanitizer sees a shared-memory exchange that lacks one of them as a data race -- the class of
     bug a GPU hides until the warp scheduler changes.  First the detector is shown to work (a kernel with a missing
@@ -95,8 +114,7 @@ def test_emulated_kernels_are_race_free_under_thread_sanitizer(tmp_path_factory)
     assert r.returncode == 0 and n >= 2, f"ThreadSanitizer did not report the seeded races ({n}):\n{r.stderr[-1500:]}"
     r, n = _tsan_warnings([sanity, "sync"], 120)
     assert r.returncode == 0 and n == 0, r.stderr[-1500:]
-    vit = _tsan_build(tmp_path_factory, "emu_vit_tsan",
-                      [os.path.join(emu, "emu_vit.cpp"), os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp")])
+    vit = _tsan_build(tmp_path_factory, "emu_vit_tsan", EMU_VIT_SRC)
     cases = [["0", "ws", "2", "noise", "1"]]
     ctl_cases = []
     if os.environ.get("LDVB_EMU_TSAN") == "1":
