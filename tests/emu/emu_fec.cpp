@@ -4,7 +4,13 @@
 // cut out of k_fec.cu by the test (everything inside its anonymous namespace; the launchers stay behind) and included
 // here as FEC_DEV_INC.  The checker is the oracle's C restatement (liboracle.so): RS packets, flags and corrected-bit
 // counts, de-randomised TS.  Built with -fsanitize=thread the same run is the race check of these kernels.
-// Usage: emu_fec <case: rs|rs_deint|realign|derand> <seed>; exit code 0 = equal.
+// `deconv`: the algebraic deconvolver (k_deconv_tiled + the carry thread k_deconv) against the oracle's deconvol_sync for
+// every code rate and each of the four sync hypotheses, two consecutive batches (carried shift register, leftover
+// bits, unread symbols), symbol bases at every 4-byte alignment.
+// `sync`: the MPEG sync tracker (k_sync_flags + k_sync_track + k_realign driven pass by pass like run_sync of pipeline.cu)
+// against the oracle's mpeg_sync on streams with a bit offset, either polarity, garbage in front (short: a search that
+// locks; long: three fruitless sweeps, next_sync), a burst that loses the lock and a re-acquisition.
+// Usage: emu_fec <case: rs|rs_deint|realign|derand|deconv|sync> <seed>; exit code 0 = equal.
 #include "cuda_emu.h"
 
 #include <cstdio>
@@ -147,14 +153,154 @@ static void case_derand(uint64_t seed) {
   if (counts[0] == nwant) CHECK(memcmp(ts.data(), want.data(), 188 * nwant) == 0, "TS bytes");
 }
 
+static void case_deconv(uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  for (int fec = 0; fec <= 5; ++fec) {
+    DeconvPolys dp;
+    if (!make_deconv(fec, &dp)) continue;               // (4/6 is a Viterbi-only trellis)
+    for (int locked = 0; locked < 4; ++locked) {
+      orc_deconv od;
+      orc_deconv_init(&od, fec);
+      orc_deconv_set(&od, locked, 0);
+      CHECK(od.punctperiod == dp.punctperiod && od.punctweight == dp.punctweight, "puncturing of fec %d", fec);
+      uint64_t reg = 0, acc = 0; int n_in = 0, n_out = 0;          // the product's carried state (HypState of pipeline.cu)
+      std::vector<uint32_t> unread;                                // symbols the previous batch left behind
+      for (int batch = 0; batch < 2; ++batch) {
+        const int mis = (int)(rng() % 4);                          // alignment of the stream's read position
+        const size_t fresh = batch ? 2000 + rng() % 3000 : 17000 + rng() % 9000;   // (first batch: several 1024-byte CTAs at every rate)
+        std::vector<uint32_t> buf(mis + unread.size() + fresh + 8, 0xdeadbeefu);
+        uint32_t *sym = buf.data() + mis;
+        for (size_t i = 0; i < unread.size(); ++i) sym[i] = unread[i];
+        for (size_t i = 0; i < fresh; ++i) sym[unread.size() + i] = (uint32_t)(rng() % 4) << 16 | (uint32_t)(rng() & 0xffff);
+        const size_t count = unread.size() + fresh;
+        const uint64_t nbytes = (count - 64) / (dp.punctweight / 2) * dp.punctperiod / 8;   // dvb.h:420
+        DeconvArgs a{};
+        a.symbols = sym; a.nbytes = nbytes; a.reg_in = reg; a.n_in = n_in; a.out_acc = acc; a.n_out = n_out;
+        for (int k = 0; k < 4; ++k) a.hyp[k] = dp.hyp_lut[locked][k];
+        a.punctperiod = dp.punctperiod; a.punctweight = dp.punctweight;
+        for (int b = 0; b < 8; ++b) a.deconv[b] = dp.deconv[b];
+        std::vector<uint8_t> out(nbytes + 8, 0xee);
+        a.out = out.data();
+        uint64_t carry[5] = {0, 0, 0, 0, 0};
+        emu::launch((unsigned)((nbytes + dev::kDcBytes - 1) / dev::kDcBytes), 256, [&] { dev::k_deconv_tiled(a, count); });
+        emu::launch(1, 32, [&] { dev::k_deconv(a, carry); });
+        std::vector<uint8_t> want(nbytes + 8, 0xee);
+        size_t consumed = 0;
+        const size_t nw = orc_deconv_run2(&od, reinterpret_cast<const uint8_t *>(sym), count, want.data(), nbytes, &consumed, 1);
+        CHECK(nw == nbytes, "fec %d hyp %d batch %d: oracle wrote %zu of %llu bytes", fec, locked, batch, nw, (unsigned long long)nbytes);
+        CHECK(memcmp(out.data(), want.data(), nbytes) == 0, "fec %d hyp %d batch %d: bytes differ from the oracle", fec, locked, batch);
+        CHECK(out[nbytes] == 0xee, "fec %d hyp %d batch %d: wrote past the end", fec, locked, batch);
+        CHECK(carry[4] == consumed, "fec %d hyp %d batch %d: consumed %llu vs oracle %zu", fec, locked, batch, (unsigned long long)carry[4], consumed);
+        const orc_dsync &os = od.syncs[locked];
+        CHECK((int)(int64_t)carry[1] == os.n_in && (int)(int64_t)carry[3] == os.n_out, "fec %d hyp %d batch %d: register fill %d/%d vs oracle %d/%d",
+              fec, locked, batch, (int)(int64_t)carry[1], (int)(int64_t)carry[3], os.n_in, os.n_out);
+        const uint64_t mo = os.n_out ? ((os.n_out >= 64) ? ~0ull : ((1ull << os.n_out) - 1)) : 0;
+        CHECK((carry[2] & mo) == (os.out & mo), "fec %d hyp %d batch %d: leftover bits", fec, locked, batch);
+        CHECK(carry[0] == os.in, "fec %d hyp %d batch %d: shift register %016llx vs oracle %016llx", fec, locked, batch,
+              (unsigned long long)carry[0], (unsigned long long)os.in);
+        reg = carry[0]; n_in = (int)(int64_t)carry[1]; acc = carry[2]; n_out = (int)(int64_t)carry[3];
+        unread.assign(sym + carry[4], sym + count);
+      }
+    }
+  }
+}
+
+static void case_sync(uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  for (int variant = 0; variant < 4; ++variant) {
+    // the byte stream mpeg_sync reads: packets with 0x47 / 0xb8 heads, inverted or not, behind a bit offset and garbage
+    const int bitoff = (int)(rng() % 8);
+    const bool inverted = (variant & 1) != 0;
+    const size_t garbage = (variant >= 2) ? 41000 + rng() % 3000 : rng() % 3000;   // (3 sweeps of 8 phases = 39 168 bytes)
+    const size_t npk = 300;   // (a search walks the 8 bit phases one 8-packet window at a time: up to 64 packets to lock)
+    std::vector<uint8_t> pk(204 * npk);
+    const size_t phase0 = rng() % 8;
+    for (size_t p = 0; p < npk; ++p) {
+      for (int i = 0; i < 204; ++i) pk[204 * p + i] = (uint8_t)rng();
+      pk[204 * p] = ((p + phase0) % 8 == 0) ? 0xb8 : 0x47;
+      if (p >= 150 && p < 156) pk[204 * p] ^= 0x21;             // a burst of bad syncs: the lock times out, then a new search
+      if (p == 100 || p == 260) pk[204 * p] ^= 0x04;            // isolated bad syncs: the lock holds
+    }
+    std::vector<uint8_t> in(garbage + pk.size() + 2);
+    for (size_t i = 0; i < garbage; ++i) in[i] = (uint8_t)rng();
+    {  // packets shifted by bitoff bits: byte k of the stream = (window of pk bytes k-1, k) >> (8 - bitoff) style
+      uint32_t w = (uint8_t)rng();
+      for (size_t k = 0; k < pk.size() + 2; ++k) {
+        const uint8_t b = k < pk.size() ? pk[k] : (uint8_t)rng();
+        w = (w << 8) | b;
+        in[garbage + k] = (uint8_t)(w >> bitoff);
+      }
+    }
+    if (inverted) for (size_t k = garbage; k < in.size(); ++k) in[k] ^= 0xff;
+    // product state (ldvb_create / reset_carry) and oracle state
+    SyncState st{};
+    st.report_state = 1; st.phase8 = -1; st.fastlock = 0; st.resync_period = 1;
+    orc_mpegsync om;
+    orc_mpegsync_init(&om);
+    std::vector<uint8_t> got, want;
+    size_t pos_p = 0, pos_o = 0;
+    for (int pass = 0; pass < 200; ++pass) {
+      // one pass of the product over the unread bytes (run_sync)
+      const uint8_t *bytes = in.data() + pos_p;
+      const uint64_t count = in.size() - pos_p;
+      uint64_t nflag = 0;
+      bool product_idle = false;
+      std::vector<uint32_t> words((count / 204) / 32 + 4, 0);
+      SyncResult r{};
+      if (st.synchronized) {
+        nflag = count >= 205 ? (count - 1) / 204 : 0;
+        if (!nflag) product_idle = true;
+        else emu::launch((unsigned)((nflag + 255) / 256), 256, [&] { dev::k_sync_flags(bytes, nflag, &st, words.data()); });
+      } else if (count < 204 * 8 + 1) {
+        product_idle = true;
+      }
+      if (!product_idle) {
+        emu::launch(1, 256, [&] { dev::k_sync_track(bytes, count, &st, words.data(), nflag, &r); });
+        if (r.produced) {
+          const size_t at = got.size();
+          got.resize(at + r.produced);
+          emu::launch((unsigned)((r.produced + 255) / 256), 256, [&] { dev::k_realign(bytes, r.produced, st.bitphase, st.polarity, got.data() + at); });
+        }
+        st = r.st;
+        pos_p += r.consumed;
+      }
+      // one run() of the oracle over ITS unread bytes
+      std::vector<uint8_t> o(in.size() + 256);
+      size_t consumed = 0, nl = 0, nlt = 0; int lock_ev[64]; int switched = 0;
+      std::vector<uint64_t> lt(in.size() / 204 + 8);
+      const size_t nw = orc_mpegsync_run2(&om, nullptr, in.data() + pos_o, in.size() - pos_o, o.data(), o.size(), &consumed, lock_ev, &nl,
+                                          lt.data(), &nlt, 1, &switched);
+      want.insert(want.end(), o.begin(), o.begin() + nw);
+      pos_o += consumed;
+      CHECK(pos_p == pos_o, "variant %d pass %d: consumed %zu vs oracle %zu", variant, pass, pos_p, pos_o);
+      CHECK(got.size() == want.size(), "variant %d pass %d: produced %zu vs oracle %zu", variant, pass, got.size(), want.size());
+      CHECK((!product_idle && r.need_next_sync) == (switched != 0), "variant %d pass %d: next_sync %d vs oracle %d", variant, pass, r.need_next_sync, switched);
+      CHECK(st.synchronized == om.synchronized && st.bitphase == om.bitphase && st.next_sync_count == om.next_sync_count, "variant %d pass %d: state", variant, pass);
+      if (st.synchronized) CHECK((st.polarity & 0xff) == om.polarity && st.phase8 == om.phase8 && st.lock_timeleft == om.lock_timeleft && st.locktime == om.locktime,
+                                 "variant %d pass %d: lock state (phase8 %d/%d, left %u/%lu, time %llu/%lu)", variant, pass, st.phase8, om.phase8,
+                                 st.lock_timeleft, om.lock_timeleft, (unsigned long long)st.locktime, om.locktime);
+      if (g_fail) return;
+      if ((product_idle || (!r.consumed && !r.produced)) && !consumed && !nw) break;
+    }
+    CHECK(got == want, "variant %d: aligned bytes", variant);
+    CHECK(got.size() >= 204 * 120, "variant %d: only %zu aligned bytes", variant, got.size());
+    // what came out are the packets themselves (from the first one the tracker locked on)
+    bool found = false;
+    for (size_t p = 0; p + 1 < npk && !found; ++p) found = got.size() >= 204 && memcmp(got.data(), pk.data() + 204 * p, 204) == 0;
+    CHECK(found, "variant %d: the aligned stream does not start with a transmitted packet", variant);
+  }
+}
+
 int main(int argc, char **argv) {
-  if (argc < 3) { fprintf(stderr, "usage: emu_fec <rs|rs_deint|realign|derand> <seed>\n"); return 2; }
+  if (argc < 3) { fprintf(stderr, "usage: emu_fec <rs|rs_deint|realign|derand|deconv|sync> <seed>\n"); return 2; }
   const std::string c = argv[1];
   const uint64_t seed = strtoull(argv[2], nullptr, 10);
   if (c == "rs") case_rs(seed, false);
   else if (c == "rs_deint") case_rs(seed, true);
   else if (c == "realign") case_realign(seed);
   else if (c == "derand") case_derand(seed);
+  else if (c == "deconv") case_deconv(seed);
+  else if (c == "sync") case_sync(seed);
   else { fprintf(stderr, "unknown case\n"); return 2; }
   if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }
   printf("emu_fec %s seed %llu: equal\n", c.c_str(), (unsigned long long)seed);

@@ -28,8 +28,8 @@ def emu_bin(tmp_path_factory):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("case,seeds", [("plan", (1, 2)), ("derand", (1, 2)), ("sync_locked", (1, 2, 3)),
-                                        ("sync_search", (1, 2)), ("deconv", (1, 2))])
+@pytest.mark.parametrize("case,seeds", [("plan", (1,)), ("derand", (1,)), ("sync_locked", (1, 2)),
+                                        ("sync_search", (1,)), ("deconv", (1,))])
 def test_control_kernel_equals_its_predecessor(emu_bin, case, seeds):
     for seed in seeds:
         r = subprocess.run([emu_bin, case, str(seed)], capture_output=True, text=True, timeout=800)
@@ -55,8 +55,7 @@ def emu_vit_bin(tmp_path_factory, oracle):
 # metrics + the tie rule), fec 0 = 1/2 through k_viterbi_ws (one warp per time segment); streams with a decodable
 # hypothesis and pure noise; segments far from / close to the start of the batch, and resync_period 1 (--fastlock).
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("args", [(5, "full", 1, "signal", 1), (5, "full", 3, "noise", 2),
-                                  (0, "ws", 1, "signal", 0), (0, "ws", 2, "noise", 1)])
+@pytest.mark.parametrize("args", [(5, "full", 1, "signal", 1), (5, "full", 3, "noise", 0), (0, "ws", 2, "noise", 1)])
 def test_viterbi_kernel_equals_its_predecessor(emu_vit_bin, args):
     """k_vit_dev.cuh (the text nvcc compiles) on the host: output bytes, entry / exit states of every time segment and
     the elected hypothesis equal those of the kernel that passed the GPU parity suite (tests/emu/vit_v1.cuh), on cold
@@ -105,7 +104,7 @@ def test_emulated_kernels_are_race_free_under_thread_sanitizer(tmp_path_factory,
     collectives, so ThreadSanitizer sees a shared-memory exchange that lacks one of them as a data race -- the class of
     bug a GPU hides until the warp scheduler changes.  First the detector is shown to work (a kernel with a missing
     __syncthreads and one with a missing __syncwarp are reported, their fixed versions are clean), then the Viterbi
-    kernel with one warp per segment runs next to its predecessor without a report.  LDVB_EMU_TSAN=1 runs every
+    kernels of rate 1/2 (a warp per segment) and 7/8 (no rescan walk) run against the oracle without a report.  LDVB_EMU_TSAN=1 runs every
     emulated kernel this way (Viterbi generic / rate 1/2 / full trellis / warp per segment, seam plan, de-randomiser,
     lock tracker, deconvolution tiles: a few minutes; all clean at the end of round 2)."""
     emu = os.path.join(ROOT, "tests", "emu")
@@ -115,11 +114,11 @@ def test_emulated_kernels_are_race_free_under_thread_sanitizer(tmp_path_factory,
     r, n = _tsan_warnings([sanity, "sync"], 120)
     assert r.returncode == 0 and n == 0, r.stderr[-1500:]
     vit = _tsan_build(tmp_path_factory, "emu_vit_tsan", EMU_VIT_SRC)
-    cases = [["0", "ws", "2", "noise", "1"]]
+    cases = [["0", "ws", "1", "signal", "0", "oracle"], ["5", "full", "1", "signal", "0", "oracle"]]
     ctl_cases = []
     if os.environ.get("LDVB_EMU_TSAN") == "1":
-        cases += [["5", "full", "1", "signal", "1"], ["5", "full", "3", "noise", "2"], ["3", "generic", "1", "signal", "0"],
-                  ["0", "r12", "1", "signal", "0"]]
+        cases += [["0", "ws", "2", "noise", "1"], ["5", "full", "1", "signal", "1"], ["5", "full", "3", "noise", "2"],
+                  ["3", "generic", "1", "signal", "0"], ["0", "r12", "1", "signal", "0"]]
         ctl_cases = ["plan", "derand", "sync_locked", "sync_search", "deconv"]
     for c in cases:
         r, n = _tsan_warnings([vit, *c], 800)

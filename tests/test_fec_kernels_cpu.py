@@ -3,8 +3,13 @@
 The device text of the file (everything inside its anonymous namespace: the launchers stay behind) is cut out here and
 compiled by g++ against `tests/emu/cuda_emu.h` together with `tests/emu/emu_fec.cpp`: the Reed-Solomon decoder with
 and without the fused de-interleaver gather (0..10 byte errors per packet: flags, corrected-bit counts and bytes equal
-the oracle's `rs_decoder`), byte re-alignment and sync flags (equal mpeg_sync's definition), and the de-randomiser's
-scan + output grids (equal the oracle's `derandomizer`, dropped packets and carried position included).  The same
+the oracle's `rs_decoder`), byte re-alignment and sync flags (equal mpeg_sync's definition), the de-randomiser's
+scan + output grids (equal the oracle's `derandomizer`, dropped packets and carried position included), and the
+algebraic deconvolver (`k_deconv_tiled` + the carry thread: bytes, symbols consumed, carried shift register and leftover
+bits equal the oracle's `deconvol_sync` for every code rate, each of the four hypotheses, over two batches), and the
+MPEG sync tracker (`k_sync_flags` + `k_sync_track` + `k_realign`, driven pass by pass like `run_sync` of pipeline.cu:
+bytes consumed and produced, lock state, `next_sync` requests and aligned bytes equal the oracle's `mpeg_sync` on
+streams with a bit offset, either polarity, garbage in front, a burst that loses the lock and a re-acquisition).  The same
 binary built with -fsanitize=thread is the race check of these kernels (see test_ctl_kernels_cpu.py).  The GPU parity
 tests check the same kernels through the C ABI; this is what can be said about them where there is no GPU.
 """
@@ -16,7 +21,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
-CASES = ["rs", "rs_deint", "realign", "derand"]
+CASES = ["rs", "rs_deint", "realign", "derand", "deconv", "sync"]
 
 
 def _build(tmp, oracle_lib, tsan):
@@ -53,7 +58,7 @@ def oracle_lib(oracle):
 def test_packet_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
     exe = _build(tmp_path_factory.mktemp("emu_fec"), oracle_lib, tsan=False)
     for case in CASES:
-        for seed in (1, 2, 3):
+        for seed in (1, 2):
             r = subprocess.run([exe, case, str(seed)], capture_output=True, text=True, timeout=500)
             assert r.returncode == 0 and "equal" in r.stdout, f"{case} seed {seed}:\n{r.stderr[-2000:]}"
 
@@ -62,6 +67,8 @@ def test_packet_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factor
 def test_packet_kernels_are_race_free_under_thread_sanitizer(oracle_lib, tmp_path_factory):
     exe = _build(tmp_path_factory.mktemp("emu_fec_tsan"), oracle_lib, tsan=True)
     for case in CASES:
+        if case == "realign":
+            continue   # (k_realign and k_sync_flags share nothing between threads; `sync` runs them anyway)
         r = subprocess.run([exe, case, "4"], capture_output=True, text=True, timeout=800,
                            env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
         n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
