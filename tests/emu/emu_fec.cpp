@@ -10,7 +10,9 @@
 // `sync`: the MPEG sync tracker (k_sync_flags + k_sync_track + k_realign driven pass by pass like run_sync of pipeline.cu)
 // against the oracle's mpeg_sync on streams with a bit offset, either polarity, garbage in front (short: a search that
 // locks; long: three fruitless sweeps, next_sync), a burst that loses the lock and a re-acquisition.
-// Usage: emu_fec <case: rs|rs_deint|realign|derand|deconv|sync> <seed>; exit code 0 = equal.
+// `hs`: the hard-decision deconvolver of the --hs path (k_hs_errors + k_hs_lock + k_hs_decode) against the oracle's
+// dvb_deconvol_sync_hard: votes every 32 chunks and every chunk, two batches (carried history, vote phase, alignment).
+// Usage: emu_fec <case: rs|rs_deint|realign|derand|deconv|sync|hs> <seed>; exit code 0 = equal.
 #include "cuda_emu.h"
 
 #include <cstdio>
@@ -259,7 +261,18 @@ static void case_sync(uint64_t seed) {
         if (r.produced) {
           const size_t at = got.size();
           got.resize(at + r.produced);
-          emu::launch((unsigned)((r.produced + 255) / 256), 256, [&] { dev::k_realign(bytes, r.produced, st.bitphase, st.polarity, got.data() + at); });
+          // (k_realign is one host thread per byte here and is checked byte for byte in case_realign: in long runs
+          //  only the two ends go through the kernel, the middle through mpeg_sync's formula)
+          const uint64_t edge = 1024;
+          if (r.produced <= 2 * edge) {
+            emu::launch((unsigned)((r.produced + 255) / 256), 256, [&] { dev::k_realign(bytes, r.produced, st.bitphase, st.polarity, got.data() + at); });
+          } else {
+            emu::launch((unsigned)(edge / 256), 256, [&] { dev::k_realign(bytes, edge, st.bitphase, st.polarity, got.data() + at); });
+            for (uint64_t i = edge; i < r.produced - edge; ++i)
+              got[at + i] = (uint8_t)((((((unsigned)bytes[i] << 8) | bytes[i + 1]) >> st.bitphase) & 0xffu) ^ (unsigned)(st.polarity & 0xff));
+            const uint64_t tail0 = r.produced - edge;
+            emu::launch((unsigned)(edge / 256), 256, [&] { dev::k_realign(bytes + tail0, edge, st.bitphase, st.polarity, got.data() + at + tail0); });
+          }
         }
         st = r.st;
         pos_p += r.consumed;
@@ -291,8 +304,53 @@ static void case_sync(uint64_t seed) {
   }
 }
 
+static void case_hs(uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  for (int period : {32, 1}) {
+    orc_hsdeconv od;
+    orc_hsdeconv_init(&od, period);
+    uint64_t hist = 0; int hist_valid = 0, phase = 0, locked = 0;     // the product's carry (pipeline.cu, --hs branch)
+    for (int batch = 0; batch < 2; ++batch) {
+      const uint64_t nchunks = batch ? 37 + rng() % 20 : 70 + rng() % 30;
+      const uint64_t nsym = nchunks * 512;
+      std::vector<uint32_t> words(nsym);
+      std::vector<uint8_t> syms(nsym);
+      // runs of one symbol sequence repeated make some alignments clearly better than others; noise in between
+      for (uint64_t i = 0; i < nsym; ++i) { syms[i] = (uint8_t)((i / 3000) % 2 ? rng() % 4 : (i * 7 + i / 5) % 4); words[i] = (uint32_t)syms[i] << 16 | (uint32_t)(rng() & 0xffff); }
+      const uint64_t ngroups_max = nchunks / period + 2;
+      std::vector<uint32_t> errors(ngroups_max * 4 + 16, 0);
+      std::vector<uint8_t> lock_of_chunk(nchunks + 16, 0xee), out(nchunks * 64 + 8, 0xee);
+      int32_t state_out[4] = {-1, -1, -1, -1};
+      HsDeconvArgs a{};
+      a.symbols = words.data(); a.nchunks = nchunks; a.hist = hist; a.hist_valid = hist_valid;
+      a.resync_phase = phase; a.resync_period = period; a.locked = locked;
+      a.errors = errors.data(); a.lock_of_chunk = lock_of_chunk.data(); a.out = out.data(); a.state_out = state_out;
+      // launch_hs_deconv (k_fec.cu)
+      const uint64_t first = (uint64_t)((period - phase) % period);
+      const uint32_t ngroups = first < nchunks ? (uint32_t)((nchunks - first + period - 1) / period) : 0;
+      if (ngroups) emu::launch(ngroups, 128, [&] { dev::k_hs_errors(a, first, ngroups); });
+      emu::launch(1, 32, [&] { dev::k_hs_lock(a, ngroups); });
+      emu::launch((unsigned)((nchunks * 64 + 255) / 256), 256, [&] { dev::k_hs_decode(a, first); });
+      std::vector<uint8_t> want(nchunks * 64 + 8, 0xee);
+      size_t consumed = 0;
+      const size_t nw = orc_hsdeconv_run(&od, syms.data(), nsym, want.data(), nchunks * 64, &consumed);
+      CHECK(nw == nchunks * 64 && consumed == nsym, "period %d batch %d: oracle wrote %zu bytes from %zu symbols", period, batch, nw, consumed);
+      CHECK(memcmp(out.data(), want.data(), nchunks * 64) == 0, "period %d batch %d: bytes differ from the oracle", period, batch);
+      for (uint64_t i = 0; i < nchunks * 64 && g_fail < 4; ++i) CHECK(out[i] == want[i], "byte %llu (chunk %llu): %02x vs %02x", (unsigned long long)i, (unsigned long long)(i / 64), out[i], want[i]);
+      CHECK(out[nchunks * 64] == 0xee, "period %d batch %d: wrote past the end", period, batch);
+      CHECK(state_out[0] == od.locked, "period %d batch %d: alignment %d vs oracle %d", period, batch, state_out[0], od.locked);
+      locked = state_out[0];
+      phase = (int)((phase + nchunks) % (uint64_t)period);
+      CHECK(phase == od.resync_phase, "period %d batch %d: vote phase", period, batch);
+      hist = 0;
+      for (int i = 0; i < 32; ++i) hist = (hist << 2) | ((words[nsym - 32 + i] >> 16) & 3u);
+      hist_valid = 32;
+    }
+  }
+}
+
 int main(int argc, char **argv) {
-  if (argc < 3) { fprintf(stderr, "usage: emu_fec <rs|rs_deint|realign|derand|deconv|sync> <seed>\n"); return 2; }
+  if (argc < 3) { fprintf(stderr, "usage: emu_fec <rs|rs_deint|realign|derand|deconv|sync|hs> <seed>\n"); return 2; }
   const std::string c = argv[1];
   const uint64_t seed = strtoull(argv[2], nullptr, 10);
   if (c == "rs") case_rs(seed, false);
@@ -301,6 +359,7 @@ int main(int argc, char **argv) {
   else if (c == "derand") case_derand(seed);
   else if (c == "deconv") case_deconv(seed);
   else if (c == "sync") case_sync(seed);
+  else if (c == "hs") case_hs(seed);
   else { fprintf(stderr, "unknown case\n"); return 2; }
   if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }
   printf("emu_fec %s seed %llu: equal\n", c.c_str(), (unsigned long long)seed);

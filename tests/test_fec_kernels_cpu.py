@@ -9,7 +9,9 @@ algebraic deconvolver (`k_deconv_tiled` + the carry thread: bytes, symbols consu
 bits equal the oracle's `deconvol_sync` for every code rate, each of the four hypotheses, over two batches), and the
 MPEG sync tracker (`k_sync_flags` + `k_sync_track` + `k_realign`, driven pass by pass like `run_sync` of pipeline.cu:
 bytes consumed and produced, lock state, `next_sync` requests and aligned bytes equal the oracle's `mpeg_sync` on
-streams with a bit offset, either polarity, garbage in front, a burst that loses the lock and a re-acquisition).  The same
+streams with a bit offset, either polarity, garbage in front, a burst that loses the lock and a re-acquisition), and the
+hard-decision deconvolver of the `--hs` path (`k_hs_errors` + `k_hs_lock` + `k_hs_decode`: bytes, alignment and vote
+phase equal the oracle's `dvb_deconvol_sync_hard`, votes every 32 chunks and every chunk, over two batches).  The same
 binary built with -fsanitize=thread is the race check of these kernels (see test_ctl_kernels_cpu.py).  The GPU parity
 tests check the same kernels through the C ABI; this is what can be said about them where there is no GPU.
 """
@@ -21,7 +23,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
-CASES = ["rs", "rs_deint", "realign", "derand", "deconv", "sync"]
+CASES = ["rs", "rs_deint", "realign", "derand", "deconv", "sync", "hs"]
 
 
 def _build(tmp, oracle_lib, tsan):
