@@ -75,3 +75,28 @@ def test_packet_kernels_are_race_free_under_thread_sanitizer(oracle_lib, tmp_pat
                            env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
         n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
         assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{case}: {n} reports\n{(r.stdout + r.stderr)[-3000:]}"
+
+
+@pytest.mark.timeout(600)
+def test_transmit_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """The integer kernels of the transmit chain (`leansdr_b200/csrc/tx.cu`: leantsgen packets, randomizer + rs_encoder,
+    interleaver, dvb_convol for every code rate and symbol width) against the oracle's restatement of leandvbtx, which
+    is pinned to the reference transmitter (tests/test_oracle_tx_cpu.py).  The device text is the first anonymous
+    namespace of tx.cu; its one dynamic shared-memory declaration is pointed at the shim's buffer."""
+    tmp = tmp_path_factory.mktemp("emu_tx")
+    src = open(os.path.join(ROOT, "leansdr_b200", "csrc", "tx.cu")).read()
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("}  // namespace\n")
+    body = src[i:j]
+    assert "<<<" not in body and "k_tx_convol" in body and "extern __shared__ float2 s_taps[];" in body
+    body = body.replace("extern __shared__ float2 s_taps[];", "float2 *s_taps = reinterpret_cast<float2 *>(emu::g_dyn_smem);")
+    inc = str(tmp / "tx_dev.inc")
+    open(inc, "w").write(body)
+    exe = str(tmp / "emu_tx")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DTX_DEV_INC="%s"' % inc,
+                        os.path.join(ROOT, "tests", "emu", "emu_tx.cpp"), os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp"),
+                        oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for seed in (1, 2):
+        r = subprocess.run([exe, str(seed)], capture_output=True, text=True, timeout=500)
+        assert r.returncode == 0 and "equal" in r.stdout, f"seed {seed}:\n{r.stderr[-2000:]}"
