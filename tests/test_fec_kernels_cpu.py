@@ -100,3 +100,36 @@ def test_transmit_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_fact
     for seed in (1, 2):
         r = subprocess.run([exe, str(seed)], capture_output=True, text=True, timeout=500)
         assert r.returncode == 0 and "equal" in r.stdout, f"seed {seed}:\n{r.stderr[-2000:]}"
+
+
+@pytest.mark.timeout(600)
+def test_telemetry_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """`k_spectrum.cu` on the host: k_meas_power (the reference's FFT butterfly order over shared memory, one barrier per
+    stage, 4096 and 1024 points) and k_meas_ema (running average, band sums of do_cnr) against the oracle's cfft_engine
+    and cnr_fft / spectrum, float for float (-ffp-contract=off; the shim's fmul / fadd are single IEEE operations like
+    the device's _rn intrinsics): power bins, the average after every measurement, the CNR value.  Then the same run
+    under ThreadSanitizer: the barrier-staged FFT is the kind of kernel a missing __syncthreads hides in."""
+    tmp = tmp_path_factory.mktemp("emu_meas")
+    src = open(os.path.join(ROOT, "leansdr_b200", "csrc", "k_spectrum.cu")).read()
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("}  // namespace\n")
+    body = src[i:j]
+    assert "<<<" not in body and "k_meas_power" in body and "k_meas_ema" in body
+    inc = str(tmp / "meas_dev.inc")
+    open(inc, "w").write(body)
+    base = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DMEAS_DEV_INC="%s"' % inc,
+            os.path.join(ROOT, "tests", "emu", "emu_meas.cpp"), oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib)]
+    exe = str(tmp / "emu_meas")
+    r = subprocess.run(base + ["-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for seed in (1, 2, 3):
+        r = subprocess.run([exe, str(seed)], capture_output=True, text=True, timeout=500)
+        assert r.returncode == 0 and "equal" in r.stdout, f"seed {seed}:\n{r.stderr[-2000:]}"
+    tsan = str(tmp / "emu_meas_tsan")
+    r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    r = subprocess.run([tsan, "4"], capture_output=True, text=True, timeout=500,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+    n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
