@@ -133,3 +133,41 @@ def test_telemetry_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_fac
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
     n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
     assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
+
+
+@pytest.mark.timeout(600)
+def test_frontend_kernel_equals_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """`k_frontend` (cconverter / scaler -> rotator -> fir_filter + decimator fused; the FIR stage of north_star) on
+    the host against the oracle's chain of the same runnables, float for float, in six configurations: f32 with the 5
+    real taps of the bench, u8 + rotator + 13 retuned (complex) taps + decimation 2, s16 through the decimator alone,
+    scaled f32 with 31 retuned taps, u16 + rotator + 7 taps, s8 with 40 taps and decimation 5; two full tiles and a ragged
+    one each.  The host-built rotator table and shifted taps (with the reference's unsigned tap-index quirk) must equal
+    the oracle's first.  The bulk copy is done at issue time and the mbarrier is a release / acquire flag; then the same
+    run under ThreadSanitizer."""
+    tmp = tmp_path_factory.mktemp("emu_front")
+    src = open(os.path.join(ROOT, "leansdr_b200", "csrc", "k_frontend.cu")).read()
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("}  // namespace\n")
+    body = src[i:j]
+    decl = "extern __shared__ __align__(128) unsigned char smem[];"
+    assert "<<<" not in body and "k_frontend" in body and decl in body
+    body = body.replace(decl, "unsigned char *smem = emu::g_dyn_smem;")
+    inc = str(tmp / "front_dev.inc")
+    open(inc, "w").write(body)
+    base = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DFRONT_DEV_INC="%s"' % inc,
+            os.path.join(ROOT, "tests", "emu", "emu_front.cpp"), os.path.join(ROOT, "leansdr_b200", "csrc", "tables.cpp"),
+            oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib)]
+    exe = str(tmp / "emu_front")
+    r = subprocess.run(base + ["-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for seed in (1, 2, 3):
+        r = subprocess.run([exe, str(seed)], capture_output=True, text=True, timeout=500)
+        assert r.returncode == 0 and "equal" in r.stdout, f"seed {seed}:\n{r.stderr[-2000:]}"
+    tsan = str(tmp / "emu_front_tsan")
+    r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    r = subprocess.run([tsan, "4"], capture_output=True, text=True, timeout=500,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+    n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
