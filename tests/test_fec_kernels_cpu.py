@@ -171,3 +171,75 @@ def test_frontend_kernel_equals_the_oracle_on_the_host(oracle_lib, tmp_path_fact
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
     n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
     assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
+
+
+@pytest.mark.timeout(600)
+def test_notch_detect_kernel_equals_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """`k_notch_detect` (auto_notch::detect: cfft_engine's 4096-point FFT in shared memory, glibc's hypotf in double,
+    the nslots largest bins with their neighbours blanked) on the host against the oracle's auto_notch made to detect on
+    every block: 1..4 slots, cf32 and u8 input, tones on random bins (two of them adjacent), noise.  Then the same run
+    under ThreadSanitizer."""
+    tmp = tmp_path_factory.mktemp("emu_nd")
+    src = open(os.path.join(ROOT, "leansdr_b200", "csrc", "k_notch.cu")).read()
+    i = src.index("__device__ __forceinline__ float2 load_sample(")
+    j = src.index("// ---------------------------------------------------------------------- apply")
+    body = src[i:j]
+    assert "<<<" not in body and "k_notch_detect" in body
+    inc = str(tmp / "detect_dev.inc")
+    open(inc, "w").write(body)
+    base = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DDETECT_DEV_INC="%s"' % inc,
+            os.path.join(ROOT, "tests", "emu", "emu_notch_detect.cpp"), oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib)]
+    exe = str(tmp / "emu_nd")
+    r = subprocess.run(base + ["-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=500)
+    assert r.returncode == 0 and "equal" in r.stdout, r.stderr[-2000:]
+    tsan = str(tmp / "emu_nd_tsan")
+    r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    r = subprocess.run([tsan, "2"], capture_output=True, text=True, timeout=500,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+    n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
+
+
+@pytest.mark.timeout(900)
+def test_notch_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """`k_notch_guess` + `k_notch_apply` + `k_notch_verify` (k_notch.cu) on the host against the oracle's
+    auto_notch::process, float for float, with 1, 2 and 3 slots: one exact segment over the batch; one segment per block
+    with guessed start states and two warm-up blocks (every segment merges bit for bit); and without warm-up blocks,
+    where nothing merges and every segment is re-run from its predecessor's exit state in rounds (the scheme of
+    run_notch / notch_verify_repair) -- the streams and the carried estimates are the oracle's either way.  The
+    asynchronous row copies are done at issue time.  Then the same run under ThreadSanitizer."""
+    tmp = tmp_path_factory.mktemp("emu_na")
+    csrc = os.path.join(ROOT, "leansdr_b200", "csrc")
+    src = open(os.path.join(csrc, "k_notch.cu")).read()
+    common = open(os.path.join(csrc, "notch_common.cuh")).read()
+    ci = common.index("namespace {\n") + len("namespace {\n")
+    cj = common.index("}  // namespace\n}  // namespace ldvb")
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("template <int FMT, int NSLOTS>\ncudaError_t launch_apply_t(")
+    vi = src.index("// entry(j) == exit(j-1), bit for bit, for every segment that started from a guess.")
+    vj = src.index("}  // namespace\n", vi)
+    body, verify = src[i:j], src[vi:vj]
+    decl = "extern __shared__ __align__(128) unsigned char smem[];"
+    assert decl in body and "<<<" not in body and "<<<" not in verify and "k_notch_verify" in verify
+    inc = str(tmp / "notch_dev.inc")
+    open(inc, "w").write(common[ci:cj] + "\n" + body.replace(decl, "unsigned char *smem = emu::g_dyn_smem;") + "\n" + verify)
+    base = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DNOTCH_DEV_INC="%s"' % inc,
+            os.path.join(ROOT, "tests", "emu", "emu_notch_apply.cpp"), oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib)]
+    exe = str(tmp / "emu_na")
+    r = subprocess.run(base + ["-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0 and "equal" in r.stdout, r.stderr[-2000:]
+    assert "0 warm-up blocks: 8 of 9 segments repaired" in r.stderr      # the repair path ran
+    tsan = str(tmp / "emu_na_tsan")
+    r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    r = subprocess.run([tsan, "2", "quick"], capture_output=True, text=True, timeout=800,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+    n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
