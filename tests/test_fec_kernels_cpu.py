@@ -243,3 +243,51 @@ def test_notch_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
     n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
     assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
+
+
+@pytest.mark.timeout(900)
+def test_fused_notch_fir_kernel_equals_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """The DEFAULT notch kernel of the receive chain, `k_notch_fir` + `k_fir_edges` (k_notchfir.cu: auto_notch and the
+    fir_filter behind it fused; a chain warp and eight worker warps per 16 segments, a block barrier per 64-sample tile,
+    five stages of asynchronous row copies), behind `k_notch_guess` and in front of `k_notch_verify`, on the host against
+    the oracle's auto_notch -> fir_filter, float for float: two consecutive batches (carried notched samples and
+    estimates), segments that merge after two warm-up blocks and segments without warm-up that are all re-run from their
+    predecessors' exit states (rewriting their edge samples), 5 real taps (the bench configuration), 13 retuned taps,
+    plain notch through the same kernel, 1 and 2 slots, the telemetry dump.  Then under ThreadSanitizer."""
+    tmp = tmp_path_factory.mktemp("emu_nf")
+    csrc = os.path.join(ROOT, "leansdr_b200", "csrc")
+    common = open(os.path.join(csrc, "notch_common.cuh")).read()
+    ci = common.index("namespace {\n") + len("namespace {\n")
+    cj = common.index("}  // namespace\n}  // namespace ldvb")
+    decl = "extern __shared__ __align__(128) unsigned char smem[];"
+    src = open(os.path.join(csrc, "k_notch.cu")).read()
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("template <int FMT, int NSLOTS>\ncudaError_t launch_apply_t(")
+    vi = src.index("// entry(j) == exit(j-1), bit for bit, for every segment that started from a guess.")
+    vj = src.index("}  // namespace\n", vi)
+    inc1 = str(tmp / "notch_dev.inc")
+    open(inc1, "w").write(common[ci:cj] + "\n" + src[i:j].replace(decl, "unsigned char *smem = emu::g_dyn_smem;") + "\n" + src[vi:vj])
+    srcf = open(os.path.join(csrc, "k_notchfir.cu")).read()
+    i = srcf.index("namespace {\n") + len("namespace {\n")
+    j = srcf.index("template <int FMT, int NSLOTS, bool FIR>\ncudaError_t launch_nf_t(")
+    body = srcf[i:j]
+    assert decl in body and "<<<" not in body and "k_notch_fir" in body and "k_fir_edges" in body
+    inc2 = str(tmp / "notchfir_dev.inc")
+    open(inc2, "w").write(common[ci:cj] + "\n" + body.replace(decl, "unsigned char *smem = emu::g_dyn_smem;"))
+    base = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DNOTCH_DEV_INC="%s"' % inc1,
+            '-DNOTCHFIR_DEV_INC="%s"' % inc2, os.path.join(ROOT, "tests", "emu", "emu_notchfir.cpp"),
+            os.path.join(csrc, "tables.cpp"), oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib)]
+    exe = str(tmp / "emu_nf")
+    r = subprocess.run(base + ["-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0 and "equal" in r.stdout, r.stderr[-2000:]
+    assert "0 warm-up blocks: 24 segments repaired" in r.stderr          # the repair path ran
+    tsan = str(tmp / "emu_nf_tsan")
+    r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    r = subprocess.run([tsan, "2", "quick"], capture_output=True, text=True, timeout=800,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+    n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
