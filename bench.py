@@ -39,6 +39,16 @@ BOUND = {"frontend": "hbm", "notch_guess": "hbm", "notch_fir": "issue/latency", 
 REF_FLAGS = ["--f32", "-f", "2400e3", "--sr", "2000e3", "--cr", "1/2", "--standard", "DVB-S", "--resample"]
 
 
+def notch_guess_bytes(n, in_bytes=8, anf=1, sms=148):
+    """Bytes k_notch_guess has to read per launch: the two 4096-sample blocks in front of every segment's warm-up
+    (k_notch.cu: `(b + warm + 2 - block0) % seg_blocks > 1` returns at once); segment length as pipeline.cu chooses
+    it for the fused kernel (16 rows per CTA, one wave of CTAs: two per SM with one notch slot, else one)."""
+    nblocks = max(1, n // 4096)
+    target = 16 * sms * (2 if anf == 1 else 1)
+    seg = min(64, max(1, -(-nblocks // target)))
+    return n * in_bytes * min(2, seg) // seg
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -468,7 +478,8 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     kern = {k: v["ms_total"] / max(v["launches"], 1) for k, v in prof.items()}
     per_step = {k: v["ms_total"] / a.steps for k, v in prof.items()}
     nloc = ch.n_halo + ch.n_chunk
-    alg_bytes = {"frontend": nloc * 16, "notch_apply": nloc * 16, "rx": nloc * 8 + int(nloc / 1.2) * 4}
+    alg_bytes = {"frontend": nloc * 16, "notch_apply": nloc * 16, "notch_fir": nloc * 16, "notch_guess": notch_guess_bytes(nloc),
+                 "rx": nloc * 8 + int(nloc / 1.2) * 4}
     dom = max(per_step, key=per_step.get)
     ab = alg_bytes.get(dom, nloc * 8)
     ach = ab / (kern[dom] * 1e-3) / 1e9
@@ -779,6 +790,7 @@ def main():
         "frontend": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),   # IQ in + cf32 out (FIR, D=1)
         "notch_apply": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),
         "notch_fir": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),    # IQ in + preprocessed cf32 out (notch + FIR fused)
+        "notch_guess": notch_guess_bytes(n, 2 if a.variant in ("u8", "hs") else 8),   # 2 blocks per segment, not the stream
         "viterbi": sym * 4 + sym // 8,
         "rx": n * 8 + sym * 4,                        # cf32 in + softsymbol out
         "rx_compact": sym * 8,

@@ -16,6 +16,25 @@ def pytest_configure(config):
         config.option.timeout = 300
 
 
+@pytest.hookimpl(tryfirst=True)
+def pytest_cmdline_main(config):
+    """The CPU suite (`-m "not gpu"`) is host work only -- oracle runs, g++ builds of the emulated kernels,
+    ThreadSanitizer binaries -- and every test is independent of the others: spread it over worker processes when
+    pytest-xdist is in the image and the caller did not choose (`-n ...`, `-p no:xdist`, LDVB_TESTS_SERIAL=1).
+    The GPU suite is left as the caller runs it (one process unless `-n` is given)."""
+    opt = config.option
+    if (os.environ.get("PYTEST_XDIST_WORKER") or os.environ.get("LDVB_TESTS_SERIAL")
+            or not config.pluginmanager.hasplugin("xdist") or getattr(opt, "numprocesses", None) is not None
+            or getattr(opt, "collectonly", False) or getattr(opt, "usepdb", False)
+            or "not gpu" not in (getattr(opt, "markexpr", "") or "")):
+        return None
+    n = min(6, max(1, (os.cpu_count() or 1) - 1))
+    if n > 1:
+        opt.numprocesses = n
+        opt.dist = "load"
+    return None
+
+
 @pytest.fixture(scope="session")
 def built():
     """Native pieces are built once per session (no-op when up to date)."""

@@ -147,12 +147,15 @@ static void run_case(std::mt19937_64 &rng, bool speculative, uint32_t warm_block
 int main(int argc, char **argv) {
   const uint64_t seed = argc > 1 ? strtoull(argv[1], nullptr, 10) : 1;
   std::mt19937_64 rng(seed);
-  run_case<1>(rng, false);
-  run_case<1>(rng, true);
+  const bool quick = argc > 2;   // (under ThreadSanitizer: one exact, one merging and one repair case -- the barriers and
+                                 //  exchanges do not depend on the slot count; the full list runs in the plain build)
+  if (!quick) {
+    run_case<1>(rng, false);
+    run_case<1>(rng, true);
+  }
   run_case<2>(rng, false);
   run_case<2>(rng, true);
-  run_case<3>(rng, true);
-  const bool quick = argc > 2;   // (under ThreadSanitizer: one repair case instead of two)
+  if (!quick) run_case<3>(rng, true);
   run_case<1>(rng, true, 0);   // the guess alone does not merge: every segment is re-run exactly, in rounds
   if (!quick) run_case<2>(rng, true, 0);
   if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }

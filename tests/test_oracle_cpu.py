@@ -400,21 +400,21 @@ def test_fastlock_oracle_equals_reference_runnables(oracle, cr, fec_id, ratio, F
 
 
 @pytest.mark.skipif(not V.have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("cr,ratio,Fs,vit,exact", [("1/2", "6/5", 2.4e6, False, True), ("3/4", "2", 4e6, False, True),
-                                                    ("7/8", "2", 4e6, True, True), ("7/8", "2", 4e6, False, False)])
-def test_fastlock_chain_vs_reference_leandvb(oracle, cr, ratio, Fs, vit, exact):
+@pytest.mark.parametrize("cr,ratio,Fs,vit,exact,npk", [("1/2", "6/5", 2.4e6, False, True, 400), ("3/4", "2", 4e6, False, True, 400),
+                                                        ("7/8", "2", 4e6, True, True, 160), ("7/8", "2", 4e6, False, False, 400)])
+def test_fastlock_chain_vs_reference_leandvb(oracle, cr, ratio, Fs, vit, exact, npk):
     """`leandvb --fastlock` (unmodified reference, default buffers) vs the oracle chain under the
     large-batch schedule.  Where the first window is already aligned the TS is identical; at 7/8
     without Viterbi the acquisition (which window sees which alignment) depends on the schedule:
     both decode the transmitted packets, the reference starts a few packets earlier."""
     O = oracle
-    raw = V.ref_iq(400, ratio=ratio, cr=cr, fmt="f32")
+    raw = V.ref_iq(npk, ratio=ratio, cr=cr, fmt="f32")    # (the oracle's 7/8 Viterbi scans 256 labels per step: fewer packets)
     flags = ["--f32", "-f", str(Fs), "--sr", "2000e3", "--cr", cr, "--fastlock"] + (["--viterbi"] if vit else [])
     want = V.ref_leandvb(raw, flags)
     got = O.Chain(O.Config(fmt="f32", fec=cr, Fs=Fs, fastlock=True, viterbi=vit)).run(raw)["ts"]
     if exact:
         n = min(len(want), len(got))
-        assert n > 300 and np.array_equal(want[:n], got[:n]) and abs(len(want) - len(got)) <= 1
+        assert n > 3 * npk // 4 and np.array_equal(want[:n], got[:n]) and abs(len(want) - len(got)) <= 1
         return
     sent = V.ts_packets(400)
 

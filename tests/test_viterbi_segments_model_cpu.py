@@ -128,7 +128,7 @@ def _same(a, b):
 
 CASES = [
     ("qpsk12-noise", "QPSK", "1/2", dict(fmt="f32", viterbi=True), dict(noise_db=25), 500),
-    ("qpsk78", "QPSK", "7/8", dict(fmt="f32", viterbi=True, fec="7/8", Fs=4e6), dict(cr="7/8", ratio="2"), 900),
+    ("qpsk78", "QPSK", "7/8", dict(fmt="f32", viterbi=True, fec="7/8", Fs=4e6), dict(cr="7/8", ratio="2"), 560),
     ("8psk23", "8PSK", "2/3", dict(fmt="f32", viterbi=True, cstln="8PSK", fec="2/3", Fs=4e6), dict(cr="2/3", ratio="2", cst="8PSK"), 500),
 ]
 
