@@ -1,0 +1,298 @@
+// emu_rx.cpp -- TEST INFRASTRUCTURE.  Runs the receiver kernels of leansdr_b200/csrc/k_rx.cu -- k_rx_serial (EXACT
+// mode, settling pass), k_rx (one lane per time span: warm-up, owned chunks, verification overlap, seam logs; repair
+// mode re-runs a span from its predecessor's end state), k_rx_stitch, k_rx_plan_local/_apply and k_rx_compact -- on the
+// host (cuda_emu.h) against the oracle's cstln_receiver (orc_rx_run, sdr.h:772-915), FIELD FOR FIELD: this file is built
+// with -ffp-contract=off and the shim's fmul / fadd / cmul are single IEEE operations like the device's _rn
+// intrinsics.  The device text is the anonymous namespace of k_rx.cu (RX_DEV_INC: its three inline-PTX statements
+// replaced by their C meaning, the dynamic shared memory pointed at the shim's buffer); asynchronous row copies are
+// done at issue time.  Launch geometry: two warps per CTA instead of twelve (the row windows of the warps are laid out
+// the same way).  Built with -fsanitize=thread the same run is the kernels' race check (rows copied by other lanes,
+// __syncwarp on both sides of a stage).  Usage: emu_rx <seed> [quick]; exit code 0 = equal.
+#include "cuda_emu.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+extern "C" {
+#include "../../oracle/dvbs_oracle.h"
+}
+
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+  const uint64_t v = ((uint64_t)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xffu) << (8 * i);
+  return r;
+}
+template <class T> inline void __stcg(T *p, T v) { *p = v; }
+template <class T> inline void __stcs(T *p, T v) { *p = v; }
+template <class T> inline T __ldcs(const T *p) { return *p; }
+#include "../../leansdr_b200/csrc/kernels.h"
+#include "../../leansdr_b200/csrc/tables.h"
+namespace ldvb {
+inline float fmul(float a, float b) { return a * b; }
+inline float fadd(float a, float b) { return a + b; }
+inline float fsub(float a, float b) { return a - b; }
+inline float2 cmul(float2 a, float2 b) { return make_float2(fsub(fmul(a.x, b.x), fmul(a.y, b.y)), fadd(fmul(a.x, b.y), fmul(a.y, b.x))); }
+inline int f2i_trunc(float a) { return (int)a; }
+inline uint32_t smem_u32(const void *p) { return (uint32_t)(reinterpret_cast<const unsigned char *>(p) - emu::g_dyn_smem); }
+inline void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
+inline void cp_async16_ca(void *dst, const void *src) { memcpy(dst, src, 16); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+namespace dev {
+#include RX_DEV_INC
+}
+}  // namespace ldvb
+using namespace ldvb;
+
+static int g_fail = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { if (g_fail < 20) { fprintf(stderr, "MISMATCH %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } ++g_fail; } } while (0)
+
+static uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+// A QPSK-like waveform at `omega` samples per symbol: linear ramps between the points, a slow carrier rotation, noise,
+// short bursts.
+static std::vector<float2> waveform(std::mt19937_64 &rng, size_t n, float omega, float amp, float cfo, float noise) {
+  std::vector<float2> x(n);
+  std::normal_distribution<float> g(0.f, noise);
+  const size_t nsym = (size_t)(n / omega) + 4;
+  std::vector<float2> s(nsym);
+  for (auto &v : s) { const unsigned b = (unsigned)(rng() & 3); v = make_float2((b & 2) ? -amp : amp, (b & 1) ? -amp : amp); }
+  for (size_t i = 0; i < n; ++i) {
+    const double t = (i + 0.37) / omega;
+    const size_t k = (size_t)t;
+    const float f = (float)(t - k);
+    const float re = s[k].x * (1 - f) + s[k + 1].x * f, im = s[k].y * (1 - f) + s[k + 1].y * f;
+    const double a = 2 * M_PI * cfo * (double)i + 0.4;
+    const float c = (float)cos(a), sn = (float)sin(a);
+    x[i] = make_float2(re * c - im * sn + g(rng), re * sn + im * c + g(rng));
+    if (i % 4099 < 3) { x[i].x *= 7.f; x[i].y *= 7.f; }   // bursts: the slicer's halving loop (sdr.h:476-481) and the mu clamp
+  }
+  return x;
+}
+
+struct Tables {
+  Cstln cst;
+  std::vector<float> trig;
+  std::vector<int16_t> pe;
+  std::vector<uint8_t> rot_perm;
+  orc_cstln *oc;
+  std::vector<float> otrig;
+};
+
+static Tables make_tables(int kind) {
+  Tables t;
+  t.cst = make_cstln(kind, 3 /* 3/4: the APSK ring ratios orc_cstln_build uses */, false);
+  t.trig = make_trig16();
+  t.oc = (orc_cstln *)malloc(sizeof(orc_cstln));
+  orc_cstln_build(t.oc, kind, 0);
+  t.otrig.resize(65536 * 2);
+  orc_trig16_build(t.otrig.data());
+  // the folded phase-error column of slicer 1, as ldvb_create lays it out (pipeline.cu)
+  t.pe.assign((size_t)256 * kPeFoldPitch, 0);
+  for (int ib = 0; ib < 256; ++ib)
+    for (int q = 0; q <= 128; ++q) {
+      const int qb = (q == 128) ? 0x80 : q;
+      const int v = t.cst.cells[(size_t)ib * 256 + qb].phase_error;
+      t.pe[(size_t)ib * kPeFoldPitch + q] = (int16_t)((q == 128) ? -v : v);
+    }
+  for (int k = 0; k < t.cst.nrotations; ++k)
+    for (int s = 0; s < t.cst.nsymbols; ++s) t.rot_perm.push_back(t.cst.rot[k][s]);
+  return t;
+}
+
+struct OracleOut {
+  std::vector<uint32_t> sym;
+  std::vector<float2> sampled;
+  std::vector<float> meas;
+  orc_rx r;
+};
+
+static void compare_state(const RxState &s, const orc_rx &r, int sampler, const char *what) {
+  CHECK(fbits(s.mu) == fbits(r.mu) && fbits(s.phase) == fbits(r.phase) && fbits(s.freqw) == fbits(r.freqw), "%s: mu/phase/freqw %g %g %g vs %g %g %g",
+        what, s.mu, s.phase, s.freqw, r.mu, r.phase, r.freqw);
+  CHECK(fbits(s.est_insp) == fbits(r.est_insp) && fbits(s.agc_gain) == fbits(r.agc_gain), "%s: AGC %g %g vs %g %g", what, s.est_insp, s.agc_gain, r.est_insp, r.agc_gain);
+  CHECK(fbits(s.est_sp) == fbits(r.est_sp) && fbits(s.est_ep) == fbits(r.est_ep), "%s: estimators", what);
+  for (int k = 0; k < 3; ++k)
+    CHECK(fbits(s.hist[4 * k]) == fbits(r.hist[k].p_re) && fbits(s.hist[4 * k + 1]) == fbits(r.hist[k].p_im) &&
+          fbits(s.hist[4 * k + 2]) == fbits(r.hist[k].c_re) && fbits(s.hist[4 * k + 3]) == fbits(r.hist[k].c_im), "%s: hist[%d]", what, k);
+  CHECK(fbits(s.freq_tap) == fbits(r.freq_tap) && s.meas_count == (uint32_t)r.meas_count, "%s: freq_tap / meas_count", what);
+  if (sampler == 1) CHECK(fbits(s.samp_freqw) == fbits(r.samp_freqw), "%s: samp_freqw", what);
+  if (sampler == 2) CHECK(s.rrc_update_phase == r.rrc_update_phase, "%s: rrc_update_phase %d vs %d", what, s.rrc_update_phase, r.rrc_update_phase);
+}
+
+template <int SLICER>
+static void run_case(std::mt19937_64 &rng, const Tables &t, int sampler, float omega, uint32_t nspans, uint32_t S, uint32_t W,
+                     const char *name) {
+  const uint64_t nchunks = (uint64_t)nspans * S - 1;          // ragged last span
+  std::vector<float> rrc;
+  int rrc_sub = 0;
+  if (sampler == 2) { int steps = 0; rrc = design_rrc(2.4e6f * omega / 1.2f, 2.0e6f, 0.35f, 10.f, 0, &steps); rrc_sub = steps; }
+  const size_t look = sampler == 2 ? rrc.size() + 8 : 8;
+  const std::vector<float2> x = waveform(rng, (size_t)nchunks * kRxChunk + look, omega, 38.f, 0.0013f, 2.5f);
+
+  // ---- oracle: one serial pass
+  OracleOut o;
+  orc_rx_init(&o.r, t.oc, t.otrig.data(), sampler);
+  orc_rx_set_omega(&o.r, omega);
+  o.r.meas_decimation = 1000;
+  if (sampler == 2) orc_rx_set_rrc(&o.r, (int)rrc.size(), rrc.data(), rrc_sub);
+  RxState st0;
+  memset(&st0, 0, sizeof st0);
+  st0.est_insp = o.r.est_insp; st0.agc_gain = o.r.agc_gain; st0.freqw = o.r.freqw; st0.freq_tap = o.r.freq_tap;
+  {
+    o.sym.resize((size_t)nchunks * kRxChunk);
+    o.sampled.resize(nchunks);
+    o.meas.resize(3 * (nchunks + 1));
+    size_t ns = 0, np = 0, nm = 0;
+    const size_t n_in = (size_t)nchunks * kRxChunk + (size_t)orc_rx_readahead(&o.r);
+    const size_t done = orc_rx_run(&o.r, reinterpret_cast<const float *>(x.data()), n_in, reinterpret_cast<uint8_t *>(o.sym.data()), &ns,
+                                   reinterpret_cast<float *>(o.sampled.data()), &np, o.meas.data(), &nm);
+    CHECK(done == (size_t)nchunks * kRxChunk, "%s: the oracle consumed %zu samples", name, done);
+    o.sym.resize(ns); o.sampled.resize(np); o.meas.resize(3 * nm);
+  }
+
+  // ---- product parameters (rx_setup, pipeline.cu)
+  RxArgs a;
+  memset(&a, 0, sizeof a);
+  RxParams &p = a.p;
+  p.cstln = reinterpret_cast<const CstlnCellDev *>(t.cst.cells.data());
+  p.trig = reinterpret_cast<const float2 *>(t.trig.data());
+  for (int s = 0; s < t.cst.nsymbols; ++s) { p.sym_re[s] = t.cst.sym_re[s]; p.sym_im[s] = t.cst.sym_im[s]; }
+  p.nsymbols = t.cst.nsymbols; p.sampler = sampler; p.omega = omega;
+  p.min_freqw = o.r.min_freqw; p.max_freqw = o.r.max_freqw;
+  p.freq_alpha = 0.04; p.freq_beta = 0.0012 / omega * 1.0f; p.gain_mu = 0.02 / (75.0f * 75.0f) * 2; p.kest = 0.01f;
+  p.allow_drift = 0; p.meas_decimation = 1000;
+  p.rrc_coeffs = rrc.data(); p.rrc_n = (int)rrc.size(); p.rrc_sub = rrc_sub;
+  p.pe16 = t.pe.data(); p.slicer = SLICER;
+  a.x = x.data(); a.nchunks = nchunks; a.avail_chunks = nchunks; a.chunk0 = 0; a.first_exact = 1;
+  a.state_in = &st0; a.warm_in = &st0; a.state_chunk = 0;
+
+  auto words_equal = [&](const uint32_t *got, size_t n, size_t at, const char *what) {
+    size_t bad = 0;
+    for (size_t i = 0; i < n && at + i < o.sym.size(); ++i) bad += (got[i] & 0xffffffu) != (o.sym[at + i] & 0xffffffu);
+    CHECK(bad == 0 && at + n <= o.sym.size(), "%s %s: %zu of %zu softsymbols differ (oracle has %zu, span at %zu)", name, what, bad, n, o.sym.size(), at);
+  };
+
+  const size_t pe_bytes = SLICER ? (size_t)256 * kPeFoldPitch * 2 : 0;
+  // ---- 1. the serial lane: one span over the batch (EXACT mode)
+  {
+    const uint32_t cap = (uint32_t)(((size_t)nchunks * kRxChunk + 3) & ~(size_t)3);
+    std::vector<uint32_t> out(cap + 4, 0xdeadbeefu);
+    RxSpanInfo info; RxState end, begin;
+    std::vector<float2> sampled(nchunks); std::vector<uint32_t> flag(nchunks, 7u);
+    std::vector<float> meas(4 * (nchunks + 1)); uint32_t nmeas = 0;
+    RxArgs b = a;
+    b.span_chunks = (uint32_t)nchunks; b.warm_chunks = 0; b.nspans = 1; b.span_cap = cap;
+    b.sym_out = out.data(); b.info = &info; b.state_end = &end; b.state_begin = &begin;
+    b.sampled = sampled.data(); b.sampled_flag = flag.data(); b.meas = meas.data(); b.meas_count = &nmeas; b.max_meas = (uint32_t)nchunks + 1;
+    std::vector<unsigned char> smem(pe_bytes + 2 * (kRxChunk + 8) * 8 + 256);
+    emu::g_dyn_smem = smem.data();
+    emu::launch(1, SLICER ? 128 : 32, [&] { dev::k_rx_serial<SLICER>(b); });
+    CHECK(info.n_out == o.sym.size(), "%s serial: %u symbols, oracle %zu", name, info.n_out, o.sym.size());
+    words_equal(out.data(), info.n_out, 0, "serial");
+    compare_state(end, o.r, sampler, "serial end state");
+    size_t k = 0;
+    for (uint64_t c = 0; c < nchunks; ++c)
+      if (flag[c]) { CHECK(k < o.sampled.size() && fbits(sampled[c].x) == fbits(o.sampled[k].x) && fbits(sampled[c].y) == fbits(o.sampled[k].y), "%s: sampled tap of chunk %llu", name, (unsigned long long)c); ++k; }
+    CHECK(k == o.sampled.size(), "%s: %zu sampled points, oracle %zu", name, k, o.sampled.size());
+    CHECK(nmeas == o.meas.size() / 3, "%s: %u measurement rows, oracle %zu", name, nmeas, o.meas.size() / 3);
+    for (uint32_t m = 0; m < nmeas && m < o.meas.size() / 3; ++m) {
+      const float mer = meas[4 * m + 3] >= 0 ? 10 * logf(meas[4 * m + 3]) / logf(10) : 0;     // the host side of the row (sdr.h:910-911)
+      CHECK(fbits(meas[4 * m + 1]) == fbits(o.meas[3 * m]) && fbits(meas[4 * m + 2]) == fbits(o.meas[3 * m + 1]) && fbits(mer) == fbits(o.meas[3 * m + 2]),
+            "%s: measurement row %u", name, m);
+    }
+  }
+
+  // ---- 2. the span kernel: every span at once (speculative), then spans 1.. re-run from their predecessors' end states
+  const uint32_t cap = (S + kRxVerifyChunks) * kRxChunk;          // a multiple of 4: symbols leave four at a time
+  std::vector<uint32_t> out((size_t)nspans * cap, 0xdeadbeefu);
+  std::vector<RxSpanInfo> info(nspans);
+  std::vector<RxState> end(nspans), begin(nspans);
+  std::vector<RxSeamSym> hlog((size_t)nspans * kRxSeamLog), tlog((size_t)nspans * kRxSeamLog);
+  RxArgs b = a;
+  b.span_chunks = S; b.warm_chunks = W; b.nspans = nspans; b.span_cap = cap;
+  b.sym_out = out.data(); b.info = info.data(); b.state_end = end.data(); b.state_begin = begin.data();
+  b.head_log = hlog.data(); b.tail_log = tlog.data();
+  const int warps = 2;
+  const size_t row_bytes = sampler == 2 ? (8 + 6) * 8 : (8 + 2) * 8;
+  std::vector<unsigned char> smem(pe_bytes + (size_t)warps * dev::kStages * 32 * row_bytes + 256);
+  emu::g_dyn_smem = smem.data();
+  emu::launch((nspans + warps * 32 - 1) / (warps * 32), warps * 32, [&] { dev::k_rx<8, SLICER>(b, nullptr, 0); });
+  // span 0 started from the true state: its symbols are the oracle's, and so is its end state's continuation
+  words_equal(out.data(), info[0].n_out, 0, "span 0");
+  for (uint32_t j = 1; j < nspans; ++j) {
+    const uint32_t list = j;
+    emu::launch(1, warps * 32, [&] { dev::k_rx<8, SLICER>(b, &list, 1); });
+  }
+  size_t at = 0;
+  for (uint32_t j = 0; j < nspans; ++j) {
+    CHECK(info[j].n_out + info[j].n_tail <= cap, "%s: span %u overflows", name, j);
+    words_equal(out.data() + (size_t)j * cap, info[j].n_out, at, "repaired span");
+    if (j + 1 < nspans) words_equal(out.data() + (size_t)j * cap + info[j].n_out, info[j].n_tail, at + info[j].n_out, "verification overlap");
+    at += info[j].n_out;
+  }
+  CHECK(at == o.sym.size(), "%s: spans hold %zu symbols, oracle %zu", name, at, o.sym.size());
+  compare_state(end[nspans - 1], o.r, sampler, "last span end state");
+
+  // ---- 3. seams of the exact spans verify under the strict rule, the plan and the compaction give the oracle's stream
+  std::vector<RxSeam> seams(nspans);
+  RxStitchArgs sa;
+  memset(&sa, 0, sizeof sa);
+  sa.info = info.data(); sa.head_log = hlog.data(); sa.tail_log = tlog.data(); sa.nspans = nspans;
+  sa.nrot = t.cst.nrotations; sa.nsymbols = t.cst.nsymbols; sa.rot_perm = t.rot_perm.data(); sa.omega = omega;
+  sa.seams = seams.data(); sa.strict = 1; sa.state_begin = begin.data(); sa.state_end = end.data();
+  sa.tol_phase = 1.f; sa.tol_freqw = 1e-3f;
+  emu::launch((nspans - 1 + 3) / 4, 128, [&] { dev::k_rx_stitch(sa, nullptr, 0); });
+  for (uint32_t j = 0; j + 1 < nspans; ++j)
+    CHECK(seams[j].ok == 1 && seams[j].rot == 0 && seams[j].mismatches == 0 && seams[j].compared >= 8 && seams[j].extend_prev == 0 &&
+          seams[j].skip_next == 0 && seams[j].dphase == 0.f && seams[j].dfreqw == 0.f,
+          "%s: seam %u ok %d rot %d mism %d of %d extend %d skip %d dphase %g dfreqw %g", name, j, seams[j].ok, seams[j].rot, seams[j].mismatches,
+          seams[j].compared, seams[j].extend_prev, seams[j].skip_next, seams[j].dphase, seams[j].dfreqw);
+  const unsigned tile = 64;                                      // (1024 spans per CTA in the library)
+  const uint32_t nblk = (nspans + tile - 1) / tile;
+  std::vector<uint64_t> span_offset((size_t)nspans + 1 + 2 * nblk + 4, 0);
+  std::vector<uint32_t> span_skip(nspans, 0);
+  std::vector<uint8_t> span_rot(nspans, 0);
+  unsigned long long result[9] = {0};
+  unsigned long long *totals = reinterpret_cast<unsigned long long *>(span_offset.data() + nspans + 1);
+  emu::launch(nblk, tile, [&] { dev::k_rx_plan_local(info.data(), seams.data(), nspans, cap, sa.nrot, 0, 0, span_offset.data(), span_skip.data(), span_rot.data(), totals, result); });
+  emu::launch(nblk, tile, [&] { dev::k_rx_plan_apply(nspans, sa.nrot, span_offset.data(), span_rot.data(), totals, result); });
+  CHECK(result[0] == 0 && result[1] == o.sym.size() && result[3] == 0, "%s: plan: %llu failed seams, %llu symbols kept (oracle %zu), %llu overflows", name,
+        result[0], result[1], o.sym.size(), result[3]);
+  std::vector<uint32_t> flat(o.sym.size() + 8, 0xdeadbeefu);
+  RxCompactArgs ca;
+  memset(&ca, 0, sizeof ca);
+  ca.sym_in = out.data(); ca.span_cap = cap; ca.nspans = nspans; ca.span_offset = span_offset.data(); ca.span_skip = span_skip.data();
+  ca.span_rot = span_rot.data(); ca.rot_perm = t.rot_perm.data(); ca.nsymbols = t.cst.nsymbols; ca.sym_out = flat.data();
+  emu::launch(nspans, 64, [&] { dev::k_rx_compact(ca, result[1]); });
+  if (result[1] == o.sym.size()) words_equal(flat.data(), o.sym.size(), 0, "compacted stream");
+  CHECK(flat[o.sym.size()] == 0xdeadbeefu, "%s: the compaction wrote past its end", name);
+  fprintf(stderr, "%s: %zu symbols over %llu chunks, %u spans, equal so far: %s\n", name, o.sym.size(), (unsigned long long)nchunks, nspans, g_fail ? "NO" : "yes");
+}
+
+int main(int argc, char **argv) {
+  const uint64_t seed = argc > 1 ? strtoull(argv[1], nullptr, 10) : 1;
+  const bool quick = argc > 2;   // (under ThreadSanitizer: the bench configuration and the generic slicer once each)
+  std::mt19937_64 rng(seed);
+  const Tables qpsk = make_tables(1);
+  run_case<1>(rng, qpsk, 1, 1.2f, quick ? 34 : 70, 3, 2, "QPSK, linear sampler, 1.2 samples per symbol, arithmetic slicer (the bench configuration)");
+  run_case<0>(rng, qpsk, 1, 1.2f, quick ? 5 : 37, 4, 1, "QPSK, linear sampler, cell-table slicer");
+  if (!quick) {
+    run_case<1>(rng, qpsk, 0, 4.0f, 9, 5, 2, "QPSK, nearest sampler, 4 samples per symbol");
+    run_case<1>(rng, qpsk, 2, 2.0f, 6, 6, 2, "QPSK, RRC sampler, 2 samples per symbol");
+    const Tables psk8 = make_tables(2);
+    run_case<0>(rng, psk8, 1, 2.0f, 7, 4, 2, "8PSK, linear sampler, 2 samples per symbol");
+    const Tables apsk = make_tables(3);
+    run_case<0>(rng, apsk, 2, 2.0f, 5, 4, 0, "16APSK, RRC sampler, no warm-up");
+  }
+  if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }
+  printf("emu_rx seed %llu: equal\n", (unsigned long long)seed);
+  return 0;
+}

@@ -291,3 +291,64 @@ def test_fused_notch_fir_kernel_equals_the_oracle_on_the_host(oracle_lib, tmp_pa
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
     n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
     assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
+
+
+def _rx_device_text(tmp):
+    """The device code of k_rx.cu (its first anonymous namespace: every kernel of the receiver stage, k_ctl_rx.cuh
+    included) with the three inline-PTX statements replaced by what they mean and the dynamic shared memory pointed at
+    the shim's buffer."""
+    csrc = os.path.join(ROOT, "leansdr_b200", "csrc")
+    src = open(os.path.join(csrc, "k_rx.cu")).read()
+    i = src.index("namespace {\n") + len("namespace {\n")
+    j = src.index("}  // namespace\n\ncudaError_t launch_rx_power(")
+    body = src[i:j]
+    subs = [
+        ("extern __shared__ __align__(128) unsigned char smem[];", "unsigned char *smem = emu::g_dyn_smem;", 2),
+        ('asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(addr));',
+         "v = *reinterpret_cast<const short *>(emu::g_dyn_smem + addr);", 1),
+        ('asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(Ii) : "f"(I));', "Ii = f2i_trunc(I);", 1),
+        ('asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(Qi) : "f"(Q));', "Qi = f2i_trunc(Q);", 1),
+        ('#include "k_ctl_rx.cuh"', '#include "%s"' % os.path.join(csrc, "k_ctl_rx.cuh"), 1),
+    ]
+    for old, new, count in subs:
+        assert body.count(old) == count, (old, body.count(old))
+        body = body.replace(old, new)
+    # what is left of inline PTX is the evict_last table load, compiled out by LDVB_RX_TRIG_EVICT_LAST=0 (then __ldg)
+    assert body.count("asm") == 1 and "<<<" not in body
+    for k in ("k_rx_serial", "k_rx(", "k_rx_stitch(", "k_rx_compact(", "rx_warm_state"):
+        assert k in body, k
+    inc = str(tmp / "rx_dev.inc")
+    open(inc, "w").write(body)
+    return inc
+
+
+@pytest.mark.timeout(900)
+def test_receiver_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
+    """The receiver stage (k_rx.cu: the dominant kernel of the chain) on the host against the oracle's cstln_receiver,
+    field for field: `k_rx_serial` (EXACT mode: softsymbols, end state, sampled-point tap, measurement rows), `k_rx`
+    with one lane per time span (span 0 from the true state equals the oracle at once; every other span is then re-run
+    from its predecessor's end state, the repair path of FAST mode, and the spans with their verification overlaps
+    are the oracle's stream), `k_rx_stitch` on those exact spans (every seam verifies under the strict rule with zero
+    state difference), `k_rx_plan_local/_apply` + `k_rx_compact` (the contiguous stream is the oracle's).  QPSK with the
+    arithmetic slicer and the phase-error column in shared memory (the bench configuration), the cell-table slicer,
+    nearest / linear / RRC samplers, 8PSK and 16APSK.  Then the same kernels under ThreadSanitizer."""
+    tmp = tmp_path_factory.mktemp("emu_rx")
+    inc = _rx_device_text(tmp)
+    csrc = os.path.join(ROOT, "leansdr_b200", "csrc")
+    base = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-w", "-I", CUDA_INC, '-DRX_DEV_INC="%s"' % inc,
+            "-DLDVB_RX_TRIG_EVICT_LAST=0", os.path.join(ROOT, "tests", "emu", "emu_rx.cpp"),
+            os.path.join(csrc, "tables.cpp"), oracle_lib, "-Wl,-rpath," + os.path.dirname(oracle_lib)]
+    exe = str(tmp / "emu_rx")
+    r = subprocess.run(base + ["-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0 and "equal" in r.stdout, r.stderr[-3000:]
+    assert r.stderr.count("equal so far: yes") == 6
+    tsan = str(tmp / "emu_rx_tsan")
+    r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ cannot link ThreadSanitizer here: " + r.stderr[-300:])
+    r = subprocess.run([tsan, "3", "quick"], capture_output=True, text=True, timeout=800,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0"))
+    n = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert r.returncode == 0 and "equal" in r.stdout and n == 0, f"{n} reports\n{(r.stdout + r.stderr)[-3000:]}"
