@@ -277,6 +277,98 @@ static void run_case(std::mt19937_64 &rng, const Tables &t, int sampler, float o
   fprintf(stderr, "%s: %zu symbols over %llu chunks, %u spans, equal so far: %s\n", name, o.sym.size(), (unsigned long long)nchunks, nspans, g_fail ? "NO" : "yes");
 }
 
+// --hs: fast_qpsk_receiver<u8> (sdr.h:946-1189), sampler kRxSamplerHs of the same kernels.  Integer loop state in the float
+// fields of RxState; the input is the u8 stream as the front end converts it (value - 128).
+static void run_case_hs(std::mt19937_64 &rng, float omega, uint32_t nspans, uint32_t S, uint32_t W, const char *name) {
+  const uint64_t nchunks = (uint64_t)nspans * S - 1;
+  const size_t n = (size_t)nchunks * kRxChunk + 8;
+  const std::vector<float2> w = waveform(rng, n, omega, 60.f, 0.0009f, 3.f);
+  std::vector<uint8_t> u8(2 * n);
+  std::vector<float2> x(n);
+  for (size_t i = 0; i < n; ++i) {
+    auto q = [](float v) { const int k = (int)lrintf(v) + 128; return (uint8_t)(k < 0 ? 0 : k > 255 ? 255 : k); };
+    u8[2 * i] = q(w[i].x); u8[2 * i + 1] = q(w[i].y);
+    x[i] = make_float2((float)((int)u8[2 * i] - 128), (float)((int)u8[2 * i + 1] - 128));
+  }
+  orc_hsrx *r = (orc_hsrx *)malloc(sizeof(orc_hsrx));
+  orc_hsrx_init(r);
+  orc_hsrx_set_omega(r, omega);
+  orc_hsrx_config(r, 0, 1000);
+  const long lo = r->min_freqw, hi = r->max_freqw;
+  std::vector<uint8_t> osym((size_t)nchunks * kRxChunk);
+  std::vector<float> ofreq(nchunks + 1);
+  size_t ns = 0, nf = 0;
+  const size_t done = orc_hsrx_run(r, u8.data(), (size_t)nchunks * kRxChunk + 1, osym.data(), &ns, ofreq.data(), &nf);
+  CHECK(done == (size_t)nchunks * kRxChunk, "%s: the oracle consumed %zu samples", name, done);
+
+  const HsTables ht = make_hs_tables();
+  RxState st0;
+  memset(&st0, 0, sizeof st0);
+  RxArgs a;
+  memset(&a, 0, sizeof a);
+  RxParams &p = a.p;
+  p.nsymbols = 4; p.sampler = kRxSamplerHs; p.omega = omega; p.min_freqw = (float)lo; p.max_freqw = (float)hi;
+  p.gain_mu = 0.02 / (75.0f * 75.0f) * 2; p.kest = 0.01f; p.allow_drift = 0; p.meas_decimation = 1000;
+  p.hs_polar = ht.polar.data(); p.hs_rect = ht.rect.data(); p.hs_sincos = ht.sincos.data();
+  p.hs_freq_beta = (long long)(signed long)(0.0012 * 256 * 65536 / omega * 1.0f);
+  a.x = x.data(); a.nchunks = nchunks; a.avail_chunks = nchunks; a.first_exact = 1; a.state_in = &st0; a.warm_in = &st0;
+
+  auto syms_equal = [&](const uint32_t *got, size_t cnt, size_t at, const char *what) {
+    size_t bad = 0;
+    for (size_t i = 0; i < cnt && at + i < ns; ++i) bad += ((got[i] >> 16) & 0xffu) != osym[at + i];
+    CHECK(bad == 0 && at + cnt <= ns, "%s %s: %zu of %zu hard symbols differ (oracle has %zu, span at %zu)", name, what, bad, cnt, ns, at);
+  };
+  auto state_equal = [&](const RxState &s, const char *what) {
+    CHECK(fbits(s.mu) == fbits(r->mu) && s.phase == (float)r->phase && s.freqw == (float)r->freqw && s.meas_count == (uint32_t)r->meas_count,
+          "%s %s: mu %g phase %g freqw %g count %u vs %g %u %ld %lu", name, what, s.mu, s.phase, s.freqw, s.meas_count, r->mu, r->phase, r->freqw, r->meas_count);
+    for (int k = 0; k < 3; ++k)
+      CHECK(s.hist[4 * k] == (float)r->hist[k].p_re && s.hist[4 * k + 1] == (float)r->hist[k].p_im && s.hist[4 * k + 2] == (float)r->hist[k].c_re &&
+            s.hist[4 * k + 3] == (float)r->hist[k].c_im, "%s %s: hist[%d]", name, what, k);
+  };
+  {
+    const uint32_t cap = (uint32_t)(((size_t)nchunks * kRxChunk + 3) & ~(size_t)3);
+    std::vector<uint32_t> out(cap + 4, 0xdeadbeefu);
+    RxSpanInfo info; RxState end;
+    std::vector<float> meas(4 * (nchunks + 1)); uint32_t nmeas = 0;
+    RxArgs b = a;
+    b.span_chunks = (uint32_t)nchunks; b.nspans = 1; b.span_cap = cap; b.sym_out = out.data(); b.info = &info; b.state_end = &end;
+    b.meas = meas.data(); b.meas_count = &nmeas; b.max_meas = (uint32_t)nchunks + 1;
+    std::vector<unsigned char> smem(2 * (kRxChunk + 8) * 8 + 256);
+    emu::g_dyn_smem = smem.data();
+    emu::launch(1, 32, [&] { dev::k_rx_serial<0>(b); });
+    CHECK(info.n_out == ns, "%s serial: %u symbols, oracle %zu", name, info.n_out, ns);
+    syms_equal(out.data(), info.n_out, 0, "serial");
+    state_equal(end, "serial end state");
+    CHECK(nmeas == nf, "%s: %u frequency rows, oracle %zu", name, nmeas, nf);
+    for (uint32_t m = 0; m < nmeas && m < nf; ++m) CHECK(fbits(meas[4 * m + 1]) == fbits(ofreq[m]), "%s: frequency row %u", name, m);
+  }
+  const uint32_t cap = (S + kRxVerifyChunks) * kRxChunk;
+  std::vector<uint32_t> out((size_t)nspans * cap, 0xdeadbeefu);
+  std::vector<RxSpanInfo> info(nspans);
+  std::vector<RxState> end(nspans);
+  std::vector<RxSeamSym> hlog((size_t)nspans * kRxSeamLog), tlog((size_t)nspans * kRxSeamLog);
+  RxArgs b = a;
+  b.span_chunks = S; b.warm_chunks = W; b.nspans = nspans; b.span_cap = cap; b.sym_out = out.data(); b.info = info.data();
+  b.state_end = end.data(); b.head_log = hlog.data(); b.tail_log = tlog.data();
+  const int warps = 2;
+  std::vector<unsigned char> smem((size_t)warps * dev::kStages * 32 * (8 + 2) * 8 + 256);
+  emu::g_dyn_smem = smem.data();
+  emu::launch((nspans + warps * 32 - 1) / (warps * 32), warps * 32, [&] { dev::k_rx<8, 0>(b, nullptr, 0); });
+  for (uint32_t j = 1; j < nspans; ++j) {
+    const uint32_t list = j;
+    emu::launch(1, warps * 32, [&] { dev::k_rx<8, 0>(b, &list, 1); });
+  }
+  size_t at = 0;
+  for (uint32_t j = 0; j < nspans; ++j) {
+    syms_equal(out.data() + (size_t)j * cap, info[j].n_out, at, "repaired span");
+    at += info[j].n_out;
+  }
+  CHECK(at == ns, "%s: spans hold %zu symbols, oracle %zu", name, at, ns);
+  state_equal(end[nspans - 1], "last span end state");
+  free(r);
+  fprintf(stderr, "%s: %zu symbols over %llu chunks, %u spans, equal so far: %s\n", name, ns, (unsigned long long)nchunks, nspans, g_fail ? "NO" : "yes");
+}
+
 int main(int argc, char **argv) {
   const uint64_t seed = argc > 1 ? strtoull(argv[1], nullptr, 10) : 1;
   const bool quick = argc > 2;   // (under ThreadSanitizer: the bench configuration and the generic slicer once each)
@@ -291,6 +383,7 @@ int main(int argc, char **argv) {
     run_case<0>(rng, psk8, 1, 2.0f, 7, 4, 2, "8PSK, linear sampler, 2 samples per symbol");
     const Tables apsk = make_tables(3);
     run_case<0>(rng, apsk, 2, 2.0f, 5, 4, 0, "16APSK, RRC sampler, no warm-up");
+    run_case_hs(rng, 1.2f, 9, 4, 2, "--hs: fast_qpsk_receiver, 1.2 samples per symbol");
   }
   if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }
   printf("emu_rx seed %llu: equal\n", (unsigned long long)seed);

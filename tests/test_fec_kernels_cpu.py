@@ -331,7 +331,8 @@ def test_receiver_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_fact
     are the oracle's stream), `k_rx_stitch` on those exact spans (every seam verifies under the strict rule with zero
     state difference), `k_rx_plan_local/_apply` + `k_rx_compact` (the contiguous stream is the oracle's).  QPSK with the
     arithmetic slicer and the phase-error column in shared memory (the bench configuration), the cell-table slicer,
-    nearest / linear / RRC samplers, 8PSK and 16APSK.  Then the same kernels under ThreadSanitizer."""
+    nearest / linear / RRC samplers, 8PSK and 16APSK, and the integer receiver of `--hs` (fast_qpsk_receiver: hard symbols,
+    loop state, frequency rows).  Then the same kernels under ThreadSanitizer."""
     tmp = tmp_path_factory.mktemp("emu_rx")
     inc = _rx_device_text(tmp)
     csrc = os.path.join(ROOT, "leansdr_b200", "csrc")
@@ -343,7 +344,7 @@ def test_receiver_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_fact
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=800)
     assert r.returncode == 0 and "equal" in r.stdout, r.stderr[-3000:]
-    assert r.stderr.count("equal so far: yes") == 6
+    assert r.stderr.count("equal so far: yes") == 7
     tsan = str(tmp / "emu_rx_tsan")
     r = subprocess.run(base + ["-g", "-fsanitize=thread", "-o", tsan], capture_output=True, text=True)
     if r.returncode != 0:
