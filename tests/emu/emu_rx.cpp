@@ -58,7 +58,7 @@ static uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 // A QPSK-like waveform at `omega` samples per symbol: linear ramps between the points, a slow carrier rotation, noise,
 // short bursts.
-static std::vector<float2> waveform(std::mt19937_64 &rng, size_t n, float omega, float amp, float cfo, float noise) {
+static std::vector<float2> waveform(std::mt19937_64 &rng, size_t n, float omega, float amp, float cfo, float noise, bool bursts = true, bool shaped = false) {
   std::vector<float2> x(n);
   std::normal_distribution<float> g(0.f, noise);
   const size_t nsym = (size_t)(n / omega) + 4;
@@ -67,12 +67,13 @@ static std::vector<float2> waveform(std::mt19937_64 &rng, size_t n, float omega,
   for (size_t i = 0; i < n; ++i) {
     const double t = (i + 0.37) / omega;
     const size_t k = (size_t)t;
-    const float f = (float)(t - k);
+    float f = (float)(t - k);
+    if (shaped) f = f < 0.6f ? 0.f : (f - 0.6f) / 0.4f;   // plateaus with short transitions (little inter-symbol interference)
     const float re = s[k].x * (1 - f) + s[k + 1].x * f, im = s[k].y * (1 - f) + s[k + 1].y * f;
     const double a = 2 * M_PI * cfo * (double)i + 0.4;
     const float c = (float)cos(a), sn = (float)sin(a);
     x[i] = make_float2(re * c - im * sn + g(rng), re * sn + im * c + g(rng));
-    if (i % 4099 < 3) { x[i].x *= 7.f; x[i].y *= 7.f; }   // bursts: the slicer's halving loop (sdr.h:476-481) and the mu clamp
+    if (bursts && i % 4099 < 3) { x[i].x *= 7.f; x[i].y *= 7.f; }   // bursts: the slicer's halving loop (sdr.h:476-481) and the mu clamp
   }
   return x;
 }
@@ -369,6 +370,125 @@ static void run_case_hs(std::mt19937_64 &rng, float omega, uint32_t nspans, uint
   fprintf(stderr, "%s: %zu symbols over %llu chunks, %u spans, equal so far: %s\n", name, ns, (unsigned long long)nchunks, nspans, g_fail ? "NO" : "yes");
 }
 
+// FAST mode as rx_fast_launch / run_receiver (pipeline.cu) schedule it: a serial settling pass, then every span at once from
+// the carried loop state (frequency, AGC) after 4 warm-up chunks, strict seams (every hard decision of the overlap and the
+// loop states agree), failed seams repaired by an exact re-run of the later span.  The claim of that mode, checked here on the
+// kernels themselves: the stitched stream carries the ORACLE's hard decisions (the soft costs may differ by the AGC state
+// a span started from), and with every span repaired it is the oracle's stream word for word (run_case above).
+static void run_fast_case(std::mt19937_64 &rng, const Tables &t, float noise, bool shaped, size_t max_flips, uint32_t settle, uint32_t nspans, uint32_t S, const char *name) {
+  const float omega = 1.2f;
+  const uint32_t W = 4;
+  const uint64_t nchunks = settle + (uint64_t)nspans * S;
+  const std::vector<float2> x = waveform(rng, (size_t)nchunks * kRxChunk + 8, omega, 38.f, 0.0013f, noise, false, shaped);
+  orc_rx orx;
+  orc_rx_init(&orx, t.oc, t.otrig.data(), 1);
+  orc_rx_set_omega(&orx, omega);
+  std::vector<uint32_t> osym((size_t)nchunks * kRxChunk);
+  size_t ns = 0;
+  orc_rx_run(&orx, reinterpret_cast<const float *>(x.data()), (size_t)nchunks * kRxChunk + 1, reinterpret_cast<uint8_t *>(osym.data()), &ns, nullptr, nullptr, nullptr, nullptr);
+
+  RxState st0;
+  memset(&st0, 0, sizeof st0);
+  st0.est_insp = 75.0f * 75.0f; st0.agc_gain = 1;
+  RxArgs a;
+  memset(&a, 0, sizeof a);
+  RxParams &p = a.p;
+  p.cstln = reinterpret_cast<const CstlnCellDev *>(t.cst.cells.data());
+  p.trig = reinterpret_cast<const float2 *>(t.trig.data());
+  for (int k = 0; k < t.cst.nsymbols; ++k) { p.sym_re[k] = t.cst.sym_re[k]; p.sym_im[k] = t.cst.sym_im[k]; }
+  p.nsymbols = t.cst.nsymbols; p.sampler = 1; p.omega = omega; p.min_freqw = orx.min_freqw; p.max_freqw = orx.max_freqw;
+  p.freq_alpha = 0.04; p.freq_beta = 0.0012 / omega * 1.0f; p.gain_mu = 0.02 / (75.0f * 75.0f) * 2; p.kest = 0.01f;
+  p.meas_decimation = 1048576; p.pe16 = t.pe.data(); p.slicer = 1;
+  a.x = x.data();
+  const size_t pe_bytes = (size_t)256 * kPeFoldPitch * 2;
+  // ---- settling pass: the serial lane over the first chunks
+  std::vector<uint32_t> head_sym((size_t)settle * kRxChunk + 4);
+  RxSpanInfo hinfo; RxState settled;
+  {
+    RxArgs b = a;
+    b.nchunks = settle; b.avail_chunks = nchunks; b.first_exact = 1; b.state_in = &st0; b.warm_in = &st0;
+    b.span_chunks = settle; b.nspans = 1; b.span_cap = (uint32_t)(((size_t)settle * kRxChunk + 3) & ~(size_t)3);
+    b.sym_out = head_sym.data(); b.info = &hinfo; b.state_end = &settled;
+    std::vector<unsigned char> smem(pe_bytes + 2 * (kRxChunk + 8) * 8 + 256);
+    emu::g_dyn_smem = smem.data();
+    emu::launch(1, 128, [&] { dev::k_rx_serial<1>(b); });
+  }
+  size_t bad = 0;
+  for (uint32_t i = 0; i < hinfo.n_out; ++i) bad += (head_sym[i] & 0xffffffu) != (osym[i] & 0xffffffu);
+  CHECK(bad == 0, "%s: settling pass: %zu softsymbols differ", name, bad);
+  // ---- the spans
+  const uint32_t cap = ((uint32_t)((S + kRxVerifyChunks + 1) * kRxChunk / omega) + 64 + 3u) & ~3u;
+  std::vector<uint32_t> out((size_t)nspans * cap, 0xdeadbeefu);
+  std::vector<RxSpanInfo> info(nspans);
+  std::vector<RxState> end(nspans), begin(nspans);
+  std::vector<RxSeamSym> hlog((size_t)nspans * kRxSeamLog), tlog((size_t)nspans * kRxSeamLog);
+  RxArgs b = a;
+  b.nchunks = nchunks; b.avail_chunks = nchunks; b.chunk0 = settle; b.first_exact = 1; b.state_in = &settled; b.warm_in = &settled;
+  b.state_chunk = settle; b.span_chunks = S; b.warm_chunks = W; b.nspans = nspans; b.span_cap = cap;
+  b.sym_out = out.data(); b.info = info.data(); b.state_end = end.data(); b.state_begin = begin.data();
+  b.head_log = hlog.data(); b.tail_log = tlog.data();
+  const int warps = 2;
+  std::vector<unsigned char> smem(pe_bytes + (size_t)warps * dev::kStages * 32 * (8 + 2) * 8 + 256);
+  emu::g_dyn_smem = smem.data();
+  emu::launch((nspans + warps * 32 - 1) / (warps * 32), warps * 32, [&] { dev::k_rx<8, 1>(b, nullptr, 0); });
+  std::vector<RxSeam> seams(nspans);
+  RxStitchArgs sa;
+  memset(&sa, 0, sizeof sa);
+  sa.info = info.data(); sa.head_log = hlog.data(); sa.tail_log = tlog.data(); sa.nspans = nspans;
+  sa.nrot = t.cst.nrotations; sa.nsymbols = t.cst.nsymbols; sa.rot_perm = t.rot_perm.data(); sa.omega = omega;
+  sa.seams = seams.data(); sa.strict = 1; sa.state_begin = begin.data(); sa.state_end = end.data();
+  sa.tol_phase = 65536.0f / (float)sa.nrot / 16.0f; sa.tol_freqw = (p.max_freqw - p.min_freqw) / 64.0f;
+  emu::launch((nspans - 1 + 3) / 4, 128, [&] { dev::k_rx_stitch(sa, nullptr, 0); });
+  uint32_t failed = 0, rotated = 0, shifted = 0;
+  for (uint32_t j = 0; j + 1 < nspans; ++j) { failed += !seams[j].ok; rotated += seams[j].rot != 0; shifted += seams[j].extend_prev || seams[j].skip_next; }
+  // repair in stream order: the later span of a failed seam is re-run from its predecessor's end state, its next seam judged again
+  uint32_t repaired = 0;
+  for (uint32_t j = 0; j + 1 < nspans; ++j) {
+    if (seams[j].ok) continue;
+    const uint32_t list = j + 1;
+    emu::launch(1, warps * 32, [&] { dev::k_rx<8, 1>(b, &list, 1); });
+    ++repaired;
+    const uint32_t sl[2] = {j, j + 1};
+    emu::launch(1, 128, [&] { dev::k_rx_stitch(sa, sl, j + 2 < nspans ? 2 : 1); });
+    CHECK(seams[j].ok && seams[j].mismatches == 0 && seams[j].rot == 0, "%s: seam %u does not verify after the exact re-run", name, j);
+  }
+  const unsigned tile = 64;
+  const uint32_t nblk = (nspans + tile - 1) / tile;
+  std::vector<uint64_t> span_offset((size_t)nspans + 1 + 2 * nblk + 4, 0);
+  std::vector<uint32_t> span_skip(nspans, 0);
+  std::vector<uint8_t> span_rot(nspans, 0);
+  unsigned long long result[9] = {0};
+  unsigned long long *totals = reinterpret_cast<unsigned long long *>(span_offset.data() + nspans + 1);
+  emu::launch(nblk, tile, [&] { dev::k_rx_plan_local(info.data(), seams.data(), nspans, cap, sa.nrot, 0, 0, span_offset.data(), span_skip.data(), span_rot.data(), totals, result); });
+  emu::launch(nblk, tile, [&] { dev::k_rx_plan_apply(nspans, sa.nrot, span_offset.data(), span_rot.data(), totals, result); });
+  CHECK(result[0] == 0 && result[3] == 0, "%s: plan: %llu failed seams, %llu overflows", name, result[0], result[3]);
+  CHECK(hinfo.n_out + result[1] == ns, "%s: %u + %llu symbols, oracle %zu", name, hinfo.n_out, result[1], ns);
+  std::vector<uint32_t> flat((size_t)result[1] + 8, 0xdeadbeefu);
+  RxCompactArgs ca;
+  memset(&ca, 0, sizeof ca);
+  ca.sym_in = out.data(); ca.span_cap = cap; ca.nspans = nspans; ca.span_offset = span_offset.data(); ca.span_skip = span_skip.data();
+  ca.span_rot = span_rot.data(); ca.rot_perm = t.rot_perm.data(); ca.nsymbols = t.cst.nsymbols; ca.sym_out = flat.data();
+  emu::launch(nspans, 64, [&] { dev::k_rx_compact(ca, result[1]); });
+  size_t hard = 0, cost = 0;
+  if (hinfo.n_out + result[1] == ns)
+    for (size_t i = 0; i < result[1]; ++i) {
+      const uint32_t g = flat[i], w = osym[hinfo.n_out + i];
+      cost += (g & 0xffffu) != (w & 0xffffu);
+      if (((g >> 16) & 0xffu) != ((w >> 16) & 0xffu)) {
+        // a decision may only flip where it is marginal: the oracle's own confidence (cost, the gap between the two nearest
+        // points: up to 2 * 53 * 53 * 2 for a sample on a constellation point) is a few per cent of the scale
+        ++hard;
+        const int oc = (int)(short)(w & 0xffffu), gc = (int)(short)(g & 0xffffu);
+        CHECK(abs(oc) < 600 && abs(gc) < 600, "%s: symbol %zu flipped with costs %d (oracle) and %d", name, i, oc, gc);
+      }
+    }
+  CHECK(hard <= max_flips, "%s: %zu of %llu hard decisions differ from the oracle", name, hard, result[1]);
+  fprintf(stderr, "%s: %u spans of %u chunks after %u settling chunks: %u seams failed the strict rule and were repaired (%u rotated, %u shifted by a symbol), "
+          "%llu symbols, hard decisions differing from the oracle: %zu, soft costs differing: %zu, equal so far: %s\n",
+          name, nspans, S, settle, failed, rotated, shifted, result[1], hard, cost, g_fail ? "NO" : "yes");
+  (void)repaired;
+}
+
 int main(int argc, char **argv) {
   const uint64_t seed = argc > 1 ? strtoull(argv[1], nullptr, 10) : 1;
   const bool quick = argc > 2;   // (under ThreadSanitizer: the bench configuration and the generic slicer once each)
@@ -384,6 +504,8 @@ int main(int argc, char **argv) {
     const Tables apsk = make_tables(3);
     run_case<0>(rng, apsk, 2, 2.0f, 5, 4, 0, "16APSK, RRC sampler, no warm-up");
     run_case_hs(rng, 1.2f, 9, 4, 2, "--hs: fast_qpsk_receiver, 1.2 samples per symbol");
+    run_fast_case(rng, qpsk, 2.5f, true, 0, 600, 64, 4, "FAST mode, QPSK at 1.2 samples per symbol, clean decisions");
+    run_fast_case(rng, qpsk, 2.5f, false, 8, 600, 64, 4, "FAST mode, QPSK at 1.2 samples per symbol, heavy inter-symbol interference");
   }
   if (g_fail) { fprintf(stderr, "%d mismatches\n", g_fail); return 1; }
   printf("emu_rx seed %llu: equal\n", (unsigned long long)seed);
