@@ -79,8 +79,11 @@ def test_packet_kernels_are_race_free_under_thread_sanitizer(oracle_lib, tmp_pat
 
 @pytest.mark.timeout(600)
 def test_transmit_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_factory):
-    """The integer kernels of the transmit chain (`leansdr_b200/csrc/tx.cu`: leantsgen packets, randomizer + rs_encoder,
-    interleaver, dvb_convol for every code rate and symbol width) against the oracle's restatement of leandvbtx, which
+    """The kernels of the transmit chain (`leansdr_b200/csrc/tx.cu`: leantsgen packets, randomizer + rs_encoder,
+    interleaver, dvb_convol for every code rate and symbol width; then, float for float, `k_tx_resample` =
+    cstln_transmitter + fir_resampler + decimator at 6/5, 2/1 and 12/5 from symbols and from cf32 in two ragged
+    launches, and `k_tx_amp2` / `k_tx_agc` / `k_tx_scale` = simple_agc in two pushes with the carried estimate, RRC
+    taps and amplitude included) against the oracle's restatement of leandvbtx, which
     is pinned to the reference transmitter (tests/test_oracle_tx_cpu.py).  The device text is the first anonymous
     namespace of tx.cu; its one dynamic shared-memory declaration is pointed at the shim's buffer."""
     tmp = tmp_path_factory.mktemp("emu_tx")
