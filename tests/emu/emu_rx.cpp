@@ -256,6 +256,24 @@ static void run_case(std::mt19937_64 &rng, const Tables &t, int sampler, float o
           seams[j].skip_next == 0 && seams[j].dphase == 0.f && seams[j].dfreqw == 0.f,
           "%s: seam %u ok %d rot %d mism %d of %d extend %d skip %d dphase %g dfreqw %g", name, j, seams[j].ok, seams[j].rot, seams[j].mismatches,
           seams[j].compared, seams[j].extend_prev, seams[j].skip_next, seams[j].dphase, seams[j].dfreqw);
+  {
+    // the seam between two ranks of the time-sharded mode (k_rx_stitch_pair: the earlier span's tail log and end state are
+    // imported): the same judgement as k_rx_stitch's on seam 0
+    RxStitchArgs sp = sa;
+    sp.info = info.data() + 1; sp.head_log = hlog.data() + kRxSeamLog; sp.state_begin = begin.data() + 1;
+    RxSeam pair;
+    memset(&pair, 0xff, sizeof pair);
+    emu::launch(1, 32, [&] { dev::k_rx_stitch_pair(sp, tlog.data(), info[0].n_tail, &end[0], &pair); });
+    CHECK(memcmp(&pair, &seams[0], sizeof pair) == 0, "%s: k_rx_stitch_pair differs from k_rx_stitch on seam 0", name);
+    // mean power of the first samples (what decides the cold-start settling pass)
+    float pw = -1.f;
+    const uint32_t npw = (uint32_t)std::min<size_t>(3000, x.size());
+    emu::launch(1, 256, [&] { dev::k_rx_power(x.data(), npw, &pw); });
+    double ref = 0;
+    for (uint32_t i = 0; i < npw; ++i) ref += (double)x[i].x * x[i].x + (double)x[i].y * x[i].y;
+    ref /= npw;
+    CHECK(fabs(pw - ref) <= 1e-4 * ref, "%s: k_rx_power %g vs %g", name, pw, ref);
+  }
   const unsigned tile = 64;                                      // (1024 spans per CTA in the library)
   const uint32_t nblk = (nspans + tile - 1) / tile;
   std::vector<uint64_t> span_offset((size_t)nspans + 1 + 2 * nblk + 4, 0);

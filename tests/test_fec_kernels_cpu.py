@@ -332,7 +332,7 @@ def test_receiver_kernels_equal_the_oracle_on_the_host(oracle_lib, tmp_path_fact
     with one lane per time span (span 0 from the true state equals the oracle at once; every other span is then re-run
     from its predecessor's end state, the repair path of FAST mode, and the spans with their verification overlaps
     are the oracle's stream), `k_rx_stitch` on those exact spans (every seam verifies under the strict rule with zero
-    state difference), `k_rx_plan_local/_apply` + `k_rx_compact` (the contiguous stream is the oracle's).  QPSK with the
+    state difference), `k_rx_stitch_pair` (the seam between two ranks: same judgement), `k_rx_power`, `k_rx_plan_local/_apply` + `k_rx_compact` (the contiguous stream is the oracle's).  QPSK with the
     arithmetic slicer and the phase-error column in shared memory (the bench configuration), the cell-table slicer,
     nearest / linear / RRC samplers, 8PSK and 16APSK, and the integer receiver of `--hs` (fast_qpsk_receiver: hard symbols,
     loop state, frequency rows).  FAST mode on the kernels themselves, scheduled as run_receiver does (serial settling
