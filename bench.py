@@ -478,7 +478,7 @@ def bench_time_sharded(a, rank, world, local, W, workload, dist, torch, P):
     kern = {k: v["ms_total"] / max(v["launches"], 1) for k, v in prof.items()}
     per_step = {k: v["ms_total"] / a.steps for k, v in prof.items()}
     nloc = ch.n_halo + ch.n_chunk
-    alg_bytes = {"frontend": nloc * 16, "notch_apply": nloc * 16, "notch_fir": nloc * 16, "notch_guess": notch_guess_bytes(nloc, anf=a.anf),
+    alg_bytes = {"frontend": nloc * 16, "notch_apply": nloc * 16, "notch_fir": nloc * 16, "notch_guess": notch_guess_bytes(nloc, anf=a.anf) if "notch_fir" in kern else nloc * 8,   # (unfused: one-block segments, every block read)
                  "rx": nloc * 8 + int(nloc / 1.2) * 4}
     dom = max(per_step, key=per_step.get)
     ab = alg_bytes.get(dom, nloc * 8)
@@ -790,7 +790,8 @@ def main():
         "frontend": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),   # IQ in + cf32 out (FIR, D=1)
         "notch_apply": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),
         "notch_fir": n * ((2 if a.variant in ("u8", "hs") else 8) + 8),    # IQ in + preprocessed cf32 out (notch + FIR fused)
-        "notch_guess": notch_guess_bytes(n, 2 if a.variant in ("u8", "hs") else 8, anf=a.anf),   # 2 blocks per segment, not the stream
+        "notch_guess": (notch_guess_bytes(n, 2 if a.variant in ("u8", "hs") else 8, anf=a.anf) if "notch_fir" in prof
+                        else n * (2 if a.variant in ("u8", "hs") else 8)),   # 2 blocks per segment, not the stream
         "viterbi": sym * 4 + sym // 8,
         "rx": n * 8 + sym * 4,                        # cf32 in + softsymbol out
         "rx_compact": sym * 8,
