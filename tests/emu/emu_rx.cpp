@@ -512,8 +512,8 @@ int main(int argc, char **argv) {
   const bool quick = argc > 2;   // (under ThreadSanitizer: the bench configuration and the generic slicer once each)
   std::mt19937_64 rng(seed);
   const Tables qpsk = make_tables(1);
-  run_case<1>(rng, qpsk, 1, 1.2f, quick ? 34 : 70, 3, 2, "QPSK, linear sampler, 1.2 samples per symbol, arithmetic slicer (the bench configuration)");
-  run_case<0>(rng, qpsk, 1, 1.2f, quick ? 5 : 37, 4, 1, "QPSK, linear sampler, cell-table slicer");
+  run_case<1>(rng, qpsk, 1, 1.2f, quick ? 33 : 40, quick ? 2 : 3, quick ? 1 : 2, "QPSK, linear sampler, 1.2 samples per symbol, arithmetic slicer (the bench configuration)");
+  run_case<0>(rng, qpsk, 1, 1.2f, quick ? 5 : 12, 4, 1, "QPSK, linear sampler, cell-table slicer");
   if (!quick) {
     run_case<1>(rng, qpsk, 0, 4.0f, 9, 5, 2, "QPSK, nearest sampler, 4 samples per symbol");
     run_case<1>(rng, qpsk, 2, 2.0f, 6, 6, 2, "QPSK, RRC sampler, 2 samples per symbol");
