@@ -217,6 +217,7 @@ static void run_case(std::mt19937_64 &rng, const Tables &t, int sampler, float o
   std::vector<RxSpanInfo> info(nspans);
   std::vector<RxState> end(nspans), begin(nspans);
   std::vector<RxSeamSym> hlog((size_t)nspans * kRxSeamLog), tlog((size_t)nspans * kRxSeamLog);
+  CHECK((reinterpret_cast<uintptr_t>(out.data()) & 15u) == 0 && cap % 4 == 0, "%s: the 16-byte emission path is not the one under test", name);
   RxArgs b = a;
   b.span_chunks = S; b.warm_chunks = W; b.nspans = nspans; b.span_cap = cap;
   b.sym_out = out.data(); b.info = info.data(); b.state_end = end.data(); b.state_begin = begin.data();
